@@ -1,0 +1,149 @@
+/* lgs_b200.h -- C ABI of the B200-native scan-matching / occupancy-grid backend.
+ *
+ * This is the drop-in boundary: the C++ adapters that subclass the
+ * reference's ScanMatcher / LoopDetector (adapters/) call ONLY these entry
+ * points.  Conventions: extern "C", opaque handles, int status return (0 = LGS_OK), no
+ * exceptions across the boundary, caller-owned host buffers, callee-owned device buffers
+ * freed by the matching *_destroy.  One lgs_ctx owns one CUDA stream + scratch and may be
+ * used by one host thread at a time; different contexts may be used concurrently (the
+ * reference calls OptimizePose from the front-end thread and Detect from the back-end
+ * thread, lidar_graph_slam_backend.cpp:39-40).  There is no CPU fallback: every call fails
+ * with LGS_ERR_CUDA when no sm_100-class device is usable.
+ *
+ * Reference interfaces replaced (file:line under the reference tree):
+ *   lgs_grid_*                 GridMap<T> storage read through Value(x, y, unknown)
+ *                              (grid_map/grid_map.hpp:859-873) and
+ *                              WorldCoordinateToGridCellIndex (grid_map.hpp:779-790)
+ *   lgs_precompute*            PrecomputeGridMap / PrecomputeGridMaps / SlidingWindowMaxRow /
+ *                              SlidingWindowMaxCol (mapping/grid_map_builder.cpp:403-536,
+ *                              util.hpp:199-253)
+ *   lgs_rtcsm_*                ScanMatcherRealTimeCorrelative::OptimizePose(grid, coarse, scan,
+ *                              pose, thr) incl. ComputeSearchStep / ComputeScanIndices /
+ *                              ComputeScore / EvaluateHighResolutionMap
+ *                              (mapping/scan_matcher_real_time_correlative.cpp:50-256)
+ *   lgs_bb_*                   ScanMatcherBranchBound::OptimizePose(grid, pyramids, scan, pose,
+ *                              thr) + ScorePixelAccurate::Score
+ *                              (mapping/scan_matcher_branch_bound.cpp:47-163,
+ *                              mapping/score_function_pixel_accurate.cpp:19-76)
+ *   lgs_grid_integrate_scans   GridMapBuilder::UpdateGridMap / ConstructMapFromScans scan
+ *                              integration loops (mapping/grid_map_builder.cpp:170-186, :311-328),
+ *                              Bresenham (util.hpp:257-303), BinaryBayesGridCell::Update
+ *                              (grid_map/binary_bayes_grid_cell.hpp:75-119)
+ *
+ * Matchers return window INDICES + score; the adapter rebuilds the pose with the reference's
+ * own expression (sensorPose.mX + bestWinX * stepX, scan_matcher_real_time_correlative.cpp:
+ * 122-125) and runs the host tail (Cost, ComputeCovariance, MoveBackward) unchanged.
+ */
+#ifndef LGS_B200_H
+#define LGS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGS_OK            0
+#define LGS_ERR_INVALID   1   /* bad argument */
+#define LGS_ERR_CUDA      2   /* CUDA runtime error or no usable device */
+#define LGS_ERR_NOMEM     3
+#define LGS_ERR_APRON     4   /* search window wider than the grid's zero apron */
+#define LGS_ERR_OVERFLOW  5   /* an internal work list overflowed its capacity */
+
+typedef struct lgs_ctx lgs_ctx;
+typedef struct lgs_grid lgs_grid;
+typedef struct lgs_rtcsm_batch lgs_rtcsm_batch;
+typedef struct lgs_pyramid lgs_pyramid;
+typedef struct lgs_bb_batch lgs_bb_batch;
+
+/* ---- context --------------------------------------------------------------------------- */
+int lgs_ctx_create(int device, lgs_ctx** out);
+int lgs_ctx_destroy(lgs_ctx* ctx);
+const char* lgs_ctx_last_error(const lgs_ctx* ctx);
+int lgs_ctx_synchronize(lgs_ctx* ctx);
+/* The cudaStream_t every call on this context is ordered on (for event timing). */
+void* lgs_ctx_stream(lgs_ctx* ctx);
+/* CUDA-event stopwatch on the context stream: start, enqueue work, stop -> milliseconds. */
+int lgs_ctx_timer_start(lgs_ctx* ctx);
+int lgs_ctx_timer_stop(lgs_ctx* ctx, float* ms);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long lgs_ctx_launch_count(const lgs_ctx* ctx);
+const char* lgs_version(void);
+
+/* ---- dense device grid ---------------------------------------------------------------------
+ * Row-major double[ny][nx], 0.0 = unknown, surrounded by `apron` zero cells on every side so
+ * that out-of-map reads return 0.0 exactly like GridMap::Value(x, y, unknown).  Cell (0,0)'s
+ * lower-left corner is at (min_x, min_y); index = floor((p - min) / res). */
+int lgs_grid_create(lgs_ctx* ctx, int nx, int ny, double min_x, double min_y, double res,
+                    int apron, lgs_grid** out);
+int lgs_grid_destroy(lgs_grid* g);
+int lgs_grid_upload(lgs_grid* g, const double* dense);       /* host [ny][nx] -> device */
+int lgs_grid_download(const lgs_grid* g, double* dense);     /* device -> host [ny][nx] */
+int lgs_grid_info(const lgs_grid* g, int* nx, int* ny, double* min_x, double* min_y,
+                  double* res, int* apron);
+
+/* ---- sliding-window-max precompute ---------------------------------------------------------
+ * out(x,y) = max grid[xs..xs+w) x [ys..ys+w), xs = min(x, max(nx-w, 0)) (the reference repeats
+ * the last full window at the upper edges).  `out` must have the geometry of `in`. */
+int lgs_precompute(lgs_ctx* ctx, const lgs_grid* in, int win, lgs_grid* out);
+/* Levels 0..height_max with windows 1, 2, ..., 2^height_max (PrecomputeGridMaps). */
+int lgs_pyramid_create(lgs_ctx* ctx, const lgs_grid* in, int height_max, lgs_pyramid** out);
+int lgs_pyramid_destroy(lgs_pyramid* p);
+int lgs_pyramid_download(const lgs_pyramid* p, int level, double* dense);
+int lgs_pyramid_levels(const lgs_pyramid* p);
+
+/* ---- scans -------------------------------------------------------------------------------- */
+typedef struct lgs_scan_batch {
+    int n_scans;
+    const int* beam_begin;      /* [n_scans + 1] offsets into angles / ranges              */
+    const double* angles;       /* ScanData::Angles()                                       */
+    const double* ranges;       /* ScanData::Ranges()                                       */
+    const double* sensor_pose;  /* [n_scans][3] Compound(initialPose, RelativeSensorPose()) */
+} lgs_scan_batch;
+
+typedef struct lgs_match_result {
+    int found;                  /* scoreMax > scoreThreshold                               */
+    int ix, iy, it;             /* bestWinX / bestWinY / bestWinTheta                      */
+    int win_x, win_y, win_t;    /* window half sizes derived like the reference            */
+    int n_fixups;               /* projected points re-derived on the host (near cell edge)*/
+    double step_x, step_y, step_t;
+    double score;               /* scoreMax (un-normalised sum), = threshold if !found     */
+    long long n_scored;         /* hypotheses / nodes actually summed on the device        */
+    int exact_replay;           /* 1 if the sequential CPU-order replay decided the winner */
+    int reserved;
+} lgs_match_result;
+
+/* ---- real-time correlative matcher ------------------------------------------------------ */
+typedef struct lgs_rtcsm_params {
+    int low_res;                /* mLowResolution  */
+    double range_x, range_y;    /* mRangeX, mRangeY (metres) */
+    double range_theta;         /* mRangeTheta (radians)     */
+    double scan_range_max;      /* mScanRangeMax             */
+} lgs_rtcsm_params;
+
+/* A batch object owns the device copies of the scans and all scratch (projected indices,
+ * score tables).  upload = host prep + H2D; run = kernels only (asynchronous on the context
+ * stream, inputs resident); results = D2H of the result records (+ rare host fix-ups). */
+int lgs_rtcsm_batch_create(lgs_ctx* ctx, const lgs_rtcsm_params* params, lgs_rtcsm_batch** out);
+int lgs_rtcsm_batch_destroy(lgs_rtcsm_batch* b);
+/* norm_threshold: [n_scans] normalised score thresholds, or NULL for DBL_MIN (the 1-argument
+ * OptimizePose overload).  `grid` supplies the geometry the window is derived from. */
+int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_scan_batch* scans,
+                           const double* norm_threshold);
+int lgs_rtcsm_batch_run(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse);
+int lgs_rtcsm_batch_results(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse,
+                            lgs_match_result* out);
+/* Test/diagnostic access to the per-match scratch of scan `m` after a run:
+ * fine[nT][nyw][nxw], coarse[nT][nbx][nby], cells[nT][nKept][2] (projected cell indices,
+ * un-clamped), dims = {nT, nxw, nyw, nbx, nby, nKept}.  Any pointer may be NULL. */
+int lgs_rtcsm_batch_debug(lgs_rtcsm_batch* b, int m, int* dims, double* fine, double* coarse,
+                          int* cells);
+/* Algorithmic work of the last upload: hypotheses (fine + coarse) and gathered cells. */
+int lgs_rtcsm_batch_work(const lgs_rtcsm_batch* b, long long* hypotheses, long long* gathers);
+/* Convenience: upload + run + results. */
+int lgs_rtcsm_match(lgs_ctx* ctx, const lgs_grid* grid, const lgs_grid* coarse,
+                    const lgs_rtcsm_params* params, const lgs_scan_batch* scans,
+                    const double* norm_threshold, lgs_match_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGS_B200_H */

@@ -1,0 +1,296 @@
+"""ctypes binding to liblgs_b200.so, the C-ABI of the sm_100a backend (include/lgs_b200.h).
+
+This is plumbing for tests and bench.py: every compute call goes through the C ABI exactly
+as the C++ adapters (adapters/) do.  There is NO fallback: if the shared library is missing
+or no B200-class GPU is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblgs_b200.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+vp = C.c_void_p
+
+ERRORS = {1: "LGS_ERR_INVALID", 2: "LGS_ERR_CUDA", 3: "LGS_ERR_NOMEM", 4: "LGS_ERR_APRON",
+          5: "LGS_ERR_OVERFLOW"}
+
+
+class LgsError(RuntimeError):
+    pass
+
+
+class ScanBatch(C.Structure):
+    _fields_ = [("n_scans", C.c_int), ("beam_begin", c_ip), ("angles", c_dp), ("ranges", c_dp),
+                ("sensor_pose", c_dp)]
+
+
+class MatchResult(C.Structure):
+    _fields_ = [("found", C.c_int), ("ix", C.c_int), ("iy", C.c_int), ("it", C.c_int),
+                ("win_x", C.c_int), ("win_y", C.c_int), ("win_t", C.c_int),
+                ("n_fixups", C.c_int), ("step_x", C.c_double), ("step_y", C.c_double),
+                ("step_t", C.c_double), ("score", C.c_double), ("n_scored", C.c_longlong),
+                ("exact_replay", C.c_int), ("reserved", C.c_int)]
+
+
+class RtcsmParams(C.Structure):
+    _fields_ = [("low_res", C.c_int), ("range_x", C.c_double), ("range_y", C.c_double),
+                ("range_theta", C.c_double), ("scan_range_max", C.c_double)]
+
+
+# name -> (restype, argtypes); also the list tests use to check the exported symbols.
+SIGNATURES = {
+    "lgs_version": (C.c_char_p, []),
+    "lgs_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "lgs_ctx_destroy": (C.c_int, [vp]),
+    "lgs_ctx_last_error": (C.c_char_p, [vp]),
+    "lgs_ctx_synchronize": (C.c_int, [vp]),
+    "lgs_ctx_stream": (vp, [vp]),
+    "lgs_ctx_timer_start": (C.c_int, [vp]),
+    "lgs_ctx_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    "lgs_ctx_launch_count": (C.c_longlong, [vp]),
+    "lgs_grid_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                  C.c_int, C.POINTER(vp)]),
+    "lgs_grid_destroy": (C.c_int, [vp]),
+    "lgs_grid_upload": (C.c_int, [vp, c_dp]),
+    "lgs_grid_download": (C.c_int, [vp, c_dp]),
+    "lgs_grid_info": (C.c_int, [vp, c_ip, c_ip, c_dp, c_dp, c_dp, c_ip]),
+    "lgs_precompute": (C.c_int, [vp, vp, C.c_int, vp]),
+    "lgs_pyramid_create": (C.c_int, [vp, vp, C.c_int, C.POINTER(vp)]),
+    "lgs_pyramid_destroy": (C.c_int, [vp]),
+    "lgs_pyramid_download": (C.c_int, [vp, C.c_int, c_dp]),
+    "lgs_pyramid_levels": (C.c_int, [vp]),
+    "lgs_rtcsm_batch_create": (C.c_int, [vp, C.POINTER(RtcsmParams), C.POINTER(vp)]),
+    "lgs_rtcsm_batch_destroy": (C.c_int, [vp]),
+    "lgs_rtcsm_batch_upload": (C.c_int, [vp, vp, C.POINTER(ScanBatch), c_dp]),
+    "lgs_rtcsm_batch_run": (C.c_int, [vp, vp, vp]),
+    "lgs_rtcsm_batch_results": (C.c_int, [vp, vp, vp, C.POINTER(MatchResult)]),
+    "lgs_rtcsm_batch_debug": (C.c_int, [vp, C.c_int, c_ip, c_dp, c_dp, c_ip]),
+    "lgs_rtcsm_batch_work": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "lgs_rtcsm_match": (C.c_int, [vp, vp, vp, C.POINTER(RtcsmParams), C.POINTER(ScanBatch), c_dp,
+                                  C.POINTER(MatchResult)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load liblgs_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LgsError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(c_dp)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.h = vp()
+        rc = lib().lgs_ctx_create(device, C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise LgsError(f"lgs_ctx_create(device={device}) failed with {ERRORS.get(rc, rc)}: "
+                           "a B200-class GPU is required, there is no CPU fallback")
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = lib().lgs_ctx_last_error(self.h)
+            raise LgsError(f"{ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def synchronize(self):
+        self.check(lib().lgs_ctx_synchronize(self.h))
+
+    def stream(self) -> int:
+        return lib().lgs_ctx_stream(self.h) or 0
+
+    def timer_start(self):
+        self.check(lib().lgs_ctx_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self.check(lib().lgs_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return lib().lgs_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().lgs_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Grid:
+    """Dense device grid (double[ny][nx], 0.0 = unknown, zero apron)."""
+
+    def __init__(self, ctx: Context, nx, ny, min_x, min_y, res, apron=64):
+        self.ctx = ctx
+        self.nx, self.ny, self.min_x, self.min_y, self.res, self.apron = \
+            int(nx), int(ny), float(min_x), float(min_y), float(res), int(apron)
+        self.h = vp()
+        ctx.check(lib().lgs_grid_create(ctx.h, self.nx, self.ny, self.min_x, self.min_y,
+                                        self.res, self.apron, C.byref(self.h)))
+
+    @classmethod
+    def from_dense(cls, ctx, dense, min_x, min_y, res, apron=64):
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        g = cls(ctx, dense.shape[1], dense.shape[0], min_x, min_y, res, apron)
+        g.upload(dense)
+        return g
+
+    def like(self):
+        return Grid(self.ctx, self.nx, self.ny, self.min_x, self.min_y, self.res, self.apron)
+
+    def upload(self, dense):
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        assert dense.shape == (self.ny, self.nx), (dense.shape, (self.ny, self.nx))
+        self.ctx.check(lib().lgs_grid_upload(self.h, _dptr(dense)))
+
+    def download(self):
+        out = np.empty((self.ny, self.nx), dtype=np.float64)
+        self.ctx.check(lib().lgs_grid_download(self.h, _dptr(out)))
+        return out
+
+    def precompute(self, win: int) -> "Grid":
+        out = self.like()
+        self.ctx.check(lib().lgs_precompute(self.ctx.h, self.h, int(win), out.h))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lgs_grid_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pyramid:
+    def __init__(self, ctx: Context, grid: Grid, height_max: int):
+        self.ctx, self.grid, self.height_max = ctx, grid, int(height_max)
+        self.h = vp()
+        ctx.check(lib().lgs_pyramid_create(ctx.h, grid.h, self.height_max, C.byref(self.h)))
+
+    def download(self, level: int):
+        out = np.empty((self.grid.ny, self.grid.nx), dtype=np.float64)
+        self.ctx.check(lib().lgs_pyramid_download(self.h, int(level), _dptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lgs_pyramid_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scans:
+    """Host-side scan batch in the C-ABI layout (keeps the numpy arrays alive)."""
+
+    def __init__(self, angles_list, ranges_list, sensor_poses, pinned: bool = False):
+        n = len(ranges_list)
+        assert len(angles_list) == n and len(sensor_poses) == n
+        counts = [len(r) for r in ranges_list]
+        self.beam_begin = np.zeros(n + 1, dtype=np.int32)
+        self.beam_begin[1:] = np.cumsum(counts)
+        self.angles = np.ascontiguousarray(np.concatenate(angles_list) if n else np.zeros(0),
+                                           dtype=np.float64)
+        self.ranges = np.ascontiguousarray(np.concatenate(ranges_list) if n else np.zeros(0),
+                                           dtype=np.float64)
+        self.sensor_pose = np.ascontiguousarray(np.asarray(sensor_poses, dtype=np.float64)
+                                                .reshape(n, 3))
+        self.n = n
+        self.c = ScanBatch(n, self.beam_begin.ctypes.data_as(c_ip), _dptr(self.angles),
+                           _dptr(self.ranges), _dptr(self.sensor_pose))
+
+    @property
+    def nbytes(self) -> int:
+        return (self.beam_begin.nbytes + self.angles.nbytes + self.ranges.nbytes +
+                self.sensor_pose.nbytes)
+
+
+class RtcsmBatch:
+    """lgs_rtcsm_batch: upload (host prep + H2D) / run (kernels) / results (D2H)."""
+
+    def __init__(self, ctx: Context, low_res=5, range_x=1.0, range_y=1.0,
+                 range_theta=1.0471975512, scan_range_max=20.0):
+        self.ctx = ctx
+        self.params = RtcsmParams(int(low_res), float(range_x), float(range_y),
+                                  float(range_theta), float(scan_range_max))
+        self.h = vp()
+        ctx.check(lib().lgs_rtcsm_batch_create(ctx.h, C.byref(self.params), C.byref(self.h)))
+        self.n = 0
+
+    def upload(self, grid: Grid, scans: Scans, norm_threshold=None):
+        thr = None
+        if norm_threshold is not None:
+            self._thr = np.ascontiguousarray(np.broadcast_to(
+                np.asarray(norm_threshold, dtype=np.float64), (scans.n,)))
+            thr = _dptr(self._thr)
+        self._scans = scans
+        self.ctx.check(lib().lgs_rtcsm_batch_upload(self.h, grid.h, C.byref(scans.c), thr))
+        self.n = scans.n
+
+    def run(self, grid: Grid, coarse: Grid):
+        self.ctx.check(lib().lgs_rtcsm_batch_run(self.h, grid.h, coarse.h))
+
+    def results(self, grid: Grid, coarse: Grid):
+        out = (MatchResult * max(self.n, 1))()
+        self.ctx.check(lib().lgs_rtcsm_batch_results(self.h, grid.h, coarse.h, out))
+        return list(out)[:self.n]
+
+    def work(self):
+        h, g = C.c_longlong(), C.c_longlong()
+        self.ctx.check(lib().lgs_rtcsm_batch_work(self.h, C.byref(h), C.byref(g)))
+        return h.value, g.value
+
+    def debug(self, m: int):
+        dims = (C.c_int * 6)()
+        self.ctx.check(lib().lgs_rtcsm_batch_debug(self.h, m, dims, None, None, None))
+        nt, nxw, nyw, nbx, nby, nk = list(dims)
+        fine = np.empty((nt, nyw, nxw), dtype=np.float64)
+        coarse = np.empty((nt, nbx, nby), dtype=np.float64)
+        cells = np.empty((nt, max(nk, 0), 2), dtype=np.int32)
+        self.ctx.check(lib().lgs_rtcsm_batch_debug(self.h, m, dims, _dptr(fine), _dptr(coarse),
+                                                   cells.ctypes.data_as(c_ip)))
+        return fine, coarse, cells
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lgs_rtcsm_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

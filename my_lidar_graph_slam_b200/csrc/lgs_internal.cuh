@@ -1,0 +1,86 @@
+// lgs_internal.cuh -- shared declarations of the sm_100a backend (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lgs_b200.h"
+
+struct lgs_grid {
+    lgs_ctx* ctx = nullptr;
+    int nx = 0, ny = 0, apron = 0;
+    int pitch = 0;        // nx + 2 * apron (cells)
+    int rows = 0;         // ny + 2 * apron
+    double min_x = 0, min_y = 0, res = 0;
+    double* d = nullptr;  // rows * pitch doubles; cell (x, y) at d[(y + apron) * pitch + x + apron]
+    __host__ __device__ const double* origin() const { return d + (size_t)apron * pitch + apron; }
+    __host__ __device__ double* origin() { return d + (size_t)apron * pitch + apron; }
+};
+
+int lgs_fail(lgs_ctx* ctx, int code, const char* fmt, ...);
+
+#define LGS_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return lgs_fail((ctx), LGS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__,   \
+                            #call, cudaGetErrorString(e__));                             \
+    } while (0)
+
+#define LGS_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        LGS_CUDA((ctx), cudaGetLastError());                                             \
+    } while (0)
+
+// Simple growable device / pinned-host buffers owned by batch objects.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct lgs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    long long launches = 0;
+    char err[512] = {0};
+    DevBuf<double> scratch;   // reusable device scratch (precompute intermediate)
+};
+
+// Fractional-cell guard band (in cells): a projected coordinate closer than this to a cell
+// edge is re-derived on the host with glibc sin/cos, because CUDA's double sin/cos may
+// differ from glibc's in the last ulp.  Device-vs-host differences are
+// below 1e-11 cells for |coordinates| < 1e4 m, so 1e-9 leaves two orders of magnitude.
+#define LGS_EDGE_EPS 1e-9

@@ -1,0 +1,97 @@
+"""Deterministic synthetic 2D worlds and laser scans.
+
+Axis-aligned rectangular rooms/corridors with analytic ray casting and Gaussian range
+noise.  The same scans feed the oracle and the CUDA path, so everything here is plain
+numpy with explicit seeds (world layout 1, range noise 2, pose perturbations 3).
+This is benchmark / test tooling, not part of the device hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class World:
+    """A set of axis-aligned wall segments inside an outer rectangle."""
+
+    def __init__(self, size_x: float = 40.0, size_y: float = 40.0, n_boxes: int = 12,
+                 seed: int = 1):
+        rng = np.random.default_rng(seed)
+        self.size_x, self.size_y = float(size_x), float(size_y)
+        hx, hy = size_x / 2.0, size_y / 2.0
+        segs = [(-hx, -hy, hx, -hy), (hx, -hy, hx, hy), (hx, hy, -hx, hy), (-hx, hy, -hx, -hy)]
+        self.boxes = []
+        for _ in range(n_boxes):
+            w, h = rng.uniform(1.0, 0.2 * size_x), rng.uniform(1.0, 0.2 * size_y)
+            cx = rng.uniform(-hx + w / 2 + 1.0, hx - w / 2 - 1.0)
+            cy = rng.uniform(-hy + h / 2 + 1.0, hy - h / 2 - 1.0)
+            x0, x1, y0, y1 = cx - w / 2, cx + w / 2, cy - h / 2, cy + h / 2
+            self.boxes.append((x0, y0, x1, y1))
+            segs += [(x0, y0, x1, y0), (x1, y0, x1, y1), (x1, y1, x0, y1), (x0, y1, x0, y0)]
+        s = np.asarray(segs, dtype=np.float64)
+        self.horizontal = s[s[:, 1] == s[:, 3]]   # y = const
+        self.vertical = s[s[:, 0] == s[:, 2]]     # x = const
+
+    def is_free(self, x: float, y: float, margin: float = 0.4) -> bool:
+        if abs(x) > self.size_x / 2 - margin or abs(y) > self.size_y / 2 - margin:
+            return False
+        for (x0, y0, x1, y1) in self.boxes:
+            if x0 - margin <= x <= x1 + margin and y0 - margin <= y <= y1 + margin:
+                return False
+        return True
+
+    def cast(self, x: float, y: float, angles: np.ndarray) -> np.ndarray:
+        """Distance to the first wall along each absolute angle."""
+        c, s = np.cos(angles), np.sin(angles)
+        best = np.full(angles.shape, 1e9)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for seg in self.horizontal:       # y = seg[1], x in [min, max]
+                t = (seg[1] - y) / s
+                xi = x + t * c
+                ok = (t > 1e-9) & (xi >= min(seg[0], seg[2])) & (xi <= max(seg[0], seg[2]))
+                best = np.where(ok & (t < best), t, best)
+            for seg in self.vertical:         # x = seg[0], y in [min, max]
+                t = (seg[0] - x) / c
+                yi = y + t * s
+                ok = (t > 1e-9) & (yi >= min(seg[1], seg[3])) & (yi <= max(seg[1], seg[3]))
+                best = np.where(ok & (t < best), t, best)
+        return best
+
+
+def beam_angles(n_beams: int = 1081, fov_deg: float = 270.0) -> np.ndarray:
+    fov = np.deg2rad(fov_deg)
+    return np.ascontiguousarray(-fov / 2.0 + fov * np.arange(n_beams) / (n_beams - 1))
+
+
+def make_scan(world: World, pose, angles: np.ndarray, noise_rng: np.random.Generator | None,
+              sigma: float = 0.01, max_range: float = 30.0) -> np.ndarray:
+    """Ranges of one scan taken with the *sensor* at `pose` = (x, y, theta)."""
+    r = world.cast(pose[0], pose[1], pose[2] + angles)
+    if noise_rng is not None:
+        r = r + noise_rng.normal(0.0, sigma, size=r.shape)
+    return np.ascontiguousarray(np.clip(r, 0.02, max_range))
+
+
+def trajectory(world: World, n: int, step: float = 0.25, seed: int = 1,
+               start=None) -> np.ndarray:
+    """A smooth random walk of `n` poses that stays in free space."""
+    rng = np.random.default_rng(seed + 1000)
+    if start is None:
+        while True:
+            x, y = rng.uniform(-world.size_x / 2, world.size_x / 2), rng.uniform(
+                -world.size_y / 2, world.size_y / 2)
+            if world.is_free(x, y, 0.8):
+                break
+        th = rng.uniform(-np.pi, np.pi)
+    else:
+        x, y, th = start
+    out = np.empty((n, 3))
+    for k in range(n):
+        out[k] = (x, y, th)
+        for _ in range(64):
+            nth = th + rng.normal(0.0, 0.15)
+            nx, ny = x + step * np.cos(nth), y + step * np.sin(nth)
+            if world.is_free(nx, ny, 0.6):
+                x, y, th = nx, ny, nth
+                break
+            th += rng.uniform(0.5, 1.5)
+    return out
