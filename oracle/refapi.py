@@ -267,7 +267,7 @@ def move_backward(a, b):
 
 
 def rtcsm_match(m: RefMap, angles, ranges, init_pose, *, low_res=5, range_x=1.0, range_y=1.0,
-                range_t=1.0471975512, scan_range_max=20.0, thr=None, pre: RefPre | None = None,
+                range_theta=1.0471975512, scan_range_max=20.0, thr=None, pre: RefPre | None = None,
                 rel=(0.0, 0.0, 0.0), scan_min_range=0.02, scan_max_range=30.0,
                 cost=DEFAULT_COST) -> MatchResult:
     """ScanMatcherRealTimeCorrelative::OptimizePose (5-argument overload).
@@ -281,7 +281,7 @@ def rtcsm_match(m: RefMap, angles, ranges, init_pose, *, low_res=5, range_x=1.0,
     if thr is None:
         thr = float(np.finfo(np.float64).tiny)
     lib().ref_rtcsm_match(m.h, pre.h if pre is not None else None, low_res, range_x, range_y,
-                          range_t, scan_range_max, costv, _arr3(init_pose), _arr3(rel), len(a),
+                          range_theta, scan_range_max, costv, _arr3(init_pose), _arr3(rel), len(a),
                           ap, rp, scan_min_range, scan_max_range, thr, C.byref(out))
     return out
 
@@ -304,7 +304,7 @@ def rtcsm_score_table(m: RefMap, pre: RefPre, use_coarse, low_res, scan_range_ma
 
 
 def bb_match(m: RefMap, angles, ranges, init_pose, *, height_max=6, range_x=2.0, range_y=2.0,
-             range_t=1.0, scan_range_max=20.0, score_range_min=0.01, score_range_max=20.0,
+             range_theta=1.0, scan_range_max=20.0, score_range_min=0.01, score_range_max=20.0,
              thr=0.6, pyramid=None, rel=(0.0, 0.0, 0.0), scan_min_range=0.02,
              scan_max_range=30.0, cost=DEFAULT_COST) -> MatchResult:
     """ScanMatcherBranchBound::OptimizePose (5-argument overload)."""
@@ -315,7 +315,7 @@ def bb_match(m: RefMap, angles, ranges, init_pose, *, height_max=6, range_x=2.0,
     pyr = None
     if pyramid is not None:
         pyr = (C.c_void_p * len(pyramid))(*[p.h for p in pyramid])
-    lib().ref_bb_match(m.h, pyr, height_max, range_x, range_y, range_t, scan_range_max,
+    lib().ref_bb_match(m.h, pyr, height_max, range_x, range_y, range_theta, scan_range_max,
                        score_range_min, score_range_max, costv, _arr3(init_pose), _arr3(rel),
                        len(a), ap, rp, scan_min_range, scan_max_range, thr, C.byref(out))
     return out

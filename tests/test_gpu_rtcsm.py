@@ -125,16 +125,26 @@ def test_rtcsm_scan_overhanging_lower_left_edge(ctx):
     assert np.array_equal(grid.download(), refmap.dense())
     params = dict(low_res=5, range_x=1.0, range_y=1.0, range_theta=0.2, scan_range_max=20.0)
     angles = synth.beam_angles(181, 180.0)
-    replayed = 0
+    replayed = differs_from_exhaustive = 0
     for k in range(10):
-        ranges = rng.uniform(0.3, 3.0, angles.shape)
-        init = np.array([-1.0 + rng.uniform(-0.2, 0.6), -2.0 + rng.uniform(-0.2, 0.6), rng.uniform(0, 1.5)])
+        # short beams pointing at the x < 0 half plane from just inside the left edge: for many
+        # window offsets the coarse index is negative (reads 0) while the fine cells are inside
+        ranges = rng.uniform(0.1, 0.5, angles.shape)
+        init = np.array([-1.0 + rng.uniform(0.0, 0.3), -2.0 + rng.uniform(0.5, 3.0),
+                         np.pi + rng.uniform(-0.3, 0.3)])
         ref = R.rtcsm_match(refmap, angles, ranges, init, pre=pre, **params)
-        out, = _run_one(ctx, grid, coarse, params, angles, ranges, init)
+        batch = capi.RtcsmBatch(ctx, **params)
+        batch.upload(grid, capi.Scans([angles], [ranges], [init]))
+        batch.run(grid, coarse)
+        out, = batch.results(grid, coarse)
         assert (out.found, out.ix, out.iy, out.it) == (ref.found, ref.ix, ref.iy, ref.it)
         assert out.score == ref.score
         replayed += out.exact_replay
+        fine, _, _ = batch.debug(0)
+        differs_from_exhaustive += int(fine.max() != ref.score)
     assert replayed > 0, "scene was meant to exercise the sequential CPU-order replay"
+    # in this scene the reference's pruned search really does miss the exhaustive optimum
+    assert differs_from_exhaustive > 0
 
 
 def _run_one(ctx, grid, coarse, params, angles, ranges, init, thr=None):
