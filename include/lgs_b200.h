@@ -129,6 +129,10 @@ int lgs_rtcsm_batch_destroy(lgs_rtcsm_batch* b);
 int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_scan_batch* scans,
                            const double* norm_threshold);
 int lgs_rtcsm_batch_run(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse);
+/* Same as run, but brackets the three kernels with CUDA events and waits:
+ * ms[0] = projection, ms[1] = sweep (the hot kernel), ms[2] = selection. */
+int lgs_rtcsm_batch_run_timed(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse,
+                              float* ms);
 int lgs_rtcsm_batch_results(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse,
                             lgs_match_result* out);
 /* Test/diagnostic access to the per-match scratch of scan `m` after a run:

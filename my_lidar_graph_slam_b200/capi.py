@@ -70,6 +70,7 @@ SIGNATURES = {
     "lgs_rtcsm_batch_destroy": (C.c_int, [vp]),
     "lgs_rtcsm_batch_upload": (C.c_int, [vp, vp, C.POINTER(ScanBatch), c_dp]),
     "lgs_rtcsm_batch_run": (C.c_int, [vp, vp, vp]),
+    "lgs_rtcsm_batch_run_timed": (C.c_int, [vp, vp, vp, C.POINTER(C.c_float)]),
     "lgs_rtcsm_batch_results": (C.c_int, [vp, vp, vp, C.POINTER(MatchResult)]),
     "lgs_rtcsm_batch_debug": (C.c_int, [vp, C.c_int, c_ip, c_dp, c_dp, c_ip]),
     "lgs_rtcsm_batch_work": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
@@ -262,6 +263,12 @@ class RtcsmBatch:
 
     def run(self, grid: Grid, coarse: Grid):
         self.ctx.check(lib().lgs_rtcsm_batch_run(self.h, grid.h, coarse.h))
+
+    def run_timed(self, grid: Grid, coarse: Grid):
+        """-> (ms_project, ms_sweep, ms_select), CUDA events around each kernel."""
+        ms = (C.c_float * 3)()
+        self.ctx.check(lib().lgs_rtcsm_batch_run_timed(self.h, grid.h, coarse.h, ms))
+        return tuple(ms)
 
     def results(self, grid: Grid, coarse: Grid):
         out = (MatchResult * max(self.n, 1))()

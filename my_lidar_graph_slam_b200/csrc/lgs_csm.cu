@@ -311,7 +311,7 @@ struct lgs_rtcsm_batch {
     bool uploaded = false, ran = false;
 };
 
-static int csm_launch_sweep_select(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse) {
+static int csm_launch_sweep(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse) {
     lgs_ctx* c = b->ctx;
     const CsmWindow& w = b->win;
     for (int m0 = 0; m0 < b->nMatch; m0 += 65535) {
@@ -323,11 +323,21 @@ static int csm_launch_sweep_select(lgs_rtcsm_batch* b, const lgs_grid* grid, con
             b->dFine.p, b->dCoarse.p);
         LGS_LAUNCH_CHECK(c);
     }
-    csm_select_kernel<<<b->nMatch, 256, 0, c->stream>>>(b->dDescs.p, w, b->dFine.p, b->dCoarse.p,
-                                                        b->dBlockMax.p, b->dBlockArg.p,
-                                                        b->dResults.p);
+    return LGS_OK;
+}
+
+static int csm_launch_select(lgs_rtcsm_batch* b) {
+    lgs_ctx* c = b->ctx;
+    csm_select_kernel<<<b->nMatch, 256, 0, c->stream>>>(b->dDescs.p, b->win, b->dFine.p,
+                                                        b->dCoarse.p, b->dBlockMax.p,
+                                                        b->dBlockArg.p, b->dResults.p);
     LGS_LAUNCH_CHECK(c);
     return LGS_OK;
+}
+
+static int csm_launch_sweep_select(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse) {
+    const int rc = csm_launch_sweep(b, grid, coarse);
+    return rc != LGS_OK ? rc : csm_launch_select(b);
 }
 
 extern "C" {
@@ -477,16 +487,20 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     return LGS_OK;
 }
 
-int lgs_rtcsm_batch_run(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse) {
+static int csm_run_impl(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse, float* ms) {
     if (!b || !grid || !coarse) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
     if (!b->uploaded) return lgs_fail(c, LGS_ERR_INVALID, "rtcsm_batch_run before upload");
     if (coarse->nx != grid->nx || coarse->ny != grid->ny || coarse->pitch != grid->pitch ||
         grid->pitch != b->geom.pitch || grid->nx != b->geom.nx || grid->ny != b->geom.ny)
         return lgs_fail(c, LGS_ERR_INVALID, "rtcsm_batch_run: grid geometry mismatch");
+    if (ms) ms[0] = ms[1] = ms[2] = 0.f;
     if (b->nMatch == 0) { b->ran = true; return LGS_OK; }
     LGS_CUDA(c, cudaSetDevice(c->device));
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (ms) for (auto& e : ev) LGS_CUDA(c, cudaEventCreate(&e));
     LGS_CUDA(c, cudaMemsetAsync(b->dFlagCount.p, 0, sizeof(int), c->stream));
+    if (ms) LGS_CUDA(c, cudaEventRecord(ev[0], c->stream));
     for (int m0 = 0; m0 < b->nMatch; m0 += 65535) {
         const int nm = std::min(65535, b->nMatch - m0);
         const long long per = (long long)b->maxNT * b->maxKeptPad;
@@ -497,10 +511,30 @@ int lgs_rtcsm_batch_run(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid
                                                            b->dFlagCount.p);
         LGS_LAUNCH_CHECK(c);
     }
-    const int rc = csm_launch_sweep_select(b, grid, coarse);
+    if (ms) LGS_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    int rc = csm_launch_sweep(b, grid, coarse);
     if (rc != LGS_OK) return rc;
+    if (ms) LGS_CUDA(c, cudaEventRecord(ev[2], c->stream));
+    rc = csm_launch_select(b);
+    if (rc != LGS_OK) return rc;
+    if (ms) {
+        LGS_CUDA(c, cudaEventRecord(ev[3], c->stream));
+        LGS_CUDA(c, cudaEventSynchronize(ev[3]));
+        for (int k = 0; k < 3; ++k) LGS_CUDA(c, cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     b->ran = true;
     return LGS_OK;
+}
+
+int lgs_rtcsm_batch_run(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse) {
+    return csm_run_impl(b, grid, coarse, nullptr);
+}
+
+int lgs_rtcsm_batch_run_timed(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse,
+                              float* ms) {
+    if (!ms) return LGS_ERR_INVALID;
+    return csm_run_impl(b, grid, coarse, ms);
 }
 
 int lgs_rtcsm_batch_results(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse,

@@ -95,3 +95,80 @@ def trajectory(world: World, n: int, step: float = 0.25, seed: int = 1,
                 break
             th += rng.uniform(0.5, 1.5)
     return out
+
+
+def rasterize_map(scan_poses, angles, ranges_list, res: float = 0.05, patch: int = 64,
+                  rmin: float = 0.01, rmax: float = 20.0, p_hit: float = 0.6,
+                  p_miss: float = 0.45):
+    """Numpy stand-in for scan integration, used ONLY to synthesise benchmark grids without
+    touching the oracle: per-cell hit/miss counts folded through the odds product, clamped to
+    [1e-3, 0.999], 0.0 = unknown, geometry aligned to `patch` cells.  Order-insensitive, so it
+    is not bit-identical to the reference integration -- it only reproduces its value
+    distribution (free ~1e-3..0.45, walls ~0.6..0.999).  Returns (dense[ny][nx], min_x, min_y).
+    """
+    pts = []
+    for pose, r in zip(scan_poses, ranges_list):
+        ok = (r > rmin) & (r < rmax)
+        pts.append(np.stack([pose[0] + r[ok] * np.cos(pose[2] + angles[ok]),
+                             pose[1] + r[ok] * np.sin(pose[2] + angles[ok])], 1))
+        pts.append(np.asarray(pose[:2])[None, :])
+    allp = np.concatenate(pts)
+    lo = np.floor(allp.min(0) / (res * patch)) * (res * patch)
+    hi = np.ceil((allp.max(0) + 1e-9) / (res * patch)) * (res * patch)
+    nx, ny = int(round((hi[0] - lo[0]) / res)), int(round((hi[1] - lo[1]) / res))
+    hits = np.zeros((ny, nx), dtype=np.int32)
+    miss = np.zeros((ny, nx), dtype=np.int32)
+    for pose, r in zip(scan_poses, ranges_list):
+        ok = (r > rmin) & (r < rmax)
+        rr, aa = r[ok], pose[2] + angles[ok]
+        c, s = np.cos(aa), np.sin(aa)
+        ex = np.floor((pose[0] + rr * c - lo[0]) / res).astype(np.int64)
+        ey = np.floor((pose[1] + rr * s - lo[1]) / res).astype(np.int64)
+        np.add.at(hits, (ey, ex), 1)
+        nstep = int(np.ceil(rr.max() / (0.5 * res)))
+        t = (np.arange(nstep) * 0.5 * res)[None, :]
+        valid = t < (rr[:, None] - res)
+        mx = np.floor((pose[0] + t * c[:, None] - lo[0]) / res).astype(np.int64)
+        my = np.floor((pose[1] + t * s[:, None] - lo[1]) / res).astype(np.int64)
+        lin = (np.arange(len(rr))[:, None] * (nx * ny) + my * nx + mx)[valid]
+        lin = np.unique(lin) % (nx * ny)          # one miss per (beam, cell)
+        np.add.at(miss.reshape(-1), lin, 1)
+    odds = (p_hit / (1 - p_hit)) ** hits * (p_miss / (1 - p_miss)) ** miss
+    dense = np.clip(odds / (1 + odds), 1e-3, 1 - 1e-3)
+    dense[(hits + miss) == 0] = 0.0
+    return np.ascontiguousarray(dense), float(lo[0]), float(lo[1])
+
+
+class RoomsWorld(World):
+    """Office-like world: a lattice of `room` x `room` metre rooms whose walls each have one
+    door gap.  Most beams end within one room (ranges below ~room * 1.4) while a few pass
+    through doors, which is the range distribution config C2 assumes (ScanRangeMax 5.7 m keeps
+    nearly every beam) on a map that still spans hundreds of cells."""
+
+    def __init__(self, size: float = 40.0, room: float = 5.0, door: float = 1.2, seed: int = 1):
+        rng = np.random.default_rng(seed)
+        self.size_x = self.size_y = float(size)
+        self.boxes = []
+        h = size / 2.0
+        n = int(round(size / room))
+        segs = [(-h, -h, h, -h), (h, -h, h, h), (h, h, -h, h), (-h, h, -h, -h)]
+        for i in range(1, n):          # interior wall lines
+            c = -h + i * room
+            for j in range(n):         # one wall piece per room side, with a door gap
+                a0 = -h + j * room
+                g = a0 + rng.uniform(0.4, room - door - 0.4)
+                segs += [(c, a0, c, g), (c, g + door, c, a0 + room)]          # vertical wall x = c
+                g = a0 + rng.uniform(0.4, room - door - 0.4)
+                segs += [(a0, c, g, c), (g + door, c, a0 + room, c)]          # horizontal wall y = c
+        s = np.asarray(segs, dtype=np.float64)
+        self.horizontal = s[s[:, 1] == s[:, 3]]
+        self.vertical = s[s[:, 0] == s[:, 2]]
+        self.room, self.n_rooms = room, n
+
+    def is_free(self, x: float, y: float, margin: float = 0.4) -> bool:
+        h = self.size_x / 2.0
+        if abs(x) > h - margin or abs(y) > h - margin:
+            return False
+        fx = (x + h) % self.room
+        fy = (y + h) % self.room
+        return (margin <= fx <= self.room - margin) and (margin <= fy <= self.room - margin)
