@@ -67,6 +67,11 @@ int lgs_ctx_timer_stop(lgs_ctx* ctx, float* ms);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long lgs_ctx_launch_count(const lgs_ctx* ctx);
 const char* lgs_version(void);
+/* Test hook: width (in cells) of the guard band around cell edges inside which a projected
+ * point is re-derived on the host with glibc sin/cos (default 1e-9).  Raising it only moves
+ * more points onto the exact host path; results must not change. */
+void lgs_set_edge_eps(double eps);
+double lgs_get_edge_eps(void);
 
 /* ---- dense device grid ---------------------------------------------------------------------
  * Row-major double[ny][nx], 0.0 = unknown, surrounded by `apron` zero cells on every side so
@@ -97,6 +102,8 @@ typedef struct lgs_scan_batch {
     const double* angles;       /* ScanData::Angles()                                       */
     const double* ranges;       /* ScanData::Ranges()                                       */
     const double* sensor_pose;  /* [n_scans][3] Compound(initialPose, RelativeSensorPose()) */
+    const double* range_min;    /* [n_scans] ScanData::MinRange(), NULL = 0 (branch-and-bound only) */
+    const double* range_max;    /* [n_scans] ScanData::MaxRange(), NULL = +inf                      */
 } lgs_scan_batch;
 
 typedef struct lgs_match_result {
@@ -146,6 +153,36 @@ int lgs_rtcsm_batch_work(const lgs_rtcsm_batch* b, long long* hypotheses, long l
 int lgs_rtcsm_match(lgs_ctx* ctx, const lgs_grid* grid, const lgs_grid* coarse,
                     const lgs_rtcsm_params* params, const lgs_scan_batch* scans,
                     const double* norm_threshold, lgs_match_result* out);
+
+/* ---- branch-and-bound matcher (loop detection) ------------------------------------------------
+ * One query = (scan, sensor pose, submap pyramid).  All queries of a batch are searched
+ * breadth-first, level by level, together. */
+typedef struct lgs_bb_params {
+    int node_height_max;            /* mNodeHeightMax (pyramids need levels 0..node_height_max) */
+    double range_x, range_y;        /* mRangeX, mRangeY (metres) */
+    double range_theta;             /* mRangeTheta (radians)     */
+    double scan_range_max;          /* mScanRangeMax             */
+    double score_range_min;         /* ScorePixelAccurate::mUsableRangeMin */
+    double score_range_max;         /* ScorePixelAccurate::mUsableRangeMax */
+} lgs_bb_params;
+
+int lgs_bb_batch_create(lgs_ctx* ctx, const lgs_bb_params* params, lgs_bb_batch** out);
+int lgs_bb_batch_destroy(lgs_bb_batch* b);
+/* scans->n_scans queries; pyramids[q] is the submap query q is matched against (pyramids may
+ * repeat); norm_threshold[q] as for the correlative matcher. */
+int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans,
+                        lgs_pyramid* const* pyramids, const double* norm_threshold);
+int lgs_bb_batch_run(lgs_bb_batch* b);
+int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out);
+/* Nodes scored per tree level (index = height) and gathered cells during the last run. */
+int lgs_bb_batch_work(const lgs_bb_batch* b, long long* nodes_per_level, int n_levels,
+                      long long* gathers);
+/* Test hook: force the sequential CPU-order replay for every query of the next runs. */
+int lgs_bb_batch_force_replay(lgs_bb_batch* b, int on);
+/* Convenience: upload + run + results. */
+int lgs_bb_match(lgs_ctx* ctx, const lgs_bb_params* params, const lgs_scan_batch* scans,
+                 lgs_pyramid* const* pyramids, const double* norm_threshold,
+                 lgs_match_result* out);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -28,7 +29,7 @@ class LgsError(RuntimeError):
 
 class ScanBatch(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("beam_begin", c_ip), ("angles", c_dp), ("ranges", c_dp),
-                ("sensor_pose", c_dp)]
+                ("sensor_pose", c_dp), ("range_min", c_dp), ("range_max", c_dp)]
 
 
 class MatchResult(C.Structure):
@@ -39,6 +40,12 @@ class MatchResult(C.Structure):
                 ("exact_replay", C.c_int), ("reserved", C.c_int)]
 
 
+class BbParams(C.Structure):
+    _fields_ = [("node_height_max", C.c_int), ("range_x", C.c_double), ("range_y", C.c_double),
+                ("range_theta", C.c_double), ("scan_range_max", C.c_double),
+                ("score_range_min", C.c_double), ("score_range_max", C.c_double)]
+
+
 class RtcsmParams(C.Structure):
     _fields_ = [("low_res", C.c_int), ("range_x", C.c_double), ("range_y", C.c_double),
                 ("range_theta", C.c_double), ("scan_range_max", C.c_double)]
@@ -47,6 +54,8 @@ class RtcsmParams(C.Structure):
 # name -> (restype, argtypes); also the list tests use to check the exported symbols.
 SIGNATURES = {
     "lgs_version": (C.c_char_p, []),
+    "lgs_set_edge_eps": (None, [C.c_double]),
+    "lgs_get_edge_eps": (C.c_double, []),
     "lgs_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "lgs_ctx_destroy": (C.c_int, [vp]),
     "lgs_ctx_last_error": (C.c_char_p, [vp]),
@@ -76,6 +85,16 @@ SIGNATURES = {
     "lgs_rtcsm_batch_work": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "lgs_rtcsm_match": (C.c_int, [vp, vp, vp, C.POINTER(RtcsmParams), C.POINTER(ScanBatch), c_dp,
                                   C.POINTER(MatchResult)]),
+    "lgs_bb_batch_create": (C.c_int, [vp, C.POINTER(BbParams), C.POINTER(vp)]),
+    "lgs_bb_batch_destroy": (C.c_int, [vp]),
+    "lgs_bb_batch_upload": (C.c_int, [vp, C.POINTER(ScanBatch), C.POINTER(vp), c_dp]),
+    "lgs_bb_batch_run": (C.c_int, [vp]),
+    "lgs_bb_batch_results": (C.c_int, [vp, C.POINTER(MatchResult)]),
+    "lgs_bb_batch_work": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int,
+                                    C.POINTER(C.c_longlong)]),
+    "lgs_bb_batch_force_replay": (C.c_int, [vp, C.c_int]),
+    "lgs_bb_match": (C.c_int, [vp, C.POINTER(BbParams), C.POINTER(ScanBatch), C.POINTER(vp), c_dp,
+                               C.POINTER(MatchResult)]),
 }
 
 _lib = None
@@ -103,6 +122,7 @@ def _dptr(a):
 class Context:
     def __init__(self, device: int = 0):
         self.h = vp()
+        self._children = weakref.WeakSet()   # device objects that must die before the context
         rc = lib().lgs_ctx_create(device, C.byref(self.h))
         if rc != 0:
             self.h = None
@@ -131,8 +151,13 @@ class Context:
     def launch_count(self) -> int:
         return lib().lgs_ctx_launch_count(self.h)
 
+    def adopt(self, child):
+        self._children.add(child)
+
     def close(self):
         if self.h:
+            for child in list(self._children):
+                child.close()
             lib().lgs_ctx_destroy(self.h)
             self.h = None
 
@@ -153,6 +178,7 @@ class Grid:
         self.h = vp()
         ctx.check(lib().lgs_grid_create(ctx.h, self.nx, self.ny, self.min_x, self.min_y,
                                         self.res, self.apron, C.byref(self.h)))
+        ctx.adopt(self)
 
     @classmethod
     def from_dense(cls, ctx, dense, min_x, min_y, res, apron=64):
@@ -196,6 +222,7 @@ class Pyramid:
         self.ctx, self.grid, self.height_max = ctx, grid, int(height_max)
         self.h = vp()
         ctx.check(lib().lgs_pyramid_create(ctx.h, grid.h, self.height_max, C.byref(self.h)))
+        ctx.adopt(self)
 
     def download(self, level: int):
         out = np.empty((self.grid.ny, self.grid.nx), dtype=np.float64)
@@ -217,7 +244,7 @@ class Pyramid:
 class Scans:
     """Host-side scan batch in the C-ABI layout (keeps the numpy arrays alive)."""
 
-    def __init__(self, angles_list, ranges_list, sensor_poses, pinned: bool = False):
+    def __init__(self, angles_list, ranges_list, sensor_poses, range_min=None, range_max=None):
         n = len(ranges_list)
         assert len(angles_list) == n and len(sensor_poses) == n
         counts = [len(r) for r in ranges_list]
@@ -230,8 +257,14 @@ class Scans:
         self.sensor_pose = np.ascontiguousarray(np.asarray(sensor_poses, dtype=np.float64)
                                                 .reshape(n, 3))
         self.n = n
+        self.range_min = None if range_min is None else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(range_min, dtype=np.float64), (n,)))
+        self.range_max = None if range_max is None else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(range_max, dtype=np.float64), (n,)))
         self.c = ScanBatch(n, self.beam_begin.ctypes.data_as(c_ip), _dptr(self.angles),
-                           _dptr(self.ranges), _dptr(self.sensor_pose))
+                           _dptr(self.ranges), _dptr(self.sensor_pose),
+                           None if self.range_min is None else _dptr(self.range_min),
+                           None if self.range_max is None else _dptr(self.range_max))
 
     @property
     def nbytes(self) -> int:
@@ -249,6 +282,7 @@ class RtcsmBatch:
                                   float(range_theta), float(scan_range_max))
         self.h = vp()
         ctx.check(lib().lgs_rtcsm_batch_create(ctx.h, C.byref(self.params), C.byref(self.h)))
+        ctx.adopt(self)
         self.n = 0
 
     def upload(self, grid: Grid, scans: Scans, norm_threshold=None):
@@ -301,3 +335,62 @@ class RtcsmBatch:
             self.close()
         except Exception:
             pass
+
+
+class BbBatch:
+    """lgs_bb_batch: breadth-first branch-and-bound over a batch of (scan, pyramid) queries."""
+
+    def __init__(self, ctx: Context, node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0,
+                 scan_range_max=20.0, score_range_min=0.01, score_range_max=20.0):
+        self.ctx = ctx
+        self.params = BbParams(int(node_height_max), float(range_x), float(range_y),
+                               float(range_theta), float(scan_range_max),
+                               float(score_range_min), float(score_range_max))
+        self.h = vp()
+        ctx.check(lib().lgs_bb_batch_create(ctx.h, C.byref(self.params), C.byref(self.h)))
+        ctx.adopt(self)
+        self.n = 0
+
+    def upload(self, scans: Scans, pyramids, norm_threshold=0.6):
+        assert len(pyramids) == scans.n
+        self._pyr = (vp * max(scans.n, 1))(*[p.h for p in pyramids])
+        self._keep = (scans, list(pyramids))
+        thr = None
+        if norm_threshold is not None:
+            self._thr = np.ascontiguousarray(np.broadcast_to(
+                np.asarray(norm_threshold, dtype=np.float64), (scans.n,)))
+            thr = _dptr(self._thr)
+        self.ctx.check(lib().lgs_bb_batch_upload(self.h, C.byref(scans.c), self._pyr, thr))
+        self.n = scans.n
+
+    def run(self):
+        self.ctx.check(lib().lgs_bb_batch_run(self.h))
+
+    def results(self):
+        out = (MatchResult * max(self.n, 1))()
+        self.ctx.check(lib().lgs_bb_batch_results(self.h, out))
+        return list(out)[:self.n]
+
+    def work(self):
+        lv = (C.c_longlong * 21)()
+        g = C.c_longlong()
+        self.ctx.check(lib().lgs_bb_batch_work(self.h, lv, 21, C.byref(g)))
+        return list(lv)[:self.params.node_height_max + 1], g.value
+
+    def force_replay(self, on: bool):
+        self.ctx.check(lib().lgs_bb_batch_force_replay(self.h, int(on)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lgs_bb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def set_edge_eps(eps: float):
+    lib().lgs_set_edge_eps(float(eps))

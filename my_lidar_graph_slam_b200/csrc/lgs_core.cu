@@ -17,7 +17,12 @@ int lgs_fail(lgs_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
+double g_lgs_edge_eps = LGS_EDGE_EPS_DEFAULT;
+
 extern "C" {
+
+void lgs_set_edge_eps(double eps) { g_lgs_edge_eps = (eps > 0.0 && eps < 0.5) ? eps : LGS_EDGE_EPS_DEFAULT; }
+double lgs_get_edge_eps(void) { return g_lgs_edge_eps; }
 
 const char* lgs_version(void) { return "lgs_b200 0.1 (sm_100a)"; }
 

@@ -8,7 +8,7 @@
 // Exactness strategy:
 //  * csm_project_kernel projects every kept beam once per theta with the reference's exact
 //    operation order (IEEE add/mul/div intrinsics, never fused).  Only sin/cos can differ from
-//    glibc by an ulp, which can change floor() only within LGS_EDGE_EPS of a cell edge; such
+//    glibc by an ulp, which can change floor() only within the edge guard band of a cell edge; such
 //    points are flagged and re-derived on the host with glibc before the result is accepted.
 //  * csm_sweep_kernel gives every hypothesis its own thread, which sums the gathered cells in
 //    beam order in double: the score is bit-identical to the CPU loop by construction, so no
@@ -74,7 +74,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // :178-203; sensor_data.hpp:162-173; grid_map.hpp:779-790.
 __global__ void csm_project_kernel(const CsmDesc* __restrict__ descs,
                                    const double* __restrict__ angles,
-                                   const double* __restrict__ ranges, GridGeom g, CsmWindow w,
+                                   const double* __restrict__ ranges, GridGeom g, CsmWindow w, double eps,
                                    int* __restrict__ offs, int2* __restrict__ cells,
                                    FlagEntry* __restrict__ flags, int* __restrict__ flagCount) {
     const CsmDesc d = descs[blockIdx.y];
@@ -100,8 +100,7 @@ __global__ void csm_project_kernel(const CsmDesc* __restrict__ descs,
     const double qy = __ddiv_rn(__dsub_rn(hy, g.minY), g.res);
     const double fx = floor(qx), fy = floor(qy);
     const double rx = qx - fx, ry = qy - fy;
-    const bool edge = !(rx >= LGS_EDGE_EPS && rx <= 1.0 - LGS_EDGE_EPS &&
-                        ry >= LGS_EDGE_EPS && ry <= 1.0 - LGS_EDGE_EPS);
+    const bool edge = !(rx >= eps && rx <= 1.0 - eps && ry >= eps && ry <= 1.0 - eps);
     if (edge) {
         const int k = atomicAdd(flagCount, 1);
         if (k < kFlagCap) flags[k] = FlagEntry{(int)blockIdx.y, t, i};
@@ -507,7 +506,7 @@ static int csm_run_impl(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid
         dim3 gridDim((unsigned)((per + 255) / 256), nm);
         csm_project_kernel<<<gridDim, 256, 0, c->stream>>>(b->dDescs.p + m0, b->dAngles.p,
                                                            b->dRanges.p, b->geom, b->win,
-                                                           b->dOffs.p, b->dCells.p, b->dFlags.p,
+                                                           g_lgs_edge_eps, b->dOffs.p, b->dCells.p, b->dFlags.p,
                                                            b->dFlagCount.p);
         LGS_LAUNCH_CHECK(c);
     }

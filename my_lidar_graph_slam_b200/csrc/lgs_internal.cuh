@@ -83,4 +83,8 @@ struct lgs_ctx {
 // edge is re-derived on the host with glibc sin/cos, because CUDA's double sin/cos may
 // differ from glibc's in the last ulp.  Device-vs-host differences are
 // below 1e-11 cells for |coordinates| < 1e4 m, so 1e-9 leaves two orders of magnitude.
-#define LGS_EDGE_EPS 1e-9
+#define LGS_EDGE_EPS_DEFAULT 1e-9
+extern double g_lgs_edge_eps;
+
+// Pyramid levels are plain grids sharing the geometry of the map they were built from.
+const lgs_grid* lgs_pyramid_level(const lgs_pyramid* p, int level);
