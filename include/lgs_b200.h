@@ -85,6 +85,43 @@ int lgs_grid_download(const lgs_grid* g, double* dense);     /* device -> host [
 int lgs_grid_info(const lgs_grid* g, int* nx, int* ny, double* min_x, double* min_y,
                   double* res, int* apron);
 
+/* Mirror of GridMap::Resize's patch copy (grid_map.hpp:652-711): the grid becomes nx x ny cells
+ * at (min_x, min_y); new cell (x, y) takes old cell (x + shift_x, y + shift_y), 0.0 elsewhere. */
+int lgs_grid_resize(lgs_grid* g, int nx, int ny, double min_x, double min_y, int shift_x,
+                    int shift_y);
+int lgs_grid_clear(lgs_grid* g);                             /* GridMap::Reset */
+
+/* ---- occupancy-grid scan integration ---------------------------------------------------------
+ * Per scan: sensor position and the hit points of the beams that passed the range filter, in
+ * beam order, exactly as ComputeBoundingBoxAndScanPoints / ConstructMapFromScans produce them
+ * (grid_map_builder.cpp:335-380, :240-277).  Scans are applied in order; every touched cell
+ * must already be inside the grid (expand first).  n_updates (optional) receives the number of
+ * BinaryBayesGridCell::Update calls the CPU would have made. */
+typedef struct lgs_hit_batch {
+    int n_scans;
+    const double* sensor_xy;    /* [n_scans][2]           */
+    const int* hit_begin;       /* [n_scans + 1]          */
+    const double* hit_xy;       /* [hit_begin[n_scans]][2] */
+} lgs_hit_batch;
+int lgs_grid_integrate_scans(lgs_ctx* ctx, lgs_grid* grid, const lgs_hit_batch* scans,
+                             double p_hit, double p_miss, long long* n_updates);
+
+/* Host helpers (glibc arithmetic, no device work) for callers that do not link the reference:
+ * range filter + HitPoint + bounding box of one scan; GridMap::Resize / Expand geometry. */
+typedef struct lgs_geometry {
+    int nx, ny;                 /* cells (multiples of patch) */
+    double min_x, min_y, res;
+    int patch;                  /* cells per patch side       */
+} lgs_geometry;
+int lgs_scan_hit_points(const double* sensor_pose, int n, const double* angles,
+                        const double* ranges, double range_min, double range_max,
+                        double* hit_xy, int* n_hit, double* bbox);
+int lgs_geometry_resize(const lgs_geometry* cur, double min_x, double min_y, double max_x,
+                        double max_y, lgs_geometry* out, int* shift_x, int* shift_y);
+int lgs_geometry_expand(const lgs_geometry* cur, double min_x, double min_y, double max_x,
+                        double max_y, double enlarge_step, lgs_geometry* out, int* shift_x,
+                        int* shift_y, int* changed);
+
 /* ---- sliding-window-max precompute ---------------------------------------------------------
  * out(x,y) = max grid[xs..xs+w) x [ys..ys+w), xs = min(x, max(nx-w, 0)) (the reference repeats
  * the last full window at the upper edges).  `out` must have the geometry of `in`. */

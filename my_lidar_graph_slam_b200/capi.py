@@ -394,3 +394,89 @@ class BbBatch:
 
 def set_edge_eps(eps: float):
     lib().lgs_set_edge_eps(float(eps))
+
+
+# ---- occupancy-grid integration + host geometry helpers ------------------------------------------
+class HitBatch(C.Structure):
+    _fields_ = [("n_scans", C.c_int), ("sensor_xy", c_dp), ("hit_begin", c_ip), ("hit_xy", c_dp)]
+
+
+class Geometry(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("min_x", C.c_double), ("min_y", C.c_double),
+                ("res", C.c_double), ("patch", C.c_int)]
+
+    def as_tuple(self):
+        return (self.nx, self.ny, self.min_x, self.min_y, self.res)
+
+
+SIGNATURES.update({
+    "lgs_grid_resize": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "lgs_grid_clear": (C.c_int, [vp]),
+    "lgs_grid_integrate_scans": (C.c_int, [vp, vp, C.POINTER(HitBatch), C.c_double, C.c_double,
+                                           C.POINTER(C.c_longlong)]),
+    "lgs_scan_hit_points": (C.c_int, [c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double, c_dp,
+                                      c_ip, c_dp]),
+    "lgs_geometry_resize": (C.c_int, [C.POINTER(Geometry)] + [C.c_double] * 4 +
+                            [C.POINTER(Geometry), c_ip, c_ip]),
+    "lgs_geometry_expand": (C.c_int, [C.POINTER(Geometry)] + [C.c_double] * 5 +
+                            [C.POINTER(Geometry), c_ip, c_ip, c_ip]),
+})
+
+
+def scan_hit_points(sensor_pose, angles, ranges, range_min, range_max):
+    """Range filter + HitPoint + bbox with the host's glibc arithmetic -> (hit_xy, bbox)."""
+    a = np.ascontiguousarray(angles, dtype=np.float64)
+    r = np.ascontiguousarray(ranges, dtype=np.float64)
+    sp = np.ascontiguousarray(sensor_pose, dtype=np.float64)
+    out = np.empty((len(a), 2), dtype=np.float64)
+    n = C.c_int()
+    bbox = np.empty(4, dtype=np.float64)
+    rc = lib().lgs_scan_hit_points(_dptr(sp), len(a), _dptr(a), _dptr(r), range_min, range_max,
+                                   _dptr(out), C.byref(n), _dptr(bbox))
+    if rc != 0:
+        raise LgsError(ERRORS.get(rc, rc))
+    return out[:n.value].copy(), bbox
+
+
+def geometry_expand(geo: Geometry, bbox, enlarge_step=5.0):
+    out = Geometry()
+    sx, sy, ch = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().lgs_geometry_expand(C.byref(geo), bbox[0], bbox[1], bbox[2], bbox[3], enlarge_step,
+                                   C.byref(out), C.byref(sx), C.byref(sy), C.byref(ch))
+    if rc != 0:
+        raise LgsError(ERRORS.get(rc, rc))
+    return out, sx.value, sy.value, bool(ch.value)
+
+
+def geometry_resize(geo: Geometry, bbox):
+    out = Geometry()
+    sx, sy = C.c_int(), C.c_int()
+    rc = lib().lgs_geometry_resize(C.byref(geo), bbox[0], bbox[1], bbox[2], bbox[3], C.byref(out),
+                                   C.byref(sx), C.byref(sy))
+    if rc != 0:
+        raise LgsError(ERRORS.get(rc, rc))
+    return out, sx.value, sy.value
+
+
+def grid_resize(grid: Grid, geo: Geometry, shift_x: int, shift_y: int):
+    grid.ctx.check(lib().lgs_grid_resize(grid.h, geo.nx, geo.ny, geo.min_x, geo.min_y, shift_x, shift_y))
+    grid.nx, grid.ny, grid.min_x, grid.min_y = geo.nx, geo.ny, geo.min_x, geo.min_y
+
+
+def grid_clear(grid: Grid):
+    grid.ctx.check(lib().lgs_grid_clear(grid.h))
+
+
+def integrate_scans(ctx: Context, grid: Grid, sensor_xy, hits_list, p_hit=0.6, p_miss=0.45) -> int:
+    """lgs_grid_integrate_scans for scans given as (sensor_xy[k][2], [hit_xy arrays]) -> updates."""
+    n = len(hits_list)
+    begin = np.zeros(n + 1, dtype=np.int32)
+    begin[1:] = np.cumsum([len(h) for h in hits_list])
+    hit = np.ascontiguousarray(np.concatenate(hits_list) if n and begin[-1] else np.zeros((0, 2)),
+                               dtype=np.float64)
+    sxy = np.asarray(sensor_xy, dtype=np.float64)
+    sxy = np.ascontiguousarray(sxy.reshape(n, -1)[:, :2]) if n else np.zeros((0, 2))
+    hb = HitBatch(n, _dptr(sxy), begin.ctypes.data_as(c_ip), _dptr(hit))
+    cnt = C.c_longlong()
+    ctx.check(lib().lgs_grid_integrate_scans(ctx.h, grid.h, C.byref(hb), p_hit, p_miss, C.byref(cnt)))
+    return cnt.value

@@ -1,0 +1,431 @@
+// lgs_integrate.cu -- occupancy-grid scan integration on sm_100a.
+//
+// Replaces the integration loops of GridMapBuilder::UpdateGridMap / ConstructMapFromScans
+// (mapping/grid_map_builder.cpp:170-186, :311-328): for every beam that passed the range
+// filter, the cells on Bresenham(sensorCell -> hitCell) (util.hpp:257-303) except the last get
+// Update(pMiss), the last gets Update(pHit) (BinaryBayesGridCell::Update,
+// grid_map/binary_bayes_grid_cell.hpp:75-119).
+//
+// The cell update is order dependent at the bit level: each cell must see its
+// touches in (scan, beam) order.  Instead of scattering updates (atomics cannot be ordered),
+// every grid cell is OWNED by one thread, which walks the scans of the batch in order and, for
+// each scan, the beams that can touch the cell in beam order, deciding membership in O(1) from
+// the closed form of the reference's Bresenham:
+//     x-major (|dx| > |dy|):  y_k = y0 + sy * floor((2|dy|k + |dx|) / (2|dx|)),  k = 0..|dx|
+//     y-major (otherwise)  :  x_k = x0 + sx * floor((2|dx|k + |dy|) / (2|dy|)),  k = 0..|dy|
+// (cells k < length are misses, k = length is the hit).  That is conflict free by
+// construction and applies exactly the CPU's IEEE sequence (div/mul/add intrinsics, no FMA).
+//
+// Finding the candidate beams of a cell:
+//  * far field (Chebyshev distance to the sensor cell > kNear): beams are angularly sorted, so
+//    the candidates are a binary-searched window of +-(2.5 / d + 0.002) rad around the cell's
+//    direction -- a proven superset (cell centres on a Bresenham line lie within 0.5 cell of
+//    the centre-to-centre segment, whose end points are within 0.71 cell of the true ray);
+//  * near field (<= kNear cells): nearly every beam passes, so one warp per (scan, near cell)
+//    tests all beams with ballots once and stores the ordered touch sequence run-length
+//    encoded (M^a H^b M^c ...); the owning thread then just applies the runs, stopping a run
+//    early once the value reaches its fixed point.
+// Scans whose beams are not angularly monotone fall back to testing every beam (still exact).
+#include <cmath>
+
+#include "lgs_internal.cuh"
+
+namespace {
+
+constexpr int kNear = 16;                      // near-field half width (cells)
+constexpr int kNearW = 2 * kNear + 1;
+constexpr int kRuns = 15;                      // RLE runs kept per (scan, near cell)
+constexpr unsigned short kRleOverflow = 0xFFFF;
+constexpr float kTwoPi = 6.28318530717958647692f;
+
+struct ScanMeta {
+    int sx, sy;          // sensor cell
+    int beamBegin, n;    // beams of this scan
+    int maxLen;          // max Chebyshev ray length in cells
+    int unsorted;        // beams not angularly monotone -> test all beams
+    float ang0;          // world angle of beam 0
+    int bad;             // a touched cell lies outside the grid
+};
+
+struct GridRef {
+    double* origin;
+    int nx, ny, pitch;
+    double minX, minY, res;
+};
+
+__device__ __forceinline__ double clampProb(double v) {
+    // std::clamp(v, ProbabilityMin, ProbabilityMax)  (binary_bayes_grid_cell.hpp:50-52, :97-101)
+    const double lo = 1e-3, hi = 1.0 - 1e-3;
+    return v < lo ? lo : (hi < v ? hi : v);
+}
+
+// BinaryBayesGridCell<double>::Update (binary_bayes_grid_cell.hpp:75-92); oddsP = ValueToOdds(p).
+__device__ __forceinline__ double bayesUpdate(double v, double p, double oddsP) {
+    if (v == 0.0) return clampProb(p);
+    const double cv = clampProb(v);
+    const double oldOdds = __ddiv_rn(cv, __dsub_rn(1.0, cv));           // ValueToOdds
+    const double o = __dmul_rn(oldOdds, oddsP);
+    const double nv = clampProb(__ddiv_rn(o, __dadd_rn(1.0, o)));       // OddsToValue
+    return clampProb(nv);
+}
+
+// 0 = not on the ray, 1 = miss cell, 2 = hit cell.  (rx, ry) = cell - sensorCell, (ex, ey) = hitCell - sensorCell.
+__device__ __forceinline__ int rayTouch(int rx, int ry, int ex, int ey) {
+    const int ax = abs(ex), ay = abs(ey);
+    if (ax > ay) {                                   // util.hpp:276-287
+        const int k = ex < 0 ? -rx : rx;
+        if (k < 0 || k > ax) return 0;
+        const int yk = (2 * ay * k + ax) / (2 * ax);
+        if (ry != (ey < 0 ? -yk : yk)) return 0;
+        return k == ax ? 2 : 1;
+    }
+    const int k = ey < 0 ? -ry : ry;                 // util.hpp:288-299 (also dx == dy == 0)
+    if (k < 0 || k > ay) return 0;
+    const int xk = ay == 0 ? 0 : (2 * ax * k + ay) / (2 * ay);
+    if (rx != (ex < 0 ? -xk : xk)) return 0;
+    return k == ay ? 2 : 1;
+}
+
+__device__ __forceinline__ float wrapBeta(float a) {   // into [-0.01, 2*pi - 0.01)
+    a = fmodf(a, kTwoPi);
+    if (a < -0.01f) a += kTwoPi;
+    if (a >= kTwoPi - 0.01f) a -= kTwoPi;
+    return a;
+}
+
+// ---- pre-pass A: sensor cells ---------------------------------------------------------------------
+__global__ void integ_sensor_kernel(const double* __restrict__ sensorXY, const int* __restrict__ hitBegin,
+                                    const double* __restrict__ hitXY, int nScans, GridRef g,
+                                    ScanMeta* __restrict__ meta) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nScans) return;
+    ScanMeta m;
+    // WorldCoordinateToGridCellIndex (grid_map.hpp:779-790)
+    m.sx = __double2int_rd(__ddiv_rn(__dsub_rn(sensorXY[2 * s], g.minX), g.res));
+    m.sy = __double2int_rd(__ddiv_rn(__dsub_rn(sensorXY[2 * s + 1], g.minY), g.res));
+    m.beamBegin = hitBegin[s];
+    m.n = hitBegin[s + 1] - hitBegin[s];
+    m.maxLen = 0; m.unsorted = 0; m.bad = 0;
+    m.ang0 = 0.f;
+    if (m.n > 0)
+        m.ang0 = atan2f((float)(hitXY[2 * (size_t)m.beamBegin + 1] - sensorXY[2 * s + 1]),
+                        (float)(hitXY[2 * (size_t)m.beamBegin] - sensorXY[2 * s]));
+    if (m.sx < 0 || m.sx >= g.nx || m.sy < 0 || m.sy >= g.ny) m.bad = 1;
+    meta[s] = m;
+}
+
+// ---- pre-pass B: per beam end cell (relative), angle ------------------------------------------------
+__global__ void integ_beam_kernel(const double* __restrict__ sensorXY, const double* __restrict__ hitXY,
+                                  int nScans, GridRef g, ScanMeta* __restrict__ meta,
+                                  int2* __restrict__ rel, float* __restrict__ beta) {
+    const int s = blockIdx.y;
+    const ScanMeta m = meta[s];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.n) return;
+    const size_t b = (size_t)m.beamBegin + i;
+    const double hx = hitXY[2 * b], hy = hitXY[2 * b + 1];
+    const int ex = __double2int_rd(__ddiv_rn(__dsub_rn(hx, g.minX), g.res));
+    const int ey = __double2int_rd(__ddiv_rn(__dsub_rn(hy, g.minY), g.res));
+    if (ex < 0 || ex >= g.nx || ey < 0 || ey >= g.ny) atomicOr(&meta[s].bad, 1);
+    const int dx = ex - m.sx, dy = ey - m.sy;
+    rel[b] = make_int2(dx, dy);
+    atomicMax(&meta[s].maxLen, max(abs(dx), abs(dy)));
+    const float a = atan2f((float)(hy - sensorXY[2 * s + 1]), (float)(hx - sensorXY[2 * s]));
+    beta[b] = i == 0 ? 0.f : wrapBeta(a - m.ang0);
+}
+
+__global__ void integ_sorted_kernel(ScanMeta* __restrict__ meta, const float* __restrict__ beta) {
+    const int s = blockIdx.y;
+    const ScanMeta m = meta[s];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1 || i >= m.n) return;
+    const size_t b = (size_t)m.beamBegin + i;
+    if (beta[b] < beta[b - 1]) atomicOr(&meta[s].unsorted, 1);
+}
+
+// ---- pre-pass C: near-field touch sequences, run-length encoded ---------------------------------------
+// One warp per (scan, near cell).  Entry = (type << 15) | count with type 1 = hit; 0 terminates.
+__global__ void __launch_bounds__(128)
+integ_near_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
+                  unsigned short* __restrict__ table) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nScans * kNearW * kNearW) return;
+    const int s = warp / (kNearW * kNearW);
+    const int c = warp - s * (kNearW * kNearW);
+    const int rx = c % kNearW - kNear, ry = c / kNearW - kNear;
+    const ScanMeta m = meta[s];
+    unsigned short* out = table + (size_t)warp * (kRuns + 1);
+    int nRuns = 0, curType = -1, curCount = 0;
+    bool overflow = false;
+    for (int base = 0; base < m.n; base += 32) {
+        const int i = base + lane;
+        int ty = 0;
+        if (i < m.n) {
+            const int2 e = __ldg(rel + m.beamBegin + i);
+            ty = rayTouch(rx, ry, e.x, e.y);
+        }
+        unsigned touched = __ballot_sync(0xffffffffu, ty != 0);
+        const unsigned hits = __ballot_sync(0xffffffffu, ty == 2);
+        while (touched) {                       // uniform across the warp
+            const int bit = __ffs(touched) - 1;
+            const int type = (hits >> bit) & 1;
+            // length of the run of equal type among the touched bits starting at `bit`
+            const unsigned same = type ? (touched & hits) : (touched & ~hits);
+            const unsigned other = touched & ~same;
+            const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xffffffffu;
+            const unsigned runBits = same & upto;
+            const int cnt = __popc(runBits);
+            if (type == curType) {
+                curCount += cnt;
+            } else {
+                if (curType >= 0) {
+                    if (nRuns < kRuns) { if (lane == 0) out[nRuns] = (unsigned short)((curType << 15) | curCount); }
+                    else overflow = true;
+                    ++nRuns;
+                }
+                curType = type; curCount = cnt;
+            }
+            touched &= ~runBits;
+        }
+    }
+    if (curType >= 0) {
+        if (nRuns < kRuns) { if (lane == 0) out[nRuns] = (unsigned short)((curType << 15) | curCount); }
+        else overflow = true;
+        ++nRuns;
+    }
+    if (lane == 0) {
+        if (overflow || m.n > 32767) out[0] = kRleOverflow;
+        else out[nRuns] = 0;
+    }
+}
+
+// ---- main kernel: one thread owns one cell ---------------------------------------------------------
+__global__ void __launch_bounds__(256)
+integ_apply_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel,
+                   const float* __restrict__ beta, const unsigned short* __restrict__ nearTab,
+                   int nScans, GridRef g, int x0, int y0, int x1, int y1, double pHit, double pMiss,
+                   double oddsHit, double oddsMiss, unsigned long long* __restrict__ nUpdates) {
+    const int cx = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const bool inside = cx < x1 && cy < y1;
+    double v = 0.0;
+    double* cell = nullptr;
+    if (inside) { cell = g.origin + (size_t)cy * g.pitch + cx; v = *cell; }
+    const double v0 = v;
+    unsigned count = 0;
+    if (inside) {
+        for (int s = 0; s < nScans; ++s) {
+            const ScanMeta m = meta[s];
+            const int rx = cx - m.sx, ry = cy - m.sy;
+            const int cheb = max(abs(rx), abs(ry));
+            if (cheb > m.maxLen || m.n == 0) continue;
+            const int2* __restrict__ e = rel + m.beamBegin;
+            bool all = m.unsorted != 0;
+            if (cheb <= kNear) {
+                const unsigned short* t = nearTab + ((size_t)s * kNearW * kNearW + (ry + kNear) * kNearW + (rx + kNear)) * (kRuns + 1);
+                if (t[0] != kRleOverflow) {
+                    for (int k = 0; k < kRuns; ++k) {
+                        const unsigned short ent = t[k];
+                        if (ent == 0) break;
+                        const int cnt = ent & 0x7fff;
+                        const bool hit = (ent >> 15) != 0;
+                        count += cnt;
+                        for (int j = 0; j < cnt; ++j) {
+                            const double nv = hit ? bayesUpdate(v, pHit, oddsHit) : bayesUpdate(v, pMiss, oddsMiss);
+                            if (nv == v) break;        // fixed point: the rest of the run is a no-op
+                            v = nv;
+                        }
+                    }
+                    continue;
+                }
+                all = true;
+            }
+            if (all) {
+                for (int i = 0; i < m.n; ++i) {
+                    const int2 ee = __ldg(e + i);
+                    const int ty = rayTouch(rx, ry, ee.x, ee.y);
+                    if (ty) { v = ty == 2 ? bayesUpdate(v, pHit, oddsHit) : bayesUpdate(v, pMiss, oddsMiss); ++count; }
+                }
+                continue;
+            }
+            // far field: angular window of candidate beams
+            const float* __restrict__ bt = beta + m.beamBegin;
+            const float d = sqrtf((float)(rx * rx + ry * ry));
+            const float delta = 2.5f / d + 2e-3f;
+            const float bc = wrapBeta(atan2f((float)ry, (float)rx) - m.ang0);
+            const float bLast = __ldg(bt + m.n - 1);
+#pragma unroll 1
+            for (int w = -1; w <= 1; ++w) {
+                const float lo = bc + w * kTwoPi - delta, hi = bc + w * kTwoPi + delta;
+                if (hi < -0.01f || lo > bLast) continue;
+                int a = 0, b = m.n;                  // first i with beta[i] >= lo
+                while (a < b) {
+                    const int mid = (a + b) >> 1;
+                    if (__ldg(bt + mid) < lo) a = mid + 1; else b = mid;
+                }
+                for (int i = a; i < m.n && __ldg(bt + i) <= hi; ++i) {
+                    const int2 ee = __ldg(e + i);
+                    const int ty = rayTouch(rx, ry, ee.x, ee.y);
+                    if (ty) { v = ty == 2 ? bayesUpdate(v, pHit, oddsHit) : bayesUpdate(v, pMiss, oddsMiss); ++count; }
+                }
+            }
+        }
+        if (v != v0) *cell = v;
+    }
+    // block-level count of applied updates
+    __shared__ unsigned sCount[8];
+    unsigned c = count;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) sCount[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int k = 0; k < (int)(blockDim.x * blockDim.y + 31) / 32; ++k) tot += sCount[k];
+        if (tot) atomicAdd(nUpdates, tot);
+    }
+}
+
+__global__ void grid_shift_copy_kernel(const double* __restrict__ src, int srcNx, int srcNy, int srcPitch,
+                                       double* __restrict__ dst, int dstNx, int dstNy, int dstPitch,
+                                       int shiftX, int shiftY) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= dstNx || y >= dstNy) return;
+    const int ox = x + shiftX, oy = y + shiftY;
+    double v = 0.0;
+    if (ox >= 0 && ox < srcNx && oy >= 0 && oy < srcNy) v = src[(size_t)oy * srcPitch + ox];
+    dst[(size_t)y * dstPitch + x] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* scans, double pHit,
+                             double pMiss, long long* nUpdatesOut) {
+    if (!c || !grid || !scans) return LGS_ERR_INVALID;
+    if (nUpdatesOut) *nUpdatesOut = 0;
+    const int n = scans->n_scans;
+    if (n < 0 || (n > 0 && (!scans->sensor_xy || !scans->hit_begin)))
+        return lgs_fail(c, LGS_ERR_INVALID, "integrate: bad scan batch");
+    if (n == 0) return LGS_OK;
+    const long long total = scans->hit_begin[n];
+    if (total > 0 && !scans->hit_xy) return lgs_fail(c, LGS_ERR_INVALID, "integrate: hit_xy is NULL");
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    int maxBeams = 0;
+    for (int s = 0; s < n; ++s) maxBeams = std::max(maxBeams, scans->hit_begin[s + 1] - scans->hit_begin[s]);
+
+    // Device staging (freed at the end; integration is called per batch of scans).
+    double *dSensor = nullptr, *dHit = nullptr;
+    int* dBegin = nullptr;
+    ScanMeta* dMeta = nullptr;
+    int2* dRel = nullptr;
+    float* dBeta = nullptr;
+    unsigned short* dNear = nullptr;
+    unsigned long long* dCount = nullptr;
+    const size_t nearEntries = (size_t)n * kNearW * kNearW * (kRuns + 1);
+    auto freeAll = [&]() {
+        cudaFree(dSensor); cudaFree(dHit); cudaFree(dBegin); cudaFree(dMeta); cudaFree(dRel);
+        cudaFree(dBeta); cudaFree(dNear); cudaFree(dCount);
+    };
+#define INTEG_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeAll(); \
+        return lgs_fail(c, LGS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } } while (0)
+    INTEG_CUDA(cudaMalloc(&dSensor, (size_t)n * 2 * sizeof(double)));
+    INTEG_CUDA(cudaMalloc(&dHit, std::max<size_t>((size_t)total, 1) * 2 * sizeof(double)));
+    INTEG_CUDA(cudaMalloc(&dBegin, (size_t)(n + 1) * sizeof(int)));
+    INTEG_CUDA(cudaMalloc(&dMeta, (size_t)n * sizeof(ScanMeta)));
+    INTEG_CUDA(cudaMalloc(&dRel, std::max<size_t>((size_t)total, 1) * sizeof(int2)));
+    INTEG_CUDA(cudaMalloc(&dBeta, std::max<size_t>((size_t)total, 1) * sizeof(float)));
+    INTEG_CUDA(cudaMalloc(&dNear, nearEntries * sizeof(unsigned short)));
+    INTEG_CUDA(cudaMalloc(&dCount, sizeof(unsigned long long)));
+    INTEG_CUDA(cudaMemcpyAsync(dSensor, scans->sensor_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (total)
+        INTEG_CUDA(cudaMemcpyAsync(dHit, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    INTEG_CUDA(cudaMemcpyAsync(dBegin, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    INTEG_CUDA(cudaMemsetAsync(dCount, 0, sizeof(unsigned long long), c->stream));
+
+    GridRef g{grid->origin(), grid->nx, grid->ny, grid->pitch, grid->min_x, grid->min_y, grid->res};
+    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(dSensor, dBegin, dHit, n, g, dMeta);
+    c->launches++;
+    if (maxBeams > 0) {
+        dim3 gb((maxBeams + 127) / 128, n);
+        integ_beam_kernel<<<gb, 128, 0, c->stream>>>(dSensor, dHit, n, g, dMeta, dRel, dBeta);
+        integ_sorted_kernel<<<gb, 128, 0, c->stream>>>(dMeta, dBeta);
+        const long long warps = (long long)n * kNearW * kNearW;
+        integ_near_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(dMeta, dRel, n, dNear);
+        c->launches += 3;
+    }
+    INTEG_CUDA(cudaGetLastError());
+    // The apply kernel's extent needs the scans' reach: read the metadata back (small).
+    std::vector<ScanMeta> meta(n);
+    INTEG_CUDA(cudaMemcpyAsync(meta.data(), dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, c->stream));
+    INTEG_CUDA(cudaStreamSynchronize(c->stream));
+    int x0 = grid->nx, y0 = grid->ny, x1 = 0, y1 = 0;
+    for (int s = 0; s < n; ++s) {
+        if (meta[s].bad) {
+            freeAll();
+            return lgs_fail(c, LGS_ERR_INVALID, "integrate: scan %d touches cells outside the %dx%d grid "
+                            "(expand the map first, as GridMap::Expand does)", s, grid->nx, grid->ny);
+        }
+        if (meta[s].n == 0) continue;
+        x0 = std::min(x0, meta[s].sx - meta[s].maxLen); x1 = std::max(x1, meta[s].sx + meta[s].maxLen + 1);
+        y0 = std::min(y0, meta[s].sy - meta[s].maxLen); y1 = std::max(y1, meta[s].sy + meta[s].maxLen + 1);
+    }
+    x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, grid->nx); y1 = std::min(y1, grid->ny);
+    if (x1 > x0 && y1 > y0) {
+        // ValueToOdds(prob) for the two observations (binary_bayes_grid_cell.hpp:104-113), host IEEE.
+        auto clampP = [](double v) { const double lo = 1e-3, hi = 1.0 - 1e-3; return v < lo ? lo : (hi < v ? hi : v); };
+        const double oddsHit = clampP(pHit) / (1.0 - clampP(pHit));
+        const double oddsMiss = clampP(pMiss) / (1.0 - clampP(pMiss));
+        dim3 block(32, 8), gridDim((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
+        integ_apply_kernel<<<gridDim, block, 0, c->stream>>>(dMeta, dRel, dBeta, dNear, n, g, x0, y0, x1, y1,
+                                                             pHit, pMiss, oddsHit, oddsMiss, dCount);
+        c->launches++;
+        INTEG_CUDA(cudaGetLastError());
+    }
+    unsigned long long cnt = 0;
+    INTEG_CUDA(cudaMemcpyAsync(&cnt, dCount, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    INTEG_CUDA(cudaStreamSynchronize(c->stream));
+    if (nUpdatesOut) *nUpdatesOut = (long long)cnt;
+    freeAll();
+#undef INTEG_CUDA
+    return LGS_OK;
+}
+
+int lgs_grid_resize(lgs_grid* g, int nx, int ny, double minX, double minY, int shiftX, int shiftY) {
+    if (!g) return LGS_ERR_INVALID;
+    lgs_ctx* c = g->ctx;
+    if (nx < 0 || ny < 0) return lgs_fail(c, LGS_ERR_INVALID, "grid_resize: %dx%d", nx, ny);
+    const long long pitch = (long long)nx + 2LL * g->apron, rows = (long long)ny + 2LL * g->apron;
+    if (pitch * rows >= (1LL << 31)) return lgs_fail(c, LGS_ERR_INVALID, "grid_resize: too many cells");
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    double* nd = nullptr;
+    const size_t bytes = (size_t)pitch * rows * sizeof(double);
+    cudaError_t e = cudaMalloc(&nd, bytes);
+    if (e != cudaSuccess) return lgs_fail(c, LGS_ERR_NOMEM, "grid_resize: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    LGS_CUDA(c, cudaMemsetAsync(nd, 0, bytes, c->stream));
+    if (nx > 0 && ny > 0) {
+        dim3 gridDim((nx + 255) / 256, ny);
+        grid_shift_copy_kernel<<<gridDim, 256, 0, c->stream>>>(g->origin(), g->nx, g->ny, g->pitch,
+                                                               nd + (size_t)g->apron * pitch + g->apron,
+                                                               nx, ny, (int)pitch, shiftX, shiftY);
+        LGS_LAUNCH_CHECK(c);
+    }
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(g->d);
+    g->d = nd; g->nx = nx; g->ny = ny; g->pitch = (int)pitch; g->rows = (int)rows;
+    g->min_x = minX; g->min_y = minY;
+    return LGS_OK;
+}
+
+int lgs_grid_clear(lgs_grid* g) {
+    if (!g) return LGS_ERR_INVALID;
+    lgs_ctx* c = g->ctx;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaMemsetAsync(g->d, 0, (size_t)g->pitch * g->rows * sizeof(double), c->stream));
+    return LGS_OK;
+}
+
+}  // extern "C"

@@ -399,6 +399,60 @@ void ref_host_tail(const RefMap* map, const double* cost, const double* bestSens
         for (int j = 0; j < 3; ++j) cov[3 * i + j] = c(i, j);
 }
 
+// Range filter + HitPoint + bounding box exactly as GridMapBuilder does it
+// (ComputeBoundingBoxAndScanPoints, grid_map_builder.cpp:335-380).  usable = {min, max}.
+int ref_hit_points(const double* robotPose, const double* rel, int n, const double* angles,
+                   const double* ranges, double scanMinRange, double scanMaxRange,
+                   double usableMin, double usableMax, double* sensorPose, double* hitXY,
+                   double* bbox) {
+    GridMapBuilder b(0.05, 64, 10, 20.0, usableMin, usableMax, 0.6, 0.45);
+    const auto scan = MakeScan(robotPose, rel, n, angles, ranges, scanMinRange, scanMaxRange);
+    const RobotPose2D<double> rp(robotPose[0], robotPose[1], robotPose[2]);
+    Point2D<double> bl, tr;
+    std::vector<Point2D<double>> hits;
+    b.ComputeBoundingBoxAndScanPoints(rp, scan, bl, tr, hits);
+    const auto sp = Compound(rp, scan->RelativeSensorPose());
+    sensorPose[0] = sp.mX; sensorPose[1] = sp.mY; sensorPose[2] = sp.mTheta;
+    for (size_t i = 0; i < hits.size(); ++i) { hitXY[2 * i] = hits[i].mX; hitXY[2 * i + 1] = hits[i].mY; }
+    bbox[0] = bl.mX; bbox[1] = bl.mY; bbox[2] = tr.mX; bbox[3] = tr.mY;
+    return static_cast<int>(hits.size());
+}
+
+// The per-scan integration loop of UpdateGridMap (grid_map_builder.cpp:159-186) applied to an
+// existing map with caller-supplied sensor position and hit points (every touched cell must be
+// inside the map): WorldCoordinateToGridCellIndex, ComputeMissedGridCellIndices (Bresenham
+// minus the last cell), Update(miss)..., Update(hit) -- all the reference's own functions.
+int ref_map_integrate_hits(RefMap* h, const double* sensorXY, int n, const double* hitXY,
+                           double pHit, double pMiss) {
+    GridMapBuilder b(h->m.Resolution(), h->m.PatchSize(), 10, 20.0, 0.01, 20.0, pHit, pMiss);
+    const Point2D<int> s = h->m.WorldCoordinateToGridCellIndex(sensorXY[0], sensorXY[1]);
+    int updates = 0;
+    for (int i = 0; i < n; ++i) {
+        const Point2D<int> e = h->m.WorldCoordinateToGridCellIndex(hitXY[2 * i], hitXY[2 * i + 1]);
+        const std::vector<Point2D<int>> missed = b.ComputeMissedGridCellIndices(s, e);
+        for (const auto& c : missed) {
+            if (!h->m.IsInside(c)) return -1;
+            h->m.Update(c, pMiss);
+        }
+        if (!h->m.IsInside(e)) return -1;
+        h->m.Update(e, pHit);
+        updates += static_cast<int>(missed.size()) + 1;
+    }
+    return updates;
+}
+
+// GridMap::Resize / Expand / Reset on an oracle map (grid_map.hpp:652-736, :740-752).
+void ref_map_resize(RefMap* h, double minX, double minY, double maxX, double maxY) {
+    h->m.Resize(minX, minY, maxX, maxY);
+}
+void ref_map_expand(RefMap* h, double minX, double minY, double maxX, double maxY, double step) {
+    h->m.Expand(minX, minY, maxX, maxY, step);
+}
+void ref_map_reset(RefMap* h) { h->m.Reset(); }
+RefMap* ref_map_create_empty(double res, int patch, double centerX, double centerY) {
+    return new RefMap{GridMapType(res, patch, 0, 0, Point2D<double>(centerX, centerY))};
+}
+
 const char* ref_version(void) { return "my-lidar-graph-slam reference objects (unmodified)"; }
 
 }  // extern "C"

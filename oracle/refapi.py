@@ -340,3 +340,62 @@ def host_tail(m: RefMap, best_sensor_pose, angles, ranges, *, rel=(0.0, 0.0, 0.0
     lib().ref_host_tail(m.h, (C.c_double * 7)(*cost), _arr3(best_sensor_pose), _arr3(rel),
                         len(a), ap, rp, scan_min_range, scan_max_range, C.byref(nc), est, cov)
     return nc.value, tuple(est), np.array(cov).reshape(3, 3)
+
+
+# ---- integration helpers ---------------------------------------------------------------------
+def _bind_integration():
+    L = lib()
+    if getattr(L, "_integ_bound", False):
+        return L
+    vp = C.c_void_p
+    L.ref_hit_points.restype = C.c_int
+    L.ref_hit_points.argtypes = [c_dp, c_dp, C.c_int, c_dp, c_dp] + [C.c_double] * 4 + [c_dp] * 3
+    L.ref_map_integrate_hits.restype = C.c_int
+    L.ref_map_integrate_hits.argtypes = [vp, c_dp, C.c_int, c_dp, C.c_double, C.c_double]
+    L.ref_map_resize.argtypes = [vp] + [C.c_double] * 4
+    L.ref_map_expand.argtypes = [vp] + [C.c_double] * 5
+    L.ref_map_reset.argtypes = [vp]
+    L.ref_map_create_empty.restype = vp
+    L.ref_map_create_empty.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double]
+    L._integ_bound = True
+    return L
+
+
+def hit_points(robot_pose, angles, ranges, *, rel=(0.0, 0.0, 0.0), scan_min_range=0.02,
+               scan_max_range=30.0, usable_min=0.01, usable_max=20.0):
+    """-> (sensor_pose[3], hit_xy[k][2], bbox[4]) via ComputeBoundingBoxAndScanPoints."""
+    L = _bind_integration()
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    sp = (C.c_double * 3)()
+    bbox = (C.c_double * 4)()
+    out = np.empty((len(a), 2), dtype=np.float64)
+    k = L.ref_hit_points(_arr3(robot_pose), _arr3(rel), len(a), ap, rp, scan_min_range,
+                         scan_max_range, usable_min, usable_max, sp, out.ctypes.data_as(c_dp), bbox)
+    return np.array(sp), out[:k].copy(), np.array(bbox)
+
+
+def empty_map(center_x, center_y, res=0.05, patch=64) -> RefMap:
+    return RefMap(_bind_integration().ref_map_create_empty(res, patch, center_x, center_y))
+
+
+def map_integrate_hits(m: RefMap, sensor_xy, hit_xy, p_hit=0.6, p_miss=0.45) -> int:
+    L = _bind_integration()
+    s, sp = _d(np.asarray(sensor_xy, dtype=np.float64)[:2])
+    h, hp = _d(hit_xy)
+    n = L.ref_map_integrate_hits(m.h, sp, len(h), hp, p_hit, p_miss)
+    if n < 0:
+        raise RuntimeError("a touched cell lies outside the oracle map")
+    return n
+
+
+def map_resize(m: RefMap, min_x, min_y, max_x, max_y):
+    _bind_integration().ref_map_resize(m.h, min_x, min_y, max_x, max_y)
+
+
+def map_expand(m: RefMap, min_x, min_y, max_x, max_y, step=5.0):
+    _bind_integration().ref_map_expand(m.h, min_x, min_y, max_x, max_y, step)
+
+
+def map_reset(m: RefMap):
+    _bind_integration().ref_map_reset(m.h)

@@ -1,0 +1,110 @@
+"""GPU parity: occupancy-grid scan integration vs the reference's GridMapBuilder (every cell bit-exact)."""
+import numpy as np
+import pytest
+
+from my_lidar_graph_slam_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.int64)
+
+
+def _scene(seed=3, n=40, beams=1081, fov=270.0):
+    world = synth.RoomsWorld(40.0, 5.0, seed=seed)
+    angles = synth.beam_angles(beams, fov)
+    traj = synth.trajectory(world, n, step=0.25, seed=seed)
+    noise = np.random.default_rng(seed + 1)
+    scans = [synth.make_scan(world, p, angles, noise) for p in traj]
+    return angles, traj, scans
+
+
+def test_incremental_local_map_matches_builder(ctx):
+    """UpdateGridMap path: grow (Expand, 5 m slack) + integrate one scan at a time, 40 scans."""
+    from oracle import refapi as R
+    angles, traj, scans = _scene()
+    builder = R.RefBuilder()
+    geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
+    grid = capi.Grid(ctx, 0, 0, geo.min_x, geo.min_y, 0.05, apron=2)
+    updates = 0
+    for k, (p, r) in enumerate(zip(traj, scans)):
+        builder.append_scan(p, angles, r)
+        hits, bbox = capi.scan_hit_points(p, angles, r, 0.02, 20.0)   # zero relative sensor pose
+        geo, sx, sy, changed = capi.geometry_expand(geo, bbox)
+        if changed:
+            capi.grid_resize(grid, geo, sx, sy)
+        updates += capi.integrate_scans(ctx, grid, [p], [hits])
+        if k in (0, 7, 39):
+            ref = builder.local_map(0)
+            assert geo.as_tuple() == ref.geometry()
+            assert np.array_equal(_bits(grid.download()), _bits(ref.dense())), f"after scan {k}"
+    assert updates > 40 * 50_000
+
+
+def test_batched_construct_map_matches_latest_map(ctx):
+    """ConstructMapFromScans path: tight Resize + Reset + all scans of the window in ONE batch."""
+    from oracle import refapi as R
+    angles, traj, scans = _scene(seed=5, n=14)
+    builder = R.RefBuilder(n_latest=10)
+    for p, r in zip(traj, scans):
+        builder.append_scan(p, angles, r)
+    ref = builder.latest_map()                     # scans 4..13
+    # replay the latest map's geometry history like UpdateLatestMap does every frame
+    geo = capi.Geometry(0, 0, 0.0, 0.0, 0.05, 64)
+    for last in range(len(traj)):
+        lo = max(0, last - 9)
+        hp = [capi.scan_hit_points(traj[k], angles, scans[k], 0.02, 20.0) for k in range(lo, last + 1)]
+        bl = np.min([[b[0], b[1]] for _, b in hp], axis=0)
+        # grid_map_builder.cpp:236-237 seeds the top-right bound with numeric_limits<double>::min()
+        tr = np.maximum(np.max([[b[2], b[3]] for _, b in hp], axis=0), np.finfo(np.float64).tiny)
+        geo, _, _ = capi.geometry_resize(geo, (bl[0], bl[1], tr[0], tr[1]))
+    assert geo.as_tuple() == ref.geometry()
+    grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=2)
+    capi.integrate_scans(ctx, grid, traj[4:14], [h for h, _ in hp])
+    assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
+    # a second pass over the same scans (e.g. AfterLoopClosure re-integration into a Reset map)
+    capi.grid_clear(grid)
+    capi.integrate_scans(ctx, grid, traj[4:9], [h for h, _ in hp[:5]])
+    capi.integrate_scans(ctx, grid, traj[9:14], [h for h, _ in hp[5:]])
+    assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
+
+
+@pytest.mark.parametrize("case", ["unsorted", "full_circle", "short_rays", "dense_hits"])
+def test_adversarial_scans_match_reference_loop(ctx, case):
+    """Synthetic hit sets that stress the candidate search: non-monotone beams (fallback path),
+    a 360-degree scan (angle wrap), rays shorter than a cell, and many hits in few cells (long
+    mixed miss/hit sequences in the near field -> RLE overflow fallback)."""
+    from oracle import refapi as R
+    rng = np.random.default_rng({"unsorted": 1, "full_circle": 2, "short_rays": 3, "dense_hits": 4}[case])
+    ref = R.RefMap.from_dense(np.zeros((256, 256)), -6.4, -6.4)
+    grid = capi.Grid(ctx, 256, 256, -6.4, -6.4, 0.05, apron=1)
+    for s in range(6):
+        sensor = rng.uniform(-1.5, 1.5, 2)
+        n = 700
+        if case == "unsorted":
+            ang = rng.uniform(-np.pi, np.pi, n)
+            rad = rng.uniform(0.05, 4.0, n)
+        elif case == "full_circle":
+            ang = np.linspace(-np.pi, np.pi, n, endpoint=False) + rng.uniform(-3, 3)
+            rad = rng.uniform(0.5, 4.5, n)
+        elif case == "short_rays":
+            ang = np.linspace(-2.0, 2.0, n)
+            rad = np.where(rng.random(n) < 0.5, rng.uniform(0.001, 0.12, n), rng.uniform(0.2, 3.0, n))
+        else:
+            ang = np.linspace(-1.0, 1.0, n)
+            rad = np.where(np.arange(n) % 3 == 0, rng.uniform(0.3, 0.5, n), rng.uniform(0.9, 1.1, n))
+        hits = np.ascontiguousarray(sensor[None, :] + rad[:, None] * np.stack([np.cos(ang), np.sin(ang)], 1))
+        want = R.map_integrate_hits(ref, sensor, hits)
+        got = capi.integrate_scans(ctx, grid, [sensor], [hits])
+        assert got == want
+        assert np.array_equal(_bits(grid.download()), _bits(ref.dense())), f"{case}: scan {s}"
+
+
+def test_integrate_rejects_cells_outside_grid_and_handles_empty(ctx):
+    grid = capi.Grid(ctx, 64, 64, 0.0, 0.0, 0.05, apron=1)
+    assert capi.integrate_scans(ctx, grid, np.zeros((0, 2)), []) == 0
+    assert capi.integrate_scans(ctx, grid, [[1.0, 1.0]], [np.zeros((0, 2))]) == 0
+    with pytest.raises(capi.LgsError, match="outside"):
+        capi.integrate_scans(ctx, grid, [[1.0, 1.0]], [np.array([[5.0, 1.0]])])
+    assert not grid.download().any()
