@@ -6,7 +6,9 @@ import functools
 import numpy as np
 
 from my_lidar_graph_slam_b200 import synth
-from oracle import refapi as R
+from oracle import backend
+
+R = backend()
 
 
 @functools.lru_cache(maxsize=8)

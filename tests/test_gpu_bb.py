@@ -21,7 +21,8 @@ def _ref_kwargs(p):
 @pytest.fixture(scope="module")
 def submap(ctx):
     """A reference-built local map (40 scans) + reference and device pyramids."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     world = synth.RoomsWorld(40.0, 5.0, seed=3)
     angles = synth.beam_angles(1081, 270.0)
     traj = synth.trajectory(world, 60, step=0.25, seed=3)
@@ -54,7 +55,8 @@ def _same(out, ref):
 
 
 def test_bb_batch_matches_reference(ctx, submap):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     qs = _queries(submap, 8)
     batch = capi.BbBatch(ctx, **DEF)
     scans = capi.Scans([submap["angles"]] * len(qs), [s for s, _ in qs], [p for _, p in qs],
@@ -90,7 +92,8 @@ def test_bb_batch_matches_reference(ctx, submap):
     (dict(DEF, node_height_max=2, range_x=0.4, range_y=0.4, range_theta=0.05), None),  # DBL_MIN: full tree
 ])
 def test_bb_parameter_sweep(ctx, submap, params, thr):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     H = params["node_height_max"]
     pyr = capi.Pyramid(ctx, submap["grid"], H)
     refpyr = submap["refmap"].pyramid(H)
@@ -108,7 +111,8 @@ def test_bb_parameter_sweep(ctx, submap, params, thr):
 
 def test_bb_near_edge_fixups_do_not_change_results(ctx, submap):
     """Widen the edge guard band so ~5 % of the projected points take the host-exact path."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     qs = _queries(submap, 2, seed=21)
     capi.set_edge_eps(0.025)
     try:
@@ -129,7 +133,8 @@ def test_bb_near_edge_fixups_do_not_change_results(ctx, submap):
 def test_bb_low_edge_overhang_uses_replay(ctx):
     """H12: window indices straddling zero make the win-max values non-bounds; the result must
     still be the reference's (order-dependent) answer."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     rng = np.random.default_rng(17)
     ny, nx = 128, 192
     dense = np.where(rng.random((ny, nx)) < 0.25, rng.uniform(0.05, 0.95, (ny, nx)), 0.0)

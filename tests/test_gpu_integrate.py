@@ -22,7 +22,8 @@ def _scene(seed=3, n=40, beams=1081, fov=270.0):
 
 def test_incremental_local_map_matches_builder(ctx):
     """UpdateGridMap path: grow (Expand, 5 m slack) + integrate one scan at a time, 40 scans."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     angles, traj, scans = _scene()
     builder = R.RefBuilder()
     geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
@@ -44,7 +45,8 @@ def test_incremental_local_map_matches_builder(ctx):
 
 def test_batched_construct_map_matches_latest_map(ctx):
     """ConstructMapFromScans path: tight Resize + Reset + all scans of the window in ONE batch."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     angles, traj, scans = _scene(seed=5, n=14)
     builder = R.RefBuilder(n_latest=10)
     for p, r in zip(traj, scans):
@@ -75,7 +77,8 @@ def test_adversarial_scans_match_reference_loop(ctx, case):
     """Synthetic hit sets that stress the candidate search: non-monotone beams (fallback path),
     a 360-degree scan (angle wrap), rays shorter than a cell, and many hits in few cells (long
     mixed miss/hit sequences in the near field -> RLE overflow fallback)."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     rng = np.random.default_rng({"unsorted": 1, "full_circle": 2, "short_rays": 3, "dense_hits": 4}[case])
     ref = R.RefMap.from_dense(np.zeros((256, 256)), -6.4, -6.4)
     grid = capi.Grid(ctx, 256, 256, -6.4, -6.4, 0.05, apron=1)

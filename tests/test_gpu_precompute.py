@@ -13,7 +13,8 @@ def _bits(a):
 
 @pytest.mark.parametrize("win", [1, 2, 3, 5, 8, 64, 100])
 def test_precompute_matches_reference(ctx, win):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     from scenes import room_scene
     _, _, _, builder = room_scene(seed=1)
     refmap = builder.latest_map()
@@ -27,7 +28,8 @@ def test_precompute_matches_reference(ctx, win):
 @pytest.mark.parametrize("shape", [(64, 64), (64, 192), (128, 64)])
 def test_pyramid_matches_reference_small_maps(ctx, shape):
     """Windows up to 2^7 = 128 exceed one or both map extents (n < 2w and n < w branches)."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     rng = np.random.default_rng(11)
     dense = np.where(rng.random(shape) < 0.3, rng.uniform(0.001, 0.999, shape), 0.0)
     refmap = R.RefMap.from_dense(dense, -3.2, 1.6)

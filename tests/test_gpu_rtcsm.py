@@ -28,7 +28,8 @@ def _device_maps(ctx, refmap, win, apron=32):
 
 
 def test_rtcsm_c2_winner_and_tables_bit_exact(ctx):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     from scenes import room_scene
     scene = room_scene(seed=1)
     world, angles, traj, builder = scene
@@ -65,7 +66,8 @@ def test_rtcsm_c2_winner_and_tables_bit_exact(ctx):
 
 
 def test_rtcsm_batch_matches_reference(ctx):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     from scenes import room_scene
     scene = room_scene(seed=2)
     world, angles, traj, builder = scene
@@ -91,7 +93,8 @@ def test_rtcsm_batch_matches_reference(ctx):
     (dict(low_res=7, range_x=1.5, range_y=0.7, range_theta=0.2, scan_range_max=10.0), 0.5),
 ])
 def test_rtcsm_parameter_sweep(ctx, params, thr):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     from scenes import room_scene
     scene = room_scene(seed=3, n_beams=361, fov=180.0)
     world, angles, traj, builder = scene
@@ -113,7 +116,8 @@ def test_rtcsm_parameter_sweep(ctx, params, thr):
 
 def test_rtcsm_scan_overhanging_lower_left_edge(ctx):
     """H12: scans hanging over the lower-left map edge, where coarse values are not bounds."""
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     rng = np.random.default_rng(7)
     ny, nx = 128, 128
     dense = np.where(rng.random((ny, nx)) < 0.25, rng.uniform(0.05, 0.95, (ny, nx)), 0.0)
@@ -155,7 +159,8 @@ def _run_one(ctx, grid, coarse, params, angles, ranges, init, thr=None):
 
 
 def test_rtcsm_empty_and_degenerate(ctx):
-    from oracle import refapi as R
+    from oracle import backend
+    R = backend()
     dense = np.zeros((64, 64))
     dense[10:20, 30] = 0.9
     refmap = R.RefMap.from_dense(dense, 0.0, 0.0)
