@@ -1,0 +1,79 @@
+/* create_cuda_backends.hpp -- factory functions for the B200 backends, written the way
+ * slam_launcher.cpp writes its own (CreateScanMatcherRealTimeCorrelative :296-323,
+ * CreateLoopDetectorBranchBound, CreateScanMatcher :325-342, CreateLoopDetector :482-497).
+ *
+ * They are templates over the property-tree type so that this header also compiles where
+ * Boost is absent; in slam_launcher.cpp instantiate them with boost::property_tree::ptree and
+ * pass the launcher's own CreateCostFunction (see INTEGRATION.md for the five-line patch).
+ *
+ * New settings keys (all optional): "Device" (int, default 0) in the matcher / detector group.
+ */
+#ifndef LGS_ADAPTERS_CREATE_CUDA_BACKENDS_HPP
+#define LGS_ADAPTERS_CREATE_CUDA_BACKENDS_HPP
+
+#include <memory>
+#include <string>
+
+#include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
+#include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
+
+namespace LgsB200 {
+
+namespace Mapping = MyLidarGraphSlam::Mapping;
+
+/* "ScanMatcherType": "RealTimeCorrelativeCuda" -- same keys and defaults as
+ * launcher_settings_default.json:42-50 / slam_launcher.cpp:302-306 */
+template <typename Ptree, typename CostFactory>
+std::shared_ptr<Mapping::ScanMatcher> CreateScanMatcherRealTimeCorrelativeCuda(
+    const Ptree& jsonSettings, const std::string& configGroup, CostFactory createCostFunction)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    const int lowResolution = config.get("LowResolutionMapWinSize", 10);
+    const double rangeX = config.get("SearchRangeX", 0.75);
+    const double rangeY = config.get("SearchRangeY", 0.75);
+    const double rangeTheta = config.get("SearchRangeTheta", 0.5);
+    const double scanRangeMax = config.get("ScanRangeMax", 20.0);
+    const int device = config.get("Device", 0);
+    const std::string costType = config.get("CostType", std::string("GreedyEndpoint"));
+    const std::string costConfigGroup =
+        config.get("CostConfigGroup", std::string("CostGreedyEndpoint"));
+    auto pCostFunc = createCostFunction(jsonSettings, costType, costConfigGroup);
+    return std::make_shared<Mapping::ScanMatcherRealTimeCorrelativeCuda>(
+        pCostFunc, lowResolution, rangeX, rangeY, rangeTheta, scanRangeMax, device);
+}
+
+/* "LoopDetectorType": "BranchBoundCuda" -- reads the detector group
+ * (launcher_settings_default.json:128-132), its scan matcher group (:134-150) and the
+ * pixel-accurate score group (:152-160) exactly like the CPU factories do */
+template <typename Ptree, typename CostFactory>
+std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorBranchBoundCuda(
+    const Ptree& jsonSettings, const std::string& configGroup, CostFactory createCostFunction)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    const double scoreThreshold = config.template get<double>("ScoreThreshold");
+    const int device = config.get("Device", 0);
+    const std::string matcherGroup = config.template get<std::string>("ScanMatcherConfigGroup");
+
+    const Ptree& matcher = jsonSettings.get_child(matcherGroup);
+    const int nodeHeightMax = matcher.template get<int>("NodeHeightMax");
+    const double rangeX = matcher.template get<double>("SearchRangeX");
+    const double rangeY = matcher.template get<double>("SearchRangeY");
+    const double rangeTheta = matcher.template get<double>("SearchRangeTheta");
+    const double scanRangeMax = matcher.template get<double>("ScanRangeMax");
+    const std::string scoreGroup = matcher.template get<std::string>("ScoreConfigGroup");
+    const std::string costType = matcher.template get<std::string>("CostType");
+    const std::string costGroup = matcher.template get<std::string>("CostConfigGroup");
+
+    const Ptree& score = jsonSettings.get_child(scoreGroup);
+    const double usableRangeMin = score.template get<double>("UsableRangeMin");
+    const double usableRangeMax = score.template get<double>("UsableRangeMax");
+
+    auto pCostFunc = createCostFunction(jsonSettings, costType, costGroup);
+    return std::make_shared<Mapping::LoopDetectorBranchBoundCuda>(
+        usableRangeMin, usableRangeMax, pCostFunc, nodeHeightMax, rangeX, rangeY, rangeTheta,
+        scanRangeMax, scoreThreshold, device);
+}
+
+} /* namespace LgsB200 */
+
+#endif

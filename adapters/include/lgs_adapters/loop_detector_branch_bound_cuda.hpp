@@ -1,0 +1,65 @@
+/* loop_detector_branch_bound_cuda.hpp
+ *
+ * Drop-in replacement for LoopDetectorBranchBound + ScanMatcherBranchBound + ScorePixelAccurate
+ * (mapping/loop_detector_branch_bound.hpp:17-51, scan_matcher_branch_bound.hpp:19-98,
+ * score_function_pixel_accurate.hpp) behind the unchanged LoopDetector interface
+ * (mapping/loop_detector.hpp:92-107).  All (node, local map) pairs of one Detect() call are
+ * searched as ONE batch on the B200; the win-max pyramids stay on the device, cached per local
+ * map index and rebuilt when the builder resets LocalMapInfo::mPrecomputed
+ * (grid_map_builder.cpp:70-72).  Selected by the type string "BranchBoundCuda". */
+#ifndef LGS_ADAPTERS_LOOP_DETECTOR_BRANCH_BOUND_CUDA_HPP
+#define LGS_ADAPTERS_LOOP_DETECTOR_BRANCH_BOUND_CUDA_HPP
+
+#include <map>
+#include <vector>
+
+#include "lgs_b200.h"
+#include "my_lidar_graph_slam/mapping/cost_function.hpp"
+#include "my_lidar_graph_slam/mapping/loop_detector.hpp"
+
+namespace MyLidarGraphSlam {
+namespace Mapping {
+
+class LoopDetectorBranchBoundCuda final : public LoopDetector
+{
+public:
+    /* Parameters: ScorePixelAccurate(usableRangeMin, usableRangeMax), then
+     * ScanMatcherBranchBound(costFunc, nodeHeightMax, rangeX, rangeY, rangeTheta, scanRangeMax),
+     * then LoopDetectorBranchBound(scoreThreshold) -- in the reference's own order */
+    LoopDetectorBranchBoundCuda(const double scoreUsableRangeMin,
+                                const double scoreUsableRangeMax,
+                                const CostFuncPtr& costFunc,
+                                const int nodeHeightMax,
+                                const double rangeX,
+                                const double rangeY,
+                                const double rangeTheta,
+                                const double scanRangeMax,
+                                const double scoreThreshold,
+                                const int device = 0);
+    ~LoopDetectorBranchBoundCuda();
+
+    void Detect(LoopDetectionQueryVector& loopDetectionQueries,
+                LoopDetectionResultVector& loopDetectionResults) override;
+
+    /* Per-pair device results of the last Detect() (query-major, node-minor order) */
+    const std::vector<lgs_match_result>& LastResults() const { return this->mLast; }
+
+private:
+    struct DeviceMap { lgs_grid* mGrid; lgs_pyramid* mPyramid; };
+
+    lgs_pyramid* PyramidFor(LocalMapInfo& localMapInfo);
+
+    const CostFuncPtr             mCostFunc;
+    const lgs_bb_params           mParams;
+    const double                  mScoreThreshold;
+    lgs_ctx*                      mCtx;
+    lgs_bb_batch*                 mBatch;
+    std::map<int, DeviceMap>      mDeviceMaps;
+    std::vector<double>           mDense;
+    std::vector<lgs_match_result> mLast;
+};
+
+} /* namespace Mapping */
+} /* namespace MyLidarGraphSlam */
+
+#endif

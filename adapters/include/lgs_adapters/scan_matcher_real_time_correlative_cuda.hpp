@@ -1,0 +1,67 @@
+/* scan_matcher_real_time_correlative_cuda.hpp
+ *
+ * Drop-in replacement for MyLidarGraphSlam::Mapping::ScanMatcherRealTimeCorrelative
+ * (mapping/scan_matcher_real_time_correlative.hpp:16-93) whose exhaustive (x, y, theta) sweep
+ * runs on a B200 through the C ABI in include/lgs_b200.h.  Same constructor parameters, same
+ * ScanMatcher interface, same results (winning indices bit-exact, hence identical poses); the
+ * host tail (Cost, ComputeCovariance, MoveBackward) is the reference's own code.
+ * Selected by the type string "RealTimeCorrelativeCuda" (see INTEGRATION.md). */
+#ifndef LGS_ADAPTERS_SCAN_MATCHER_REAL_TIME_CORRELATIVE_CUDA_HPP
+#define LGS_ADAPTERS_SCAN_MATCHER_REAL_TIME_CORRELATIVE_CUDA_HPP
+
+#include <vector>
+
+#include "lgs_b200.h"
+#include "my_lidar_graph_slam/mapping/cost_function.hpp"
+#include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher.hpp"
+
+namespace MyLidarGraphSlam {
+namespace Mapping {
+
+class ScanMatcherRealTimeCorrelativeCuda final : public ScanMatcher
+{
+public:
+    ScanMatcherRealTimeCorrelativeCuda(const CostFuncPtr& costFunc,
+                                       const int lowResolution,
+                                       const double rangeX,
+                                       const double rangeY,
+                                       const double rangeTheta,
+                                       const double scanRangeMax,
+                                       const int device = 0);
+    ~ScanMatcherRealTimeCorrelativeCuda();
+
+    /* Optimize the robot pose by scan matching (threshold = DBL_MIN, whole window) */
+    ScanMatchingSummary OptimizePose(const ScanMatchingQuery& queryInfo) override;
+
+    /* Same as the reference's 5-argument overload minus the precomputed map, which now lives
+     * on the device */
+    ScanMatchingSummary OptimizePose(const GridMapType& gridMap,
+                                     const Sensor::ScanDataPtr<double>& scanData,
+                                     const RobotPose2D<double>& initialPose,
+                                     const double normalizedScoreThreshold);
+
+    /* Details of the last match (window indices, score, device counters) */
+    const lgs_match_result& LastResult() const { return this->mLast; }
+
+private:
+    void UploadMap(const GridMapType& gridMap);
+
+    const CostFuncPtr   mCostFunc;
+    const int           mLowResolution;
+    const double        mRangeX;
+    const double        mRangeY;
+    const double        mRangeTheta;
+    const double        mScanRangeMax;
+    lgs_ctx*            mCtx;
+    lgs_grid*           mGrid;
+    lgs_grid*           mCoarse;
+    lgs_rtcsm_batch*    mBatch;
+    std::vector<double> mDense;
+    lgs_match_result    mLast;
+};
+
+} /* namespace Mapping */
+} /* namespace MyLidarGraphSlam */
+
+#endif

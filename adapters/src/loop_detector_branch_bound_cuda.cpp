@@ -1,0 +1,162 @@
+/* loop_detector_branch_bound_cuda.cpp */
+
+#include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
+
+#include <cassert>
+
+#include "lgs_adapters/grid_map_flatten.hpp"
+#include "my_lidar_graph_slam/util.hpp"
+
+namespace MyLidarGraphSlam {
+namespace Mapping {
+
+namespace {
+void Check(lgs_ctx* ctx, int rc, const char* what)
+{
+    if (rc != LGS_OK) {
+        std::cerr << "lgs_b200: " << what << " failed (" << rc << "): "
+                  << (ctx ? lgs_ctx_last_error(ctx) : "no context") << std::endl;
+        std::abort();
+    }
+}
+} /* namespace */
+
+LoopDetectorBranchBoundCuda::LoopDetectorBranchBoundCuda(
+    const double scoreUsableRangeMin, const double scoreUsableRangeMax,
+    const CostFuncPtr& costFunc, const int nodeHeightMax, const double rangeX,
+    const double rangeY, const double rangeTheta, const double scanRangeMax,
+    const double scoreThreshold, const int device) :
+    mCostFunc(costFunc),
+    mParams { nodeHeightMax, rangeX, rangeY, rangeTheta, scanRangeMax,
+              scoreUsableRangeMin, scoreUsableRangeMax },
+    mScoreThreshold(scoreThreshold), mCtx(nullptr), mBatch(nullptr)
+{
+    assert(scoreThreshold > 0.0);      /* loop_detector_branch_bound.cpp:20-21 */
+    assert(scoreThreshold <= 1.0);
+    Check(nullptr, lgs_ctx_create(device, &this->mCtx), "lgs_ctx_create (a B200 is required)");
+    Check(this->mCtx, lgs_bb_batch_create(this->mCtx, &this->mParams, &this->mBatch),
+          "lgs_bb_batch_create");
+}
+
+LoopDetectorBranchBoundCuda::~LoopDetectorBranchBoundCuda()
+{
+    lgs_bb_batch_destroy(this->mBatch);
+    for (auto& kv : this->mDeviceMaps) {
+        lgs_pyramid_destroy(kv.second.mPyramid);
+        lgs_grid_destroy(kv.second.mGrid);
+    }
+    lgs_ctx_destroy(this->mCtx);
+}
+
+/* Device pyramid of a local map: built on first use, rebuilt when the builder has reset
+ * mPrecomputed after a loop closure (loop_detector_branch_bound.cpp:51-60) */
+lgs_pyramid* LoopDetectorBranchBoundCuda::PyramidFor(LocalMapInfo& localMapInfo)
+{
+    auto it = this->mDeviceMaps.find(localMapInfo.mIdx);
+    if (it != this->mDeviceMaps.end() && localMapInfo.mPrecomputed)
+        return it->second.mPyramid;
+    if (it != this->mDeviceMaps.end()) {
+        lgs_pyramid_destroy(it->second.mPyramid);
+        lgs_grid_destroy(it->second.mGrid);
+        this->mDeviceMaps.erase(it);
+    }
+    const GridMapType& map = localMapInfo.mMap;
+    DeviceMap dev { nullptr, nullptr };
+    Check(this->mCtx, lgs_grid_create(this->mCtx, map.NumOfGridCellsX(),
+          map.NumOfGridCellsY(), map.MinPos().mX, map.MinPos().mY, map.Resolution(), 1,
+          &dev.mGrid), "lgs_grid_create");
+    LgsB200::FlattenGridMap(map, this->mDense);
+    Check(this->mCtx, lgs_grid_upload(dev.mGrid, this->mDense.data()), "lgs_grid_upload");
+    Check(this->mCtx, lgs_pyramid_create(this->mCtx, dev.mGrid, this->mParams.node_height_max,
+          &dev.mPyramid), "lgs_pyramid_create");
+    this->mDeviceMaps.emplace(localMapInfo.mIdx, dev);
+    /* The host-side pyramids stay empty; the flag alone is what the SLAM parent copies back
+     * (lidar_graph_slam.cpp:285-303) */
+    localMapInfo.mPrecomputed = true;
+    return dev.mPyramid;
+}
+
+void LoopDetectorBranchBoundCuda::Detect(
+    LoopDetectionQueryVector& loopDetectionQueries,
+    LoopDetectionResultVector& loopDetectionResults)
+{
+    loopDetectionResults.clear();
+    this->mLast.clear();
+
+    if (loopDetectionQueries.empty())
+        return;
+
+    /* Gather every (node, local map) pair of every query into one device batch */
+    std::vector<int> beamBegin { 0 };
+    std::vector<double> angles, ranges, poses, rangeMin, rangeMax, thresholds;
+    std::vector<lgs_pyramid*> pyramids;
+
+    for (auto& query : loopDetectionQueries) {
+        auto& localMapInfo = query.mLocalMapInfo;
+        assert(query.mLocalMapNode.Index() >= localMapInfo.mPoseGraphNodeIdxMin &&
+               query.mLocalMapNode.Index() <= localMapInfo.mPoseGraphNodeIdxMax);
+        assert(localMapInfo.mFinished);
+        lgs_pyramid* pyramid = this->PyramidFor(localMapInfo);
+
+        for (const auto& node : query.mPoseGraphNodes) {
+            const auto& scanData = node.ScanData();
+            const RobotPose2D<double> sensorPose =
+                Compound(node.Pose(), scanData->RelativeSensorPose());
+            angles.insert(angles.end(), scanData->Angles().begin(), scanData->Angles().end());
+            ranges.insert(ranges.end(), scanData->Ranges().begin(), scanData->Ranges().end());
+            beamBegin.push_back(static_cast<int>(ranges.size()));
+            poses.insert(poses.end(), { sensorPose.mX, sensorPose.mY, sensorPose.mTheta });
+            rangeMin.push_back(scanData->MinRange());
+            rangeMax.push_back(scanData->MaxRange());
+            thresholds.push_back(this->mScoreThreshold);
+            pyramids.push_back(pyramid);
+        }
+    }
+
+    const int numOfPairs = static_cast<int>(pyramids.size());
+    this->mLast.resize(numOfPairs);
+    if (numOfPairs > 0) {
+        const lgs_scan_batch scans { numOfPairs, beamBegin.data(), angles.data(), ranges.data(),
+                                     poses.data(), rangeMin.data(), rangeMax.data() };
+        Check(this->mCtx, lgs_bb_batch_upload(this->mBatch, &scans, pyramids.data(),
+              thresholds.data()), "lgs_bb_batch_upload");
+        Check(this->mCtx, lgs_bb_batch_run(this->mBatch), "lgs_bb_batch_run");
+        Check(this->mCtx, lgs_bb_batch_results(this->mBatch, this->mLast.data()),
+              "lgs_bb_batch_results");
+    }
+
+    /* Host tail and loop closing edges in the reference's order
+     * (loop_detector_branch_bound.cpp:63-88, scan_matcher_branch_bound.cpp:143-162) */
+    int pairIdx = 0;
+    for (auto& query : loopDetectionQueries) {
+        const auto& localMap = query.mLocalMapInfo.mMap;
+        const auto& localMapNode = query.mLocalMapNode;
+
+        for (const auto& node : query.mPoseGraphNodes) {
+            const lgs_match_result& r = this->mLast[pairIdx++];
+            if (!r.found)
+                continue;
+
+            const auto& scanData = node.ScanData();
+            const RobotPose2D<double> sensorPose =
+                Compound(node.Pose(), scanData->RelativeSensorPose());
+            const RobotPose2D<double> bestSensorPose {
+                sensorPose.mX + r.ix * r.step_x,
+                sensorPose.mY + r.iy * r.step_y,
+                sensorPose.mTheta + r.it * r.step_t };
+            const RobotPose2D<double> correspondingPose =
+                MoveBackward(bestSensorPose, scanData->RelativeSensorPose());
+            const Eigen::Matrix3d covarianceMatrix =
+                this->mCostFunc->ComputeCovariance(localMap, scanData, bestSensorPose);
+
+            const RobotPose2D<double> relativePose =
+                InverseCompound(localMapNode.Pose(), correspondingPose);
+            loopDetectionResults.emplace_back(
+                relativePose, localMapNode.Pose(),
+                localMapNode.Index(), node.Index(), covarianceMatrix);
+        }
+    }
+}
+
+} /* namespace Mapping */
+} /* namespace MyLidarGraphSlam */

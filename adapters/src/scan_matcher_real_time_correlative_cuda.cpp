@@ -1,0 +1,126 @@
+/* scan_matcher_real_time_correlative_cuda.cpp */
+
+#include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
+
+#include <cmath>
+#include <limits>
+
+#include "lgs_adapters/grid_map_flatten.hpp"
+#include "my_lidar_graph_slam/util.hpp"
+
+namespace MyLidarGraphSlam {
+namespace Mapping {
+
+namespace {
+void Check(lgs_ctx* ctx, int rc, const char* what)
+{
+    /* Same failure behaviour as the reference: assertion + abort (util.hpp:29-38) */
+    if (rc != LGS_OK) {
+        std::cerr << "lgs_b200: " << what << " failed (" << rc << "): "
+                  << (ctx ? lgs_ctx_last_error(ctx) : "no context") << std::endl;
+        std::abort();
+    }
+}
+} /* namespace */
+
+ScanMatcherRealTimeCorrelativeCuda::ScanMatcherRealTimeCorrelativeCuda(
+    const CostFuncPtr& costFunc, const int lowResolution, const double rangeX,
+    const double rangeY, const double rangeTheta, const double scanRangeMax,
+    const int device) :
+    mCostFunc(costFunc), mLowResolution(lowResolution), mRangeX(rangeX),
+    mRangeY(rangeY), mRangeTheta(rangeTheta), mScanRangeMax(scanRangeMax),
+    mCtx(nullptr), mGrid(nullptr), mCoarse(nullptr), mBatch(nullptr), mLast()
+{
+    Check(nullptr, lgs_ctx_create(device, &this->mCtx), "lgs_ctx_create (a B200 is required)");
+    const lgs_rtcsm_params params { lowResolution, rangeX, rangeY, rangeTheta, scanRangeMax };
+    Check(this->mCtx, lgs_rtcsm_batch_create(this->mCtx, &params, &this->mBatch),
+          "lgs_rtcsm_batch_create");
+}
+
+ScanMatcherRealTimeCorrelativeCuda::~ScanMatcherRealTimeCorrelativeCuda()
+{
+    lgs_rtcsm_batch_destroy(this->mBatch);
+    lgs_grid_destroy(this->mCoarse);
+    lgs_grid_destroy(this->mGrid);
+    lgs_ctx_destroy(this->mCtx);
+}
+
+void ScanMatcherRealTimeCorrelativeCuda::UploadMap(const GridMapType& gridMap)
+{
+    const int nx = gridMap.NumOfGridCellsX(), ny = gridMap.NumOfGridCellsY();
+    int curNx = -1, curNy = -1;
+    double curMinX = 0.0, curMinY = 0.0, curRes = 0.0;
+    if (this->mGrid != nullptr)
+        lgs_grid_info(this->mGrid, &curNx, &curNy, &curMinX, &curMinY, &curRes, nullptr);
+    if (curNx != nx || curNy != ny || curMinX != gridMap.MinPos().mX ||
+        curMinY != gridMap.MinPos().mY || curRes != gridMap.Resolution()) {
+        lgs_grid_destroy(this->mCoarse);
+        lgs_grid_destroy(this->mGrid);
+        /* The zero apron must cover the fine search window (H2: it is asymmetric) */
+        const double res = gridMap.Resolution();
+        const int winX = static_cast<int>(std::ceil(0.5 * this->mRangeX / res));
+        const int winY = static_cast<int>(std::ceil(0.5 * this->mRangeY / res));
+        const int spanX = ((2 * winX) / this->mLowResolution + 1) * this->mLowResolution;
+        const int spanY = ((2 * winY) / this->mLowResolution + 1) * this->mLowResolution;
+        const int apron = std::max(spanX, spanY);
+        Check(this->mCtx, lgs_grid_create(this->mCtx, nx, ny, gridMap.MinPos().mX,
+              gridMap.MinPos().mY, res, apron, &this->mGrid), "lgs_grid_create");
+        Check(this->mCtx, lgs_grid_create(this->mCtx, nx, ny, gridMap.MinPos().mX,
+              gridMap.MinPos().mY, res, apron, &this->mCoarse), "lgs_grid_create");
+    }
+    LgsB200::FlattenGridMap(gridMap, this->mDense);
+    Check(this->mCtx, lgs_grid_upload(this->mGrid, this->mDense.data()), "lgs_grid_upload");
+    /* ComputeCoarserMap (scan_matcher_real_time_correlative.cpp:148-153) on the device */
+    Check(this->mCtx, lgs_precompute(this->mCtx, this->mGrid, this->mLowResolution,
+          this->mCoarse), "lgs_precompute");
+}
+
+ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
+    const ScanMatchingQuery& queryInfo)
+{
+    return this->OptimizePose(queryInfo.mGridMap, queryInfo.mScanData,
+                              queryInfo.mInitialPose,
+                              std::numeric_limits<double>::min());
+}
+
+ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
+    const GridMapType& gridMap,
+    const Sensor::ScanDataPtr<double>& scanData,
+    const RobotPose2D<double>& initialPose,
+    const double normalizedScoreThreshold)
+{
+    this->UploadMap(gridMap);
+
+    const RobotPose2D<double> sensorPose =
+        Compound(initialPose, scanData->RelativeSensorPose());
+    const int beamBegin[2] = { 0, static_cast<int>(scanData->NumOfScans()) };
+    const double pose[3] = { sensorPose.mX, sensorPose.mY, sensorPose.mTheta };
+    const lgs_scan_batch scans { 1, beamBegin, scanData->Angles().data(),
+                                 scanData->Ranges().data(), pose, nullptr, nullptr };
+    Check(this->mCtx, lgs_rtcsm_batch_upload(this->mBatch, this->mGrid, &scans,
+          &normalizedScoreThreshold), "lgs_rtcsm_batch_upload");
+    Check(this->mCtx, lgs_rtcsm_batch_run(this->mBatch, this->mGrid, this->mCoarse),
+          "lgs_rtcsm_batch_run");
+    Check(this->mCtx, lgs_rtcsm_batch_results(this->mBatch, this->mGrid, this->mCoarse,
+          &this->mLast), "lgs_rtcsm_batch_results");
+
+    /* From here on: the reference's own host tail
+     * (scan_matcher_real_time_correlative.cpp:118-144) */
+    const bool poseFound = this->mLast.found != 0;
+    const RobotPose2D<double> bestSensorPose {
+        sensorPose.mX + this->mLast.ix * this->mLast.step_x,
+        sensorPose.mY + this->mLast.iy * this->mLast.step_y,
+        sensorPose.mTheta + this->mLast.it * this->mLast.step_t };
+    const double costVal = this->mCostFunc->Cost(gridMap, scanData, bestSensorPose);
+    const double normalizedCost = costVal / scanData->NumOfScans();
+    const RobotPose2D<double> estimatedPose =
+        MoveBackward(bestSensorPose, scanData->RelativeSensorPose());
+    const Eigen::Matrix3d estimatedCovariance =
+        this->mCostFunc->ComputeCovariance(gridMap, scanData, bestSensorPose);
+
+    return ScanMatchingSummary {
+        poseFound, normalizedCost, initialPose, estimatedPose, estimatedCovariance };
+}
+
+} /* namespace Mapping */
+} /* namespace MyLidarGraphSlam */

@@ -1,0 +1,176 @@
+/* test_adapters.cpp -- runs the CUDA adapters side by side with the reference's own classes on a
+ * synthetic office world and requires IDENTICAL outputs: every field of ScanMatchingSummary and
+ * of each LoopDetectionResult (poses, cost, covariance), compared as bit patterns.
+ * Built here against /root/reference (adapters/Makefile), run on the GPU box by
+ * tests/test_gpu_adapters.py.  Exit code 0 = all identical. */
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+
+#include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
+#include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
+#include "my_lidar_graph_slam/mapping/cost_function_greedy_endpoint.hpp"
+#include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
+#include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_real_time_correlative.hpp"
+
+using namespace MyLidarGraphSlam;
+using namespace MyLidarGraphSlam::Mapping;
+
+namespace {
+
+/* 24 m x 24 m lattice of 4 m rooms with door gaps; analytic ray casting */
+struct World {
+    struct Seg { double x0, y0, x1, y1; };
+    std::vector<Seg> segs;
+    explicit World(unsigned seed) {
+        std::mt19937 g(seed);
+        std::uniform_real_distribution<double> u(0.4, 4.0 - 1.2 - 0.4);
+        const double h = 12.0, room = 4.0, door = 1.2;
+        segs = {{-h, -h, h, -h}, {h, -h, h, h}, {h, h, -h, h}, {-h, h, -h, -h}};
+        for (int i = 1; i < 6; ++i) {
+            const double c = -h + i * room;
+            for (int j = 0; j < 6; ++j) {
+                const double a0 = -h + j * room;
+                double gp = a0 + u(g);
+                segs.push_back({c, a0, c, gp}); segs.push_back({c, gp + door, c, a0 + room});
+                gp = a0 + u(g);
+                segs.push_back({a0, c, gp, c}); segs.push_back({gp + door, c, a0 + room, c});
+            }
+        }
+    }
+    double Cast(double x, double y, double a) const {
+        const double c = std::cos(a), s = std::sin(a);
+        double best = 1e9;
+        for (const auto& sg : segs) {
+            if (sg.y0 == sg.y1) {
+                if (std::fabs(s) < 1e-12) continue;
+                const double t = (sg.y0 - y) / s, xi = x + t * c;
+                if (t > 1e-9 && xi >= std::min(sg.x0, sg.x1) && xi <= std::max(sg.x0, sg.x1)) best = std::min(best, t);
+            } else {
+                if (std::fabs(c) < 1e-12) continue;
+                const double t = (sg.x0 - x) / c, yi = y + t * s;
+                if (t > 1e-9 && yi >= std::min(sg.y0, sg.y1) && yi <= std::max(sg.y0, sg.y1)) best = std::min(best, t);
+            }
+        }
+        return best;
+    }
+};
+
+const RobotPose2D<double> kRelSensor(0.12, -0.03, 0.05);   /* non-trivial sensor mounting */
+
+Sensor::ScanDataPtr<double> MakeScan(const World& w, const RobotPose2D<double>& robot, int n,
+                                     std::mt19937& g) {
+    std::normal_distribution<double> noise(0.0, 0.01);
+    const RobotPose2D<double> sp = Compound(robot, kRelSensor);
+    const double fov = 4.71238898038469;
+    std::vector<double> ang(n), rng(n);
+    for (int i = 0; i < n; ++i) {
+        ang[i] = -fov / 2 + fov * i / (n - 1);
+        rng[i] = std::min(30.0, std::max(0.02, w.Cast(sp.mX, sp.mY, sp.mTheta + ang[i]) + noise(g)));
+    }
+    return std::make_shared<Sensor::ScanData<double>>(
+        "L", 0.0, robot, RobotPose2D<double>(0, 0, 0), kRelSensor, 0.02, 30.0, -fov / 2, fov / 2,
+        std::move(ang), std::move(rng));
+}
+
+bool SameBits(double a, double b) { return std::memcmp(&a, &b, sizeof a) == 0; }
+bool SamePose(const RobotPose2D<double>& a, const RobotPose2D<double>& b) {
+    return SameBits(a.mX, b.mX) && SameBits(a.mY, b.mY) && SameBits(a.mTheta, b.mTheta);
+}
+bool SameMat(const Eigen::Matrix3d& a, const Eigen::Matrix3d& b) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) if (!SameBits(a(i, j), b(i, j))) return false;
+    return true;
+}
+
+}  // namespace
+
+int main() {
+    std::mt19937 g(5);
+    const World world(7);
+    auto poseGraph = std::make_shared<PoseGraph>();
+    GridMapBuilder builder(0.05, 64, 10, 6.0, 0.01, 20.0, 0.6, 0.45);   /* new local map every 6 m */
+    /* drive around inside one room row, through doors where they line up */
+    std::vector<RobotPose2D<double>> path;
+    for (int k = 0; k < 60; ++k)
+        path.emplace_back(-9.8 + 0.33 * k * std::cos(0.02 * k), -9.9 + 0.9 * std::sin(0.21 * k), 0.03 * k);
+    for (const auto& p : path) {
+        poseGraph->AppendNode(p, MakeScan(world, p, 541, g));
+        builder.AppendScan(poseGraph);
+    }
+    std::printf("local maps: %zu, latest map %dx%d\n", builder.LocalMaps().size(),
+                builder.LatestMap().NumOfGridCellsX(), builder.LatestMap().NumOfGridCellsY());
+    /* cost function exactly as slam_launcher.cpp:60-72 builds it from the default settings */
+    auto cost = std::make_shared<CostGreedyEndpoint>(0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0);
+    int failures = 0;
+
+    /* ---- front-end matcher ---- */
+    {
+        ScanMatcherRealTimeCorrelative ref(cost, 5, 1.0, 1.0, 0.6, 20.0);
+        ScanMatcherRealTimeCorrelativeCuda gpu(cost, 5, 1.0, 1.0, 0.6, 20.0, 0);
+        std::uniform_real_distribution<double> dxy(-0.3, 0.3), dth(-0.15, 0.15);
+        for (int k = 0; k < 6; ++k) {
+            const RobotPose2D<double> truth = path[50 + k];
+            const auto scan = MakeScan(world, truth, 541, g);
+            const RobotPose2D<double> init(truth.mX + dxy(g), truth.mY + dxy(g), truth.mTheta + dth(g));
+            ScanMatchingQuery q1(GridMapType(builder.LatestMap()), scan, init);
+            ScanMatchingQuery q2(GridMapType(builder.LatestMap()), scan, init);
+            const ScanMatchingSummary a = ref.OptimizePose(q1);
+            const ScanMatchingSummary b = gpu.OptimizePose(q2);
+            const bool ok = a.mPoseFound == b.mPoseFound && SameBits(a.mNormalizedCost, b.mNormalizedCost) &&
+                            SamePose(a.mInitialPose, b.mInitialPose) && SamePose(a.mEstimatedPose, b.mEstimatedPose) &&
+                            SameMat(a.mEstimatedCovariance, b.mEstimatedCovariance);
+            std::printf("rtcsm %d: found %d/%d pose (%.4f %.4f %.4f) idx (%d %d %d) score %.6f %s\n", k,
+                        a.mPoseFound, b.mPoseFound, b.mEstimatedPose.mX, b.mEstimatedPose.mY, b.mEstimatedPose.mTheta,
+                        gpu.LastResult().ix, gpu.LastResult().iy, gpu.LastResult().it, gpu.LastResult().score,
+                        ok ? "IDENTICAL" : "MISMATCH");
+            failures += !ok;
+        }
+    }
+
+    /* ---- loop detector ---- */
+    {
+        auto score = std::make_shared<ScorePixelAccurate>(0.01, 20.0);
+        auto bb = std::make_shared<ScanMatcherBranchBound>(score, cost, 6, 2.0, 2.0, 1.0, 20.0);
+        LoopDetectorBranchBound ref(bb, 0.6);
+        LoopDetectorBranchBoundCuda gpu(0.01, 20.0, cost, 6, 2.0, 2.0, 1.0, 20.0, 0.6, 0);
+        std::uniform_real_distribution<double> dxy(-0.5, 0.5), dth(-0.25, 0.25);
+        for (int round = 0; round < 2; ++round) {   /* second round hits the device pyramid cache */
+            LoopDetectionQueryVector q1, q2;
+            for (size_t m = 0; m + 1 < builder.LocalMaps().size() && m < 3; ++m) {
+                LocalMapInfo info = builder.LocalMapAt(static_cast<int>(m));
+                info.mFinished = true;
+                std::vector<PoseGraph::Node> n1, n2;
+                for (int j = 0; j < 3; ++j) {   /* revisit poses inside this local map, perturbed */
+                    const int idx = info.mPoseGraphNodeIdxMin + 2 + 3 * j + round;
+                    const RobotPose2D<double> truth = poseGraph->NodeAt(idx).Pose();
+                    const auto scan = MakeScan(world, truth, 541, g);
+                    const RobotPose2D<double> pert(truth.mX + dxy(g), truth.mY + dxy(g), truth.mTheta + dth(g));
+                    n1.emplace_back(1000 + j, pert, scan);
+                    n2.emplace_back(1000 + j, pert, scan);
+                }
+                const PoseGraph::Node& mapNode = poseGraph->NodeAt(info.mPoseGraphNodeIdxMin);
+                q1.emplace_back(std::move(n1), info, mapNode);
+                q2.emplace_back(std::move(n2), info, mapNode);
+            }
+            LoopDetectionResultVector r1, r2;
+            ref.Detect(q1, r1);
+            gpu.Detect(q2, r2);
+            bool ok = r1.size() == r2.size();
+            for (size_t i = 0; ok && i < r1.size(); ++i)
+                ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) &&
+                     SamePose(r1[i].mStartNodePose, r2[i].mStartNodePose) &&
+                     r1[i].mStartNodeIdx == r2[i].mStartNodeIdx && r1[i].mEndNodeIdx == r2[i].mEndNodeIdx &&
+                     SameMat(r1[i].mEstimatedCovMat, r2[i].mEstimatedCovMat);
+            for (auto& q : q2) ok = ok && q.mLocalMapInfo.mPrecomputed;
+            std::printf("loop round %d: %zu queries, %zu pairs, loops ref %zu / cuda %zu %s\n", round, q1.size(),
+                        gpu.LastResults().size(), r1.size(), r2.size(), ok ? "IDENTICAL" : "MISMATCH");
+            failures += !ok;
+            if (r1.empty()) { std::printf("expected at least one detected loop\n"); ++failures; }
+        }
+    }
+    std::printf(failures ? "FAILED (%d)\n" : "ALL IDENTICAL\n", failures);
+    return failures ? 1 : 0;
+}
