@@ -43,14 +43,28 @@ METRIC = "pose hypotheses scored/sec (real-time correlative sweep, C2)"
 UNIT = "hypotheses/s"
 
 
+def build_map_on_gpu(ctx, poses, angles, ranges_list, apron, usable=(0.02, 20.0)):
+    """Product path: range filter + hit points on the host (lgs_scan_hit_points), map geometry
+    grown like GridMap::Expand (lgs_geometry_expand), then ONE lgs_grid_integrate_scans batch."""
+    from my_lidar_graph_slam_b200 import capi
+    geo = capi.Geometry(0, 0, float(poses[0][0]), float(poses[0][1]), 0.05, 64)
+    hits = []
+    for p, r in zip(poses, ranges_list):
+        h, bbox = capi.scan_hit_points(p, angles, r, usable[0], usable[1])
+        geo, _, _, _ = capi.geometry_expand(geo, bbox)
+        hits.append(h)
+    grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=apron)
+    updates = capi.integrate_scans(ctx, grid, np.asarray(poses)[:, :2], hits)
+    return grid, updates
+
+
 def c2_workload(n_matches: int, seed: int = 1):
-    """Map from 10 scans + n_matches (scan, perturbed initial pose) pairs, all seeded."""
+    """Map scans + n_matches (scan, perturbed initial pose) pairs, all seeded."""
     world = synth.RoomsWorld(40.0, 5.0, seed=seed + 1)   # office-like: most ranges < 5.7 m
     angles = synth.beam_angles(1081, 270.0)
     traj = synth.trajectory(world, 10, step=0.4, seed=seed + 1)
     noise = np.random.default_rng(seed + 1)           # range noise
     map_scans = [synth.make_scan(world, p, angles, noise) for p in traj]
-    dense, min_x, min_y = synth.rasterize_map(traj, angles, map_scans)
     pert = np.random.default_rng(seed + 2)            # pose perturbations
     ranges, inits = [], []
     while len(ranges) < n_matches:
@@ -62,7 +76,7 @@ def c2_workload(n_matches: int, seed: int = 1):
         ranges.append(synth.make_scan(world, true, angles, noise))
         inits.append(true + np.array([pert.uniform(-0.3, 0.3), pert.uniform(-0.3, 0.3),
                                       pert.uniform(-0.2, 0.2)]))
-    return dense, min_x, min_y, angles, ranges, np.asarray(inits)
+    return traj, map_scans, angles, ranges, np.asarray(inits)
 
 
 class ClockSampler:
@@ -154,7 +168,13 @@ def run_reference(args, rank, world_size):
         return
     per_step = max(cores, 8)
     total = per_step * (args.steps + args.warmup)
-    dense, min_x, min_y, angles, ranges, inits = c2_workload(total, seed=1)
+    traj, map_scans, angles, ranges, inits = c2_workload(total, seed=1)
+    builder = R.RefBuilder(n_latest=len(traj))
+    for p, r in zip(traj, map_scans):
+        builder.append_scan(p, angles, r)
+    refmap = builder.local_map(0)
+    dense = refmap.dense()
+    _, _, min_x, min_y, _ = refmap.geometry()
     times, hyps = [], 0
     for s in range(args.steps + args.warmup):
         sl = slice(s * per_step, (s + 1) * per_step)
@@ -177,6 +197,182 @@ def run_reference(args, rank, world_size):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+
+# ---- extra workloads reported beside the headline (same JSON line, key "extra") --------------------
+BB = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0, scan_range_max=20.0,
+          score_range_min=0.01, score_range_max=20.0)
+
+
+def c4_submap_scans(world, angles, submap_id, n_scans, anchor):
+    """Deterministic scans of one submap: the first ten submaps start near `anchor` (they contain
+    the query location), the others anywhere in the world."""
+    rng = np.random.default_rng(10_000 + submap_id)
+    if submap_id < 10:
+        start = (anchor[0] + rng.uniform(-0.5, 0.5), anchor[1] + rng.uniform(-0.5, 0.5),
+                 anchor[2] + rng.uniform(-0.3, 0.3))
+        if not world.is_free(start[0], start[1], 0.6):
+            start = tuple(anchor)
+        traj = synth.trajectory(world, n_scans, step=0.3, seed=submap_id, start=start)
+    else:
+        traj = synth.trajectory(world, n_scans, step=0.3, seed=submap_id)
+    return traj, [synth.make_scan(world, p, angles, rng) for p in traj]
+
+
+def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps, steps, with_cpu):
+    """C4: one 1081-beam scan against n_submaps submaps, 7 pyramid levels, threshold 0.6.
+    Submap i lives on rank i mod N; results are all-gathered (32-byte records)."""
+    from my_lidar_graph_slam_b200 import capi, sharding
+    world = synth.RoomsWorld(60.0, 5.0, seed=4)
+    angles = synth.beam_angles(1081, 270.0)
+    anchor = synth.trajectory(world, 1, seed=77)[0]
+    mine = sharding.owned(n_submaps, rank, world_size)
+    t0 = time.perf_counter()
+    grids, pyramids, cells = [], [], 0
+    for g in mine:
+        traj, scans = c4_submap_scans(world, angles, int(g), 8, anchor)
+        grid, _ = build_map_on_gpu(ctx, traj, angles, scans, apron=1)
+        grids.append(grid)
+        cells += grid.nx * grid.ny
+    build_s = time.perf_counter() - t0
+    ctx.synchronize()
+    ctx.timer_start()
+    for grid in grids:
+        pyramids.append(capi.Pyramid(ctx, grid, 6))
+    pyr_ms = ctx.timer_stop()
+    qrng = np.random.default_rng(5)
+    truth = anchor + np.array([0.2, -0.1, 0.05])
+    scan = synth.make_scan(world, truth, angles, qrng)
+    init = truth + np.array([0.4, -0.3, 0.1])
+    nq = len(mine)
+    scans = capi.Scans([angles] * nq, [scan] * nq, [init] * nq, range_min=0.02, range_max=30.0)
+    batch = capi.BbBatch(ctx, **BB)
+    dev = f"cuda:{local_rank}" if world_size > 1 else None
+
+    def step():
+        batch.upload(scans, pyramids, 0.6)
+        batch.run()
+        res = batch.results()
+        return sharding.all_gather_records(sharding.pack(res, mine), n_submaps, rank, world_size, dev)
+
+    for _ in range(3):
+        rec = step()
+    ctx.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rec = step()
+    ctx.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # kernels only (scan + pyramids resident)
+    batch.upload(scans, pyramids, 0.6)
+    barrier()
+    ctx.timer_start()
+    for _ in range(steps):
+        batch.run()
+    dev_ms = max_over_ranks(ctx.timer_stop())
+    levels, gathers = batch.work()
+    out = {"workload": f"C4 branch-and-bound loop detection: 1 scan x {n_submaps} submaps, 7 levels, "
+                       "2 m x 2 m x 1 rad, thr 0.6",
+           "loop_queries_per_s": n_submaps * steps / (dev_ms * 1e-3),
+           "loop_queries_per_s_e2e": n_submaps * steps / e2e_s,
+           "ms_per_query_batch": dev_ms / steps, "ms_per_query_batch_e2e": 1e3 * e2e_s / steps,
+           "nodes_scored_per_batch_rank0": int(sum(levels)), "nodes_per_level_rank0": levels,
+           "gathered_cells_per_batch_rank0": int(gathers),
+           "loops_found": int((rec["found"] != 0).sum()), "best_submap": sharding.best_candidate(rec),
+           "submaps_per_rank": int(nq), "submap_cells_rank0": int(cells),
+           "pyramid_build_ms_rank0": pyr_ms,
+           "pyramid_cells_levels_per_s": cells * 7 / (pyr_ms * 1e-3) if pyr_ms > 0 else None,
+           "submap_build_s_rank0": build_s, "n_gpus": world_size,
+           "scaling": "strong (fixed 500 submaps, round-robin over ranks, all-gather of records)"}
+    if with_cpu and rank == 0:
+        try:
+            from oracle import refapi as R
+            if R.available():
+                cores = os.cpu_count() or 1
+                ns = min(nq, max(cores, 16))
+                from concurrent.futures import ThreadPoolExecutor
+                maps = []
+                for k in range(ns):
+                    g = grids[k]
+                    m = R.RefMap.from_dense(g.download(), g.min_x, g.min_y)
+                    maps.append((m, m.pyramid(6)))
+
+                def one(k):
+                    return R.bb_match(maps[k][0], angles, scan, init, pyramid=maps[k][1], thr=0.6)
+                one(0)
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(max_workers=cores) as ex:
+                    ref = list(ex.map(one, range(ns)))
+                dt = time.perf_counter() - t0
+                bad = sum((a.found, a.ix, a.iy, a.it) != (int(b["found"]), int(b["ix"]), int(b["iy"]), int(b["it"]))
+                          or (a.found and a.score != float(b["score"]))
+                          for a, b in zip(ref, rec[mine[:ns]]))
+                out["cpu_baseline"] = {"value": ns / dt, "unit": "loop queries/s", "cores": cores,
+                                       "kind": "reference",
+                                       "sample": f"first {ns} submaps on {cores} threads ({dt:.1f} s), "
+                                                 f"pyramids prebuilt; GPU results identical on {ns - bad}/{ns}"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
+    for p in pyramids:
+        p.close()
+    for g in grids:
+        g.close()
+    return out
+
+
+def run_c3(ctx, n_distinct, n_total, with_cpu):
+    """C3 (bounded sample): 1081-beam scans along a trajectory integrated into one pre-sized map
+    in batches of 64, host hit points in, cell updates applied in (scan, beam) order."""
+    from my_lidar_graph_slam_b200 import capi
+    world = synth.RoomsWorld(40.0, 5.0, seed=6)
+    angles = synth.beam_angles(1081, 270.0)
+    traj = synth.trajectory(world, n_distinct, step=0.1, seed=6)
+    rng = np.random.default_rng(7)
+    ranges = [synth.make_scan(world, p, angles, rng) for p in traj]
+    hits = [capi.scan_hit_points(p, angles, r, 0.02, 20.0)[0] for p, r in zip(traj, ranges)]
+    geo = capi.Geometry(0, 0, -20.0, -20.0, 0.05, 64)
+    geo, _, _, _ = capi.geometry_expand(geo, (-20.5, -20.5, 20.5, 20.5), 0.0)
+    grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
+    B = 64
+    capi.integrate_scans(ctx, grid, traj[:B, :2], hits[:B])          # warm-up
+    capi.grid_clear(grid)
+    ctx.synchronize()
+    updates, done = 0, 0
+    t0 = time.perf_counter()
+    while done < n_total:
+        k = done % n_distinct
+        e = min(k + B, n_distinct)
+        updates += capi.integrate_scans(ctx, grid, traj[k:e, :2], hits[k:e])
+        done += e - k
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"workload": f"C3 occupancy-grid integration (bounded sample: {done} scans = {n_distinct} distinct "
+                       f"scans streamed repeatedly, batches of {B}) into one {geo.nx}x{geo.ny} map",
+           "scans_per_s": done / dt, "cell_updates_per_s": updates / dt,
+           "cell_updates_per_scan": updates / done, "e2e": True,
+           "algorithmic_GBps": updates * 16 / dt / 1e9}
+    if with_cpu:
+        try:
+            from oracle import refapi as R
+            if R.available():
+                m = R.RefMap.from_dense(np.zeros((geo.ny, geo.nx)), geo.min_x, geo.min_y)
+                ns = min(n_distinct, 256)
+                t0 = time.perf_counter()
+                for k in range(ns):
+                    R.map_integrate_hits(m, traj[k, :2], hits[k])
+                dtc = time.perf_counter() - t0
+                capi.grid_clear(grid)
+                capi.integrate_scans(ctx, grid, traj[:ns, :2], hits[:ns])
+                same = bool(np.array_equal(grid.download().view(np.int64), m.dense().view(np.int64)))
+                out["cpu_baseline"] = {"value": ns / dtc, "unit": "scans/s", "cores": 1, "kind": "reference",
+                                       "sample": f"{ns} scans through the reference integration loop on 1 thread "
+                                                 f"({dtc:.1f} s; order-dependent, single map); GPU map bit-identical: {same}"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
+    grid.close()
+    return out
 
 
 def run_b200(args, rank, world_size, local_rank):
@@ -209,9 +405,10 @@ def run_b200(args, rank, world_size, local_rank):
         return float(t.item())
 
     M = args.matches
-    dense, min_x, min_y, angles, ranges, inits = c2_workload(M, seed=1 + rank)
+    traj, map_scans, angles, ranges, inits = c2_workload(M, seed=1 + rank)
     ctx = capi.Context(local_rank)
-    grid = capi.Grid.from_dense(ctx, dense, min_x, min_y, 0.05, apron=32)
+    grid, _ = build_map_on_gpu(ctx, traj, angles, map_scans, apron=32)
+    dense, min_x, min_y = grid.download(), grid.min_x, grid.min_y
     coarse = grid.like()
     scans = capi.Scans([angles] * M, ranges, inits)
     batch = capi.RtcsmBatch(ctx, **C2)
@@ -277,6 +474,13 @@ def run_b200(args, rank, world_size, local_rank):
     assert all((a.found, a.ix, a.iy, a.it, a.score) == (b.found, b.ix, b.iy, b.it, b.score)
                for a, b in zip(results_dev, res_e2e))
 
+    extra = {}
+    if not args.no_extra:
+        extra["loop_detection"] = run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
+                                         args.submaps, max(3, min(args.steps, 10)),
+                                         world_size == 1 and not args.no_cpu_baseline)
+        if rank == 0:
+            extra["grid_integration"] = run_c3(ctx, 256, args.c3_scans, not args.no_cpu_baseline)
     if rank != 0:
         return
     # ---- CPU baseline: the unmodified reference on a bounded sample, parity-checked ------------
@@ -286,7 +490,7 @@ def run_b200(args, rank, world_size, local_rank):
             from oracle import refapi as R
             if R.available():
                 cores = os.cpu_count() or 1
-                ns = min(M, max(2 * cores, 16))
+                ns = min(M, max(16 * cores, 64))
                 dt, ref = ref_time_matches(dense, min_x, min_y, angles, ranges[:ns], inits[:ns], cores)
                 bad = sum((a.found, a.ix, a.iy, a.it, a.score) != (b.found, b.ix, b.iy, b.it, b.score)
                           for a, b in zip(ref, results_dev[:ns]))
@@ -322,6 +526,7 @@ def run_b200(args, rank, world_size, local_rank):
                              "roofline is not the binding limit; see DESIGN.md"},
         "kernel_ms": {"csm_project": k_proj, "csm_sweep": k_sweep, "csm_select": k_sel},
         "cpu_baseline": cpu,
+        "extra": extra,
     }
     print(json.dumps(line))
 
@@ -334,6 +539,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--matches", type=int, default=1000, help="matches per step (C2: 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C3 side measurements")
+    ap.add_argument("--submaps", type=int, default=500, help="C4: submaps per loop query batch")
+    ap.add_argument("--c3-scans", type=int, default=4096, help="C3: scans in the bounded sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))

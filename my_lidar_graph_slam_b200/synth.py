@@ -39,21 +39,42 @@ class World:
                 return False
         return True
 
+    def _lines(self):
+        """Group collinear wall pieces: {coordinate: sorted interval end points} per axis."""
+        if getattr(self, "_line_cache", None) is None:
+            out = []
+            for segs, fixed, lo, hi in ((self.horizontal, 1, 0, 2), (self.vertical, 0, 1, 3)):
+                groups = {}
+                for sg in segs:
+                    groups.setdefault(float(sg[fixed]), []).append((min(sg[lo], sg[hi]), max(sg[lo], sg[hi])))
+                lines = []
+                for coord, iv in sorted(groups.items()):
+                    iv.sort()
+                    merged = [list(iv[0])]
+                    for a, b in iv[1:]:
+                        if a <= merged[-1][1]:
+                            merged[-1][1] = max(merged[-1][1], b)
+                        else:
+                            merged.append([a, b])
+                    lines.append((coord, np.asarray(merged).reshape(-1)))
+                out.append(lines)
+            self._line_cache = out
+        return self._line_cache
+
     def cast(self, x: float, y: float, angles: np.ndarray) -> np.ndarray:
         """Distance to the first wall along each absolute angle."""
         c, s = np.cos(angles), np.sin(angles)
         best = np.full(angles.shape, 1e9)
+        hor, ver = self._lines()
         with np.errstate(divide="ignore", invalid="ignore"):
-            for seg in self.horizontal:       # y = seg[1], x in [min, max]
-                t = (seg[1] - y) / s
-                xi = x + t * c
-                ok = (t > 1e-9) & (xi >= min(seg[0], seg[2])) & (xi <= max(seg[0], seg[2]))
-                best = np.where(ok & (t < best), t, best)
-            for seg in self.vertical:         # x = seg[0], y in [min, max]
-                t = (seg[0] - x) / c
-                yi = y + t * s
-                ok = (t > 1e-9) & (yi >= min(seg[1], seg[3])) & (yi <= max(seg[1], seg[3]))
-                best = np.where(ok & (t < best), t, best)
+            for coord, ends in hor:           # wall pieces on the line y = coord
+                t = (coord - y) / s
+                inside = np.searchsorted(ends, x + t * c, side="right") % 2 == 1
+                best = np.where(inside & (t > 1e-9) & (t < best), t, best)
+            for coord, ends in ver:           # wall pieces on the line x = coord
+                t = (coord - x) / c
+                inside = np.searchsorted(ends, y + t * s, side="right") % 2 == 1
+                best = np.where(inside & (t > 1e-9) & (t < best), t, best)
         return best
 
 
