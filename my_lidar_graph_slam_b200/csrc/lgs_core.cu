@@ -124,7 +124,7 @@ int lgs_grid_destroy(lgs_grid* g) {
     if (!g) return LGS_OK;
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
-    if (g->d) cudaFree(g->d);
+    if (g->d && g->owns) cudaFree(g->d);
     delete g;
     return LGS_OK;
 }

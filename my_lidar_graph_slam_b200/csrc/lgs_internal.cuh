@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@ struct lgs_grid {
     int pitch = 0;        // nx + 2 * apron (cells)
     int rows = 0;         // ny + 2 * apron
     double min_x = 0, min_y = 0, res = 0;
+    bool owns = true;     // false for pyramid levels (views into the pyramid's slab)
     double* d = nullptr;  // rows * pitch doubles; cell (x, y) at d[(y + apron) * pitch + x + apron]
     __host__ __device__ const double* origin() const { return d + (size_t)apron * pitch + apron; }
     __host__ __device__ double* origin() { return d + (size_t)apron * pitch + apron; }

@@ -75,7 +75,8 @@ bool same_geometry(const lgs_grid* a, const lgs_grid* b) {
 
 struct lgs_pyramid {
     lgs_ctx* ctx = nullptr;
-    std::vector<lgs_grid*> levels;
+    double* slab = nullptr;             // all levels, contiguous
+    std::vector<lgs_grid*> levels;      // headers into the slab (owns == false)
 };
 
 const lgs_grid* lgs_pyramid_level(const lgs_pyramid* p, int level) {
@@ -109,10 +110,25 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
     LGS_CUDA(c, cudaSetDevice(c->device));
     lgs_pyramid* p = new lgs_pyramid();
     p->ctx = c;
+    // One slab for all levels (one cudaMalloc + one memset instead of one per level): every level
+    // is a grid header pointing into it, with the input's geometry and zero apron.
+    const size_t levelCells = (size_t)in->pitch * in->rows;
+    const size_t bytes = levelCells * (size_t)(heightMax + 1) * sizeof(double);
+    cudaError_t me = cudaMalloc(&p->slab, std::max<size_t>(bytes, 8));
+    if (me != cudaSuccess) {
+        delete p;
+        return lgs_fail(c, LGS_ERR_NOMEM, "pyramid: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(me));
+    }
+    me = cudaMemsetAsync(p->slab, 0, std::max<size_t>(bytes, 8), c->stream);
+    if (me != cudaSuccess) {
+        cudaFree(p->slab); delete p;
+        return lgs_fail(c, LGS_ERR_CUDA, "pyramid: memset -> %s", cudaGetErrorString(me));
+    }
     for (int h = 0; h <= heightMax; ++h) {
-        lgs_grid* g = nullptr;
-        const int rc = lgs_grid_create(c, in->nx, in->ny, in->min_x, in->min_y, in->res, in->apron, &g);
-        if (rc != LGS_OK) { lgs_pyramid_destroy(p); return rc; }
+        lgs_grid* g = new lgs_grid(*in);
+        g->ctx = c;
+        g->d = p->slab + levelCells * h;
+        g->owns = false;
         p->levels.push_back(g);
     }
     if (in->nx > 0 && in->ny > 0) {
@@ -144,7 +160,10 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
 
 int lgs_pyramid_destroy(lgs_pyramid* p) {
     if (!p) return LGS_OK;
-    for (lgs_grid* g : p->levels) lgs_grid_destroy(g);
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    for (lgs_grid* g : p->levels) delete g;
+    if (p->slab) cudaFree(p->slab);
     delete p;
     return LGS_OK;
 }
