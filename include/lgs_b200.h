@@ -106,6 +106,10 @@ typedef struct lgs_hit_batch {
 int lgs_grid_integrate_scans(lgs_ctx* ctx, lgs_grid* grid, const lgs_hit_batch* scans,
                              double p_hit, double p_miss, long long* n_updates);
 
+/* Diagnostics: cells (cumulative over this context) whose fast candidate search disagreed with
+ * the mark pass and were redone by the exhaustive exact path; expected to stay 0. */
+long long lgs_ctx_integrate_fallback_cells(const lgs_ctx* ctx);
+
 /* Host helpers (glibc arithmetic, no device work) for callers that do not link the reference:
  * range filter + HitPoint + bounding box of one scan; GridMap::Resize / Expand geometry. */
 typedef struct lgs_geometry {

@@ -414,6 +414,7 @@ SIGNATURES.update({
     "lgs_grid_clear": (C.c_int, [vp]),
     "lgs_grid_integrate_scans": (C.c_int, [vp, vp, C.POINTER(HitBatch), C.c_double, C.c_double,
                                            C.POINTER(C.c_longlong)]),
+    "lgs_ctx_integrate_fallback_cells": (C.c_longlong, [vp]),
     "lgs_scan_hit_points": (C.c_int, [c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double, c_dp,
                                       c_ip, c_dp]),
     "lgs_geometry_resize": (C.c_int, [C.POINTER(Geometry)] + [C.c_double] * 4 +

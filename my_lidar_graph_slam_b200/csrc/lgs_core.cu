@@ -55,6 +55,7 @@ int lgs_ctx_destroy(lgs_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     c->scratch.release();
+    if (c->integ) { c->integ->release(); delete c->integ; }
     delete c;
     return LGS_OK;
 }

@@ -200,80 +200,142 @@ integ_near_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ re
     }
 }
 
-// ---- main kernel: one thread owns one cell ---------------------------------------------------------
-__global__ void __launch_bounds__(256)
-integ_apply_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel,
-                   const float* __restrict__ beta, const unsigned short* __restrict__ nearTab,
-                   int nScans, GridRef g, int x0, int y0, int x1, int y1, double pHit, double pMiss,
-                   double oddsHit, double oddsMiss, unsigned long long* __restrict__ nUpdates) {
-    const int cx = x0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int cy = y0 + blockIdx.y * blockDim.y + threadIdx.y;
-    const bool inside = cx < x1 && cy < y1;
-    double v = 0.0;
-    double* cell = nullptr;
-    if (inside) { cell = g.origin + (size_t)cy * g.pitch + cx; v = *cell; }
-    const double v0 = v;
-    unsigned count = 0;
-    if (inside) {
-        for (int s = 0; s < nScans; ++s) {
-            const ScanMeta m = meta[s];
-            const int rx = cx - m.sx, ry = cy - m.sy;
-            const int cheb = max(abs(rx), abs(ry));
-            if (cheb > m.maxLen || m.n == 0) continue;
-            const int2* __restrict__ e = rel + m.beamBegin;
-            bool all = m.unsorted != 0;
-            if (cheb <= kNear) {
-                const unsigned short* t = nearTab + ((size_t)s * kNearW * kNearW + (ry + kNear) * kNearW + (rx + kNear)) * (kRuns + 1);
-                if (t[0] != kRleOverflow) {
-                    for (int k = 0; k < kRuns; ++k) {
-                        const unsigned short ent = t[k];
-                        if (ent == 0) break;
-                        const int cnt = ent & 0x7fff;
-                        const bool hit = (ent >> 15) != 0;
-                        count += cnt;
-                        for (int j = 0; j < cnt; ++j) {
-                            const double nv = hit ? bayesUpdate(v, pHit, oddsHit) : bayesUpdate(v, pMiss, oddsMiss);
-                            if (nv == v) break;        // fixed point: the rest of the run is a no-op
-                            v = nv;
-                        }
-                    }
-                    continue;
-                }
-                all = true;
-            }
-            if (all) {
-                for (int i = 0; i < m.n; ++i) {
-                    const int2 ee = __ldg(e + i);
-                    const int ty = rayTouch(rx, ry, ee.x, ee.y);
-                    if (ty) { v = ty == 2 ? bayesUpdate(v, pHit, oddsHit) : bayesUpdate(v, pMiss, oddsMiss); ++count; }
-                }
-                continue;
-            }
-            // far field: angular window of candidate beams
-            const float* __restrict__ bt = beta + m.beamBegin;
-            const float d = sqrtf((float)(rx * rx + ry * ry));
-            const float delta = 2.5f / d + 2e-3f;
-            const float bc = wrapBeta(atan2f((float)ry, (float)rx) - m.ang0);
-            const float bLast = __ldg(bt + m.n - 1);
-#pragma unroll 1
-            for (int w = -1; w <= 1; ++w) {
-                const float lo = bc + w * kTwoPi - delta, hi = bc + w * kTwoPi + delta;
-                if (hi < -0.01f || lo > bLast) continue;
-                int a = 0, b = m.n;                  // first i with beta[i] >= lo
-                while (a < b) {
-                    const int mid = (a + b) >> 1;
-                    if (__ldg(bt + mid) < lo) a = mid + 1; else b = mid;
-                }
-                for (int i = a; i < m.n && __ldg(bt + i) <= hi; ++i) {
-                    const int2 ee = __ldg(e + i);
-                    const int ty = rayTouch(rx, ry, ee.x, ee.y);
-                    if (ty) { v = ty == 2 ? bayesUpdate(v, pHit, oddsHit) : bayesUpdate(v, pMiss, oddsMiss); ++count; }
-                }
+// ---- mark pass: which scans touch which cells (idempotent, order free) -----------------------------
+// One thread per (scan, beam) walks the reference's Bresenham (util.hpp:257-303) and ORs the scan's
+// bit into every cell it touches; `expect` counts the touches so the owner can verify that its
+// candidate search found every one of them.
+__global__ void __launch_bounds__(128)
+integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
+                  int x0, int y0, int rw, unsigned long long* __restrict__ mask,
+                  unsigned* __restrict__ expect) {
+    const int s = blockIdx.y;
+    const ScanMeta m = meta[s];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.n) return;
+    const int2 e = __ldg(rel + m.beamBegin + i);
+    const unsigned long long bit = 1ull << s;
+    int x = m.sx, y = m.sy;
+    const int x1 = m.sx + e.x, y1 = m.sy + e.y;
+    const int sx = e.x < 0 ? -1 : 1, sy = e.y < 0 ? -1 : 1;
+    const int dx = abs(e.x * 2), dy = abs(e.y * 2);
+#define MARK() do { const size_t c = (size_t)(y - y0) * rw + (x - x0); atomicOr(mask + c, bit); atomicAdd(expect + c, 1u); } while (0)
+    MARK();
+    if (dx > dy) {
+        int err = dy - dx / 2;
+        while (x != x1) {
+            if (err >= 0) { y += sy; err -= dx; }
+            x += sx; err += dy;
+            MARK();
+        }
+    } else {
+        int err = dx - dy / 2;
+        while (y != y1) {
+            if (err >= 0) { x += sx; err -= dy; }
+            y += sy; err += dx;
+            MARK();
+        }
+    }
+#undef MARK
+}
+
+// ---- apply pass: one thread owns one cell ----------------------------------------------------------
+struct ApplyArgs {
+    const ScanMeta* meta;
+    const int2* rel;
+    const float* beta;
+    const unsigned short* nearTab;
+    const unsigned long long* mask;
+    const unsigned* expect;
+    double pHit, pMiss, oddsHit, oddsMiss;
+};
+
+// All touches of scan `s` on the cell at (rx, ry) from its sensor cell, in beam order, by testing
+// every beam (exact, slow): the fallback when the fast search cannot be used or disagrees.
+__device__ __forceinline__ double applyAllBeams(double v, const ScanMeta& m, const int2* __restrict__ e,
+                                                int rx, int ry, const ApplyArgs& a, unsigned& count) {
+    for (int i = 0; i < m.n; ++i) {
+        const int2 ee = __ldg(e + i);
+        const int ty = rayTouch(rx, ry, ee.x, ee.y);
+        if (ty) { v = ty == 2 ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss); ++count; }
+    }
+    return v;
+}
+
+__device__ __forceinline__ double applyScan(double v, int s, int cx, int cy, const ApplyArgs& a,
+                                            unsigned& count) {
+    const ScanMeta m = a.meta[s];
+    const int rx = cx - m.sx, ry = cy - m.sy;
+    const int cheb = max(abs(rx), abs(ry));
+    const int2* __restrict__ e = a.rel + m.beamBegin;
+    if (cheb <= kNear) {
+        const unsigned short* t = a.nearTab + ((size_t)s * kNearW * kNearW + (ry + kNear) * kNearW + (rx + kNear)) * (kRuns + 1);
+        if (t[0] == kRleOverflow) return applyAllBeams(v, m, e, rx, ry, a, count);
+        for (int k = 0; k < kRuns; ++k) {
+            const unsigned short ent = t[k];
+            if (ent == 0) break;
+            const int cnt = ent & 0x7fff;
+            const bool hit = (ent >> 15) != 0;
+            count += cnt;
+            for (int j = 0; j < cnt; ++j) {
+                const double nv = hit ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
+                if (nv == v) break;        // fixed point: the rest of the run is a no-op
+                v = nv;
             }
         }
-        if (v != v0) *cell = v;
+        return v;
     }
-    // block-level count of applied updates
+    if (m.unsorted) return applyAllBeams(v, m, e, rx, ry, a, count);
+    // far field: angular window of candidate beams
+    const float* __restrict__ bt = a.beta + m.beamBegin;
+    const float d = sqrtf((float)(rx * rx + ry * ry));
+    const float delta = 2.5f / d + 2e-3f;
+    const float bc = wrapBeta(atan2f((float)ry, (float)rx) - m.ang0);
+    const float bLast = __ldg(bt + m.n - 1);
+#pragma unroll 1
+    for (int w = -1; w <= 1; ++w) {
+        const float lo = bc + w * kTwoPi - delta, hi = bc + w * kTwoPi + delta;
+        if (hi < -0.01f || lo > bLast) continue;
+        int lb = 0, ub = m.n;                  // first i with beta[i] >= lo
+        while (lb < ub) {
+            const int mid = (lb + ub) >> 1;
+            if (__ldg(bt + mid) < lo) lb = mid + 1; else ub = mid;
+        }
+        for (int i = lb; i < m.n && __ldg(bt + i) <= hi; ++i) {
+            const int2 ee = __ldg(e + i);
+            const int ty = rayTouch(rx, ry, ee.x, ee.y);
+            if (ty) { v = ty == 2 ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss); ++count; }
+        }
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+integ_apply_kernel(ApplyArgs a, GridRef g, int x0, int y0, int x1, int y1,
+                   unsigned long long* __restrict__ counters /* [0] updates, [1] fallback cells */) {
+    const int cx = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    unsigned count = 0;
+    if (cx < x1 && cy < y1) {
+        const size_t ridx = (size_t)(cy - y0) * (x1 - x0) + (cx - x0);
+        unsigned long long mk = a.mask[ridx];
+        if (mk) {
+            double* cell = g.origin + (size_t)cy * g.pitch + cx;
+            const double v0 = *cell;
+            double v = v0;
+            for (unsigned long long r = mk; r; r &= r - 1) v = applyScan(v, __ffsll((long long)r) - 1, cx, cy, a, count);
+            if (count != a.expect[ridx]) {
+                // The fast search disagrees with the mark pass: redo this cell the slow, exact way.
+                v = v0; count = 0;
+                for (unsigned long long r = mk; r; r &= r - 1) {
+                    const int s = __ffsll((long long)r) - 1;
+                    const ScanMeta m = a.meta[s];
+                    v = applyAllBeams(v, m, a.rel + m.beamBegin, cx - m.sx, cy - m.sy, a, count);
+                }
+                atomicAdd(counters + 1, 1ull);
+            }
+            if (v != v0) *cell = v;
+        }
+    }
     __shared__ unsigned sCount[8];
     unsigned c = count;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
@@ -283,7 +345,7 @@ integ_apply_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ r
     if (tid == 0) {
         unsigned long long tot = 0;
         for (int k = 0; k < (int)(blockDim.x * blockDim.y + 31) / 32; ++k) tot += sCount[k];
-        if (tot) atomicAdd(nUpdates, tot);
+        if (tot) atomicAdd(counters, tot);
     }
 }
 
@@ -314,85 +376,88 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     const long long total = scans->hit_begin[n];
     if (total > 0 && !scans->hit_xy) return lgs_fail(c, LGS_ERR_INVALID, "integrate: hit_xy is NULL");
     LGS_CUDA(c, cudaSetDevice(c->device));
+    if (!c->integ) c->integ = new lgs_integ_ws();
+    lgs_integ_ws& w = *c->integ;
+
+    // Stage the whole batch once; the kernels then run in sub-batches of <= 64 scans (one mask bit each).
+    LGS_CUDA(c, w.sensor.reserve((size_t)n * 2));
+    LGS_CUDA(c, w.hit.reserve(std::max<size_t>((size_t)total, 1) * 2));
+    LGS_CUDA(c, w.begin.reserve((size_t)n + 1));
+    LGS_CUDA(c, w.meta.reserve((size_t)n * sizeof(ScanMeta)));
+    LGS_CUDA(c, w.rel.reserve(std::max<size_t>((size_t)total, 1)));
+    LGS_CUDA(c, w.beta.reserve(std::max<size_t>((size_t)total, 1)));
+    LGS_CUDA(c, w.nearTab.reserve((size_t)std::min(n, 64) * kNearW * kNearW * (kRuns + 1)));
+    LGS_CUDA(c, w.counters.reserve(2));
+    LGS_CUDA(c, w.hMeta.reserve((size_t)n * sizeof(ScanMeta)));
+    LGS_CUDA(c, w.hCounters.reserve(2));
+    LGS_CUDA(c, cudaMemcpyAsync(w.sensor.p, scans->sensor_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (total)
+        LGS_CUDA(c, cudaMemcpyAsync(w.hit.p, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(w.begin.p, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemsetAsync(w.counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+
     int maxBeams = 0;
     for (int s = 0; s < n; ++s) maxBeams = std::max(maxBeams, scans->hit_begin[s + 1] - scans->hit_begin[s]);
-
-    // Device staging (freed at the end; integration is called per batch of scans).
-    double *dSensor = nullptr, *dHit = nullptr;
-    int* dBegin = nullptr;
-    ScanMeta* dMeta = nullptr;
-    int2* dRel = nullptr;
-    float* dBeta = nullptr;
-    unsigned short* dNear = nullptr;
-    unsigned long long* dCount = nullptr;
-    const size_t nearEntries = (size_t)n * kNearW * kNearW * (kRuns + 1);
-    auto freeAll = [&]() {
-        cudaFree(dSensor); cudaFree(dHit); cudaFree(dBegin); cudaFree(dMeta); cudaFree(dRel);
-        cudaFree(dBeta); cudaFree(dNear); cudaFree(dCount);
-    };
-#define INTEG_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeAll(); \
-        return lgs_fail(c, LGS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } } while (0)
-    INTEG_CUDA(cudaMalloc(&dSensor, (size_t)n * 2 * sizeof(double)));
-    INTEG_CUDA(cudaMalloc(&dHit, std::max<size_t>((size_t)total, 1) * 2 * sizeof(double)));
-    INTEG_CUDA(cudaMalloc(&dBegin, (size_t)(n + 1) * sizeof(int)));
-    INTEG_CUDA(cudaMalloc(&dMeta, (size_t)n * sizeof(ScanMeta)));
-    INTEG_CUDA(cudaMalloc(&dRel, std::max<size_t>((size_t)total, 1) * sizeof(int2)));
-    INTEG_CUDA(cudaMalloc(&dBeta, std::max<size_t>((size_t)total, 1) * sizeof(float)));
-    INTEG_CUDA(cudaMalloc(&dNear, nearEntries * sizeof(unsigned short)));
-    INTEG_CUDA(cudaMalloc(&dCount, sizeof(unsigned long long)));
-    INTEG_CUDA(cudaMemcpyAsync(dSensor, scans->sensor_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (total)
-        INTEG_CUDA(cudaMemcpyAsync(dHit, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    INTEG_CUDA(cudaMemcpyAsync(dBegin, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    INTEG_CUDA(cudaMemsetAsync(dCount, 0, sizeof(unsigned long long), c->stream));
-
+    ScanMeta* dMeta = reinterpret_cast<ScanMeta*>(w.meta.p);
+    ScanMeta* hMeta = reinterpret_cast<ScanMeta*>(w.hMeta.p);
     GridRef g{grid->origin(), grid->nx, grid->ny, grid->pitch, grid->min_x, grid->min_y, grid->res};
-    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(dSensor, dBegin, dHit, n, g, dMeta);
-    c->launches++;
+    // Pre-pass over the whole batch: sensor cells, relative end cells, beam angles, sortedness.
+    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(w.sensor.p, w.begin.p, w.hit.p, n, g, dMeta);
+    LGS_LAUNCH_CHECK(c);
     if (maxBeams > 0) {
         dim3 gb((maxBeams + 127) / 128, n);
-        integ_beam_kernel<<<gb, 128, 0, c->stream>>>(dSensor, dHit, n, g, dMeta, dRel, dBeta);
-        integ_sorted_kernel<<<gb, 128, 0, c->stream>>>(dMeta, dBeta);
-        const long long warps = (long long)n * kNearW * kNearW;
-        integ_near_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(dMeta, dRel, n, dNear);
-        c->launches += 3;
+        integ_beam_kernel<<<gb, 128, 0, c->stream>>>(w.sensor.p, w.hit.p, n, g, dMeta, w.rel.p, w.beta.p);
+        LGS_LAUNCH_CHECK(c);
+        integ_sorted_kernel<<<gb, 128, 0, c->stream>>>(dMeta, w.beta.p);
+        LGS_LAUNCH_CHECK(c);
     }
-    INTEG_CUDA(cudaGetLastError());
-    // The apply kernel's extent needs the scans' reach: read the metadata back (small).
-    std::vector<ScanMeta> meta(n);
-    INTEG_CUDA(cudaMemcpyAsync(meta.data(), dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, c->stream));
-    INTEG_CUDA(cudaStreamSynchronize(c->stream));
-    int x0 = grid->nx, y0 = grid->ny, x1 = 0, y1 = 0;
-    for (int s = 0; s < n; ++s) {
-        if (meta[s].bad) {
-            freeAll();
+    LGS_CUDA(c, cudaMemcpyAsync(hMeta, dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < n; ++s)
+        if (hMeta[s].bad)
             return lgs_fail(c, LGS_ERR_INVALID, "integrate: scan %d touches cells outside the %dx%d grid "
                             "(expand the map first, as GridMap::Expand does)", s, grid->nx, grid->ny);
+
+    // ValueToOdds(prob) for the two observations (binary_bayes_grid_cell.hpp:104-113), host IEEE.
+    auto clampP = [](double v) { const double lo = 1e-3, hi = 1.0 - 1e-3; return v < lo ? lo : (hi < v ? hi : v); };
+    const double oddsHit = clampP(pHit) / (1.0 - clampP(pHit));
+    const double oddsMiss = clampP(pMiss) / (1.0 - clampP(pMiss));
+
+    for (int s0 = 0; s0 < n; s0 += 64) {
+        const int ns = std::min(64, n - s0);
+        int x0 = grid->nx, y0 = grid->ny, x1 = 0, y1 = 0, subBeams = 0;
+        for (int s = s0; s < s0 + ns; ++s) {
+            if (hMeta[s].n == 0) continue;
+            subBeams = std::max(subBeams, hMeta[s].n);
+            x0 = std::min(x0, hMeta[s].sx - hMeta[s].maxLen); x1 = std::max(x1, hMeta[s].sx + hMeta[s].maxLen + 1);
+            y0 = std::min(y0, hMeta[s].sy - hMeta[s].maxLen); y1 = std::max(y1, hMeta[s].sy + hMeta[s].maxLen + 1);
         }
-        if (meta[s].n == 0) continue;
-        x0 = std::min(x0, meta[s].sx - meta[s].maxLen); x1 = std::max(x1, meta[s].sx + meta[s].maxLen + 1);
-        y0 = std::min(y0, meta[s].sy - meta[s].maxLen); y1 = std::max(y1, meta[s].sy + meta[s].maxLen + 1);
-    }
-    x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, grid->nx); y1 = std::min(y1, grid->ny);
-    if (x1 > x0 && y1 > y0) {
-        // ValueToOdds(prob) for the two observations (binary_bayes_grid_cell.hpp:104-113), host IEEE.
-        auto clampP = [](double v) { const double lo = 1e-3, hi = 1.0 - 1e-3; return v < lo ? lo : (hi < v ? hi : v); };
-        const double oddsHit = clampP(pHit) / (1.0 - clampP(pHit));
-        const double oddsMiss = clampP(pMiss) / (1.0 - clampP(pMiss));
+        x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, grid->nx); y1 = std::min(y1, grid->ny);
+        if (subBeams == 0 || x1 <= x0 || y1 <= y0) continue;
+        const size_t region = (size_t)(x1 - x0) * (y1 - y0);
+        LGS_CUDA(c, w.mask.reserve(region));
+        LGS_CUDA(c, w.expect.reserve(region));
+        LGS_CUDA(c, cudaMemsetAsync(w.mask.p, 0, region * sizeof(unsigned long long), c->stream));
+        LGS_CUDA(c, cudaMemsetAsync(w.expect.p, 0, region * sizeof(unsigned), c->stream));
+        dim3 gm((subBeams + 127) / 128, ns);
+        integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p, w.expect.p);
+        LGS_LAUNCH_CHECK(c);
+        const long long warps = (long long)ns * kNearW * kNearW;
+        integ_near_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, w.nearTab.p);
+        LGS_LAUNCH_CHECK(c);
+        ApplyArgs a{dMeta + s0, w.rel.p, w.beta.p, w.nearTab.p, w.mask.p, w.expect.p, pHit, pMiss, oddsHit, oddsMiss};
         dim3 block(32, 8), gridDim((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
-        integ_apply_kernel<<<gridDim, block, 0, c->stream>>>(dMeta, dRel, dBeta, dNear, n, g, x0, y0, x1, y1,
-                                                             pHit, pMiss, oddsHit, oddsMiss, dCount);
-        c->launches++;
-        INTEG_CUDA(cudaGetLastError());
+        integ_apply_kernel<<<gridDim, block, 0, c->stream>>>(a, g, x0, y0, x1, y1, w.counters.p);
+        LGS_LAUNCH_CHECK(c);
     }
-    unsigned long long cnt = 0;
-    INTEG_CUDA(cudaMemcpyAsync(&cnt, dCount, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
-    INTEG_CUDA(cudaStreamSynchronize(c->stream));
-    if (nUpdatesOut) *nUpdatesOut = (long long)cnt;
-    freeAll();
-#undef INTEG_CUDA
+    LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (nUpdatesOut) *nUpdatesOut = (long long)w.hCounters.p[0];
+    w.fallbackCells += (long long)w.hCounters.p[1];
     return LGS_OK;
 }
+
+long long lgs_ctx_integrate_fallback_cells(const lgs_ctx* c) { return (c && c->integ) ? c->integ->fallbackCells : 0; }
 
 int lgs_grid_resize(lgs_grid* g, int nx, int ny, double minX, double minY, int shiftX, int shiftY) {
     if (!g) return LGS_ERR_INVALID;

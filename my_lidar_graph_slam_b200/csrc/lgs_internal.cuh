@@ -71,6 +71,26 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// Persistent scratch of lgs_grid_integrate_scans (grown on demand, freed with the context).
+struct lgs_integ_ws {
+    DevBuf<double> sensor, hit;
+    DevBuf<int> begin;
+    DevBuf<char> meta;
+    DevBuf<int2> rel;
+    DevBuf<float> beta;
+    DevBuf<unsigned short> nearTab;
+    DevBuf<unsigned long long> mask, counters;
+    DevBuf<unsigned> expect;
+    PinBuf<char> hMeta;
+    PinBuf<unsigned long long> hCounters;
+    long long fallbackCells = 0;
+    void release() {
+        sensor.release(); hit.release(); begin.release(); meta.release(); rel.release(); beta.release();
+        nearTab.release(); mask.release(); counters.release(); expect.release(); hMeta.release();
+        hCounters.release();
+    }
+};
+
 struct lgs_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -79,6 +99,7 @@ struct lgs_ctx {
     long long launches = 0;
     char err[512] = {0};
     DevBuf<double> scratch;   // reusable device scratch (precompute intermediate)
+    lgs_integ_ws* integ = nullptr;
 };
 
 // Fractional-cell guard band (in cells): a projected coordinate closer than this to a cell

@@ -111,3 +111,19 @@ def test_integrate_rejects_cells_outside_grid_and_handles_empty(ctx):
     with pytest.raises(capi.LgsError, match="outside"):
         capi.integrate_scans(ctx, grid, [[1.0, 1.0]], [np.array([[5.0, 1.0]])])
     assert not grid.download().any()
+
+
+def test_fast_candidate_search_never_needs_the_exhaustive_fallback(ctx):
+    """The mark pass counts every touch; a cell whose angular-window search finds a different
+    number is redone exhaustively and counted.  On real scan geometry that must never happen."""
+    angles, traj, scans = _scene(seed=9, n=24)
+    geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
+    hits = []
+    for p, r in zip(traj, scans):
+        h, bbox = capi.scan_hit_points(p, angles, r, 0.02, 20.0)
+        geo, _, _, _ = capi.geometry_expand(geo, bbox)
+        hits.append(h)
+    grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
+    before = capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h)
+    assert capi.integrate_scans(ctx, grid, traj[:, :2], hits) > 24 * 50_000
+    assert capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h) == before
