@@ -52,6 +52,8 @@ struct CsmWindow {           // identical for every match of a batch (depends on
     int lowRes;
     int tilesFine, tilesCoarse;   // thread blocks per theta
     int block;               // threads per block
+    int hpt;                 // fine hypotheses per thread (1 or 4)
+    int slots;               // thread slots per theta = ceil(nHyp / hpt) rounded up to a warp
 };
 
 struct GridGeom {
@@ -117,8 +119,8 @@ __global__ void csm_project_kernel(const CsmDesc* __restrict__ descs,
 // offsets are staged in shared memory; each thread sums grid[base + off[i]] in beam order.
 // Lanes are consecutive x offsets so a warp's gathers for one beam fall in 1-3 cache lines.
 // scan_matcher_real_time_correlative.cpp:98-102 (coarse), :207-224, :239-244 (fine).
-template <int UNROLL>
-__global__ void __launch_bounds__(512)
+template <int UNROLL, int HPT>
+__global__ void __launch_bounds__(256)
 csm_sweep_kernel(const CsmDesc* __restrict__ descs, const double* __restrict__ fineGrid,
                  const double* __restrict__ coarseGrid, int pitch, CsmWindow w,
                  const int* __restrict__ offs, double* __restrict__ fineTab,
@@ -133,32 +135,67 @@ csm_sweep_kernel(const CsmDesc* __restrict__ descs, const double* __restrict__ f
         for (int k = threadIdx.x; k < d.nKeptPad / 4; k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
-
-    const bool isCoarse = blockIdx.x >= (unsigned)w.tilesFine;
-    const int tile = isCoarse ? blockIdx.x - w.tilesFine : blockIdx.x;
-    const int h = tile * blockDim.x + threadIdx.x;
-    const int nxh = isCoarse ? w.nbx : w.nxw;
-    const int nyh = isCoarse ? w.nby : w.nyw;
-    if (h >= nxh * nyh) return;
-    const int oy = h / nxh, ox = h - oy * nxh;
-    const int stride = isCoarse ? w.lowRes : 1;
-    const int baseOff = (-w.winY + oy * stride) * pitch + (-w.winX + ox * stride);
-    const double* __restrict__ gp = (isCoarse ? coarseGrid : fineGrid) + baseOff;
-
-    double acc = 0.0;
     const int n = d.nKeptPad;   // multiple of kBeamPad >= UNROLL
+
+    if (blockIdx.x >= (unsigned)w.tilesFine) {
+        // Coarse hypotheses (stride lowRes on the win-max map), one per thread.
+        const int h = (blockIdx.x - w.tilesFine) * blockDim.x + threadIdx.x;
+        if (h >= w.nbx * w.nby) return;
+        const int oy = h / w.nbx, ox = h - oy * w.nbx;
+        const double* __restrict__ gp =
+            coarseGrid + (-w.winY + oy * w.lowRes) * pitch + (-w.winX + ox * w.lowRes);
+        double acc = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < n; i += UNROLL) {
+            double v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(gp + sOff[i + u]);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) acc = __dadd_rn(acc, v[u]);
+        }
+        // stored in the CPU's visit order: x outer, y inner
+        coarseTab[d.coarseBegin + ((long long)t * w.nbx + ox) * w.nby + oy] = acc;
+        return;
+    }
+
+    // Fine hypotheses: thread slot j owns hypotheses j, j + S, ..., j + (HPT-1) S of the flattened
+    // (y, x) window, so one shared-memory offset load feeds HPT gathers and a warp's lanes stay
+    // on consecutive x cells for every one of them.
+    const int nHyp = w.nxw * w.nyw;
+    const int S = w.slots;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    const double* __restrict__ gp[HPT];
+    double acc[HPT];
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {
+        const int h = min(j + k * S, nHyp - 1);          // out-of-range slots alias the last one
+        const int oy = h / w.nxw, ox = h - oy * w.nxw;
+        gp[k] = fineGrid + (-w.winY + oy) * pitch + (-w.winX + ox);
+        acc[k] = 0.0;
+    }
 #pragma unroll 1
     for (int i = 0; i < n; i += UNROLL) {
-        double v[UNROLL];
+        double v[UNROLL][HPT];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(gp + sOff[i + u]);
+        for (int u = 0; u < UNROLL; ++u) {
+            const int o = sOff[i + u];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) acc = __dadd_rn(acc, v[u]);   // beam order, like the CPU
+            for (int k = 0; k < HPT; ++k) v[u][k] = __ldg(gp[k] + o);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) acc[k] = __dadd_rn(acc[k], v[u][k]);   // beam order, like the CPU
     }
-    if (isCoarse)   // stored in the CPU's visit order: x outer, y inner
-        coarseTab[d.coarseBegin + ((long long)t * w.nbx + ox) * w.nby + oy] = acc;
-    else
-        fineTab[d.fineBegin + ((long long)t * w.nyw + oy) * w.nxw + ox] = acc;
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {
+        const int h = j + k * S;
+        if (h < nHyp) {
+            const int oy = h / w.nxw, ox = h - oy * w.nxw;
+            fineTab[d.fineBegin + ((long long)t * w.nyw + oy) * w.nxw + ox] = acc[k];
+        }
+    }
 }
 
 // ---- K3: block maxima + CPU-order selection -----------------------------------------------------
@@ -317,9 +354,14 @@ static int csm_launch_sweep(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_
         const int nm = std::min(65535, b->nMatch - m0);
         dim3 gridDim(w.tilesFine + w.tilesCoarse, b->maxNT, nm);
         const size_t smem = (size_t)b->maxKeptPad * sizeof(int);
-        csm_sweep_kernel<kBeamPad><<<gridDim, w.block, smem, c->stream>>>(
-            b->dDescs.p + m0, grid->origin(), coarse->origin(), grid->pitch, w, b->dOffs.p,
-            b->dFine.p, b->dCoarse.p);
+        if (w.hpt == 4)
+            csm_sweep_kernel<4, 4><<<gridDim, w.block, smem, c->stream>>>(
+                b->dDescs.p + m0, grid->origin(), coarse->origin(), grid->pitch, w, b->dOffs.p,
+                b->dFine.p, b->dCoarse.p);
+        else
+            csm_sweep_kernel<kBeamPad, 1><<<gridDim, w.block, smem, c->stream>>>(
+                b->dDescs.p + m0, grid->origin(), coarse->origin(), grid->pitch, w, b->dOffs.p,
+                b->dFine.p, b->dCoarse.p);
         LGS_LAUNCH_CHECK(c);
     }
     return LGS_OK;
@@ -391,8 +433,10 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     if (std::max(w.nxw, w.nyw) > grid->apron)
         return lgs_fail(c, LGS_ERR_APRON, "rtcsm: window %dx%d cells needs apron >= %d, grid has %d",
                         w.nxw, w.nyw, std::max(w.nxw, w.nyw), grid->apron);
-    w.block = pick_block(w.nxw * w.nyw);
-    w.tilesFine = (w.nxw * w.nyw + w.block - 1) / w.block;
+    w.hpt = (w.nxw * w.nyw >= 512) ? 4 : 1;
+    w.slots = (((w.nxw * w.nyw + w.hpt - 1) / w.hpt) + 31) / 32 * 32;
+    w.block = pick_block(w.slots);
+    w.tilesFine = (w.slots + w.block - 1) / w.block;
     w.tilesCoarse = (w.nbx * w.nby + w.block - 1) / w.block;
     b->geom = GridGeom{grid->min_x, grid->min_y, grid->res, grid->nx, grid->ny, grid->pitch};
 
@@ -479,9 +523,14 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
                                     cudaMemcpyHostToDevice, c->stream));
     }
     if ((size_t)b->maxKeptPad * sizeof(int) > 48 * 1024)
-        LGS_CUDA(c, cudaFuncSetAttribute(csm_sweep_kernel<kBeamPad>,
+    {
+        LGS_CUDA(c, cudaFuncSetAttribute(csm_sweep_kernel<kBeamPad, 1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          b->maxKeptPad * (int)sizeof(int)));
+        LGS_CUDA(c, cudaFuncSetAttribute(csm_sweep_kernel<4, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         b->maxKeptPad * (int)sizeof(int)));
+    }
     b->uploaded = true;
     return LGS_OK;
 }
