@@ -246,12 +246,13 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
     scan = synth.make_scan(world, truth, angles, qrng)
     init = truth + np.array([0.4, -0.3, 0.1])
     nq = len(mine)
-    scans = capi.Scans([angles] * nq, [scan] * nq, [init] * nq, range_min=0.02, range_max=30.0)
+    scans = capi.Scans([angles], [scan], [init], range_min=0.02, range_max=30.0)   # ONE query scan
+    pair_scan = np.zeros(nq, dtype=np.int32)
     batch = capi.BbBatch(ctx, **BB)
     dev = f"cuda:{local_rank}" if world_size > 1 else None
 
     def step():
-        batch.upload(scans, pyramids, 0.6)
+        batch.upload_pairs(scans, pair_scan, pyramids, 0.6)
         batch.run()
         res = batch.results()
         return sharding.all_gather_records(sharding.pack(res, mine), n_submaps, rank, world_size, dev)
@@ -266,7 +267,7 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
     ctx.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     # kernels only (scan + pyramids resident)
-    batch.upload(scans, pyramids, 0.6)
+    batch.upload_pairs(scans, pair_scan, pyramids, 0.6)
     barrier()
     ctx.timer_start()
     for _ in range(steps):

@@ -213,6 +213,11 @@ int lgs_bb_batch_destroy(lgs_bb_batch* b);
  * repeat); norm_threshold[q] as for the correlative matcher. */
 int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans,
                         lgs_pyramid* const* pyramids, const double* norm_threshold);
+/* Same, for scans shared by several queries: pair q matches scans[pair_scan[q]] against
+ * pyramids[q]; the scan is projected once (config C4: 1 scan x 500 submaps). */
+int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int n_pairs,
+                              const int* pair_scan, lgs_pyramid* const* pyramids,
+                              const double* norm_threshold);
 int lgs_bb_batch_run(lgs_bb_batch* b);
 int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out);
 /* Nodes scored per tree level (index = height) and gathered cells during the last run. */

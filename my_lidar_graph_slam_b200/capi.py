@@ -88,6 +88,7 @@ SIGNATURES = {
     "lgs_bb_batch_create": (C.c_int, [vp, C.POINTER(BbParams), C.POINTER(vp)]),
     "lgs_bb_batch_destroy": (C.c_int, [vp]),
     "lgs_bb_batch_upload": (C.c_int, [vp, C.POINTER(ScanBatch), C.POINTER(vp), c_dp]),
+    "lgs_bb_batch_upload_pairs": (C.c_int, [vp, C.POINTER(ScanBatch), C.c_int, c_ip, C.POINTER(vp), c_dp]),
     "lgs_bb_batch_run": (C.c_int, [vp]),
     "lgs_bb_batch_results": (C.c_int, [vp, C.POINTER(MatchResult)]),
     "lgs_bb_batch_work": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int,
@@ -362,6 +363,22 @@ class BbBatch:
             thr = _dptr(self._thr)
         self.ctx.check(lib().lgs_bb_batch_upload(self.h, C.byref(scans.c), self._pyr, thr))
         self.n = scans.n
+
+    def upload_pairs(self, scans: Scans, pair_scan, pyramids, norm_threshold=0.6):
+        """Pair q = (scans[pair_scan[q]], pyramids[q]); shared scans are projected once."""
+        n = len(pyramids)
+        self._pairs = np.ascontiguousarray(pair_scan, dtype=np.int32)
+        assert len(self._pairs) == n
+        self._pyr = (vp * max(n, 1))(*[p.h for p in pyramids])
+        self._keep = (scans, list(pyramids))
+        thr = None
+        if norm_threshold is not None:
+            self._thr = np.ascontiguousarray(np.broadcast_to(
+                np.asarray(norm_threshold, dtype=np.float64), (n,)))
+            thr = _dptr(self._thr)
+        self.ctx.check(lib().lgs_bb_batch_upload_pairs(self.h, C.byref(scans.c), n,
+                                                       self._pairs.ctypes.data_as(c_ip), self._pyr, thr))
+        self.n = n
 
     def run(self):
         self.ctx.check(lib().lgs_bb_batch_run(self.h))

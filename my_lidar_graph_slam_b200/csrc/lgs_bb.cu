@@ -26,7 +26,7 @@
 // per node and beam.  In exact arithmetic that is I0 + nx with I0 the index at nx = 0; all
 // rounding errors together stay below 1e-11 cells, so I0 + nx is exact unless the fractional
 // cell coordinate lies within the guard band of an edge.  Such (theta, beam) pairs are flagged
-// by bb_project_kernel and get per-offset index tables computed on the host with the CPU's
+// by bb_index_kernel and get per-offset index tables computed on the host with the CPU's
 // own expression (and glibc sin/cos, H5).
 #include <cfloat>
 #include <cmath>
@@ -35,30 +35,39 @@
 
 namespace {
 
-constexpr int kBeamPadBB = 4;
 constexpr int kFlagCapBB = 1 << 16;
 constexpr int kMaxLevels = 21;
+constexpr int kWarpPerNodeBelow = 0;        // levels with fewer nodes score one warp per node (off: slower)
+constexpr int kDeepUnrollBelow = 1 << 30;  // levels with fewer nodes keep 32 instead of 16 beams in flight (measured: always better)
+
+struct BbScan {                     // one per DISTINCT (scan, sensor pose): hit points are map independent
+    double sx, sy, st, stepT;
+    int winT, nT, nTpad;            // theta slices, padded to a multiple of 4
+    int nUse, beamBegin;            // usable beams (ScorePixelAccurate range filter)
+    int pad;
+    long long hitBegin;             // into hits: nUse * nTpad (double2), beam-major
+};
 
 struct BbQuery {
-    double sx, sy, st, stepT;
     double thrAbs;
-    double minX, minY, res;
+    double minX, minY, res, invRes;
     int nx, ny, pitch;              // submap geometry
-    int winX, winY, winT, nT;
+    int winX, winY, winT, nT, nTpad;
     int nrx, nry;                   // roots per axis
-    int nUse, nUsePad, beamBegin;   // usable beams
+    int nUse, scan;                 // usable beams, index of the distinct scan
     int rootBegin;                  // first root of this query in the level-H pool
-    long long tabBegin;             // into base-index table: nT * nUsePad int2
+    long long tabBegin;             // into the base-index table: nUse * nTpad int2, beam-major
     const double* level[kMaxLevels];// origin() of every pyramid level
 };
 
 struct Node {            // 32 bytes
-    int x, y;            // window offsets of the node's lower-left corner
+    short x, y;          // window offsets of the node's lower-left corner
     int t;               // theta index 0..nT-1
     int q;               // query
-    long long rank;      // CPU visit order among nodes of the same height (lower = earlier)
     int parent;          // index in the pool one level up (-1 for roots)
-    int childBase;       // first of 4 children (visit order) one level down, -1 if pruned
+    int childBase;       // child c (visit order) lives at childBase + c * childStride, -1 if pruned
+    int childStride;
+    long long rank;      // CPU visit order among nodes of the same height (lower = earlier)
 };
 
 struct BbBest {          // per query
@@ -76,30 +85,43 @@ struct BbResult {
 
 struct BbFlag { int q, t, i; };
 
-// ---- projection: base cell index of every (query, theta, usable beam) at node offset (0, 0) ----
-__global__ void bb_project_kernel(const BbQuery* __restrict__ qs, const double* __restrict__ angles,
-                                  const double* __restrict__ ranges, double eps,
-                                  int2* __restrict__ tab, BbFlag* __restrict__ flags,
-                                  int* __restrict__ flagCount) {
-    const BbQuery& d = qs[blockIdx.y];
+// ---- stage A: world hit point of every (distinct scan, usable beam, theta) at node offset (0, 0) ----
+// Threads are theta-fastest so neighbouring lanes differ by one angular step: their hit points are
+// a fraction of a cell apart, which keeps every later table read and map gather coalesced.
+__global__ void bb_hit_kernel(const BbScan* __restrict__ scans, const double* __restrict__ angles,
+                              const double* __restrict__ ranges, double2* __restrict__ hits) {
+    const BbScan& u = scans[blockIdx.y];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)d.nT * d.nUsePad) return;
-    const int t = (int)(idx / d.nUsePad);
-    const int i = (int)(idx - (long long)t * d.nUsePad);
-    if (i >= d.nUse) {   // padding beam: far outside every map -> reads the zero apron
-        tab[d.tabBegin + idx] = make_int2(-(1 << 28), -(1 << 28));
-        return;
-    }
+    if (idx >= (long long)u.nUse * u.nTpad) return;
+    const int i = (int)(idx / u.nTpad);
+    const int t = (int)(idx - (long long)i * u.nTpad);
+    if (t >= u.nT) { hits[u.hitBegin + idx] = make_double2(0.0, 0.0); return; }
     // nodePose.mTheta = sensorPose.mTheta + node.mTheta * stepTheta  (scan_matcher_branch_bound.cpp:96-99)
-    const double theta = __dadd_rn(d.st, __dmul_rn((double)(t - d.winT), d.stepT));
-    const double a = __dadd_rn(theta, angles[d.beamBegin + i]);
+    const double theta = __dadd_rn(u.st, __dmul_rn((double)(t - u.winT), u.stepT));
+    const double a = __dadd_rn(theta, angles[u.beamBegin + i]);
     double s, c;
     sincos(a, &s, &c);
-    const double r = ranges[d.beamBegin + i];
-    const double hx = __dadd_rn(d.sx, __dmul_rn(r, c));          // sensor_data.hpp:171-172
-    const double hy = __dadd_rn(d.sy, __dmul_rn(r, s));
-    const double qx = __ddiv_rn(__dsub_rn(hx, d.minX), d.res);    // grid_map.hpp:784-787
-    const double qy = __ddiv_rn(__dsub_rn(hy, d.minY), d.res);
+    const double r = ranges[u.beamBegin + i];
+    hits[u.hitBegin + idx] = make_double2(__dadd_rn(u.sx, __dmul_rn(r, c)),      // sensor_data.hpp:171-172
+                                          __dadd_rn(u.sy, __dmul_rn(r, s)));
+}
+
+// ---- stage B: base cell index in the query's submap + near-edge flags -----------------------------
+__global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
+                                const double2* __restrict__ hits, double eps, int2* __restrict__ tab,
+                                BbFlag* __restrict__ flags, int* __restrict__ flagCount) {
+    const BbQuery& d = qs[blockIdx.y];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)d.nUse * d.nTpad) return;
+    const int i = (int)(idx / d.nTpad);
+    const int t = (int)(idx - (long long)i * d.nTpad);
+    if (t >= d.nT) { tab[d.tabBegin + idx] = make_int2(-(1 << 28), -(1 << 28)); return; }
+    const double2 h = hits[scans[d.scan].hitBegin + idx];
+    // grid_map.hpp:784-787 divides by the resolution; multiplying by its reciprocal differs from
+    // that by < 1e-12 cells, far inside the guard band, so floor() agrees for every unflagged
+    // point and flagged ones are re-derived on the host with the real division anyway.
+    const double qx = __dmul_rn(__dsub_rn(h.x, d.minX), d.invRes);
+    const double qy = __dmul_rn(__dsub_rn(h.y, d.minY), d.invRes);
     const double fx = floor(qx), fy = floor(qy);
     const double rx = qx - fx, ry = qy - fy;
     const bool edge = !(rx >= eps && rx <= 1.0 - eps && ry >= eps && ry <= 1.0 - eps);
@@ -127,16 +149,19 @@ __global__ void bb_roots_kernel(const BbQuery* __restrict__ qs, int nq, int heig
     const int ky = (k / d.nT) % d.nry;
     const int kx = k / (d.nT * d.nry);
     Node n;
-    n.x = -d.winX + (kx << height);
-    n.y = -d.winY + (ky << height);
+    n.x = (short)(-d.winX + (kx << height));
+    n.y = (short)(-d.winY + (ky << height));
     n.t = t; n.q = q;
     n.rank = (long long)(nRoots - 1 - k);
-    n.parent = -1; n.childBase = -1;
+    n.parent = -1; n.childBase = -1; n.childStride = 0;
     pool[d.rootBegin + k] = n;
 }
 
 // ---- node scoring + expansion (hot kernel) -------------------------------------------------------
-// One thread per node; ScorePixelAccurate::Score on pyramid level `height`.
+// One thread per node; ScorePixelAccurate::Score on pyramid level `height`, summed in beam order.
+// Survivors of a warp allocate their children together (one atomic per warp) and store them
+// child-major, so the next level's lanes again walk neighbouring thetas with equal offsets.
+template <int U>                           // beams in flight per thread (two dependent latencies each)
 __global__ void __launch_bounds__(128)
 bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                 const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
@@ -144,48 +169,165 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                 Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
                 BbBest* __restrict__ best) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nNodes) return;
-    Node n = nodes[k];
+    const bool active = k < nNodes;
+    Node n;
+    bool survive = false;
+    if (active) {
+        n = nodes[k];
+        const BbQuery& d = qs[n.q];
+        const double* __restrict__ lvl = d.level[height];
+        const int stride = d.nTpad;
+        const int2* __restrict__ tb = tab + d.tabBegin + n.t;
+        const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
+        const int nxo = n.x, nyo = n.y;
+        double acc = 0.0;
+        auto cellOf = [&](const int2 c) -> const double* {
+            int ix, iy;
+            if (c.x != INT_MIN) {
+                ix = c.x + nxo; iy = c.y + nyo;
+            } else {   // near-edge beam: indices from the host-computed exact table
+                const int* e = exactIdx + (long long)c.y * (exactSpanX + exactSpanY);
+                ix = e[nxo + d.winX];
+                iy = e[exactSpanX + nyo + d.winY];
+            }
+            ix = min(max(ix, -1), gx);          // out of the map -> zero apron (Value(idx, unknown))
+            iy = min(max(iy, -1), gy);
+            return lvl + (long long)iy * pitch + ix;
+        };
+        int i = 0;
+#pragma unroll 1
+        for (; i + U <= nb; i += U) {
+            int2 c[U];
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) c[u] = __ldg(tb + (long long)(i + u) * stride);
+            bool exact = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) exact |= c[u].x == INT_MIN;
+            if (!exact) {      // branch free: all U gathers in flight together
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int ix = min(max(c[u].x + nxo, -1), gx);
+                    const int iy = min(max(c[u].y + nyo, -1), gy);
+                    v[u] = __ldg(lvl + (long long)iy * pitch + ix);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = __ldg(cellOf(c[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, v[u]);   // unknown cells add 0.0
+        }
+        for (; i < nb; ++i) acc = __dadd_rn(acc, __ldg(cellOf(__ldg(tb + (long long)i * stride))));
+        scores[k] = acc;
+        if (acc > d.thrAbs) {                                     // :108 with scoreMax >= threshold
+            if (height == 0)
+                atomicMax(&best[n.q].scoreBits, (unsigned long long)__double_as_longlong(acc));
+            else
+                survive = true;
+        } else {
+            nodes[k].childBase = -1;
+        }
+    }
+    if (height == 0) return;
+    const unsigned m = __ballot_sync(0xffffffffu, survive);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int cnt = __popc(m);
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(nextCount, 4 * cnt);
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (!survive) return;
+    const int r = __popc(m & ((1u << lane) - 1u));
+    nodes[k].childBase = base + r;
+    nodes[k].childStride = cnt;
+    if (base + 4 * cnt > nextCap) return;       // host grows the pool and re-runs this level
+    const int w = 1 << (height - 1);
+    // visit (pop) order: (x+w, y+w), (x, y+w), (x+w, y), (x, y)   (:134-137)
+    const int dx[4] = {w, 0, w, 0}, dy[4] = {w, w, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        Node ch;
+        ch.x = (short)(n.x + dx[c]); ch.y = (short)(n.y + dy[c]); ch.t = n.t; ch.q = n.q;
+        ch.rank = n.rank * 4 + c;
+        ch.parent = k; ch.childBase = -1; ch.childStride = 0;
+        next[base + c * cnt + r] = ch;
+    }
+}
+
+// ---- node scoring, one WARP per node (small levels) ------------------------------------------------
+// Few nodes cannot hide the two dependent memory latencies (index table, then map cell) of a
+// 1000-beam walk.  Here the 32 lanes fetch 32 consecutive beams at once (8 rounds in flight) and the
+// values are then added strictly in beam order through warp shuffles, so the sum is still
+// bit-identical to the CPU's.
+__global__ void __launch_bounds__(128)
+bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
+                     const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
+                     Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
+                     Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
+                     BbBest* __restrict__ best) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= nNodes) return;                       // whole warp
+    const Node n = nodes[k];
     const BbQuery& d = qs[n.q];
     const double* __restrict__ lvl = d.level[height];
-    const int2* __restrict__ tb = tab + d.tabBegin + (long long)n.t * d.nUsePad;
-    const int pitch = d.pitch, gx = d.nx, gy = d.ny;
+    const int stride = d.nTpad;
+    const int2* __restrict__ tb = tab + d.tabBegin + n.t;
+    const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
+    const int nxo = n.x, nyo = n.y;
+    constexpr int CH = 8;
     double acc = 0.0;
-    const int nb = d.nUsePad;
-#pragma unroll 4
-    for (int i = 0; i < nb; ++i) {
-        const int2 c = __ldg(tb + i);
-        int ix, iy;
-        if (c.x != INT_MIN) {
-            ix = c.x + n.x; iy = c.y + n.y;
-        } else {   // near-edge beam: indices from the host-computed exact table
-            const int* e = exactIdx + (long long)c.y * (exactSpanX + exactSpanY);
-            ix = e[n.x + d.winX];
-            iy = e[exactSpanX + n.y + d.winY];
+#pragma unroll 1
+    for (int base = 0; base < nb; base += 32 * CH) {
+        int2 c[CH];
+        double v[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int i = base + u * 32 + lane;
+            c[u] = i < nb ? __ldg(tb + (long long)i * stride) : make_int2(-(1 << 28), -(1 << 28));
         }
-        ix = min(max(ix, -1), gx);          // out of the map -> zero apron (Value(idx, unknown))
-        iy = min(max(iy, -1), gy);
-        acc = __dadd_rn(acc, __ldg(lvl + (long long)iy * pitch + ix));   // unknown cells add 0.0
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            int ix, iy;
+            if (c[u].x != INT_MIN) {
+                ix = c[u].x + nxo; iy = c[u].y + nyo;
+            } else {
+                const int* e = exactIdx + (long long)c[u].y * (exactSpanX + exactSpanY);
+                ix = e[nxo + d.winX];
+                iy = e[exactSpanX + nyo + d.winY];
+            }
+            ix = min(max(ix, -1), gx);
+            iy = min(max(iy, -1), gy);
+            v[u] = __ldg(lvl + (long long)iy * pitch + ix);      // padding lanes read the zero apron
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            if (base + u * 32 >= nb) break;                      // uniform
+#pragma unroll
+            for (int l = 0; l < 32; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v[u], l));
+        }
     }
+    if (lane != 0) return;
     scores[k] = acc;
-    if (!(acc > d.thrAbs)) { nodes[k].childBase = -1; return; }   // :108 with scoreMax >= threshold
+    if (!(acc > d.thrAbs)) { nodes[k].childBase = -1; return; }
     if (height == 0) {
         atomicMax(&best[n.q].scoreBits, (unsigned long long)__double_as_longlong(acc));
         return;
     }
     const int slot = atomicAdd(nextCount, 4);
     nodes[k].childBase = slot;
-    if (slot + 4 > nextCap) return;           // host grows the pool and re-runs this level
+    nodes[k].childStride = 1;
+    if (slot + 4 > nextCap) return;
     const int w = 1 << (height - 1);
-    // visit (pop) order: (x+w, y+w), (x, y+w), (x+w, y), (x, y)   (:134-137)
     const int dx[4] = {w, 0, w, 0}, dy[4] = {w, w, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        Node m;
-        m.x = n.x + dx[c]; m.y = n.y + dy[c]; m.t = n.t; m.q = n.q;
-        m.rank = n.rank * 4 + c;
-        m.parent = k; m.childBase = -1;
-        next[slot + c] = m;
+    for (int cidx = 0; cidx < 4; ++cidx) {
+        Node ch;
+        ch.x = (short)(n.x + dx[cidx]); ch.y = (short)(n.y + dy[cidx]); ch.t = n.t; ch.q = n.q;
+        ch.rank = n.rank * 4 + cidx;
+        ch.parent = k; ch.childBase = -1; ch.childStride = 0;
+        next[slot + cidx] = ch;
     }
 }
 
@@ -260,8 +402,8 @@ __global__ void bb_replay_kernel(const BbQuery* __restrict__ qs, int nq, int hei
             const double s = lv.v[h].scores[idx];
             if (s <= bestScore) continue;                               // :108
             if (h == 0) { bestScore = s; bestLeaf = idx; continue; }    // :114-120
-            const int cb = lv.v[h].nodes[idx].childBase;                // s > best >= thr => expanded
-            for (int c = 3; c >= 0; --c) { stackIdx[sp] = cb + c; stackH[sp] = h - 1; ++sp; }
+            const Node nd = lv.v[h].nodes[idx];                         // s > best >= thr => expanded
+            for (int c = 3; c >= 0; --c) { stackIdx[sp] = nd.childBase + c * nd.childStride; stackH[sp] = h - 1; ++sp; }
         }
     }
     BbResult r;
@@ -287,9 +429,11 @@ struct lgs_bb_batch {
     lgs_ctx* ctx = nullptr;
     lgs_bb_params params{};
     int nq = 0, H = 0;
-    int maxNT = 0, maxUsePad = 0, maxRoots = 0;
+    int maxRoots = 0;
+    long long maxPerScan = 0;       // max nUse * nTpad over the distinct scans / queries
     int spanX = 0, spanY = 0;
     std::vector<BbQuery> qs;
+    std::vector<BbScan> us;         // distinct (scan, pose) pairs
     std::vector<double> hAngles, hRanges;
     std::vector<int> fixups;
     long long nTab = 0;
@@ -298,6 +442,8 @@ struct lgs_bb_batch {
     long long nodesPerLevel[kMaxLevels] = {0};
     long long gathers = 0;
     DevBuf<BbQuery> dQs;
+    DevBuf<BbScan> dUs;
+    DevBuf<double2> dHits;
     DevBuf<double> dAngles, dRanges;
     DevBuf<int2> dTab;
     DevBuf<BbFlag> dFlags;
@@ -329,7 +475,7 @@ int lgs_bb_batch_destroy(lgs_bb_batch* b) {
     if (!b) return LGS_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    b->dQs.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release();
+    b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release();
     b->dFlags.release(); b->dCounters.release(); b->dExact.release(); b->dBest.release();
     b->dRes.release(); b->hRes.release(); b->hCounters.release();
     for (int h = 0; h < kMaxLevels; ++h) { b->dNodes[h].release(); b->dScores[h].release(); }
@@ -346,23 +492,39 @@ int lgs_bb_batch_force_replay(lgs_bb_batch* b, int on) {
 int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans, lgs_pyramid* const* pyramids,
                         const double* normThr) {
     if (!b || !scans) return LGS_ERR_INVALID;
+    return lgs_bb_batch_upload_pairs(b, scans, scans->n_scans, nullptr, pyramids, normThr);
+}
+
+int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int nPairs,
+                              const int* pairScan, lgs_pyramid* const* pyramids,
+                              const double* normThr) {
+    if (!b || !scans) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
-    const int n = scans->n_scans;
-    if (n < 0 || (n > 0 && (!scans->beam_begin || !scans->sensor_pose || !pyramids)))
+    const int n = nPairs;
+    if (n < 0 || scans->n_scans < 0 || (n > 0 && (!scans->beam_begin || !scans->sensor_pose || !pyramids)))
         return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_upload: bad arguments");
+    for (int q = 0; q < n; ++q) {
+        const int sq = pairScan ? pairScan[q] : q;
+        if (sq < 0 || sq >= scans->n_scans)
+            return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_upload: pair %d names scan %d of %d", q, sq, scans->n_scans);
+    }
     LGS_CUDA(c, cudaSetDevice(c->device));
     const lgs_bb_params& p = b->params;
     const int H = b->H;
     b->uploaded = false; b->ran = false;
     b->nq = n;
     b->qs.assign(n, BbQuery{});
+    b->us.clear();
     b->fixups.assign(n, 0);
     b->hAngles.clear(); b->hRanges.clear();
-    b->maxNT = 0; b->maxUsePad = kBeamPadBB; b->maxRoots = 0; b->spanX = 0; b->spanY = 0;
-    long long nTab = 0, roots = 0;
+    b->maxRoots = 0; b->maxPerScan = 0; b->spanX = 0; b->spanY = 0;
+    long long nTab = 0, roots = 0, nHits = 0;
     const int winSizeMax = 1 << H;
+    // Pairs that name the same scan share its projected hit points (1 scan x many submaps).
+    std::vector<int> scanToUnique(std::max(scans->n_scans, 1), -1);
     for (int q = 0; q < n; ++q) {
-        const int b0 = scans->beam_begin[q], b1 = scans->beam_begin[q + 1];
+        const int sq = pairScan ? pairScan[q] : q;
+        const int b0 = scans->beam_begin[sq], b1 = scans->beam_begin[sq + 1];
         const int nb = b1 - b0;
         if (nb <= 0) return lgs_fail(c, LGS_ERR_INVALID, "bb: scan %d has no beams", q);
         const lgs_pyramid* pyr = pyramids[q];
@@ -372,9 +534,7 @@ int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans, lgs_pyrami
         if (g0->ctx->device != c->device)
             return lgs_fail(c, LGS_ERR_INVALID, "bb: pyramid of query %d lives on another device", q);
         BbQuery& d = b->qs[q];
-        d.sx = scans->sensor_pose[3 * q]; d.sy = scans->sensor_pose[3 * q + 1];
-        d.st = scans->sensor_pose[3 * q + 2];
-        d.minX = g0->min_x; d.minY = g0->min_y; d.res = g0->res;
+        d.minX = g0->min_x; d.minY = g0->min_y; d.res = g0->res; d.invRes = 1.0 / g0->res;
         d.nx = g0->nx; d.ny = g0->ny; d.pitch = g0->pitch;
         for (int h = 0; h <= H; ++h) d.level[h] = lgs_pyramid_level(pyr, h)->origin();
         // ComputeSearchStep (scan_matcher_branch_bound.cpp:178-197)
@@ -383,39 +543,55 @@ int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans, lgs_pyrami
         const double maxRange = std::min(maxR, p.scan_range_max);
         const double th = d.res / maxRange;
         const double stepX = d.res, stepY = d.res;
-        d.stepT = std::acos(1.0 - 0.5 * th * th);
+        const double stepT = std::acos(1.0 - 0.5 * th * th);
         d.winX = static_cast<int>(std::ceil(0.5 * p.range_x / stepX));                 // :68-73
         d.winY = static_cast<int>(std::ceil(0.5 * p.range_y / stepY));
-        d.winT = static_cast<int>(std::ceil(0.5 * p.range_theta / d.stepT));
-        if (!(d.stepT > 0.0) || d.winT < 0 || d.winT > (1 << 20))
-            return lgs_fail(c, LGS_ERR_INVALID, "bb: scan %d gives stepTheta=%g winTheta=%d", q, d.stepT, d.winT);
+        d.winT = static_cast<int>(std::ceil(0.5 * p.range_theta / stepT));
+        if (!(stepT > 0.0) || d.winT < 0 || d.winT > (1 << 20))
+            return lgs_fail(c, LGS_ERR_INVALID, "bb: scan %d gives stepTheta=%g winTheta=%d", q, stepT, d.winT);
+        if (d.winX + 2 * winSizeMax > 32000 || d.winY + 2 * winSizeMax > 32000)
+            return lgs_fail(c, LGS_ERR_INVALID, "bb: search window too large for 16-bit node offsets");
         d.nT = 2 * d.winT + 1;
+        d.nTpad = (d.nT + 3) / 4 * 4;
         d.nrx = (2 * d.winX) / winSizeMax + 1;                                         // :85-86
         d.nry = (2 * d.winY) / winSizeMax + 1;
         const double thr = normThr ? normThr[q] : DBL_MIN;
         d.thrAbs = thr * static_cast<double>(static_cast<size_t>(nb));                 // :75-76
         // ScorePixelAccurate range filter (score_function_pixel_accurate.cpp:27-41)
-        const double sMin = scans->range_min ? scans->range_min[q] : 0.0;
-        const double sMax = scans->range_max ? scans->range_max[q] : HUGE_VAL;
+        const double sMin = scans->range_min ? scans->range_min[sq] : 0.0;
+        const double sMax = scans->range_max ? scans->range_max[sq] : HUGE_VAL;
         const double minRange = std::max(p.score_range_min, sMin);
         const double maxRangeS = std::min(p.score_range_max, sMax);
-        d.beamBegin = (int)b->hAngles.size();
-        for (int i = b0; i < b1; ++i) {
-            const double r = scans->ranges[i];
-            if (r >= maxRangeS || r <= minRange) continue;
-            b->hAngles.push_back(scans->angles[i]);
-            b->hRanges.push_back(r);
+        int uidx = scanToUnique[sq];
+        if (uidx >= 0 && b->us[uidx].stepT != stepT) uidx = -1;      // other map resolution
+        if (uidx < 0) {
+            BbScan u{};
+            u.sx = scans->sensor_pose[3 * sq]; u.sy = scans->sensor_pose[3 * sq + 1];
+            u.st = scans->sensor_pose[3 * sq + 2];
+            u.stepT = stepT; u.winT = d.winT; u.nT = d.nT; u.nTpad = d.nTpad;
+            u.beamBegin = (int)b->hAngles.size();
+            for (int i = b0; i < b1; ++i) {
+                const double r = scans->ranges[i];
+                if (r >= maxRangeS || r <= minRange) continue;
+                b->hAngles.push_back(scans->angles[i]);
+                b->hRanges.push_back(r);
+            }
+            u.nUse = (int)b->hAngles.size() - u.beamBegin;
+            u.hitBegin = nHits;
+            nHits += (long long)u.nUse * u.nTpad;
+            uidx = (int)b->us.size();
+            b->us.push_back(u);
+            scanToUnique[sq] = uidx;
         }
-        d.nUse = (int)b->hAngles.size() - d.beamBegin;
-        d.nUsePad = std::max(kBeamPadBB, (d.nUse + kBeamPadBB - 1) / kBeamPadBB * kBeamPadBB);
+        d.scan = uidx;
+        d.nUse = b->us[uidx].nUse;
         d.tabBegin = nTab;
-        nTab += (long long)d.nT * d.nUsePad;
+        nTab += (long long)d.nUse * d.nTpad;
         const long long nr = (long long)d.nrx * d.nry * d.nT;
         if (roots + nr > (1LL << 30)) return lgs_fail(c, LGS_ERR_INVALID, "bb: too many root nodes");
         d.rootBegin = (int)roots;
         roots += nr;
-        b->maxNT = std::max(b->maxNT, d.nT);
-        b->maxUsePad = std::max(b->maxUsePad, d.nUsePad);
+        b->maxPerScan = std::max(b->maxPerScan, (long long)d.nUse * d.nTpad);
         b->maxRoots = std::max<long long>(b->maxRoots, nr);
         b->spanX = std::max(b->spanX, d.nrx * winSizeMax);
         b->spanY = std::max(b->spanY, d.nry * winSizeMax);
@@ -425,9 +601,11 @@ int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans, lgs_pyrami
     if (n == 0) { b->uploaded = true; return LGS_OK; }
     const size_t nk = b->hAngles.size();
     LGS_CUDA(c, b->dQs.reserve(n));
+    LGS_CUDA(c, b->dUs.reserve(b->us.size()));
+    LGS_CUDA(c, b->dHits.reserve(std::max<long long>(nHits, 1)));
     LGS_CUDA(c, b->dAngles.reserve(std::max<size_t>(nk, 1)));
     LGS_CUDA(c, b->dRanges.reserve(std::max<size_t>(nk, 1)));
-    LGS_CUDA(c, b->dTab.reserve(nTab));
+    LGS_CUDA(c, b->dTab.reserve(std::max<long long>(nTab, 1)));
     LGS_CUDA(c, b->dFlags.reserve(kFlagCapBB));
     LGS_CUDA(c, b->dCounters.reserve(2 + kMaxLevels));
     LGS_CUDA(c, b->hCounters.reserve(2 + kMaxLevels));
@@ -437,6 +615,7 @@ int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans, lgs_pyrami
     LGS_CUDA(c, b->dNodes[H].reserve(roots));
     LGS_CUDA(c, b->dScores[H].reserve(roots));
     LGS_CUDA(c, cudaMemcpyAsync(b->dQs.p, b->qs.data(), n * sizeof(BbQuery), cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(b->dUs.p, b->us.data(), b->us.size() * sizeof(BbScan), cudaMemcpyHostToDevice, c->stream));
     if (nk) {
         LGS_CUDA(c, cudaMemcpyAsync(b->dAngles.p, b->hAngles.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(b->dRanges.p, b->hRanges.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -457,11 +636,12 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
     LGS_CUDA(c, cudaSetDevice(c->device));
     LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, (2 + kMaxLevels) * sizeof(int), c->stream));
     {
-        const long long per = (long long)b->maxNT * b->maxUsePad;
-        dim3 gridDim((unsigned)((per + 255) / 256), n);
-        bb_project_kernel<<<gridDim, 256, 0, c->stream>>>(b->dQs.p, b->dAngles.p, b->dRanges.p,
-                                                          g_lgs_edge_eps, b->dTab.p, b->dFlags.p,
-                                                          b->dCounters.p);
+        const unsigned gx = (unsigned)((std::max<long long>(b->maxPerScan, 1) + 255) / 256);
+        bb_hit_kernel<<<dim3(gx, (unsigned)b->us.size()), 256, 0, c->stream>>>(b->dUs.p, b->dAngles.p,
+                                                                              b->dRanges.p, b->dHits.p);
+        LGS_LAUNCH_CHECK(c);
+        bb_index_kernel<<<dim3(gx, n), 256, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dHits.p, g_lgs_edge_eps,
+                                                            b->dTab.p, b->dFlags.p, b->dCounters.p);
         LGS_LAUNCH_CHECK(c);
         dim3 gridR((b->maxRoots + 127) / 128, n);
         bb_roots_kernel<<<gridR, 128, 0, c->stream>>>(b->dQs.p, n, H, b->dNodes[H].p);
@@ -483,18 +663,19 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
         std::vector<int> exact((size_t)nFlag * (spanX + spanY), 0);
         for (int k = 0; k < nFlag; ++k) {
             const BbQuery& d = b->qs[fl[k].q];
+            const BbScan& u = b->us[d.scan];
             const double stepX = d.res, stepY = d.res;
-            const double theta = d.st + static_cast<double>(fl[k].t - d.winT) * d.stepT;
-            const double a = theta + b->hAngles[d.beamBegin + fl[k].i];
+            const double theta = u.st + static_cast<double>(fl[k].t - d.winT) * u.stepT;
+            const double a = theta + b->hAngles[u.beamBegin + fl[k].i];
             const double cosT = std::cos(a), sinT = std::sin(a);
-            const double r = b->hRanges[d.beamBegin + fl[k].i];
+            const double r = b->hRanges[u.beamBegin + fl[k].i];
             int* e = exact.data() + (size_t)k * (spanX + spanY);
             for (int o = 0; o < spanX; ++o) {
-                const double px = d.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
+                const double px = u.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
                 e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res));
             }
             for (int o = 0; o < spanY; ++o) {
-                const double py = d.sy + static_cast<double>(o - d.winY) * stepY;
+                const double py = u.sy + static_cast<double>(o - d.winY) * stepY;
                 e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res));
             }
             b->fixups[fl[k].q]++;
@@ -506,6 +687,10 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
     }
 
     // Level-synchronous expansion of the static-threshold superset.
+    int warpBelow = kWarpPerNodeBelow;
+    int deepBelow = kDeepUnrollBelow;
+    if (const char* e = getenv("LGS_BB_WARP_BELOW")) warpBelow = atoi(e);     // tuning hooks
+    if (const char* e = getenv("LGS_BB_DEEP_BELOW")) deepBelow = atoi(e);
     int nNodes = b->totalRoots;
     for (int h = H; h >= 0; --h) {
         b->nodesPerLevel[h] = nNodes;
@@ -516,10 +701,21 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
             LGS_CUDA(c, b->dNodes[h - 1].reserve(std::min<long long>(4LL * nNodes, 1 << 16)));
         for (int attempt = 0; attempt < 2; ++attempt) {
             LGS_CUDA(c, cudaMemsetAsync(nextCount, 0, sizeof(int), c->stream));
-            bb_score_kernel<<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
-                b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
-                nextCount, b->dBest.p);
+            if (nNodes >= warpBelow && nNodes >= deepBelow)
+                bb_score_kernel<16><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
+                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                    nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
+                    nextCount, b->dBest.p);
+            else if (nNodes >= warpBelow)
+                bb_score_kernel<32><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
+                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                    nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
+                    nextCount, b->dBest.p);
+            else
+                bb_score_warp_kernel<<<(nNodes + 3) / 4, 128, 0, c->stream>>>(
+                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                    nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
+                    nextCount, b->dBest.p);
             LGS_LAUNCH_CHECK(c);
             if (h == 0) break;
             LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p + 1 + h, nextCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -568,7 +764,7 @@ int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out) {
         o.found = r.found; o.ix = r.ix; o.iy = r.iy; o.it = r.it;
         o.win_x = d.winX; o.win_y = d.winY; o.win_t = d.winT;
         o.n_fixups = b->fixups[q];
-        o.step_x = d.res; o.step_y = d.res; o.step_t = d.stepT;
+        o.step_x = d.res; o.step_y = d.res; o.step_t = b->us[d.scan].stepT;
         o.score = r.score;
         o.n_scored = total;          // batch-wide count of nodes scored (all queries)
         o.exact_replay = r.exactReplay;
