@@ -37,7 +37,7 @@ namespace {
 
 constexpr int kFlagCapBB = 1 << 16;
 constexpr int kMaxLevels = 21;
-constexpr int kWarpPerNodeBelow = 0;        // levels with fewer nodes score one warp per node (off: slower)
+constexpr int kWarpPerNodeBelow = 8192;     // levels with fewer nodes score one warp per node
 constexpr int kDeepUnrollBelow = 1 << 30;  // levels with fewer nodes keep 32 instead of 16 beams in flight (measured: always better)
 
 struct BbScan {                     // one per DISTINCT (scan, sensor pose): hit points are map independent
@@ -90,11 +90,12 @@ struct BbFlag { int q, t, i; };
 // a fraction of a cell apart, which keeps every later table read and map gather coalesced.
 __global__ void bb_hit_kernel(const BbScan* __restrict__ scans, const double* __restrict__ angles,
                               const double* __restrict__ ranges, double2* __restrict__ hits) {
-    const BbScan& u = scans[blockIdx.y];
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)u.nUse * u.nTpad) return;
-    const int i = (int)(idx / u.nTpad);
-    const int t = (int)(idx - (long long)i * u.nTpad);
+    // grid = (theta blocks, beams, distinct scans): no index arithmetic, theta-fastest
+    const BbScan& u = scans[blockIdx.z];
+    const int i = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u.nUse || t >= u.nTpad) return;
+    const long long idx = (long long)i * u.nTpad + t;
     if (t >= u.nT) { hits[u.hitBegin + idx] = make_double2(0.0, 0.0); return; }
     // nodePose.mTheta = sensorPose.mTheta + node.mTheta * stepTheta  (scan_matcher_branch_bound.cpp:96-99)
     const double theta = __dadd_rn(u.st, __dmul_rn((double)(t - u.winT), u.stepT));
@@ -106,34 +107,46 @@ __global__ void bb_hit_kernel(const BbScan* __restrict__ scans, const double* __
                                           __dadd_rn(u.sy, __dmul_rn(r, s)));
 }
 
-// ---- stage B: base cell index in the query's submap + near-edge flags -----------------------------
+// ---- stage B: base cell index in every query's submap + near-edge flags -----------------------------
+// One thread loads a hit point once and converts it for up to kIdxChunk queries that share the
+// scan, so the (L2 resident) hit array is read once per chunk instead of once per query.
+constexpr int kIdxChunk = 16;
+struct IdxChunk { int scan, begin, count; };
+
 __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
+                                const IdxChunk* __restrict__ chunks, const int* __restrict__ qlist,
                                 const double2* __restrict__ hits, double eps, int2* __restrict__ tab,
                                 BbFlag* __restrict__ flags, int* __restrict__ flagCount) {
-    const BbQuery& d = qs[blockIdx.y];
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)d.nUse * d.nTpad) return;
-    const int i = (int)(idx / d.nTpad);
-    const int t = (int)(idx - (long long)i * d.nTpad);
-    if (t >= d.nT) { tab[d.tabBegin + idx] = make_int2(-(1 << 28), -(1 << 28)); return; }
-    const double2 h = hits[scans[d.scan].hitBegin + idx];
-    // grid_map.hpp:784-787 divides by the resolution; multiplying by its reciprocal differs from
-    // that by < 1e-12 cells, far inside the guard band, so floor() agrees for every unflagged
-    // point and flagged ones are re-derived on the host with the real division anyway.
-    const double qx = __dmul_rn(__dsub_rn(h.x, d.minX), d.invRes);
-    const double qy = __dmul_rn(__dsub_rn(h.y, d.minY), d.invRes);
-    const double fx = floor(qx), fy = floor(qy);
-    const double rx = qx - fx, ry = qy - fy;
-    const bool edge = !(rx >= eps && rx <= 1.0 - eps && ry >= eps && ry <= 1.0 - eps);
-    int2 v = make_int2(__double2int_rd(qx), __double2int_rd(qy));
-    if (edge) {
-        const int k = atomicAdd(flagCount, 1);
-        if (k < kFlagCapBB) {
-            flags[k] = BbFlag{(int)blockIdx.y, t, i};
-            v = make_int2(INT_MIN, k);      // sentinel: use the exact per-offset table k
+    const IdxChunk ch = chunks[blockIdx.z];
+    const BbScan& u = scans[ch.scan];
+    const int i = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u.nUse || t >= u.nTpad) return;
+    const long long idx = (long long)i * u.nTpad + t;
+    const bool padT = t >= u.nT;
+    const double2 h = padT ? make_double2(0.0, 0.0) : hits[u.hitBegin + idx];
+    for (int k = 0; k < ch.count; ++k) {
+        const int q = __ldg(qlist + ch.begin + k);
+        const BbQuery& d = qs[q];
+        if (padT) { tab[d.tabBegin + idx] = make_int2(-(1 << 28), -(1 << 28)); continue; }
+        // grid_map.hpp:784-787 divides by the resolution; multiplying by its reciprocal differs from
+        // that by < 1e-12 cells, far inside the guard band, so floor() agrees for every unflagged
+        // point and flagged ones are re-derived on the host with the real division anyway.
+        const double qx = __dmul_rn(__dsub_rn(h.x, d.minX), d.invRes);
+        const double qy = __dmul_rn(__dsub_rn(h.y, d.minY), d.invRes);
+        const double fx = floor(qx), fy = floor(qy);
+        const double rx = qx - fx, ry = qy - fy;
+        const bool edge = !(rx >= eps && rx <= 1.0 - eps && ry >= eps && ry <= 1.0 - eps);
+        int2 v = make_int2(__double2int_rd(qx), __double2int_rd(qy));
+        if (edge) {
+            const int f = atomicAdd(flagCount, 1);
+            if (f < kFlagCapBB) {
+                flags[f] = BbFlag{q, t, i};
+                v = make_int2(INT_MIN, f);      // sentinel: use the exact per-offset table f
+            }
         }
+        tab[d.tabBegin + idx] = v;
     }
-    tab[d.tabBegin + idx] = v;
 }
 
 // ---- roots --------------------------------------------------------------------------------------
@@ -256,16 +269,20 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
 }
 
 // ---- node scoring, one WARP per node (small levels) ------------------------------------------------
-// Few nodes cannot hide the two dependent memory latencies (index table, then map cell) of a
-// 1000-beam walk.  Here the 32 lanes fetch 32 consecutive beams at once (8 rounds in flight) and the
-// values are then added strictly in beam order through warp shuffles, so the sum is still
-// bit-identical to the CPU's.
+// A level with few nodes cannot hide the two dependent memory latencies (index table, then map
+// cell) of a 1000-beam walk with one thread per node.  Here the 32 lanes fetch the node's beams 512
+// at a time (16 independent load pairs in flight per lane), park the values in shared memory in
+// beam order, and lane 0 then adds them strictly in that order: still bit-identical to the CPU sum,
+// but a level costs ~2 memory latencies + one dependent add chain instead of ~70 latencies.
 __global__ void __launch_bounds__(128)
 bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                      const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
                      Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
                      Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
                      BbBest* __restrict__ best) {
+    constexpr int CH = 16, STAGE = 32 * CH;
+    __shared__ double sv[4][STAGE];
+    const int wib = threadIdx.x >> 5;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (k >= nNodes) return;                       // whole warp
@@ -276,37 +293,59 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
     const int2* __restrict__ tb = tab + d.tabBegin + n.t;
     const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
     const int nxo = n.x, nyo = n.y;
-    constexpr int CH = 8;
     double acc = 0.0;
 #pragma unroll 1
-    for (int base = 0; base < nb; base += 32 * CH) {
+    for (int base = 0; base < nb; base += STAGE) {
         int2 c[CH];
         double v[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             const int i = base + u * 32 + lane;
+            // a beam past the end projects far outside -> clamps into the zero apron (adds 0.0)
             c[u] = i < nb ? __ldg(tb + (long long)i * stride) : make_int2(-(1 << 28), -(1 << 28));
         }
+        bool exact = false;
 #pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            int ix, iy;
-            if (c[u].x != INT_MIN) {
-                ix = c[u].x + nxo; iy = c[u].y + nyo;
-            } else {
-                const int* e = exactIdx + (long long)c[u].y * (exactSpanX + exactSpanY);
-                ix = e[nxo + d.winX];
-                iy = e[exactSpanX + nyo + d.winY];
+        for (int u = 0; u < CH; ++u) exact |= c[u].x == INT_MIN;
+        if (!__any_sync(0xffffffffu, exact)) {      // branch free: all gathers in flight together
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int ix = min(max(c[u].x + nxo, -1), gx);
+                const int iy = min(max(c[u].y + nyo, -1), gy);
+                v[u] = __ldg(lvl + (long long)iy * pitch + ix);
             }
-            ix = min(max(ix, -1), gx);
-            iy = min(max(iy, -1), gy);
-            v[u] = __ldg(lvl + (long long)iy * pitch + ix);      // padding lanes read the zero apron
+        } else {
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                int ix, iy;
+                if (c[u].x != INT_MIN) {
+                    ix = c[u].x + nxo; iy = c[u].y + nyo;
+                } else {   // near-edge beam: indices from the host-computed exact table
+                    const int* e = exactIdx + (long long)c[u].y * (exactSpanX + exactSpanY);
+                    ix = e[nxo + d.winX];
+                    iy = e[exactSpanX + nyo + d.winY];
+                }
+                ix = min(max(ix, -1), gx);
+                iy = min(max(iy, -1), gy);
+                v[u] = __ldg(lvl + (long long)iy * pitch + ix);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            if (base + u * 32 >= nb) break;                      // uniform
+        for (int u = 0; u < CH; ++u) sv[wib][u * 32 + lane] = v[u];
+        __syncwarp();
+        if (lane == 0) {
+            const int m = min(STAGE, nb - base);
+            int j = 0;
+            for (; j + 8 <= m; j += 8) {
+                double t8[8];
 #pragma unroll
-            for (int l = 0; l < 32; ++l) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v[u], l));
+                for (int u = 0; u < 8; ++u) t8[u] = sv[wib][j + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t8[u]);      // beam order
+            }
+            for (; j < m; ++j) acc = __dadd_rn(acc, sv[wib][j]);
         }
+        __syncwarp();
     }
     if (lane != 0) return;
     scores[k] = acc;
@@ -430,10 +469,14 @@ struct lgs_bb_batch {
     lgs_bb_params params{};
     int nq = 0, H = 0;
     int maxRoots = 0;
-    long long maxPerScan = 0;       // max nUse * nTpad over the distinct scans / queries
+    int maxNTpad = 0, maxUse = 0;   // launch extents of the projection kernels
     int spanX = 0, spanY = 0;
     std::vector<BbQuery> qs;
     std::vector<BbScan> us;         // distinct (scan, pose) pairs
+    std::vector<IdxChunk> chunks;   // <= kIdxChunk queries of one scan each
+    std::vector<int> qlist;         // queries grouped by scan
+    DevBuf<IdxChunk> dChunks;
+    DevBuf<int> dQlist;
     std::vector<double> hAngles, hRanges;
     std::vector<int> fixups;
     long long nTab = 0;
@@ -475,7 +518,7 @@ int lgs_bb_batch_destroy(lgs_bb_batch* b) {
     if (!b) return LGS_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release();
+    b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dChunks.release(); b->dQlist.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release();
     b->dFlags.release(); b->dCounters.release(); b->dExact.release(); b->dBest.release();
     b->dRes.release(); b->hRes.release(); b->hCounters.release();
     for (int h = 0; h < kMaxLevels; ++h) { b->dNodes[h].release(); b->dScores[h].release(); }
@@ -517,11 +560,12 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     b->us.clear();
     b->fixups.assign(n, 0);
     b->hAngles.clear(); b->hRanges.clear();
-    b->maxRoots = 0; b->maxPerScan = 0; b->spanX = 0; b->spanY = 0;
+    b->maxRoots = 0; b->maxNTpad = 0; b->maxUse = 0; b->spanX = 0; b->spanY = 0;
     long long nTab = 0, roots = 0, nHits = 0;
     const int winSizeMax = 1 << H;
     // Pairs that name the same scan share its projected hit points (1 scan x many submaps).
     std::vector<int> scanToUnique(std::max(scans->n_scans, 1), -1);
+    std::vector<double> scanMaxR(std::max(scans->n_scans, 1), -1.0);
     for (int q = 0; q < n; ++q) {
         const int sq = pairScan ? pairScan[q] : q;
         const int b0 = scans->beam_begin[sq], b1 = scans->beam_begin[sq + 1];
@@ -538,8 +582,12 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         d.nx = g0->nx; d.ny = g0->ny; d.pitch = g0->pitch;
         for (int h = 0; h <= H; ++h) d.level[h] = lgs_pyramid_level(pyr, h)->origin();
         // ComputeSearchStep (scan_matcher_branch_bound.cpp:178-197)
-        double maxR = scans->ranges[b0];
-        for (int i = b0 + 1; i < b1; ++i) maxR = std::max(maxR, scans->ranges[i]);
+        if (scanMaxR[sq] < 0.0) {      // std::max_element over the scan, once per scan
+            double m = scans->ranges[b0];
+            for (int i = b0 + 1; i < b1; ++i) m = std::max(m, scans->ranges[i]);
+            scanMaxR[sq] = m < 0.0 ? 0.0 : m;
+        }
+        const double maxR = scanMaxR[sq];
         const double maxRange = std::min(maxR, p.scan_range_max);
         const double th = d.res / maxRange;
         const double stepX = d.res, stepY = d.res;
@@ -591,17 +639,31 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         if (roots + nr > (1LL << 30)) return lgs_fail(c, LGS_ERR_INVALID, "bb: too many root nodes");
         d.rootBegin = (int)roots;
         roots += nr;
-        b->maxPerScan = std::max(b->maxPerScan, (long long)d.nUse * d.nTpad);
+        b->maxNTpad = std::max(b->maxNTpad, d.nTpad);
+        b->maxUse = std::max(b->maxUse, d.nUse);
         b->maxRoots = std::max<long long>(b->maxRoots, nr);
         b->spanX = std::max(b->spanX, d.nrx * winSizeMax);
         b->spanY = std::max(b->spanY, d.nry * winSizeMax);
     }
     b->nTab = nTab;
     b->totalRoots = (int)roots;
+    {   // group the queries by distinct scan, kIdxChunk per index-kernel block
+        std::vector<std::vector<int>> byScan(b->us.size());
+        for (int q = 0; q < n; ++q) byScan[b->qs[q].scan].push_back(q);
+        b->qlist.clear(); b->chunks.clear();
+        for (size_t u = 0; u < byScan.size(); ++u)
+            for (size_t k = 0; k < byScan[u].size(); k += kIdxChunk) {
+                const int cnt = (int)std::min<size_t>(kIdxChunk, byScan[u].size() - k);
+                b->chunks.push_back(IdxChunk{(int)u, (int)b->qlist.size(), cnt});
+                b->qlist.insert(b->qlist.end(), byScan[u].begin() + k, byScan[u].begin() + k + cnt);
+            }
+    }
     if (n == 0) { b->uploaded = true; return LGS_OK; }
     const size_t nk = b->hAngles.size();
     LGS_CUDA(c, b->dQs.reserve(n));
     LGS_CUDA(c, b->dUs.reserve(b->us.size()));
+    LGS_CUDA(c, b->dChunks.reserve(std::max<size_t>(b->chunks.size(), 1)));
+    LGS_CUDA(c, b->dQlist.reserve(std::max<size_t>(b->qlist.size(), 1)));
     LGS_CUDA(c, b->dHits.reserve(std::max<long long>(nHits, 1)));
     LGS_CUDA(c, b->dAngles.reserve(std::max<size_t>(nk, 1)));
     LGS_CUDA(c, b->dRanges.reserve(std::max<size_t>(nk, 1)));
@@ -616,6 +678,8 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     LGS_CUDA(c, b->dScores[H].reserve(roots));
     LGS_CUDA(c, cudaMemcpyAsync(b->dQs.p, b->qs.data(), n * sizeof(BbQuery), cudaMemcpyHostToDevice, c->stream));
     LGS_CUDA(c, cudaMemcpyAsync(b->dUs.p, b->us.data(), b->us.size() * sizeof(BbScan), cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(b->dChunks.p, b->chunks.data(), b->chunks.size() * sizeof(IdxChunk), cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(b->dQlist.p, b->qlist.data(), b->qlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (nk) {
         LGS_CUDA(c, cudaMemcpyAsync(b->dAngles.p, b->hAngles.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(b->dRanges.p, b->hRanges.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -636,13 +700,19 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
     LGS_CUDA(c, cudaSetDevice(c->device));
     LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, (2 + kMaxLevels) * sizeof(int), c->stream));
     {
-        const unsigned gx = (unsigned)((std::max<long long>(b->maxPerScan, 1) + 255) / 256);
-        bb_hit_kernel<<<dim3(gx, (unsigned)b->us.size()), 256, 0, c->stream>>>(b->dUs.p, b->dAngles.p,
-                                                                              b->dRanges.p, b->dHits.p);
-        LGS_LAUNCH_CHECK(c);
-        bb_index_kernel<<<dim3(gx, n), 256, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dHits.p, g_lgs_edge_eps,
-                                                            b->dTab.p, b->dFlags.p, b->dCounters.p);
-        LGS_LAUNCH_CHECK(c);
+        const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
+        for (size_t u0 = 0; u0 < b->us.size(); u0 += 65535) {
+            const unsigned nu = (unsigned)std::min<size_t>(65535, b->us.size() - u0);
+            bb_hit_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(b->dUs.p + u0, b->dAngles.p, b->dRanges.p, b->dHits.p);
+            LGS_LAUNCH_CHECK(c);
+        }
+        for (size_t c0 = 0; c0 < b->chunks.size(); c0 += 65535) {
+            const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
+            bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dChunks.p + c0, b->dQlist.p,
+                                                                     b->dHits.p, g_lgs_edge_eps, b->dTab.p,
+                                                                     b->dFlags.p, b->dCounters.p);
+            LGS_LAUNCH_CHECK(c);
+        }
         dim3 gridR((b->maxRoots + 127) / 128, n);
         bb_roots_kernel<<<gridR, 128, 0, c->stream>>>(b->dQs.p, n, H, b->dNodes[H].p);
         LGS_LAUNCH_CHECK(c);
