@@ -565,7 +565,8 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     const int winSizeMax = 1 << H;
     // Pairs that name the same scan share its projected hit points (1 scan x many submaps).
     std::vector<int> scanToUnique(std::max(scans->n_scans, 1), -1);
-    std::vector<double> scanMaxR(std::max(scans->n_scans, 1), -1.0);
+    std::vector<double> scanMaxR(std::max(scans->n_scans, 1), 0.0);
+    std::vector<char> haveMaxR(std::max(scans->n_scans, 1), 0);
     for (int q = 0; q < n; ++q) {
         const int sq = pairScan ? pairScan[q] : q;
         const int b0 = scans->beam_begin[sq], b1 = scans->beam_begin[sq + 1];
@@ -582,10 +583,11 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         d.nx = g0->nx; d.ny = g0->ny; d.pitch = g0->pitch;
         for (int h = 0; h <= H; ++h) d.level[h] = lgs_pyramid_level(pyr, h)->origin();
         // ComputeSearchStep (scan_matcher_branch_bound.cpp:178-197)
-        if (scanMaxR[sq] < 0.0) {      // std::max_element over the scan, once per scan
+        if (!haveMaxR[sq]) {           // std::max_element over the scan, once per scan
             double m = scans->ranges[b0];
             for (int i = b0 + 1; i < b1; ++i) m = std::max(m, scans->ranges[i]);
-            scanMaxR[sq] = m < 0.0 ? 0.0 : m;
+            scanMaxR[sq] = m;
+            haveMaxR[sq] = 1;
         }
         const double maxR = scanMaxR[sq];
         const double maxRange = std::min(maxR, p.scan_range_max);

@@ -18,7 +18,7 @@
 //
 // Finding the candidate beams of a cell:
 //  * far field (Chebyshev distance to the sensor cell > kNear): beams are angularly sorted, so
-//    the candidates are a binary-searched window of +-(2.5 / d + 0.002) rad around the cell's
+//    the candidates are a binary-searched window of +-(2.2 / d + 0.001) rad around the cell's
 //    direction -- a proven superset (cell centres on a Bresenham line lie within 0.5 cell of
 //    the centre-to-centre segment, whose end points are within 0.71 cell of the true ray);
 //  * near field (<= kNear cells): nearly every beam passes, so one warp per (scan, near cell)
@@ -36,6 +36,7 @@ constexpr int kNear = 16;                      // near-field half width (cells)
 constexpr int kNearW = 2 * kNear + 1;
 constexpr int kRuns = 15;                      // RLE runs kept per (scan, near cell)
 constexpr unsigned short kRleOverflow = 0xFFFF;
+constexpr int kListCap = 32;                   // touches recorded per cell and sub-batch before falling back
 constexpr float kTwoPi = 6.28318530717958647692f;
 
 struct ScanMeta {
@@ -70,20 +71,23 @@ __device__ __forceinline__ double bayesUpdate(double v, double p, double oddsP) 
 }
 
 // 0 = not on the ray, 1 = miss cell, 2 = hit cell.  (rx, ry) = cell - sensorCell, (ex, ey) = hitCell - sensorCell.
+// Division free: with k the step along the major axis, the reference's minor coordinate is
+// floor((2|minor| k + |major|) / (2|major|)) (util.hpp:276-299), i.e. the cell is on the ray iff
+//     2|major| t <= 2|minor| k + |major| < 2|major| (t + 1),   t = signed minor offset >= 0.
 __device__ __forceinline__ int rayTouch(int rx, int ry, int ex, int ey) {
     const int ax = abs(ex), ay = abs(ey);
-    if (ax > ay) {                                   // util.hpp:276-287
-        const int k = ex < 0 ? -rx : rx;
-        if (k < 0 || k > ax) return 0;
-        const int yk = (2 * ay * k + ax) / (2 * ax);
-        if (ry != (ey < 0 ? -yk : yk)) return 0;
-        return k == ax ? 2 : 1;
+    int k, t, amaj, amin;
+    if (ax > ay) {                                   // x-major (util.hpp:276-287)
+        k = ex < 0 ? -rx : rx; t = ey < 0 ? -ry : ry; amaj = ax; amin = ay;
+    } else {                                         // y-major (util.hpp:288-299), also dx == dy == 0
+        k = ey < 0 ? -ry : ry; t = ex < 0 ? -rx : rx; amaj = ay; amin = ax;
     }
-    const int k = ey < 0 ? -ry : ry;                 // util.hpp:288-299 (also dx == dy == 0)
-    if (k < 0 || k > ay) return 0;
-    const int xk = ay == 0 ? 0 : (2 * ax * k + ay) / (2 * ay);
-    if (rx != (ex < 0 ? -xk : xk)) return 0;
-    return k == ay ? 2 : 1;
+    if (k < 0 || k > amaj || t < 0) return 0;
+    const int lhs = 2 * amin * k + amaj;             // < 2^31 for maps below 16k cells per side
+    const int m2 = 2 * amaj;
+    if (amaj == 0) return (t == 0) ? 2 : 0;          // zero-length ray: the sensor cell is the hit
+    if (m2 * t > lhs || lhs >= m2 * (t + 1)) return 0;
+    return k == amaj ? 2 : 1;
 }
 
 __device__ __forceinline__ float wrapBeta(float a) {   // into [-0.01, 2*pi - 0.01)
@@ -207,7 +211,7 @@ integ_near_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ re
 __global__ void __launch_bounds__(128)
 integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
                   int x0, int y0, int rw, unsigned long long* __restrict__ mask,
-                  unsigned* __restrict__ expect) {
+                  unsigned* __restrict__ expect, unsigned* __restrict__ lists) {
     const int s = blockIdx.y;
     const ScanMeta m = meta[s];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,7 +222,11 @@ integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ re
     const int x1 = m.sx + e.x, y1 = m.sy + e.y;
     const int sx = e.x < 0 ? -1 : 1, sy = e.y < 0 ? -1 : 1;
     const int dx = abs(e.x * 2), dy = abs(e.y * 2);
-#define MARK() do { const size_t c = (size_t)(y - y0) * rw + (x - x0); atomicOr(mask + c, bit); atomicAdd(expect + c, 1u); } while (0)
+    // key = 1 + ((scan << 17) | (beam << 1) | isHit): ascending key == the CPU's (scan, beam) order
+    const unsigned keyMiss = 1u + (((unsigned)s << 17) | ((unsigned)i << 1));
+#define MARK() do { const size_t c = (size_t)(y - y0) * rw + (x - x0); atomicOr(mask + c, bit);              \
+        const unsigned slot = atomicAdd(expect + c, 1u);                                                     \
+        if (slot < (unsigned)kListCap) lists[c * kListCap + slot] = keyMiss + ((x == x1 && y == y1) ? 1u : 0u); } while (0)
     MARK();
     if (dx > dy) {
         int err = dy - dx / 2;
@@ -246,6 +254,7 @@ struct ApplyArgs {
     const unsigned short* nearTab;
     const unsigned long long* mask;
     const unsigned* expect;
+    const unsigned* lists;
     double pHit, pMiss, oddsHit, oddsMiss;
 };
 
@@ -288,7 +297,7 @@ __device__ __forceinline__ double applyScan(double v, int s, int cx, int cy, con
     // far field: angular window of candidate beams
     const float* __restrict__ bt = a.beta + m.beamBegin;
     const float d = sqrtf((float)(rx * rx + ry * ry));
-    const float delta = 2.5f / d + 2e-3f;
+    const float delta = 2.2f / d + 1e-3f;
     const float bc = wrapBeta(atan2f((float)ry, (float)rx) - m.ang0);
     const float bLast = __ldg(bt + m.n - 1);
 #pragma unroll 1
@@ -322,8 +331,26 @@ integ_apply_kernel(ApplyArgs a, GridRef g, int x0, int y0, int x1, int y1,
             double* cell = g.origin + (size_t)cy * g.pitch + cx;
             const double v0 = *cell;
             double v = v0;
-            for (unsigned long long r = mk; r; r &= r - 1) v = applyScan(v, __ffsll((long long)r) - 1, cx, cy, a, count);
-            if (count != a.expect[ridx]) {
+            const unsigned nTouch = a.expect[ridx];
+            if (nTouch <= (unsigned)kListCap && nTouch <= 32767u * 2u) {
+                // The mark pass recorded every touch of this cell: apply them in ascending key order
+                // (selection by repeated minimum; the list is tiny and L1 resident).
+                const unsigned* __restrict__ L = a.lists + ridx * kListCap;
+                unsigned prev = 0;
+                for (unsigned step = 0; step < nTouch; ++step) {
+                    unsigned bestKey = 0xffffffffu;
+                    for (unsigned j = 0; j < nTouch; ++j) {
+                        const unsigned key = __ldg(L + j);
+                        if (key > prev && key < bestKey) bestKey = key;
+                    }
+                    prev = bestKey;
+                    v = ((bestKey - 1u) & 1u) ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
+                }
+                count = nTouch;
+            } else {
+                for (unsigned long long r = mk; r; r &= r - 1) v = applyScan(v, __ffsll((long long)r) - 1, cx, cy, a, count);
+            }
+            if (count != nTouch) {
                 // The fast search disagrees with the mark pass: redo this cell the slow, exact way.
                 v = v0; count = 0;
                 for (unsigned long long r = mk; r; r &= r - 1) {
@@ -387,14 +414,14 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     LGS_CUDA(c, w.rel.reserve(std::max<size_t>((size_t)total, 1)));
     LGS_CUDA(c, w.beta.reserve(std::max<size_t>((size_t)total, 1)));
     LGS_CUDA(c, w.nearTab.reserve((size_t)std::min(n, 64) * kNearW * kNearW * (kRuns + 1)));
-    LGS_CUDA(c, w.counters.reserve(2));
+    LGS_CUDA(c, w.counters.reserve(8));
     LGS_CUDA(c, w.hMeta.reserve((size_t)n * sizeof(ScanMeta)));
-    LGS_CUDA(c, w.hCounters.reserve(2));
+    LGS_CUDA(c, w.hCounters.reserve(8));
     LGS_CUDA(c, cudaMemcpyAsync(w.sensor.p, scans->sensor_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (total)
         LGS_CUDA(c, cudaMemcpyAsync(w.hit.p, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     LGS_CUDA(c, cudaMemcpyAsync(w.begin.p, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    LGS_CUDA(c, cudaMemsetAsync(w.counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    LGS_CUDA(c, cudaMemsetAsync(w.counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
 
     int maxBeams = 0;
     for (int s = 0; s < n; ++s) maxBeams = std::max(maxBeams, scans->hit_begin[s + 1] - scans->hit_begin[s]);
@@ -423,8 +450,12 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     const double oddsHit = clampP(pHit) / (1.0 - clampP(pHit));
     const double oddsMiss = clampP(pMiss) / (1.0 - clampP(pMiss));
 
-    for (int s0 = 0; s0 < n; s0 += 64) {
-        const int ns = std::min(64, n - s0);
+    // Sub-batches: every scan owns one mask bit (<= 64), and fewer scans per launch keep the
+    // per-cell touch count inside the recorded list (kListCap), which is the fast path.
+    int sub = 16;
+    if (const char* e = getenv("LGS_INTEG_SUB")) sub = std::min(64, std::max(1, atoi(e)));   // tuning hook
+    for (int s0 = 0; s0 < n; s0 += sub) {
+        const int ns = std::min(sub, n - s0);
         int x0 = grid->nx, y0 = grid->ny, x1 = 0, y1 = 0, subBeams = 0;
         for (int s = s0; s < s0 + ns; ++s) {
             if (hMeta[s].n == 0) continue;
@@ -440,17 +471,18 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         LGS_CUDA(c, cudaMemsetAsync(w.mask.p, 0, region * sizeof(unsigned long long), c->stream));
         LGS_CUDA(c, cudaMemsetAsync(w.expect.p, 0, region * sizeof(unsigned), c->stream));
         dim3 gm((subBeams + 127) / 128, ns);
-        integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p, w.expect.p);
+        LGS_CUDA(c, w.lists.reserve(region * kListCap));
+        integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p, w.expect.p, w.lists.p);
         LGS_LAUNCH_CHECK(c);
         const long long warps = (long long)ns * kNearW * kNearW;
         integ_near_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, w.nearTab.p);
         LGS_LAUNCH_CHECK(c);
-        ApplyArgs a{dMeta + s0, w.rel.p, w.beta.p, w.nearTab.p, w.mask.p, w.expect.p, pHit, pMiss, oddsHit, oddsMiss};
+        ApplyArgs a{dMeta + s0, w.rel.p, w.beta.p, w.nearTab.p, w.mask.p, w.expect.p, w.lists.p, pHit, pMiss, oddsHit, oddsMiss};
         dim3 block(32, 8), gridDim((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
         integ_apply_kernel<<<gridDim, block, 0, c->stream>>>(a, g, x0, y0, x1, y1, w.counters.p);
         LGS_LAUNCH_CHECK(c);
     }
-    LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (nUpdatesOut) *nUpdatesOut = (long long)w.hCounters.p[0];
     w.fallbackCells += (long long)w.hCounters.p[1];

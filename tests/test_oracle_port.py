@@ -51,23 +51,20 @@ def test_bresenham_closed_form_used_by_the_kernel():
     """The O(1) membership test of lgs_integrate.cu (rayTouch) against the oracle's Bresenham."""
     rng = np.random.default_rng(3)
 
-    def touch(rx, ry, ex, ey):
+    def touch(rx, ry, ex, ey):        # same division-free logic as rayTouch in lgs_integrate.cu
         ax, ay = abs(ex), abs(ey)
         if ax > ay:
-            k = -rx if ex < 0 else rx
-            if k < 0 or k > ax:
-                return 0
-            yk = (2 * ay * k + ax) // (2 * ax)
-            if ry != (-yk if ey < 0 else yk):
-                return 0
-            return 2 if k == ax else 1
-        k = -ry if ey < 0 else ry
-        if k < 0 or k > ay:
+            k, t, amaj, amin = (-rx if ex < 0 else rx), (-ry if ey < 0 else ry), ax, ay
+        else:
+            k, t, amaj, amin = (-ry if ey < 0 else ry), (-rx if ex < 0 else rx), ay, ax
+        if k < 0 or k > amaj or t < 0:
             return 0
-        xk = 0 if ay == 0 else (2 * ax * k + ay) // (2 * ay)
-        if rx != (-xk if ex < 0 else xk):
+        if amaj == 0:
+            return 2 if t == 0 else 0
+        lhs, m2 = 2 * amin * k + amaj, 2 * amaj
+        if m2 * t > lhs or lhs >= m2 * (t + 1):
             return 0
-        return 2 if k == ay else 1
+        return 2 if k == amaj else 1
 
     for _ in range(300):
         ex, ey = (int(v) for v in rng.integers(-25, 26, 2))
