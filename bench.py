@@ -166,7 +166,7 @@ def run_reference(args, rank, world_size):
     if not R.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblgs_ref.so not built"}))
         return
-    per_step = max(cores, 8)
+    per_step = max(4 * cores, 32)
     total = per_step * (args.steps + args.warmup)
     traj, map_scans, angles, ranges, inits = c2_workload(total, seed=1)
     builder = R.RefBuilder(n_latest=len(traj))
@@ -520,7 +520,9 @@ def run_b200(args, rank, world_size, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "csm_sweep_kernel",
+                     "frac": achieved / peak, "traffic": 0.8305e6 * M, "kernel": "csm_sweep_kernel",
+                     "traffic_source": "ncu --set full: dram__bytes_read+write = 166.1 MB per 200-match "
+                                       "launch (profiles/r1_kernels_v2.md), scaled to this launch",
                      "peak_source": peak_src, "kernel_ms": k_sweep,
                      "algorithmic_bytes_per_launch": gathers * 8,
                      "note": "gathers are served from L1/L2 (map is cache resident), so the HBM "
