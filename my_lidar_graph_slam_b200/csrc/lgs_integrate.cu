@@ -36,7 +36,6 @@ constexpr int kNear = 16;                      // near-field half width (cells)
 constexpr int kNearW = 2 * kNear + 1;
 constexpr int kRuns = 15;                      // RLE runs kept per (scan, near cell)
 constexpr unsigned short kRleOverflow = 0xFFFF;
-constexpr int kListCap = 32;                   // touches recorded per cell and sub-batch before falling back
 constexpr float kTwoPi = 6.28318530717958647692f;
 
 struct ScanMeta {
@@ -204,14 +203,19 @@ integ_near_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ re
     }
 }
 
-// ---- mark pass: which scans touch which cells (idempotent, order free) -----------------------------
-// One thread per (scan, beam) walks the reference's Bresenham (util.hpp:257-303) and ORs the scan's
-// bit into every cell it touches; `expect` counts the touches so the owner can verify that its
-// candidate search found every one of them.
+// ---- ray walks: counting sort of the far-field touches by cell ----------------------------------------
+// One thread per (scan, beam) walks the reference's Bresenham (util.hpp:257-303) twice.  Pass 1
+// (FILL = false) ORs the scan's bit into every touched cell and counts the far-field touches per
+// cell; after an exclusive prefix sum over the counts, pass 2 (FILL = true) drops one 32-bit key per
+// far-field touch into the cell's own segment.  Near-field touches (<= kNear cells from the sensor
+// cell: thousands per cell) are not recorded; the run-length table covers them.
+//   key = 1 + ((scan << 17) | (beam << 1) | isHit): ascending key == the CPU's (scan, beam) order.
+template <bool FILL>
 __global__ void __launch_bounds__(128)
-integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
+integ_walk_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
                   int x0, int y0, int rw, unsigned long long* __restrict__ mask,
-                  unsigned* __restrict__ expect, unsigned* __restrict__ lists) {
+                  unsigned* __restrict__ cnt, const unsigned* __restrict__ local,
+                  const unsigned* __restrict__ blockSums, unsigned* __restrict__ keys) {
     const int s = blockIdx.y;
     const ScanMeta m = meta[s];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,79 +226,147 @@ integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ re
     const int x1 = m.sx + e.x, y1 = m.sy + e.y;
     const int sx = e.x < 0 ? -1 : 1, sy = e.y < 0 ? -1 : 1;
     const int dx = abs(e.x * 2), dy = abs(e.y * 2);
-    // key = 1 + ((scan << 17) | (beam << 1) | isHit): ascending key == the CPU's (scan, beam) order
     const unsigned keyMiss = 1u + (((unsigned)s << 17) | ((unsigned)i << 1));
-#define MARK() do { const size_t c = (size_t)(y - y0) * rw + (x - x0); atomicOr(mask + c, bit);              \
-        const unsigned slot = atomicAdd(expect + c, 1u);                                                     \
-        if (slot < (unsigned)kListCap) lists[c * kListCap + slot] = keyMiss + ((x == x1 && y == y1) ? 1u : 0u); } while (0)
-    MARK();
+    auto touch = [&]() {
+        const size_t c = (size_t)(y - y0) * rw + (x - x0);
+        const bool nearField = max(abs(x - m.sx), abs(y - m.sy)) <= kNear;
+        if (!FILL) {
+            if (!(mask[c] & bit)) atomicOr(mask + c, bit);      // racy pre-check only saves atomics
+            if (!nearField) atomicAdd(cnt + c, 1u);
+        } else if (!nearField) {
+            const unsigned slot = local[c] + blockSums[c >> 10] + atomicAdd(cnt + c, 1u);
+            keys[slot] = keyMiss + ((x == x1 && y == y1) ? 1u : 0u);
+        }
+    };
+    touch();
     if (dx > dy) {
         int err = dy - dx / 2;
         while (x != x1) {
             if (err >= 0) { y += sy; err -= dx; }
             x += sx; err += dy;
-            MARK();
+            touch();
         }
     } else {
         int err = dx - dy / 2;
         while (y != y1) {
             if (err >= 0) { x += sx; err -= dy; }
             y += sy; err += dx;
-            MARK();
+            touch();
         }
     }
-#undef MARK
+}
+
+// Exclusive prefix sum over the per-cell counts: 1024 cells per block, then the block totals.
+__global__ void __launch_bounds__(256)
+integ_scan_blocks_kernel(const unsigned* __restrict__ cnt, size_t n, unsigned* __restrict__ local,
+                         unsigned* __restrict__ blockSums) {
+    __shared__ unsigned sWarp[8];
+    const size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+    unsigned v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = base + k < n ? cnt[base + k] : 0u; sum += v[k]; }
+    unsigned inc = sum;                                   // inclusive scan of the per-thread sums
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sWarp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned w = lane < 8 ? sWarp[lane] : 0u;
+        for (int o = 1; o < 8; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < 8) sWarp[lane] = w;
+    }
+    __syncthreads();
+    unsigned run = inc - sum + (wid ? sWarp[wid - 1] : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (base + k < n) local[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 255) blockSums[blockIdx.x] = sWarp[7];
+}
+
+__global__ void __launch_bounds__(1024)
+integ_scan_sums_kernel(unsigned* __restrict__ blockSums, int nBlocks) {
+    __shared__ unsigned sWarp[32];
+    __shared__ unsigned sCarry;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < nBlocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < nBlocks ? blockSums[i] : 0u;
+        unsigned inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sWarp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned w = sWarp[lane];
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            sWarp[lane] = w;
+        }
+        __syncthreads();
+        const unsigned excl = sCarry + inc - v + (wid ? sWarp[wid - 1] : 0u);
+        if (i < nBlocks) blockSums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) sCarry = excl + v;
+        __syncthreads();
+    }
 }
 
 // ---- apply pass: one thread owns one cell ----------------------------------------------------------
+constexpr unsigned kSortCap = 160;     // recorded touches a thread orders by repeated-minimum selection
+
 struct ApplyArgs {
     const ScanMeta* meta;
     const int2* rel;
     const float* beta;
     const unsigned short* nearTab;
     const unsigned long long* mask;
-    const unsigned* expect;
-    const unsigned* lists;
+    const unsigned* cnt;          // far-field touches per cell
+    const unsigned* local;        // exclusive prefix sum within 1024-cell blocks
+    const unsigned* blockSums;    // exclusive prefix sum of the block totals
+    const unsigned* keys;
     double pHit, pMiss, oddsHit, oddsMiss;
 };
 
-// All touches of scan `s` on the cell at (rx, ry) from its sensor cell, in beam order, by testing
-// every beam (exact, slow): the fallback when the fast search cannot be used or disagrees.
+__device__ __forceinline__ double applyTouch(double v, bool hit, const ApplyArgs& a) {
+    return hit ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
+}
+
+// All touches of scan `m` on the cell at (rx, ry) from its sensor cell, in beam order, by testing
+// every beam (exact, slow): the fallback when the fast paths cannot be used or disagree.
 __device__ __forceinline__ double applyAllBeams(double v, const ScanMeta& m, const int2* __restrict__ e,
                                                 int rx, int ry, const ApplyArgs& a, unsigned& count) {
     for (int i = 0; i < m.n; ++i) {
         const int2 ee = __ldg(e + i);
         const int ty = rayTouch(rx, ry, ee.x, ee.y);
-        if (ty) { v = ty == 2 ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss); ++count; }
+        if (ty) { v = applyTouch(v, ty == 2, a); ++count; }
     }
     return v;
 }
 
-__device__ __forceinline__ double applyScan(double v, int s, int cx, int cy, const ApplyArgs& a,
-                                            unsigned& count) {
-    const ScanMeta m = a.meta[s];
-    const int rx = cx - m.sx, ry = cy - m.sy;
-    const int cheb = max(abs(rx), abs(ry));
-    const int2* __restrict__ e = a.rel + m.beamBegin;
-    if (cheb <= kNear) {
-        const unsigned short* t = a.nearTab + ((size_t)s * kNearW * kNearW + (ry + kNear) * kNearW + (rx + kNear)) * (kRuns + 1);
-        if (t[0] == kRleOverflow) return applyAllBeams(v, m, e, rx, ry, a, count);
-        for (int k = 0; k < kRuns; ++k) {
-            const unsigned short ent = t[k];
-            if (ent == 0) break;
-            const int cnt = ent & 0x7fff;
-            const bool hit = (ent >> 15) != 0;
-            count += cnt;
-            for (int j = 0; j < cnt; ++j) {
-                const double nv = hit ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
-                if (nv == v) break;        // fixed point: the rest of the run is a no-op
-                v = nv;
-            }
+// Near field of scan s: apply the run-length encoded touch sequence.
+__device__ __forceinline__ double applyNear(double v, int s, const ScanMeta& m, int rx, int ry,
+                                            const ApplyArgs& a, unsigned& count) {
+    const unsigned short* t = a.nearTab + ((size_t)s * kNearW * kNearW + (ry + kNear) * kNearW + (rx + kNear)) * (kRuns + 1);
+    if (t[0] == kRleOverflow) return applyAllBeams(v, m, a.rel + m.beamBegin, rx, ry, a, count);
+    for (int k = 0; k < kRuns; ++k) {
+        const unsigned short ent = t[k];
+        if (ent == 0) break;
+        const int cnt = ent & 0x7fff;
+        const bool hit = (ent >> 15) != 0;
+        count += cnt;
+        for (int j = 0; j < cnt; ++j) {
+            const double nv = applyTouch(v, hit, a);
+            if (nv == v) break;        // fixed point: the rest of the run is a no-op
+            v = nv;
         }
-        return v;
     }
+    return v;
+}
+
+// Far field of scan s without a recorded list: binary-searched angular window of candidate beams.
+__device__ __forceinline__ double applyFarSearch(double v, const ScanMeta& m, int rx, int ry,
+                                                 const ApplyArgs& a, unsigned& count) {
+    const int2* __restrict__ e = a.rel + m.beamBegin;
     if (m.unsorted) return applyAllBeams(v, m, e, rx, ry, a, count);
-    // far field: angular window of candidate beams
     const float* __restrict__ bt = a.beta + m.beamBegin;
     const float d = sqrtf((float)(rx * rx + ry * ry));
     const float delta = 2.2f / d + 1e-3f;
@@ -312,7 +384,7 @@ __device__ __forceinline__ double applyScan(double v, int s, int cx, int cy, con
         for (int i = lb; i < m.n && __ldg(bt + i) <= hi; ++i) {
             const int2 ee = __ldg(e + i);
             const int ty = rayTouch(rx, ry, ee.x, ee.y);
-            if (ty) { v = ty == 2 ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss); ++count; }
+            if (ty) { v = applyTouch(v, ty == 2, a); ++count; }
         }
     }
     return v;
@@ -323,48 +395,55 @@ integ_apply_kernel(ApplyArgs a, GridRef g, int x0, int y0, int x1, int y1,
                    unsigned long long* __restrict__ counters /* [0] updates, [1] fallback cells */) {
     const int cx = x0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int cy = y0 + blockIdx.y * blockDim.y + threadIdx.y;
-    unsigned count = 0;
+    unsigned total = 0;
     if (cx < x1 && cy < y1) {
         const size_t ridx = (size_t)(cy - y0) * (x1 - x0) + (cx - x0);
-        unsigned long long mk = a.mask[ridx];
+        const unsigned long long mk = a.mask[ridx];
         if (mk) {
             double* cell = g.origin + (size_t)cy * g.pitch + cx;
             const double v0 = *cell;
             double v = v0;
-            const unsigned nTouch = a.expect[ridx];
-            if (nTouch <= (unsigned)kListCap && nTouch <= 32767u * 2u) {
-                // The mark pass recorded every touch of this cell: apply them in ascending key order
-                // (selection by repeated minimum; the list is tiny and L1 resident).
-                const unsigned* __restrict__ L = a.lists + ridx * kListCap;
-                unsigned prev = 0;
-                for (unsigned step = 0; step < nTouch; ++step) {
+            const unsigned nFar = a.cnt[ridx];
+            const unsigned* __restrict__ K = a.keys + a.local[ridx] + a.blockSums[ridx >> 10];
+            unsigned nearCount = 0, farCount = 0;
+            unsigned prev = 0;
+            for (unsigned long long r = mk; r; r &= r - 1) {           // scans in order
+                const int s = __ffsll((long long)r) - 1;
+                const ScanMeta m = a.meta[s];
+                const int rx = cx - m.sx, ry = cy - m.sy;
+                if (max(abs(rx), abs(ry)) <= kNear) { v = applyNear(v, s, m, rx, ry, a, nearCount); continue; }
+                if (nFar > kSortCap) { v = applyFarSearch(v, m, rx, ry, a, farCount); continue; }
+                // this scan's recorded touches in ascending key (= beam) order, by repeated minimum
+                const unsigned hiKey = (((unsigned)s + 1u) << 17);     // keys of scan s are in (s<<17, hiKey]
+                prev = max(prev, (unsigned)s << 17);
+                for (;;) {
                     unsigned bestKey = 0xffffffffu;
-                    for (unsigned j = 0; j < nTouch; ++j) {
-                        const unsigned key = __ldg(L + j);
+                    for (unsigned j = 0; j < nFar; ++j) {
+                        const unsigned key = __ldg(K + j);
                         if (key > prev && key < bestKey) bestKey = key;
                     }
+                    if (bestKey > hiKey) break;
                     prev = bestKey;
-                    v = ((bestKey - 1u) & 1u) ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
+                    v = applyTouch(v, ((bestKey - 1u) & 1u) != 0u, a);
+                    ++farCount;
                 }
-                count = nTouch;
-            } else {
-                for (unsigned long long r = mk; r; r &= r - 1) v = applyScan(v, __ffsll((long long)r) - 1, cx, cy, a, count);
             }
-            if (count != nTouch) {
-                // The fast search disagrees with the mark pass: redo this cell the slow, exact way.
-                v = v0; count = 0;
+            if (farCount != nFar) {
+                // The fast paths disagree with the count pass: redo this cell the slow, exact way.
+                v = v0; nearCount = 0; farCount = 0;
                 for (unsigned long long r = mk; r; r &= r - 1) {
                     const int s = __ffsll((long long)r) - 1;
                     const ScanMeta m = a.meta[s];
-                    v = applyAllBeams(v, m, a.rel + m.beamBegin, cx - m.sx, cy - m.sy, a, count);
+                    v = applyAllBeams(v, m, a.rel + m.beamBegin, cx - m.sx, cy - m.sy, a, farCount);
                 }
                 atomicAdd(counters + 1, 1ull);
             }
+            total = nearCount + farCount;
             if (v != v0) *cell = v;
         }
     }
     __shared__ unsigned sCount[8];
-    unsigned c = count;
+    unsigned c = total;
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     if ((tid & 31) == 0) sCount[tid >> 5] = c;
@@ -425,6 +504,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
 
     int maxBeams = 0;
     for (int s = 0; s < n; ++s) maxBeams = std::max(maxBeams, scans->hit_begin[s + 1] - scans->hit_begin[s]);
+    if (maxBeams > 32767) return lgs_fail(c, LGS_ERR_INVALID, "integrate: %d beams in one scan (limit 32767)", maxBeams);
     ScanMeta* dMeta = reinterpret_cast<ScanMeta*>(w.meta.p);
     ScanMeta* hMeta = reinterpret_cast<ScanMeta*>(w.hMeta.p);
     GridRef g{grid->origin(), grid->nx, grid->ny, grid->pitch, grid->min_x, grid->min_y, grid->res};
@@ -450,9 +530,8 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     const double oddsHit = clampP(pHit) / (1.0 - clampP(pHit));
     const double oddsMiss = clampP(pMiss) / (1.0 - clampP(pMiss));
 
-    // Sub-batches: every scan owns one mask bit (<= 64), and fewer scans per launch keep the
-    // per-cell touch count inside the recorded list (kListCap), which is the fast path.
-    int sub = 16;
+    // Sub-batches: every scan owns one mask bit (<= 64).
+    int sub = 64;
     if (const char* e = getenv("LGS_INTEG_SUB")) sub = std::min(64, std::max(1, atoi(e)));   // tuning hook
     for (int s0 = 0; s0 < n; s0 += sub) {
         const int ns = std::min(sub, n - s0);
@@ -466,18 +545,35 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, grid->nx); y1 = std::min(y1, grid->ny);
         if (subBeams == 0 || x1 <= x0 || y1 <= y0) continue;
         const size_t region = (size_t)(x1 - x0) * (y1 - y0);
+        const int nScanBlocks = (int)((region + 1023) / 1024);
+        long long subTouches = 0;                       // upper bound of recorded keys: sum of ray lengths
+        for (int s = s0; s < s0 + ns; ++s) subTouches += (long long)hMeta[s].n * (hMeta[s].maxLen + 1);
         LGS_CUDA(c, w.mask.reserve(region));
         LGS_CUDA(c, w.expect.reserve(region));
+        LGS_CUDA(c, w.local.reserve(region));
+        LGS_CUDA(c, w.blockSums.reserve((size_t)nScanBlocks));
+        LGS_CUDA(c, w.lists.reserve((size_t)std::max<long long>(subTouches, 1)));
         LGS_CUDA(c, cudaMemsetAsync(w.mask.p, 0, region * sizeof(unsigned long long), c->stream));
         LGS_CUDA(c, cudaMemsetAsync(w.expect.p, 0, region * sizeof(unsigned), c->stream));
         dim3 gm((subBeams + 127) / 128, ns);
-        LGS_CUDA(c, w.lists.reserve(region * kListCap));
-        integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p, w.expect.p, w.lists.p);
+        integ_walk_kernel<false><<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p,
+                                                            w.expect.p, nullptr, nullptr, nullptr);
+        LGS_LAUNCH_CHECK(c);
+        integ_scan_blocks_kernel<<<nScanBlocks, 256, 0, c->stream>>>(w.expect.p, region, w.local.p, w.blockSums.p);
+        LGS_LAUNCH_CHECK(c);
+        integ_scan_sums_kernel<<<1, 1024, 0, c->stream>>>(w.blockSums.p, nScanBlocks);
+        LGS_LAUNCH_CHECK(c);
+        // pass 2 re-uses the count array as the per-cell cursor; the apply kernel needs the counts,
+        // which the cursors equal again once every touch has been recorded
+        LGS_CUDA(c, cudaMemsetAsync(w.expect.p, 0, region * sizeof(unsigned), c->stream));
+        integ_walk_kernel<true><<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p,
+                                                           w.expect.p, w.local.p, w.blockSums.p, w.lists.p);
         LGS_LAUNCH_CHECK(c);
         const long long warps = (long long)ns * kNearW * kNearW;
         integ_near_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, w.nearTab.p);
         LGS_LAUNCH_CHECK(c);
-        ApplyArgs a{dMeta + s0, w.rel.p, w.beta.p, w.nearTab.p, w.mask.p, w.expect.p, w.lists.p, pHit, pMiss, oddsHit, oddsMiss};
+        ApplyArgs a{dMeta + s0, w.rel.p, w.beta.p, w.nearTab.p, w.mask.p, w.expect.p, w.local.p, w.blockSums.p,
+                    w.lists.p, pHit, pMiss, oddsHit, oddsMiss};
         dim3 block(32, 8), gridDim((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
         integ_apply_kernel<<<gridDim, block, 0, c->stream>>>(a, g, x0, y0, x1, y1, w.counters.p);
         LGS_LAUNCH_CHECK(c);

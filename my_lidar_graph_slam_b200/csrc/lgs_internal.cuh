@@ -80,13 +80,13 @@ struct lgs_integ_ws {
     DevBuf<float> beta;
     DevBuf<unsigned short> nearTab;
     DevBuf<unsigned long long> mask, counters;
-    DevBuf<unsigned> expect, lists;
+    DevBuf<unsigned> expect, lists, local, blockSums;
     PinBuf<char> hMeta;
     PinBuf<unsigned long long> hCounters;
     long long fallbackCells = 0;
     void release() {
         sensor.release(); hit.release(); begin.release(); meta.release(); rel.release(); beta.release();
-        nearTab.release(); mask.release(); counters.release(); expect.release(); lists.release(); hMeta.release();
+        nearTab.release(); mask.release(); counters.release(); expect.release(); lists.release(); local.release(); blockSums.release(); hMeta.release();
         hCounters.release();
     }
 };
