@@ -485,16 +485,31 @@ def grid_clear(grid: Grid):
     grid.ctx.check(lib().lgs_grid_clear(grid.h))
 
 
+class PackedHits:
+    """Host-side lgs_hit_batch (contiguous arrays kept alive), built once and integrated many times."""
+
+    def __init__(self, sensor_xy, hits_list):
+        n = len(hits_list)
+        self.n = n
+        self.begin = np.zeros(n + 1, dtype=np.int32)
+        self.begin[1:] = np.cumsum([len(h) for h in hits_list])
+        self.hit = np.ascontiguousarray(np.concatenate(hits_list) if n and self.begin[-1] else np.zeros((0, 2)),
+                                        dtype=np.float64)
+        sxy = np.asarray(sensor_xy, dtype=np.float64)
+        self.sxy = np.ascontiguousarray(sxy.reshape(n, -1)[:, :2]) if n else np.zeros((0, 2))
+        self.c = HitBatch(n, _dptr(self.sxy), self.begin.ctypes.data_as(c_ip), _dptr(self.hit))
+
+    @property
+    def nbytes(self):
+        return self.hit.nbytes + self.sxy.nbytes + self.begin.nbytes
+
+
+def integrate_packed(ctx: Context, grid: Grid, packed: PackedHits, p_hit=0.6, p_miss=0.45) -> int:
+    cnt = C.c_longlong()
+    ctx.check(lib().lgs_grid_integrate_scans(ctx.h, grid.h, C.byref(packed.c), p_hit, p_miss, C.byref(cnt)))
+    return cnt.value
+
+
 def integrate_scans(ctx: Context, grid: Grid, sensor_xy, hits_list, p_hit=0.6, p_miss=0.45) -> int:
     """lgs_grid_integrate_scans for scans given as (sensor_xy[k][2], [hit_xy arrays]) -> updates."""
-    n = len(hits_list)
-    begin = np.zeros(n + 1, dtype=np.int32)
-    begin[1:] = np.cumsum([len(h) for h in hits_list])
-    hit = np.ascontiguousarray(np.concatenate(hits_list) if n and begin[-1] else np.zeros((0, 2)),
-                               dtype=np.float64)
-    sxy = np.asarray(sensor_xy, dtype=np.float64)
-    sxy = np.ascontiguousarray(sxy.reshape(n, -1)[:, :2]) if n else np.zeros((0, 2))
-    hb = HitBatch(n, _dptr(sxy), begin.ctypes.data_as(c_ip), _dptr(hit))
-    cnt = C.c_longlong()
-    ctx.check(lib().lgs_grid_integrate_scans(ctx.h, grid.h, C.byref(hb), p_hit, p_miss, C.byref(cnt)))
-    return cnt.value
+    return integrate_packed(ctx, grid, PackedHits(sensor_xy, hits_list), p_hit, p_miss)

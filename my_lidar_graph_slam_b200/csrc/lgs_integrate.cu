@@ -7,43 +7,52 @@
 // grid_map/binary_bayes_grid_cell.hpp:75-119).
 //
 // The cell update is order dependent at the bit level: each cell must see its
-// touches in (scan, beam) order.  Instead of scattering updates (atomics cannot be ordered),
-// every grid cell is OWNED by one thread, which walks the scans of the batch in order and, for
-// each scan, the beams that can touch the cell in beam order, deciding membership in O(1) from
-// the closed form of the reference's Bresenham:
-//     x-major (|dx| > |dy|):  y_k = y0 + sy * floor((2|dy|k + |dx|) / (2|dx|)),  k = 0..|dx|
-//     y-major (otherwise)  :  x_k = x0 + sx * floor((2|dx|k + |dy|) / (2|dy|)),  k = 0..|dy|
-// (cells k < length are misses, k = length is the hit).  That is conflict free by
-// construction and applies exactly the CPU's IEEE sequence (div/mul/add intrinsics, no FMA).
+// touches in (scan, beam) order, so updates cannot be scattered with atomics.  But WHICH touches a
+// cell sees, and in which order, does not depend on the cell values.  The work is therefore split
+// like a tiled rasteriser, over chunks of <= 64 scans:
 //
-// Finding the candidate beams of a cell:
-//  * far field (Chebyshev distance to the sensor cell > kNear): beams are angularly sorted, so
-//    the candidates are a binary-searched window of +-(2.2 / d + 0.001) rad around the cell's
-//    direction -- a proven superset (cell centres on a Bresenham line lie within 0.5 cell of
-//    the centre-to-centre segment, whose end points are within 0.71 cell of the true ray);
-//  * near field (<= kNear cells): nearly every beam passes, so one warp per (scan, near cell)
-//    tests all beams with ballots once and stores the ordered touch sequence run-length
-//    encoded (M^a H^b M^c ...); the owning thread then just applies the runs, stopping a run
-//    early once the value reaches its fixed point.
-// Scans whose beams are not angularly monotone fall back to testing every beam (still exact).
+//   1. mark   one thread per (scan, beam) walks the reference's Bresenham and, whenever the ray
+//             enters another 16x16-cell tile, folds its beam index into the tile's [kmin, kmax)
+//             range for that scan (idempotent atomics: min / max / or -- order free);
+//   2. pairs  every tile turns its scan mask into a contiguous, scan-ordered run of
+//             (tile, scan, kmin, kmax) pairs;
+//   3. touch  fully parallel over the pairs: one block per pair drops the cells of the beams
+//             kmin..kmax that fall into the tile into per-cell bitmaps in shared memory (bit = beam,
+//             so ascending bits ARE the CPU's beam order), using the closed form of the
+//             reference's Bresenham (step k of a ray is independent of step k - 1):
+//                 x-major (|dx| > |dy|):  y_k = y0 + sy * floor((2|dy|k + |dx|) / (2|dx|)),  k = 0..|dx|
+//                 y-major (otherwise)  :  x_k = x0 + sx * floor((2|dx|k + |dy|) / (2|dy|)),  k = 0..|dy|
+//             (cells k < length are misses, k = length is the hit), then every cell packs its
+//             ordered miss/hit sequence into one 32-bit record (raw bits up to 26 touches,
+//             three run lengths beyond -- the near field is M^a H^b M^c);
+//   4. fold   one thread OWNS one cell and applies the records of its tile in scan order with
+//             exactly the CPU's IEEE sequence (div/mul/add intrinsics, no FMA), leaving a run early
+//             once the value reaches its fixed point (the probability clamp makes runs idempotent).
+//
+// Nothing depends on beams being angularly sorted: an unsorted scan only widens [kmin, kmax).
+// A record that fits neither format (alternating hits and misses in a cell crossed by > 26 beams)
+// is marked, and the owner re-derives that (cell, scan) by testing the beams kmin..kmax itself.
 #include <cmath>
 
 #include "lgs_internal.cuh"
 
 namespace {
 
-constexpr int kNear = 16;                      // near-field half width (cells)
-constexpr int kNearW = 2 * kNear + 1;
-constexpr int kRuns = 15;                      // RLE runs kept per (scan, near cell)
-constexpr unsigned short kRleOverflow = 0xFFFF;
-constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr int kTile = 16;                      // tile side (cells)
+constexpr int kTileShift = 4;
+constexpr int kTileCells = kTile * kTile;      // = threads per block of the touch / fold passes
+constexpr int kChunk = 64;                     // scans per chunk (one mask bit each)
+constexpr int kSeg = 128;                      // beams per shared-memory bitmap segment
+constexpr int kSegWords = kSeg / 32;
+constexpr unsigned kRawMax = 26;               // touches a raw record holds
+constexpr unsigned kRecOverflow = 0xFFFFFFFFu;
+constexpr unsigned kRecSide = 31u << 26;
+constexpr size_t kRecordBudget = (size_t)1 << 30;   // bytes of records per chunk before it is split
 
 struct ScanMeta {
     int sx, sy;          // sensor cell
     int beamBegin, n;    // beams of this scan
     int maxLen;          // max Chebyshev ray length in cells
-    int unsorted;        // beams not angularly monotone -> test all beams
-    float ang0;          // world angle of beam 0
     int bad;             // a touched cell lies outside the grid
 };
 
@@ -89,17 +98,9 @@ __device__ __forceinline__ int rayTouch(int rx, int ry, int ex, int ey) {
     return k == amaj ? 2 : 1;
 }
 
-__device__ __forceinline__ float wrapBeta(float a) {   // into [-0.01, 2*pi - 0.01)
-    a = fmodf(a, kTwoPi);
-    if (a < -0.01f) a += kTwoPi;
-    if (a >= kTwoPi - 0.01f) a -= kTwoPi;
-    return a;
-}
-
 // ---- pre-pass A: sensor cells ---------------------------------------------------------------------
 __global__ void integ_sensor_kernel(const double* __restrict__ sensorXY, const int* __restrict__ hitBegin,
-                                    const double* __restrict__ hitXY, int nScans, GridRef g,
-                                    ScanMeta* __restrict__ meta) {
+                                    int nScans, GridRef g, ScanMeta* __restrict__ meta) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nScans) return;
     ScanMeta m;
@@ -108,351 +109,306 @@ __global__ void integ_sensor_kernel(const double* __restrict__ sensorXY, const i
     m.sy = __double2int_rd(__ddiv_rn(__dsub_rn(sensorXY[2 * s + 1], g.minY), g.res));
     m.beamBegin = hitBegin[s];
     m.n = hitBegin[s + 1] - hitBegin[s];
-    m.maxLen = 0; m.unsorted = 0; m.bad = 0;
-    m.ang0 = 0.f;
-    if (m.n > 0)
-        m.ang0 = atan2f((float)(hitXY[2 * (size_t)m.beamBegin + 1] - sensorXY[2 * s + 1]),
-                        (float)(hitXY[2 * (size_t)m.beamBegin] - sensorXY[2 * s]));
-    if (m.sx < 0 || m.sx >= g.nx || m.sy < 0 || m.sy >= g.ny) m.bad = 1;
+    m.maxLen = 0;
+    m.bad = (m.sx < 0 || m.sx >= g.nx || m.sy < 0 || m.sy >= g.ny) ? 1 : 0;
     meta[s] = m;
 }
 
-// ---- pre-pass B: per beam end cell (relative), angle ------------------------------------------------
-__global__ void integ_beam_kernel(const double* __restrict__ sensorXY, const double* __restrict__ hitXY,
-                                  int nScans, GridRef g, ScanMeta* __restrict__ meta,
-                                  int2* __restrict__ rel, float* __restrict__ beta) {
+// ---- pre-pass B: per beam end cell relative to the sensor cell ---------------------------------------
+__global__ void integ_beam_kernel(const double* __restrict__ hitXY, GridRef g, ScanMeta* __restrict__ meta,
+                                  int2* __restrict__ rel) {
     const int s = blockIdx.y;
-    const ScanMeta m = meta[s];
+    const int n = meta[s].n, beamBegin = meta[s].beamBegin, sx = meta[s].sx, sy = meta[s].sy;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.n) return;
-    const size_t b = (size_t)m.beamBegin + i;
-    const double hx = hitXY[2 * b], hy = hitXY[2 * b + 1];
-    const int ex = __double2int_rd(__ddiv_rn(__dsub_rn(hx, g.minX), g.res));
-    const int ey = __double2int_rd(__ddiv_rn(__dsub_rn(hy, g.minY), g.res));
-    if (ex < 0 || ex >= g.nx || ey < 0 || ey >= g.ny) atomicOr(&meta[s].bad, 1);
-    const int dx = ex - m.sx, dy = ey - m.sy;
-    rel[b] = make_int2(dx, dy);
-    atomicMax(&meta[s].maxLen, max(abs(dx), abs(dy)));
-    const float a = atan2f((float)(hy - sensorXY[2 * s + 1]), (float)(hx - sensorXY[2 * s]));
-    beta[b] = i == 0 ? 0.f : wrapBeta(a - m.ang0);
+    int len = 0;
+    if (i < n) {
+        const size_t b = (size_t)beamBegin + i;
+        const double2 h = reinterpret_cast<const double2*>(hitXY)[b];
+        const int ex = __double2int_rd(__ddiv_rn(__dsub_rn(h.x, g.minX), g.res));
+        const int ey = __double2int_rd(__ddiv_rn(__dsub_rn(h.y, g.minY), g.res));
+        if (ex < 0 || ex >= g.nx || ey < 0 || ey >= g.ny) atomicOr(&meta[s].bad, 1);
+        const int dx = ex - sx, dy = ey - sy;
+        rel[b] = make_int2(dx, dy);
+        len = max(abs(dx), abs(dy));
+    }
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(&meta[s].maxLen, len);
 }
 
-__global__ void integ_sorted_kernel(ScanMeta* __restrict__ meta, const float* __restrict__ beta) {
-    const int s = blockIdx.y;
-    const ScanMeta m = meta[s];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 1 || i >= m.n) return;
-    const size_t b = (size_t)m.beamBegin + i;
-    if (beta[b] < beta[b - 1]) atomicOr(&meta[s].unsorted, 1);
-}
-
-// ---- pre-pass C: near-field touch sequences, run-length encoded ---------------------------------------
-// One warp per (scan, near cell).  Entry = (type << 15) | count with type 1 = hit; 0 terminates.
+// ---- 1. mark: beam index range per (tile, scan) ------------------------------------------------------
+// One thread per (scan, beam, 16-step piece of the ray); consecutive lanes = consecutive beams at
+// the same distance from the sensor, so a warp's atomics mostly hit the same few addresses.
+// (x0, y0) = tile-aligned origin of the chunk's region, tw = tiles per region row.  The racy
+// pre-reads only save atomics: kmin only ever decreases and kmax only ever increases.
 __global__ void __launch_bounds__(128)
-integ_near_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
-                  unsigned short* __restrict__ table) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= nScans * kNearW * kNearW) return;
-    const int s = warp / (kNearW * kNearW);
-    const int c = warp - s * (kNearW * kNearW);
-    const int rx = c % kNearW - kNear, ry = c / kNearW - kNear;
-    const ScanMeta m = meta[s];
-    unsigned short* out = table + (size_t)warp * (kRuns + 1);
-    int nRuns = 0, curType = -1, curCount = 0;
-    bool overflow = false;
-    for (int base = 0; base < m.n; base += 32) {
-        const int i = base + lane;
-        int ty = 0;
-        if (i < m.n) {
-            const int2 e = __ldg(rel + m.beamBegin + i);
-            ty = rayTouch(rx, ry, e.x, e.y);
-        }
-        unsigned touched = __ballot_sync(0xffffffffu, ty != 0);
-        const unsigned hits = __ballot_sync(0xffffffffu, ty == 2);
-        while (touched) {                       // uniform across the warp
-            const int bit = __ffs(touched) - 1;
-            const int type = (hits >> bit) & 1;
-            // length of the run of equal type among the touched bits starting at `bit`
-            const unsigned same = type ? (touched & hits) : (touched & ~hits);
-            const unsigned other = touched & ~same;
-            const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xffffffffu;
-            const unsigned runBits = same & upto;
-            const int cnt = __popc(runBits);
-            if (type == curType) {
-                curCount += cnt;
-            } else {
-                if (curType >= 0) {
-                    if (nRuns < kRuns) { if (lane == 0) out[nRuns] = (unsigned short)((curType << 15) | curCount); }
-                    else overflow = true;
-                    ++nRuns;
-                }
-                curType = type; curCount = cnt;
-            }
-            touched &= ~runBits;
-        }
-    }
-    if (curType >= 0) {
-        if (nRuns < kRuns) { if (lane == 0) out[nRuns] = (unsigned short)((curType << 15) | curCount); }
-        else overflow = true;
-        ++nRuns;
-    }
-    if (lane == 0) {
-        if (overflow || m.n > 32767) out[0] = kRleOverflow;
-        else out[nRuns] = 0;
-    }
-}
-
-// ---- ray walks: counting sort of the far-field touches by cell ----------------------------------------
-// One thread per (scan, beam) walks the reference's Bresenham (util.hpp:257-303) twice.  Pass 1
-// (FILL = false) ORs the scan's bit into every touched cell and counts the far-field touches per
-// cell; after an exclusive prefix sum over the counts, pass 2 (FILL = true) drops one 32-bit key per
-// far-field touch into the cell's own segment.  Near-field touches (<= kNear cells from the sensor
-// cell: thousands per cell) are not recorded; the run-length table covers them.
-//   key = 1 + ((scan << 17) | (beam << 1) | isHit): ascending key == the CPU's (scan, beam) order.
-template <bool FILL>
-__global__ void __launch_bounds__(128)
-integ_walk_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int nScans,
-                  int x0, int y0, int rw, unsigned long long* __restrict__ mask,
-                  unsigned* __restrict__ cnt, const unsigned* __restrict__ local,
-                  const unsigned* __restrict__ blockSums, unsigned* __restrict__ keys) {
+integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int x0, int y0, int tw,
+                  int beamsPad, unsigned* __restrict__ kmin, unsigned* __restrict__ kmax) {
     const int s = blockIdx.y;
     const ScanMeta m = meta[s];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t % beamsPad, piece = t / beamsPad;
     if (i >= m.n) return;
     const int2 e = __ldg(rel + m.beamBegin + i);
-    const unsigned long long bit = 1ull << s;
-    int x = m.sx, y = m.sy;
-    const int x1 = m.sx + e.x, y1 = m.sy + e.y;
-    const int sx = e.x < 0 ? -1 : 1, sy = e.y < 0 ? -1 : 1;
-    const int dx = abs(e.x * 2), dy = abs(e.y * 2);
-    const unsigned keyMiss = 1u + (((unsigned)s << 17) | ((unsigned)i << 1));
-    auto touch = [&]() {
-        const size_t c = (size_t)(y - y0) * rw + (x - x0);
-        const bool nearField = max(abs(x - m.sx), abs(y - m.sy)) <= kNear;
-        if (!FILL) {
-            if (!(mask[c] & bit)) atomicOr(mask + c, bit);      // racy pre-check only saves atomics
-            if (!nearField) atomicAdd(cnt + c, 1u);
-        } else if (!nearField) {
-            const unsigned slot = local[c] + blockSums[c >> 10] + atomicAdd(cnt + c, 1u);
-            keys[slot] = keyMiss + ((x == x1 && y == y1) ? 1u : 0u);
-        }
-    };
-    touch();
-    if (dx > dy) {
-        int err = dy - dx / 2;
-        while (x != x1) {
-            if (err >= 0) { y += sy; err -= dx; }
-            x += sx; err += dy;
-            touch();
-        }
-    } else {
-        int err = dx - dy / 2;
-        while (y != y1) {
-            if (err >= 0) { x += sx; err -= dy; }
-            y += sy; err += dx;
-            touch();
-        }
+    const int ax = abs(e.x), ay = abs(e.y);
+    const bool xMajor = ax > ay;                            // util.hpp:276 vs :288
+    const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
+    const int kBegin = piece * kTile;
+    if (kBegin > amaj) return;
+    const int kEnd = min(kBegin + kTile - 1, amaj);
+    const int sMaj = (xMajor ? e.x : e.y) < 0 ? -1 : 1, sMin = (xMajor ? e.y : e.x) < 0 ? -1 : 1;
+    const int bx = m.sx - x0, by = m.sy - y0;
+    int last = -1;
+    for (int k = kBegin; k <= kEnd; ++k) {
+        const int minor = amaj ? (int)((unsigned)(2 * amin * k + amaj) / (unsigned)(2 * amaj)) : 0;
+        const int x = bx + (xMajor ? sMaj * k : sMin * minor);
+        const int y = by + (xMajor ? sMin * minor : sMaj * k);
+        const int tile = (y >> kTileShift) * tw + (x >> kTileShift);
+        if (tile == last) continue;
+        last = tile;
+        const size_t idx = (size_t)tile * kChunk + s;
+        if (__ldcg(kmin + idx) > (unsigned)i) atomicMin(kmin + idx, (unsigned)i);
+        if (__ldcg(kmax + idx) < (unsigned)i + 1u) atomicMax(kmax + idx, (unsigned)i + 1u);
     }
 }
 
-// Exclusive prefix sum over the per-cell counts: 1024 cells per block, then the block totals.
-__global__ void __launch_bounds__(256)
-integ_scan_blocks_kernel(const unsigned* __restrict__ cnt, size_t n, unsigned* __restrict__ local,
-                         unsigned* __restrict__ blockSums) {
-    __shared__ unsigned sWarp[8];
-    const size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
-    unsigned v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { v[k] = base + k < n ? cnt[base + k] : 0u; sum += v[k]; }
-    unsigned inc = sum;                                   // inclusive scan of the per-thread sums
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) sWarp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        unsigned w = lane < 8 ? sWarp[lane] : 0u;
-        for (int o = 1; o < 8; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-        if (lane < 8) sWarp[lane] = w;
+// ---- 2. pairs: scan-ordered (tile, scan, k0, k1) runs; resets the mark buffers -------------------------
+// One warp per tile: lanes read the tile's 64 kmax entries (non-zero = the scan touches the tile).
+__global__ void __launch_bounds__(128)
+integ_pairs_kernel(int nTiles, unsigned* __restrict__ kmin, unsigned* __restrict__ kmax,
+                   uint2* __restrict__ tileInfo, int4* __restrict__ pairs, unsigned* __restrict__ nPairs) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= nTiles) return;
+    const size_t idx = (size_t)t * kChunk + lane;
+    const unsigned hiA = kmax[idx], hiB = kmax[idx + 32];
+    const unsigned mA = __ballot_sync(0xffffffffu, hiA != 0u), mB = __ballot_sync(0xffffffffu, hiB != 0u);
+    const unsigned cnt = (unsigned)(__popc(mA) + __popc(mB));
+    unsigned base = 0;
+    if (cnt && lane == 0) base = atomicAdd(nPairs, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane == 0) tileInfo[t] = make_uint2(base, cnt);
+    const unsigned below = (1u << lane) - 1u;
+    if (hiA) {
+        pairs[base + __popc(mA & below)] = make_int4(t, lane, (int)kmin[idx], (int)hiA);
+        kmin[idx] = 0xFFFFFFFFu; kmax[idx] = 0u;
     }
-    __syncthreads();
-    unsigned run = inc - sum + (wid ? sWarp[wid - 1] : 0u);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { if (base + k < n) local[base + k] = run; run += v[k]; }
-    if (threadIdx.x == 255) blockSums[blockIdx.x] = sWarp[7];
-}
-
-__global__ void __launch_bounds__(1024)
-integ_scan_sums_kernel(unsigned* __restrict__ blockSums, int nBlocks) {
-    __shared__ unsigned sWarp[32];
-    __shared__ unsigned sCarry;
-    if (threadIdx.x == 0) sCarry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < nBlocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const unsigned v = i < nBlocks ? blockSums[i] : 0u;
-        unsigned inc = v;
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) sWarp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned w = sWarp[lane];
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-            sWarp[lane] = w;
-        }
-        __syncthreads();
-        const unsigned excl = sCarry + inc - v + (wid ? sWarp[wid - 1] : 0u);
-        if (i < nBlocks) blockSums[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) sCarry = excl + v;
-        __syncthreads();
+    if (hiB) {
+        pairs[base + __popc(mA) + __popc(mB & below)] = make_int4(t, lane + 32, (int)kmin[idx + 32], (int)hiB);
+        kmin[idx + 32] = 0xFFFFFFFFu; kmax[idx + 32] = 0u;
     }
 }
 
-// ---- apply pass: one thread owns one cell ----------------------------------------------------------
-constexpr unsigned kSortCap = 160;     // recorded touches a thread orders by repeated-minimum selection
-
-struct ApplyArgs {
-    const ScanMeta* meta;
-    const int2* rel;
-    const float* beta;
-    const unsigned short* nearTab;
-    const unsigned long long* mask;
-    const unsigned* cnt;          // far-field touches per cell
-    const unsigned* local;        // exclusive prefix sum within 1024-cell blocks
-    const unsigned* blockSums;    // exclusive prefix sum of the block totals
-    const unsigned* keys;
-    double pHit, pMiss, oddsHit, oddsMiss;
+// ---- 3. touch: ordered miss/hit sequence of every cell of a (tile, scan) pair ----------------------------
+// Record formats (32 bit):   0                      no touch
+//   raw  [31] = 0, [30:26] = count (1..26), [25:0] = types in order (1 = hit)
+//   runs [31] = 1, [30] = type of the first run, [29:20] [19:10] [9:0] = three alternating run lengths
+//   side [31] = 0, [30:26] = 31, [25:0] = offset (units of 8 words) of the cell's raw touch / hit
+//        bitmap words in the side buffer: sequences that fit neither format (a near cell whose
+//        beams alternate between ending in it and passing through)
+//   0xFFFFFFFF               side buffer exhausted: the owner re-derives the sequence from the beams
+struct TouchSeq {
+    unsigned cnt = 0, raw = 0, r0 = 0, r1 = 0, r2 = 0;
+    int nrun = 0, cur = -1, first = 0;
+    __device__ __forceinline__ void append(int type, unsigned n) {
+        if (cnt < kRawMax && type) raw |= (n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u)) << cnt;
+        cnt += n;
+        if (type != cur) { cur = type; if (++nrun == 1) first = type; }
+        if (nrun == 1) r0 += n; else if (nrun == 2) r1 += n; else if (nrun == 3) r2 += n;
+    }
+    __device__ __forceinline__ unsigned record() const {
+        if (cnt == 0) return 0u;
+        if (cnt <= kRawMax) return (cnt << 26) | (raw & ((1u << 26) - 1u));
+        if (nrun <= 3 && r0 < 1023u && r1 < 1023u && r2 < 1023u)
+            return 0x80000000u | ((unsigned)first << 30) | (r0 << 20) | (r1 << 10) | r2;
+        return kRecOverflow;
+    }
 };
 
-__device__ __forceinline__ double applyTouch(double v, bool hit, const ApplyArgs& a) {
-    return hit ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
-}
-
-// All touches of scan `m` on the cell at (rx, ry) from its sensor cell, in beam order, by testing
-// every beam (exact, slow): the fallback when the fast paths cannot be used or disagree.
-__device__ __forceinline__ double applyAllBeams(double v, const ScanMeta& m, const int2* __restrict__ e,
-                                                int rx, int ry, const ApplyArgs& a, unsigned& count) {
-    for (int i = 0; i < m.n; ++i) {
-        const int2 ee = __ldg(e + i);
-        const int ty = rayTouch(rx, ry, ee.x, ee.y);
-        if (ty) { v = applyTouch(v, ty == 2, a); ++count; }
-    }
-    return v;
-}
-
-// Near field of scan s: apply the run-length encoded touch sequence.
-__device__ __forceinline__ double applyNear(double v, int s, const ScanMeta& m, int rx, int ry,
-                                            const ApplyArgs& a, unsigned& count) {
-    const unsigned short* t = a.nearTab + ((size_t)s * kNearW * kNearW + (ry + kNear) * kNearW + (rx + kNear)) * (kRuns + 1);
-    if (t[0] == kRleOverflow) return applyAllBeams(v, m, a.rel + m.beamBegin, rx, ry, a, count);
-    for (int k = 0; k < kRuns; ++k) {
-        const unsigned short ent = t[k];
-        if (ent == 0) break;
-        const int cnt = ent & 0x7fff;
-        const bool hit = (ent >> 15) != 0;
-        count += cnt;
-        for (int j = 0; j < cnt; ++j) {
-            const double nv = applyTouch(v, hit, a);
-            if (nv == v) break;        // fixed point: the rest of the run is a no-op
-            v = nv;
-        }
-    }
-    return v;
-}
-
-// Far field of scan s without a recorded list: binary-searched angular window of candidate beams.
-__device__ __forceinline__ double applyFarSearch(double v, const ScanMeta& m, int rx, int ry,
-                                                 const ApplyArgs& a, unsigned& count) {
-    const int2* __restrict__ e = a.rel + m.beamBegin;
-    if (m.unsorted) return applyAllBeams(v, m, e, rx, ry, a, count);
-    const float* __restrict__ bt = a.beta + m.beamBegin;
-    const float d = sqrtf((float)(rx * rx + ry * ry));
-    const float delta = 2.2f / d + 1e-3f;
-    const float bc = wrapBeta(atan2f((float)ry, (float)rx) - m.ang0);
-    const float bLast = __ldg(bt + m.n - 1);
-#pragma unroll 1
-    for (int w = -1; w <= 1; ++w) {
-        const float lo = bc + w * kTwoPi - delta, hi = bc + w * kTwoPi + delta;
-        if (hi < -0.01f || lo > bLast) continue;
-        int lb = 0, ub = m.n;                  // first i with beta[i] >= lo
-        while (lb < ub) {
-            const int mid = (lb + ub) >> 1;
-            if (__ldg(bt + mid) < lo) lb = mid + 1; else ub = mid;
-        }
-        for (int i = lb; i < m.n && __ldg(bt + i) <= hi; ++i) {
-            const int2 ee = __ldg(e + i);
-            const int ty = rayTouch(rx, ry, ee.x, ee.y);
-            if (ty) { v = applyTouch(v, ty == 2, a); ++count; }
-        }
-    }
-    return v;
-}
-
-__global__ void __launch_bounds__(256)
-integ_apply_kernel(ApplyArgs a, GridRef g, int x0, int y0, int x1, int y1,
-                   unsigned long long* __restrict__ counters /* [0] updates, [1] fallback cells */) {
-    const int cx = x0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int cy = y0 + blockIdx.y * blockDim.y + threadIdx.y;
-    unsigned total = 0;
-    if (cx < x1 && cy < y1) {
-        const size_t ridx = (size_t)(cy - y0) * (x1 - x0) + (cx - x0);
-        const unsigned long long mk = a.mask[ridx];
-        if (mk) {
-            double* cell = g.origin + (size_t)cy * g.pitch + cx;
-            const double v0 = *cell;
-            double v = v0;
-            const unsigned nFar = a.cnt[ridx];
-            const unsigned* __restrict__ K = a.keys + a.local[ridx] + a.blockSums[ridx >> 10];
-            unsigned nearCount = 0, farCount = 0;
-            unsigned prev = 0;
-            for (unsigned long long r = mk; r; r &= r - 1) {           // scans in order
-                const int s = __ffsll((long long)r) - 1;
-                const ScanMeta m = a.meta[s];
-                const int rx = cx - m.sx, ry = cy - m.sy;
-                if (max(abs(rx), abs(ry)) <= kNear) { v = applyNear(v, s, m, rx, ry, a, nearCount); continue; }
-                if (nFar > kSortCap) { v = applyFarSearch(v, m, rx, ry, a, farCount); continue; }
-                // this scan's recorded touches in ascending key (= beam) order, by repeated minimum
-                const unsigned hiKey = (((unsigned)s + 1u) << 17);     // keys of scan s are in (s<<17, hiKey]
-                prev = max(prev, (unsigned)s << 17);
-                for (;;) {
-                    unsigned bestKey = 0xffffffffu;
-                    for (unsigned j = 0; j < nFar; ++j) {
-                        const unsigned key = __ldg(K + j);
-                        if (key > prev && key < bestKey) bestKey = key;
+__global__ void __launch_bounds__(kTileCells)
+integ_touch_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel,
+                   const int4* __restrict__ pairs, const unsigned* __restrict__ nPairs, int x0, int y0,
+                   int tw, unsigned* __restrict__ records, unsigned* __restrict__ side,
+                   unsigned* __restrict__ sideCursor, unsigned sideCap,
+                   unsigned long long* __restrict__ counters) {
+    __shared__ unsigned sTouch[kSegWords * kTileCells];     // [word][cell]
+    __shared__ unsigned sHit[kSegWords * kTileCells];
+    __shared__ unsigned sSum[kTileCells / 32];
+    const int tid = threadIdx.x;
+    const unsigned nP = *nPairs;
+    unsigned total = 0, overflow = 0;
+    for (unsigned p = blockIdx.x; p < nP; p += gridDim.x) {
+        const int4 pr = pairs[p];
+        const ScanMeta m = meta[pr.y];
+        const int ox = x0 + (pr.x % tw) * kTile - m.sx;     // tile origin relative to the sensor cell
+        const int oy = y0 + (pr.x / tw) * kTile - m.sy;
+        const int2* __restrict__ E = rel + m.beamBegin;
+        TouchSeq seq;
+        unsigned rec = 0u, sideOff = 0u;
+        // pass 0 builds the records; pass 1 (only if a cell of this pair fits no record format)
+        // repeats the bitmaps and streams the raw words of those cells to the side buffer
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int seg = pr.z; seg < pr.w; seg += kSeg) {
+#pragma unroll
+                for (int w = 0; w < kSegWords; ++w) { sTouch[w * kTileCells + tid] = 0u; sHit[w * kTileCells + tid] = 0u; }
+                __syncthreads();
+                const int nb = min(kSeg, pr.w - seg);
+                for (int it = tid; it < nb * kTile; it += kTileCells) {
+                    const int b = it >> kTileShift, j = it & (kTile - 1);
+                    const int2 e = __ldg(E + seg + b);
+                    const int ax = abs(e.x), ay = abs(e.y);
+                    const bool xMajor = ax > ay;
+                    const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
+                    const int eMaj = xMajor ? e.x : e.y, eMin = xMajor ? e.y : e.x;
+                    const int oMaj = xMajor ? ox : oy, oMin = xMajor ? oy : ox;
+                    const int rMaj = oMaj + j;                               // this item's column (row)
+                    const int k = eMaj < 0 ? -rMaj : rMaj;                   // step along the major axis
+                    if (k < 0 || k > amaj) continue;
+                    const int minor = amaj ? (int)((unsigned)(2 * amin * k + amaj) / (unsigned)(2 * amaj)) : 0;
+                    const int lMin = (eMin < 0 ? -minor : minor) - oMin;
+                    if ((unsigned)lMin >= (unsigned)kTile) continue;
+                    const int cell = xMajor ? (lMin * kTile + j) : (j * kTile + lMin);
+                    const unsigned bitb = 1u << (b & 31);
+                    atomicOr(&sTouch[(b >> 5) * kTileCells + cell], bitb);
+                    if (k == amaj) atomicOr(&sHit[(b >> 5) * kTileCells + cell], bitb);
+                }
+                __syncthreads();
+                if (pass == 0) {
+#pragma unroll
+                    for (int w = 0; w < kSegWords; ++w) {
+                        unsigned t = sTouch[w * kTileCells + tid];
+                        if (t == 0u) continue;
+                        const unsigned h = sHit[w * kTileCells + tid];
+                        while (t) {                              // maximal runs of equal type, ascending beams
+                            const int type = (h >> (__ffs(t) - 1)) & 1;
+                            const unsigned same = type ? (t & h) : (t & ~h);
+                            const unsigned other = t & ~same;
+                            const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
+                            const unsigned run = same & upto;
+                            seq.append(type, (unsigned)__popc(run));
+                            t &= ~run;
+                        }
                     }
-                    if (bestKey > hiKey) break;
-                    prev = bestKey;
-                    v = applyTouch(v, ((bestKey - 1u) & 1u) != 0u, a);
-                    ++farCount;
+                } else if ((rec >> 26) == 31u) {
+                    unsigned* out = side + (size_t)sideOff + (size_t)((seg - pr.z) / kSeg) * (2 * kSegWords);
+#pragma unroll
+                    for (int w = 0; w < kSegWords; ++w) {
+                        out[2 * w] = sTouch[w * kTileCells + tid];
+                        out[2 * w + 1] = sHit[w * kTileCells + tid];
+                    }
                 }
+                __syncthreads();
             }
-            if (farCount != nFar) {
-                // The fast paths disagree with the count pass: redo this cell the slow, exact way.
-                v = v0; nearCount = 0; farCount = 0;
-                for (unsigned long long r = mk; r; r &= r - 1) {
-                    const int s = __ffsll((long long)r) - 1;
-                    const ScanMeta m = a.meta[s];
-                    v = applyAllBeams(v, m, a.rel + m.beamBegin, cx - m.sx, cy - m.sy, a, farCount);
+            if (pass == 0) {
+                rec = seq.record();
+                if (rec == kRecOverflow) {
+                    const unsigned words = (unsigned)((pr.w - pr.z + kSeg - 1) / kSeg) * (2 * kSegWords);
+                    sideOff = atomicAdd(sideCursor, words);
+                    if (sideOff + words <= sideCap) rec = kRecSide | (sideOff >> 3);
                 }
-                atomicAdd(counters + 1, 1ull);
+                if (!__syncthreads_or((rec >> 26) == 31u)) break;
             }
-            total = nearCount + farCount;
-            if (v != v0) *cell = v;
         }
+        records[(size_t)p * kTileCells + tid] = rec;
+        total += seq.cnt;
+        overflow += rec == kRecOverflow ? 1u : 0u;
     }
-    __shared__ unsigned sCount[8];
-    unsigned c = total;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if ((tid & 31) == 0) sCount[tid >> 5] = c;
+    // one atomic per block: touches (= Update calls of the CPU) and overflowed records
+    unsigned v = total | 0u;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    unsigned ov = overflow;
+    for (int o = 16; o > 0; o >>= 1) ov += __shfl_down_sync(0xffffffffu, ov, o);
+    if ((tid & 31) == 0) sSum[tid >> 5] = v;
     __syncthreads();
     if (tid == 0) {
         unsigned long long tot = 0;
-        for (int k = 0; k < (int)(blockDim.x * blockDim.y + 31) / 32; ++k) tot += sCount[k];
+        for (int k = 0; k < kTileCells / 32; ++k) tot += sSum[k];
         if (tot) atomicAdd(counters, tot);
     }
+    if ((tid & 31) == 0 && ov) atomicAdd(counters + 1, (unsigned long long)ov);
+}
+
+// ---- 4. fold: one thread owns one cell ---------------------------------------------------------------
+struct FoldArgs {
+    const ScanMeta* meta;
+    const int2* rel;
+    const uint2* tileInfo;
+    const int4* pairs;
+    const unsigned* records;
+    const unsigned* side;
+    double pHit, pMiss, oddsHit, oddsMiss;
+};
+
+__device__ __forceinline__ double applyRun(double v, bool hit, unsigned n, const FoldArgs& a) {
+    const double p = hit ? a.pHit : a.pMiss, odds = hit ? a.oddsHit : a.oddsMiss;
+    for (unsigned j = 0; j < n; ++j) {
+        const double nv = bayesUpdate(v, p, odds);
+        if (nv == v) break;                // fixed point: the rest of the run is a no-op
+        v = nv;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kTileCells)
+integ_fold_kernel(FoldArgs a, GridRef g, int x0, int y0, int tw) {
+    const uint2 info = a.tileInfo[blockIdx.x];
+    if (info.y == 0u) return;
+    const int tid = threadIdx.x;
+    const int cx = x0 + (blockIdx.x % tw) * kTile + (tid & (kTile - 1));
+    const int cy = y0 + (blockIdx.x / tw) * kTile + (tid >> kTileShift);
+    const bool inside = cx < g.nx && cy < g.ny;
+    double* cell = g.origin + (size_t)cy * g.pitch + cx;
+    const double v0 = inside ? *cell : 0.0;
+    double v = v0;
+    const unsigned* __restrict__ R = a.records + (size_t)info.x * kTileCells + tid;
+    unsigned next = __ldcs(R);
+    for (unsigned j = 0; j < info.y; ++j) {
+        const unsigned rec = next;
+        if (j + 1 < info.y) next = __ldcs(R + (size_t)(j + 1) * kTileCells);
+        if (rec == 0u) continue;
+        if (rec == kRecOverflow) {
+            const int4 pr = a.pairs[info.x + j];
+            const ScanMeta m = a.meta[pr.y];
+            const int2* __restrict__ E = a.rel + m.beamBegin;
+            const int rx = cx - m.sx, ry = cy - m.sy;
+            for (int i = pr.z; i < pr.w; ++i) {
+                const int2 e = __ldg(E + i);
+                const int ty = rayTouch(rx, ry, e.x, e.y);
+                if (ty) v = ty == 2 ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
+            }
+        } else if ((rec >> 26) == 31u) {
+            const int4 pr = a.pairs[info.x + j];
+            const unsigned* __restrict__ S = a.side + (size_t)(rec & ((1u << 26) - 1u)) * 8u;
+            const int nW = ((pr.w - pr.z + kSeg - 1) / kSeg) * kSegWords;
+            for (int w = 0; w < nW; ++w) {
+                unsigned t = S[2 * w];
+                const unsigned h = S[2 * w + 1];
+                while (t) {
+                    const bool hit = (h >> (__ffs(t) - 1)) & 1u;
+                    const unsigned same = hit ? (t & h) : (t & ~h);
+                    const unsigned other = t & ~same;
+                    const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
+                    const unsigned run = same & upto;
+                    v = applyRun(v, hit, (unsigned)__popc(run), a);
+                    t &= ~run;
+                }
+            }
+        } else if (rec >> 31) {
+            const bool first = (rec >> 30) & 1u;
+            v = applyRun(v, first, (rec >> 20) & 1023u, a);
+            v = applyRun(v, !first, (rec >> 10) & 1023u, a);
+            v = applyRun(v, first, rec & 1023u, a);
+        } else {
+            unsigned cnt = rec >> 26, bits = rec & ((1u << 26) - 1u);
+            while (cnt) {
+                const bool hit = bits & 1u;
+                const unsigned diff = hit ? ~bits : bits;        // first touch of the other type
+                const unsigned n = min(cnt, diff ? (unsigned)(__ffs(diff) - 1) : 32u);
+                v = applyRun(v, hit, n, a);
+                bits >>= n; cnt -= n;
+            }
+        }
+    }
+    if (inside && v != v0) *cell = v;
 }
 
 __global__ void grid_shift_copy_kernel(const double* __restrict__ src, int srcNx, int srcNy, int srcPitch,
@@ -485,14 +441,12 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     if (!c->integ) c->integ = new lgs_integ_ws();
     lgs_integ_ws& w = *c->integ;
 
-    // Stage the whole batch once; the kernels then run in sub-batches of <= 64 scans (one mask bit each).
+    // Stage the whole batch once; the passes then run over chunks of <= 64 scans (one mask bit each).
     LGS_CUDA(c, w.sensor.reserve((size_t)n * 2));
     LGS_CUDA(c, w.hit.reserve(std::max<size_t>((size_t)total, 1) * 2));
     LGS_CUDA(c, w.begin.reserve((size_t)n + 1));
     LGS_CUDA(c, w.meta.reserve((size_t)n * sizeof(ScanMeta)));
     LGS_CUDA(c, w.rel.reserve(std::max<size_t>((size_t)total, 1)));
-    LGS_CUDA(c, w.beta.reserve(std::max<size_t>((size_t)total, 1)));
-    LGS_CUDA(c, w.nearTab.reserve((size_t)std::min(n, 64) * kNearW * kNearW * (kRuns + 1)));
     LGS_CUDA(c, w.counters.reserve(8));
     LGS_CUDA(c, w.hMeta.reserve((size_t)n * sizeof(ScanMeta)));
     LGS_CUDA(c, w.hCounters.reserve(8));
@@ -504,18 +458,15 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
 
     int maxBeams = 0;
     for (int s = 0; s < n; ++s) maxBeams = std::max(maxBeams, scans->hit_begin[s + 1] - scans->hit_begin[s]);
-    if (maxBeams > 32767) return lgs_fail(c, LGS_ERR_INVALID, "integrate: %d beams in one scan (limit 32767)", maxBeams);
     ScanMeta* dMeta = reinterpret_cast<ScanMeta*>(w.meta.p);
     ScanMeta* hMeta = reinterpret_cast<ScanMeta*>(w.hMeta.p);
     GridRef g{grid->origin(), grid->nx, grid->ny, grid->pitch, grid->min_x, grid->min_y, grid->res};
-    // Pre-pass over the whole batch: sensor cells, relative end cells, beam angles, sortedness.
-    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(w.sensor.p, w.begin.p, w.hit.p, n, g, dMeta);
+    // Pre-pass over the whole batch: sensor cells, relative end cells, ray lengths, bounds check.
+    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(w.sensor.p, w.begin.p, n, g, dMeta);
     LGS_LAUNCH_CHECK(c);
     if (maxBeams > 0) {
         dim3 gb((maxBeams + 127) / 128, n);
-        integ_beam_kernel<<<gb, 128, 0, c->stream>>>(w.sensor.p, w.hit.p, n, g, dMeta, w.rel.p, w.beta.p);
-        LGS_LAUNCH_CHECK(c);
-        integ_sorted_kernel<<<gb, 128, 0, c->stream>>>(dMeta, w.beta.p);
+        integ_beam_kernel<<<gb, 128, 0, c->stream>>>(w.hit.p, g, dMeta, w.rel.p);
         LGS_LAUNCH_CHECK(c);
     }
     LGS_CUDA(c, cudaMemcpyAsync(hMeta, dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, c->stream));
@@ -530,52 +481,75 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     const double oddsHit = clampP(pHit) / (1.0 - clampP(pHit));
     const double oddsMiss = clampP(pMiss) / (1.0 - clampP(pMiss));
 
-    // Sub-batches: every scan owns one mask bit (<= 64).
-    int sub = 64;
-    if (const char* e = getenv("LGS_INTEG_SUB")) sub = std::min(64, std::max(1, atoi(e)));   // tuning hook
-    for (int s0 = 0; s0 < n; s0 += sub) {
-        const int ns = std::min(sub, n - s0);
-        int x0 = grid->nx, y0 = grid->ny, x1 = 0, y1 = 0, subBeams = 0;
-        for (int s = s0; s < s0 + ns; ++s) {
-            if (hMeta[s].n == 0) continue;
-            subBeams = std::max(subBeams, hMeta[s].n);
-            x0 = std::min(x0, hMeta[s].sx - hMeta[s].maxLen); x1 = std::max(x1, hMeta[s].sx + hMeta[s].maxLen + 1);
-            y0 = std::min(y0, hMeta[s].sy - hMeta[s].maxLen); y1 = std::max(y1, hMeta[s].sy + hMeta[s].maxLen + 1);
+    // Side buffer for touch sequences that fit no record format (words; LGS_INTEG_SIDE_WORDS is a test
+    // hook that shrinks it to exercise the exhaustive fallback).
+    size_t sideCap = (size_t)8 << 20;
+    if (const char* e = getenv("LGS_INTEG_SIDE_WORDS")) sideCap = (size_t)std::max(8, atoi(e));
+    // tiles of scan s's reach: the square of half side maxLen around the sensor cell
+    auto tileSpan = [](int lo, int hi) { return (hi >> kTileShift) - (lo >> kTileShift) + 1; };
+    int s0 = 0;
+    while (s0 < n) {
+        // grow the chunk while it stays within 64 scans and the record budget
+        int x0 = grid->nx, y0 = grid->ny, x1 = -1, y1 = -1, subBeams = 0, subLen = 0, ns = 0;
+        size_t pairBound = 0;
+        while (s0 + ns < n && ns < kChunk) {
+            const ScanMeta& m = hMeta[s0 + ns];
+            if (m.n > 0) {
+                const int lx = std::max(m.sx - m.maxLen, 0), hx = std::min(m.sx + m.maxLen, grid->nx - 1);
+                const int ly = std::max(m.sy - m.maxLen, 0), hy = std::min(m.sy + m.maxLen, grid->ny - 1);
+                const size_t pb = (size_t)tileSpan(lx, hx) * tileSpan(ly, hy);
+                if (ns > 0 && (pairBound + pb) * kTileCells * sizeof(unsigned) > kRecordBudget) break;
+                pairBound += pb;
+                x0 = std::min(x0, lx); x1 = std::max(x1, hx);
+                y0 = std::min(y0, ly); y1 = std::max(y1, hy);
+                subBeams = std::max(subBeams, m.n);
+                subLen = std::max(subLen, m.maxLen);
+            }
+            ++ns;
         }
-        x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, grid->nx); y1 = std::min(y1, grid->ny);
-        if (subBeams == 0 || x1 <= x0 || y1 <= y0) continue;
-        const size_t region = (size_t)(x1 - x0) * (y1 - y0);
-        const int nScanBlocks = (int)((region + 1023) / 1024);
-        long long subTouches = 0;                       // upper bound of recorded keys: sum of ray lengths
-        for (int s = s0; s < s0 + ns; ++s) subTouches += (long long)hMeta[s].n * (hMeta[s].maxLen + 1);
-        LGS_CUDA(c, w.mask.reserve(region));
-        LGS_CUDA(c, w.expect.reserve(region));
-        LGS_CUDA(c, w.local.reserve(region));
-        LGS_CUDA(c, w.blockSums.reserve((size_t)nScanBlocks));
-        LGS_CUDA(c, w.lists.reserve((size_t)std::max<long long>(subTouches, 1)));
-        LGS_CUDA(c, cudaMemsetAsync(w.mask.p, 0, region * sizeof(unsigned long long), c->stream));
-        LGS_CUDA(c, cudaMemsetAsync(w.expect.p, 0, region * sizeof(unsigned), c->stream));
-        dim3 gm((subBeams + 127) / 128, ns);
-        integ_walk_kernel<false><<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p,
-                                                            w.expect.p, nullptr, nullptr, nullptr);
+        const int cs = s0;
+        s0 += ns;
+        if (subBeams == 0 || x1 < x0 || y1 < y0) continue;
+        x0 &= ~(kTile - 1); y0 &= ~(kTile - 1);                       // tile-aligned region origin
+        const int tw = tileSpan(x0, x1), th = tileSpan(y0, y1);
+        const size_t nTiles = (size_t)tw * th;
+        if (nTiles * kChunk >= ((size_t)1 << 31)) return lgs_fail(c, LGS_ERR_INVALID, "integrate: region of %dx%d tiles is too large", tw, th);
+        pairBound = std::min(pairBound, nTiles * ns);
+
+        // mark buffers: kept in their reset state by the pair pass; (re)initialise what is new
+        if (w.dirty) { w.cleanTiles = 0; w.dirty = false; }
+        if (nTiles * kChunk > w.kmin.cap) w.cleanTiles = 0;           // reserve() reallocates
+        LGS_CUDA(c, w.kmin.reserve(nTiles * kChunk));
+        LGS_CUDA(c, w.kmax.reserve(nTiles * kChunk));
+        LGS_CUDA(c, w.tileInfo.reserve(nTiles));
+        LGS_CUDA(c, w.pairs.reserve(pairBound));
+        LGS_CUDA(c, w.records.reserve(pairBound * kTileCells));
+        if (nTiles > w.cleanTiles) {
+            const size_t a0 = w.cleanTiles, cnt = w.kmin.cap / kChunk - a0;   // initialise up to the capacity
+            LGS_CUDA(c, cudaMemsetAsync(w.kmin.p + a0 * kChunk, 0xFF, cnt * kChunk * sizeof(unsigned), c->stream));
+            LGS_CUDA(c, cudaMemsetAsync(w.kmax.p + a0 * kChunk, 0, cnt * kChunk * sizeof(unsigned), c->stream));
+            w.cleanTiles = w.kmin.cap / kChunk;
+        }
+        LGS_CUDA(c, w.side.reserve(sideCap));
+        unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 4);   // [0] pairs, [1] side-buffer cursor
+        LGS_CUDA(c, cudaMemsetAsync(nPairs, 0, 2 * sizeof(unsigned), c->stream));
+
+        w.dirty = true;
+        const int beamsPad = (subBeams + 31) & ~31, pieces = subLen / kTile + 1;
+        dim3 gm((unsigned)(((size_t)beamsPad * pieces + 127) / 128), ns);
+        integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + cs, w.rel.p, x0, y0, tw, beamsPad, w.kmin.p, w.kmax.p);
         LGS_LAUNCH_CHECK(c);
-        integ_scan_blocks_kernel<<<nScanBlocks, 256, 0, c->stream>>>(w.expect.p, region, w.local.p, w.blockSums.p);
+        integ_pairs_kernel<<<(unsigned)((nTiles * 32 + 127) / 128), 128, 0, c->stream>>>((int)nTiles, w.kmin.p, w.kmax.p,
+                                                                                       w.tileInfo.p, w.pairs.p, nPairs);
         LGS_LAUNCH_CHECK(c);
-        integ_scan_sums_kernel<<<1, 1024, 0, c->stream>>>(w.blockSums.p, nScanBlocks);
+        w.dirty = false;
+        const unsigned touchBlocks = (unsigned)std::min<size_t>(pairBound, (size_t)c->sm_count * 8);
+        integ_touch_kernel<<<touchBlocks, kTileCells, 0, c->stream>>>(dMeta + cs, w.rel.p, w.pairs.p, nPairs, x0, y0, tw,
+                                                                      w.records.p, w.side.p, nPairs + 1, (unsigned)sideCap,
+                                                                      w.counters.p);
         LGS_LAUNCH_CHECK(c);
-        // pass 2 re-uses the count array as the per-cell cursor; the apply kernel needs the counts,
-        // which the cursors equal again once every touch has been recorded
-        LGS_CUDA(c, cudaMemsetAsync(w.expect.p, 0, region * sizeof(unsigned), c->stream));
-        integ_walk_kernel<true><<<gm, 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, x0, y0, x1 - x0, w.mask.p,
-                                                           w.expect.p, w.local.p, w.blockSums.p, w.lists.p);
-        LGS_LAUNCH_CHECK(c);
-        const long long warps = (long long)ns * kNearW * kNearW;
-        integ_near_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(dMeta + s0, w.rel.p, ns, w.nearTab.p);
-        LGS_LAUNCH_CHECK(c);
-        ApplyArgs a{dMeta + s0, w.rel.p, w.beta.p, w.nearTab.p, w.mask.p, w.expect.p, w.local.p, w.blockSums.p,
-                    w.lists.p, pHit, pMiss, oddsHit, oddsMiss};
-        dim3 block(32, 8), gridDim((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
-        integ_apply_kernel<<<gridDim, block, 0, c->stream>>>(a, g, x0, y0, x1, y1, w.counters.p);
+        FoldArgs a{dMeta + cs, w.rel.p, w.tileInfo.p, w.pairs.p, w.records.p, w.side.p, pHit, pMiss, oddsHit, oddsMiss};
+        integ_fold_kernel<<<(unsigned)nTiles, kTileCells, 0, c->stream>>>(a, g, x0, y0, tw);
         LGS_LAUNCH_CHECK(c);
     }
     LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

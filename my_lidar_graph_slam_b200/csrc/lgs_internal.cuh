@@ -75,19 +75,24 @@ struct PinBuf {
 struct lgs_integ_ws {
     DevBuf<double> sensor, hit;
     DevBuf<int> begin;
-    DevBuf<char> meta;
-    DevBuf<int2> rel;
-    DevBuf<float> beta;
-    DevBuf<unsigned short> nearTab;
-    DevBuf<unsigned long long> mask, counters;
-    DevBuf<unsigned> expect, lists, local, blockSums;
+    DevBuf<char> meta;                       // ScanMeta per scan
+    DevBuf<int2> rel;                        // per beam: hit cell - sensor cell
+    DevBuf<unsigned> kmin, kmax;             // per (tile, scan): beam index range [kmin, kmax)
+    DevBuf<uint2> tileInfo;                  // per tile: {first pair, pairs}
+    DevBuf<int4> pairs;                      // {tile, scan, k0, k1}
+    DevBuf<unsigned> records;                // per (pair, cell): encoded ordered touch sequence
+    DevBuf<unsigned> side;                   // raw touch / hit bitmap words of sequences no record holds
+    DevBuf<unsigned long long> counters;
     PinBuf<char> hMeta;
     PinBuf<unsigned long long> hCounters;
+    size_t cleanTiles = 0;                   // kmin / kmax are in their reset state up to here
+    bool dirty = false;                      // a call failed between the mark and the pair pass
     long long fallbackCells = 0;
     void release() {
-        sensor.release(); hit.release(); begin.release(); meta.release(); rel.release(); beta.release();
-        nearTab.release(); mask.release(); counters.release(); expect.release(); lists.release(); local.release(); blockSums.release(); hMeta.release();
-        hCounters.release();
+        sensor.release(); hit.release(); begin.release(); meta.release(); rel.release();
+        side.release(); kmin.release(); kmax.release(); tileInfo.release(); pairs.release();
+        records.release(); counters.release(); hMeta.release(); hCounters.release();
+        cleanTiles = 0;
     }
 };
 

@@ -113,9 +113,10 @@ def test_integrate_rejects_cells_outside_grid_and_handles_empty(ctx):
     assert not grid.download().any()
 
 
-def test_fast_candidate_search_never_needs_the_exhaustive_fallback(ctx):
-    """The mark pass counts every touch; a cell whose angular-window search finds a different
-    number is redone exhaustively and counted.  On real scan geometry that must never happen."""
+def test_real_scans_never_need_the_exhaustive_fallback(ctx):
+    """Touch sequences that fit no 32-bit record go to the side buffer; only when that is exhausted
+    does the owning thread re-derive a (cell, scan) from the beams.  On real scan geometry the
+    default side buffer must always suffice."""
     angles, traj, scans = _scene(seed=9, n=24)
     geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
     hits = []
@@ -127,3 +128,34 @@ def test_fast_candidate_search_never_needs_the_exhaustive_fallback(ctx):
     before = capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h)
     assert capi.integrate_scans(ctx, grid, traj[:, :2], hits) > 24 * 50_000
     assert capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h) == before
+
+
+def test_exhausted_side_buffer_falls_back_to_exact_beam_tests(ctx, monkeypatch):
+    """LGS_INTEG_SIDE_WORDS shrinks the side buffer to nothing: every long mixed sequence takes the
+    exhaustive per-beam path in the fold pass and the map must still be bit-identical."""
+    from oracle import backend
+    R = backend()
+    angles, traj, scans = _scene(seed=11, n=12)
+    geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
+    hits = []
+    for p, r in zip(traj, scans):
+        h, bbox = capi.scan_hit_points(p, angles, r, 0.02, 20.0)
+        geo, _, _, _ = capi.geometry_expand(geo, bbox)
+        hits.append(h)
+    ref = R.RefMap.from_dense(np.zeros((geo.ny, geo.nx)), geo.min_x, geo.min_y)
+    want = sum(R.map_integrate_hits(ref, p[:2], h) for p, h in zip(traj, hits))
+    maps = []
+    for side in ("8", None):
+        if side:
+            monkeypatch.setenv("LGS_INTEG_SIDE_WORDS", side)
+        else:
+            monkeypatch.delenv("LGS_INTEG_SIDE_WORDS")
+        grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
+        before = capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h)
+        assert capi.integrate_scans(ctx, grid, traj[:, :2], hits) == want
+        used_fallback = capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h) - before
+        maps.append((grid.download(), used_fallback))
+        grid.close()
+    assert maps[0][1] > 0 and maps[1][1] == 0
+    assert np.array_equal(_bits(maps[0][0]), _bits(ref.dense()))
+    assert np.array_equal(_bits(maps[1][0]), _bits(ref.dense()))
