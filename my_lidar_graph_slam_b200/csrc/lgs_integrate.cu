@@ -47,6 +47,7 @@ constexpr int kSegWords = kSeg / 32;
 constexpr unsigned kRawMax = 26;               // touches a raw record holds
 constexpr unsigned kRecOverflow = 0xFFFFFFFFu;
 constexpr unsigned kRecSide = 31u << 26;
+constexpr int kFoldBatch = 8;                  // records a fold thread keeps in flight
 constexpr size_t kRecordBudget = (size_t)1 << 30;   // bytes of records per chunk before it is split
 
 struct ScanMeta {
@@ -98,6 +99,18 @@ __device__ __forceinline__ int rayTouch(int rx, int ry, int ex, int ey) {
     return k == amaj ? 2 : 1;
 }
 
+// Minor-axis offset of step k of a ray: floor((2 amin k + amaj) / (2 amaj)) (util.hpp:276-299), amaj > 0.
+// For rays up to 2047 cells the dividend is below 2^24, i.e. exact in float: one reciprocal, one
+// multiply and an integer correction replace the 32-bit division; longer rays divide.
+__device__ __forceinline__ int minorAt(int amin, int amaj, int k) {
+    const int lhs = 2 * amin * k + amaj, m2 = 2 * amaj;
+    if (amaj > 2047) return (int)((unsigned)lhs / (unsigned)m2);
+    int q = __float2int_rz(__fmul_rn((float)lhs, __frcp_rn((float)m2)));
+    const int r = lhs - q * m2;
+    if (r < 0) --q; else if (r >= m2) ++q;
+    return q;
+}
+
 // ---- pre-pass A: sensor cells ---------------------------------------------------------------------
 __global__ void integ_sensor_kernel(const double* __restrict__ sensorXY, const int* __restrict__ hitBegin,
                                     int nScans, GridRef g, ScanMeta* __restrict__ meta) {
@@ -136,45 +149,73 @@ __global__ void integ_beam_kernel(const double* __restrict__ hitXY, GridRef g, S
 }
 
 // ---- 1. mark: beam index range per (tile, scan) ------------------------------------------------------
-// One thread per (scan, beam, 16-step piece of the ray); consecutive lanes = consecutive beams at
-// the same distance from the sensor, so a warp's atomics mostly hit the same few addresses.
-// (x0, y0) = tile-aligned origin of the chunk's region, tw = tiles per region row.  The racy
-// pre-reads only save atomics: kmin only ever decreases and kmax only ever increases.
+// One thread per (scan, beam, 16-step piece of the ray); a warp = 32 consecutive beams at the same
+// distance from the sensor, which mostly cross the same tiles.  A 16-step piece of a (monotone)
+// Bresenham path visits at most 3 tiles; for each of them the warp groups the lanes that share the
+// tile and issues ONE atomicMin (lowest beam of the group) and ONE atomicMax (highest beam).
+// (x0, y0) = tile-aligned origin of the chunk's region, tw = tiles per region row.
 __global__ void __launch_bounds__(128)
 integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel, int x0, int y0, int tw,
                   int beamsPad, unsigned* __restrict__ kmin, unsigned* __restrict__ kmax) {
     const int s = blockIdx.y;
     const ScanMeta m = meta[s];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = t % beamsPad, piece = t / beamsPad;
-    if (i >= m.n) return;
-    const int2 e = __ldg(rel + m.beamBegin + i);
-    const int ax = abs(e.x), ay = abs(e.y);
-    const bool xMajor = ax > ay;                            // util.hpp:276 vs :288
-    const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
-    const int kBegin = piece * kTile;
-    if (kBegin > amaj) return;
-    const int kEnd = min(kBegin + kTile - 1, amaj);
-    const int sMaj = (xMajor ? e.x : e.y) < 0 ? -1 : 1, sMin = (xMajor ? e.y : e.x) < 0 ? -1 : 1;
-    const int bx = m.sx - x0, by = m.sy - y0;
-    int last = -1;
-    for (int k = kBegin; k <= kEnd; ++k) {
-        const int minor = amaj ? (int)((unsigned)(2 * amin * k + amaj) / (unsigned)(2 * amaj)) : 0;
-        const int x = bx + (xMajor ? sMaj * k : sMin * minor);
-        const int y = by + (xMajor ? sMin * minor : sMaj * k);
-        const int tile = (y >> kTileShift) * tw + (x >> kTileShift);
-        if (tile == last) continue;
-        last = tile;
-        const size_t idx = (size_t)tile * kChunk + s;
-        if (__ldcg(kmin + idx) > (unsigned)i) atomicMin(kmin + idx, (unsigned)i);
-        if (__ldcg(kmax + idx) < (unsigned)i + 1u) atomicMax(kmax + idx, (unsigned)i + 1u);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;        // beamsPad is a multiple of 32:
+    const int i = t % beamsPad, piece = t / beamsPad;           // a warp never straddles two pieces
+    const int lane = threadIdx.x & 31;
+    int tiles[3] = {-1, -1, -1};
+    if (i < m.n) {
+        const int2 e = __ldg(rel + m.beamBegin + i);
+        const int ax = abs(e.x), ay = abs(e.y);
+        const bool xMajor = ax > ay;                            // util.hpp:276 vs :288
+        const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
+        const int kBegin = piece * kTile;
+        if (kBegin <= amaj) {
+            const int kEnd = min(kBegin + kTile - 1, amaj);
+            const int sMaj = (xMajor ? e.x : e.y) < 0 ? -1 : 1, sMin = (xMajor ? e.y : e.x) < 0 ? -1 : 1;
+            const int bx = m.sx - x0, by = m.sy - y0;
+            const int m2 = 2 * amaj, d2 = 2 * amin;
+            int minor = amaj ? minorAt(amin, amaj, kBegin) : 0;
+            int rem = d2 * kBegin + amaj - minor * m2;
+            int nt = 0, last = -1;
+            for (int k = kBegin; k <= kEnd; ++k) {
+                const int x = bx + (xMajor ? sMaj * k : sMin * minor);
+                const int y = by + (xMajor ? sMin * minor : sMaj * k);
+                const int tile = (y >> kTileShift) * tw + (x >> kTileShift);
+                if (tile != last) {
+                    last = tile;
+                    if (nt == 0) tiles[0] = tile; else if (nt == 1) tiles[1] = tile; else tiles[2] = tile;
+                    ++nt;
+                }
+                rem += d2;
+                if (rem >= m2) { rem -= m2; ++minor; }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int mine = tiles[u];
+        unsigned pending = __ballot_sync(0xffffffffu, mine >= 0);
+        while (pending) {
+            const int leader = __ffs(pending) - 1;
+            const int tl = __shfl_sync(0xffffffffu, mine, leader);
+            const unsigned grp = __ballot_sync(0xffffffffu, mine == tl);
+            if (lane == leader) {
+                const size_t idx = (size_t)tl * kChunk + s;
+                atomicMin(kmin + idx, (unsigned)i);                             // lowest lane = lowest beam
+                atomicMax(kmax + idx, (unsigned)(i + (31 - __clz(grp)) - lane) + 1u);
+            }
+            pending &= ~grp;
+        }
     }
 }
 
-// ---- 2. pairs: scan-ordered (tile, scan, k0, k1) runs; resets the mark buffers -------------------------
+// ---- 2. pairs: scan-ordered pair descriptors per tile; resets the mark buffers --------------------------
+// Descriptor = two int4: {ox, oy, k0, k1} (tile origin relative to the scan's sensor cell, beam range)
+// and {beamBegin, tile, scan, 0}, so the touch pass needs no further dependent look-ups.
 // One warp per tile: lanes read the tile's 64 kmax entries (non-zero = the scan touches the tile).
 __global__ void __launch_bounds__(128)
-integ_pairs_kernel(int nTiles, unsigned* __restrict__ kmin, unsigned* __restrict__ kmax,
+integ_pairs_kernel(int nTiles, const ScanMeta* __restrict__ meta, int x0, int y0, int tw,
+                   unsigned* __restrict__ kmin, unsigned* __restrict__ kmax,
                    uint2* __restrict__ tileInfo, int4* __restrict__ pairs, unsigned* __restrict__ nPairs) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -188,12 +229,18 @@ integ_pairs_kernel(int nTiles, unsigned* __restrict__ kmin, unsigned* __restrict
     base = __shfl_sync(0xffffffffu, base, 0);
     if (lane == 0) tileInfo[t] = make_uint2(base, cnt);
     const unsigned below = (1u << lane) - 1u;
+    const int tx = x0 + (t % tw) * kTile, ty = y0 + (t / tw) * kTile;
+    auto emit = [&](unsigned slot, int s, unsigned lo, unsigned hi) {
+        const ScanMeta m = meta[s];
+        pairs[2 * (size_t)slot] = make_int4(tx - m.sx, ty - m.sy, (int)lo, (int)hi);
+        pairs[2 * (size_t)slot + 1] = make_int4(m.beamBegin, t, s, 0);
+    };
     if (hiA) {
-        pairs[base + __popc(mA & below)] = make_int4(t, lane, (int)kmin[idx], (int)hiA);
+        emit(base + __popc(mA & below), lane, kmin[idx], hiA);
         kmin[idx] = 0xFFFFFFFFu; kmax[idx] = 0u;
     }
     if (hiB) {
-        pairs[base + __popc(mA) + __popc(mB & below)] = make_int4(t, lane + 32, (int)kmin[idx + 32], (int)hiB);
+        emit(base + __popc(mA) + __popc(mB & below), lane + 32, kmin[idx + 32], hiB);
         kmin[idx + 32] = 0xFFFFFFFFu; kmax[idx + 32] = 0u;
     }
 }
@@ -202,8 +249,8 @@ integ_pairs_kernel(int nTiles, unsigned* __restrict__ kmin, unsigned* __restrict
 // Record formats (32 bit):   0                      no touch
 //   raw  [31] = 0, [30:26] = count (1..26), [25:0] = types in order (1 = hit)
 //   runs [31] = 1, [30] = type of the first run, [29:20] [19:10] [9:0] = three alternating run lengths
-//   side [31] = 0, [30:26] = 31, [25:0] = offset (units of 8 words) of the cell's raw touch / hit
-//        bitmap words in the side buffer: sequences that fit neither format (a near cell whose
+//   side [31] = 0, [30:26] = 31, [25:0] = offset (units of 8 words) of the cell's non-empty raw
+//        touch / hit bitmap words in the side buffer: sequences that fit neither format (a near cell whose
 //        beams alternate between ending in it and passing through)
 //   0xFFFFFFFF               side buffer exhausted: the owner re-derives the sequence from the beams
 struct TouchSeq {
@@ -224,59 +271,82 @@ struct TouchSeq {
     }
 };
 
-__global__ void __launch_bounds__(kTileCells)
-integ_touch_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ rel,
-                   const int4* __restrict__ pairs, const unsigned* __restrict__ nPairs, int x0, int y0,
-                   int tw, unsigned* __restrict__ records, unsigned* __restrict__ side,
+__global__ void __launch_bounds__(kTileCells, 5)
+integ_touch_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs,
+                   const unsigned* __restrict__ nPairs, unsigned* __restrict__ records, unsigned* __restrict__ side,
                    unsigned* __restrict__ sideCursor, unsigned sideCap,
                    unsigned long long* __restrict__ counters) {
-    __shared__ unsigned sTouch[kSegWords * kTileCells];     // [word][cell]
-    __shared__ unsigned sHit[kSegWords * kTileCells];
+    __shared__ unsigned sBits[2][2 * kSegWords * kTileCells];   // double buffered; [touch | hit][word][cell]
+    int buf = 0;
     __shared__ unsigned sSum[kTileCells / 32];
     const int tid = threadIdx.x;
     const unsigned nP = *nPairs;
     unsigned total = 0, overflow = 0;
+    int4 nextA = make_int4(0, 0, 0, 0), nextB = nextA;
+    if (blockIdx.x < nP) { nextA = pairs[2 * (size_t)blockIdx.x]; nextB = pairs[2 * (size_t)blockIdx.x + 1]; }
     for (unsigned p = blockIdx.x; p < nP; p += gridDim.x) {
-        const int4 pr = pairs[p];
-        const ScanMeta m = meta[pr.y];
-        const int ox = x0 + (pr.x % tw) * kTile - m.sx;     // tile origin relative to the sensor cell
-        const int oy = y0 + (pr.x / tw) * kTile - m.sy;
-        const int2* __restrict__ E = rel + m.beamBegin;
+        const int4 pr = nextA;                              // .x/.y tile origin - sensor cell, .z/.w beams
+        const int2* __restrict__ E = rel + nextB.x;
+        if (p + gridDim.x < nP) {                           // the next descriptor is in flight meanwhile
+            nextA = pairs[2 * (size_t)(p + gridDim.x)];
+            nextB = pairs[2 * (size_t)(p + gridDim.x) + 1];
+        }
+        const int ox = pr.x, oy = pr.y;
         TouchSeq seq;
         unsigned rec = 0u, sideOff = 0u;
+        int wFirst = 0x7fffffff, wLast = -1;                   // non-empty bitmap words of this cell
         // pass 0 builds the records; pass 1 (only if a cell of this pair fits no record format)
         // repeats the bitmaps and streams the raw words of those cells to the side buffer
         for (int pass = 0; pass < 2; ++pass) {
             for (int seg = pr.z; seg < pr.w; seg += kSeg) {
-#pragma unroll
-                for (int w = 0; w < kSegWords; ++w) { sTouch[w * kTileCells + tid] = 0u; sHit[w * kTileCells + tid] = 0u; }
+                // Two barriers per segment: the buffer cleared here was last read two segments ago.
+                buf ^= 1;
+                unsigned* sTouch = sBits[buf];
+                unsigned* sHit = sBits[buf] + kSegWords * kTileCells;
+                const int nW = (min(kSeg, pr.w - seg) + 31) >> 5;
+                for (int w = 0; w < nW; ++w) { sTouch[w * kTileCells + tid] = 0u; sHit[w * kTileCells + tid] = 0u; }
                 __syncthreads();
                 const int nb = min(kSeg, pr.w - seg);
-                for (int it = tid; it < nb * kTile; it += kTileCells) {
-                    const int b = it >> kTileShift, j = it & (kTile - 1);
+                if (tid < nb) {
+                    // one thread per beam: the <= 16 steps whose major coordinate lies inside the tile;
+                    // the minor coordinate floor((2 amin k + amaj) / (2 amaj)) is divided out once and
+                    // then carried with its remainder (2 amin <= 2 amaj: at most one increment a step)
+                    const int b = tid;
                     const int2 e = __ldg(E + seg + b);
                     const int ax = abs(e.x), ay = abs(e.y);
                     const bool xMajor = ax > ay;
                     const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
                     const int eMaj = xMajor ? e.x : e.y, eMin = xMajor ? e.y : e.x;
                     const int oMaj = xMajor ? ox : oy, oMin = xMajor ? oy : ox;
-                    const int rMaj = oMaj + j;                               // this item's column (row)
-                    const int k = eMaj < 0 ? -rMaj : rMaj;                   // step along the major axis
-                    if (k < 0 || k > amaj) continue;
-                    const int minor = amaj ? (int)((unsigned)(2 * amin * k + amaj) / (unsigned)(2 * amaj)) : 0;
-                    const int lMin = (eMin < 0 ? -minor : minor) - oMin;
-                    if ((unsigned)lMin >= (unsigned)kTile) continue;
-                    const int cell = xMajor ? (lMin * kTile + j) : (j * kTile + lMin);
-                    const unsigned bitb = 1u << (b & 31);
-                    atomicOr(&sTouch[(b >> 5) * kTileCells + cell], bitb);
-                    if (k == amaj) atomicOr(&sHit[(b >> 5) * kTileCells + cell], bitb);
+                    const int kLo = max(eMaj >= 0 ? oMaj : -oMaj - (kTile - 1), 0);
+                    const int kHi = min(eMaj >= 0 ? oMaj + (kTile - 1) : -oMaj, amaj);
+                    if (kLo <= kHi) {
+                        const int m2 = 2 * amaj, d2 = 2 * amin;
+                        int minor = amaj ? minorAt(amin, amaj, kLo) : 0;
+                        int rem = d2 * kLo + amaj - minor * m2;
+                        const unsigned bitb = 1u << (b & 31);
+                        unsigned* tw_ = sTouch + (b >> 5) * kTileCells;
+                        unsigned* hw_ = sHit + (b >> 5) * kTileCells;
+                        for (int k = kLo; k <= kHi; ++k) {
+                            const int j = eMaj >= 0 ? k - oMaj : -k - oMaj;              // column (row) in the tile
+                            const int lMin = (eMin < 0 ? -minor : minor) - oMin;
+                            if ((unsigned)lMin < (unsigned)kTile) {
+                                const int cell = xMajor ? (lMin * kTile + j) : (j * kTile + lMin);
+                                atomicOr(tw_ + cell, bitb);
+                                if (k == amaj) atomicOr(hw_ + cell, bitb);
+                            }
+                            rem += d2;
+                            if (rem >= m2) { rem -= m2; ++minor; }
+                        }
+                    }
                 }
                 __syncthreads();
                 if (pass == 0) {
-#pragma unroll
-                    for (int w = 0; w < kSegWords; ++w) {
+                    for (int w = 0; w < nW; ++w) {
                         unsigned t = sTouch[w * kTileCells + tid];
                         if (t == 0u) continue;
+                        const int gw = ((seg - pr.z) / kSeg) * kSegWords + w;
+                        wFirst = min(wFirst, gw); wLast = gw;
                         const unsigned h = sHit[w * kTileCells + tid];
                         while (t) {                              // maximal runs of equal type, ascending beams
                             const int type = (h >> (__ffs(t) - 1)) & 1;
@@ -289,21 +359,26 @@ integ_touch_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ r
                         }
                     }
                 } else if ((rec >> 26) == 31u) {
-                    unsigned* out = side + (size_t)sideOff + (size_t)((seg - pr.z) / kSeg) * (2 * kSegWords);
-#pragma unroll
-                    for (int w = 0; w < kSegWords; ++w) {
-                        out[2 * w] = sTouch[w * kTileCells + tid];
-                        out[2 * w + 1] = sHit[w * kTileCells + tid];
+                    unsigned* out = side + (size_t)sideOff + 2;
+                    for (int w = 0; w < nW; ++w) {
+                        const int gw = ((seg - pr.z) / kSeg) * kSegWords + w;
+                        if (gw < wFirst || gw > wLast) continue;
+                        out[2 * (gw - wFirst)] = sTouch[w * kTileCells + tid];
+                        out[2 * (gw - wFirst) + 1] = sHit[w * kTileCells + tid];
                     }
                 }
-                __syncthreads();
             }
             if (pass == 0) {
                 rec = seq.record();
                 if (rec == kRecOverflow) {
-                    const unsigned words = (unsigned)((pr.w - pr.z + kSeg - 1) / kSeg) * (2 * kSegWords);
+                    // header {first word | words << 16, -} + (touch, hit) word pairs, in units of 8 words
+                    const unsigned nWords = (unsigned)(wLast - wFirst + 1);
+                    const unsigned words = (2u + 2u * nWords + 7u) & ~7u;
                     sideOff = atomicAdd(sideCursor, words);
-                    if (sideOff + words <= sideCap) rec = kRecSide | (sideOff >> 3);
+                    if (sideOff + words <= sideCap && nWords < 65536u) {
+                        rec = kRecSide | (sideOff >> 3);
+                        side[sideOff] = (unsigned)wFirst | (nWords << 16);
+                    }
                 }
                 if (!__syncthreads_or((rec >> 26) == 31u)) break;
             }
@@ -329,24 +404,52 @@ integ_touch_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ r
 
 // ---- 4. fold: one thread owns one cell ---------------------------------------------------------------
 struct FoldArgs {
-    const ScanMeta* meta;
     const int2* rel;
     const uint2* tileInfo;
     const int4* pairs;
     const unsigned* records;
     const unsigned* side;
+    unsigned long long* diag;      // LGS_INTEG_TIMING: [2] max / [3] sum of computed updates per thread
     double pHit, pMiss, oddsHit, oddsMiss;
 };
 
-__device__ __forceinline__ double applyRun(double v, bool hit, unsigned n, const FoldArgs& a) {
-    const double p = hit ? a.pHit : a.pMiss, odds = hit ? a.oddsHit : a.oddsMiss;
-    for (unsigned j = 0; j < n; ++j) {
-        const double nv = bayesUpdate(v, p, odds);
-        if (nv == v) break;                // fixed point: the rest of the run is a no-op
-        v = nv;
+// One thread owns one cell.  Raw records (the common case) are queued per lane and applied only when
+// some lane of the warp is about to overflow its 64-touch queue: neighbouring cells see similar
+// numbers of touches over a chunk, so the lanes of a warp then have similar amounts of work, while
+// applying every record at once would run the ~100-instruction update under heavy divergence.
+// A touch that cannot change the value (cell already at the clamp the observation pushes towards:
+// the clamp makes the update idempotent there) is skipped without arithmetic.
+struct Folder {
+    const FoldArgs& a;
+    double v;
+    unsigned long long q = 0ull;
+    int qn = 0;
+    bool missSat, hitSat;
+    unsigned computed = 0;
+    __device__ __forceinline__ Folder(const FoldArgs& args, double v0) : a(args), v(v0) {
+        const double lo = 1e-3, hi = 1.0 - 1e-3;
+        missSat = bayesUpdate(lo, a.pMiss, a.oddsMiss) == lo;
+        hitSat = bayesUpdate(hi, a.pHit, a.oddsHit) == hi;
     }
-    return v;
-}
+    __device__ __forceinline__ bool saturated(bool hit) const {
+        return hit ? (hitSat && v == 1.0 - 1e-3) : (missSat && v == 1e-3);
+    }
+    __device__ __forceinline__ void touch(bool hit) {
+        if (!saturated(hit)) { v = bayesUpdate(v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss); ++computed; }
+    }
+    __device__ __forceinline__ void drain() {
+        while (qn) { touch(q & 1ull); q >>= 1; --qn; }
+    }
+    __device__ __forceinline__ void run(bool hit, unsigned n) {
+        for (unsigned j = 0; j < n; ++j) {
+            if (saturated(hit)) break;
+            const double nv = bayesUpdate(v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss);
+            ++computed;
+            if (nv == v) break;            // fixed point: the rest of the run is a no-op
+            v = nv;
+        }
+    }
+};
 
 __global__ void __launch_bounds__(kTileCells)
 integ_fold_kernel(FoldArgs a, GridRef g, int x0, int y0, int tw) {
@@ -358,57 +461,73 @@ integ_fold_kernel(FoldArgs a, GridRef g, int x0, int y0, int tw) {
     const bool inside = cx < g.nx && cy < g.ny;
     double* cell = g.origin + (size_t)cy * g.pitch + cx;
     const double v0 = inside ? *cell : 0.0;
-    double v = v0;
+    Folder f(a, v0);
+    // Records are prefetched kFoldBatch pairs at a time (they do not depend on the cell value): the
+    // loads of the next batch are in flight while this thread's own column of the shared staging
+    // buffer is consumed, so a tile touched by all 64 scans pays 8 memory round trips, not 64.
+    __shared__ unsigned sRec[kFoldBatch * kTileCells];
     const unsigned* __restrict__ R = a.records + (size_t)info.x * kTileCells + tid;
-    unsigned next = __ldcs(R);
+    unsigned pre[kFoldBatch];
+#pragma unroll
+    for (int u = 0; u < kFoldBatch; ++u) pre[u] = (unsigned)u < info.y ? __ldcs(R + (size_t)u * kTileCells) : 0u;
     for (unsigned j = 0; j < info.y; ++j) {
-        const unsigned rec = next;
-        if (j + 1 < info.y) next = __ldcs(R + (size_t)(j + 1) * kTileCells);
-        if (rec == 0u) continue;
+        const unsigned u0 = j % kFoldBatch;
+        if (u0 == 0u) {
+#pragma unroll
+            for (int u = 0; u < kFoldBatch; ++u) sRec[u * kTileCells + tid] = pre[u];
+#pragma unroll
+            for (int u = 0; u < kFoldBatch; ++u) {
+                const unsigned jj = j + kFoldBatch + u;
+                pre[u] = jj < info.y ? __ldcs(R + (size_t)jj * kTileCells) : 0u;
+            }
+        }
+        const unsigned rec = sRec[u0 * kTileCells + tid];
+        if (__any_sync(0xffffffffu, f.qn > 64 - (int)kRawMax)) f.drain();
+        const unsigned cnt = rec >> 26;
+        if (cnt <= kRawMax) {                                   // raw (or empty): queue
+            f.q |= (unsigned long long)(rec & ((1u << 26) - 1u)) << f.qn;
+            f.qn += (int)cnt;
+            continue;
+        }
+        f.drain();
         if (rec == kRecOverflow) {
-            const int4 pr = a.pairs[info.x + j];
-            const ScanMeta m = a.meta[pr.y];
-            const int2* __restrict__ E = a.rel + m.beamBegin;
-            const int rx = cx - m.sx, ry = cy - m.sy;
+            const int4 pr = a.pairs[2 * (size_t)(info.x + j)];
+            const int2* __restrict__ E = a.rel + a.pairs[2 * (size_t)(info.x + j) + 1].x;
+            const int rx = pr.x + (tid & (kTile - 1)), ry = pr.y + (tid >> kTileShift);
             for (int i = pr.z; i < pr.w; ++i) {
                 const int2 e = __ldg(E + i);
                 const int ty = rayTouch(rx, ry, e.x, e.y);
-                if (ty) v = ty == 2 ? bayesUpdate(v, a.pHit, a.oddsHit) : bayesUpdate(v, a.pMiss, a.oddsMiss);
+                if (ty) f.touch(ty == 2);
             }
-        } else if ((rec >> 26) == 31u) {
-            const int4 pr = a.pairs[info.x + j];
+        } else if (cnt == 31u) {
             const unsigned* __restrict__ S = a.side + (size_t)(rec & ((1u << 26) - 1u)) * 8u;
-            const int nW = ((pr.w - pr.z + kSeg - 1) / kSeg) * kSegWords;
-            for (int w = 0; w < nW; ++w) {
-                unsigned t = S[2 * w];
-                const unsigned h = S[2 * w + 1];
+            const unsigned nWords = S[0] >> 16;
+            const uint2* __restrict__ W = reinterpret_cast<const uint2*>(S + 2);
+            uint2 nx = W[0];
+            for (unsigned w = 0; w < nWords; ++w) {
+                unsigned t = nx.x;
+                const unsigned h = nx.y;
+                if (w + 1 < nWords) nx = W[w + 1];
                 while (t) {
                     const bool hit = (h >> (__ffs(t) - 1)) & 1u;
                     const unsigned same = hit ? (t & h) : (t & ~h);
                     const unsigned other = t & ~same;
                     const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
                     const unsigned run = same & upto;
-                    v = applyRun(v, hit, (unsigned)__popc(run), a);
+                    f.run(hit, (unsigned)__popc(run));
                     t &= ~run;
                 }
             }
-        } else if (rec >> 31) {
+        } else {                                                // three alternating runs
             const bool first = (rec >> 30) & 1u;
-            v = applyRun(v, first, (rec >> 20) & 1023u, a);
-            v = applyRun(v, !first, (rec >> 10) & 1023u, a);
-            v = applyRun(v, first, rec & 1023u, a);
-        } else {
-            unsigned cnt = rec >> 26, bits = rec & ((1u << 26) - 1u);
-            while (cnt) {
-                const bool hit = bits & 1u;
-                const unsigned diff = hit ? ~bits : bits;        // first touch of the other type
-                const unsigned n = min(cnt, diff ? (unsigned)(__ffs(diff) - 1) : 32u);
-                v = applyRun(v, hit, n, a);
-                bits >>= n; cnt -= n;
-            }
+            f.run(first, (rec >> 20) & 1023u);
+            f.run(!first, (rec >> 10) & 1023u);
+            f.run(first, rec & 1023u);
         }
     }
-    if (inside && v != v0) *cell = v;
+    f.drain();
+    if (a.diag) { atomicMax(a.diag + 2, (unsigned long long)f.computed); atomicAdd(a.diag + 3, (unsigned long long)f.computed); }
+    if (inside && f.v != v0) *cell = f.v;
 }
 
 __global__ void grid_shift_copy_kernel(const double* __restrict__ src, int srcNx, int srcNy, int srcPitch,
@@ -487,6 +606,22 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     if (const char* e = getenv("LGS_INTEG_SIDE_WORDS")) sideCap = (size_t)std::max(8, atoi(e));
     // tiles of scan s's reach: the square of half side maxLen around the sensor cell
     auto tileSpan = [](int lo, int hi) { return (hi >> kTileShift) - (lo >> kTileShift) + 1; };
+    // LGS_INTEG_TIMING=1 (diagnostic): CUDA-event time of every pass, summed over the call, to stderr.
+    const bool timing = getenv("LGS_INTEG_TIMING") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    auto stamp = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
+    // The fold pass runs on a second stream so that it overlaps the next chunk's touch passes
+    // (LGS_INTEG_TIMING serialises everything on the context stream to time the passes).
+    const bool overlap = !timing;
+    if (!w.foldStream) {
+        LGS_CUDA(c, cudaStreamCreateWithFlags(&w.foldStream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            LGS_CUDA(c, cudaEventCreateWithFlags(&w.evTouch[b], cudaEventDisableTiming));
+            LGS_CUDA(c, cudaEventCreateWithFlags(&w.evFold[b], cudaEventDisableTiming));
+        }
+    }
+    bool usedBuf[2] = {false, false};
+    int chunkIdx = 0, lastBuf = -1;
     int s0 = 0;
     while (s0 < n) {
         // grow the chunk while it stays within 64 scans and the record budget
@@ -521,39 +656,67 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         if (nTiles * kChunk > w.kmin.cap) w.cleanTiles = 0;           // reserve() reallocates
         LGS_CUDA(c, w.kmin.reserve(nTiles * kChunk));
         LGS_CUDA(c, w.kmax.reserve(nTiles * kChunk));
-        LGS_CUDA(c, w.tileInfo.reserve(nTiles));
-        LGS_CUDA(c, w.pairs.reserve(pairBound));
-        LGS_CUDA(c, w.records.reserve(pairBound * kTileCells));
+        const int buf = chunkIdx & 1;
+        ++chunkIdx;
+        // this buffer's previous fold (chunk k - 2) must be done before it is overwritten; waiting on
+        // the host (rarely blocks: the fold runs two chunks behind) also makes reallocation safe
+        if (usedBuf[buf]) LGS_CUDA(c, cudaEventSynchronize(w.evFold[buf]));
+        LGS_CUDA(c, w.tileInfo[buf].reserve(nTiles));
+        LGS_CUDA(c, w.pairs[buf].reserve(2 * pairBound));
+        LGS_CUDA(c, w.records[buf].reserve(pairBound * kTileCells));
+        LGS_CUDA(c, w.side[buf].reserve(sideCap));
         if (nTiles > w.cleanTiles) {
             const size_t a0 = w.cleanTiles, cnt = w.kmin.cap / kChunk - a0;   // initialise up to the capacity
             LGS_CUDA(c, cudaMemsetAsync(w.kmin.p + a0 * kChunk, 0xFF, cnt * kChunk * sizeof(unsigned), c->stream));
             LGS_CUDA(c, cudaMemsetAsync(w.kmax.p + a0 * kChunk, 0, cnt * kChunk * sizeof(unsigned), c->stream));
             w.cleanTiles = w.kmin.cap / kChunk;
         }
-        LGS_CUDA(c, w.side.reserve(sideCap));
-        unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 4);   // [0] pairs, [1] side-buffer cursor
+        unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 4 + buf);   // [0] pairs, [1] side-buffer cursor
         LGS_CUDA(c, cudaMemsetAsync(nPairs, 0, 2 * sizeof(unsigned), c->stream));
 
         w.dirty = true;
+        stamp();
         const int beamsPad = (subBeams + 31) & ~31, pieces = subLen / kTile + 1;
         dim3 gm((unsigned)(((size_t)beamsPad * pieces + 127) / 128), ns);
         integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + cs, w.rel.p, x0, y0, tw, beamsPad, w.kmin.p, w.kmax.p);
         LGS_LAUNCH_CHECK(c);
-        integ_pairs_kernel<<<(unsigned)((nTiles * 32 + 127) / 128), 128, 0, c->stream>>>((int)nTiles, w.kmin.p, w.kmax.p,
-                                                                                       w.tileInfo.p, w.pairs.p, nPairs);
+        stamp();
+        integ_pairs_kernel<<<(unsigned)((nTiles * 32 + 127) / 128), 128, 0, c->stream>>>((int)nTiles, dMeta + cs, x0, y0, tw, w.kmin.p, w.kmax.p,
+                                                                                       w.tileInfo[buf].p, w.pairs[buf].p, nPairs);
         LGS_LAUNCH_CHECK(c);
+        stamp();
         w.dirty = false;
-        const unsigned touchBlocks = (unsigned)std::min<size_t>(pairBound, (size_t)c->sm_count * 8);
-        integ_touch_kernel<<<touchBlocks, kTileCells, 0, c->stream>>>(dMeta + cs, w.rel.p, w.pairs.p, nPairs, x0, y0, tw,
-                                                                      w.records.p, w.side.p, nPairs + 1, (unsigned)sideCap,
+        const unsigned touchBlocks = (unsigned)std::min<size_t>(pairBound, (size_t)c->sm_count * 5);
+        integ_touch_kernel<<<touchBlocks, kTileCells, 0, c->stream>>>(w.rel.p, w.pairs[buf].p, nPairs, w.records[buf].p,
+                                                                      w.side[buf].p, nPairs + 1, (unsigned)sideCap,
                                                                       w.counters.p);
         LGS_LAUNCH_CHECK(c);
-        FoldArgs a{dMeta + cs, w.rel.p, w.tileInfo.p, w.pairs.p, w.records.p, w.side.p, pHit, pMiss, oddsHit, oddsMiss};
-        integ_fold_kernel<<<(unsigned)nTiles, kTileCells, 0, c->stream>>>(a, g, x0, y0, tw);
+        stamp();
+        // fold on its own stream: it only has to follow this chunk's touch pass and the previous fold
+        LGS_CUDA(c, cudaEventRecord(w.evTouch[buf], c->stream));
+        cudaStream_t fs = overlap ? w.foldStream : c->stream;
+        if (overlap) LGS_CUDA(c, cudaStreamWaitEvent(fs, w.evTouch[buf], 0));
+        FoldArgs a{w.rel.p, w.tileInfo[buf].p, w.pairs[buf].p, w.records[buf].p, w.side[buf].p,
+                   timing ? w.counters.p : nullptr, pHit, pMiss, oddsHit, oddsMiss};
+        integ_fold_kernel<<<(unsigned)nTiles, kTileCells, 0, fs>>>(a, g, x0, y0, tw);
         LGS_LAUNCH_CHECK(c);
+        LGS_CUDA(c, cudaEventRecord(w.evFold[buf], fs));
+        usedBuf[buf] = true;
+        lastBuf = buf;
+        stamp();
     }
+    if (overlap && lastBuf >= 0) LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evFold[lastBuf], 0));
     LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (timing) {
+        float t[4] = {0, 0, 0, 0};
+        for (size_t k = 0; k + 5 <= evs.size(); k += 5)      // 5 stamps per chunk
+            for (int j = 0; j < 4; ++j) { float ms = 0; cudaEventElapsedTime(&ms, evs[k + j], evs[k + j + 1]); t[j] += ms; }
+        fprintf(stderr, "[lgs integrate] %d scans: mark %.3f ms, pairs %.3f ms, touch %.3f ms, fold %.3f ms; computed updates: "
+                "max per cell and call %llu, total %llu of %llu touches\n", n, t[0], t[1], t[2], t[3],
+                w.hCounters.p[2], w.hCounters.p[3], w.hCounters.p[0]);
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    }
     if (nUpdatesOut) *nUpdatesOut = (long long)w.hCounters.p[0];
     w.fallbackCells += (long long)w.hCounters.p[1];
     return LGS_OK;

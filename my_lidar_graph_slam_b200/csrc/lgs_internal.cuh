@@ -78,10 +78,14 @@ struct lgs_integ_ws {
     DevBuf<char> meta;                       // ScanMeta per scan
     DevBuf<int2> rel;                        // per beam: hit cell - sensor cell
     DevBuf<unsigned> kmin, kmax;             // per (tile, scan): beam index range [kmin, kmax)
-    DevBuf<uint2> tileInfo;                  // per tile: {first pair, pairs}
-    DevBuf<int4> pairs;                      // {tile, scan, k0, k1}
-    DevBuf<unsigned> records;                // per (pair, cell): encoded ordered touch sequence
-    DevBuf<unsigned> side;                   // raw touch / hit bitmap words of sequences no record holds
+    // Double buffered: the fold pass of chunk k (own stream) overlaps the mark / pairs / touch
+    // passes of chunk k + 1.
+    DevBuf<uint2> tileInfo[2];               // per tile: {first pair, pairs}
+    DevBuf<int4> pairs[2];                   // two int4 per (tile, scan) pair
+    DevBuf<unsigned> records[2];             // per (pair, cell): encoded ordered touch sequence
+    DevBuf<unsigned> side[2];                // raw touch / hit bitmap words of sequences no record holds
+    cudaStream_t foldStream = nullptr;
+    cudaEvent_t evTouch[2] = {nullptr, nullptr}, evFold[2] = {nullptr, nullptr};
     DevBuf<unsigned long long> counters;
     PinBuf<char> hMeta;
     PinBuf<unsigned long long> hCounters;
@@ -90,8 +94,15 @@ struct lgs_integ_ws {
     long long fallbackCells = 0;
     void release() {
         sensor.release(); hit.release(); begin.release(); meta.release(); rel.release();
-        side.release(); kmin.release(); kmax.release(); tileInfo.release(); pairs.release();
-        records.release(); counters.release(); hMeta.release(); hCounters.release();
+        kmin.release(); kmax.release(); counters.release(); hMeta.release(); hCounters.release();
+        for (int b = 0; b < 2; ++b) {
+            tileInfo[b].release(); pairs[b].release(); records[b].release(); side[b].release();
+            if (evTouch[b]) cudaEventDestroy(evTouch[b]);
+            if (evFold[b]) cudaEventDestroy(evFold[b]);
+            evTouch[b] = evFold[b] = nullptr;
+        }
+        if (foldStream) cudaStreamDestroy(foldStream);
+        foldStream = nullptr;
         cleanTiles = 0;
     }
 };
