@@ -458,6 +458,15 @@ def run_b200(args, rank, world_size, local_rank):
     k_proj, k_sweep, k_sel = (statistics.mean(x[i] for x in sweep_ms) for i in range(3))
     peak, peak_src = measured_peaks()
     achieved = gathers * 8 / (k_sweep * 1e-3) / 1e9
+    # measured gather ceilings for this map size (lgs_measure_gather_peak; SURVEY 8(d) asks for a
+    # micro-benchmark of the same access width because MEASURED_PEAKS.json has no L1/L2 figure)
+    gnx, gny = int(dense.shape[1]), int(dense.shape[0])
+    gather_peak = {
+        "rows32_aligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 32, True, True),
+        "rows32_unaligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 32, False, True),
+        "rows25_unaligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 25, False, True),
+        "rows25_unaligned_l2": capi.measure_gather_peak(ctx, gnx, gny, 25, False, False),
+    }
     results_dev = batch.results(grid, coarse)
 
     # ---- end to end through the public API with host buffers ---------------------------------
@@ -529,6 +538,12 @@ def run_b200(args, rank, world_size, local_rank):
                      "algorithmic_bytes_per_launch": gathers * 8,
                      "note": "gathers are served from L1/L2 (map is cache resident), so the HBM "
                              "roofline is not the binding limit; see DESIGN.md"},
+        "gather_roofline": {"bound": "l1 gather (8-byte warp-wide loads, map cache resident)",
+                            "achieved": achieved, "peak": gather_peak["rows32_aligned_l1"], "unit": "GB/s",
+                            "frac": achieved / gather_peak["rows32_aligned_l1"], "measured_peaks": gather_peak,
+                            "peak_source": "lgs_measure_gather_peak in this run: best of 3 launches, rows of 32 "
+                                           "doubles on 256-byte boundaries, L1-friendly walk over an array of "
+                                           "the map's size; the other entries are the sweep's own shapes"},
         "kernel_ms": {"csm_project": k_proj, "csm_sweep": k_sweep, "csm_select": k_sel},
         "cpu_baseline": cpu,
         "extra": extra,

@@ -67,6 +67,12 @@ int lgs_ctx_timer_stop(lgs_ctx* ctx, float* ms);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long lgs_ctx_launch_count(const lgs_ctx* ctx);
 const char* lgs_version(void);
+/* Diagnostic (bench.py roofline): measured bandwidth, in GB/s of useful bytes, of warp-wide 8-byte
+ * gathers of `row_lanes` (25 or 32) consecutive doubles from an nx x ny array -- the access shape of
+ * the scoring kernels.  aligned: rows start on 256-byte boundaries; local: successive rows move by a
+ * few cells (L1 hits) instead of uniformly at random (L2 hits). */
+int lgs_measure_gather_peak(lgs_ctx* ctx, int nx, int ny, int row_lanes, int aligned, int local,
+                            double* gbps);
 /* Test hook: width (in cells) of the guard band around cell edges inside which a projected
  * point is re-derived on the host with glibc sin/cos (default 1e-9).  Raising it only moves
  * more points onto the exact host path; results must not change. */
@@ -82,6 +88,13 @@ int lgs_grid_create(lgs_ctx* ctx, int nx, int ny, double min_x, double min_y, do
 int lgs_grid_destroy(lgs_grid* g);
 int lgs_grid_upload(lgs_grid* g, const double* dense);       /* host [ny][nx] -> device */
 int lgs_grid_download(const lgs_grid* g, double* dense);     /* device -> host [ny][nx] */
+/* Large maps split into row bands (one per GPU): declare this grid to hold cells
+ * [off_x, off_x + nx) x [off_y, off_y + ny) of a larger map whose cell (0, 0) has its lower-left
+ * corner at (min_x, min_y).  World -> cell conversion stays floor((p - min) / res) of the WHOLE map,
+ * so results are bit-identical to matching against it as long as every cell a match reads lies
+ * inside the band (the caller sizes the margin).  Honoured by lgs_precompute / lgs_pyramid_* (which
+ * are geometry free) and lgs_bb_*; the correlative matcher and the integration reject windows. */
+int lgs_grid_set_window(lgs_grid* g, int off_x, int off_y);
 int lgs_grid_info(const lgs_grid* g, int* nx, int* ny, double* min_x, double* min_y,
                   double* res, int* apron);
 

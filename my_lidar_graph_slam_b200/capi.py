@@ -54,6 +54,8 @@ class RtcsmParams(C.Structure):
 # name -> (restype, argtypes); also the list tests use to check the exported symbols.
 SIGNATURES = {
     "lgs_version": (C.c_char_p, []),
+    "lgs_measure_gather_peak": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_double)]),
     "lgs_set_edge_eps": (None, [C.c_double]),
     "lgs_get_edge_eps": (C.c_double, []),
     "lgs_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
@@ -69,6 +71,7 @@ SIGNATURES = {
     "lgs_grid_destroy": (C.c_int, [vp]),
     "lgs_grid_upload": (C.c_int, [vp, c_dp]),
     "lgs_grid_download": (C.c_int, [vp, c_dp]),
+    "lgs_grid_set_window": (C.c_int, [vp, C.c_int, C.c_int]),
     "lgs_grid_info": (C.c_int, [vp, c_ip, c_ip, c_dp, c_dp, c_dp, c_ip]),
     "lgs_precompute": (C.c_int, [vp, vp, C.c_int, vp]),
     "lgs_pyramid_create": (C.c_int, [vp, vp, C.c_int, C.POINTER(vp)]),
@@ -189,7 +192,15 @@ class Grid:
         return g
 
     def like(self):
-        return Grid(self.ctx, self.nx, self.ny, self.min_x, self.min_y, self.res, self.apron)
+        g = Grid(self.ctx, self.nx, self.ny, self.min_x, self.min_y, self.res, self.apron)
+        if getattr(self, "off", (0, 0)) != (0, 0):
+            g.set_window(*self.off)
+        return g
+
+    def set_window(self, off_x: int, off_y: int):
+        """This grid holds cells [off, off + n) of a larger map with corner (min_x, min_y)."""
+        self.ctx.check(lib().lgs_grid_set_window(self.h, int(off_x), int(off_y)))
+        self.off = (int(off_x), int(off_y))
 
     def upload(self, dense):
         dense = np.ascontiguousarray(dense, dtype=np.float64)
@@ -513,3 +524,10 @@ def integrate_packed(ctx: Context, grid: Grid, packed: PackedHits, p_hit=0.6, p_
 def integrate_scans(ctx: Context, grid: Grid, sensor_xy, hits_list, p_hit=0.6, p_miss=0.45) -> int:
     """lgs_grid_integrate_scans for scans given as (sensor_xy[k][2], [hit_xy arrays]) -> updates."""
     return integrate_packed(ctx, grid, PackedHits(sensor_xy, hits_list), p_hit, p_miss)
+
+
+def measure_gather_peak(ctx: Context, nx=960, ny=640, row_lanes=25, aligned=False, local=True) -> float:
+    """Measured GB/s of warp-wide 8-byte row gathers from an nx x ny array (lgs_measure_gather_peak)."""
+    g = C.c_double()
+    ctx.check(lib().lgs_measure_gather_peak(ctx.h, nx, ny, row_lanes, int(aligned), int(local), C.byref(g)))
+    return g.value

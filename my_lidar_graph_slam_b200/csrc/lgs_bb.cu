@@ -52,6 +52,7 @@ struct BbQuery {
     double thrAbs;
     double minX, minY, res, invRes;
     int nx, ny, pitch;              // submap geometry
+    int offX, offY;                 // window origin (cells) when the grid is a band of a larger map
     int winX, winY, winT, nT, nTpad;
     int nrx, nry;                   // roots per axis
     int nUse, scan;                 // usable beams, index of the distinct scan
@@ -137,7 +138,7 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
         const double fx = floor(qx), fy = floor(qy);
         const double rx = qx - fx, ry = qy - fy;
         const bool edge = !(rx >= eps && rx <= 1.0 - eps && ry >= eps && ry <= 1.0 - eps);
-        int2 v = make_int2(__double2int_rd(qx), __double2int_rd(qy));
+        int2 v = make_int2(__double2int_rd(qx) - d.offX, __double2int_rd(qy) - d.offY);
         if (edge) {
             const int f = atomicAdd(flagCount, 1);
             if (f < kFlagCapBB) {
@@ -581,6 +582,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         BbQuery& d = b->qs[q];
         d.minX = g0->min_x; d.minY = g0->min_y; d.res = g0->res; d.invRes = 1.0 / g0->res;
         d.nx = g0->nx; d.ny = g0->ny; d.pitch = g0->pitch;
+        d.offX = g0->off_x; d.offY = g0->off_y;
         for (int h = 0; h <= H; ++h) d.level[h] = lgs_pyramid_level(pyr, h)->origin();
         // ComputeSearchStep (scan_matcher_branch_bound.cpp:178-197)
         if (!haveMaxR[sq]) {           // std::max_element over the scan, once per scan
@@ -744,11 +746,11 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
             int* e = exact.data() + (size_t)k * (spanX + spanY);
             for (int o = 0; o < spanX; ++o) {
                 const double px = u.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
-                e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res));
+                e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res)) - d.offX;
             }
             for (int o = 0; o < spanY; ++o) {
                 const double py = u.sy + static_cast<double>(o - d.winY) * stepY;
-                e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res));
+                e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res)) - d.offY;
             }
             b->fixups[fl[k].q]++;
         }

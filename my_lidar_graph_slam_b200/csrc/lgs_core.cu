@@ -155,6 +155,13 @@ int lgs_grid_download(const lgs_grid* g, double* dense) {
     return LGS_OK;
 }
 
+int lgs_grid_set_window(lgs_grid* g, int off_x, int off_y) {
+    if (!g) return LGS_ERR_INVALID;
+    if (off_x < 0 || off_y < 0) return lgs_fail(g->ctx, LGS_ERR_INVALID, "grid_set_window: negative offset");
+    g->off_x = off_x; g->off_y = off_y;
+    return LGS_OK;
+}
+
 int lgs_grid_info(const lgs_grid* g, int* nx, int* ny, double* min_x, double* min_y, double* res,
                   int* apron) {
     if (!g) return LGS_ERR_INVALID;

@@ -414,6 +414,8 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     const int n = scans->n_scans;
     if (n < 0 || (n > 0 && (!scans->beam_begin || !scans->sensor_pose)))
         return lgs_fail(c, LGS_ERR_INVALID, "rtcsm_batch_upload: bad scan batch");
+    if (grid->off_x || grid->off_y)
+        return lgs_fail(c, LGS_ERR_INVALID, "rtcsm_batch_upload: windowed grids (lgs_grid_set_window) are not supported");
     LGS_CUDA(c, cudaSetDevice(c->device));
     const lgs_rtcsm_params& p = b->params;
     b->uploaded = false; b->ran = false;

@@ -554,6 +554,8 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     if (n < 0 || (n > 0 && (!scans->sensor_xy || !scans->hit_begin)))
         return lgs_fail(c, LGS_ERR_INVALID, "integrate: bad scan batch");
     if (n == 0) return LGS_OK;
+    if (grid->off_x || grid->off_y)
+        return lgs_fail(c, LGS_ERR_INVALID, "integrate: windowed grids (lgs_grid_set_window) are not supported");
     const long long total = scans->hit_begin[n];
     if (total > 0 && !scans->hit_xy) return lgs_fail(c, LGS_ERR_INVALID, "integrate: hit_xy is NULL");
     LGS_CUDA(c, cudaSetDevice(c->device));

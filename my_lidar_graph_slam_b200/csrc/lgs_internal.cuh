@@ -18,6 +18,10 @@ struct lgs_grid {
     int pitch = 0;        // nx + 2 * apron (cells)
     int rows = 0;         // ny + 2 * apron
     double min_x = 0, min_y = 0, res = 0;
+    // Window into a larger map (large-map row bands): the grid stores cells
+    // [off, off + n) of a map whose cell (0, 0) has its corner at (min_x, min_y); world -> cell
+    // conversions stay global (bit-identical to the whole map) and subtract the offset.
+    int off_x = 0, off_y = 0;
     bool owns = true;     // false for pyramid levels (views into the pyramid's slab)
     double* d = nullptr;  // rows * pitch doubles; cell (x, y) at d[(y + apron) * pitch + x + apron]
     __host__ __device__ const double* origin() const { return d + (size_t)apron * pitch + apron; }

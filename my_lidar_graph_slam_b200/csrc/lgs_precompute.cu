@@ -68,7 +68,7 @@ winmax_double_kernel(const double* __restrict__ in, double* __restrict__ out, in
 
 bool same_geometry(const lgs_grid* a, const lgs_grid* b) {
     return a->nx == b->nx && a->ny == b->ny && a->min_x == b->min_x && a->min_y == b->min_y &&
-           a->res == b->res;
+           a->res == b->res && a->off_x == b->off_x && a->off_y == b->off_y;
 }
 
 }  // namespace

@@ -51,6 +51,33 @@ def all_gather_records(local: np.ndarray, n_items: int, rank: int, world: int, d
     return out
 
 
+def all_gather_variable(local: np.ndarray, n_items: int, world: int, device=None):
+    """All-gather record arrays whose per-rank counts are arbitrary (queries follow the band their
+    sensor cell falls in): one all-reduce(MAX) of the counts, then one padded all-gather."""
+    if world == 1:
+        out = np.zeros(n_items, dtype=RECORD)
+        out[local["submap"]] = local
+        return out
+    import torch
+    import torch.distributed as dist
+    cnt = torch.tensor([len(local)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+    per = max(int(cnt.item()), 1)
+    buf = np.zeros(per, dtype=RECORD)
+    buf["submap"] = -1
+    buf[:len(local)] = local
+    send = torch.from_numpy(buf.view(np.uint8).copy())
+    if device is not None:
+        send = send.to(device)
+    recv = torch.empty(world * send.numel(), dtype=torch.uint8, device=send.device)
+    dist.all_gather_into_tensor(recv, send)
+    allrec = recv.cpu().numpy().view(RECORD)
+    allrec = allrec[allrec["submap"] >= 0]
+    out = np.zeros(n_items, dtype=RECORD)
+    out[allrec["submap"]] = allrec
+    return out
+
+
 def best_candidate(records: np.ndarray):
     """Index of the found record with the highest score (ties: lowest submap index), or -1."""
     ok = np.flatnonzero(records["found"] != 0)

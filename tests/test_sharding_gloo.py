@@ -59,3 +59,59 @@ def test_all_gather_records_world2_gloo():
     assert full0["ix"].tolist() == list(range(n_items)) and full0["found"].tolist() == [1, 0, 0, 1, 0, 0, 1]
     best = got[0][2]
     assert full0["found"][best] == 1 and full0["score"][best] == max(full0["score"][[0, 3, 6]])
+
+
+# ---- large-map row bands (C5) ------------------------------------------------------------------------
+def test_row_bands_partition_the_map_and_route_queries():
+    from my_lidar_graph_slam_b200 import largemap
+    for ny in (1, 7, 1000, 8000):
+        for world in (1, 2, 3, 8):
+            bands = [largemap.band_rows(ny, world, g) for g in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == ny
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            rows = np.arange(-3, ny + 3)
+            own = largemap.owner_of_rows(rows, ny, world)
+            for r, g in zip(np.clip(rows, 0, ny - 1), own):
+                assert bands[g][0] <= r < bands[g][1] or bands[g][0] == bands[g][1]
+    below, above = largemap.margins(0.05, 20.0, 2.0, 6)
+    assert below == 402 + 20 + 2 and above == 402 + 20 + 64 + 63 + 2
+    assert largemap.window_rows(8000, 8, 0, below, above) == (0, 1000 + above)
+    assert largemap.window_rows(8000, 8, 7, below, above) == (7000 - below, 8000)
+    assert largemap.sensor_rows([0.0, -0.01, 0.05], 0.0, 0.05).tolist() == [0, -1, 1]
+
+
+def _band_worker(rank, world, port, n_queries, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from my_lidar_graph_slam_b200 import largemap, sharding
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rows = (np.arange(n_queries) * 37) % 100                 # sensor rows of the queries in a 100-row map
+    mine = np.flatnonzero(largemap.owner_of_rows(rows, 100, world) == rank)
+
+    class R:
+        def __init__(self, g):
+            self.found, self.ix, self.iy, self.it, self.score = 1, int(rows[g]), g, rank, float(g)
+    local = sharding.pack([R(int(g)) for g in mine], mine)
+    full = sharding.all_gather_variable(local, n_queries, world)
+    q.put((rank, full.tobytes()))
+    dist.destroy_process_group()
+
+
+def test_band_routed_queries_all_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    from my_lidar_graph_slam_b200 import largemap, sharding
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, n = _free_port(), 11
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1]
+    full = np.frombuffer(got[0][1], dtype=sharding.RECORD)
+    rows = (np.arange(n) * 37) % 100
+    assert full["submap"].tolist() == list(range(n)) and full["ix"].tolist() == rows.tolist()
+    assert full["it"].tolist() == largemap.owner_of_rows(rows, 100, 2).tolist()    # uneven: 6 vs 5 queries
