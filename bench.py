@@ -236,6 +236,14 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
         grids.append(grid)
         cells += grid.nx * grid.ny
     build_s = time.perf_counter() - t0
+    # pyramids: the first build grows the stream-ordered memory pool (one-time allocation cost); the
+    # timed build is a REbuild of every pyramid, which is what the loop detector does whenever a
+    # submap has changed (loop_detector_branch_bound.cpp:44-53)
+    for grid in grids:
+        pyramids.append(capi.Pyramid(ctx, grid, 6))
+    for p in pyramids:
+        p.close()
+    pyramids = []
     ctx.synchronize()
     ctx.timer_start()
     for grid in grids:
@@ -320,6 +328,94 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
         p.close()
     for g in grids:
         g.close()
+    return out
+
+
+def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_ranks, side, n_queries, steps):
+    """C5: one side x side map (8 x 8 stitched copies of a GPU-integrated 1000 x 1000 tile), 7 pyramid
+    levels, split into world_size row bands (band + margin per GPU, largemap.py), then a batch of loop
+    queries routed to the band of their sensor cell and all-gathered."""
+    from my_lidar_graph_slam_b200 import capi, largemap, sharding
+    T = 1000                                            # tile side (cells) = 50 m
+    world = synth.RoomsWorld(40.0, 5.0, seed=12)
+    angles = synth.beam_angles(1081, 270.0)
+    traj = np.concatenate([synth.trajectory(world, 10, step=0.5, seed=40 + k, start=(x, y, 0.4 * k))
+                           for k, (x, y) in enumerate(((-12.5, -12.5), (2.5, -7.5), (-7.5, 7.5), (12.5, 12.5)))])
+    rng = np.random.default_rng(13)
+    scans = [synth.make_scan(world, p, angles, rng) for p in traj]
+    hits = [capi.scan_hit_points(p, angles, r, 0.02, 20.0)[0] for p, r in zip(traj, scans)]
+    tile_grid = capi.Grid(ctx, T, T, -25.0, -25.0, 0.05, apron=1)
+    capi.integrate_scans(ctx, tile_grid, traj[:, :2], hits)
+    tile = tile_grid.download()
+    tile_grid.close()
+    n_t = side // T
+    ny = nx = n_t * T
+
+    def rows_provider(a, b):                            # rows [a, b) of the stitched map
+        return np.tile(tile[np.arange(a, b) % T], (1, n_t))
+
+    band = largemap.BandedMap(ctx, rows_provider, nx, ny, -25.0, -25.0, 0.05, rank, world_size, BB["node_height_max"],
+                              reach_m=BB["score_range_max"], range_y_m=BB["range_y"])
+    ctx.synchronize()
+    barrier()
+    ctx.timer_start()
+    band.build_pyramid()
+    pyr_ms = max_over_ranks(ctx.timer_stop())
+    owned_cells = (band.r1 - band.r0) * nx
+    # queries: a pose of the tile trajectory moved into a random tile, perturbed
+    qr = np.random.default_rng(14)
+    q_scans, q_init = [], []
+    for k in range(n_queries):
+        base = traj[int(qr.integers(0, len(traj)))]
+        off = np.array([qr.integers(0, n_t) * T * 0.05, qr.integers(0, n_t) * T * 0.05, 0.0])
+        q_scans.append(synth.make_scan(world, base, angles, qr))
+        q_init.append(base + off + np.array([qr.uniform(-0.4, 0.4), qr.uniform(-0.4, 0.4), qr.uniform(-0.1, 0.1)]))
+    q_init = np.asarray(q_init)
+    owner = largemap.owner_of_rows(largemap.sensor_rows(q_init[:, 1], -25.0, 0.05), ny, world_size)
+    mine = np.flatnonzero(owner == rank)
+    dev = f"cuda:{local_rank}" if world_size > 1 else None
+    batch = capi.BbBatch(ctx, **BB)
+    sc = capi.Scans([angles] * len(mine), [q_scans[k] for k in mine], [q_init[k] for k in mine],
+                    range_min=0.02, range_max=30.0) if len(mine) else None
+
+    def step():
+        res = []
+        if sc is not None:
+            batch.upload(sc, [band.pyramid] * len(mine), 0.6)
+            batch.run()
+            res = batch.results()
+        return sharding.all_gather_variable(sharding.pack(res, mine), n_queries, world_size, dev)
+
+    for _ in range(2):
+        rec = step()
+    ctx.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rec = step()
+    ctx.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    dev_ms = 0.0
+    if sc is not None:
+        batch.upload(sc, [band.pyramid] * len(mine), 0.6)
+    barrier()
+    ctx.timer_start()
+    for _ in range(steps):
+        if sc is not None:
+            batch.run()
+    dev_ms = max_over_ranks(ctx.timer_stop())
+    out = {"workload": f"C5 large map {nx}x{ny} cells (8x8 stitched GPU-integrated tiles), 7 levels, "
+                       f"{world_size} row band(s) + margins, {n_queries} loop queries routed by sensor row",
+           "precompute_ms": pyr_ms,
+           "precompute_cells_levels_per_s": sum_over_ranks(float(owned_cells)) * 7 / (pyr_ms * 1e-3),
+           "precompute_algorithmic_GBps": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9,
+           "band_rows_rank0": [int(band.w0), int(band.w1)], "queries_rank0": int(len(mine)),
+           "loop_queries_per_s": n_queries * steps / (dev_ms * 1e-3) if dev_ms > 0 else None,
+           "loop_queries_per_s_e2e": n_queries * steps / e2e_s,
+           "loops_found": int((rec["found"] != 0).sum()), "n_gpus": world_size,
+           "scaling": "strong (fixed map and query batch; bands and their queries per rank, all-gather of records)"}
+    batch.close()
+    band.close()
     return out
 
 
@@ -493,6 +589,9 @@ def run_b200(args, rank, world_size, local_rank):
                                          world_size == 1 and not args.no_cpu_baseline)
         if rank == 0:
             extra["grid_integration"] = run_c3(ctx, 256, args.c3_scans, not args.no_cpu_baseline)
+        if args.c5_side > 0:
+            extra["large_map"] = run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_ranks,
+                                        args.c5_side, args.c5_queries, max(2, min(args.steps, 5)))
     if rank != 0:
         return
     # ---- CPU baseline: the unmodified reference on a bounded sample, parity-checked ------------
@@ -561,6 +660,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C3 side measurements")
     ap.add_argument("--submaps", type=int, default=500, help="C4: submaps per loop query batch")
+    ap.add_argument("--c5-side", type=int, default=8000, help="C5: map side in cells (multiple of 1000; 0 = skip)")
+    ap.add_argument("--c5-queries", type=int, default=256, help="C5: loop queries per batch")
     ap.add_argument("--c3-scans", type=int, default=4096, help="C3: scans in the bounded sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

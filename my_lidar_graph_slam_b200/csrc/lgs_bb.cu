@@ -577,6 +577,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         if (!pyr || lgs_pyramid_levels(pyr) < H + 1)
             return lgs_fail(c, LGS_ERR_INVALID, "bb: query %d needs a pyramid with %d levels", q, H + 1);
         const lgs_grid* g0 = lgs_pyramid_level(pyr, 0);
+        lgs_pyramid_note_user(pyr, c);
         if (g0->ctx->device != c->device)
             return lgs_fail(c, LGS_ERR_INVALID, "bb: pyramid of query %d lives on another device", q);
         BbQuery& d = b->qs[q];

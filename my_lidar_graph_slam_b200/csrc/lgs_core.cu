@@ -39,6 +39,13 @@ int lgs_ctx_create(int device, lgs_ctx** out) {
         cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return LGS_ERR_CUDA; }
     if (prop.major < 10) { delete c; return LGS_ERR_CUDA; }   // sm_100a code only
     c->sm_count = prop.multiProcessorCount;
+    {   // keep freed stream-ordered allocations (pyramid slabs) in the pool instead of returning them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         delete c;

@@ -131,3 +131,6 @@ extern double g_lgs_edge_eps;
 
 // Pyramid levels are plain grids sharing the geometry of the map they were built from.
 const lgs_grid* lgs_pyramid_level(const lgs_pyramid* p, int level);
+// A matcher of context `user` is about to read the pyramid (its slab is freed stream-ordered on the
+// owner's stream, so foreign readers make the destroy synchronise the device first).
+void lgs_pyramid_note_user(const lgs_pyramid* p, const lgs_ctx* user);

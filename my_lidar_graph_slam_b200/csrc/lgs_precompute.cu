@@ -50,20 +50,56 @@ winmax_x_kernel(const double* __restrict__ in, double* __restrict__ out, int nx,
     out[(size_t)y * pitchOut + x] = m;
 }
 
-// Pyramid doubling step: window 2w from window w (both axes at once).
+// Pyramid doubling step: window 2w from window w (both axes at once).  A block covers
+// CELLS * 256 consecutive cells of one row; thread t owns cells t, t + 256, ... so every load and
+// store is coalesced and CELLS * 4 independent loads are in flight per thread.  The output level is
+// larger than L2 on big maps and is next read by a later launch: streaming stores.
+template <int CELLS>
 __global__ void __launch_bounds__(256)
 winmax_double_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny,
                      int pitch, int w) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= nx) return;
-    int x0, x1, y0, y1;
-    if (nx >= 2 * w) { x0 = min(x, nx - 2 * w); x1 = x0 + w; } else { x0 = 0; x1 = nx - 1; }
+    int y0, y1;
     if (ny >= 2 * w) { y0 = min(y, ny - 2 * w); y1 = y0 + w; } else { y0 = 0; y1 = ny - 1; }
     const double* r0 = in + (size_t)y0 * pitch;
     const double* r1 = in + (size_t)y1 * pitch;
-    const double m = fmax(fmax(__ldg(r0 + x0), __ldg(r0 + x1)), fmax(__ldg(r1 + x0), __ldg(r1 + x1)));
-    out[(size_t)y * pitch + x] = m;
+    double* o = out + (size_t)y * pitch;
+    const int xb = blockIdx.x * (CELLS * 256) + threadIdx.x;
+    double m[CELLS];
+#pragma unroll
+    for (int k = 0; k < CELLS; ++k) {
+        const int x = min(xb + k * 256, nx - 1);
+        int x0, x1;
+        if (nx >= 2 * w) { x0 = min(x, nx - 2 * w); x1 = x0 + w; } else { x0 = 0; x1 = nx - 1; }
+        m[k] = fmax(fmax(__ldg(r0 + x0), __ldg(r0 + x1)), fmax(__ldg(r1 + x0), __ldg(r1 + x1)));
+    }
+#pragma unroll
+    for (int k = 0; k < CELLS; ++k) {
+        const int x = xb + k * 256;
+        if (x < nx) __stcs(o + x, m[k]);
+    }
+}
+
+// Zero the apron of every level of a pyramid slab (the interior is fully written by the level
+// kernels, so clearing the whole slab would double the write traffic of a build).
+__global__ void __launch_bounds__(256)
+zero_apron_kernel(double* __restrict__ slab, size_t levelCells, int nLevels, int pitch, int rows, int apron) {
+    const long long band = (long long)apron * pitch;                       // full rows at the bottom / top
+    const long long side = (long long)(rows - 2 * apron) * (2 * apron);     // left + right columns
+    const long long per = 2 * band + side;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * nLevels) return;
+    const int lvl = (int)(t / per);
+    const long long r = t - (long long)lvl * per;
+    size_t cell;
+    if (r < band) cell = (size_t)r;
+    else if (r < 2 * band) cell = (size_t)(rows - apron) * pitch + (size_t)(r - band);
+    else {
+        const long long q = r - 2 * band;
+        const int row = apron + (int)(q / (2 * apron)), k = (int)(q % (2 * apron));
+        cell = (size_t)row * pitch + (k < apron ? k : pitch - 2 * apron + k);
+    }
+    slab[levelCells * lvl + cell] = 0.0;
 }
 
 bool same_geometry(const lgs_grid* a, const lgs_grid* b) {
@@ -77,7 +113,12 @@ struct lgs_pyramid {
     lgs_ctx* ctx = nullptr;
     double* slab = nullptr;             // all levels, contiguous
     std::vector<lgs_grid*> levels;      // headers into the slab (owns == false)
+    bool foreign = false;               // read by a context other than the owner (another stream)
 };
+
+void lgs_pyramid_note_user(const lgs_pyramid* p, const lgs_ctx* user) {
+    if (p && user != p->ctx) const_cast<lgs_pyramid*>(p)->foreign = true;
+}
 
 const lgs_grid* lgs_pyramid_level(const lgs_pyramid* p, int level) {
     return (p && level >= 0 && level < (int)p->levels.size()) ? p->levels[level] : nullptr;
@@ -114,15 +155,26 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
     // is a grid header pointing into it, with the input's geometry and zero apron.
     const size_t levelCells = (size_t)in->pitch * in->rows;
     const size_t bytes = levelCells * (size_t)(heightMax + 1) * sizeof(double);
-    cudaError_t me = cudaMalloc(&p->slab, std::max<size_t>(bytes, 8));
+    // Stream-ordered allocation from the device pool (kept warm by lgs_ctx_create's release
+    // threshold): rebuilding a pyramid does not pay a synchronous cudaMalloc of the whole slab.
+    cudaError_t me = cudaMallocAsync(&p->slab, std::max<size_t>(bytes, 8), c->stream);
     if (me != cudaSuccess) {
         delete p;
-        return lgs_fail(c, LGS_ERR_NOMEM, "pyramid: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(me));
+        return lgs_fail(c, LGS_ERR_NOMEM, "pyramid: cudaMallocAsync(%zu) -> %s", bytes, cudaGetErrorString(me));
     }
-    me = cudaMemsetAsync(p->slab, 0, std::max<size_t>(bytes, 8), c->stream);
+    if (in->apron > 0 && in->rows > 2 * in->apron) {
+        const long long per = 2LL * in->apron * in->pitch + (long long)(in->rows - 2 * in->apron) * 2 * in->apron;
+        const long long n = per * (heightMax + 1);
+        zero_apron_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(p->slab, levelCells, heightMax + 1,
+                                                                            in->pitch, in->rows, in->apron);
+        c->launches++;
+        me = cudaGetLastError();
+    } else {
+        me = cudaMemsetAsync(p->slab, 0, std::max<size_t>(bytes, 8), c->stream);
+    }
     if (me != cudaSuccess) {
-        cudaFree(p->slab); delete p;
-        return lgs_fail(c, LGS_ERR_CUDA, "pyramid: memset -> %s", cudaGetErrorString(me));
+        cudaFreeAsync(p->slab, c->stream); delete p;
+        return lgs_fail(c, LGS_ERR_CUDA, "pyramid: apron clear -> %s", cudaGetErrorString(me));
     }
     for (int h = 0; h <= heightMax; ++h) {
         lgs_grid* g = new lgs_grid(*in);
@@ -141,9 +193,10 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
             lgs_pyramid_destroy(p);
             return lgs_fail(c, LGS_ERR_CUDA, "pyramid: level-0 copy -> %s", cudaGetErrorString(e));
         }
-        dim3 block(256), gridDim((in->nx + 255) / 256, in->ny);
+        constexpr int kCells = 4;
+        dim3 block(256), gridDim((in->nx + kCells * 256 - 1) / (kCells * 256), in->ny);
         for (int h = 1; h <= heightMax; ++h) {
-            winmax_double_kernel<<<gridDim, block, 0, c->stream>>>(
+            winmax_double_kernel<kCells><<<gridDim, block, 0, c->stream>>>(
                 p->levels[h - 1]->origin(), p->levels[h]->origin(), in->nx, in->ny, in->pitch,
                 1 << (h - 1));
             c->launches++;
@@ -161,9 +214,9 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
 int lgs_pyramid_destroy(lgs_pyramid* p) {
     if (!p) return LGS_OK;
     cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
     for (lgs_grid* g : p->levels) delete g;
-    if (p->slab) cudaFree(p->slab);
+    if (p->foreign) cudaDeviceSynchronize();               // another context's stream may still read it
+    if (p->slab) cudaFreeAsync(p->slab, p->ctx->stream);   // ordered after every use on the context stream
     delete p;
     return LGS_OK;
 }
