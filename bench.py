@@ -434,6 +434,8 @@ def run_c3(ctx, n_distinct, n_total, with_cpu):
     grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
     B = int(os.environ.get("C3_BATCH", "256"))
     batches = [capi.PackedHits(traj[k:k + B, :2], hits[k:k + B]) for k in range(0, n_distinct, B)]
+    for b in batches:                                                 # page-locked host inputs
+        capi.pin(ctx, b.hit, b.sxy, b.begin)
     capi.integrate_packed(ctx, grid, batches[0])                      # warm-up
     capi.grid_clear(grid)
     ctx.synchronize()
@@ -470,6 +472,8 @@ def run_c3(ctx, n_distinct, n_total, with_cpu):
                                                  f"({dtc:.1f} s; order-dependent, single map); GPU map bit-identical: {same}"}
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
+    for b in batches:
+        capi.unpin(ctx, b.hit, b.sxy, b.begin)
     grid.close()
     return out
 
@@ -516,6 +520,9 @@ def run_b200(args, rank, world_size, local_rank):
     def step_device():
         ctx.check(lib.lgs_precompute(ctx.h, grid.h, 5, coarse.h))
         batch.run(grid, coarse)
+
+    # host inputs of the end-to-end path are page-locked (lgs_host_pin), as the bench contract asks
+    capi.pin(ctx, dense, scans.angles, scans.ranges, scans.sensor_pose)
 
     def step_e2e():
         grid.upload(dense)

@@ -66,6 +66,10 @@ int lgs_ctx_timer_start(lgs_ctx* ctx);
 int lgs_ctx_timer_stop(lgs_ctx* ctx, float* ms);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long lgs_ctx_launch_count(const lgs_ctx* ctx);
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) so that the H2D copies of the
+ * upload calls run at full PCIe / C2C speed and asynchronously; optional, any host memory works. */
+int lgs_host_pin(lgs_ctx* ctx, void* ptr, unsigned long long bytes);
+int lgs_host_unpin(lgs_ctx* ctx, void* ptr);
 const char* lgs_version(void);
 /* Diagnostic (bench.py roofline): measured bandwidth, in GB/s of useful bytes, of warp-wide 8-byte
  * gathers of `row_lanes` (25 or 32) consecutive doubles from an nx x ny array -- the access shape of

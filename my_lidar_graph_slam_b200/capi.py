@@ -54,6 +54,8 @@ class RtcsmParams(C.Structure):
 # name -> (restype, argtypes); also the list tests use to check the exported symbols.
 SIGNATURES = {
     "lgs_version": (C.c_char_p, []),
+    "lgs_host_pin": (C.c_int, [vp, vp, C.c_ulonglong]),
+    "lgs_host_unpin": (C.c_int, [vp, vp]),
     "lgs_measure_gather_peak": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_double)]),
     "lgs_set_edge_eps": (None, [C.c_double]),
@@ -531,3 +533,16 @@ def measure_gather_peak(ctx: Context, nx=960, ny=640, row_lanes=25, aligned=Fals
     g = C.c_double()
     ctx.check(lib().lgs_measure_gather_peak(ctx.h, nx, ny, row_lanes, int(aligned), int(local), C.byref(g)))
     return g.value
+
+
+def pin(ctx: Context, *arrays):
+    """Page-lock numpy arrays in place (lgs_host_pin) so uploads from them run at full speed."""
+    for a in arrays:
+        if a is not None and a.nbytes:
+            ctx.check(lib().lgs_host_pin(ctx.h, a.ctypes.data_as(vp), a.nbytes))
+
+
+def unpin(ctx: Context, *arrays):
+    for a in arrays:
+        if a is not None and a.nbytes:
+            lib().lgs_host_unpin(ctx.h, a.ctypes.data_as(vp))

@@ -76,6 +76,19 @@ int lgs_ctx_synchronize(lgs_ctx* c) {
     return LGS_OK;
 }
 
+int lgs_host_pin(lgs_ctx* c, void* ptr, unsigned long long bytes) {
+    if (!c || !ptr || bytes == 0) return LGS_ERR_INVALID;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return LGS_OK;
+}
+
+int lgs_host_unpin(lgs_ctx* c, void* ptr) {
+    if (!c || !ptr) return LGS_ERR_INVALID;
+    LGS_CUDA(c, cudaHostUnregister(ptr));
+    return LGS_OK;
+}
+
 void* lgs_ctx_stream(lgs_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int lgs_ctx_timer_start(lgs_ctx* c) {

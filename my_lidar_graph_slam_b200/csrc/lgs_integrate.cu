@@ -283,14 +283,24 @@ integ_touch_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs,
     const unsigned nP = *nPairs;
     unsigned total = 0, overflow = 0;
     int4 nextA = make_int4(0, 0, 0, 0), nextB = nextA;
-    if (blockIdx.x < nP) { nextA = pairs[2 * (size_t)blockIdx.x]; nextB = pairs[2 * (size_t)blockIdx.x + 1]; }
+    // Threads per beam in the scatter step: 4 (4 steps each) for segments of <= 64 beams, else 2.
+    auto lanesPerBeam = [](int nb) { return nb <= kTileCells / 4 ? 4 : 2; };
+    int2 eNext = make_int2(0, 0);                            // this thread's beam of the next pair's first segment
+    if (blockIdx.x < nP) {
+        nextA = pairs[2 * (size_t)blockIdx.x]; nextB = pairs[2 * (size_t)blockIdx.x + 1];
+        const int nb = min(kSeg, nextA.w - nextA.z), b = tid / lanesPerBeam(nb);
+        if (b < nb) eNext = __ldg(rel + nextB.x + nextA.z + b);
+    }
     for (unsigned p = blockIdx.x; p < nP; p += gridDim.x) {
         const int4 pr = nextA;                              // .x/.y tile origin - sensor cell, .z/.w beams
         const int2* __restrict__ E = rel + nextB.x;
-        if (p + gridDim.x < nP) {                           // the next descriptor is in flight meanwhile
+        const int2 eFirst = eNext;
+        const bool more = p + gridDim.x < nP;
+        if (more) {                                         // the next descriptor is in flight meanwhile
             nextA = pairs[2 * (size_t)(p + gridDim.x)];
             nextB = pairs[2 * (size_t)(p + gridDim.x) + 1];
         }
+        bool fetched = false;
         const int ox = pr.x, oy = pr.y;
         TouchSeq seq;
         unsigned rec = 0u, sideOff = 0u;
@@ -307,19 +317,22 @@ integ_touch_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs,
                 for (int w = 0; w < nW; ++w) { sTouch[w * kTileCells + tid] = 0u; sHit[w * kTileCells + tid] = 0u; }
                 __syncthreads();
                 const int nb = min(kSeg, pr.w - seg);
-                if (tid < nb) {
-                    // one thread per beam: the <= 16 steps whose major coordinate lies inside the tile;
-                    // the minor coordinate floor((2 amin k + amaj) / (2 amaj)) is divided out once and
-                    // then carried with its remainder (2 amin <= 2 amaj: at most one increment a step)
-                    const int b = tid;
-                    const int2 e = __ldg(E + seg + b);
+                const int per = lanesPerBeam(nb), b = tid / per;
+                if (b < nb) {
+                    // `per` threads per beam share the <= 16 steps whose major coordinate lies inside
+                    // the tile; the minor coordinate floor((2 amin k + amaj) / (2 amaj)) is divided
+                    // out once per thread and then carried with its remainder (2 amin <= 2 amaj: at
+                    // most one increment a step)
+                    const int2 e = (pass == 0 && seg == pr.z) ? eFirst : __ldg(E + seg + b);
                     const int ax = abs(e.x), ay = abs(e.y);
                     const bool xMajor = ax > ay;
                     const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
                     const int eMaj = xMajor ? e.x : e.y, eMin = xMajor ? e.y : e.x;
                     const int oMaj = xMajor ? ox : oy, oMin = xMajor ? oy : ox;
-                    const int kLo = max(eMaj >= 0 ? oMaj : -oMaj - (kTile - 1), 0);
-                    const int kHi = min(eMaj >= 0 ? oMaj + (kTile - 1) : -oMaj, amaj);
+                    const int steps = kTile / per, sub = tid - b * per;
+                    const int kBase = (eMaj >= 0 ? oMaj : -oMaj - (kTile - 1)) + sub * steps;
+                    const int kLo = max(kBase, 0);
+                    const int kHi = min(kBase + steps - 1, amaj);
                     if (kLo <= kHi) {
                         const int m2 = 2 * amaj, d2 = 2 * amin;
                         int minor = amaj ? minorAt(amin, amaj, kLo) : 0;
@@ -339,6 +352,11 @@ integ_touch_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs,
                             if (rem >= m2) { rem -= m2; ++minor; }
                         }
                     }
+                }
+                if (more && !fetched) {                     // next pair's beams: in flight during the extraction
+                    fetched = true;
+                    const int nbN = min(kSeg, nextA.w - nextA.z), bN = tid / lanesPerBeam(nbN);
+                    if (bN < nbN) eNext = __ldg(rel + nextB.x + nextA.z + bN);
                 }
                 __syncthreads();
                 if (pass == 0) {
@@ -437,8 +455,24 @@ struct Folder {
     __device__ __forceinline__ void touch(bool hit) {
         if (!saturated(hit)) { v = bayesUpdate(v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss); ++computed; }
     }
+    // Every iteration performs exactly one COMPUTED update per lane: a lane first drops, without
+    // iterating, the leading touches that cannot change a value sitting on a clamp, so a warp
+    // iterates max-over-lanes(computed updates) times, not max-over-lanes(queue length) times.
     __device__ __forceinline__ void drain() {
-        while (qn) { touch(q & 1ull); q >>= 1; --qn; }
+        while (qn) {
+            const bool atLo = missSat && v == 1e-3, atHi = hitSat && v == 1.0 - 1e-3;
+            if (atLo || atHi) {
+                const unsigned long long x = atLo ? q : ~q;            // first touch of the other type
+                const int n = min(qn, x ? __ffsll((long long)x) - 1 : 64);
+                q = n >= 64 ? 0ull : q >> n;
+                qn -= n;
+                if (!qn) break;
+            }
+            const bool hit = q & 1ull;
+            v = bayesUpdate(v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss);
+            ++computed;
+            q >>= 1; --qn;
+        }
     }
     __device__ __forceinline__ void run(bool hit, unsigned n) {
         for (unsigned j = 0; j < n; ++j) {
@@ -610,6 +644,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     auto tileSpan = [](int lo, int hi) { return (hi >> kTileShift) - (lo >> kTileShift) + 1; };
     // LGS_INTEG_TIMING=1 (diagnostic): CUDA-event time of every pass, summed over the call, to stderr.
     const bool timing = getenv("LGS_INTEG_TIMING") != nullptr;
+    const bool diag = timing && getenv("LGS_INTEG_DIAG") != nullptr;   // + per-cell update counts (slows the fold)
     std::vector<cudaEvent_t> evs;
     auto stamp = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
     // The fold pass runs on a second stream so that it overlaps the next chunk's touch passes
@@ -699,7 +734,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         cudaStream_t fs = overlap ? w.foldStream : c->stream;
         if (overlap) LGS_CUDA(c, cudaStreamWaitEvent(fs, w.evTouch[buf], 0));
         FoldArgs a{w.rel.p, w.tileInfo[buf].p, w.pairs[buf].p, w.records[buf].p, w.side[buf].p,
-                   timing ? w.counters.p : nullptr, pHit, pMiss, oddsHit, oddsMiss};
+                   diag ? w.counters.p : nullptr, pHit, pMiss, oddsHit, oddsMiss};
         integ_fold_kernel<<<(unsigned)nTiles, kTileCells, 0, fs>>>(a, g, x0, y0, tw);
         LGS_LAUNCH_CHECK(c);
         LGS_CUDA(c, cudaEventRecord(w.evFold[buf], fs));
