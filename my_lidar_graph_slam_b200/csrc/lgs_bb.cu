@@ -117,7 +117,7 @@ struct IdxChunk { int scan, begin, count; };
 __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
                                 const IdxChunk* __restrict__ chunks, const int* __restrict__ qlist,
                                 const double2* __restrict__ hits, double eps, int2* __restrict__ tab,
-                                BbFlag* __restrict__ flags, int* __restrict__ flagCount) {
+                                BbFlag* __restrict__ flags, int* __restrict__ flagCount, int speculative) {
     const IdxChunk ch = chunks[blockIdx.z];
     const BbScan& u = scans[ch.scan];
     const int i = blockIdx.y;
@@ -141,7 +141,7 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
         int2 v = make_int2(__double2int_rd(qx) - d.offX, __double2int_rd(qy) - d.offY);
         if (edge) {
             const int f = atomicAdd(flagCount, 1);
-            if (f < kFlagCapBB) {
+            if (f < kFlagCapBB && !speculative) {   // speculative runs are redone if any point is flagged
                 flags[f] = BbFlag{q, t, i};
                 v = make_int2(INT_MIN, f);      // sentinel: use the exact per-offset table f
             }
@@ -179,9 +179,12 @@ template <int U>                           // beams in flight per thread (two de
 __global__ void __launch_bounds__(128)
 bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                 const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
-                Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
-                Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
-                BbBest* __restrict__ best) {
+                Node* __restrict__ nodes, double* __restrict__ scores, int nMax,
+                const int* __restrict__ nDev, Node* __restrict__ next, int nextCap,
+                int* __restrict__ nextCount, BbBest* __restrict__ best) {
+    // nDev (speculative, sync-free runs): the level's node count lives on the device; the launch
+    // covers the pool capacity nMax and surplus threads leave here
+    const int nNodes = nDev ? min(__ldg(nDev), nMax) : nMax;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = k < nNodes;
     Node n;
@@ -278,10 +281,11 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
 __global__ void __launch_bounds__(128)
 bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                      const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
-                     Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
-                     Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
-                     BbBest* __restrict__ best) {
+                     Node* __restrict__ nodes, double* __restrict__ scores, int nMax,
+                     const int* __restrict__ nDev, Node* __restrict__ next, int nextCap,
+                     int* __restrict__ nextCount, BbBest* __restrict__ best) {
     constexpr int CH = 16, STAGE = 32 * CH;
+    const int nNodes = nDev ? min(__ldg(nDev), nMax) : nMax;
     __shared__ double sv[4][STAGE];
     const int wib = threadIdx.x >> 5;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -373,7 +377,8 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
 
 // ---- winner among the leaves: (score desc, rank asc) ---------------------------------------------
 __global__ void bb_leaf_rank_kernel(const Node* __restrict__ leaves, const double* __restrict__ scores,
-                                    int n, BbBest* __restrict__ best) {
+                                    int nMax, const int* __restrict__ nDev, BbBest* __restrict__ best) {
+    const int n = nDev ? min(__ldg(nDev), nMax) : nMax;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int q = leaves[k].q;
@@ -382,7 +387,8 @@ __global__ void bb_leaf_rank_kernel(const Node* __restrict__ leaves, const doubl
 }
 
 __global__ void bb_leaf_pick_kernel(const Node* __restrict__ leaves, const double* __restrict__ scores,
-                                    int n, BbBest* __restrict__ best) {
+                                    int nMax, const int* __restrict__ nDev, BbBest* __restrict__ best) {
+    const int n = nDev ? min(__ldg(nDev), nMax) : nMax;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int q = leaves[k].q;
@@ -483,6 +489,11 @@ struct lgs_bb_batch {
     long long nTab = 0;
     int totalRoots = 0;
     bool uploaded = false, ran = false, forceReplay = false;
+    // Speculative (sync-free) runs: launches are sized by the node pools' capacities and read the
+    // level counts on the device; lgs_bb_batch_results validates (no pool overflow, no near-edge
+    // flag) and otherwise repeats the run level-synchronously.  Hints = counts of the last run.
+    bool haveHints = false, pendingValidate = false;
+    long long hint[kMaxLevels] = {0};
     long long nodesPerLevel[kMaxLevels] = {0};
     long long gathers = 0;
     DevBuf<BbQuery> dQs;
@@ -694,8 +705,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     return LGS_OK;
 }
 
-int lgs_bb_batch_run(lgs_bb_batch* b) {
-    if (!b) return LGS_ERR_INVALID;
+static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     lgs_ctx* c = b->ctx;
     if (!b->uploaded) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_run before upload");
     const int H = b->H, n = b->nq;
@@ -715,7 +725,7 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
             const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
             bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dChunks.p + c0, b->dQlist.p,
                                                                      b->dHits.p, g_lgs_edge_eps, b->dTab.p,
-                                                                     b->dFlags.p, b->dCounters.p);
+                                                                     b->dFlags.p, b->dCounters.p, spec ? 1 : 0);
             LGS_LAUNCH_CHECK(c);
         }
         dim3 gridR((b->maxRoots + 127) / 128, n);
@@ -724,48 +734,101 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
         bb_init_best_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(b->dBest.p, n);
         LGS_LAUNCH_CHECK(c);
     }
-    // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
-    LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-    const int nFlag = b->hCounters.p[0];
-    std::fill(b->fixups.begin(), b->fixups.end(), 0);
     const int spanX = b->spanX, spanY = b->spanY;
-    if (nFlag > kFlagCapBB)
-        return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: %d near-edge points exceed the fix-up list", nFlag);
-    if (nFlag > 0) {
-        std::vector<BbFlag> fl(nFlag);
-        LGS_CUDA(c, cudaMemcpy(fl.data(), b->dFlags.p, nFlag * sizeof(BbFlag), cudaMemcpyDeviceToHost));
-        std::vector<int> exact((size_t)nFlag * (spanX + spanY), 0);
-        for (int k = 0; k < nFlag; ++k) {
-            const BbQuery& d = b->qs[fl[k].q];
-            const BbScan& u = b->us[d.scan];
-            const double stepX = d.res, stepY = d.res;
-            const double theta = u.st + static_cast<double>(fl[k].t - d.winT) * u.stepT;
-            const double a = theta + b->hAngles[u.beamBegin + fl[k].i];
-            const double cosT = std::cos(a), sinT = std::sin(a);
-            const double r = b->hRanges[u.beamBegin + fl[k].i];
-            int* e = exact.data() + (size_t)k * (spanX + spanY);
-            for (int o = 0; o < spanX; ++o) {
-                const double px = u.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
-                e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res)) - d.offX;
-            }
-            for (int o = 0; o < spanY; ++o) {
-                const double py = u.sy + static_cast<double>(o - d.winY) * stepY;
-                e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res)) - d.offY;
-            }
-            b->fixups[fl[k].q]++;
-        }
-        LGS_CUDA(c, b->dExact.reserve(exact.size()));
-        LGS_CUDA(c, cudaMemcpy(b->dExact.p, exact.data(), exact.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (spec) {
+        LGS_CUDA(c, b->dExact.reserve(1));      // no fix-up tables: a flagged point invalidates the run
     } else {
-        LGS_CUDA(c, b->dExact.reserve(1));
-    }
+        // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
+        LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+        const int nFlag = b->hCounters.p[0];
+        std::fill(b->fixups.begin(), b->fixups.end(), 0);
+        if (nFlag > kFlagCapBB)
+            return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: %d near-edge points exceed the fix-up list", nFlag);
+        if (nFlag > 0) {
+            std::vector<BbFlag> fl(nFlag);
+            LGS_CUDA(c, cudaMemcpy(fl.data(), b->dFlags.p, nFlag * sizeof(BbFlag), cudaMemcpyDeviceToHost));
+            std::vector<int> exact((size_t)nFlag * (spanX + spanY), 0);
+            for (int k = 0; k < nFlag; ++k) {
+                const BbQuery& d = b->qs[fl[k].q];
+                const BbScan& u = b->us[d.scan];
+                const double stepX = d.res, stepY = d.res;
+                const double theta = u.st + static_cast<double>(fl[k].t - d.winT) * u.stepT;
+                const double a = theta + b->hAngles[u.beamBegin + fl[k].i];
+                const double cosT = std::cos(a), sinT = std::sin(a);
+                const double r = b->hRanges[u.beamBegin + fl[k].i];
+                int* e = exact.data() + (size_t)k * (spanX + spanY);
+                for (int o = 0; o < spanX; ++o) {
+                    const double px = u.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
+                    e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res)) - d.offX;
+                }
+                for (int o = 0; o < spanY; ++o) {
+                    const double py = u.sy + static_cast<double>(o - d.winY) * stepY;
+                    e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res)) - d.offY;
+                }
+                b->fixups[fl[k].q]++;
+            }
+            LGS_CUDA(c, b->dExact.reserve(exact.size()));
+            LGS_CUDA(c, cudaMemcpy(b->dExact.p, exact.data(), exact.size() * sizeof(int), cudaMemcpyHostToDevice));
+        } else {
+            LGS_CUDA(c, b->dExact.reserve(1));
+        }
 
+    }
     // Level-synchronous expansion of the static-threshold superset.
     int warpBelow = kWarpPerNodeBelow;
     int deepBelow = kDeepUnrollBelow;
     if (const char* e = getenv("LGS_BB_WARP_BELOW")) warpBelow = atoi(e);     // tuning hooks
     if (const char* e = getenv("LGS_BB_DEEP_BELOW")) deepBelow = atoi(e);
+    if (spec) {
+        for (int h = H; h >= 0; --h) {
+            const long long expect = h == H ? b->totalRoots : b->hint[h];
+            if (h < H && b->dNodes[h].cap == 0) break;
+            const int nMax = h == H ? b->totalRoots : (int)b->dNodes[h].cap;
+            const int* nDev = h == H ? nullptr : b->dCounters.p + 2 + h;      // children of level h + 1
+            if (nMax == 0) break;
+            LGS_CUDA(c, b->dScores[h].reserve(nMax));
+            if (h > 0) {
+                const size_t want = (size_t)std::min<long long>(std::max<long long>(4LL * expect, 64), 1 << 16);
+                if (b->dNodes[h - 1].cap < want) LGS_CUDA(c, b->dNodes[h - 1].reserve(want));
+            }
+            Node* next = h > 0 ? b->dNodes[h - 1].p : nullptr;
+            const int nextCap = h > 0 ? (int)b->dNodes[h - 1].cap : 0;
+            int* nextCount = b->dCounters.p + 1 + h;
+            if (expect >= warpBelow && expect >= deepBelow)
+                bb_score_kernel<16><<<(nMax + 127) / 128, 128, 0, c->stream>>>(
+                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                    nMax, nDev, next, nextCap, nextCount, b->dBest.p);
+            else if (expect >= warpBelow)
+                bb_score_kernel<32><<<(nMax + 127) / 128, 128, 0, c->stream>>>(
+                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                    nMax, nDev, next, nextCap, nextCount, b->dBest.p);
+            else
+                bb_score_warp_kernel<<<(nMax + 3) / 4, 128, 0, c->stream>>>(
+                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                    nMax, nDev, next, nextCap, nextCount, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+        }
+        const int leafMax = H == 0 ? b->totalRoots : (int)b->dNodes[0].cap;
+        const int* leafDev = H == 0 ? nullptr : b->dCounters.p + 2;
+        if (leafMax > 0) {
+            bb_leaf_rank_kernel<<<(leafMax + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafMax, leafDev, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+            bb_leaf_pick_kernel<<<(leafMax + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafMax, leafDev, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+        }
+        LevelViews lvs;
+        for (int h = 0; h < kMaxLevels; ++h) lvs.v[h] = LevelView{b->dNodes[h].p, b->dScores[h].p};
+        bb_verify_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(b->dQs.p, n, H, lvs, b->dBest.p, b->dRes.p,
+                                                              b->forceReplay ? 1 : 0);
+        LGS_LAUNCH_CHECK(c);
+        bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(b->dQs.p, n, H, lvs, b->dBest.p, b->dRes.p);
+        LGS_LAUNCH_CHECK(c);
+        LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, (2 + kMaxLevels) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        b->pendingValidate = true;
+        b->ran = true;
+        return LGS_OK;
+    }
     int nNodes = b->totalRoots;
     for (int h = H; h >= 0; --h) {
         b->nodesPerLevel[h] = nNodes;
@@ -779,17 +842,17 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
             if (nNodes >= warpBelow && nNodes >= deepBelow)
                 bb_score_kernel<16><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
                     b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
+                    nNodes, nullptr, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
                     nextCount, b->dBest.p);
             else if (nNodes >= warpBelow)
                 bb_score_kernel<32><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
                     b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
+                    nNodes, nullptr, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
                     nextCount, b->dBest.p);
             else
                 bb_score_warp_kernel<<<(nNodes + 3) / 4, 128, 0, c->stream>>>(
                     b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nNodes, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
+                    nNodes, nullptr, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
                     nextCount, b->dBest.p);
             LGS_LAUNCH_CHECK(c);
             if (h == 0) break;
@@ -806,9 +869,9 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
     // Winner, verification, replay.
     const int nLeaves = (int)b->nodesPerLevel[0];
     if (nLeaves > 0) {
-        bb_leaf_rank_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, b->dBest.p);
+        bb_leaf_rank_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, nullptr, b->dBest.p);
         LGS_LAUNCH_CHECK(c);
-        bb_leaf_pick_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, b->dBest.p);
+        bb_leaf_pick_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, nullptr, b->dBest.p);
         LGS_LAUNCH_CHECK(c);
     }
     LevelViews lv;
@@ -819,14 +882,46 @@ int lgs_bb_batch_run(lgs_bb_batch* b) {
     bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p);
     LGS_LAUNCH_CHECK(c);
     b->ran = true;
+    b->pendingValidate = false;
+    for (int h = 0; h < kMaxLevels; ++h) b->hint[h] = b->nodesPerLevel[h];
+    b->haveHints = true;
     return LGS_OK;
 }
+
+// Wait for a speculative run and validate it; repeat level-synchronously if it cannot be trusted.
+static int bb_finish(lgs_bb_batch* b) {
+    lgs_ctx* c = b->ctx;
+    if (!b->pendingValidate) return LGS_OK;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    b->pendingValidate = false;
+    const int H = b->H;
+    bool ok = b->hCounters.p[0] == 0;                        // no near-edge point
+    for (int h = 1; h <= H && ok; ++h)
+        ok = (size_t)b->hCounters.p[1 + h] <= b->dNodes[h - 1].cap;   // no pool overflow
+    if (!ok) return bb_run_impl(b, false);
+    for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
+    b->nodesPerLevel[H] = b->totalRoots;
+    for (int h = 1; h <= H; ++h) b->nodesPerLevel[h - 1] = b->hCounters.p[1 + h];
+    for (int h = 0; h < kMaxLevels; ++h) b->hint[h] = b->nodesPerLevel[h];
+    std::fill(b->fixups.begin(), b->fixups.end(), 0);
+    return LGS_OK;
+}
+
+int lgs_bb_batch_run(lgs_bb_batch* b) {
+    if (!b) return LGS_ERR_INVALID;
+    // LGS_BB_SYNC=1 (diagnostic) forces the level-synchronous path
+    const bool spec = b->haveHints && !b->forceReplay && getenv("LGS_BB_SYNC") == nullptr;
+    return bb_run_impl(b, spec);
+}
+
 
 int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out) {
     if (!b || (!out && b->nq > 0)) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
     if (!b->ran) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_results before run");
     if (b->nq == 0) return LGS_OK;
+    { const int rc = bb_finish(b); if (rc != LGS_OK) return rc; }
     LGS_CUDA(c, cudaSetDevice(c->device));
     LGS_CUDA(c, cudaMemcpyAsync(b->hRes.p, b->dRes.p, b->nq * sizeof(BbResult), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -850,6 +945,7 @@ int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out) {
 
 int lgs_bb_batch_work(const lgs_bb_batch* b, long long* nodesPerLevel, int nLevels, long long* gathers) {
     if (!b) return LGS_ERR_INVALID;
+    { const int rc = bb_finish(const_cast<lgs_bb_batch*>(b)); if (rc != LGS_OK) return rc; }
     long long total = 0;
     for (int h = 0; h < kMaxLevels; ++h) {
         if (nodesPerLevel && h < nLevels) nodesPerLevel[h] = b->nodesPerLevel[h];

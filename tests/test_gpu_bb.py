@@ -171,3 +171,31 @@ def test_bb_empty_batch_and_bad_pyramid(ctx, submap):
     scan, init = _queries(submap, 1)[0]
     with pytest.raises(capi.LgsError, match="INVALID"):
         batch.upload(capi.Scans([submap["angles"]], [scan], [init]), [shallow], 0.6)
+
+
+def test_speculative_sync_free_runs_match_the_level_synchronous_run(ctx, submap, monkeypatch):
+    """The first run of a batch object is level-synchronous; later runs launch every level without
+    waiting for its node count (pool capacities + device-side counts) and are validated afterwards.
+    Both must give identical results -- also when the pools sized by a small batch overflow."""
+    qs = _queries(submap, 6, seed=21)
+    mk = lambda sub: capi.Scans([submap["angles"]] * len(sub), [s for s, _ in sub], [p for _, p in sub],
+                                range_min=0.02, range_max=30.0)
+    key = lambda o: (o.found, o.ix, o.iy, o.it, o.score)
+    monkeypatch.setenv("LGS_BB_SYNC", "1")
+    ref_batch = capi.BbBatch(ctx, **DEF)
+    ref_batch.upload(mk(qs), [submap["pyr"]] * len(qs), 0.5)
+    ref_batch.run()
+    want = [key(o) for o in ref_batch.results()]
+    want_levels = ref_batch.work()[0]
+    monkeypatch.delenv("LGS_BB_SYNC")
+    batch = capi.BbBatch(ctx, **DEF)
+    batch.upload(mk(qs[:1]), [submap["pyr"]], 0.5)        # small batch: sizes the pools, leaves hints
+    batch.run()
+    assert [key(o) for o in batch.results()] == want[:1]
+    batch.upload(mk(qs), [submap["pyr"]] * len(qs), 0.5)   # 6x the work: speculative run overflows -> redone
+    batch.run()
+    assert [key(o) for o in batch.results()] == want
+    for _ in range(3):                                    # steady state: speculative runs validate
+        batch.run()
+        assert [key(o) for o in batch.results()] == want
+        assert batch.work()[0] == want_levels
