@@ -220,7 +220,7 @@ def c4_submap_scans(world, angles, submap_id, n_scans, anchor):
     return traj, [synth.make_scan(world, p, angles, rng) for p in traj]
 
 
-def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps, steps, with_cpu):
+def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps, steps, with_cpu, n_batched_scans=8):
     """C4: one 1081-beam scan against n_submaps submaps, 7 pyramid levels, threshold 0.6.
     Submap i lives on rank i mod N; results are all-gathered (32-byte records)."""
     from my_lidar_graph_slam_b200 import capi, sharding
@@ -262,8 +262,8 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
     def step():
         batch.upload_pairs(scans, pair_scan, pyramids, 0.6)
         batch.run()
-        res = batch.results()
-        return sharding.all_gather_records(sharding.pack(res, mine), n_submaps, rank, world_size, dev)
+        res = batch.results_array()
+        return sharding.all_gather_records(sharding.pack_array(res, mine), n_submaps, rank, world_size, dev)
 
     for _ in range(3):
         rec = step()
@@ -295,6 +295,49 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
            "pyramid_cells_levels_per_s": cells * 7 / (pyr_ms * 1e-3) if pyr_ms > 0 else None,
            "submap_build_s_rank0": build_s, "n_gpus": world_size,
            "scaling": "strong (fixed 500 submaps, round-robin over ranks, all-gather of records)"}
+    # Throughput form of the same workload: a batch of Q query scans x all submaps per step (the
+    # reference's Detect() takes a vector of queries, loop_detector.hpp:92-107).  One scan x 500
+    # submaps is ~1 ms of device time, too little to amortise launch latency once it is split 8 ways.
+    Q = n_batched_scans
+    if Q > 1:
+        qscans, qinits = [], []
+        for k in range(Q):
+            t = anchor + np.array([0.3 * np.cos(k), 0.3 * np.sin(k), 0.04 * k])
+            qscans.append(synth.make_scan(world, t, angles, qrng))
+            qinits.append(t + np.array([0.3, -0.2, 0.08]))
+        scansQ = capi.Scans([angles] * Q, qscans, qinits, range_min=0.02, range_max=30.0)
+        pair_scanQ = np.repeat(np.arange(Q, dtype=np.int32), nq)
+        pyrQ = pyramids * Q
+        idsQ = np.concatenate([k * n_submaps + mine for k in range(Q)]) if nq else np.zeros(0, dtype=np.int64)
+        batchQ = capi.BbBatch(ctx, **BB)
+
+        def stepQ():
+            batchQ.upload_pairs(scansQ, pair_scanQ, pyrQ, 0.6)
+            batchQ.run()
+            res = batchQ.results_array()
+            return sharding.all_gather_variable(sharding.pack_array(res, idsQ), Q * n_submaps, world_size, dev)
+
+        for _ in range(2):
+            recQ = stepQ()
+        ctx.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            recQ = stepQ()
+        ctx.synchronize()
+        eQ = max_over_ranks(time.perf_counter() - t0)
+        batchQ.upload_pairs(scansQ, pair_scanQ, pyrQ, 0.6)
+        barrier()
+        ctx.timer_start()
+        for _ in range(steps):
+            batchQ.run()
+        dQ = max_over_ranks(ctx.timer_stop())
+        out["batched"] = {"workload": f"{Q} query scans x {n_submaps} submaps per step",
+                          "loop_queries_per_s": Q * n_submaps * steps / (dQ * 1e-3),
+                          "loop_queries_per_s_e2e": Q * n_submaps * steps / eQ,
+                          "ms_per_step": dQ / steps, "ms_per_step_e2e": 1e3 * eQ / steps,
+                          "loops_found": int((recQ["found"] != 0).sum())}
+        batchQ.close()
     if with_cpu and rank == 0:
         try:
             from oracle import refapi as R

@@ -40,6 +40,14 @@ class MatchResult(C.Structure):
                 ("exact_replay", C.c_int), ("reserved", C.c_int)]
 
 
+MATCH_DTYPE = np.dtype([("found", np.int32), ("ix", np.int32), ("iy", np.int32), ("it", np.int32),
+                        ("win_x", np.int32), ("win_y", np.int32), ("win_t", np.int32), ("n_fixups", np.int32),
+                        ("step_x", np.float64), ("step_y", np.float64), ("step_t", np.float64),
+                        ("score", np.float64), ("n_scored", np.int64), ("exact_replay", np.int32),
+                        ("reserved", np.int32)])
+assert MATCH_DTYPE.itemsize == C.sizeof(MatchResult)
+
+
 class BbParams(C.Structure):
     _fields_ = [("node_height_max", C.c_int), ("range_x", C.c_double), ("range_y", C.c_double),
                 ("range_theta", C.c_double), ("scan_range_max", C.c_double),
@@ -382,8 +390,10 @@ class BbBatch:
         n = len(pyramids)
         self._pairs = np.ascontiguousarray(pair_scan, dtype=np.int32)
         assert len(self._pairs) == n
-        self._pyr = (vp * max(n, 1))(*[p.h for p in pyramids])
-        self._keep = (scans, list(pyramids))
+        if getattr(self, "_pyr_src", None) is not pyramids:         # same list object: reuse the handle array
+            self._pyr = (vp * max(n, 1))(*[p.h for p in pyramids])
+            self._pyr_src = pyramids
+        self._keep = (scans, pyramids)
         thr = None
         if norm_threshold is not None:
             self._thr = np.ascontiguousarray(np.broadcast_to(
@@ -400,6 +410,12 @@ class BbBatch:
         out = (MatchResult * max(self.n, 1))()
         self.ctx.check(lib().lgs_bb_batch_results(self.h, out))
         return list(out)[:self.n]
+
+    def results_array(self) -> np.ndarray:
+        """Results as a numpy structured array with MatchResult's fields (no per-record objects)."""
+        out = np.zeros(max(self.n, 1), dtype=MATCH_DTYPE)
+        self.ctx.check(lib().lgs_bb_batch_results(self.h, out.ctypes.data_as(C.POINTER(MatchResult))))
+        return out[:self.n]
 
     def work(self):
         lv = (C.c_longlong * 21)()

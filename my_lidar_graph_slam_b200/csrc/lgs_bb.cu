@@ -117,7 +117,7 @@ struct IdxChunk { int scan, begin, count; };
 __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
                                 const IdxChunk* __restrict__ chunks, const int* __restrict__ qlist,
                                 const double2* __restrict__ hits, double eps, int2* __restrict__ tab,
-                                BbFlag* __restrict__ flags, int* __restrict__ flagCount, int speculative) {
+                                BbFlag* __restrict__ flags, int* __restrict__ flagCount) {
     const IdxChunk ch = chunks[blockIdx.z];
     const BbScan& u = scans[ch.scan];
     const int i = blockIdx.y;
@@ -141,7 +141,7 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
         int2 v = make_int2(__double2int_rd(qx) - d.offX, __double2int_rd(qy) - d.offY);
         if (edge) {
             const int f = atomicAdd(flagCount, 1);
-            if (f < kFlagCapBB && !speculative) {   // speculative runs are redone if any point is flagged
+            if (f < kFlagCapBB) {
                 flags[f] = BbFlag{q, t, i};
                 v = make_int2(INT_MIN, f);      // sentinel: use the exact per-offset table f
             }
@@ -490,8 +490,8 @@ struct lgs_bb_batch {
     int totalRoots = 0;
     bool uploaded = false, ran = false, forceReplay = false;
     // Speculative (sync-free) runs: launches are sized by the node pools' capacities and read the
-    // level counts on the device; lgs_bb_batch_results validates (no pool overflow, no near-edge
-    // flag) and otherwise repeats the run level-synchronously.  Hints = counts of the last run.
+    // level counts on the device; lgs_bb_batch_results validates (no pool overflow) and otherwise
+    // repeats the run level-synchronously.  Hints = counts of the last run.
     bool haveHints = false, pendingValidate = false;
     long long hint[kMaxLevels] = {0};
     long long nodesPerLevel[kMaxLevels] = {0};
@@ -725,7 +725,7 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
             const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
             bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dChunks.p + c0, b->dQlist.p,
                                                                      b->dHits.p, g_lgs_edge_eps, b->dTab.p,
-                                                                     b->dFlags.p, b->dCounters.p, spec ? 1 : 0);
+                                                                     b->dFlags.p, b->dCounters.p);
             LGS_LAUNCH_CHECK(c);
         }
         dim3 gridR((b->maxRoots + 127) / 128, n);
@@ -735,9 +735,7 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
         LGS_LAUNCH_CHECK(c);
     }
     const int spanX = b->spanX, spanY = b->spanY;
-    if (spec) {
-        LGS_CUDA(c, b->dExact.reserve(1));      // no fix-up tables: a flagged point invalidates the run
-    } else {
+    {   // the one host round trip a speculative run keeps (the flag count is almost always 0)
         // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
         LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LGS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -896,7 +894,7 @@ static int bb_finish(lgs_bb_batch* b) {
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
     b->pendingValidate = false;
     const int H = b->H;
-    bool ok = b->hCounters.p[0] == 0;                        // no near-edge point
+    bool ok = true;
     for (int h = 1; h <= H && ok; ++h)
         ok = (size_t)b->hCounters.p[1 + h] <= b->dNodes[h - 1].cap;   // no pool overflow
     if (!ok) return bb_run_impl(b, false);
@@ -904,7 +902,6 @@ static int bb_finish(lgs_bb_batch* b) {
     b->nodesPerLevel[H] = b->totalRoots;
     for (int h = 1; h <= H; ++h) b->nodesPerLevel[h - 1] = b->hCounters.p[1 + h];
     for (int h = 0; h < kMaxLevels; ++h) b->hint[h] = b->nodesPerLevel[h];
-    std::fill(b->fixups.begin(), b->fixups.end(), 0);
     return LGS_OK;
 }
 

@@ -27,6 +27,15 @@ def pack(results, global_ids) -> np.ndarray:
     return rec
 
 
+def pack_array(results: np.ndarray, global_ids) -> np.ndarray:
+    """pack() for a structured result array (capi.BbBatch.results_array), vectorised."""
+    rec = np.zeros(len(global_ids), dtype=RECORD)
+    for f in ("found", "ix", "iy", "it", "score"):
+        rec[f] = results[f]
+    rec["submap"] = global_ids
+    return rec
+
+
 def all_gather_records(local: np.ndarray, n_items: int, rank: int, world: int, device=None):
     """All-gather per-rank record arrays -> one array of n_items records in global order."""
     if world == 1:
