@@ -14,6 +14,7 @@
 #include <memory>
 #include <string>
 
+#include "lgs_adapters/grid_map_builder_cuda.hpp"
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
 #include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
 
@@ -72,6 +73,30 @@ std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorBranchBoundCuda(
     return std::make_shared<Mapping::LoopDetectorBranchBoundCuda>(
         usableRangeMin, usableRangeMax, pCostFunc, nodeHeightMax, rangeX, rangeY, rangeTheta,
         scanRangeMax, scoreThreshold, device);
+}
+
+/* "GridMapBuilder": { ..., "Backend": "Cuda", "Device": 0 } -- the other keys are the ones
+ * CreateGridMapBuilder reads (slam_launcher.cpp:711-737, launcher_settings_default.json:175-185).
+ * GridMapBuilder is a concrete class, so the caller holds the result by its own type (or behind
+ * the two-line interface sketched in INTEGRATION.md). */
+template <typename Ptree>
+std::shared_ptr<Mapping::GridMapBuilderCuda> CreateGridMapBuilderCuda(
+    const Ptree& jsonSettings, const std::string& configGroup)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    /* same keys and defaults as slam_launcher.cpp:718-729 */
+    const double mapResolution = config.get("Map.Resolution", 0.05);
+    const int patchSize = config.get("Map.PatchSize", 64);
+    const int numOfLatestScans = config.get("Map.NumOfScansForLatestMap", 5);
+    const double travelDistThreshold = config.get("Map.TravelDistThresholdForLocalMap", 20.0);
+    const double usableRangeMin = config.get("UsableRangeMin", 0.01);
+    const double usableRangeMax = config.get("UsableRangeMax", 50.0);
+    const double probHit = config.get("ProbabilityHit", 0.9);
+    const double probMiss = config.get("ProbabilityMiss", 0.1);
+    const int device = config.get("Device", 0);
+    return std::make_shared<Mapping::GridMapBuilderCuda>(
+        mapResolution, patchSize, numOfLatestScans, travelDistThreshold, usableRangeMin,
+        usableRangeMax, probHit, probMiss, device);
 }
 
 } /* namespace LgsB200 */

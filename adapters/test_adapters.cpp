@@ -3,11 +3,13 @@
  * of each LoopDetectionResult (poses, cost, covariance), compared as bit patterns.
  * Built here against /root/reference (adapters/Makefile), run on the GPU box by
  * tests/test_gpu_adapters.py.  Exit code 0 = all identical. */
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <random>
 
+#include "lgs_adapters/grid_map_builder_cuda.hpp"
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
 #include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
 #include "my_lidar_graph_slam/mapping/cost_function_greedy_endpoint.hpp"
@@ -85,6 +87,42 @@ bool SameMat(const Eigen::Matrix3d& a, const Eigen::Matrix3d& b) {
     return true;
 }
 
+/* Geometry, patch allocation and every cell value, as bit patterns */
+bool SameMap(const GridMapType& a, const GridMapType& b) {
+    if (a.NumOfGridCellsX() != b.NumOfGridCellsX() || a.NumOfGridCellsY() != b.NumOfGridCellsY() ||
+        a.NumOfPatchesX() != b.NumOfPatchesX() || a.NumOfPatchesY() != b.NumOfPatchesY() ||
+        !SameBits(a.MinPos().mX, b.MinPos().mX) || !SameBits(a.MinPos().mY, b.MinPos().mY))
+        return false;
+    const int patch = a.PatchSize();
+    for (int py = 0; py < a.NumOfPatchesY(); ++py)
+        for (int px = 0; px < a.NumOfPatchesX(); ++px) {
+            if (a.PatchIsAllocated(px, py) != b.PatchIsAllocated(px, py)) return false;
+            if (!a.PatchIsAllocated(px, py)) continue;
+            const auto* ca = a.PatchAt(px, py).Data();
+            const auto* cb = b.PatchAt(px, py).Data();
+            for (int k = 0; k < patch * patch; ++k)
+                if (!SameBits(ca[k].Value(), cb[k].Value())) return false;
+        }
+    return true;
+}
+
+template <typename A, typename B>
+bool SameBuilders(const A& a, const B& b) {
+    if (a.LocalMaps().size() != b.LocalMaps().size() || !SameBits(a.AccumTravelDist(), b.AccumTravelDist()) ||
+        a.LatestScanIdxMin() != b.LatestScanIdxMin() || a.LatestScanIdxMax() != b.LatestScanIdxMax() ||
+        !SameMap(a.LatestMap(), b.LatestMap()))
+        return false;
+    for (std::size_t m = 0; m < a.LocalMaps().size(); ++m) {
+        const LocalMapInfo& x = a.LocalMaps()[m];
+        const LocalMapInfo& y = b.LocalMaps()[m];
+        if (x.mIdx != y.mIdx || x.mPoseGraphNodeIdxMin != y.mPoseGraphNodeIdxMin ||
+            x.mPoseGraphNodeIdxMax != y.mPoseGraphNodeIdxMax || x.mFinished != y.mFinished ||
+            x.mPrecomputed != y.mPrecomputed || !SameMap(x.mMap, y.mMap))
+            return false;
+    }
+    return true;
+}
+
 }  // namespace
 
 int main() {
@@ -92,19 +130,79 @@ int main() {
     const World world(7);
     auto poseGraph = std::make_shared<PoseGraph>();
     GridMapBuilder builder(0.05, 64, 10, 6.0, 0.01, 20.0, 0.6, 0.45);   /* new local map every 6 m */
+    GridMapBuilderCuda builderCuda(0.05, 64, 10, 6.0, 0.01, 20.0, 0.6, 0.45, 0);
+    int failures = 0;
     /* drive around inside one room row, through doors where they line up */
     std::vector<RobotPose2D<double>> path;
     for (int k = 0; k < 60; ++k)
         path.emplace_back(-9.8 + 0.33 * k * std::cos(0.02 * k), -9.9 + 0.9 * std::sin(0.21 * k), 0.03 * k);
-    for (const auto& p : path) {
-        poseGraph->AppendNode(p, MakeScan(world, p, 541, g));
-        builder.AppendScan(poseGraph);
+    {   /* ---- grid map builder: every frame, then a loop closure, then the global map ---- */
+        int frame = 0, bad = 0;
+        double msRef = 0.0, msCuda = 0.0, worstCuda = 0.0;
+        int worstFrame = -1;
+        for (const auto& p : path) {
+            poseGraph->AppendNode(p, MakeScan(world, p, 541, g));
+            const auto t0 = std::chrono::steady_clock::now();
+            const bool c1 = builder.AppendScan(poseGraph);
+            const auto t1 = std::chrono::steady_clock::now();
+            const bool c2 = builderCuda.AppendScan(poseGraph);
+            const auto t2 = std::chrono::steady_clock::now();
+            if (frame >= 5) {
+                const double dc = std::chrono::duration<double, std::milli>(t2 - t1).count();
+                msRef += std::chrono::duration<double, std::milli>(t1 - t0).count();
+                msCuda += dc;
+                if (dc > worstCuda) { worstCuda = dc; worstFrame = frame; }
+            }
+            if (c1 != c2 || !SameBuilders(builder, builderCuda)) {
+                if (bad++ < 5) std::printf("builder frame %d: MISMATCH\n", frame);
+            }
+            ++frame;
+        }
+        std::printf("builder: %d frames, %zu local maps, %lld cell updates on the device %s\n", frame,
+                    builderCuda.LocalMaps().size(), builderCuda.NumOfCellUpdates(), bad ? "MISMATCH" : "IDENTICAL");
+        failures += bad != 0;
+        std::printf("builder AppendScan per frame (541 beams, after 5 warm-up frames): reference %.2f ms, cuda %.2f ms "
+                    "(worst cuda frame %d: %.2f ms, mean without it %.2f ms)\n",
+                    msRef / (frame - 5), msCuda / (frame - 5), worstFrame, worstCuda,
+                    (msCuda - worstCuda) / (frame - 6));
+        /* pretend a loop closure moved the nodes (smooth drift correction), rebuild everything */
+        auto corrected = std::make_shared<PoseGraph>(*poseGraph);
+        for (int i = 0; i < static_cast<int>(corrected->Nodes().size()); ++i) {
+            RobotPose2D<double>& q = corrected->NodeAt(i).Pose();
+            q.mX += 0.004 * i; q.mY -= 0.003 * i; q.mTheta += 0.0005 * i;
+        }
+        GridMapBuilder refCopy(builder);
+        refCopy.LocalMapAt(0).mPrecomputed = true;
+        builderCuda.LocalMapAt(0).mPrecomputed = true;
+        (void)builderCuda.ConstructGlobalMap(poseGraph);   /* grows the device workspace once (not timed) */
+        const auto a0 = std::chrono::steady_clock::now();
+        refCopy.AfterLoopClosure(corrected);
+        const auto a1 = std::chrono::steady_clock::now();
+        builderCuda.AfterLoopClosure(corrected);
+        const auto a2 = std::chrono::steady_clock::now();
+        bool ok = SameBuilders(refCopy, builderCuda);
+        std::printf("builder AfterLoopClosure (%d nodes): reference %.1f ms, cuda %.1f ms %s\n", frame,
+                    std::chrono::duration<double, std::milli>(a1 - a0).count(),
+                    std::chrono::duration<double, std::milli>(a2 - a1).count(), ok ? "IDENTICAL" : "MISMATCH");
+        failures += !ok;
+        /* keep mapping after the closure: the device mirror of the current local map must follow */
+        for (int k = 0; k < 4; ++k) {
+            const RobotPose2D<double> p(path.back().mX + 0.3 * (k + 1), path.back().mY + 0.1 * k, path.back().mTheta);
+            corrected->AppendNode(p, MakeScan(world, p, 541, g));
+            refCopy.AppendScan(corrected);
+            builderCuda.AppendScan(corrected);
+        }
+        ok = SameBuilders(refCopy, builderCuda);
+        std::printf("builder frames after the closure: %s\n", ok ? "IDENTICAL" : "MISMATCH");
+        failures += !ok;
+        ok = SameMap(refCopy.ConstructGlobalMap(corrected), builderCuda.ConstructGlobalMap(corrected));
+        std::printf("builder ConstructGlobalMap: %s\n", ok ? "IDENTICAL" : "MISMATCH");
+        failures += !ok;
     }
     std::printf("local maps: %zu, latest map %dx%d\n", builder.LocalMaps().size(),
                 builder.LatestMap().NumOfGridCellsX(), builder.LatestMap().NumOfGridCellsY());
     /* cost function exactly as slam_launcher.cpp:60-72 builds it from the default settings */
     auto cost = std::make_shared<CostGreedyEndpoint>(0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0);
-    int failures = 0;
 
     /* ---- front-end matcher ---- */
     {

@@ -126,10 +126,11 @@ int lgs_grid_create(lgs_ctx* c, int nx, int ny, double min_x, double min_y, doub
     g->pitch = (int)pitch; g->rows = (int)rows;
     g->min_x = min_x; g->min_y = min_y; g->res = res;
     const size_t bytes = (size_t)pitch * rows * sizeof(double);
-    cudaError_t e = cudaMalloc(&g->d, bytes);
+    // stream-ordered pool allocation: lgs_grid_resize can then swap buffers without a device sync
+    cudaError_t e = cudaMallocAsync(&g->d, std::max<size_t>(bytes, 8), c->stream);
     if (e != cudaSuccess) {
         delete g;
-        return lgs_fail(c, LGS_ERR_NOMEM, "grid_create: cudaMalloc(%zu) -> %s", bytes,
+        return lgs_fail(c, LGS_ERR_NOMEM, "grid_create: cudaMallocAsync(%zu) -> %s", bytes,
                         cudaGetErrorString(e));
     }
     e = cudaMemsetAsync(g->d, 0, bytes, c->stream);
@@ -144,8 +145,10 @@ int lgs_grid_create(lgs_ctx* c, int nx, int ny, double min_x, double min_y, doub
 int lgs_grid_destroy(lgs_grid* g) {
     if (!g) return LGS_OK;
     cudaSetDevice(g->ctx->device);
-    cudaStreamSynchronize(g->ctx->stream);
-    if (g->d && g->owns) cudaFree(g->d);
+    if (g->d && g->owns) {
+        cudaDeviceSynchronize();            // readers on other contexts' streams (like cudaFree did)
+        cudaFreeAsync(g->d, g->ctx->stream);
+    }
     delete g;
     return LGS_OK;
 }

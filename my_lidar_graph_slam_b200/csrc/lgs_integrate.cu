@@ -770,8 +770,10 @@ int lgs_grid_resize(lgs_grid* g, int nx, int ny, double minX, double minY, int s
     LGS_CUDA(c, cudaSetDevice(c->device));
     double* nd = nullptr;
     const size_t bytes = (size_t)pitch * rows * sizeof(double);
-    cudaError_t e = cudaMalloc(&nd, bytes);
-    if (e != cudaSuccess) return lgs_fail(c, LGS_ERR_NOMEM, "grid_resize: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    // stream-ordered: the new buffer comes from the pool and the old one returns to it after the
+    // copy, without synchronising the device (a map that grows every few frames pays microseconds)
+    cudaError_t e = cudaMallocAsync(&nd, std::max<size_t>(bytes, 8), c->stream);
+    if (e != cudaSuccess) return lgs_fail(c, LGS_ERR_NOMEM, "grid_resize: cudaMallocAsync(%zu) -> %s", bytes, cudaGetErrorString(e));
     LGS_CUDA(c, cudaMemsetAsync(nd, 0, bytes, c->stream));
     if (nx > 0 && ny > 0) {
         dim3 gridDim((nx + 255) / 256, ny);
@@ -780,8 +782,7 @@ int lgs_grid_resize(lgs_grid* g, int nx, int ny, double minX, double minY, int s
                                                                nx, ny, (int)pitch, shiftX, shiftY);
         LGS_LAUNCH_CHECK(c);
     }
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(g->d);
+    LGS_CUDA(c, cudaFreeAsync(g->d, c->stream));
     g->d = nd; g->nx = nx; g->ny = ny; g->pitch = (int)pitch; g->rows = (int)rows;
     g->min_x = minX; g->min_y = minY;
     return LGS_OK;
