@@ -159,3 +159,33 @@ def test_exhausted_side_buffer_falls_back_to_exact_beam_tests(ctx, monkeypatch):
     assert maps[0][1] > 0 and maps[1][1] == 0
     assert np.array_equal(_bits(maps[0][0]), _bits(ref.dense()))
     assert np.array_equal(_bits(maps[1][0]), _bits(ref.dense()))
+
+
+def test_many_chunks_overlapped_fold_matches_reference(ctx):
+    """150 scans in ONE call = three 64-scan chunks whose fold passes run on a second stream under the
+    next chunk's mark/touch passes (double-buffered records): every cell must still be bit-identical,
+    and so must a second call that re-integrates on top of the first (no stale workspace state)."""
+    from oracle import backend
+    R = backend()
+    world = synth.RoomsWorld(40.0, 5.0, seed=21)
+    angles = synth.beam_angles(721, 240.0)
+    traj = synth.trajectory(world, 150, step=0.12, seed=21)
+    noise = np.random.default_rng(22)
+    geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
+    hits = []
+    for p in traj:
+        h, bbox = capi.scan_hit_points(p, angles, synth.make_scan(world, p, angles, noise), 0.02, 20.0)
+        geo, _, _, _ = capi.geometry_expand(geo, bbox)
+        hits.append(h)
+    ref = R.RefMap.from_dense(np.zeros((geo.ny, geo.nx)), geo.min_x, geo.min_y)
+    grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
+    for rep in range(2):
+        want = sum(R.map_integrate_hits(ref, p[:2], h) for p, h in zip(traj, hits))
+        assert capi.integrate_scans(ctx, grid, traj[:, :2], hits) == want
+        assert np.array_equal(_bits(grid.download()), _bits(ref.dense())), f"pass {rep}"
+    # a call with empty scans in the middle and a one-beam scan
+    mixed = [hits[0], np.zeros((0, 2)), hits[1][:1], hits[2]]
+    pos = [traj[0, :2], traj[1, :2], traj[1, :2], traj[2, :2]]
+    want = sum(R.map_integrate_hits(ref, p, h) for p, h in zip(pos, mixed) if len(h))
+    assert capi.integrate_scans(ctx, grid, np.asarray(pos), mixed) == want
+    assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))

@@ -73,3 +73,50 @@ def test_precompute_properties_at_full_size(ctx):
             y0, x0 = min(y, n - w), min(x, n - w)
             assert cur[y, x] == dense[y0:y0 + w, x0:x0 + w].max()
         prev = cur
+
+
+def test_pyramid_apron_is_zero_when_the_pool_hands_back_dirty_memory(ctx):
+    """Pyramid slabs come from the stream-ordered pool and only their apron is cleared.  Dirty the
+    pool with an all-ones pyramid of the same size, free it, build the real one and match a scan
+    whose window hangs over the map edge: stale apron cells would change the scores."""
+    from my_lidar_graph_slam_b200 import synth
+    from oracle import backend
+    R = backend()
+    world = synth.World(16.0, 16.0, 5, seed=4)
+    angles = synth.beam_angles(361, 180.0)
+    traj = synth.trajectory(world, 8, step=0.2, seed=4)
+    noise = np.random.default_rng(5)
+    builder = R.RefBuilder()
+    for p in traj[:6]:
+        builder.append_scan(p, angles, synth.make_scan(world, p, angles, noise))
+    refmap = builder.latest_map()
+    nx, ny, mx, my, res = refmap.geometry()
+    ones = capi.Grid.from_dense(ctx, np.full((ny, nx), 0.999), mx, my, res, apron=2)
+    for _ in range(3):
+        capi.Pyramid(ctx, ones, 6).close()
+    grid = capi.Grid.from_dense(ctx, refmap.dense(), mx, my, res, apron=2)
+    pyr = capi.Pyramid(ctx, grid, 6)
+    refpyr = refmap.pyramid(6)
+    for lvl in range(7):
+        assert np.array_equal(pyr.download(lvl).view(np.int64), refpyr[lvl].dense().view(np.int64))
+    bb = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=0.4, scan_range_max=20.0,
+              score_range_min=0.01, score_range_max=20.0)
+    # the latest map is resized tightly around its scans, so node windows (up to +107 cells) and the
+    # beams that end on the outer walls read beyond the map's upper / right edge all the time
+    found = 0
+    for k, shift in enumerate(([-0.5, -0.4, 0.05], [0.6, 0.3, -0.08], [0.2, -0.7, 0.1])):
+        scan = synth.make_scan(world, traj[6], angles, np.random.default_rng(50 + k))
+        init = traj[6] + np.array(shift)
+        batch = capi.BbBatch(ctx, **bb)
+        batch.upload(capi.Scans([angles], [scan], [init], range_min=0.02, range_max=30.0), [pyr], 0.2)
+        batch.run()
+        (out,) = batch.results()
+        ref = R.bb_match(refmap, angles, scan, init, pyramid=refpyr, thr=0.2, height_max=6, range_x=2.0,
+                         range_y=2.0, range_theta=0.4, scan_range_max=20.0, score_range_min=0.01,
+                         score_range_max=20.0)
+        assert (out.found, out.ix, out.iy, out.it) == (ref.found, ref.ix, ref.iy, ref.it)
+        if ref.found:
+            assert out.score == ref.score
+            found += 1
+        batch.close()
+    assert found >= 2
