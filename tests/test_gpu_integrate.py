@@ -189,3 +189,29 @@ def test_many_chunks_overlapped_fold_matches_reference(ctx):
     want = sum(R.map_integrate_hits(ref, p, h) for p, h in zip(pos, mixed) if len(h))
     assert capi.integrate_scans(ctx, grid, np.asarray(pos), mixed) == want
     assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
+
+
+def test_very_long_rays_use_the_integer_division_path_and_split_chunks(ctx):
+    """Rays longer than 2047 cells leave the float-reciprocal fast path of the Bresenham closed form,
+    and their huge tile bounding boxes make the record budget split the call into small chunks."""
+    from oracle import backend
+    R = backend()
+    rng = np.random.default_rng(31)
+    nx, ny = 4480, 448                                   # 224 m x 22.4 m at 0.05 m
+    ref = R.RefMap.from_dense(np.zeros((ny, nx)), 0.0, 0.0)
+    grid = capi.Grid(ctx, nx, ny, 0.0, 0.0, 0.05, apron=1)
+    sensors, hits = [], []
+    for s in range(9):
+        sensor = np.array([rng.uniform(1.0, 12.0), rng.uniform(8.0, 14.0)])
+        n = 160
+        ang = np.sort(rng.uniform(-0.04, 0.04, n))
+        rad = np.where(rng.random(n) < 0.7, rng.uniform(110.0, 205.0, n), rng.uniform(0.3, 40.0, n))
+        h = sensor[None, :] + rad[:, None] * np.stack([np.cos(ang), np.sin(ang)], 1)
+        h[:, 0] = np.clip(h[:, 0], 0.01, nx * 0.05 - 0.01)
+        h[:, 1] = np.clip(h[:, 1], 0.01, ny * 0.05 - 0.01)
+        sensors.append(sensor)
+        hits.append(np.ascontiguousarray(h))
+    want = sum(R.map_integrate_hits(ref, p, h) for p, h in zip(sensors, hits))
+    assert capi.integrate_scans(ctx, grid, np.asarray(sensors), hits) == want
+    assert want > 9 * 160 * 1500
+    assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
