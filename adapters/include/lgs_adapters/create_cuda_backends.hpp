@@ -16,6 +16,7 @@
 
 #include "lgs_adapters/grid_map_builder_cuda.hpp"
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
+#include "lgs_adapters/loop_detector_real_time_correlative_cuda.hpp"
 #include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
 
 namespace LgsB200 {
@@ -73,6 +74,21 @@ std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorBranchBoundCuda(
     return std::make_shared<Mapping::LoopDetectorBranchBoundCuda>(
         usableRangeMin, usableRangeMax, pCostFunc, nodeHeightMax, rangeX, rangeY, rangeTheta,
         scanRangeMax, scoreThreshold, device);
+}
+
+/* "LoopDetectorType": "RealTimeCorrelativeCuda" -- the detector group names its matcher group
+ * exactly like CreateLoopDetectorRealTimeCorrelative does (slam_launcher.cpp:418-446); the matcher is
+ * created by CreateScanMatcherRealTimeCorrelativeCuda above */
+template <typename Ptree, typename CostFactory>
+std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorRealTimeCorrelativeCuda(
+    const Ptree& jsonSettings, const std::string& configGroup, CostFactory createCostFunction)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    const double scoreThreshold = config.template get<double>("ScoreThreshold");
+    const std::string matcherGroup = config.template get<std::string>("ScanMatcherConfigGroup");
+    auto pScanMatcher = std::dynamic_pointer_cast<Mapping::ScanMatcherRealTimeCorrelativeCuda>(
+        CreateScanMatcherRealTimeCorrelativeCuda(jsonSettings, matcherGroup, createCostFunction));
+    return std::make_shared<Mapping::LoopDetectorRealTimeCorrelativeCuda>(pScanMatcher, scoreThreshold);
 }
 
 /* "GridMapBuilder": { ..., "Backend": "Cuda", "Device": 0 } -- the other keys are the ones

@@ -41,6 +41,14 @@ public:
                                      const RobotPose2D<double>& initialPose,
                                      const double normalizedScoreThreshold);
 
+    /* All (scan, initial pose) pairs against ONE map in one device batch (the map is uploaded and
+     * its coarse map computed once): what LoopDetectorRealTimeCorrelativeCuda issues per query */
+    std::vector<ScanMatchingSummary> OptimizePoses(
+        const GridMapType& gridMap,
+        const std::vector<Sensor::ScanDataPtr<double>>& scans,
+        const std::vector<RobotPose2D<double>>& initialPoses,
+        const double normalizedScoreThreshold);
+
     /* Details of the last match (window indices, score, device counters) */
     const lgs_match_result& LastResult() const { return this->mLast; }
 

@@ -122,5 +122,53 @@ ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
         poseFound, normalizedCost, initialPose, estimatedPose, estimatedCovariance };
 }
 
+std::vector<ScanMatchingSummary> ScanMatcherRealTimeCorrelativeCuda::OptimizePoses(
+    const GridMapType& gridMap,
+    const std::vector<Sensor::ScanDataPtr<double>>& scans,
+    const std::vector<RobotPose2D<double>>& initialPoses,
+    const double normalizedScoreThreshold)
+{
+    std::vector<ScanMatchingSummary> summaries;
+    const int n = static_cast<int>(scans.size());
+    if (n == 0)
+        return summaries;
+    this->UploadMap(gridMap);
+
+    std::vector<int> beamBegin(1, 0);
+    std::vector<double> angles, ranges, poses, thresholds(n, normalizedScoreThreshold);
+    std::vector<RobotPose2D<double>> sensorPoses;
+    for (int k = 0; k < n; ++k) {
+        const RobotPose2D<double> sensorPose = Compound(initialPoses[k], scans[k]->RelativeSensorPose());
+        sensorPoses.push_back(sensorPose);
+        poses.insert(poses.end(), { sensorPose.mX, sensorPose.mY, sensorPose.mTheta });
+        angles.insert(angles.end(), scans[k]->Angles().begin(), scans[k]->Angles().end());
+        ranges.insert(ranges.end(), scans[k]->Ranges().begin(), scans[k]->Ranges().end());
+        beamBegin.push_back(static_cast<int>(angles.size()));
+    }
+    const lgs_scan_batch batch { n, beamBegin.data(), angles.data(), ranges.data(), poses.data(),
+                                 nullptr, nullptr };
+    std::vector<lgs_match_result> results(n);
+    Check(this->mCtx, lgs_rtcsm_batch_upload(this->mBatch, this->mGrid, &batch, thresholds.data()),
+          "lgs_rtcsm_batch_upload");
+    Check(this->mCtx, lgs_rtcsm_batch_run(this->mBatch, this->mGrid, this->mCoarse), "lgs_rtcsm_batch_run");
+    Check(this->mCtx, lgs_rtcsm_batch_results(this->mBatch, this->mGrid, this->mCoarse, results.data()),
+          "lgs_rtcsm_batch_results");
+
+    /* per match: the reference's own host tail (scan_matcher_real_time_correlative.cpp:118-144) */
+    for (int k = 0; k < n; ++k) {
+        const lgs_match_result& r = results[k];
+        const RobotPose2D<double> bestSensorPose {
+            sensorPoses[k].mX + r.ix * r.step_x, sensorPoses[k].mY + r.iy * r.step_y,
+            sensorPoses[k].mTheta + r.it * r.step_t };
+        const double costVal = this->mCostFunc->Cost(gridMap, scans[k], bestSensorPose);
+        summaries.emplace_back(
+            r.found != 0, costVal / scans[k]->NumOfScans(), initialPoses[k],
+            MoveBackward(bestSensorPose, scans[k]->RelativeSensorPose()),
+            this->mCostFunc->ComputeCovariance(gridMap, scans[k], bestSensorPose));
+    }
+    this->mLast = results.back();
+    return summaries;
+}
+
 } /* namespace Mapping */
 } /* namespace MyLidarGraphSlam */

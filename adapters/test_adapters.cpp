@@ -11,10 +11,12 @@
 
 #include "lgs_adapters/grid_map_builder_cuda.hpp"
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
+#include "lgs_adapters/loop_detector_real_time_correlative_cuda.hpp"
 #include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
 #include "my_lidar_graph_slam/mapping/cost_function_greedy_endpoint.hpp"
 #include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/loop_detector_real_time_correlative.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_real_time_correlative.hpp"
 
@@ -268,6 +270,49 @@ int main() {
             failures += !ok;
             if (r1.empty()) { std::printf("expected at least one detected loop\n"); ++failures; }
         }
+    }
+    /* ---- loop detector built on the correlative matcher ---- */
+    {
+        auto refMatcher = std::make_shared<ScanMatcherRealTimeCorrelative>(cost, 5, 1.5, 1.5, 0.6, 20.0);
+        auto gpuMatcher = std::make_shared<ScanMatcherRealTimeCorrelativeCuda>(cost, 5, 1.5, 1.5, 0.6, 20.0, 0);
+        LoopDetectorRealTimeCorrelative ref(refMatcher, 0.55);
+        LoopDetectorRealTimeCorrelativeCuda gpu(gpuMatcher, 0.55);
+        std::uniform_real_distribution<double> dxy(-0.5, 0.5), dth(-0.2, 0.2);
+        LoopDetectionQueryVector q1, q2;
+        for (size_t m = 0; m + 1 < builder.LocalMaps().size() && m < 3; ++m) {
+            LocalMapInfo info = builder.LocalMapAt(static_cast<int>(m));
+            info.mFinished = true;
+            std::vector<PoseGraph::Node> n1, n2;
+            for (int j = 0; j < 4; ++j) {
+                const int idx = info.mPoseGraphNodeIdxMin + 1 + 3 * j;
+                const RobotPose2D<double> truth = poseGraph->NodeAt(idx).Pose();
+                const auto scan = MakeScan(world, truth, 541, g);
+                /* the last node is far off: its score stays below the threshold (no edge emitted) */
+                const double far = j == 3 ? 3.0 : 0.0;
+                const RobotPose2D<double> pert(truth.mX + dxy(g) + far, truth.mY + dxy(g) - far, truth.mTheta + dth(g));
+                n1.emplace_back(2000 + j, pert, scan);
+                n2.emplace_back(2000 + j, pert, scan);
+            }
+            const PoseGraph::Node& mapNode = poseGraph->NodeAt(info.mPoseGraphNodeIdxMin);
+            q1.emplace_back(std::move(n1), info, mapNode);
+            q2.emplace_back(std::move(n2), info, mapNode);
+        }
+        LoopDetectionResultVector r1, r2;
+        ref.Detect(q1, r1);
+        gpu.Detect(q2, r2);
+        bool ok = r1.size() == r2.size();
+        for (size_t i = 0; ok && i < r1.size(); ++i)
+            ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) &&
+                 SamePose(r1[i].mStartNodePose, r2[i].mStartNodePose) &&
+                 r1[i].mStartNodeIdx == r2[i].mStartNodeIdx && r1[i].mEndNodeIdx == r2[i].mEndNodeIdx &&
+                 SameMat(r1[i].mEstimatedCovMat, r2[i].mEstimatedCovMat);
+        for (auto& q : q2) ok = ok && q.mLocalMapInfo.mPrecomputed;
+        size_t nodes = 0;
+        for (auto& q : q1) nodes += q.mPoseGraphNodes.size();
+        std::printf("correlative loop detector: %zu queries, %zu nodes, loops ref %zu / cuda %zu %s\n", q1.size(), nodes,
+                    r1.size(), r2.size(), ok ? "IDENTICAL" : "MISMATCH");
+        failures += !ok;
+        if (r1.empty() || r1.size() == nodes) { std::printf("expected some but not all nodes to close a loop\n"); ++failures; }
     }
     std::printf(failures ? "FAILED (%d)\n" : "ALL IDENTICAL\n", failures);
     return failures ? 1 : 0;
