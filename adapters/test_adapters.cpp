@@ -7,8 +7,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <string>
+#include <type_traits>
 #include <random>
 
+#include "lgs_adapters/create_cuda_backends.hpp"
 #include "lgs_adapters/grid_map_builder_cuda.hpp"
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
 #include "lgs_adapters/loop_detector_real_time_correlative_cuda.hpp"
@@ -88,6 +92,24 @@ bool SameMat(const Eigen::Matrix3d& a, const Eigen::Matrix3d& b) {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) if (!SameBits(a(i, j), b(i, j))) return false;
     return true;
 }
+
+/* The smallest property-tree look-alike the factory templates need (Boost is absent here): every
+ * key is looked up in one flat table, get_child returns the tree itself. */
+struct FlatTree {
+    std::map<std::string, std::string> kv;
+    const FlatTree& get_child(const std::string&) const { return *this; }
+    template <typename T> T conv(const std::string& v) const {
+        if constexpr (std::is_same<T, std::string>::value) return v;
+        else if constexpr (std::is_same<T, int>::value) return std::stoi(v);
+        else return static_cast<T>(std::stod(v));
+    }
+    template <typename T> T get(const std::string& key) const { return conv<T>(kv.at(key)); }
+    template <typename T> T get(const std::string& key, const T& def) const {
+        const auto it = kv.find(key);
+        return it == kv.end() ? def : conv<T>(it->second);
+    }
+    std::string get(const std::string& key, const char* def) const { return get<std::string>(key, def); }
+};
 
 /* Geometry, patch allocation and every cell value, as bit patterns */
 bool SameMap(const GridMapType& a, const GridMapType& b) {
@@ -313,6 +335,24 @@ int main() {
                     r1.size(), r2.size(), ok ? "IDENTICAL" : "MISMATCH");
         failures += !ok;
         if (r1.empty() || r1.size() == nodes) { std::printf("expected some but not all nodes to close a loop\n"); ++failures; }
+    }
+    /* ---- the JSON factories of create_cuda_backends.hpp (instantiated with a flat key table) ---- */
+    {
+        FlatTree t;
+        t.kv = {{"LowResolutionMapWinSize", "5"}, {"SearchRangeX", "1.0"}, {"SearchRangeY", "1.0"},
+                {"SearchRangeTheta", "0.6"}, {"ScanRangeMax", "20.0"}, {"ScoreThreshold", "0.6"},
+                {"ScanMatcherConfigGroup", "M"}, {"NodeHeightMax", "6"}, {"ScoreConfigGroup", "S"},
+                {"CostType", "GreedyEndpoint"}, {"CostConfigGroup", "C"}, {"UsableRangeMin", "0.01"},
+                {"UsableRangeMax", "20.0"}, {"Map.NumOfScansForLatestMap", "10"},
+                {"ProbabilityHit", "0.6"}, {"ProbabilityMiss", "0.45"}};
+        auto costFactory = [&](const FlatTree&, const std::string&, const std::string&) { return CostFuncPtr(cost); };
+        auto m = LgsB200::CreateScanMatcherRealTimeCorrelativeCuda(t, "M", costFactory);
+        auto d1 = LgsB200::CreateLoopDetectorBranchBoundCuda(t, "D", costFactory);
+        auto d2 = LgsB200::CreateLoopDetectorRealTimeCorrelativeCuda(t, "D", costFactory);
+        auto b = LgsB200::CreateGridMapBuilderCuda(t, "G");
+        const bool ok = m && d1 && d2 && b && b->LocalMaps().empty();
+        std::printf("factories: %s\n", ok ? "constructed" : "FAILED");
+        failures += !ok;
     }
     std::printf(failures ? "FAILED (%d)\n" : "ALL IDENTICAL\n", failures);
     return failures ? 1 : 0;
