@@ -233,14 +233,20 @@ int main() {
         ScanMatcherRealTimeCorrelative ref(cost, 5, 1.0, 1.0, 0.6, 20.0);
         ScanMatcherRealTimeCorrelativeCuda gpu(cost, 5, 1.0, 1.0, 0.6, 20.0, 0);
         std::uniform_real_distribution<double> dxy(-0.3, 0.3), dth(-0.15, 0.15);
+        double msMatchRef = 0.0, msMatchCuda = 0.0;
         for (int k = 0; k < 6; ++k) {
             const RobotPose2D<double> truth = path[50 + k];
             const auto scan = MakeScan(world, truth, 541, g);
             const RobotPose2D<double> init(truth.mX + dxy(g), truth.mY + dxy(g), truth.mTheta + dth(g));
             ScanMatchingQuery q1(GridMapType(builder.LatestMap()), scan, init);
             ScanMatchingQuery q2(GridMapType(builder.LatestMap()), scan, init);
+            const auto m0 = std::chrono::steady_clock::now();
             const ScanMatchingSummary a = ref.OptimizePose(q1);
+            const auto m1 = std::chrono::steady_clock::now();
             const ScanMatchingSummary b = gpu.OptimizePose(q2);
+            const auto m2 = std::chrono::steady_clock::now();
+            if (k > 0) { msMatchRef += std::chrono::duration<double, std::milli>(m1 - m0).count();
+                         msMatchCuda += std::chrono::duration<double, std::milli>(m2 - m1).count(); }
             const bool ok = a.mPoseFound == b.mPoseFound && SameBits(a.mNormalizedCost, b.mNormalizedCost) &&
                             SamePose(a.mInitialPose, b.mInitialPose) && SamePose(a.mEstimatedPose, b.mEstimatedPose) &&
                             SameMat(a.mEstimatedCovariance, b.mEstimatedCovariance);
@@ -250,6 +256,8 @@ int main() {
                         ok ? "IDENTICAL" : "MISMATCH");
             failures += !ok;
         }
+        std::printf("rtcsm OptimizePose(query) per call (map upload + coarse map + sweep + host tail): "
+                    "reference %.2f ms, cuda %.2f ms\n", msMatchRef / 5, msMatchCuda / 5);
     }
 
     /* ---- loop detector ---- */
@@ -278,8 +286,18 @@ int main() {
                 q2.emplace_back(std::move(n2), info, mapNode);
             }
             LoopDetectionResultVector r1, r2;
+            const auto d0 = std::chrono::steady_clock::now();
             ref.Detect(q1, r1);
+            const auto d1 = std::chrono::steady_clock::now();
             gpu.Detect(q2, r2);
+            const auto d2 = std::chrono::steady_clock::now();
+            long long fix = 0, replay = 0;
+            for (const auto& r : gpu.LastResults()) { fix += r.n_fixups; replay += r.exact_replay; }
+            std::printf("loop round %d Detect: reference %.1f ms, cuda %.1f ms (%lld nodes scored, %lld host fix-ups, "
+                        "%lld CPU-order replays)\n", round,
+                        std::chrono::duration<double, std::milli>(d1 - d0).count(),
+                        std::chrono::duration<double, std::milli>(d2 - d1).count(),
+                        gpu.LastResults().empty() ? 0LL : gpu.LastResults()[0].n_scored, fix, replay);
             bool ok = r1.size() == r2.size();
             for (size_t i = 0; ok && i < r1.size(); ++i)
                 ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) &&
