@@ -668,15 +668,28 @@ def run_b200(args, rank, world_size, local_rank):
                for a, b in zip(results_dev, res_e2e))
 
     extra = {}
+
+    def side(name, fn):
+        """A side measurement must never take the headline line down with it (single process only:
+        with several ranks a failure has to propagate, or the other ranks wait in a collective)."""
+        if world_size > 1:
+            extra[name] = fn()
+            return
+        try:
+            extra[name] = fn()
+        except Exception as e:                                   # noqa: BLE001
+            extra[name] = {"error": f"{type(e).__name__}: {e}"}
+
     if not args.no_extra:
-        extra["loop_detection"] = run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
-                                         args.submaps, max(3, min(args.steps, 10)),
-                                         world_size == 1 and not args.no_cpu_baseline)
+        side("loop_detection", lambda: run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
+                                              args.submaps, max(3, min(args.steps, 10)),
+                                              world_size == 1 and not args.no_cpu_baseline))
         if rank == 0:
-            extra["grid_integration"] = run_c3(ctx, 256, args.c3_scans, not args.no_cpu_baseline)
+            side("grid_integration", lambda: run_c3(ctx, 256, args.c3_scans, not args.no_cpu_baseline))
         if args.c5_side > 0:
-            extra["large_map"] = run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_ranks,
-                                        args.c5_side, args.c5_queries, max(2, min(args.steps, 5)))
+            side("large_map", lambda: run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
+                                             sum_over_ranks, args.c5_side, args.c5_queries,
+                                             max(2, min(args.steps, 5))))
     if rank != 0:
         return
     # ---- CPU baseline: the unmodified reference on a bounded sample, parity-checked ------------
