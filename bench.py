@@ -464,7 +464,7 @@ def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_
 
 def run_c3(ctx, n_distinct, n_total, with_cpu):
     """C3 (bounded sample): 1081-beam scans along a trajectory integrated into one pre-sized map
-    in batches (default 256 scans per call), host hit points in, cell updates applied in (scan, beam) order."""
+    in calls of up to 1024 scans, page-locked host hit points in, cell updates applied in (scan, beam) order."""
     from my_lidar_graph_slam_b200 import capi
     world = synth.RoomsWorld(40.0, 5.0, seed=6)
     angles = synth.beam_angles(1081, 270.0)
@@ -475,7 +475,7 @@ def run_c3(ctx, n_distinct, n_total, with_cpu):
     geo = capi.Geometry(0, 0, -20.0, -20.0, 0.05, 64)
     geo, _, _, _ = capi.geometry_expand(geo, (-20.5, -20.5, 20.5, 20.5), 0.0)
     grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
-    B = int(os.environ.get("C3_BATCH", "256"))
+    B = int(os.environ.get("C3_BATCH", "1024"))
     batches = [capi.PackedHits(traj[k:k + B, :2], hits[k:k + B]) for k in range(0, n_distinct, B)]
     for b in batches:                                                 # page-locked host inputs
         capi.pin(ctx, b.hit, b.sxy, b.begin)
@@ -685,7 +685,7 @@ def run_b200(args, rank, world_size, local_rank):
                                               args.submaps, max(3, min(args.steps, 10)),
                                               world_size == 1 and not args.no_cpu_baseline))
         if rank == 0:
-            side("grid_integration", lambda: run_c3(ctx, 256, args.c3_scans, not args.no_cpu_baseline))
+            side("grid_integration", lambda: run_c3(ctx, 1024, args.c3_scans, not args.no_cpu_baseline))
         if args.c5_side > 0:
             side("large_map", lambda: run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
                                              sum_over_ranks, args.c5_side, args.c5_queries,
@@ -763,7 +763,7 @@ def main():
     ap.add_argument("--submaps", type=int, default=500, help="C4: submaps per loop query batch")
     ap.add_argument("--c5-side", type=int, default=8000, help="C5: map side in cells (multiple of 1000; 0 = skip)")
     ap.add_argument("--c5-queries", type=int, default=256, help="C5: loop queries per batch")
-    ap.add_argument("--c3-scans", type=int, default=4096, help="C3: scans in the bounded sample")
+    ap.add_argument("--c3-scans", type=int, default=8192, help="C3: scans in the bounded sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
