@@ -271,7 +271,7 @@ struct TouchSeq {
     }
 };
 
-__global__ void __launch_bounds__(kTileCells, 5)
+__global__ void __launch_bounds__(kTileCells, 4)
 integ_touch_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs,
                    const unsigned* __restrict__ nPairs, unsigned* __restrict__ records, unsigned* __restrict__ side,
                    unsigned* __restrict__ sideCursor, unsigned sideCap,
@@ -723,7 +723,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         LGS_LAUNCH_CHECK(c);
         stamp();
         w.dirty = false;
-        const unsigned touchBlocks = (unsigned)std::min<size_t>(pairBound, (size_t)c->sm_count * 5);
+        const unsigned touchBlocks = (unsigned)std::min<size_t>(pairBound, (size_t)c->sm_count * 4);
         integ_touch_kernel<<<touchBlocks, kTileCells, 0, c->stream>>>(w.rel.p, w.pairs[buf].p, nPairs, w.records[buf].p,
                                                                       w.side[buf].p, nPairs + 1, (unsigned)sideCap,
                                                                       w.counters.p);
