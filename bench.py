@@ -491,8 +491,8 @@ def run_c3(ctx, n_distinct, n_total, with_cpu):
             h2d += b.nbytes
     ctx.synchronize()
     dt = time.perf_counter() - t0
-    out = {"workload": f"C3 occupancy-grid integration (bounded sample: {done} scans = {n_distinct} distinct "
-                       f"scans streamed repeatedly, batches of {B}) into one {geo.nx}x{geo.ny} map",
+    out = {"workload": f"C3 occupancy-grid integration: {done} scans streamed ({n_distinct} distinct 1081-beam "
+                       f"scans along a trajectory, repeated; calls of {B} scans) into one {geo.nx}x{geo.ny} map",
            "scans_per_s": done / dt, "cell_updates_per_s": updates / dt,
            "cell_updates_per_scan": updates / done, "e2e": True,
            "h2d_bytes_per_scan": h2d / done,
@@ -763,7 +763,7 @@ def main():
     ap.add_argument("--submaps", type=int, default=500, help="C4: submaps per loop query batch")
     ap.add_argument("--c5-side", type=int, default=8000, help="C5: map side in cells (multiple of 1000; 0 = skip)")
     ap.add_argument("--c5-queries", type=int, default=256, help="C5: loop queries per batch")
-    ap.add_argument("--c3-scans", type=int, default=8192, help="C3: scans in the bounded sample")
+    ap.add_argument("--c3-scans", type=int, default=102400, help="C3: scans streamed (BASELINE config: 100k)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
