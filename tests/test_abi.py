@@ -31,3 +31,14 @@ def test_no_cpu_fallback_without_gpu():
     h = C.c_void_p()
     rc = capi.lib().lgs_ctx_create(10_000, C.byref(h))   # no such device anywhere
     assert rc == 2 and not h.value
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary must be bindable from C (no C++ or torch types in the signatures)."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "lgs_b200.h"\nint main(void) { lgs_match_result r; r.found = 0; return r.found + LGS_OK; }\n')
+    p = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout
