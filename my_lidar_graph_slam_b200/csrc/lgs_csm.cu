@@ -54,6 +54,8 @@ struct CsmWindow {           // identical for every match of a batch (depends on
     int block;               // threads per block
     int hpt;                 // fine hypotheses per thread (1 or 4)
     int slots;               // thread slots per theta = ceil(nHyp / hpt) rounded up to a warp
+    int rows;                // > 0: row-mapped sweep, fine rows per thread (4 or 5)
+    int xChunks, rowGroups;  // warps per theta = xChunks * rowGroups (lanes = 32 consecutive x)
 };
 
 struct GridGeom {
@@ -196,6 +198,89 @@ csm_sweep_kernel(const CsmDesc* __restrict__ descs, const double* __restrict__ f
             fineTab[d.fineBegin + ((long long)t * w.nyw + oy) * w.nxw + ox] = acc[k];
         }
     }
+}
+
+// ---- K2b: the sweep, row mapped --------------------------------------------------------------------
+// Same arithmetic as csm_sweep_kernel, different ownership: a warp's lanes are the x offsets of ONE
+// window row (25 of 32 lanes for config C2) and a thread owns ROWS consecutive rows.  A 32-lane
+// request then touches the 2-3 cache lines of a single 25-cell row (2.5 L1 wavefronts on average)
+// instead of the 3.8 lines of 1.28 rows of the flattened mapping: ~15 % fewer L1 wavefronts for the
+// same gathers, and the L1 data pipe is what bounds this kernel (profiles/r1_kernels_v2.md).
+template <int UNROLL, int ROWS>
+__global__ void __launch_bounds__(256)
+csm_sweep_rows_kernel(const CsmDesc* __restrict__ descs, const double* __restrict__ fineGrid,
+                      const double* __restrict__ coarseGrid, int pitch, CsmWindow w,
+                      const int* __restrict__ offs, double* __restrict__ fineTab,
+                      double* __restrict__ coarseTab) {
+    extern __shared__ int sOff[];
+    const CsmDesc d = descs[blockIdx.z];
+    const int t = blockIdx.y;
+    if (t >= d.nT) return;
+    {   // stage this theta's offsets (nKeptPad is a multiple of 4 ints = 16 B)
+        const int4* src = reinterpret_cast<const int4*>(offs + d.offBegin + (long long)t * d.nKeptPad);
+        int4* dst = reinterpret_cast<int4*>(sOff);
+        for (int k = threadIdx.x; k < d.nKeptPad / 4; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int n = d.nKeptPad;   // multiple of kBeamPad >= UNROLL
+
+    if (blockIdx.x >= (unsigned)w.tilesFine) {
+        // Coarse hypotheses (stride lowRes on the win-max map), one per thread.
+        const int h = (blockIdx.x - w.tilesFine) * blockDim.x + threadIdx.x;
+        if (h >= w.nbx * w.nby) return;
+        const int oy = h / w.nbx, ox = h - oy * w.nbx;
+        const double* __restrict__ gp =
+            coarseGrid + (-w.winY + oy * w.lowRes) * pitch + (-w.winX + ox * w.lowRes);
+        double acc = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < n; i += UNROLL) {
+            double v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(gp + sOff[i + u]);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) acc = __dadd_rn(acc, v[u]);
+        }
+        coarseTab[d.coarseBegin + ((long long)t * w.nbx + ox) * w.nby + oy] = acc;
+        return;
+    }
+
+    const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int xc = wg % w.xChunks, rg = wg / w.xChunks;
+    const int ox = xc * 32 + (threadIdx.x & 31);
+    if (rg >= w.rowGroups || ox >= w.nxw) return;
+    const int oy0 = rg * ROWS;
+    const double* __restrict__ gp = fineGrid + (-w.winY + oy0) * pitch + (-w.winX + ox);
+    double acc[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) acc[k] = 0.0;
+    const int nRows = min(ROWS, w.nyw - oy0);
+    if (nRows == ROWS) {
+#pragma unroll 1
+        for (int i = 0; i < n; i += UNROLL) {
+            double v[UNROLL][ROWS];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const double* __restrict__ q = gp + sOff[i + u];
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) v[u][k] = __ldg(q + k * pitch);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) acc[k] = __dadd_rn(acc[k], v[u][k]);   // beam order, like the CPU
+        }
+    } else {                                   // last row group of a window whose height is no multiple of ROWS
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const double* __restrict__ q = gp + sOff[i];
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k)
+                if (k < nRows) acc[k] = __dadd_rn(acc[k], __ldg(q + k * pitch));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k)
+        if (k < nRows) fineTab[d.fineBegin + ((long long)t * w.nyw + oy0 + k) * w.nxw + ox] = acc[k];
 }
 
 // ---- K3: block maxima + CPU-order selection -----------------------------------------------------
@@ -354,7 +439,15 @@ static int csm_launch_sweep(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_
         const int nm = std::min(65535, b->nMatch - m0);
         dim3 gridDim(w.tilesFine + w.tilesCoarse, b->maxNT, nm);
         const size_t smem = (size_t)b->maxKeptPad * sizeof(int);
-        if (w.hpt == 4)
+        if (w.rows == 5)
+            csm_sweep_rows_kernel<4, 5><<<gridDim, w.block, smem, c->stream>>>(
+                b->dDescs.p + m0, grid->origin(), coarse->origin(), grid->pitch, w, b->dOffs.p,
+                b->dFine.p, b->dCoarse.p);
+        else if (w.rows == 4)
+            csm_sweep_rows_kernel<4, 4><<<gridDim, w.block, smem, c->stream>>>(
+                b->dDescs.p + m0, grid->origin(), coarse->origin(), grid->pitch, w, b->dOffs.p,
+                b->dFine.p, b->dCoarse.p);
+        else if (w.hpt == 4)
             csm_sweep_kernel<4, 4><<<gridDim, w.block, smem, c->stream>>>(
                 b->dDescs.p + m0, grid->origin(), coarse->origin(), grid->pitch, w, b->dOffs.p,
                 b->dFine.p, b->dCoarse.p);
@@ -439,6 +532,22 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     w.slots = (((w.nxw * w.nyw + w.hpt - 1) / w.hpt) + 31) / 32 * 32;
     w.block = pick_block(w.slots);
     w.tilesFine = (w.slots + w.block - 1) / w.block;
+    w.rows = 0; w.xChunks = 1; w.rowGroups = 0;
+    if (w.hpt == 4 && getenv("LGS_CSM_FLAT") == nullptr) {
+        // row-mapped sweep: lanes = x offsets of one window row, ROWS rows per thread
+        w.rows = (w.nyw % 5 == 0) ? 5 : 4;
+        w.xChunks = (w.nxw + 31) / 32;
+        w.rowGroups = (w.nyw + w.rows - 1) / w.rows;
+        const int warps = w.xChunks * w.rowGroups;
+        int wpb = std::min(8, warps);                        // warps per block: fewest idle warps, larger wins
+        long long bestWaste = 1LL << 60;
+        for (int cand = std::min(8, warps); cand >= 2; --cand) {
+            const long long waste = (long long)((warps + cand - 1) / cand) * cand - warps;
+            if (waste < bestWaste) { bestWaste = waste; wpb = cand; }
+        }
+        w.block = wpb * 32;
+        w.tilesFine = (warps + wpb - 1) / wpb;
+    }
     w.tilesCoarse = (w.nbx * w.nby + w.block - 1) / w.block;
     b->geom = GridGeom{grid->min_x, grid->min_y, grid->res, grid->nx, grid->ny, grid->pitch};
 
@@ -530,6 +639,12 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          b->maxKeptPad * (int)sizeof(int)));
         LGS_CUDA(c, cudaFuncSetAttribute(csm_sweep_kernel<4, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         b->maxKeptPad * (int)sizeof(int)));
+        LGS_CUDA(c, cudaFuncSetAttribute(csm_sweep_rows_kernel<4, 5>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         b->maxKeptPad * (int)sizeof(int)));
+        LGS_CUDA(c, cudaFuncSetAttribute(csm_sweep_rows_kernel<4, 4>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          b->maxKeptPad * (int)sizeof(int)));
     }
