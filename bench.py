@@ -731,7 +731,7 @@ def run_b200(args, rank, world_size, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": 0.8305e6 * M, "kernel": "csm_sweep_kernel",
+                     "frac": achieved / peak, "traffic": 0.8305e6 * M, "kernel": "csm_sweep_rows_kernel<4,5>",
                      "traffic_source": "ncu --set full: dram__bytes_read+write = 166.1 MB per 200-match "
                                        "launch (profiles/r1_kernels_v2.md), scaled to this launch",
                      "peak_source": peak_src, "kernel_ms": k_sweep,
