@@ -146,7 +146,7 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
                 v = make_int2(INT_MIN, f);      // sentinel: use the exact per-offset table f
             }
         }
-        tab[d.tabBegin + idx] = v;
+        __stcs(tab + d.tabBegin + idx, v);            // 1.3 GB written once, read back by a later launch: streaming
     }
 }
 
