@@ -771,7 +771,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world_size)
     else:
-        run_b200(args, rank, world_size, local_rank)
+        try:
+            run_b200(args, rank, world_size, local_rank)
+        finally:
+            if world_size > 1:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
