@@ -166,7 +166,7 @@ def run_reference(args, rank, world_size):
     if not R.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblgs_ref.so not built"}))
         return
-    per_step = max(4 * cores, 32)
+    per_step = max(16 * cores, 64)      # enough matches per step to keep every host thread busy
     total = per_step * (args.steps + args.warmup)
     traj, map_scans, angles, ranges, inits = c2_workload(total, seed=1)
     builder = R.RefBuilder(n_latest=len(traj))
