@@ -46,6 +46,8 @@ struct BbScan {                     // one per DISTINCT (scan, sensor pose): hit
     int nUse, beamBegin;            // usable beams (ScorePixelAccurate range filter)
     int pad;
     long long hitBegin;             // into hits: nUse * nTpad (double2), beam-major
+    double invRes;                  // 1 / resolution of the maps this scan is matched against
+    int sortBegin, sortCount;       // this scan's queries sorted by frac(min * invRes) (flag search)
 };
 
 struct BbQuery {
@@ -85,6 +87,7 @@ struct BbResult {
 };
 
 struct BbFlag { int q, t, i; };
+constexpr int kFlagInline = 8;      // the root-from-hit-points path handles up to this many near-edge points
 
 // ---- stage A: world hit point of every (distinct scan, usable beam, theta) at node offset (0, 0) ----
 // Threads are theta-fastest so neighbouring lanes differ by one angular step: their hit points are
@@ -150,6 +153,194 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
     }
 }
 
+// ---- stage B': near-edge flags without the all-pairs pass ------------------------------------------------
+// A point is near an edge in query q iff frac((h - min_q) / res) is within eps of 0 or 1, i.e. iff
+// frac(h / res) and frac(min_q / res) are within eps of each other (mod 1, up to ~1e-10 of rounding).
+// The queries of a scan are sorted by frac(min_q / res) per axis on the host; a hit point binary
+// searches the +-delta window (delta = eps + 1e-7, a superset) and runs the exact test of the
+// reference expression only on those candidates.  Every near-edge (query, theta, beam) is registered
+// exactly once: through the x list if x is near an edge, else through the y list.
+__global__ void bb_flagsearch_kernel(const BbScan* __restrict__ scans, const BbQuery* __restrict__ qs,
+                                     const double2* __restrict__ hits, const double* __restrict__ sortFx,
+                                     const int* __restrict__ sortQx, const double* __restrict__ sortFy,
+                                     const int* __restrict__ sortQy, double eps, double delta,
+                                     BbFlag* __restrict__ flags, int* __restrict__ flagCount) {
+    const BbScan& u = scans[blockIdx.z];
+    const int i = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u.nUse || t >= u.nT) return;
+    const double2 h = hits[u.hitBegin + (long long)i * u.nTpad + t];
+    auto test = [&](int q, bool viaX) {
+        const BbQuery& d = qs[q];
+        const double qx = __dmul_rn(__dsub_rn(h.x, d.minX), d.invRes);
+        const double qy = __dmul_rn(__dsub_rn(h.y, d.minY), d.invRes);
+        const double rx = qx - floor(qx), ry = qy - floor(qy);
+        const bool edgeX = !(rx >= eps && rx <= 1.0 - eps), edgeY = !(ry >= eps && ry <= 1.0 - eps);
+        if (viaX ? !edgeX : (!edgeY || edgeX)) return;
+        const int f = atomicAdd(flagCount, 1);
+        if (f < kFlagCapBB) flags[f] = BbFlag{q, t, i};
+    };
+    auto window = [&](const double* __restrict__ F, const int* __restrict__ Q, double lo, double hi, bool viaX) {
+        int a = 0, b = u.sortCount;                          // first entry >= lo
+        while (a < b) { const int m = (a + b) >> 1; if (F[u.sortBegin + m] < lo) a = m + 1; else b = m; }
+        for (; a < u.sortCount && F[u.sortBegin + a] <= hi; ++a) test(Q[u.sortBegin + a], viaX);
+    };
+    auto axis = [&](double coord, const double* __restrict__ F, const int* __restrict__ Q, bool viaX) {
+        const double a = __dmul_rn(coord, u.invRes);
+        const double fa = a - floor(a);
+        window(F, Q, fa - delta, fa + delta, viaX);
+        if (fa - delta < 0.0) window(F, Q, fa - delta + 1.0, 2.0, viaX);     // wrap around 0 / 1
+        if (fa + delta >= 1.0) window(F, Q, -1.0, fa + delta - 1.0, viaX);
+    };
+    axis(h.x, sortFx, sortQx, true);
+    axis(h.y, sortFy, sortQy, false);
+}
+
+// ---- root level straight from the hit points ------------------------------------------------------------
+// The root level visits every (query, theta), so it would read the whole per-query index table once;
+// instead it converts the shared hit points on the fly (the reference's expression in double: every
+// point outside the eps band floors identically, the <= kFlagInline points inside it come from the
+// host's tables) and only the (query, theta) rows that survive get table rows (bb_index_slots_kernel).
+// A survivor's row slot is childBase / 4: children are allocated four per survivor.
+template <int U>
+__global__ void __launch_bounds__(128)
+bb_score_root_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
+                     const double2* __restrict__ hits, const BbFlag* __restrict__ flags, int nFlag,
+                     const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
+                     Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
+                     Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
+                     int2* __restrict__ slotQT, int* __restrict__ slotOut, BbBest* __restrict__ best) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = k < nNodes;
+    Node n;
+    bool survive = false;
+    if (active) {
+        n = nodes[k];
+        const BbQuery& d = qs[n.q];
+        const double* __restrict__ lvl = d.level[height];
+        const int stride = d.nTpad;
+        const double2* __restrict__ hb = hits + scans[d.scan].hitBegin + n.t;
+        const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
+        const double minX = d.minX, minY = d.minY, invRes = d.invRes;
+        const int ox = n.x - d.offX, oy = n.y - d.offY;       // node offset minus window origin
+        bool hasFlag = false;
+        for (int f = 0; f < nFlag; ++f) hasFlag |= flags[f].q == n.q && flags[f].t == n.t;
+        double acc = 0.0;
+        auto cellAt = [&](int i) -> const double* {           // slow path: a flagged beam may be among them
+            int ix, iy, ff = -1;
+            for (int f = 0; f < nFlag; ++f)
+                if (flags[f].q == n.q && flags[f].t == n.t && flags[f].i == i) ff = f;
+            if (ff < 0) {
+                const double2 h = __ldg(hb + (long long)i * stride);
+                ix = __double2int_rd(__dmul_rn(__dsub_rn(h.x, minX), invRes)) + ox;
+                iy = __double2int_rd(__dmul_rn(__dsub_rn(h.y, minY), invRes)) + oy;
+            } else {
+                const int* e = exactIdx + (long long)ff * (exactSpanX + exactSpanY);
+                ix = e[n.x + d.winX];
+                iy = e[exactSpanX + n.y + d.winY];
+            }
+            ix = min(max(ix, -1), gx);
+            iy = min(max(iy, -1), gy);
+            return lvl + (long long)iy * pitch + ix;
+        };
+        int i = 0;
+        bool hasNaN = false;
+        if (!hasFlag) {
+#pragma unroll 1
+            for (; i + U <= nb; i += U) {
+                // three separate unrolled loops, so that U hit points, then U map cells are in flight
+                // together (one fused loop lets the compiler serialise the two dependent latencies)
+                double2 hp[U];
+                long long off[U];
+                double v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) hp[u] = __ldg(hb + (long long)(i + u) * stride);
+                // a value that depends on ALL loads gates the rest, so the U loads are issued back to
+                // back (the full-table kernel gets the same effect from its sentinel test)
+                bool odd = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) odd |= !(hp[u].x == hp[u].x);
+                if (odd) { hasNaN = true; break; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int ix = min(max(__double2int_rd(__dmul_rn(__dsub_rn(hp[u].x, minX), invRes)) + ox, -1), gx);
+                    const int iy = min(max(__double2int_rd(__dmul_rn(__dsub_rn(hp[u].y, minY), invRes)) + oy, -1), gy);
+                    off[u] = (long long)iy * pitch + ix;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = __ldg(lvl + off[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, v[u]);   // unknown cells add 0.0
+            }
+        }
+        (void)hasNaN;                        // a NaN hit point simply continues on the one-beam path below
+        for (; i < nb; ++i) acc = __dadd_rn(acc, __ldg(cellAt(i)));
+        scores[k] = acc;
+        if (acc > d.thrAbs) {                                     // :108 with scoreMax >= threshold
+            if (height == 0)
+                atomicMax(&best[n.q].scoreBits, (unsigned long long)__double_as_longlong(acc));
+            else
+                survive = true;
+        } else {
+            nodes[k].childBase = -1;
+        }
+    }
+    if (height == 0) return;
+    const unsigned m = __ballot_sync(0xffffffffu, survive);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int cnt = __popc(m);
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(nextCount, 4 * cnt);
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (!survive) return;
+    const int r = __popc(m & ((1u << lane) - 1u));
+    nodes[k].childBase = base + r;
+    nodes[k].childStride = cnt;
+    if (base + 4 * cnt > nextCap) return;       // the pool is too small: this run is repeated
+    const int slot = (base >> 2) + r;           // nextCount only ever grows by multiples of four
+    slotQT[slot] = make_int2(n.q, n.t);
+    const int w = 1 << (height - 1);
+    const int dx[4] = {w, 0, w, 0}, dy[4] = {w, w, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        Node ch;
+        ch.x = (short)(n.x + dx[c]); ch.y = (short)(n.y + dy[c]); ch.t = n.t; ch.q = n.q;
+        ch.rank = n.rank * 4 + c;
+        ch.parent = k; ch.childBase = -1; ch.childStride = 0;
+        next[base + c * cnt + r] = ch;
+        slotOut[base + c * cnt + r] = slot;
+    }
+}
+
+// ---- index rows of the surviving (query, theta) pairs ------------------------------------------------------
+// tab2[beam * slotStride + slot] = cell of the beam at node offset (0, 0); slots of neighbouring thetas
+// are neighbours (warp-aggregated allocation), so the deeper levels' table reads stay coalesced.
+__global__ void bb_index_slots_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
+                                      const double2* __restrict__ hits, const int2* __restrict__ slotQT,
+                                      const int* __restrict__ childCount, int slotStride,
+                                      const BbFlag* __restrict__ flags, int nFlag, int2* __restrict__ tab2) {
+    constexpr int kBeamsPerThread = 8;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= min(__ldg(childCount) >> 2, slotStride)) return;
+    const int2 qt = slotQT[slot];
+    const BbQuery& d = qs[qt.x];
+    const double2* __restrict__ hb = hits + scans[d.scan].hitBegin + qt.y;
+    const double minX = d.minX, minY = d.minY, invRes = d.invRes;
+    const int offX = d.offX, offY = d.offY, nb = d.nUse, stride = d.nTpad;
+#pragma unroll
+    for (int j = 0; j < kBeamsPerThread; ++j) {
+        const int i = blockIdx.y * kBeamsPerThread + j;
+        if (i >= nb) break;
+        const double2 h = __ldg(hb + (long long)i * stride);
+        int2 v = make_int2(__double2int_rd(__dmul_rn(__dsub_rn(h.x, minX), invRes)) - offX,
+                           __double2int_rd(__dmul_rn(__dsub_rn(h.y, minY), invRes)) - offY);
+        for (int f = 0; f < nFlag; ++f)
+            if (flags[f].q == qt.x && flags[f].t == qt.y && flags[f].i == i) v = make_int2(INT_MIN, f);
+        tab2[(long long)i * slotStride + slot] = v;
+    }
+}
+
 // ---- roots --------------------------------------------------------------------------------------
 __global__ void bb_roots_kernel(const BbQuery* __restrict__ qs, int nq, int height,
                                 Node* __restrict__ pool) {
@@ -181,7 +372,10 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                 const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
                 Node* __restrict__ nodes, double* __restrict__ scores, int nMax,
                 const int* __restrict__ nDev, Node* __restrict__ next, int nextCap,
-                int* __restrict__ nextCount, BbBest* __restrict__ best) {
+                int* __restrict__ nextCount, BbBest* __restrict__ best,
+                const int* __restrict__ slotIn, int* __restrict__ slotOut, int slotStride) {
+    // slotIn != nullptr: `tab` holds one row per surviving (query, theta) (bb_index_slots_kernel) and
+    // slotIn[k] is node k's row; otherwise `tab` is the full per-query table.
     // nDev (speculative, sync-free runs): the level's node count lives on the device; the launch
     // covers the pool capacity nMax and surplus threads leave here
     const int nNodes = nDev ? min(__ldg(nDev), nMax) : nMax;
@@ -193,8 +387,8 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
         n = nodes[k];
         const BbQuery& d = qs[n.q];
         const double* __restrict__ lvl = d.level[height];
-        const int stride = d.nTpad;
-        const int2* __restrict__ tb = tab + d.tabBegin + n.t;
+        const int stride = slotIn ? slotStride : d.nTpad;
+        const int2* __restrict__ tb = slotIn ? tab + slotIn[k] : tab + d.tabBegin + n.t;
         const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
         const int nxo = n.x, nyo = n.y;
         double acc = 0.0;
@@ -269,6 +463,7 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
         ch.rank = n.rank * 4 + c;
         ch.parent = k; ch.childBase = -1; ch.childStride = 0;
         next[base + c * cnt + r] = ch;
+        if (slotIn) slotOut[base + c * cnt + r] = slotIn[k];
     }
 }
 
@@ -283,7 +478,8 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
                      const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
                      Node* __restrict__ nodes, double* __restrict__ scores, int nMax,
                      const int* __restrict__ nDev, Node* __restrict__ next, int nextCap,
-                     int* __restrict__ nextCount, BbBest* __restrict__ best) {
+                     int* __restrict__ nextCount, BbBest* __restrict__ best,
+                     const int* __restrict__ slotIn, int* __restrict__ slotOut, int slotStride) {
     constexpr int CH = 16, STAGE = 32 * CH;
     const int nNodes = nDev ? min(__ldg(nDev), nMax) : nMax;
     __shared__ double sv[4][STAGE];
@@ -294,8 +490,8 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
     const Node n = nodes[k];
     const BbQuery& d = qs[n.q];
     const double* __restrict__ lvl = d.level[height];
-    const int stride = d.nTpad;
-    const int2* __restrict__ tb = tab + d.tabBegin + n.t;
+    const int stride = slotIn ? slotStride : d.nTpad;
+    const int2* __restrict__ tb = slotIn ? tab + slotIn[k] : tab + d.tabBegin + n.t;
     const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
     const int nxo = n.x, nyo = n.y;
     double acc = 0.0;
@@ -372,6 +568,7 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
         ch.rank = n.rank * 4 + cidx;
         ch.parent = k; ch.childBase = -1; ch.childStride = 0;
         next[slot + cidx] = ch;
+        if (slotIn) slotOut[slot + cidx] = slotIn[k];
     }
 }
 
@@ -500,7 +697,16 @@ struct lgs_bb_batch {
     DevBuf<BbScan> dUs;
     DevBuf<double2> dHits;
     DevBuf<double> dAngles, dRanges;
-    DevBuf<int2> dTab;
+    DevBuf<int2> dTab;               // full per-query index table (only the many-flags fallback path)
+    DevBuf<int2> dTab2, dSlotQT;     // rows of the surviving (query, theta) pairs; their (q, t)
+    DevBuf<int> dSlot[kMaxLevels];   // row slot of every node of a level
+    DevBuf<double> dSortFx, dSortFy; // per scan: its queries sorted by frac(min * invRes), per axis
+    DevBuf<int> dSortQx, dSortQy;
+    std::vector<double> hSortFx, hSortFy;
+    std::vector<int> hSortQx, hSortQy;
+    bool slotPath = false;           // the last run scored the root level from the hit points
+    int nFlagRun = 0;                // near-edge points of the last run
+    int slotLaunch = 0;              // slots the speculative run built index rows for
     DevBuf<BbFlag> dFlags;
     DevBuf<int> dCounters;          // [0] flag count, [1 + h] node count of level h
     DevBuf<int> dExact;
@@ -530,7 +736,9 @@ int lgs_bb_batch_destroy(lgs_bb_batch* b) {
     if (!b) return LGS_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dChunks.release(); b->dQlist.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release();
+    b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dChunks.release(); b->dQlist.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release(); b->dTab2.release(); b->dSlotQT.release();
+    for (auto& sl : b->dSlot) sl.release();
+    b->dSortFx.release(); b->dSortFy.release(); b->dSortQx.release(); b->dSortQy.release();
     b->dFlags.release(); b->dCounters.release(); b->dExact.release(); b->dBest.release();
     b->dRes.release(); b->hRes.release(); b->hCounters.release();
     for (int h = 0; h < kMaxLevels; ++h) { b->dNodes[h].release(); b->dScores[h].release(); }
@@ -627,12 +835,13 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         const double minRange = std::max(p.score_range_min, sMin);
         const double maxRangeS = std::min(p.score_range_max, sMax);
         int uidx = scanToUnique[sq];
-        if (uidx >= 0 && b->us[uidx].stepT != stepT) uidx = -1;      // other map resolution
+        if (uidx >= 0 && (b->us[uidx].stepT != stepT || b->us[uidx].invRes != d.invRes)) uidx = -1;   // other map resolution
         if (uidx < 0) {
             BbScan u{};
             u.sx = scans->sensor_pose[3 * sq]; u.sy = scans->sensor_pose[3 * sq + 1];
             u.st = scans->sensor_pose[3 * sq + 2];
             u.stepT = stepT; u.winT = d.winT; u.nT = d.nT; u.nTpad = d.nTpad;
+            u.invRes = d.invRes; u.sortBegin = 0; u.sortCount = 0;
             u.beamBegin = (int)b->hAngles.size();
             for (int i = b0; i < b1; ++i) {
                 const double r = scans->ranges[i];
@@ -667,6 +876,25 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         std::vector<std::vector<int>> byScan(b->us.size());
         for (int q = 0; q < n; ++q) byScan[b->qs[q].scan].push_back(q);
         b->qlist.clear(); b->chunks.clear();
+        // flag search: the queries of every scan sorted by the fractional part of min * invRes
+        b->hSortFx.clear(); b->hSortFy.clear(); b->hSortQx.clear(); b->hSortQy.clear();
+        for (size_t u = 0; u < byScan.size(); ++u) {
+            std::vector<std::pair<double, int>> fx, fy;
+            for (int q : byScan[u]) {
+                const BbQuery& d = b->qs[q];
+                const double ax = d.minX * d.invRes, ay = d.minY * d.invRes;
+                fx.emplace_back(ax - std::floor(ax), q);
+                fy.emplace_back(ay - std::floor(ay), q);
+            }
+            std::sort(fx.begin(), fx.end());
+            std::sort(fy.begin(), fy.end());
+            b->us[u].sortBegin = (int)b->hSortFx.size();
+            b->us[u].sortCount = (int)fx.size();
+            for (size_t k = 0; k < fx.size(); ++k) {
+                b->hSortFx.push_back(fx[k].first); b->hSortQx.push_back(fx[k].second);
+                b->hSortFy.push_back(fy[k].first); b->hSortQy.push_back(fy[k].second);
+            }
+        }
         for (size_t u = 0; u < byScan.size(); ++u)
             for (size_t k = 0; k < byScan[u].size(); k += kIdxChunk) {
                 const int cnt = (int)std::min<size_t>(kIdxChunk, byScan[u].size() - k);
@@ -683,7 +911,10 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     LGS_CUDA(c, b->dHits.reserve(std::max<long long>(nHits, 1)));
     LGS_CUDA(c, b->dAngles.reserve(std::max<size_t>(nk, 1)));
     LGS_CUDA(c, b->dRanges.reserve(std::max<size_t>(nk, 1)));
-    LGS_CUDA(c, b->dTab.reserve(std::max<long long>(nTab, 1)));
+    LGS_CUDA(c, b->dSortFx.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
+    LGS_CUDA(c, b->dSortFy.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
+    LGS_CUDA(c, b->dSortQx.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
+    LGS_CUDA(c, b->dSortQy.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
     LGS_CUDA(c, b->dFlags.reserve(kFlagCapBB));
     LGS_CUDA(c, b->dCounters.reserve(2 + kMaxLevels));
     LGS_CUDA(c, b->hCounters.reserve(2 + kMaxLevels));
@@ -696,6 +927,13 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     LGS_CUDA(c, cudaMemcpyAsync(b->dUs.p, b->us.data(), b->us.size() * sizeof(BbScan), cudaMemcpyHostToDevice, c->stream));
     LGS_CUDA(c, cudaMemcpyAsync(b->dChunks.p, b->chunks.data(), b->chunks.size() * sizeof(IdxChunk), cudaMemcpyHostToDevice, c->stream));
     LGS_CUDA(c, cudaMemcpyAsync(b->dQlist.p, b->qlist.data(), b->qlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (!b->hSortFx.empty()) {
+        const size_t ns = b->hSortFx.size();
+        LGS_CUDA(c, cudaMemcpyAsync(b->dSortFx.p, b->hSortFx.data(), ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LGS_CUDA(c, cudaMemcpyAsync(b->dSortFy.p, b->hSortFy.data(), ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LGS_CUDA(c, cudaMemcpyAsync(b->dSortQx.p, b->hSortQx.data(), ns * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        LGS_CUDA(c, cudaMemcpyAsync(b->dSortQy.p, b->hSortQy.data(), ns * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     if (nk) {
         LGS_CUDA(c, cudaMemcpyAsync(b->dAngles.p, b->hAngles.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(b->dRanges.p, b->hRanges.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -721,11 +959,12 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
             bb_hit_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(b->dUs.p + u0, b->dAngles.p, b->dRanges.p, b->dHits.p);
             LGS_LAUNCH_CHECK(c);
         }
-        for (size_t c0 = 0; c0 < b->chunks.size(); c0 += 65535) {
-            const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
-            bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dChunks.p + c0, b->dQlist.p,
-                                                                     b->dHits.p, g_lgs_edge_eps, b->dTab.p,
-                                                                     b->dFlags.p, b->dCounters.p);
+        const double eps = g_lgs_edge_eps;
+        for (size_t u0 = 0; u0 < b->us.size(); u0 += 65535) {
+            const unsigned nu = (unsigned)std::min<size_t>(65535, b->us.size() - u0);
+            bb_flagsearch_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(
+                b->dUs.p + u0, b->dQs.p, b->dHits.p, b->dSortFx.p, b->dSortQx.p, b->dSortFy.p, b->dSortQy.p,
+                eps, eps + 1e-7, b->dFlags.p, b->dCounters.p);
             LGS_LAUNCH_CHECK(c);
         }
         dim3 gridR((b->maxRoots + 127) / 128, n);
@@ -739,7 +978,25 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
         // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
         LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-        const int nFlag = b->hCounters.p[0];
+        int nFlag = b->hCounters.p[0];
+        b->slotPath = H >= 1 && nFlag <= kFlagInline && getenv("LGS_BB_TABLE") == nullptr;
+        if (!b->slotPath) {
+            // many near-edge points (or forced): the full per-query table, whose kernel flags them itself
+            LGS_CUDA(c, b->dTab.reserve(std::max<long long>(b->nTab, 1)));
+            LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, sizeof(int), c->stream));
+            const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
+            for (size_t c0 = 0; c0 < b->chunks.size(); c0 += 65535) {
+                const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
+                bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dChunks.p + c0, b->dQlist.p,
+                                                                         b->dHits.p, g_lgs_edge_eps, b->dTab.p,
+                                                                         b->dFlags.p, b->dCounters.p);
+                LGS_LAUNCH_CHECK(c);
+            }
+            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+            nFlag = b->hCounters.p[0];
+        }
+        b->nFlagRun = nFlag;
         std::fill(b->fixups.begin(), b->fixups.end(), 0);
         if (nFlag > kFlagCapBB)
             return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: %d near-edge points exceed the fix-up list", nFlag);
@@ -778,6 +1035,71 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     int deepBelow = kDeepUnrollBelow;
     if (const char* e = getenv("LGS_BB_WARP_BELOW")) warpBelow = atoi(e);     // tuning hooks
     if (const char* e = getenv("LGS_BB_DEEP_BELOW")) deepBelow = atoi(e);
+    const bool slots = b->slotPath;
+    const int nFlag = b->nFlagRun;
+    // One level: nLaunch threads / warps, the node count either exact (nDev == nullptr) or on the device.
+    auto launchLevel = [&](int h, int nLaunch, const int* nDev, long long expect) -> int {
+        LGS_CUDA(c, b->dScores[h].reserve(nLaunch));
+        Node* next = h > 0 ? b->dNodes[h - 1].p : nullptr;
+        const int nextCap = h > 0 ? (int)b->dNodes[h - 1].cap : 0;
+        int* nextCount = b->dCounters.p + 1 + h;
+        const int slotStride = (int)(b->dNodes[H - (H > 0 ? 1 : 0)].cap / 4);
+        if (slots && h > 0) LGS_CUDA(c, b->dSlot[h - 1].reserve(std::max(nextCap, 1)));
+        if (slots && h == H) {
+            LGS_CUDA(c, b->dSlotQT.reserve(std::max(slotStride, 1)));
+            bb_score_root_kernel<16><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
+                b->dQs.p, b->dUs.p, b->dHits.p, b->dFlags.p, nFlag, b->dExact.p, spanX, spanY, h, b->dNodes[h].p,
+                b->dScores[h].p, nLaunch, next, nextCap, nextCount, b->dSlotQT.p, b->dSlot[h - 1].p, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+            return LGS_OK;
+        }
+        const int2* tab = slots ? b->dTab2.p : b->dTab.p;
+        const int* slotIn = slots ? b->dSlot[h].p : nullptr;
+        int* slotOut = slots && h > 0 ? b->dSlot[h - 1].p : nullptr;
+        if (expect >= warpBelow && expect >= deepBelow)
+            bb_score_kernel<16><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
+                b->dQs.p, tab, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                nLaunch, nDev, next, nextCap, nextCount, b->dBest.p, slotIn, slotOut, slotStride);
+        else if (expect >= warpBelow)
+            bb_score_kernel<32><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
+                b->dQs.p, tab, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                nLaunch, nDev, next, nextCap, nextCount, b->dBest.p, slotIn, slotOut, slotStride);
+        else
+            bb_score_warp_kernel<<<(nLaunch + 3) / 4, 128, 0, c->stream>>>(
+                b->dQs.p, tab, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
+                nLaunch, nDev, next, nextCap, nextCount, b->dBest.p, slotIn, slotOut, slotStride);
+        LGS_LAUNCH_CHECK(c);
+        return LGS_OK;
+    };
+    // After the root level of the slot path: index rows for the survivors (slot count = children / 4).
+    auto launchSlotIndex = [&](int nSlotsLaunch) -> int {
+        const int slotStride = (int)(b->dNodes[H - 1].cap / 4);
+        if (slotStride == 0 || nSlotsLaunch == 0) return LGS_OK;
+        LGS_CUDA(c, b->dTab2.reserve((size_t)slotStride * std::max(b->maxUse, 1)));
+        dim3 gi((nSlotsLaunch + 127) / 128, (std::max(b->maxUse, 1) + 7) / 8);
+        bb_index_slots_kernel<<<gi, 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dHits.p, b->dSlotQT.p,
+                                                        b->dCounters.p + 1 + H, slotStride, b->dFlags.p, nFlag,
+                                                        b->dTab2.p);
+        LGS_LAUNCH_CHECK(c);
+        return LGS_OK;
+    };
+    auto finish = [&](int leafLaunch, const int* leafDev) -> int {   // winner, verification, replay
+        if (leafLaunch > 0) {
+            bb_leaf_rank_kernel<<<(leafLaunch + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafLaunch, leafDev, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+            bb_leaf_pick_kernel<<<(leafLaunch + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafLaunch, leafDev, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+        }
+        LevelViews lv;
+        for (int h = 0; h < kMaxLevels; ++h) lv.v[h] = LevelView{b->dNodes[h].p, b->dScores[h].p};
+        bb_verify_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p,
+                                                              b->forceReplay ? 1 : 0);
+        LGS_LAUNCH_CHECK(c);
+        bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p);
+        LGS_LAUNCH_CHECK(c);
+        return LGS_OK;
+    };
+
     if (spec) {
         for (int h = H; h >= 0; --h) {
             const long long expect = h == H ? b->totalRoots : b->hint[h];
@@ -785,43 +1107,22 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
             const int nMax = h == H ? b->totalRoots : (int)b->dNodes[h].cap;
             const int* nDev = h == H ? nullptr : b->dCounters.p + 2 + h;      // children of level h + 1
             if (nMax == 0) break;
-            LGS_CUDA(c, b->dScores[h].reserve(nMax));
             if (h > 0) {
                 const size_t want = (size_t)std::min<long long>(std::max<long long>(4LL * expect, 64), 1 << 16);
                 if (b->dNodes[h - 1].cap < want) LGS_CUDA(c, b->dNodes[h - 1].reserve(want));
             }
-            Node* next = h > 0 ? b->dNodes[h - 1].p : nullptr;
-            const int nextCap = h > 0 ? (int)b->dNodes[h - 1].cap : 0;
-            int* nextCount = b->dCounters.p + 1 + h;
-            if (expect >= warpBelow && expect >= deepBelow)
-                bb_score_kernel<16><<<(nMax + 127) / 128, 128, 0, c->stream>>>(
-                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nMax, nDev, next, nextCap, nextCount, b->dBest.p);
-            else if (expect >= warpBelow)
-                bb_score_kernel<32><<<(nMax + 127) / 128, 128, 0, c->stream>>>(
-                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nMax, nDev, next, nextCap, nextCount, b->dBest.p);
-            else
-                bb_score_warp_kernel<<<(nMax + 3) / 4, 128, 0, c->stream>>>(
-                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nMax, nDev, next, nextCap, nextCount, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
+            int rc = launchLevel(h, nMax, nDev, expect);
+            if (rc != LGS_OK) return rc;
+            if (slots && h == H) {
+                // survivors expected from the last run (+25 %), never more than the pool can hold
+                b->slotLaunch = (int)std::min<long long>((long long)(b->dNodes[H - 1].cap / 4),
+                                                         b->hint[H - 1] / 4 + b->hint[H - 1] / 16 + 256);
+                rc = launchSlotIndex(b->slotLaunch);
+                if (rc != LGS_OK) return rc;
+            }
         }
-        const int leafMax = H == 0 ? b->totalRoots : (int)b->dNodes[0].cap;
-        const int* leafDev = H == 0 ? nullptr : b->dCounters.p + 2;
-        if (leafMax > 0) {
-            bb_leaf_rank_kernel<<<(leafMax + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafMax, leafDev, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
-            bb_leaf_pick_kernel<<<(leafMax + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafMax, leafDev, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
-        }
-        LevelViews lvs;
-        for (int h = 0; h < kMaxLevels; ++h) lvs.v[h] = LevelView{b->dNodes[h].p, b->dScores[h].p};
-        bb_verify_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(b->dQs.p, n, H, lvs, b->dBest.p, b->dRes.p,
-                                                              b->forceReplay ? 1 : 0);
-        LGS_LAUNCH_CHECK(c);
-        bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(b->dQs.p, n, H, lvs, b->dBest.p, b->dRes.p);
-        LGS_LAUNCH_CHECK(c);
+        const int rc = finish(H == 0 ? b->totalRoots : (int)b->dNodes[0].cap, H == 0 ? nullptr : b->dCounters.p + 2);
+        if (rc != LGS_OK) return rc;
         LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, (2 + kMaxLevels) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         b->pendingValidate = true;
         b->ran = true;
@@ -831,28 +1132,13 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     for (int h = H; h >= 0; --h) {
         b->nodesPerLevel[h] = nNodes;
         if (nNodes == 0) break;
-        LGS_CUDA(c, b->dScores[h].reserve(nNodes));
         int* nextCount = b->dCounters.p + 1 + h;
         if (h > 0 && b->dNodes[h - 1].cap < (size_t)std::min<long long>(4LL * nNodes, 1 << 16))
             LGS_CUDA(c, b->dNodes[h - 1].reserve(std::min<long long>(4LL * nNodes, 1 << 16)));
         for (int attempt = 0; attempt < 2; ++attempt) {
             LGS_CUDA(c, cudaMemsetAsync(nextCount, 0, sizeof(int), c->stream));
-            if (nNodes >= warpBelow && nNodes >= deepBelow)
-                bb_score_kernel<16><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
-                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nNodes, nullptr, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
-                    nextCount, b->dBest.p);
-            else if (nNodes >= warpBelow)
-                bb_score_kernel<32><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
-                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nNodes, nullptr, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
-                    nextCount, b->dBest.p);
-            else
-                bb_score_warp_kernel<<<(nNodes + 3) / 4, 128, 0, c->stream>>>(
-                    b->dQs.p, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                    nNodes, nullptr, h > 0 ? b->dNodes[h - 1].p : nullptr, h > 0 ? (int)b->dNodes[h - 1].cap : 0,
-                    nextCount, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
+            const int rc = launchLevel(h, nNodes, nullptr, nNodes);
+            if (rc != LGS_OK) return rc;
             if (h == 0) break;
             LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p + 1 + h, nextCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             LGS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -862,23 +1148,16 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
             LGS_CUDA(c, b->dNodes[h - 1].reserve((size_t)want + want / 4));   // grow, redo this level
         }
         nNodes = h > 0 ? b->hCounters.p[1 + h] : 0;
+        if (slots && h == H && nNodes > 0) {
+            const int rc = launchSlotIndex(nNodes / 4);
+            if (rc != LGS_OK) return rc;
+        }
     }
     for (int h = 0; h <= H; ++h) b->gathers += b->nodesPerLevel[h];   // refined per query below
-    // Winner, verification, replay.
-    const int nLeaves = (int)b->nodesPerLevel[0];
-    if (nLeaves > 0) {
-        bb_leaf_rank_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, nullptr, b->dBest.p);
-        LGS_LAUNCH_CHECK(c);
-        bb_leaf_pick_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, nullptr, b->dBest.p);
-        LGS_LAUNCH_CHECK(c);
+    {
+        const int rc = finish((int)b->nodesPerLevel[0], nullptr);
+        if (rc != LGS_OK) return rc;
     }
-    LevelViews lv;
-    for (int h = 0; h < kMaxLevels; ++h) lv.v[h] = LevelView{b->dNodes[h].p, b->dScores[h].p};
-    bb_verify_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p,
-                                                          b->forceReplay ? 1 : 0);
-    LGS_LAUNCH_CHECK(c);
-    bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p);
-    LGS_LAUNCH_CHECK(c);
     b->ran = true;
     b->pendingValidate = false;
     for (int h = 0; h < kMaxLevels; ++h) b->hint[h] = b->nodesPerLevel[h];
@@ -894,7 +1173,7 @@ static int bb_finish(lgs_bb_batch* b) {
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
     b->pendingValidate = false;
     const int H = b->H;
-    bool ok = true;
+    bool ok = !b->slotPath || H < 1 || b->hCounters.p[1 + H] / 4 <= b->slotLaunch;   // every survivor got its row
     for (int h = 1; h <= H && ok; ++h)
         ok = (size_t)b->hCounters.p[1 + h] <= b->dNodes[h - 1].cap;   // no pool overflow
     if (!ok) return bb_run_impl(b, false);

@@ -199,3 +199,42 @@ def test_speculative_sync_free_runs_match_the_level_synchronous_run(ctx, submap,
         batch.run()
         assert [key(o) for o in batch.results()] == want
         assert batch.work()[0] == want_levels
+
+
+def test_bb_root_from_hit_points_with_a_few_near_edge_points(ctx, submap):
+    """With at most 8 near-edge points the root level is scored straight from the hit points and only
+    surviving (query, theta) rows get index rows; the flagged points still take the host's exact
+    tables.  Widen the guard band just enough to flag a handful of points and compare with the
+    reference; LGS_BB_TABLE=1 (full per-query table) must give the same answers."""
+    import os
+    from oracle import backend
+    R = backend()
+    qs = _queries(submap, 3, seed=33)
+    scans = capi.Scans([submap["angles"]] * len(qs), [s for s, _ in qs], [p for _, p in qs],
+                       range_min=0.02, range_max=30.0)
+    refs = [R.bb_match(submap["refmap"], submap["angles"], scan, init, pyramid=submap["refpyr"],
+                       thr=0.5, **_ref_kwargs(DEF)) for scan, init in qs]
+    seen_small = False
+    try:
+        for eps in (1e-9, 3e-7, 6e-7, 1.2e-6, 2.4e-6):
+            capi.set_edge_eps(eps)
+            for table in (False, True):
+                if table:
+                    os.environ["LGS_BB_TABLE"] = "1"
+                else:
+                    os.environ.pop("LGS_BB_TABLE", None)
+                batch = capi.BbBatch(ctx, **DEF)
+                batch.upload(scans, [submap["pyr"]] * len(qs), 0.5)
+                for rep in range(2):
+                    batch.run()
+                    outs = batch.results()
+                    for out, ref in zip(outs, refs):
+                        _same(out, ref)
+                nfix = sum(o.n_fixups for o in outs)
+                if not table and 1 <= nfix <= 8:
+                    seen_small = True
+                batch.close()
+    finally:
+        os.environ.pop("LGS_BB_TABLE", None)
+        capi.set_edge_eps(1e-9)
+    assert seen_small, "no guard band produced between 1 and 8 near-edge points"
