@@ -149,7 +149,7 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
                 v = make_int2(INT_MIN, f);      // sentinel: use the exact per-offset table f
             }
         }
-        __stcs(tab + d.tabBegin + idx, v);            // 1.3 GB written once, read back by a later launch: streaming
+        tab[d.tabBegin + idx] = v;
     }
 }
 
@@ -952,6 +952,10 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     if (n == 0) { b->ran = true; return LGS_OK; }
     LGS_CUDA(c, cudaSetDevice(c->device));
     LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, (2 + kMaxLevels) * sizeof(int), c->stream));
+    // Scoring the root level from the hit points pays off when several queries share a scan (the
+    // 16-byte hit points are then L2 hits); with one scan per query the 8-byte table rows are cheaper.
+    const bool wantSlots = H >= 1 && getenv("LGS_BB_TABLE") == nullptr &&
+                           ((size_t)n >= 4 * b->us.size() || getenv("LGS_BB_SLOTS") != nullptr);
     {
         const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
         for (size_t u0 = 0; u0 < b->us.size(); u0 += 65535) {
@@ -960,7 +964,7 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
             LGS_LAUNCH_CHECK(c);
         }
         const double eps = g_lgs_edge_eps;
-        for (size_t u0 = 0; u0 < b->us.size(); u0 += 65535) {
+        for (size_t u0 = 0; wantSlots && u0 < b->us.size(); u0 += 65535) {
             const unsigned nu = (unsigned)std::min<size_t>(65535, b->us.size() - u0);
             bb_flagsearch_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(
                 b->dUs.p + u0, b->dQs.p, b->dHits.p, b->dSortFx.p, b->dSortQx.p, b->dSortFy.p, b->dSortQy.p,
@@ -976,12 +980,17 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     const int spanX = b->spanX, spanY = b->spanY;
     {   // the one host round trip a speculative run keeps (the flag count is almost always 0)
         // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
-        LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-        int nFlag = b->hCounters.p[0];
-        b->slotPath = H >= 1 && nFlag <= kFlagInline && getenv("LGS_BB_TABLE") == nullptr;
+        int nFlag = 0;
+        b->slotPath = false;
+        if (wantSlots) {
+            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+            nFlag = b->hCounters.p[0];
+            b->slotPath = nFlag <= kFlagInline;
+        }
         if (!b->slotPath) {
-            // many near-edge points (or forced): the full per-query table, whose kernel flags them itself
+            // one scan per query, many near-edge points, or forced: the full per-query table, whose
+            // kernel flags the near-edge points itself
             LGS_CUDA(c, b->dTab.reserve(std::max<long long>(b->nTab, 1)));
             LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, sizeof(int), c->stream));
             const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
@@ -1047,7 +1056,7 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
         if (slots && h > 0) LGS_CUDA(c, b->dSlot[h - 1].reserve(std::max(nextCap, 1)));
         if (slots && h == H) {
             LGS_CUDA(c, b->dSlotQT.reserve(std::max(slotStride, 1)));
-            bb_score_root_kernel<16><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
+            bb_score_root_kernel<8><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
                 b->dQs.p, b->dUs.p, b->dHits.p, b->dFlags.p, nFlag, b->dExact.p, spanX, spanY, h, b->dNodes[h].p,
                 b->dScores[h].p, nLaunch, next, nextCap, nextCount, b->dSlotQT.p, b->dSlot[h - 1].p, b->dBest.p);
             LGS_LAUNCH_CHECK(c);

@@ -8,6 +8,18 @@ from my_lidar_graph_slam_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["table", "slots"])
+def bb_root_path(request, monkeypatch):
+    """Every test runs twice: with the library's own choice between the full per-query index table and
+    the root-from-hit-points path (queries here mostly have their own scan -> table), and with the
+    hit-point path forced."""
+    if request.param == "slots":
+        monkeypatch.setenv("LGS_BB_SLOTS", "1")
+    else:
+        monkeypatch.delenv("LGS_BB_SLOTS", raising=False)
+    yield request.param
+
 DEF = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0, scan_range_max=20.0,
            score_range_min=0.01, score_range_max=20.0)
 
@@ -219,6 +231,7 @@ def test_bb_root_from_hit_points_with_a_few_near_edge_points(ctx, submap):
         for eps in (1e-9, 3e-7, 6e-7, 1.2e-6, 2.4e-6):
             capi.set_edge_eps(eps)
             for table in (False, True):
+                os.environ["LGS_BB_SLOTS"] = "1"       # one scan per query here: force the hit-point root path
                 if table:
                     os.environ["LGS_BB_TABLE"] = "1"
                 else:
@@ -236,5 +249,6 @@ def test_bb_root_from_hit_points_with_a_few_near_edge_points(ctx, submap):
                 batch.close()
     finally:
         os.environ.pop("LGS_BB_TABLE", None)
+        os.environ.pop("LGS_BB_SLOTS", None)
         capi.set_edge_eps(1e-9)
     assert seen_small, "no guard band produced between 1 and 8 near-edge points"

@@ -7,6 +7,18 @@ from my_lidar_graph_slam_b200 import capi, largemap, synth
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["table", "slots"])
+def bb_root_path(request, monkeypatch):
+    """Every test runs twice: with the library's own choice between the full per-query index table and
+    the root-from-hit-points path (queries here mostly have their own scan -> table), and with the
+    hit-point path forced."""
+    if request.param == "slots":
+        monkeypatch.setenv("LGS_BB_SLOTS", "1")
+    else:
+        monkeypatch.delenv("LGS_BB_SLOTS", raising=False)
+    yield request.param
+
 # short usable range so that three bands of a ~900-row map are real windows (margins ~100 / ~230 rows)
 P = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=0.5, scan_range_max=4.0,
          score_range_min=0.01, score_range_max=4.0)
