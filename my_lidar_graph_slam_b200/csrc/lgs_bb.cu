@@ -26,8 +26,18 @@
 // per node and beam.  In exact arithmetic that is I0 + nx with I0 the index at nx = 0; all
 // rounding errors together stay below 1e-11 cells, so I0 + nx is exact unless the fractional
 // cell coordinate lies within the guard band of an edge.  Such (theta, beam) pairs are flagged
-// by bb_index_kernel and get per-offset index tables computed on the host with the CPU's
-// own expression (and glibc sin/cos, H5).
+// (bb_flagsearch_kernel / bb_index_kernel) and get per-offset index tables computed on the host
+// with the CPU's own expression (and glibc sin/cos, H5).
+//
+// Two ways to get a beam's cell at node offset (0, 0), chosen per run:
+//  * several queries share a scan (1 scan x 500 submaps): the root level, which visits every
+//    (query, theta), converts the shared hit points on the fly (bb_score_root_kernel) and only the
+//    surviving (query, theta) pairs get index rows (bb_index_slots_kernel); the near-edge flags come
+//    from a sorted-fraction search over the scan's queries instead of an all-pairs pass;
+//  * one scan per query, or more than kFlagInline flagged points: a full per-query index table
+//    (bb_index_kernel), read by every level.
+// After a batch object's first run the levels are launched speculatively over their pools'
+// capacities with device-side node counts (no host round trip per level) and validated afterwards.
 #include <cfloat>
 #include <cmath>
 

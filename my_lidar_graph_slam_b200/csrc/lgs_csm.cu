@@ -10,9 +10,10 @@
 //    operation order (IEEE add/mul/div intrinsics, never fused).  Only sin/cos can differ from
 //    glibc by an ulp, which can change floor() only within the edge guard band of a cell edge; such
 //    points are flagged and re-derived on the host with glibc before the result is accepted.
-//  * csm_sweep_kernel gives every hypothesis its own thread, which sums the gathered cells in
-//    beam order in double: the score is bit-identical to the CPU loop by construction, so no
-//    epsilon logic is needed anywhere.
+//  * the sweep (csm_sweep_rows_kernel: lanes = the x offsets of one window row, 4-5 rows per
+//    thread; csm_sweep_kernel: one thread per hypothesis, for small windows) sums the gathered
+//    cells of every hypothesis in beam order in double: the score is bit-identical to the CPU loop
+//    by construction, so no epsilon logic is needed anywhere.
 //  * csm_select_kernel computes each coarse block's fine maximum with first-visit argmax and
 //    then reproduces the CPU's pruned visit sequence: a parallel (score desc, visit asc)
 //    reduction when every coarse score bounds its block, otherwise a sequential replay of
