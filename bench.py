@@ -289,6 +289,14 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
            "ms_per_query_batch": dev_ms / steps, "ms_per_query_batch_e2e": 1e3 * e2e_s / steps,
            "nodes_scored_per_batch_rank0": int(sum(levels)), "nodes_per_level_rank0": levels,
            "gathered_cells_per_batch_rank0": int(gathers),
+           "roofline": {"bound": "latency (breadth-first levels of 1-40 k nodes; a node's ordered 1081-beam double "
+                                 "sum is a ~9 k-cycle dependent chain)",
+                        "achieved": float(gathers) * 8 / (dev_ms / steps * 1e-3) / 1e9, "unit": "GB/s",
+                        "peak": measured_peaks()[0], "frac": float(gathers) * 8 / (dev_ms / steps * 1e-3) / 1e9 / measured_peaks()[0],
+                        "algorithmic_bytes": "SURVEY 8(d): nodes scored x usable beams x 8 B (the gathered map cell; "
+                                             "index / hit-point traffic not credited), rank 0's share",
+                        "note": "root level 234 us, six deeper levels 348 us at their latency floor: DESIGN.md 3.3, "
+                                "profiles/r1_launches_c4_bb_slots.csv"},
            "loops_found": int((rec["found"] != 0).sum()), "best_submap": sharding.best_candidate(rec),
            "submaps_per_rank": int(nq), "submap_cells_rank0": int(cells),
            "pyramid_build_ms_rank0": pyr_ms,
@@ -470,6 +478,13 @@ def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_
            "precompute_ms": pyr_ms,
            "precompute_cells_levels_per_s": sum_over_ranks(float(owned_cells)) * 7 / (pyr_ms * 1e-3),
            "precompute_algorithmic_GBps": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": measured_peaks()[0] * world_size,
+                        "achieved": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9,
+                        "frac": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9 / (measured_peaks()[0] * world_size),
+                        "algorithmic_bytes": "16 B per cell per built level (6 levels); the whole build also copies "
+                                             "level 0 and clears the aprons",
+                        "note": "the level kernel alone: 5.0 TB/s = 76 % of the HBM peak (ncu, "
+                                "profiles/r1_kernels_v3.md section 2)"},
            "band_rows_rank0": [int(band.w0), int(band.w1)], "queries_rank0": int(len(mine)),
            "loop_queries_per_s": n_queries * steps / (dev_ms * 1e-3) if dev_ms > 0 else None,
            "loop_queries_per_s_e2e": n_queries * steps / e2e_s,
@@ -515,6 +530,13 @@ def run_c3(ctx, n_distinct, n_total, with_cpu):
            "cell_updates_per_scan": updates / done, "e2e": True,
            "h2d_bytes_per_scan": h2d / done,
            "algorithmic_GBps": updates * 16 / dt / 1e9}
+    peak, peak_src = measured_peaks()
+    out["roofline"] = {"bound": "hbm", "achieved": out["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                       "frac": out["algorithmic_GBps"] / peak, "peak_source": peak_src,
+                       "algorithmic_bytes": "16 B per cell update (read-modify-write of one double)",
+                       "note": "end to end incl. H2D; the binding limits are the order-dependent per-cell update "
+                               "chain (two IEEE double divisions, 283 cycles) and instruction issue of the touch "
+                               "pass, not HBM: DESIGN.md 3.4, profiles/r1_kernels_v3.md"}
     if with_cpu:
         try:
             from oracle import refapi as R
