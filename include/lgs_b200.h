@@ -247,6 +247,36 @@ int lgs_bb_match(lgs_ctx* ctx, const lgs_bb_params* params, const lgs_scan_batch
                  lgs_pyramid* const* pyramids, const double* norm_threshold,
                  lgs_match_result* out);
 
+/* ---- CostGreedyEndpoint: the tail both matchers run on the winning pose ------------------------
+ * Replaces CostGreedyEndpoint::Cost / ComputeGradient / ComputeCovariance
+ * (cost_function_greedy_endpoint.cpp:32-171) as called from
+ * scan_matcher_real_time_correlative.cpp:126-138 and scan_matcher_branch_bound.cpp:143-162.
+ * Fields are the constructor's arguments in the constructor's meaning
+ * (cost_function_greedy_endpoint.hpp:19-25; note that slam_launcher.cpp:70-72 passes
+ * StandardDeviation and ScalingFactor swapped -- a caller that wants the launcher's behaviour swaps
+ * them the same way).  Results are bit-identical to the CPU code. */
+typedef struct lgs_cost_params {
+    double usable_range_min, usable_range_max;
+    double hit_and_missed_dist;
+    double occupancy_threshold;
+    int kernel_size;                /* 0..7 */
+    double scaling_factor;
+    double standard_deviation;
+} lgs_cost_params;
+/* Cost() of n_poses sensor poses (poses[n_poses][3]); pose p uses scan pose_scan[p] of the batch
+ * (NULL: n_poses == n_scans, pose p uses scan p).  scans->sensor_pose is not read; range_min /
+ * range_max are ScanData::MinRange / MaxRange.  n_fixups (optional): near-edge beams re-derived
+ * on the host. */
+int lgs_cost_greedy_endpoint(lgs_ctx* ctx, const lgs_grid* grid, const lgs_cost_params* params,
+                             const lgs_scan_batch* scans, int n_poses, const int* pose_scan,
+                             const double* poses, double* cost, int* n_fixups);
+/* The whole tail for one best sensor pose per scan (best_sensor_pose[n_scans][3]):
+ * normalized_cost[m] = Cost / NumOfScans, covariance[m][9] = row-major ComputeCovariance.
+ * Either output may be NULL. */
+int lgs_cost_tail(lgs_ctx* ctx, const lgs_grid* grid, const lgs_cost_params* params,
+                  const lgs_scan_batch* scans, const double* best_sensor_pose,
+                  double* normalized_cost, double* covariance, int* n_fixups);
+
 #ifdef __cplusplus
 }
 #endif

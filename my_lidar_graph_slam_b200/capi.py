@@ -562,3 +562,55 @@ def unpin(ctx: Context, *arrays):
     for a in arrays:
         if a is not None and a.nbytes:
             lib().lgs_host_unpin(ctx.h, a.ctypes.data_as(vp))
+
+
+# ---- CostGreedyEndpoint: the matchers' tail ----------------------------------------------------
+class CostParams(C.Structure):
+    """lgs_cost_params: the CostGreedyEndpoint constructor's arguments, in its order."""
+    _fields_ = [("usable_range_min", C.c_double), ("usable_range_max", C.c_double),
+                ("hit_and_missed_dist", C.c_double), ("occupancy_threshold", C.c_double),
+                ("kernel_size", C.c_int), ("scaling_factor", C.c_double),
+                ("standard_deviation", C.c_double)]
+
+    @classmethod
+    def from_ctor_args(cls, args):
+        a = list(args)
+        return cls(a[0], a[1], a[2], a[3], int(a[4]), a[5], a[6])
+
+
+# slam_launcher.cpp:60-72 with launcher_settings_default.json:2-10 (passes StandardDeviation in the
+# scaling-factor slot and vice versa)
+DEFAULT_COST_ARGS = (0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0)
+
+SIGNATURES.update({
+    "lgs_cost_greedy_endpoint": (C.c_int, [vp, vp, C.POINTER(CostParams), C.POINTER(ScanBatch), C.c_int,
+                                           c_ip, c_dp, c_dp, c_ip]),
+    "lgs_cost_tail": (C.c_int, [vp, vp, C.POINTER(CostParams), C.POINTER(ScanBatch), c_dp, c_dp, c_dp, c_ip]),
+})
+
+
+def cost_greedy_endpoint(ctx: Context, grid: Grid, scans: Scans, poses, pose_scan=None,
+                         cost=DEFAULT_COST_ARGS):
+    """CostGreedyEndpoint::Cost at each of `poses` ([n][3]) -> (costs, n_fixups)."""
+    poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 3))
+    n = len(poses)
+    ps = None if pose_scan is None else np.ascontiguousarray(pose_scan, dtype=np.int32)
+    out = np.zeros(n, dtype=np.float64)
+    fix = C.c_int()
+    params = cost if isinstance(cost, CostParams) else CostParams.from_ctor_args(cost)
+    ctx.check(lib().lgs_cost_greedy_endpoint(ctx.h, grid.h, C.byref(params), C.byref(scans.c), n,
+                                             None if ps is None else ps.ctypes.data_as(c_ip),
+                                             _dptr(poses), _dptr(out), C.byref(fix)))
+    return out, fix.value
+
+
+def cost_tail(ctx: Context, grid: Grid, scans: Scans, best_sensor_poses, cost=DEFAULT_COST_ARGS):
+    """The matchers' tail per scan -> (normalised costs [n], covariances [n][3][3], n_fixups)."""
+    best = np.ascontiguousarray(np.asarray(best_sensor_poses, dtype=np.float64).reshape(scans.n, 3))
+    nc = np.zeros(scans.n, dtype=np.float64)
+    cov = np.zeros((scans.n, 3, 3), dtype=np.float64)
+    fix = C.c_int()
+    params = cost if isinstance(cost, CostParams) else CostParams.from_ctor_args(cost)
+    ctx.check(lib().lgs_cost_tail(ctx.h, grid.h, C.byref(params), C.byref(scans.c), _dptr(best), _dptr(nc),
+                                  _dptr(cov), C.byref(fix)))
+    return nc, cov, fix.value

@@ -63,6 +63,7 @@ int lgs_ctx_destroy(lgs_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     c->scratch.release();
     if (c->integ) { c->integ->release(); delete c->integ; }
+    lgs_cost_ws_destroy(c->cost);
     delete c;
     return LGS_OK;
 }

@@ -111,6 +111,10 @@ struct lgs_integ_ws {
     }
 };
 
+// Scratch of the cost-function entry points (lgs_cost.cu).
+struct lgs_cost_ws;
+void lgs_cost_ws_destroy(lgs_cost_ws* ws);
+
 struct lgs_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -120,6 +124,7 @@ struct lgs_ctx {
     char err[512] = {0};
     DevBuf<double> scratch;   // reusable device scratch (precompute intermediate)
     lgs_integ_ws* integ = nullptr;
+    lgs_cost_ws* cost = nullptr;
 };
 
 // Fractional-cell guard band (in cells): a projected coordinate closer than this to a cell

@@ -340,6 +340,74 @@ double orc_pixel_accurate_score(const double* level, const orc_geom* g, double u
     return sum;
 }
 
+/* ---- CostGreedyEndpoint (host tail of both matchers): cost_function_greedy_endpoint.cpp ------------- */
+
+/* cost = {usableRangeMin, usableRangeMax, hitAndMissedDist, occupancyThreshold, kernelSize,
+ *         scalingFactor, standardDeviation} in the constructor's order (:9-27). */
+/* CostGreedyEndpoint::Cost: cost_function_greedy_endpoint.cpp:32-110; ScanData::HitAndMissedPoint:
+ * sensor_data.hpp:177-198; GridMap::SquaredDistance: grid_map.hpp:895-902. */
+double orc_cost_greedy_endpoint(const double* grid, const orc_geom* g, const double* cost,
+                                const double* sensor_pose, int n, const double* angles,
+                                const double* ranges, double scan_min_range, double scan_max_range) {
+    const double usable_min = cost[0], usable_max = cost[1], dist = cost[2], occ_thr = cost[3];
+    const int ks = (int)cost[4];
+    const double scaling = cost[5], variance = cost[6] * cost[6];
+    const double min_range = usable_min > scan_min_range ? usable_min : scan_min_range;   /* :39-42 */
+    const double max_range = usable_max < scan_max_range ? usable_max : scan_max_range;
+    double value = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double r = ranges[i];
+        if (r >= max_range || r <= min_range) continue;                     /* :49-50 */
+        const double c = cos(sensor_pose[2] + angles[i]);
+        const double s = sin(sensor_pose[2] + angles[i]);
+        const double hx = sensor_pose[0] + r * c, hy = sensor_pose[1] + r * s;
+        const double mx = sensor_pose[0] + (r - dist) * c, my = sensor_pose[1] + (r - dist) * s;
+        const int hix = world_to_cell(hx, g->min_x, g->res), hiy = world_to_cell(hy, g->min_y, g->res);
+        const int mix = world_to_cell(mx, g->min_x, g->res), miy = world_to_cell(my, g->min_y, g->res);
+        const double d0 = (ks + 1) * g->res;                                /* :64-66 */
+        double min_sq = d0 * d0 + d0 * d0;
+        for (int ky = -ks; ky <= ks; ++ky)
+            for (int kx = -ks; kx <= ks; ++kx) {
+                const double hv = grid_value(grid, g->nx, g->ny, hix + kx, hiy + ky);
+                const double mv = grid_value(grid, g->nx, g->ny, mix + kx, miy + ky);
+                if (hv == 0.0 || mv == 0.0) continue;                       /* :81-83 */
+                if (hv < occ_thr || mv > occ_thr) continue;                 /* :89-91 */
+                const double dx = kx * g->res, dy = ky * g->res;
+                const double sq = dx * dx + dy * dy;
+                if (sq < min_sq) min_sq = sq;                               /* std::min(sq, min_sq) */
+            }
+        value -= exp(-0.5 * min_sq / variance);                             /* :103 */
+    }
+    value *= scaling;                                                       /* :107 */
+    return value;
+}
+
+/* The matchers' tail: scan_matcher_real_time_correlative.cpp:126-138 with ComputeGradient /
+ * ComputeCovariance (cost_function_greedy_endpoint.cpp:113-171). cov is row-major 3x3. */
+void orc_cost_tail(const double* grid, const orc_geom* g, const double* cost, const double* best_pose,
+                   int n, const double* angles, const double* ranges, double scan_min_range,
+                   double scan_max_range, double* normalized_cost, double* cov) {
+    const double diff[3] = {g->res, g->res, 1e-2};                          /* :120-121 */
+    double grad[3];
+    *normalized_cost = orc_cost_greedy_endpoint(grid, g, cost, best_pose, n, angles, ranges,
+                                                scan_min_range, scan_max_range) / (double)(size_t)n;
+    for (int a = 0; a < 3; ++a) {
+        double plus[3] = {best_pose[0], best_pose[1], best_pose[2]};
+        double minus[3] = {best_pose[0], best_pose[1], best_pose[2]};
+        for (int k = 0; k < 3; ++k) {                                       /* pose +/- delta, pose.hpp:60-74 */
+            plus[k] = best_pose[k] + (k == a ? diff[a] : 0.0);
+            minus[k] = best_pose[k] - (k == a ? diff[a] : 0.0);
+        }
+        const double d = orc_cost_greedy_endpoint(grid, g, cost, plus, n, angles, ranges, scan_min_range,
+                                                  scan_max_range) -
+                         orc_cost_greedy_endpoint(grid, g, cost, minus, n, angles, ranges, scan_min_range,
+                                                  scan_max_range);
+        grad[a] = 0.5 * d / diff[a];                                        /* :139-141 */
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) cov[3 * i + j] = i == j ? grad[i] * grad[j] + 0.01 : grad[i] * grad[j];   /* :161-166 */
+}
+
 /* ---- branch-and-bound matcher: scan_matcher_branch_bound.cpp:47-163 -------------------------------- */
 
 typedef struct { int x, y, t, h; } bb_node;

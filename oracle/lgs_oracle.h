@@ -60,6 +60,12 @@ double orc_pixel_accurate_score(const double* level, const orc_geom* g, double u
                                 double usable_max, const double* sensor_pose, int n,
                                 const double* angles, const double* ranges,
                                 double scan_min_range, double scan_max_range);
+double orc_cost_greedy_endpoint(const double* grid, const orc_geom* g, const double* cost,
+                                const double* sensor_pose, int n, const double* angles,
+                                const double* ranges, double scan_min_range, double scan_max_range);
+void orc_cost_tail(const double* grid, const orc_geom* g, const double* cost, const double* best_pose,
+                   int n, const double* angles, const double* ranges, double scan_min_range,
+                   double scan_max_range, double* normalized_cost, double* cov);
 int orc_bb_match(const double* pyramid, const orc_geom* g, int height_max, double range_x,
                  double range_y, double range_theta, double scan_range_max, double usable_min,
                  double usable_max, const double* init_pose, const double* rel, int n,

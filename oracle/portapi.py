@@ -76,6 +76,10 @@ def lib():
         L.orc_pixel_accurate_score.restype = C.c_double
         L.orc_pixel_accurate_score.argtypes = [c_dp, G, C.c_double, C.c_double, c_dp, C.c_int, c_dp,
                                                c_dp, C.c_double, C.c_double]
+        L.orc_cost_greedy_endpoint.restype = C.c_double
+        L.orc_cost_greedy_endpoint.argtypes = [c_dp, G, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double]
+        L.orc_cost_tail.argtypes = [c_dp, G, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double,
+                                    c_dp, c_dp]
         L.orc_bb_match.restype = C.c_int
         L.orc_bb_match.argtypes = [c_dp, G, C.c_int] + [C.c_double] * 6 + \
             [c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double, C.c_double, C.POINTER(PortMatch)]
@@ -307,6 +311,31 @@ def rtcsm_match(m: PortMap, angles, ranges, init_pose, *, low_res=5, range_x=1.0
                           low_res, range_x, range_y, range_theta, scan_range_max, _arr3(init_pose),
                           _arr3(rel), len(a), ap, rp, TINY if thr is None else thr, C.byref(out))
     return out
+
+
+DEFAULT_COST = (0.01, 20.0, 0.075, 0.1, 1.0, 0.05, 1.0)   # ctor order, as oracle/refapi.py
+
+
+def cost_greedy_endpoint(m: PortMap, sensor_pose, angles, ranges, *, scan_min_range=0.02,
+                         scan_max_range=30.0, cost=DEFAULT_COST) -> float:
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    return lib().orc_cost_greedy_endpoint(m.d.ctypes.data_as(c_dp), C.byref(m.geo), (C.c_double * 7)(*cost),
+                                          _arr3(sensor_pose), len(a), ap, rp, scan_min_range, scan_max_range)
+
+
+def host_tail(m: PortMap, best_sensor_pose, angles, ranges, *, scan_min_range=0.02, scan_max_range=30.0,
+              cost=DEFAULT_COST):
+    """(normalised cost, None, 3x3 covariance) of the matchers' host tail (refapi.host_tail's shape; the
+    estimated pose in the middle is not restated here)."""
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    nc = C.c_double()
+    cov = (C.c_double * 9)()
+    lib().orc_cost_tail(m.d.ctypes.data_as(c_dp), C.byref(m.geo), (C.c_double * 7)(*cost),
+                        _arr3(best_sensor_pose), len(a), ap, rp, scan_min_range, scan_max_range,
+                        C.byref(nc), cov)
+    return nc.value, None, np.array(cov).reshape(3, 3)
 
 
 def rtcsm_score_table(m: PortMap, pre: PortPre, use_coarse, low_res, scan_range_max, sensor_pose,

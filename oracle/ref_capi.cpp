@@ -399,6 +399,16 @@ void ref_host_tail(const RefMap* map, const double* cost, const double* bestSens
         for (int j = 0; j < 3; ++j) cov[3 * i + j] = c(i, j);
 }
 
+// CostGreedyEndpoint::Cost at an arbitrary sensor pose (cost_function_greedy_endpoint.cpp:32-110).
+double ref_cost_greedy_endpoint(const RefMap* map, const double* cost, const double* sensorPose, int n,
+                                const double* angles, const double* ranges, double scanMinRange,
+                                double scanMaxRange) {
+    auto cf = MakeCost(cost);
+    const double zero[3] = {0, 0, 0};
+    const auto scan = MakeScan(sensorPose, zero, n, angles, ranges, scanMinRange, scanMaxRange);
+    return cf->Cost(map->m, scan, RobotPose2D<double>(sensorPose[0], sensorPose[1], sensorPose[2]));
+}
+
 // Range filter + HitPoint + bounding box exactly as GridMapBuilder does it
 // (ComputeBoundingBoxAndScanPoints, grid_map_builder.cpp:335-380).  usable = {min, max}.
 int ref_hit_points(const double* robotPose, const double* rel, int n, const double* angles,

@@ -103,6 +103,8 @@ def lib():
                                                c_dp, c_dp, C.c_double, C.c_double]
         L.ref_host_tail.argtypes = [vp, c_dp, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_double,
                                     C.c_double, c_dp, c_dp, c_dp]
+        L.ref_cost_greedy_endpoint.restype = C.c_double
+        L.ref_cost_greedy_endpoint.argtypes = [vp, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double]
         _lib = L
     return _lib
 
@@ -340,6 +342,15 @@ def host_tail(m: RefMap, best_sensor_pose, angles, ranges, *, rel=(0.0, 0.0, 0.0
     lib().ref_host_tail(m.h, (C.c_double * 7)(*cost), _arr3(best_sensor_pose), _arr3(rel),
                         len(a), ap, rp, scan_min_range, scan_max_range, C.byref(nc), est, cov)
     return nc.value, tuple(est), np.array(cov).reshape(3, 3)
+
+
+def cost_greedy_endpoint(m: RefMap, sensor_pose, angles, ranges, *, scan_min_range=0.02,
+                         scan_max_range=30.0, cost=DEFAULT_COST) -> float:
+    """CostGreedyEndpoint::Cost at one sensor pose."""
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    return lib().ref_cost_greedy_endpoint(m.h, (C.c_double * 7)(*cost), _arr3(sensor_pose), len(a), ap, rp,
+                                          scan_min_range, scan_max_range)
 
 
 # ---- integration helpers ---------------------------------------------------------------------

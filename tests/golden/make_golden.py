@@ -125,10 +125,40 @@ def edge_scene():
                         bb_int=np.asarray(bb_i, dtype=np.int64), bb_f=np.asarray(bb_f))
 
 
+COST_SETS = [(0.01, 20.0, 0.075, 0.1, 1.0, 0.05, 1.0),      # launcher defaults as the launcher passes them
+             (0.01, 20.0, 0.075, 0.1, 1.0, 1.0, 0.05),      # the header's meaning of the last two
+             (0.5, 6.0, 0.1, 0.3, 2.0, 2.5, 0.08),
+             (0.01, 20.0, 0.05, 0.5, 0.0, 1.0, 0.05),       # kernel size 0
+             (0.01, 20.0, 0.075, 0.05, 3.0, 1.0, 0.1)]
+
+
+def cost_scene():
+    """CostGreedyEndpoint::Cost and the matchers' host tail on the latest map of scene_rooms."""
+    g = np.load(os.path.join(OUT, "scene_rooms.npz"))
+    angles, traj, scans = g["angles"], g["traj"], g["scans"]
+    b = R.RefBuilder()
+    for p, s in zip(traj[:12], scans[:12]):
+        b.append_scan(p, angles, s)
+    latest = b.latest_map()
+    rng = np.random.default_rng(21)
+    poses, which, costs, ncost, cov = [], [], [], [], []
+    for k in range(6, 18):
+        for _ in range(3):
+            pose = traj[k] + np.array([rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(-0.1, 0.1)])
+            poses.append(pose); which.append(k)
+            costs.append([R.cost_greedy_endpoint(latest, pose, angles, scans[k], cost=c) for c in COST_SETS])
+            tails = [R.host_tail(latest, pose, angles, scans[k], cost=c) for c in COST_SETS]
+            ncost.append([t[0] for t in tails]); cov.append([t[2] for t in tails])
+    np.savez_compressed(os.path.join(OUT, "scene_cost.npz"), poses=np.asarray(poses),
+                        scan=np.asarray(which, dtype=np.int32), cost_sets=np.asarray(COST_SETS),
+                        cost=np.asarray(costs), normalized=np.asarray(ncost), cov=np.asarray(cov))
+
+
 if __name__ == "__main__":
     primitives()
     scene()
     edge_scene()
+    cost_scene()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

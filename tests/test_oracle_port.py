@@ -114,6 +114,41 @@ def test_edge_scene_golden_order_dependent_results():
                                thr=float(g["thrs"][k]), **bb), g["bb_int"][k], g["bb_f"][k])
 
 
+def test_cost_function_golden():
+    """CostGreedyEndpoint::Cost / ComputeCovariance (the matchers' host tail), bit for bit."""
+    g, c = np.load(os.path.join(GOLD, "scene_rooms.npz")), np.load(os.path.join(GOLD, "scene_cost.npz"))
+    angles, traj, scans = g["angles"], g["traj"], g["scans"]
+    b = P.PortBuilder()
+    for p, s in zip(traj[:12], scans[:12]):
+        b.append_scan(p, angles, s)
+    latest = b.latest_map()
+    assert len(set(c["cost"][:, 0].tolist())) > 10 and np.all(c["cost"][:, 0] < 0.0)
+    for pose, k, want, wn, wc in zip(c["poses"], c["scan"], c["cost"], c["normalized"], c["cov"]):
+        for j, cs in enumerate(c["cost_sets"]):
+            assert P.cost_greedy_endpoint(latest, pose, angles, scans[k], cost=tuple(cs)) == want[j]
+            n, _, cov = P.host_tail(latest, pose, angles, scans[k], cost=tuple(cs))
+            assert n == wn[j] and np.array_equal(cov, wc[j])
+
+
+@needs_ref
+def test_port_cost_matches_reference_objects_randomised():
+    rng = np.random.default_rng(31)
+    dense = np.where(rng.random((128, 192)) < 0.5, np.round(rng.uniform(1e-3, 0.999, (128, 192)), 2), 0.0)
+    pm, rm = P.PortMap.from_dense(dense, -3.0, -2.0), R.RefMap.from_dense(dense, -3.0, -2.0)
+    angles = synth.beam_angles(91, 360.0)
+    for _ in range(40):
+        ranges = rng.uniform(0.0, 4.0, angles.shape)
+        pose = np.array([rng.uniform(-3.5, 3.5), rng.uniform(-2.5, 3.0), rng.uniform(-4, 4)])   # partly off the map
+        cs = (rng.uniform(0.0, 0.5), rng.uniform(2.0, 5.0), rng.uniform(0.02, 0.2), rng.uniform(0.05, 0.6),
+              float(rng.integers(0, 4)), rng.uniform(0.1, 3.0), rng.uniform(0.02, 1.0))
+        kw = dict(scan_min_range=float(rng.uniform(0, 0.3)), scan_max_range=float(rng.uniform(3, 6)), cost=cs)
+        assert P.cost_greedy_endpoint(pm, pose, angles, ranges, **kw) == \
+            R.cost_greedy_endpoint(rm, pose, angles, ranges, **kw)
+        n, _, cov = P.host_tail(pm, pose, angles, ranges, **kw)
+        rn, _, rcov = R.host_tail(rm, pose, angles, ranges, **kw)
+        assert n == rn and np.array_equal(cov, rcov)
+
+
 @needs_ref
 def test_port_matches_reference_objects_randomised():
     rng = np.random.default_rng(11)
