@@ -6,7 +6,8 @@
  * Boost is absent; in slam_launcher.cpp instantiate them with boost::property_tree::ptree and
  * pass the launcher's own CreateCostFunction (see INTEGRATION.md for the five-line patch).
  *
- * New settings keys (all optional): "Device" (int, default 0) in the matcher / detector group.
+ * New settings keys (all optional): "Device" (int, default 0) and "DeviceCost" (bool, default true)
+ * in the matcher / detector group.
  */
 #ifndef LGS_ADAPTERS_CREATE_CUDA_BACKENDS_HPP
 #define LGS_ADAPTERS_CREATE_CUDA_BACKENDS_HPP
@@ -22,6 +23,25 @@
 namespace LgsB200 {
 
 namespace Mapping = MyLidarGraphSlam::Mapping;
+
+/* The CostGreedyEndpoint constructor arguments exactly as CreateCostGreedyEndpoint passes them
+ * (slam_launcher.cpp:60-72: same keys, same defaults, and StandardDeviation / ScalingFactor in the
+ * positions the launcher puts them, which the constructor reads as scaling factor / standard
+ * deviation), for the adapters that evaluate the cost function on the device */
+template <typename Ptree>
+lgs_cost_params ReadCostGreedyEndpointParams(const Ptree& jsonSettings, const std::string& configGroup)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    lgs_cost_params p;
+    p.usable_range_min = config.get("UsableRangeMin", 0.01);
+    p.usable_range_max = config.get("UsableRangeMax", 50.0);
+    p.hit_and_missed_dist = config.get("HitAndMissedDist", 0.075);
+    p.occupancy_threshold = config.get("OccupancyThreshold", 0.1);
+    p.kernel_size = config.get("KernelSize", 1);
+    p.scaling_factor = config.get("StandardDeviation", 0.05);      /* constructor's 6th argument */
+    p.standard_deviation = config.get("ScalingFactor", 1.0);       /* constructor's 7th argument */
+    return p;
+}
 
 /* "ScanMatcherType": "RealTimeCorrelativeCuda" -- same keys and defaults as
  * launcher_settings_default.json:42-50 / slam_launcher.cpp:302-306 */
@@ -40,8 +60,12 @@ std::shared_ptr<Mapping::ScanMatcher> CreateScanMatcherRealTimeCorrelativeCuda(
     const std::string costConfigGroup =
         config.get("CostConfigGroup", std::string("CostGreedyEndpoint"));
     auto pCostFunc = createCostFunction(jsonSettings, costType, costConfigGroup);
-    return std::make_shared<Mapping::ScanMatcherRealTimeCorrelativeCuda>(
+    auto pMatcher = std::make_shared<Mapping::ScanMatcherRealTimeCorrelativeCuda>(
         pCostFunc, lowResolution, rangeX, rangeY, rangeTheta, scanRangeMax, device);
+    /* "DeviceCost" (default true): evaluate the tail (Cost / ComputeCovariance) on the device */
+    if (costType == "GreedyEndpoint" && config.get("DeviceCost", true))
+        pMatcher->UseDeviceCost(ReadCostGreedyEndpointParams(jsonSettings, costConfigGroup));
+    return pMatcher;
 }
 
 /* "LoopDetectorType": "BranchBoundCuda" -- reads the detector group
@@ -71,9 +95,12 @@ std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorBranchBoundCuda(
     const double usableRangeMax = score.template get<double>("UsableRangeMax");
 
     auto pCostFunc = createCostFunction(jsonSettings, costType, costGroup);
-    return std::make_shared<Mapping::LoopDetectorBranchBoundCuda>(
+    auto pDetector = std::make_shared<Mapping::LoopDetectorBranchBoundCuda>(
         usableRangeMin, usableRangeMax, pCostFunc, nodeHeightMax, rangeX, rangeY, rangeTheta,
         scanRangeMax, scoreThreshold, device);
+    if (costType == "GreedyEndpoint" && config.get("DeviceCost", true))
+        pDetector->UseDeviceCost(ReadCostGreedyEndpointParams(jsonSettings, costGroup));
+    return pDetector;
 }
 
 /* "LoopDetectorType": "RealTimeCorrelativeCuda" -- the detector group names its matcher group

@@ -41,6 +41,11 @@ public:
     void Detect(LoopDetectionQueryVector& loopDetectionQueries,
                 LoopDetectionResultVector& loopDetectionResults) override;
 
+    /* Evaluate the covariance of the accepted matches on the device from now on; `params` are the
+     * constructor arguments of the CostGreedyEndpoint this detector was given */
+    void UseDeviceCost(const lgs_cost_params& params)
+    { this->mCostParams = params; this->mDeviceCost = true; }
+
     /* Per-pair device results of the last Detect() (query-major, node-minor order) */
     const std::vector<lgs_match_result>& LastResults() const { return this->mLast; }
 
@@ -57,6 +62,8 @@ private:
     std::map<int, DeviceMap>      mDeviceMaps;
     std::vector<double>           mDense;
     std::vector<lgs_match_result> mLast;
+    bool                          mDeviceCost;
+    lgs_cost_params               mCostParams;
 };
 
 } /* namespace Mapping */

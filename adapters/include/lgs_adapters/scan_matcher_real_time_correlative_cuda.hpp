@@ -3,8 +3,10 @@
  * Drop-in replacement for MyLidarGraphSlam::Mapping::ScanMatcherRealTimeCorrelative
  * (mapping/scan_matcher_real_time_correlative.hpp:16-93) whose exhaustive (x, y, theta) sweep
  * runs on a B200 through the C ABI in include/lgs_b200.h.  Same constructor parameters, same
- * ScanMatcher interface, same results (winning indices bit-exact, hence identical poses); the
- * host tail (Cost, ComputeCovariance, MoveBackward) is the reference's own code.
+ * ScanMatcher interface, same results (winning indices bit-exact, hence identical poses).  The
+ * tail (Cost, ComputeCovariance) is the reference's own code on the host unless UseDeviceCost()
+ * hands the CostGreedyEndpoint parameters over, in which case it runs on the device too
+ * (lgs_cost_tail, bit-identical); MoveBackward stays the reference's.
  * Selected by the type string "RealTimeCorrelativeCuda" (see INTEGRATION.md). */
 #ifndef LGS_ADAPTERS_SCAN_MATCHER_REAL_TIME_CORRELATIVE_CUDA_HPP
 #define LGS_ADAPTERS_SCAN_MATCHER_REAL_TIME_CORRELATIVE_CUDA_HPP
@@ -49,11 +51,20 @@ public:
         const std::vector<RobotPose2D<double>>& initialPoses,
         const double normalizedScoreThreshold);
 
+    /* Evaluate the tail (normalised cost + covariance) on the device from now on.  `params` are
+     * the constructor arguments of the CostGreedyEndpoint this matcher was given (the class keeps
+     * them private, so the factory that built it passes them here as well). */
+    void UseDeviceCost(const lgs_cost_params& params)
+    { this->mCostParams = params; this->mDeviceCost = true; }
+
     /* Details of the last match (window indices, score, device counters) */
     const lgs_match_result& LastResult() const { return this->mLast; }
 
 private:
     void UploadMap(const GridMapType& gridMap);
+    /* Normalised cost + covariance of every (scan, best sensor pose) pair on the device */
+    void DeviceTail(const lgs_scan_batch& scans, const std::vector<double>& bestPoses,
+                    std::vector<double>& normalizedCosts, std::vector<double>& covariances);
 
     const CostFuncPtr   mCostFunc;
     const int           mLowResolution;
@@ -67,6 +78,8 @@ private:
     lgs_rtcsm_batch*    mBatch;
     std::vector<double> mDense;
     lgs_match_result    mLast;
+    bool                mDeviceCost;
+    lgs_cost_params     mCostParams;
 };
 
 } /* namespace Mapping */

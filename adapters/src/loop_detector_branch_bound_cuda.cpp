@@ -29,7 +29,8 @@ LoopDetectorBranchBoundCuda::LoopDetectorBranchBoundCuda(
     mCostFunc(costFunc),
     mParams { nodeHeightMax, rangeX, rangeY, rangeTheta, scanRangeMax,
               scoreUsableRangeMin, scoreUsableRangeMax },
-    mScoreThreshold(scoreThreshold), mCtx(nullptr), mBatch(nullptr)
+    mScoreThreshold(scoreThreshold), mCtx(nullptr), mBatch(nullptr),
+    mDeviceCost(false), mCostParams()
 {
     assert(scoreThreshold > 0.0);      /* loop_detector_branch_bound.cpp:20-21 */
     assert(scoreThreshold <= 1.0);
@@ -132,22 +133,61 @@ void LoopDetectorBranchBoundCuda::Detect(
         const auto& localMap = query.mLocalMapInfo.mMap;
         const auto& localMapNode = query.mLocalMapNode;
 
+        /* Accepted matches of this query (one local map) */
+        std::vector<const PoseGraph::Node*> foundNodes;
+        std::vector<double> best;
         for (const auto& node : query.mPoseGraphNodes) {
             const lgs_match_result& r = this->mLast[pairIdx++];
             if (!r.found)
                 continue;
-
             const auto& scanData = node.ScanData();
             const RobotPose2D<double> sensorPose =
                 Compound(node.Pose(), scanData->RelativeSensorPose());
-            const RobotPose2D<double> bestSensorPose {
-                sensorPose.mX + r.ix * r.step_x,
-                sensorPose.mY + r.iy * r.step_y,
-                sensorPose.mTheta + r.it * r.step_t };
+            foundNodes.push_back(&node);
+            best.insert(best.end(), { sensorPose.mX + r.ix * r.step_x,
+                                      sensorPose.mY + r.iy * r.step_y,
+                                      sensorPose.mTheta + r.it * r.step_t });
+        }
+        if (foundNodes.empty())
+            continue;
+
+        /* ComputeCovariance of every accepted match: on the device in one call against the local
+         * map's device grid (lgs_cost_tail), or the reference's own code on the host */
+        std::vector<double> covariances;
+        if (this->mDeviceCost) {
+            std::vector<int> tailBegin { 0 };
+            std::vector<double> tailAngles, tailRanges, tailMin, tailMax;
+            for (const auto* node : foundNodes) {
+                const auto& scanData = node->ScanData();
+                tailAngles.insert(tailAngles.end(), scanData->Angles().begin(), scanData->Angles().end());
+                tailRanges.insert(tailRanges.end(), scanData->Ranges().begin(), scanData->Ranges().end());
+                tailBegin.push_back(static_cast<int>(tailRanges.size()));
+                tailMin.push_back(scanData->MinRange());
+                tailMax.push_back(scanData->MaxRange());
+            }
+            const int numOfFound = static_cast<int>(foundNodes.size());
+            const lgs_scan_batch tailScans { numOfFound, tailBegin.data(), tailAngles.data(),
+                                             tailRanges.data(), best.data(), tailMin.data(), tailMax.data() };
+            covariances.resize(9 * foundNodes.size());
+            Check(this->mCtx, lgs_cost_tail(this->mCtx,
+                  this->mDeviceMaps.at(query.mLocalMapInfo.mIdx).mGrid, &this->mCostParams,
+                  &tailScans, best.data(), nullptr, covariances.data(), nullptr), "lgs_cost_tail");
+        }
+
+        for (std::size_t k = 0; k < foundNodes.size(); ++k) {
+            const auto& node = *foundNodes[k];
+            const auto& scanData = node.ScanData();
+            const RobotPose2D<double> bestSensorPose { best[3 * k], best[3 * k + 1], best[3 * k + 2] };
             const RobotPose2D<double> correspondingPose =
                 MoveBackward(bestSensorPose, scanData->RelativeSensorPose());
-            const Eigen::Matrix3d covarianceMatrix =
-                this->mCostFunc->ComputeCovariance(localMap, scanData, bestSensorPose);
+            Eigen::Matrix3d covarianceMatrix;
+            if (this->mDeviceCost) {
+                const double* c = covariances.data() + 9 * k;
+                covarianceMatrix << c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8];
+            } else {
+                covarianceMatrix =
+                    this->mCostFunc->ComputeCovariance(localMap, scanData, bestSensorPose);
+            }
 
             const RobotPose2D<double> relativePose =
                 InverseCompound(localMapNode.Pose(), correspondingPose);

@@ -29,7 +29,8 @@ ScanMatcherRealTimeCorrelativeCuda::ScanMatcherRealTimeCorrelativeCuda(
     const int device) :
     mCostFunc(costFunc), mLowResolution(lowResolution), mRangeX(rangeX),
     mRangeY(rangeY), mRangeTheta(rangeTheta), mScanRangeMax(scanRangeMax),
-    mCtx(nullptr), mGrid(nullptr), mCoarse(nullptr), mBatch(nullptr), mLast()
+    mCtx(nullptr), mGrid(nullptr), mCoarse(nullptr), mBatch(nullptr), mLast(),
+    mDeviceCost(false), mCostParams()
 {
     Check(nullptr, lgs_ctx_create(device, &this->mCtx), "lgs_ctx_create (a B200 is required)");
     const lgs_rtcsm_params params { lowResolution, rangeX, rangeY, rangeTheta, scanRangeMax };
@@ -75,6 +76,25 @@ void ScanMatcherRealTimeCorrelativeCuda::UploadMap(const GridMapType& gridMap)
           this->mCoarse), "lgs_precompute");
 }
 
+namespace {
+Eigen::Matrix3d ToMatrix(const double* c)
+{
+    Eigen::Matrix3d m;
+    m << c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8];
+    return m;
+}
+} /* namespace */
+
+void ScanMatcherRealTimeCorrelativeCuda::DeviceTail(
+    const lgs_scan_batch& scans, const std::vector<double>& bestPoses,
+    std::vector<double>& normalizedCosts, std::vector<double>& covariances)
+{
+    normalizedCosts.resize(scans.n_scans);
+    covariances.resize(9 * static_cast<std::size_t>(scans.n_scans));
+    Check(this->mCtx, lgs_cost_tail(this->mCtx, this->mGrid, &this->mCostParams, &scans,
+          bestPoses.data(), normalizedCosts.data(), covariances.data(), nullptr), "lgs_cost_tail");
+}
+
 ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
     const ScanMatchingQuery& queryInfo)
 {
@@ -111,6 +131,19 @@ ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
         sensorPose.mX + this->mLast.ix * this->mLast.step_x,
         sensorPose.mY + this->mLast.iy * this->mLast.step_y,
         sensorPose.mTheta + this->mLast.it * this->mLast.step_t };
+    if (this->mDeviceCost) {
+        /* The same tail on the device (cost_function_greedy_endpoint.cpp:32-171) */
+        const double scanMin = scanData->MinRange(), scanMax = scanData->MaxRange();
+        const lgs_scan_batch tailScans { 1, beamBegin, scanData->Angles().data(),
+                                         scanData->Ranges().data(), pose, &scanMin, &scanMax };
+        std::vector<double> normalizedCosts, covariances;
+        this->DeviceTail(tailScans, { bestSensorPose.mX, bestSensorPose.mY, bestSensorPose.mTheta },
+                         normalizedCosts, covariances);
+        return ScanMatchingSummary {
+            poseFound, normalizedCosts[0], initialPose,
+            MoveBackward(bestSensorPose, scanData->RelativeSensorPose()),
+            ToMatrix(covariances.data()) };
+    }
     const double costVal = this->mCostFunc->Cost(gridMap, scanData, bestSensorPose);
     const double normalizedCost = costVal / scanData->NumOfScans();
     const RobotPose2D<double> estimatedPose =
@@ -153,6 +186,29 @@ std::vector<ScanMatchingSummary> ScanMatcherRealTimeCorrelativeCuda::OptimizePos
     Check(this->mCtx, lgs_rtcsm_batch_run(this->mBatch, this->mGrid, this->mCoarse), "lgs_rtcsm_batch_run");
     Check(this->mCtx, lgs_rtcsm_batch_results(this->mBatch, this->mGrid, this->mCoarse, results.data()),
           "lgs_rtcsm_batch_results");
+
+    if (this->mDeviceCost) {
+        std::vector<double> best, scanMin, scanMax, normalizedCosts, covariances;
+        for (int k = 0; k < n; ++k) {
+            const lgs_match_result& r = results[k];
+            best.insert(best.end(), { sensorPoses[k].mX + r.ix * r.step_x,
+                                      sensorPoses[k].mY + r.iy * r.step_y,
+                                      sensorPoses[k].mTheta + r.it * r.step_t });
+            scanMin.push_back(scans[k]->MinRange());
+            scanMax.push_back(scans[k]->MaxRange());
+        }
+        const lgs_scan_batch tailScans { n, beamBegin.data(), angles.data(), ranges.data(), poses.data(),
+                                         scanMin.data(), scanMax.data() };
+        this->DeviceTail(tailScans, best, normalizedCosts, covariances);
+        for (int k = 0; k < n; ++k)
+            summaries.emplace_back(
+                results[k].found != 0, normalizedCosts[k], initialPoses[k],
+                MoveBackward(RobotPose2D<double>(best[3 * k], best[3 * k + 1], best[3 * k + 2]),
+                             scans[k]->RelativeSensorPose()),
+                ToMatrix(covariances.data() + 9 * k));
+        this->mLast = results.back();
+        return summaries;
+    }
 
     /* per match: the reference's own host tail (scan_matcher_real_time_correlative.cpp:118-144) */
     for (int k = 0; k < n; ++k) {

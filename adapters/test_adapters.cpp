@@ -228,10 +228,14 @@ int main() {
     /* cost function exactly as slam_launcher.cpp:60-72 builds it from the default settings */
     auto cost = std::make_shared<CostGreedyEndpoint>(0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0);
 
-    /* ---- front-end matcher ---- */
-    {
+    /* the same arguments for the device evaluation of the tail (lgs_cost_tail) */
+    const lgs_cost_params costParams { 0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0 };
+
+    /* ---- front-end matcher: tail on the host (reference code), then on the device ---- */
+    for (int deviceCost = 0; deviceCost < 2; ++deviceCost) {
         ScanMatcherRealTimeCorrelative ref(cost, 5, 1.0, 1.0, 0.6, 20.0);
         ScanMatcherRealTimeCorrelativeCuda gpu(cost, 5, 1.0, 1.0, 0.6, 20.0, 0);
+        if (deviceCost) gpu.UseDeviceCost(costParams);
         std::uniform_real_distribution<double> dxy(-0.3, 0.3), dth(-0.15, 0.15);
         double msMatchRef = 0.0, msMatchCuda = 0.0;
         for (int k = 0; k < 6; ++k) {
@@ -256,8 +260,8 @@ int main() {
                         ok ? "IDENTICAL" : "MISMATCH");
             failures += !ok;
         }
-        std::printf("rtcsm OptimizePose(query) per call (map upload + coarse map + sweep + host tail): "
-                    "reference %.2f ms, cuda %.2f ms\n", msMatchRef / 5, msMatchCuda / 5);
+        std::printf("rtcsm OptimizePose(query) per call (map upload + coarse map + sweep + %s tail): "
+                    "reference %.2f ms, cuda %.2f ms\n", deviceCost ? "device" : "host", msMatchRef / 5, msMatchCuda / 5);
     }
 
     /* ---- loop detector ---- */
@@ -268,6 +272,7 @@ int main() {
         LoopDetectorBranchBoundCuda gpu(0.01, 20.0, cost, 6, 2.0, 2.0, 1.0, 20.0, 0.6, 0);
         std::uniform_real_distribution<double> dxy(-0.5, 0.5), dth(-0.25, 0.25);
         for (int round = 0; round < 2; ++round) {   /* second round hits the device pyramid cache */
+            if (round == 1) gpu.UseDeviceCost(costParams);   /* ... and evaluates the covariances on the device */
             LoopDetectionQueryVector q1, q2;
             for (size_t m = 0; m + 1 < builder.LocalMaps().size() && m < 3; ++m) {
                 LocalMapInfo info = builder.LocalMapAt(static_cast<int>(m));
@@ -315,6 +320,7 @@ int main() {
     {
         auto refMatcher = std::make_shared<ScanMatcherRealTimeCorrelative>(cost, 5, 1.5, 1.5, 0.6, 20.0);
         auto gpuMatcher = std::make_shared<ScanMatcherRealTimeCorrelativeCuda>(cost, 5, 1.5, 1.5, 0.6, 20.0, 0);
+        gpuMatcher->UseDeviceCost(costParams);
         LoopDetectorRealTimeCorrelative ref(refMatcher, 0.55);
         LoopDetectorRealTimeCorrelativeCuda gpu(gpuMatcher, 0.55);
         std::uniform_real_distribution<double> dxy(-0.5, 0.5), dth(-0.2, 0.2);
@@ -338,8 +344,14 @@ int main() {
             q2.emplace_back(std::move(n2), info, mapNode);
         }
         LoopDetectionResultVector r1, r2;
+        const auto c0 = std::chrono::steady_clock::now();
         ref.Detect(q1, r1);
+        const auto c1 = std::chrono::steady_clock::now();
         gpu.Detect(q2, r2);
+        const auto c2 = std::chrono::steady_clock::now();
+        std::printf("correlative loop detector Detect (device tail): reference %.1f ms, cuda %.1f ms\n",
+                    std::chrono::duration<double, std::milli>(c1 - c0).count(),
+                    std::chrono::duration<double, std::milli>(c2 - c1).count());
         bool ok = r1.size() == r2.size();
         for (size_t i = 0; ok && i < r1.size(); ++i)
             ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) &&
@@ -368,8 +380,22 @@ int main() {
         auto d1 = LgsB200::CreateLoopDetectorBranchBoundCuda(t, "D", costFactory);
         auto d2 = LgsB200::CreateLoopDetectorRealTimeCorrelativeCuda(t, "D", costFactory);
         auto b = LgsB200::CreateGridMapBuilderCuda(t, "G");
-        const bool ok = m && d1 && d2 && b && b->LocalMaps().empty();
-        std::printf("factories: %s\n", ok ? "constructed" : "FAILED");
+        bool ok = m && d1 && d2 && b && b->LocalMaps().empty();
+        /* the factory-made matcher evaluates its tail on the device with the parameters it read from
+         * the settings; it must agree with the reference matcher holding the launcher-made cost object */
+        {
+            ScanMatcherRealTimeCorrelative ref(cost, 5, 1.0, 1.0, 0.6, 20.0);
+            const RobotPose2D<double> truth = path[57];
+            const auto scan = MakeScan(world, truth, 541, g);
+            const RobotPose2D<double> init(truth.mX + 0.11, truth.mY - 0.17, truth.mTheta + 0.05);
+            ScanMatchingQuery q1(GridMapType(builder.LatestMap()), scan, init);
+            ScanMatchingQuery q2(GridMapType(builder.LatestMap()), scan, init);
+            const ScanMatchingSummary a = ref.OptimizePose(q1);
+            const ScanMatchingSummary c = m->OptimizePose(q2);
+            ok = ok && a.mPoseFound == c.mPoseFound && SameBits(a.mNormalizedCost, c.mNormalizedCost) &&
+                 SamePose(a.mEstimatedPose, c.mEstimatedPose) && SameMat(a.mEstimatedCovariance, c.mEstimatedCovariance);
+        }
+        std::printf("factories: %s\n", ok ? "constructed, factory-made matcher IDENTICAL" : "FAILED");
         failures += !ok;
     }
     std::printf(failures ? "FAILED (%d)\n" : "ALL IDENTICAL\n", failures);
