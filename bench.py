@@ -561,6 +561,43 @@ def run_c3(ctx, n_distinct, n_total, with_cpu):
     return out
 
 
+def run_tail(ctx, grid, dense, min_x, min_y, angles, ranges, inits, results, with_cpu):
+    """the tail both matchers run on the winning pose (CostGreedyEndpoint cost +
+    finite-difference covariance = 7 cost evaluations per match), through the C ABI with host buffers."""
+    from my_lidar_graph_slam_b200 import capi
+    M = len(results)
+    best = np.array([[inits[k][0] + r.ix * r.step_x, inits[k][1] + r.iy * r.step_y, inits[k][2] + r.it * r.step_t]
+                     for k, r in enumerate(results)])
+    scans = capi.Scans([angles] * M, ranges, inits, range_min=0.02, range_max=30.0)
+    capi.pin(ctx, scans.angles, scans.ranges)
+    capi.cost_tail(ctx, grid, scans, best)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        nc, cov, fix = capi.cost_tail(ctx, grid, scans, best)
+    dt = (time.perf_counter() - t0) / reps
+    capi.unpin(ctx, scans.angles, scans.ranges)
+    out = {"tails_per_s": M / dt, "ms_per_call": 1e3 * dt, "matches_per_call": M,
+           "cost_evaluations_per_s": 7 * M / dt, "host_fixups": int(fix),
+           "note": "lgs_cost_tail end to end (host scans in, normalised cost + 3x3 covariance out), "
+                   "one launch of cost_kernel per call; bit-identical to CostGreedyEndpoint"}
+    if with_cpu:
+        try:
+            from oracle import refapi as R
+            if R.available():
+                rm = R.RefMap.from_dense(dense, min_x, min_y)
+                ns = min(M, 32)
+                t0 = time.perf_counter()
+                ref = [R.host_tail(rm, best[k], angles, ranges[k]) for k in range(ns)]
+                cdt = (time.perf_counter() - t0) / ns
+                same = sum(ref[k][0] == nc[k] and np.array_equal(ref[k][2], cov[k]) for k in range(ns))
+                out["cpu_reference"] = {"tails_per_s": 1.0 / cdt, "cores": 1, "kind": "reference",
+                                        "sample": f"{ns} tails; identical to the device on {same}/{ns}"}
+        except Exception as e:                                   # noqa: BLE001
+            out["cpu_reference"] = {"error": str(e)}
+    return out
+
+
 def run_b200(args, rank, world_size, local_rank):
     from my_lidar_graph_slam_b200 import capi
     dist = None
@@ -725,6 +762,8 @@ def run_b200(args, rank, world_size, local_rank):
                                               args.submaps, max(3, min(args.steps, 10)),
                                               world_size == 1 and not args.no_cpu_baseline))
         if rank == 0:
+            side("matcher_tail", lambda: run_tail(ctx, grid, dense, min_x, min_y, angles, ranges, inits,
+                                                  results_dev, not args.no_cpu_baseline))
             side("grid_integration", lambda: run_c3(ctx, 1024, args.c3_scans, not args.no_cpu_baseline))
         if args.c5_side > 0:
             side("large_map", lambda: run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks,

@@ -28,7 +28,7 @@ constexpr int kMaxKernel = 7;                       // window half size K (refer
 constexpr int kTab = (kMaxKernel + 1) * (kMaxKernel + 1);
 constexpr int kChunk = 2048;                        // beams folded per shared-memory round
 constexpr int kFlagCap = 1 << 16;
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 
 struct CostTables {                                 // kernel parameter (1 KB)
     double sq[kTab];                                // SquaredDistance for (|ky|, |kx|)
@@ -58,8 +58,10 @@ __device__ __forceinline__ double cellValue(const GridView& g, int x, int y) {
     return (x >= 0 && x < g.nx && y >= 0 && y < g.ny) ? __ldg(g.origin + (long long)y * g.pitch + x) : 0.0;
 }
 
-// grid = one block per evaluated pose (poseList maps block -> pose on the fix-up pass).
-template <bool PATCHED>
+// grid = one block per evaluated pose (poseList maps block -> pose on the fix-up pass).  KT >= 0 fixes
+// the window half size at compile time (the reference default 1: all 18 cell reads of a beam are
+// issued together instead of one dependent L2 round trip per window cell); KT < 0 reads it from tab.
+template <bool PATCHED, int KT>
 __global__ void __launch_bounds__(kThreads)
 cost_kernel(const CostPose* __restrict__ poses, const int* __restrict__ poseList,
             const double* __restrict__ angles, const double* __restrict__ ranges, GridView g,
@@ -107,16 +109,33 @@ cost_kernel(const CostPose* __restrict__ poses, const int* __restrict__ poseList
                 }
                 double best = tab.sqDefault;        // :64-66
                 int arg = -1;
-                const int K = tab.K;
-                for (int ky = -K; ky <= K; ++ky)
-                    for (int kx = -K; kx <= K; ++kx) {
-                        const double hv = cellValue(g, hx + kx, hy + ky);
-                        const double mv = cellValue(g, mx + kx, my + ky);
-                        if (hv == 0.0 || mv == 0.0) continue;               // :81-83
-                        if (hv < tab.occThr || mv > tab.occThr) continue;   // :89-91
-                        const int e = abs(ky) * (K + 1) + abs(kx);
-                        if (tab.sq[e] < best) { best = tab.sq[e]; arg = e; }
+                if constexpr (KT >= 0) {
+                    constexpr int W = 2 * KT + 1;
+                    double hv[W * W], mv[W * W];
+#pragma unroll
+                    for (int w = 0; w < W * W; ++w) {
+                        hv[w] = cellValue(g, hx + w % W - KT, hy + w / W - KT);
+                        mv[w] = cellValue(g, mx + w % W - KT, my + w / W - KT);
                     }
+#pragma unroll
+                    for (int w = 0; w < W * W; ++w) {                       // ky outer, kx inner (:68-69)
+                        const int e = abs(w / W - KT) * (KT + 1) + abs(w % W - KT);
+                        const bool ok = !(hv[w] == 0.0 || mv[w] == 0.0) &&              // :81-83
+                                        !(hv[w] < tab.occThr || mv[w] > tab.occThr);    // :89-91
+                        if (ok && tab.sq[e] < best) { best = tab.sq[e]; arg = e; }
+                    }
+                } else {
+                    const int K = tab.K;
+                    for (int ky = -K; ky <= K; ++ky)
+                        for (int kx = -K; kx <= K; ++kx) {
+                            const double hv = cellValue(g, hx + kx, hy + ky);
+                            const double mv = cellValue(g, mx + kx, my + ky);
+                            if (hv == 0.0 || mv == 0.0) continue;               // :81-83
+                            if (hv < tab.occThr || mv > tab.occThr) continue;   // :89-91
+                            const int e = abs(ky) * (K + 1) + abs(kx);
+                            if (tab.sq[e] < best) { best = tab.sq[e]; arg = e; }
+                        }
+                }
                 term = arg < 0 ? tab.exDefault : tab.ex[arg];
             }
             sTerm[j] = term;
@@ -135,15 +154,16 @@ cost_kernel(const CostPose* __restrict__ poses, const int* __restrict__ poseList
 
 // Persistent scratch of the cost entry points (grown on demand, freed with the context).
 struct lgs_cost_ws {
-    DevBuf<char> dBlob;
-    PinBuf<char> hBlob;
+    DevBuf<CostPose> dPoses;
+    PinBuf<CostPose> hPoses;
+    DevBuf<double> dBeams;                           // angles, then ranges
     DevBuf<double> dCost;
     PinBuf<double> hCost;
     DevBuf<CostFlag> dFlags;
     DevBuf<int> dFlagCount;
     PinBuf<int> hFlagCount;
     void release() {
-        dBlob.release(); hBlob.release(); dCost.release(); hCost.release(); dFlags.release();
+        dPoses.release(); hPoses.release(); dBeams.release(); dCost.release(); hCost.release(); dFlags.release();
         dFlagCount.release(); hFlagCount.release();
     }
 };
@@ -204,17 +224,15 @@ int lgs_cost_greedy_endpoint(lgs_ctx* c, const lgs_grid* grid, const lgs_cost_pa
 
     const int nScans = scans->n_scans;
     const size_t nBeams = (size_t)scans->beam_begin[nScans];
-    // one pinned blob, one H2D copy: [poses][angles][ranges]
-    const size_t posesBytes = (size_t)nPoses * sizeof(CostPose);
-    const size_t blobBytes = posesBytes + 2 * nBeams * sizeof(double);
-    LGS_CUDA(c, ws->hBlob.reserve(blobBytes));
-    LGS_CUDA(c, ws->dBlob.reserve(blobBytes));
+    LGS_CUDA(c, ws->hPoses.reserve(nPoses));
+    LGS_CUDA(c, ws->dPoses.reserve(nPoses));
+    LGS_CUDA(c, ws->dBeams.reserve(2 * nBeams + 1));
     LGS_CUDA(c, ws->dCost.reserve(nPoses));
     LGS_CUDA(c, ws->hCost.reserve(nPoses));
     LGS_CUDA(c, ws->dFlags.reserve(kFlagCap));
     LGS_CUDA(c, ws->dFlagCount.reserve(1));
     LGS_CUDA(c, ws->hFlagCount.reserve(1));
-    CostPose* hp = reinterpret_cast<CostPose*>(ws->hBlob.p);
+    CostPose* hp = ws->hPoses.p;
     for (int p = 0; p < nPoses; ++p) {
         const int s = poseScan ? poseScan[p] : p;
         if (s < 0 || s >= nScans) return lgs_fail(c, LGS_ERR_INVALID, "cost: pose %d names scan %d", p, s);
@@ -225,21 +243,31 @@ int lgs_cost_greedy_endpoint(lgs_ctx* c, const lgs_grid* grid, const lgs_cost_pa
                          std::min(params->usable_range_max, scanMax),
                          scans->beam_begin[s], scans->beam_begin[s + 1] - scans->beam_begin[s]};
     }
-    double* hAngles = reinterpret_cast<double*>(ws->hBlob.p + posesBytes);
-    double* hRanges = hAngles + nBeams;
-    std::memcpy(hAngles, scans->angles, nBeams * sizeof(double));
-    std::memcpy(hRanges, scans->ranges, nBeams * sizeof(double));
-    const CostPose* dPoses = reinterpret_cast<const CostPose*>(ws->dBlob.p);
-    const double* dAngles = reinterpret_cast<const double*>(ws->dBlob.p + posesBytes);
-    const double* dRanges = dAngles + nBeams;
+    // The beams go to the device straight from the caller's arrays (full speed when the caller page
+    // locked them with lgs_host_pin, driver staged otherwise); the call is synchronous, so the rare
+    // host fix-up below reads the same arrays.
+    const double* hAngles = scans->angles;
+    const double* hRanges = scans->ranges;
+    const CostPose* dPoses = ws->dPoses.p;
+    double* dAngles = ws->dBeams.p;
+    double* dRanges = dAngles + nBeams;
 
     GridView gv{grid->origin(), grid->min_x, grid->min_y, grid->res, grid->nx, grid->ny, grid->pitch,
                 grid->off_x, grid->off_y};
-    LGS_CUDA(c, cudaMemcpyAsync(ws->dBlob.p, ws->hBlob.p, blobBytes, cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(ws->dPoses.p, hp, nPoses * sizeof(CostPose), cudaMemcpyHostToDevice, c->stream));
+    if (nBeams > 0) {
+        LGS_CUDA(c, cudaMemcpyAsync(dAngles, hAngles, nBeams * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LGS_CUDA(c, cudaMemcpyAsync(dRanges, hRanges, nBeams * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
     LGS_CUDA(c, cudaMemsetAsync(ws->dFlagCount.p, 0, sizeof(int), c->stream));
-    cost_kernel<false><<<nPoses, kThreads, 0, c->stream>>>(dPoses, nullptr, dAngles, dRanges, gv, tab,
-                                                           g_lgs_edge_eps, nullptr, nullptr, ws->dFlags.p,
-                                                           ws->dFlagCount.p, ws->dCost.p);
+    if (tab.K == 1)
+        cost_kernel<false, 1><<<nPoses, kThreads, 0, c->stream>>>(dPoses, nullptr, dAngles, dRanges, gv, tab,
+                                                                  g_lgs_edge_eps, nullptr, nullptr, ws->dFlags.p,
+                                                                  ws->dFlagCount.p, ws->dCost.p);
+    else
+        cost_kernel<false, -1><<<nPoses, kThreads, 0, c->stream>>>(dPoses, nullptr, dAngles, dRanges, gv, tab,
+                                                                   g_lgs_edge_eps, nullptr, nullptr, ws->dFlags.p,
+                                                                   ws->dFlagCount.p, ws->dCost.p);
     LGS_LAUNCH_CHECK(c);
     LGS_CUDA(c, cudaMemcpyAsync(ws->hCost.p, ws->dCost.p, nPoses * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaMemcpyAsync(ws->hFlagCount.p, ws->dFlagCount.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -283,9 +311,9 @@ int lgs_cost_greedy_endpoint(lgs_ctx* c, const lgs_grid* grid, const lgs_cost_pa
         LGS_CUDA(c, cudaMemcpyAsync(dPatches, patches.data(), nFlag * sizeof(CostPatch), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(dList, poseList.data(), nRedo * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(dBegin, patchBegin.data(), (nRedo + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        cost_kernel<true><<<nRedo, kThreads, 0, c->stream>>>(dPoses, dList, dAngles, dRanges, gv, tab,
-                                                             g_lgs_edge_eps, dPatches, dBegin, nullptr,
-                                                             nullptr, ws->dCost.p);
+        cost_kernel<true, -1><<<nRedo, kThreads, 0, c->stream>>>(dPoses, dList, dAngles, dRanges, gv, tab,
+                                                                 g_lgs_edge_eps, dPatches, dBegin, nullptr,
+                                                                 nullptr, ws->dCost.p);
         LGS_LAUNCH_CHECK(c);
         LGS_CUDA(c, cudaMemcpyAsync(ws->hCost.p, ws->dCost.p, nPoses * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         LGS_CUDA(c, cudaFreeAsync(dPatches, c->stream));
