@@ -61,6 +61,13 @@ public:
     inline int LatestScanIdxMin() const { return this->mLatestScanIdxMin; }
     inline int LatestScanIdxMax() const { return this->mLatestScanIdxMax; }
 
+    /* The latest map as it sits on the device after AppendScan / AfterLoopClosure (bit-identical
+     * to LatestMap()), for ScanMatcherRealTimeCorrelativeCuda::OptimizePose(const lgs_grid*, ...);
+     * nullptr while the device copy holds something else (after ConstructGlobalMap, until the next
+     * AppendScan).  Valid until the next call that modifies the builder. */
+    const lgs_grid* DeviceLatestMap() const
+    { return this->mScratchIsLatest ? this->mDevScratch : nullptr; }
+
     /* Cell updates applied on the device so far (= BinaryBayesGridCell::Update calls of the CPU) */
     long long NumOfCellUpdates() const { return this->mNumOfUpdates; }
 
@@ -102,6 +109,7 @@ private:
     std::vector<double>       mHitXY;
     std::vector<double>       mDense;        /* page-locked download staging */
     bool                      mDensePinned;
+    bool                      mScratchIsLatest;   /* mDevScratch == mLatestMap */
     long long                 mNumOfUpdates;
 };
 

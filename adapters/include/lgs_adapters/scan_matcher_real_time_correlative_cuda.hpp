@@ -43,6 +43,16 @@ public:
                                      const RobotPose2D<double>& initialPose,
                                      const double normalizedScoreThreshold);
 
+    /* Same match against a map that is ALREADY on the device (GridMapBuilderCuda::DeviceLatestMap):
+     * no flattening and no upload of the map, one device-to-device copy instead.  Needs
+     * UseDeviceCost(), because there is no host map for the reference's cost function to read.
+     * The caller guarantees that `deviceMap` is not being integrated into during the call (in the
+     * reference: take it under the same lock as GetLatestPoseAndMap, lidar_graph_slam.cpp:306-315) */
+    ScanMatchingSummary OptimizePose(const lgs_grid* deviceMap,
+                                     const Sensor::ScanDataPtr<double>& scanData,
+                                     const RobotPose2D<double>& initialPose,
+                                     const double normalizedScoreThreshold);
+
     /* All (scan, initial pose) pairs against ONE map in one device batch (the map is uploaded and
      * its coarse map computed once): what LoopDetectorRealTimeCorrelativeCuda issues per query */
     std::vector<ScanMatchingSummary> OptimizePoses(
@@ -61,7 +71,13 @@ public:
     const lgs_match_result& LastResult() const { return this->mLast; }
 
 private:
+    void EnsureGrids(int nx, int ny, double minX, double minY, double res);
     void UploadMap(const GridMapType& gridMap);
+    /* sweep + tail against the map in mGrid / mCoarse; hostMap may be null with the device tail */
+    ScanMatchingSummary MatchUploaded(const GridMapType* hostMap,
+                                      const Sensor::ScanDataPtr<double>& scanData,
+                                      const RobotPose2D<double>& initialPose,
+                                      const double normalizedScoreThreshold);
     /* Normalised cost + covariance of every (scan, best sensor pose) pair on the device */
     void DeviceTail(const lgs_scan_batch& scans, const std::vector<double>& bestPoses,
                     std::vector<double>& normalizedCosts, std::vector<double>& covariances);

@@ -57,6 +57,7 @@ GridMapBuilderCuda::GridMapBuilderCuda(
     mDevLocal(nullptr),
     mDevScratch(nullptr),
     mDensePinned(false),
+    mScratchIsLatest(false),
     mNumOfUpdates(0)
 {
     Check(nullptr, lgs_ctx_create(device, &this->mCtx), "lgs_ctx_create (no usable B200: no CPU fallback)");
@@ -276,6 +277,7 @@ void GridMapBuilderCuda::UpdateLatestMap(const std::shared_ptr<PoseGraph>& poseG
     this->mLatestScanIdxMax = poseGraph->LatestNode().Index();
     this->ConstructMapFromScans(this->mLatestMap, poseGraph,
                                 this->mLatestScanIdxMin, this->mLatestScanIdxMax);
+    this->mScratchIsLatest = true;
 }
 
 void GridMapBuilderCuda::ConstructMapFromScans(
@@ -294,6 +296,7 @@ void GridMapBuilderCuda::ConstructMapFromScans(
     gridMap.Reset();
 
     /* all scans in one device batch, applied in node order like the CPU loop (:285-329) */
+    this->mScratchIsLatest = false;
     this->MirrorGeometry(this->mDevScratch, gridMap);
     this->IntegrateAndSync(this->mDevScratch, gridMap, 0, 0,
                            gridMap.NumOfGridCellsX() - 1, gridMap.NumOfGridCellsY() - 1);

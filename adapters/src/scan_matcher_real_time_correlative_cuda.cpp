@@ -46,29 +46,33 @@ ScanMatcherRealTimeCorrelativeCuda::~ScanMatcherRealTimeCorrelativeCuda()
     lgs_ctx_destroy(this->mCtx);
 }
 
-void ScanMatcherRealTimeCorrelativeCuda::UploadMap(const GridMapType& gridMap)
+void ScanMatcherRealTimeCorrelativeCuda::EnsureGrids(
+    const int nx, const int ny, const double minX, const double minY, const double res)
 {
-    const int nx = gridMap.NumOfGridCellsX(), ny = gridMap.NumOfGridCellsY();
     int curNx = -1, curNy = -1;
     double curMinX = 0.0, curMinY = 0.0, curRes = 0.0;
     if (this->mGrid != nullptr)
         lgs_grid_info(this->mGrid, &curNx, &curNy, &curMinX, &curMinY, &curRes, nullptr);
-    if (curNx != nx || curNy != ny || curMinX != gridMap.MinPos().mX ||
-        curMinY != gridMap.MinPos().mY || curRes != gridMap.Resolution()) {
+    if (curNx != nx || curNy != ny || curMinX != minX || curMinY != minY || curRes != res) {
         lgs_grid_destroy(this->mCoarse);
         lgs_grid_destroy(this->mGrid);
         /* The zero apron must cover the fine search window (H2: it is asymmetric) */
-        const double res = gridMap.Resolution();
         const int winX = static_cast<int>(std::ceil(0.5 * this->mRangeX / res));
         const int winY = static_cast<int>(std::ceil(0.5 * this->mRangeY / res));
         const int spanX = ((2 * winX) / this->mLowResolution + 1) * this->mLowResolution;
         const int spanY = ((2 * winY) / this->mLowResolution + 1) * this->mLowResolution;
         const int apron = std::max(spanX, spanY);
-        Check(this->mCtx, lgs_grid_create(this->mCtx, nx, ny, gridMap.MinPos().mX,
-              gridMap.MinPos().mY, res, apron, &this->mGrid), "lgs_grid_create");
-        Check(this->mCtx, lgs_grid_create(this->mCtx, nx, ny, gridMap.MinPos().mX,
-              gridMap.MinPos().mY, res, apron, &this->mCoarse), "lgs_grid_create");
+        Check(this->mCtx, lgs_grid_create(this->mCtx, nx, ny, minX, minY, res, apron, &this->mGrid),
+              "lgs_grid_create");
+        Check(this->mCtx, lgs_grid_create(this->mCtx, nx, ny, minX, minY, res, apron, &this->mCoarse),
+              "lgs_grid_create");
     }
+}
+
+void ScanMatcherRealTimeCorrelativeCuda::UploadMap(const GridMapType& gridMap)
+{
+    this->EnsureGrids(gridMap.NumOfGridCellsX(), gridMap.NumOfGridCellsY(), gridMap.MinPos().mX,
+                      gridMap.MinPos().mY, gridMap.Resolution());
     LgsB200::FlattenGridMap(gridMap, this->mDense);
     Check(this->mCtx, lgs_grid_upload(this->mGrid, this->mDense.data()), "lgs_grid_upload");
     /* ComputeCoarserMap (scan_matcher_real_time_correlative.cpp:148-153) on the device */
@@ -110,6 +114,36 @@ ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
     const double normalizedScoreThreshold)
 {
     this->UploadMap(gridMap);
+    return this->MatchUploaded(&gridMap, scanData, initialPose, normalizedScoreThreshold);
+}
+
+ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
+    const lgs_grid* deviceMap,
+    const Sensor::ScanDataPtr<double>& scanData,
+    const RobotPose2D<double>& initialPose,
+    const double normalizedScoreThreshold)
+{
+    if (!this->mDeviceCost) {
+        std::cerr << "lgs_b200: matching against a device-resident map needs UseDeviceCost() "
+                     "(there is no host map for the reference's cost function)" << std::endl;
+        std::abort();
+    }
+    int nx = 0, ny = 0;
+    double minX = 0.0, minY = 0.0, res = 0.0;
+    Check(this->mCtx, lgs_grid_info(deviceMap, &nx, &ny, &minX, &minY, &res, nullptr), "lgs_grid_info");
+    this->EnsureGrids(nx, ny, minX, minY, res);
+    Check(this->mCtx, lgs_grid_copy(deviceMap, this->mGrid), "lgs_grid_copy");
+    Check(this->mCtx, lgs_precompute(this->mCtx, this->mGrid, this->mLowResolution,
+          this->mCoarse), "lgs_precompute");
+    return this->MatchUploaded(nullptr, scanData, initialPose, normalizedScoreThreshold);
+}
+
+ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::MatchUploaded(
+    const GridMapType* hostMap,
+    const Sensor::ScanDataPtr<double>& scanData,
+    const RobotPose2D<double>& initialPose,
+    const double normalizedScoreThreshold)
+{
 
     const RobotPose2D<double> sensorPose =
         Compound(initialPose, scanData->RelativeSensorPose());
@@ -144,6 +178,7 @@ ScanMatchingSummary ScanMatcherRealTimeCorrelativeCuda::OptimizePose(
             MoveBackward(bestSensorPose, scanData->RelativeSensorPose()),
             ToMatrix(covariances.data()) };
     }
+    const GridMapType& gridMap = *hostMap;
     const double costVal = this->mCostFunc->Cost(gridMap, scanData, bestSensorPose);
     const double normalizedCost = costVal / scanData->NumOfScans();
     const RobotPose2D<double> estimatedPose =

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <string>
 #include <type_traits>
@@ -262,6 +263,43 @@ int main() {
         }
         std::printf("rtcsm OptimizePose(query) per call (map upload + coarse map + sweep + %s tail): "
                     "reference %.2f ms, cuda %.2f ms\n", deviceCost ? "device" : "host", msMatchRef / 5, msMatchCuda / 5);
+    }
+
+    /* ---- front-end matcher fed from the builder's device-resident latest map (no host round trip) ---- */
+    {
+        auto pg = std::make_shared<PoseGraph>();
+        GridMapBuilderCuda live(0.05, 64, 10, 6.0, 0.01, 20.0, 0.6, 0.45, 0);
+        ScanMatcherRealTimeCorrelative ref(cost, 5, 1.0, 1.0, 0.6, 20.0);
+        ScanMatcherRealTimeCorrelativeCuda gpu(cost, 5, 1.0, 1.0, 0.6, 20.0, 0);
+        gpu.UseDeviceCost(costParams);
+        std::uniform_real_distribution<double> dxy(-0.3, 0.3), dth(-0.15, 0.15);
+        double msRef = 0.0, msCuda = 0.0;
+        int bad = 0, frames = 0;
+        for (int k = 0; k < 16; ++k) {
+            pg->AppendNode(path[k], MakeScan(world, path[k], 541, g));
+            live.AppendScan(pg);
+            if (live.DeviceLatestMap() == nullptr) { ++bad; continue; }
+            const RobotPose2D<double> truth = path[k + 1];
+            const auto scan = MakeScan(world, truth, 541, g);
+            const RobotPose2D<double> init(truth.mX + dxy(g), truth.mY + dxy(g), truth.mTheta + dth(g));
+            ScanMatchingQuery q1(GridMapType(live.LatestMap()), scan, init);
+            const auto m0 = std::chrono::steady_clock::now();
+            const ScanMatchingSummary a = ref.OptimizePose(q1);
+            const auto m1 = std::chrono::steady_clock::now();
+            const ScanMatchingSummary b = gpu.OptimizePose(live.DeviceLatestMap(), scan, init,
+                                                           std::numeric_limits<double>::min());
+            const auto m2 = std::chrono::steady_clock::now();
+            if (k >= 4) { msRef += std::chrono::duration<double, std::milli>(m1 - m0).count();
+                          msCuda += std::chrono::duration<double, std::milli>(m2 - m1).count(); ++frames; }
+            bad += !(a.mPoseFound == b.mPoseFound && SameBits(a.mNormalizedCost, b.mNormalizedCost) &&
+                     SamePose(a.mInitialPose, b.mInitialPose) && SamePose(a.mEstimatedPose, b.mEstimatedPose) &&
+                     SameMat(a.mEstimatedCovariance, b.mEstimatedCovariance));
+        }
+        std::printf("rtcsm against the builder's device-resident latest map (16 frames): %s; per call reference %.2f ms, "
+                    "cuda %.3f ms\n", bad ? "MISMATCH" : "IDENTICAL", msRef / frames, msCuda / frames);
+        failures += bad != 0;
+        (void)live.ConstructGlobalMap(pg);
+        if (live.DeviceLatestMap() != nullptr) { std::printf("device latest map must be invalid after ConstructGlobalMap\n"); ++failures; }
     }
 
     /* ---- loop detector ---- */

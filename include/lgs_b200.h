@@ -92,6 +92,12 @@ int lgs_grid_create(lgs_ctx* ctx, int nx, int ny, double min_x, double min_y, do
 int lgs_grid_destroy(lgs_grid* g);
 int lgs_grid_upload(lgs_grid* g, const double* dense);       /* host [ny][nx] -> device */
 int lgs_grid_download(const lgs_grid* g, double* dense);     /* device -> host [ny][nx] */
+/* Device -> device: `dst` takes the geometry (size, placement, window) and the cells of `src`,
+ * keeping its own apron (which stays 0.0).  The grids may belong to different contexts of the same
+ * device; the copy runs on dst's stream after src's stream has drained.  This is the hand-over of
+ * the builder's device-resident latest map to the matcher (no host round trip of the map,
+ * lidar_graph_slam.cpp:99 / lidar_graph_slam_frontend.cpp:93-107). */
+int lgs_grid_copy(const lgs_grid* src, lgs_grid* dst);
 /* Large maps split into row bands (one per GPU): declare this grid to hold cells
  * [off_x, off_x + nx) x [off_y, off_y + ny) of a larger map whose cell (0, 0) has its lower-left
  * corner at (min_x, min_y).  World -> cell conversion stays floor((p - min) / res) of the WHOLE map,

@@ -458,6 +458,7 @@ class Geometry(C.Structure):
 SIGNATURES.update({
     "lgs_grid_resize": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]),
     "lgs_grid_clear": (C.c_int, [vp]),
+    "lgs_grid_copy": (C.c_int, [vp, vp]),
     "lgs_grid_integrate_scans": (C.c_int, [vp, vp, C.POINTER(HitBatch), C.c_double, C.c_double,
                                            C.POINTER(C.c_longlong)]),
     "lgs_ctx_integrate_fallback_cells": (C.c_longlong, [vp]),
@@ -508,6 +509,12 @@ def geometry_resize(geo: Geometry, bbox):
 def grid_resize(grid: Grid, geo: Geometry, shift_x: int, shift_y: int):
     grid.ctx.check(lib().lgs_grid_resize(grid.h, geo.nx, geo.ny, geo.min_x, geo.min_y, shift_x, shift_y))
     grid.nx, grid.ny, grid.min_x, grid.min_y = geo.nx, geo.ny, geo.min_x, geo.min_y
+
+
+def grid_copy(src: Grid, dst: Grid):
+    """Device -> device: dst takes src's geometry and cells (lgs_grid_copy)."""
+    dst.ctx.check(lib().lgs_grid_copy(src.h, dst.h))
+    dst.nx, dst.ny, dst.min_x, dst.min_y = src.nx, src.ny, src.min_x, src.min_y
 
 
 def grid_clear(grid: Grid):

@@ -179,6 +179,30 @@ int lgs_grid_download(const lgs_grid* g, double* dense) {
     return LGS_OK;
 }
 
+int lgs_grid_copy(const lgs_grid* src, lgs_grid* dst) {
+    if (!src || !dst || src == dst) return LGS_ERR_INVALID;
+    lgs_ctx* c = dst->ctx;
+    if (src->ctx->device != c->device)
+        return lgs_fail(c, LGS_ERR_INVALID, "grid_copy: grids live on devices %d and %d", src->ctx->device, c->device);
+    if (src->res != dst->res)
+        return lgs_fail(c, LGS_ERR_INVALID, "grid_copy: resolutions %g and %g differ", src->res, dst->res);
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    if (dst->nx != src->nx || dst->ny != src->ny) {
+        // new placement, everything unknown (shifts beyond any map size)
+        const int rc = lgs_grid_resize(dst, src->nx, src->ny, src->min_x, src->min_y, 1 << 30, 1 << 30);
+        if (rc != LGS_OK) return rc;
+    }
+    dst->min_x = src->min_x; dst->min_y = src->min_y;
+    dst->off_x = src->off_x; dst->off_y = src->off_y;
+    // everything queued on the source's stream (its last integration) must have landed
+    if (src->ctx != c) LGS_CUDA(c, cudaStreamSynchronize(src->ctx->stream));
+    if (src->nx > 0 && src->ny > 0)
+        LGS_CUDA(c, cudaMemcpy2DAsync(dst->origin(), (size_t)dst->pitch * sizeof(double), src->origin(),
+                                      (size_t)src->pitch * sizeof(double), (size_t)src->nx * sizeof(double),
+                                      src->ny, cudaMemcpyDeviceToDevice, c->stream));
+    return LGS_OK;
+}
+
 int lgs_grid_set_window(lgs_grid* g, int off_x, int off_y) {
     if (!g) return LGS_ERR_INVALID;
     if (off_x < 0 || off_y < 0) return lgs_fail(g->ctx, LGS_ERR_INVALID, "grid_set_window: negative offset");

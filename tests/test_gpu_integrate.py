@@ -1,4 +1,6 @@
 """GPU parity: occupancy-grid scan integration vs the reference's GridMapBuilder (every cell bit-exact)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -215,3 +217,27 @@ def test_very_long_rays_use_the_integer_division_path_and_split_chunks(ctx):
     assert capi.integrate_scans(ctx, grid, np.asarray(sensors), hits) == want
     assert want > 9 * 160 * 1500
     assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
+
+
+def test_grid_copy_between_contexts_takes_geometry_and_cells(ctx):
+    """lgs_grid_copy: the hand-over of a device-resident map (different context, different apron)."""
+    rng = np.random.default_rng(77)
+    dense = np.where(rng.random((70, 90)) < 0.4, rng.uniform(1e-3, 0.999, (70, 90)), 0.0)
+    src = capi.Grid.from_dense(ctx, dense, -1.5, 2.25, 0.05, apron=1)
+    other = capi.Context(0)
+    dst = capi.Grid(other, 10, 20, 0.0, 0.0, 0.05, apron=17)          # other size, placement and apron
+    capi.grid_copy(src, dst)
+    assert np.array_equal(dst.download(), dense)
+    info = [C.c_int(), C.c_int(), C.c_double(), C.c_double(), C.c_double(), C.c_int()]
+    other.check(capi.lib().lgs_grid_info(dst.h, *[C.byref(v) for v in info]))
+    assert [v.value for v in info] == [90, 70, -1.5, 2.25, 0.05, 17]
+    # the apron stays zero: a 5-cell window max over the copy equals the one over the source
+    assert np.array_equal(dst.precompute(5).download(), src.precompute(5).download())
+    dense2 = np.round(dense, 1)
+    src.upload(dense2)
+    capi.grid_copy(src, dst)                                           # same size: plain copy
+    assert np.array_equal(dst.download(), dense2)
+    bad = capi.Grid(other, 90, 70, -1.5, 2.25, 0.1, apron=1)
+    with pytest.raises(capi.LgsError):
+        capi.grid_copy(src, bad)                                       # resolution mismatch
+    other.close()
