@@ -253,6 +253,30 @@ int lgs_bb_match(lgs_ctx* ctx, const lgs_bb_params* params, const lgs_scan_batch
                  lgs_pyramid* const* pyramids, const double* norm_threshold,
                  lgs_match_result* out);
 
+/* ---- exhaustive grid-search matcher ------------------------------------------------------------
+ * Replaces ScanMatcherGridSearch::OptimizePose (scan_matcher_grid_search.cpp:45-114) with
+ * ScorePixelAccurate::Score (score_function_pixel_accurate.cpp:19-76), the matcher behind
+ * LoopDetectorGridSearch (loop_detector_grid_search.cpp:26-118).  Offsets are ACCUMULATED like the
+ * reference's loops (`for (d = -range / 2; d <= range / 2; d += step)`), visit order y, x, theta,
+ * first strictly greater score wins.  Winner and score are bit-identical to the CPU code. */
+typedef struct lgs_gs_params {
+    double range_x, range_y, range_theta;   /* mRangeX, mRangeY, mRangeTheta */
+    double step_x, step_y, step_theta;      /* mStepX, mStepY, mStepTheta    */
+    double score_range_min;                 /* ScorePixelAccurate::mUsableRangeMin */
+    double score_range_max;                 /* ScorePixelAccurate::mUsableRangeMax */
+} lgs_gs_params;
+/* Query q = scan q of the batch (sensor_pose = Compound(initialPose, RelativeSensorPose())) against
+ * grids[q].  Results: found, ix / iy / it = LOOP COUNTERS of the winning dx / dy / dt (-1 if not
+ * found), win_x / win_y / win_t = the three loop lengths, score = winning score.  The winning offset
+ * itself is lgs_gs_offsets(...)[counter]; the pose is sensor_pose + offset.  score_table (optional,
+ * one query only): [win_t][win_y][win_x] scores of every hypothesis. */
+int lgs_gs_match(lgs_ctx* ctx, const lgs_gs_params* params, const lgs_scan_batch* scans,
+                 const lgs_grid* const* grids, const double* norm_threshold, lgs_match_result* out,
+                 double* score_table);
+/* The offsets the reference's accumulating loop visits for (range, step): n values, the first
+ * min(n, cap) written to out (may be NULL).  Host arithmetic only. */
+int lgs_gs_offsets(double range, double step, double* out, int cap, int* n);
+
 /* ---- CostGreedyEndpoint: the tail both matchers run on the winning pose ------------------------
  * Replaces CostGreedyEndpoint::Cost / ComputeGradient / ComputeCovariance
  * (cost_function_greedy_endpoint.cpp:32-171) as called from

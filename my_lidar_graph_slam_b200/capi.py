@@ -621,3 +621,52 @@ def cost_tail(ctx: Context, grid: Grid, scans: Scans, best_sensor_poses, cost=DE
     ctx.check(lib().lgs_cost_tail(ctx.h, grid.h, C.byref(params), C.byref(scans.c), _dptr(best), _dptr(nc),
                                   _dptr(cov), C.byref(fix)))
     return nc, cov, fix.value
+
+
+# ---- exhaustive grid-search matcher ------------------------------------------------------------
+class GsParams(C.Structure):
+    _fields_ = [("range_x", C.c_double), ("range_y", C.c_double), ("range_theta", C.c_double),
+                ("step_x", C.c_double), ("step_y", C.c_double), ("step_theta", C.c_double),
+                ("score_range_min", C.c_double), ("score_range_max", C.c_double)]
+
+
+SIGNATURES.update({
+    "lgs_gs_match": (C.c_int, [vp, C.POINTER(GsParams), C.POINTER(ScanBatch), C.POINTER(vp), c_dp,
+                               C.POINTER(MatchResult), c_dp]),
+    "lgs_gs_offsets": (C.c_int, [C.c_double, C.c_double, c_dp, C.c_int, c_ip]),
+})
+
+
+def gs_offsets(rng: float, step: float) -> np.ndarray:
+    """Offsets of the reference's accumulating loop for (range, step)."""
+    n = C.c_int()
+    rc = lib().lgs_gs_offsets(rng, step, None, 0, C.byref(n))
+    if rc != 0:
+        raise LgsError(f"lgs_gs_offsets({rng}, {step}) -> {rc}")
+    out = np.zeros(n.value, dtype=np.float64)
+    lib().lgs_gs_offsets(rng, step, _dptr(out), n.value, C.byref(n))
+    return out
+
+
+def gs_match(ctx: Context, scans: Scans, grids, *, range_x=2.0, range_y=2.0, range_theta=0.5, step_x=0.05,
+             step_y=0.05, step_theta=0.005, score_range_min=0.01, score_range_max=20.0, norm_threshold=0.5,
+             want_table=False):
+    """ScanMatcherGridSearch for every scan of the batch against grids[q] -> list of MatchResult
+    (+ the [nT][nY][nX] score table of a single query when want_table)."""
+    assert len(grids) == scans.n
+    params = GsParams(range_x, range_y, range_theta, step_x, step_y, step_theta, score_range_min,
+                      score_range_max)
+    handles = (vp * max(scans.n, 1))(*[g.h for g in grids])
+    thr = None if norm_threshold is None else np.ascontiguousarray(
+        np.broadcast_to(np.asarray(norm_threshold, dtype=np.float64), (scans.n,)))
+    out = (MatchResult * max(scans.n, 1))()
+    table = None
+    if want_table:
+        dims = [len(gs_offsets(range_theta, step_theta)), len(gs_offsets(range_y, step_y)),
+                len(gs_offsets(range_x, step_x))]
+        table = np.zeros(dims, dtype=np.float64)
+    ctx.check(lib().lgs_gs_match(ctx.h, C.byref(params), C.byref(scans.c), handles,
+                                 None if thr is None else _dptr(thr), out,
+                                 None if table is None else _dptr(table)))
+    res = [out[i] for i in range(scans.n)]
+    return (res, table) if want_table else res

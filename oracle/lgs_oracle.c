@@ -408,6 +408,56 @@ void orc_cost_tail(const double* grid, const orc_geom* g, const double* cost, co
         for (int j = 0; j < 3; ++j) cov[3 * i + j] = i == j ? grad[i] * grad[j] + 0.01 : grad[i] * grad[j];   /* :161-166 */
 }
 
+/* ---- grid-search matcher: scan_matcher_grid_search.cpp:45-114 --------------------------------------- */
+
+/* Exhaustive search with ACCUMULATED offsets (dy += sy, ...), loop order y, x, theta, strict ">".
+ * out->ix / iy / it are the loop counters of the winner, out->win_x / win_y / win_t the loop lengths. */
+int orc_gs_match(const double* grid, const orc_geom* g, double range_x, double range_y, double range_theta,
+                 double step_x, double step_y, double step_theta, double usable_min, double usable_max,
+                 const double* init_pose, const double* rel, int n, const double* angles,
+                 const double* ranges, double scan_min_range, double scan_max_range,
+                 double norm_threshold, orc_match* out) {
+    double sensor[3];
+    orc_compound(init_pose, rel, sensor);                                   /* :55-56 */
+    const double rx = range_x / 2.0, ry = range_y / 2.0, rt = range_theta / 2.0;   /* :59-61 */
+    const double threshold = norm_threshold * (double)(size_t)n;            /* :67-68 */
+    double score_max = threshold;
+    memset(out, 0, sizeof(*out));
+    out->ix = out->iy = out->it = -1;
+    out->best_sensor_pose[0] = sensor[0]; out->best_sensor_pose[1] = sensor[1];
+    out->best_sensor_pose[2] = sensor[2];                                   /* :71 */
+    long long scored = 0;
+    int ny = 0;
+    for (double dy = -ry; dy <= ry; dy += step_y, ++ny) {                   /* :74-76 */
+        int nx = 0;
+        for (double dx = -rx; dx <= rx; dx += step_x, ++nx) {
+            int nt = 0;
+            for (double dt = -rt; dt <= rt; dt += step_theta, ++nt) {
+                const double pose[3] = {sensor[0] + dx, sensor[1] + dy, sensor[2] + dt};
+                const double s = orc_pixel_accurate_score(grid, g, usable_min, usable_max, pose, n, angles,
+                                                          ranges, scan_min_range, scan_max_range);
+                ++scored;
+                if (s > score_max) {                                        /* :85-88 */
+                    score_max = s;
+                    out->ix = nx; out->iy = ny; out->it = nt;
+                    out->best_sensor_pose[0] = pose[0]; out->best_sensor_pose[1] = pose[1];
+                    out->best_sensor_pose[2] = pose[2];
+                }
+            }
+            out->win_t = nt;
+        }
+        out->win_x = nx;
+    }
+    out->win_y = ny;
+    out->found = score_max > threshold;                                     /* :94 */
+    out->step_x = step_x; out->step_y = step_y; out->step_t = step_theta;
+    out->score = orc_pixel_accurate_score(grid, g, usable_min, usable_max, out->best_sensor_pose, n, angles,
+                                          ranges, scan_min_range, scan_max_range);
+    out->sensor_pose[0] = sensor[0]; out->sensor_pose[1] = sensor[1]; out->sensor_pose[2] = sensor[2];
+    out->n_scored = scored;
+    return 0;
+}
+
 /* ---- branch-and-bound matcher: scan_matcher_branch_bound.cpp:47-163 -------------------------------- */
 
 typedef struct { int x, y, t, h; } bb_node;

@@ -66,6 +66,11 @@ double orc_cost_greedy_endpoint(const double* grid, const orc_geom* g, const dou
 void orc_cost_tail(const double* grid, const orc_geom* g, const double* cost, const double* best_pose,
                    int n, const double* angles, const double* ranges, double scan_min_range,
                    double scan_max_range, double* normalized_cost, double* cov);
+int orc_gs_match(const double* grid, const orc_geom* g, double range_x, double range_y, double range_theta,
+                 double step_x, double step_y, double step_theta, double usable_min, double usable_max,
+                 const double* init_pose, const double* rel, int n, const double* angles,
+                 const double* ranges, double scan_min_range, double scan_max_range,
+                 double norm_threshold, orc_match* out);
 int orc_bb_match(const double* pyramid, const orc_geom* g, int height_max, double range_x,
                  double range_y, double range_theta, double scan_range_max, double usable_min,
                  double usable_max, const double* init_pose, const double* rel, int n,

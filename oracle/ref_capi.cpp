@@ -26,6 +26,7 @@
 #include "my_lidar_graph_slam/mapping/loop_detector_real_time_correlative.hpp"
 #include "my_lidar_graph_slam/mapping/pose_graph.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_grid_search.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_real_time_correlative.hpp"
 #include "my_lidar_graph_slam/mapping/score_function_pixel_accurate.hpp"
 #include "my_lidar_graph_slam/util.hpp"
@@ -365,6 +366,69 @@ int ref_bb_match(const RefMap* map, RefPre* const* pyr, int nodeHeightMax, doubl
     sf->Score(maps.at(0), scan,
               RobotPose2D<double>(out->bestSensorPose[0], out->bestSensorPose[1],
                                   out->bestSensorPose[2]), sum);
+    out->score = sum.mScore;
+    return 0;
+}
+
+// ScanMatcherGridSearch::OptimizePose (scan_matcher_grid_search.cpp:45-114).  ix / iy / it are the
+// loop counters of the winning dx / dy / dt (recovered by replaying the reference's own accumulating
+// loops, :74-76); winX / winY / winT receive the numbers of steps of the three loops.
+int ref_gs_match(const RefMap* map, double rangeX, double rangeY, double rangeTheta, double stepX,
+                 double stepY, double stepTheta, double scoreRangeMin, double scoreRangeMax,
+                 const double* cost, const double* initPose, const double* rel, int n,
+                 const double* angles, const double* ranges, double scanMinRange, double scanMaxRange,
+                 double normThreshold, RefMatchResult* out) {
+    auto sf = std::make_shared<ScorePixelAccurate>(scoreRangeMin, scoreRangeMax);
+    ScanMatcherGridSearch gs(sf, MakeCost(cost), rangeX, rangeY, rangeTheta, stepX, stepY, stepTheta);
+    const auto scan = MakeScan(initPose, rel, n, angles, ranges, scanMinRange, scanMaxRange);
+    const RobotPose2D<double> init(initPose[0], initPose[1], initPose[2]);
+    const ScanMatchingSummary s = gs.OptimizePose(map->m, scan, init, normThreshold);
+
+    const RobotPose2D<double> sensorPose = Compound(init, scan->RelativeSensorPose());
+    const RobotPose2D<double> best = Compound(s.mEstimatedPose, scan->RelativeSensorPose());
+    std::memset(out, 0, sizeof(*out));
+    out->found = s.mPoseFound ? 1 : 0;
+    out->stepX = stepX; out->stepY = stepY; out->stepT = stepTheta;
+    out->sensorPose[0] = sensorPose.mX; out->sensorPose[1] = sensorPose.mY;
+    out->sensorPose[2] = sensorPose.mTheta;
+    out->ix = out->iy = out->it = -1;
+    // the winner as the matcher itself computed it: MoveBackward then Compound is not an exact
+    // round trip, so search the loop values for the pose whose MoveBackward gives the summary's
+    const double rx = rangeX / 2.0, ry = rangeY / 2.0, rt = rangeTheta / 2.0;
+    int ny = 0;
+    for (double dy = -ry; dy <= ry; dy += stepY, ++ny) {
+        int nx = 0;
+        for (double dx = -rx; dx <= rx; dx += stepX, ++nx) {
+            int nt = 0;
+            for (double dt = -rt; dt <= rt; dt += stepTheta, ++nt) {
+                if (!s.mPoseFound || out->ix >= 0) continue;
+                const RobotPose2D<double> pose { sensorPose.mX + dx, sensorPose.mY + dy, sensorPose.mTheta + dt };
+                const RobotPose2D<double> est = MoveBackward(pose, scan->RelativeSensorPose());
+                if (est.mX == s.mEstimatedPose.mX && est.mY == s.mEstimatedPose.mY &&
+                    est.mTheta == s.mEstimatedPose.mTheta) {
+                    out->ix = nx; out->iy = ny; out->it = nt;
+                    out->bestSensorPose[0] = pose.mX; out->bestSensorPose[1] = pose.mY;
+                    out->bestSensorPose[2] = pose.mTheta;
+                }
+            }
+            out->winT = nt;
+        }
+        out->winX = nx;
+    }
+    out->winY = ny;
+    if (!s.mPoseFound) {   // :71: bestSensorPose starts as sensorPose
+        out->bestSensorPose[0] = sensorPose.mX; out->bestSensorPose[1] = sensorPose.mY;
+        out->bestSensorPose[2] = sensorPose.mTheta;
+    }
+    (void)best;
+    out->estPose[0] = s.mEstimatedPose.mX; out->estPose[1] = s.mEstimatedPose.mY;
+    out->estPose[2] = s.mEstimatedPose.mTheta;
+    out->normalizedCost = s.mNormalizedCost;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out->cov[3 * i + j] = s.mEstimatedCovariance(i, j);
+    ScoreFunction::Summary sum;
+    sf->Score(map->m, scan, RobotPose2D<double>(out->bestSensorPose[0], out->bestSensorPose[1],
+                                                out->bestSensorPose[2]), sum);
     out->score = sum.mScore;
     return 0;
 }

@@ -323,6 +323,25 @@ def bb_match(m: RefMap, angles, ranges, init_pose, *, height_max=6, range_x=2.0,
     return out
 
 
+def gs_match(m: RefMap, angles, ranges, init_pose, *, range_x=2.0, range_y=2.0, range_theta=0.5,
+             step_x=0.05, step_y=0.05, step_theta=0.005, score_range_min=0.01, score_range_max=20.0,
+             thr=0.5, rel=(0.0, 0.0, 0.0), scan_min_range=0.02, scan_max_range=30.0,
+             cost=DEFAULT_COST) -> MatchResult:
+    """ScanMatcherGridSearch::OptimizePose (4-argument overload); ix / iy / it = winning loop counters,
+    winX / winY / winT = loop lengths."""
+    a, ap = _d(angles)
+    r, rp = _d(ranges)
+    out = MatchResult()
+    L = lib()
+    L.ref_gs_match.argtypes = [C.c_void_p] + [C.c_double] * 8 + [c_dp, c_dp, c_dp, C.c_int, c_dp, c_dp,
+                                                                  C.c_double, C.c_double, C.c_double,
+                                                                  C.POINTER(MatchResult)]
+    L.ref_gs_match(m.h, range_x, range_y, range_theta, step_x, step_y, step_theta, score_range_min,
+                   score_range_max, (C.c_double * 7)(*cost), _arr3(init_pose), _arr3(rel), len(a), ap, rp,
+                   scan_min_range, scan_max_range, thr, C.byref(out))
+    return out
+
+
 def pixel_accurate_score(level: RefPre, sensor_pose, angles, ranges, *, score_range_min=0.01,
                          score_range_max=20.0, scan_min_range=0.02, scan_max_range=30.0):
     a, ap = _d(angles)

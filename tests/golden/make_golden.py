@@ -154,11 +154,41 @@ def cost_scene():
                         cost=np.asarray(costs), normalized=np.asarray(ncost), cov=np.asarray(cov))
 
 
+GS_PARAMS = [dict(range_x=0.6, range_y=0.5, range_theta=0.12, step_x=0.05, step_y=0.05, step_theta=0.01),
+             dict(range_x=0.4, range_y=0.4, range_theta=0.1, step_x=0.03, step_y=0.07, step_theta=0.013),
+             dict(range_x=0.3, range_y=0.3, range_theta=0.05, step_x=0.1, step_y=0.1, step_theta=0.005)]
+
+
+def gs_scene():
+    """ScanMatcherGridSearch on the first local map of scene_rooms (small windows: the CPU search costs
+    a full projection of the scan per hypothesis)."""
+    g = np.load(os.path.join(OUT, "scene_rooms.npz"))
+    angles, traj, scans = g["angles"], g["traj"], g["scans"]
+    b = R.RefBuilder()
+    for p, s in zip(traj[:12], scans[:12]):
+        b.append_scan(p, angles, s)
+    local = b.local_map(0)
+    rng = np.random.default_rng(23)
+    inits, which, ints, flts, thrs = [], [], [], [], []
+    for k in range(12, 18):
+        init = traj[k] + np.array([rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), rng.uniform(-0.03, 0.03)])
+        for pi, p in enumerate(GS_PARAMS):
+            thr = 0.3 if pi != 2 else 0.9            # the last one is not found
+            r = R.gs_match(local, angles, scans[k], init, thr=thr, **p)
+            inits.append(init); which.append(k); thrs.append(thr)
+            ints.append([r.found, r.ix, r.iy, r.it, r.winX, r.winY, r.winT])
+            flts.append([r.score, r.normalizedCost] + list(r.estPose) + list(r.cov))
+    np.savez_compressed(os.path.join(OUT, "scene_gs.npz"), inits=np.asarray(inits),
+                        scan=np.asarray(which, dtype=np.int32), thr=np.asarray(thrs),
+                        ints=np.asarray(ints, dtype=np.int64), flts=np.asarray(flts))
+
+
 if __name__ == "__main__":
     primitives()
     scene()
     edge_scene()
     cost_scene()
+    gs_scene()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

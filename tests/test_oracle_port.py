@@ -130,6 +130,26 @@ def test_cost_function_golden():
             assert n == wn[j] and np.array_equal(cov, wc[j])
 
 
+GS_PARAMS = [dict(range_x=0.6, range_y=0.5, range_theta=0.12, step_x=0.05, step_y=0.05, step_theta=0.01),
+             dict(range_x=0.4, range_y=0.4, range_theta=0.1, step_x=0.03, step_y=0.07, step_theta=0.013),
+             dict(range_x=0.3, range_y=0.3, range_theta=0.05, step_x=0.1, step_y=0.1, step_theta=0.005)]
+
+
+def test_grid_search_golden():
+    """ScanMatcherGridSearch: winner (as loop counters), loop lengths and score."""
+    g, c = np.load(os.path.join(GOLD, "scene_rooms.npz")), np.load(os.path.join(GOLD, "scene_gs.npz"))
+    angles, traj, scans = g["angles"], g["traj"], g["scans"]
+    b = P.PortBuilder()
+    for p, s in zip(traj[:12], scans[:12]):
+        b.append_scan(p, angles, s)
+    local = b.local_map(0)
+    assert c["ints"][:, 0].sum() >= 10 and (c["ints"][:, 0] == 0).sum() >= 4
+    for n, (init, k, thr, gi, gf) in enumerate(zip(c["inits"], c["scan"], c["thr"], c["ints"], c["flts"])):
+        r = P.gs_match(local, angles, scans[k], init, thr=float(thr), **GS_PARAMS[n % 3])
+        assert [r.found, r.ix, r.iy, r.it, r.winX, r.winY, r.winT] == list(gi)
+        assert r.score == gf[0]
+
+
 @needs_ref
 def test_port_cost_matches_reference_objects_randomised():
     rng = np.random.default_rng(31)
