@@ -46,111 +46,195 @@ struct GsFlag { int q, k, b; };
 
 struct GsResult { double score; int found, ix, iy, it; };
 
-__global__ void gs_project_kernel(const GsQuery* __restrict__ queries, const double* __restrict__ angles,
-                                  const double* __restrict__ ranges, const double* __restrict__ dX,
-                                  const double* __restrict__ dY, const double* __restrict__ dT, int nX, int nY,
-                                  int nT, double eps, int* __restrict__ col, int* __restrict__ row,
-                                  GsFlag* __restrict__ flags, int* __restrict__ flagCount) {
+// Block = 128 consecutive (theta_k, beam) entries of one query, whose column / row index runs are
+// contiguous in the tables: with STAGED the block builds them in shared memory and writes them out
+// with coalesced stores (a thread's own run is nX ints, so direct stores scatter over 128 lines).
+template <bool STAGED>
+__global__ void __launch_bounds__(128)
+gs_project_kernel(const GsQuery* __restrict__ queries, const double* __restrict__ angles,
+                  const double* __restrict__ ranges, const double* __restrict__ dX,
+                  const double* __restrict__ dY, const double* __restrict__ dT, int nX, int nY,
+                  int nYp, int nT, double eps, int* __restrict__ col, int* __restrict__ row,
+                  GsFlag* __restrict__ flags, int* __restrict__ flagCount) {
+    extern __shared__ int sh[];
     const GsQuery q = queries[blockIdx.y];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nT * q.nBeams) return;
-    const int k = idx / q.nBeams, b = idx - k * q.nBeams;
-    int* c = col + q.colBegin + ((long long)k * q.nBeams + b) * nX;
-    int* rw = row + q.rowBegin + ((long long)k * q.nBeams + b) * nY;
-    const double r = ranges[q.beamBegin + b];
-    if (r >= q.maxRange || r <= q.minRange) {          // score_function_pixel_accurate.cpp:38-39
+    const int total = nT * q.nBeams;
+    const int base = blockIdx.x * blockDim.x;
+    if (base >= total) return;                         // whole block
+    const int idx = base + threadIdx.x;
+    const bool live = idx < total;
+    const int k = live ? idx / q.nBeams : 0, b = live ? idx - k * q.nBeams : 0;
+    int* c = STAGED ? sh + threadIdx.x * nX : col + q.colBegin + (long long)idx * nX;
+    int* rw = STAGED ? sh + blockDim.x * nX + threadIdx.x * nYp   // rows padded to a multiple of 4
+                     : row + q.rowBegin + (long long)idx * nYp;
+    const double r = live ? ranges[q.beamBegin + b] : 0.0;
+    if (live && (r >= q.maxRange || r <= q.minRange)) {          // score_function_pixel_accurate.cpp:38-39
         for (int i = 0; i < nX; ++i) c[i] = -1;        // (-1, -1) is an apron cell: adds +0.0
-        for (int j = 0; j < nY; ++j) rw[j] = -q.pitch;
-        return;
+        for (int j = 0; j < nYp; ++j) rw[j] = -q.pitch;
+    } else if (live) {
+        const double theta = __dadd_rn(q.st, dT[k]);   // scan_matcher_grid_search.cpp:78-80
+        double s, cs;
+        sincos(__dadd_rn(theta, angles[q.beamBegin + b]), &s, &cs);   // sensor_data.hpp:168-169
+        const double rc = __dmul_rn(r, cs), rs = __dmul_rn(r, s);
+        // floor((h - min) / res), grid_map.hpp:779-790.  The quotient is first estimated with a
+        // multiply (relative error a few ulp, i.e. < 1e-9 cells for |q| < 1e6); only an estimate
+        // within eps + 1e-6 of a cell edge -- or a huge one -- pays for the IEEE division that decides
+        // the floor and the guard band.
+        const double invRes = __ddiv_rn(1.0, q.res);
+        const double fast = eps + 1e-6;                // the estimate's band contains the guard band
+        bool edge = false;
+        for (int i = 0; i < nX; ++i) {
+            const double num = __dsub_rn(__dadd_rn(__dadd_rn(q.sx, dX[i]), rc), q.minX);
+            double qx = __dmul_rn(num, invRes);
+            double f = qx - floor(qx);
+            if (!(f >= fast && f <= 1.0 - fast && fabs(qx) < 1e6)) {
+                qx = __ddiv_rn(num, q.res);
+                f = qx - floor(qx);
+                edge |= !(f >= eps && f <= 1.0 - eps);
+            }
+            const int cx = __double2int_rd(qx) - q.offX;
+            c[i] = min(max(cx, -1), q.nx);
+        }
+        for (int j = 0; j < nY; ++j) {
+            const double num = __dsub_rn(__dadd_rn(__dadd_rn(q.sy, dY[j]), rs), q.minY);
+            double qy = __dmul_rn(num, invRes);
+            double f = qy - floor(qy);
+            if (!(f >= fast && f <= 1.0 - fast && fabs(qy) < 1e6)) {
+                qy = __ddiv_rn(num, q.res);
+                f = qy - floor(qy);
+                edge |= !(f >= eps && f <= 1.0 - eps);
+            }
+            const int cy = __double2int_rd(qy) - q.offY;
+            rw[j] = min(max(cy, -1), q.ny) * q.pitch;
+        }
+        for (int j = nY; j < nYp; ++j) rw[j] = -q.pitch;   // padding: never stored, must stay readable
+        if (edge) {
+            const int n = atomicAdd(flagCount, 1);
+            if (n < kFlagCap) flags[n] = GsFlag{(int)blockIdx.y, k, b};
+        }
     }
-    const double theta = __dadd_rn(q.st, dT[k]);       // scan_matcher_grid_search.cpp:78-80
-    double s, cs;
-    sincos(__dadd_rn(theta, angles[q.beamBegin + b]), &s, &cs);   // sensor_data.hpp:168-169
-    const double rc = __dmul_rn(r, cs), rs = __dmul_rn(r, s);
-    bool edge = false;
-    for (int i = 0; i < nX; ++i) {
-        const double hx = __dadd_rn(__dadd_rn(q.sx, dX[i]), rc);
-        const double qx = __ddiv_rn(__dsub_rn(hx, q.minX), q.res);          // grid_map.hpp:779-790
-        const double f = qx - floor(qx);
-        edge |= !(f >= eps && f <= 1.0 - eps);
-        const int cx = __double2int_rd(qx) - q.offX;
-        c[i] = min(max(cx, -1), q.nx);
-    }
-    for (int j = 0; j < nY; ++j) {
-        const double hy = __dadd_rn(__dadd_rn(q.sy, dY[j]), rs);
-        const double qy = __ddiv_rn(__dsub_rn(hy, q.minY), q.res);
-        const double f = qy - floor(qy);
-        edge |= !(f >= eps && f <= 1.0 - eps);
-        const int cy = __double2int_rd(qy) - q.offY;
-        rw[j] = min(max(cy, -1), q.ny) * q.pitch;
-    }
-    if (edge) {
-        const int n = atomicAdd(flagCount, 1);
-        if (n < kFlagCap) flags[n] = GsFlag{(int)blockIdx.y, k, b};
+    if (STAGED) {
+        __syncthreads();
+        const int n = min((int)blockDim.x, total - base);
+        int* gc = col + q.colBegin + (long long)base * nX;
+        int* gr = row + q.rowBegin + (long long)base * nYp;
+        for (int e = threadIdx.x; e < n * nX; e += blockDim.x) gc[e] = sh[e];
+        for (int e = threadIdx.x; e < n * nYp; e += blockDim.x) gr[e] = sh[blockDim.x * nX + e];
     }
 }
 
-// grid = (ceil(nX * nY / 256), nT, queries)
+constexpr int kRows = 4;          // hypotheses (consecutive y offsets) per thread in the score kernel
+static_assert(kRows == 4, "the score kernel loads a thread's row offsets as one int4");
+
+struct GsPartial { double score; long long visit; };
+
+__device__ __forceinline__ bool gsBetter(double s, long long v, double bs, long long bv) {
+    return s > bs || (s == bs && v < bv);           // strict ">" in visit order (:85)
+}
+
+// grid = (ceil(nX * ceil(nY / kRows) / 256), nT, queries).  A thread owns column offset i and kRows
+// consecutive row offsets: one column-index load serves kRows gathers, and kRows x 4 gathers are in
+// flight per thread.  Each block leaves its best (score, visit) in `partials`; the full table is
+// written only when a caller asks for it.
 __global__ void __launch_bounds__(256)
 gs_score_kernel(const GsQuery* __restrict__ queries, const int* __restrict__ col, const int* __restrict__ row,
-                int nX, int nY, double* __restrict__ scores) {
-    const GsQuery q = queries[blockIdx.z];
+                int nX, int nY, int nYp, int nT, double* __restrict__ scores, GsPartial* __restrict__ partials) {
+    const GsQuery* q = queries + blockIdx.z;
+    const int nBeams = q->nBeams;
+    const int groups = (nY + kRows - 1) / kRows;
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nX * nY) return;
+    const bool active = h < nX * groups;
     const int k = blockIdx.y;
-    const int j = h / nX, i = h - j * nX;
-    const int* c = col + q.colBegin + (long long)k * q.nBeams * nX + i;
-    const int* rw = row + q.rowBegin + (long long)k * q.nBeams * nY + j;
-    const double* g = q.origin;
-    double sum = 0.0;
+    const int jg = active ? h / nX : 0, i = active ? h - jg * nX : 0;
+    const int j0 = jg * kRows;
+    const int* c = col + q->colBegin + (long long)k * nBeams * nX + i;
+    // the kRows = 4 row offsets of a beam are one aligned 16-byte load (rows are padded to nYp)
+    const int4* rw = reinterpret_cast<const int4*>(row + q->rowBegin + (long long)k * nBeams * nYp + j0);
+    const int rowStride = nYp / 4;
+    const double* g = q->origin;
+    double sum[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) sum[r] = 0.0;
     int b = 0;
-    for (; b + 4 <= q.nBeams; b += 4) {                 // gathers of four beams in flight, adds in order
-        const double v0 = __ldg(g + (rw[0] + c[0]));
-        const double v1 = __ldg(g + (rw[nY] + c[nX]));
-        const double v2 = __ldg(g + (rw[2 * nY] + c[2 * nX]));
-        const double v3 = __ldg(g + (rw[3 * nY] + c[3 * nX]));
-        sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, v0), v1), v2), v3);
-        c += 4 * nX; rw += 4 * nY;
+    if (active) {
+        for (; b + 4 <= nBeams; b += 4) {               // 4 beams x kRows gathers in flight, adds in beam order
+            double v[4][kRows];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ci = c[u * nX];
+                const int4 ro = rw[u * rowStride];
+                v[u][0] = __ldg(g + (ro.x + ci)); v[u][1] = __ldg(g + (ro.y + ci));
+                v[u][2] = __ldg(g + (ro.z + ci)); v[u][3] = __ldg(g + (ro.w + ci));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) sum[r] = __dadd_rn(sum[r], v[u][r]);
+            c += 4 * nX; rw += 4 * rowStride;
+        }
+        for (; b < nBeams; ++b) {
+            const int ci = c[0];
+            const int4 ro = rw[0];
+            sum[0] = __dadd_rn(sum[0], __ldg(g + (ro.x + ci))); sum[1] = __dadd_rn(sum[1], __ldg(g + (ro.y + ci)));
+            sum[2] = __dadd_rn(sum[2], __ldg(g + (ro.z + ci))); sum[3] = __dadd_rn(sum[3], __ldg(g + (ro.w + ci)));
+            c += nX; rw += rowStride;
+        }
     }
-    for (; b < q.nBeams; ++b) {
-        sum = __dadd_rn(sum, __ldg(g + (rw[0] + c[0])));
-        c += nX; rw += nY;
-    }
-    scores[q.scoreBegin + ((long long)k * nY + j) * nX + i] = sum;
-}
-
-__global__ void __launch_bounds__(256)
-gs_select_kernel(const GsQuery* __restrict__ queries, const double* __restrict__ scores, int nX, int nY,
-                 int nT, GsResult* __restrict__ results) {
-    const GsQuery q = queries[blockIdx.x];
-    const long long total = (long long)nT * nY * nX;
     double best = -1.0;
     long long bestVisit = 0x7fffffffffffffffLL;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-        const int k = (int)(e / ((long long)nY * nX));
-        const int ji = (int)(e - (long long)k * nY * nX);      // j * nX + i
-        const long long visit = (long long)ji * nT + k;        // loop order y, x, theta (:74-76)
-        const double s = scores[q.scoreBegin + e];
-        if (s > best || (s == best && visit < bestVisit)) { best = s; bestVisit = visit; }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int j = j0 + r;
+            if (j >= nY) break;
+            if (scores) scores[q->scoreBegin + ((long long)k * nY + j) * nX + i] = sum[r];
+            const long long visit = ((long long)j * nX + i) * nT + k;      // loop order y, x, theta (:74-76)
+            if (gsBetter(sum[r], visit, best, bestVisit)) { best = sum[r]; bestVisit = visit; }
+        }
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        const double s = __shfl_xor_sync(0xffffffffu, best, w);
+        const long long v = __shfl_xor_sync(0xffffffffu, bestVisit, w);
+        if (gsBetter(s, v, best, bestVisit)) { best = s; bestVisit = v; }
+    }
+    __shared__ double sBest[8];
+    __shared__ long long sVisit[8];
+    if ((threadIdx.x & 31) == 0) { sBest[threadIdx.x >> 5] = best; sVisit[threadIdx.x >> 5] = bestVisit; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (gsBetter(sBest[w], sVisit[w], best, bestVisit)) { best = sBest[w]; bestVisit = sVisit[w]; }
+        partials[((long long)blockIdx.z * nT + k) * gridDim.x + blockIdx.x] = GsPartial{best, bestVisit};
+    }
+}
+
+// one block per query over its nT x tiles block partials
+__global__ void __launch_bounds__(256)
+gs_select_kernel(const GsQuery* __restrict__ queries, const GsPartial* __restrict__ partials, int perQuery,
+                 int nX, int nT, GsResult* __restrict__ results) {
+    const double threshold = queries[blockIdx.x].threshold;
+    double best = -1.0;
+    long long bestVisit = 0x7fffffffffffffffLL;
+    for (int e = threadIdx.x; e < perQuery; e += blockDim.x) {
+        const GsPartial p = partials[(long long)blockIdx.x * perQuery + e];
+        if (gsBetter(p.score, p.visit, best, bestVisit)) { best = p.score; bestVisit = p.visit; }
     }
     __shared__ double sBest[256];
     __shared__ long long sVisit[256];
     sBest[threadIdx.x] = best; sVisit[threadIdx.x] = bestVisit;
     __syncthreads();
     for (int w = 128; w > 0; w >>= 1) {
-        if (threadIdx.x < w) {
-            const double s = sBest[threadIdx.x + w];
-            const long long v = sVisit[threadIdx.x + w];
-            if (s > sBest[threadIdx.x] || (s == sBest[threadIdx.x] && v < sVisit[threadIdx.x])) {
-                sBest[threadIdx.x] = s; sVisit[threadIdx.x] = v;
-            }
+        if (threadIdx.x < w && gsBetter(sBest[threadIdx.x + w], sVisit[threadIdx.x + w], sBest[threadIdx.x],
+                                        sVisit[threadIdx.x])) {
+            sBest[threadIdx.x] = sBest[threadIdx.x + w]; sVisit[threadIdx.x] = sVisit[threadIdx.x + w];
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         GsResult r;
-        r.found = total > 0 && sBest[0] > q.threshold;   // strict, first visit among equals (:85, :94)
-        r.score = r.found ? sBest[0] : q.threshold;
+        r.found = perQuery > 0 && sBest[0] > threshold;  // strict, first visit among equals (:85, :94)
+        r.score = r.found ? sBest[0] : threshold;
         const long long v = r.found ? sVisit[0] : 0;
         const int ji = (int)(v / nT);
         r.it = r.found ? (int)(v - (long long)ji * nT) : -1;
@@ -201,6 +285,7 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
     const std::vector<double> dY = offsets(p->range_y / 2.0, p->step_y);
     const std::vector<double> dT = offsets(p->range_theta / 2.0, p->step_theta);
     const int nX = (int)dX.size(), nY = (int)dY.size(), nT = (int)dT.size();
+    const int nYp = (nY + 3) & ~3;                     // row offsets padded for 16-byte loads
     if ((long long)nX * nY * nT > (1LL << 31) || nX > (1 << 20) || nY > (1 << 20) || nT > (1 << 20))
         return lgs_fail(c, LGS_ERR_INVALID, "gs_match: %d x %d x %d hypotheses per query", nX, nY, nT);
     if (scoreTable && nQ != 1) return lgs_fail(c, LGS_ERR_INVALID, "gs_match: the score table is a 1-query diagnostic");
@@ -237,7 +322,7 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
             if (!g) { rcOut = lgs_fail(c, LGS_ERR_INVALID, "gs_match: query %d has no grid", q1); break; }
             if (g->ctx->device != c->device) { rcOut = lgs_fail(c, LGS_ERR_INVALID, "gs_match: grid of query %d on another device", q1); break; }
             const int nb = scans->beam_begin[q1 + 1] - scans->beam_begin[q1];
-            const long long cc = (long long)nT * nb * nX, rr = (long long)nT * nb * nY;
+            const long long cc = (long long)nT * nb * nX, rr = (long long)nT * nb * nYp;
             if (q1 > q0 && (size_t)(colCells + rowCells + cc + rr) * sizeof(int) > kTableBudget) break;
             GsQuery h;
             h.sx = scans->sensor_pose[3 * q1]; h.sy = scans->sensor_pose[3 * q1 + 1]; h.st = scans->sensor_pose[3 * q1 + 2];
@@ -258,11 +343,14 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         if (rcOut != LGS_OK) break;
         const int nq = (int)hq.size();
         GsQuery* dQ = nullptr; int *dCol = nullptr, *dRow = nullptr, *dFlagCount = nullptr;
-        double* dScores = nullptr; GsFlag* dFlags = nullptr; GsResult* dRes = nullptr;
+        double* dScores = nullptr; GsFlag* dFlags = nullptr; GsResult* dRes = nullptr; GsPartial* dPart = nullptr;
+        const int groups = (nY + kRows - 1) / kRows;
+        const int tiles = (int)(((long long)nX * groups + 255) / 256);
+        const int perQuery = nT * tiles;
         auto freeAll = [&]() {
             cudaFreeAsync(dQ, c->stream); cudaFreeAsync(dCol, c->stream); cudaFreeAsync(dRow, c->stream);
             cudaFreeAsync(dScores, c->stream); cudaFreeAsync(dFlags, c->stream);
-            cudaFreeAsync(dFlagCount, c->stream); cudaFreeAsync(dRes, c->stream);
+            cudaFreeAsync(dFlagCount, c->stream); cudaFreeAsync(dRes, c->stream); cudaFreeAsync(dPart, c->stream);
         };
 #define GS_TRY(call)                                                                               \
         do { cudaError_t e__ = (call);                                                             \
@@ -272,7 +360,8 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         GS_TRY(cudaMallocAsync(&dQ, nq * sizeof(GsQuery), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dCol, std::max<long long>(colCells, 1) * sizeof(int), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dRow, std::max<long long>(rowCells, 1) * sizeof(int), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dScores, std::max<long long>(scoreCells, 1) * sizeof(double), c->stream));
+        if (rcOut == LGS_OK && scoreTable) GS_TRY(cudaMallocAsync(&dScores, std::max<long long>(scoreCells, 1) * sizeof(double), c->stream));
+        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dPart, std::max<size_t>((size_t)nq * perQuery, 1) * sizeof(GsPartial), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dFlags, kFlagCap * sizeof(GsFlag), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dFlagCount, sizeof(int), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dRes, nq * sizeof(GsResult), c->stream));
@@ -283,8 +372,13 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         const long long hyp = (long long)nX * nY;
         if (maxBeams > 0 && nT > 0) {
             dim3 gp((unsigned)(((long long)nT * maxBeams + 127) / 128), nq);
-            gs_project_kernel<<<gp, 128, 0, c->stream>>>(dQ, dAngles, dRanges, ddX, ddY, ddT, nX, nY, nT, eps,
-                                                         dCol, dRow, dFlags, dFlagCount);
+            const size_t stage = (size_t)128 * (nX + nYp) * sizeof(int);
+            if (stage <= 48 * 1024)
+                gs_project_kernel<true><<<gp, 128, stage, c->stream>>>(dQ, dAngles, dRanges, ddX, ddY, ddT, nX, nY,
+                                                                       nYp, nT, eps, dCol, dRow, dFlags, dFlagCount);
+            else
+                gs_project_kernel<false><<<gp, 128, 0, c->stream>>>(dQ, dAngles, dRanges, ddX, ddY, ddT, nX, nY,
+                                                                    nYp, nT, eps, dCol, dRow, dFlags, dFlagCount);
             c->launches++;
         }
         int nFlag = 0;
@@ -316,22 +410,22 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
                 }
                 GS_TRY(cudaMemcpy(dCol + h.colBegin + ((long long)k * h.nBeams + b) * nX, hc.data(), nX * sizeof(int), cudaMemcpyHostToDevice));
                 if (rcOut == LGS_OK)
-                    GS_TRY(cudaMemcpy(dRow + h.rowBegin + ((long long)k * h.nBeams + b) * nY, hr.data(), nY * sizeof(int), cudaMemcpyHostToDevice));
+                    GS_TRY(cudaMemcpy(dRow + h.rowBegin + ((long long)k * h.nBeams + b) * nYp, hr.data(), nY * sizeof(int), cudaMemcpyHostToDevice));
                 fixups[fl[f].q]++;
             }
             if (rcOut != LGS_OK) break;
         }
         if (hyp > 0 && nT > 0) {
-            dim3 gs((unsigned)((hyp + 255) / 256), nT, nq);
-            gs_score_kernel<<<gs, 256, 0, c->stream>>>(dQ, dCol, dRow, nX, nY, dScores);
+            dim3 gs(tiles, nT, nq);
+            gs_score_kernel<<<gs, 256, 0, c->stream>>>(dQ, dCol, dRow, nX, nY, nYp, nT, dScores, dPart);
             c->launches++;
         }
-        gs_select_kernel<<<nq, 256, 0, c->stream>>>(dQ, dScores, nX, nY, nT, dRes);
+        gs_select_kernel<<<nq, 256, 0, c->stream>>>(dQ, dPart, (hyp > 0 && nT > 0) ? perQuery : 0, nX, nT, dRes);
         c->launches++;
         GS_TRY(cudaGetLastError());
         std::vector<GsResult> hr(nq);
         if (rcOut == LGS_OK) GS_TRY(cudaMemcpyAsync(hr.data(), dRes, nq * sizeof(GsResult), cudaMemcpyDeviceToHost, c->stream));
-        if (rcOut == LGS_OK && scoreTable && scoreCells > 0)
+        if (rcOut == LGS_OK && scoreTable && dScores && scoreCells > 0)
             GS_TRY(cudaMemcpyAsync(scoreTable, dScores, scoreCells * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaStreamSynchronize(c->stream));
         if (rcOut != LGS_OK) break;
