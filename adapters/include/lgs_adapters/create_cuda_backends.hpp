@@ -16,6 +16,7 @@
 #include <string>
 
 #include "lgs_adapters/grid_map_builder_cuda.hpp"
+#include "lgs_adapters/grid_search_cuda.hpp"
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
 #include "lgs_adapters/loop_detector_real_time_correlative_cuda.hpp"
 #include "lgs_adapters/scan_matcher_real_time_correlative_cuda.hpp"
@@ -116,6 +117,51 @@ std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorRealTimeCorrelativeCuda
     auto pScanMatcher = std::dynamic_pointer_cast<Mapping::ScanMatcherRealTimeCorrelativeCuda>(
         CreateScanMatcherRealTimeCorrelativeCuda(jsonSettings, matcherGroup, createCostFunction));
     return std::make_shared<Mapping::LoopDetectorRealTimeCorrelativeCuda>(pScanMatcher, scoreThreshold);
+}
+
+/* "ScanMatcherType": "GridSearchCuda" -- the keys CreateScanMatcherGridSearch reads
+ * (slam_launcher.cpp:185-228, launcher_settings_default.json:71-82) plus the pixel-accurate score
+ * group's usable range (:83-86) */
+template <typename Ptree, typename CostFactory>
+std::shared_ptr<Mapping::ScanMatcher> CreateScanMatcherGridSearchCuda(
+    const Ptree& jsonSettings, const std::string& configGroup, CostFactory createCostFunction)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    const double rangeX = config.template get<double>("SearchRangeX");
+    const double rangeY = config.template get<double>("SearchRangeY");
+    const double rangeTheta = config.template get<double>("SearchRangeTheta");
+    const double stepX = config.template get<double>("SearchStepX");
+    const double stepY = config.template get<double>("SearchStepY");
+    const double stepTheta = config.template get<double>("SearchStepTheta");
+    const int device = config.get("Device", 0);
+    const std::string scoreGroup = config.template get<std::string>("ScoreConfigGroup");
+    const std::string costType = config.template get<std::string>("CostType");
+    const std::string costGroup = config.template get<std::string>("CostConfigGroup");
+
+    const Ptree& score = jsonSettings.get_child(scoreGroup);
+    const double usableRangeMin = score.template get<double>("UsableRangeMin");
+    const double usableRangeMax = score.template get<double>("UsableRangeMax");
+
+    auto pCostFunc = createCostFunction(jsonSettings, costType, costGroup);
+    auto pMatcher = std::make_shared<Mapping::ScanMatcherGridSearchCuda>(
+        usableRangeMin, usableRangeMax, pCostFunc, rangeX, rangeY, rangeTheta, stepX, stepY, stepTheta,
+        device);
+    if (costType == "GreedyEndpoint" && config.get("DeviceCost", true))
+        pMatcher->UseDeviceCost(ReadCostGreedyEndpointParams(jsonSettings, costGroup));
+    return pMatcher;
+}
+
+/* "LoopDetectorType": "GridSearchCuda" -- like CreateLoopDetectorGridSearch (slam_launcher.cpp:386-415) */
+template <typename Ptree, typename CostFactory>
+std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorGridSearchCuda(
+    const Ptree& jsonSettings, const std::string& configGroup, CostFactory createCostFunction)
+{
+    const Ptree& config = jsonSettings.get_child(configGroup);
+    const double scoreThreshold = config.template get<double>("ScoreThreshold");
+    const std::string matcherGroup = config.template get<std::string>("ScanMatcherConfigGroup");
+    auto pScanMatcher = std::dynamic_pointer_cast<Mapping::ScanMatcherGridSearchCuda>(
+        CreateScanMatcherGridSearchCuda(jsonSettings, matcherGroup, createCostFunction));
+    return std::make_shared<Mapping::LoopDetectorGridSearchCuda>(pScanMatcher, scoreThreshold);
 }
 
 /* "GridMapBuilder": { ..., "Backend": "Cuda", "Device": 0 } -- the other keys are the ones

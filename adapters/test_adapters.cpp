@@ -21,6 +21,8 @@
 #include "my_lidar_graph_slam/mapping/cost_function_greedy_endpoint.hpp"
 #include "my_lidar_graph_slam/mapping/grid_map_builder.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector_branch_bound.hpp"
+#include "my_lidar_graph_slam/mapping/loop_detector_grid_search.hpp"
+#include "my_lidar_graph_slam/mapping/scan_matcher_grid_search.hpp"
 #include "my_lidar_graph_slam/mapping/loop_detector_real_time_correlative.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_branch_bound.hpp"
 #include "my_lidar_graph_slam/mapping/scan_matcher_real_time_correlative.hpp"
@@ -404,6 +406,69 @@ int main() {
         failures += !ok;
         if (r1.empty() || r1.size() == nodes) { std::printf("expected some but not all nodes to close a loop\n"); ++failures; }
     }
+    /* ---- grid-search matcher and the loop detector built on it (small windows: the CPU search projects
+     *      the whole scan once per hypothesis) ---- */
+    {
+        auto score = std::make_shared<ScorePixelAccurate>(0.01, 20.0);
+        auto refMatcher = std::make_shared<ScanMatcherGridSearch>(score, cost, 0.5, 0.4, 0.1, 0.05, 0.05, 0.01);
+        auto gpuMatcher = std::make_shared<ScanMatcherGridSearchCuda>(0.01, 20.0, cost, 0.5, 0.4, 0.1, 0.05, 0.05, 0.01, 0);
+        LoopDetectorGridSearch ref(refMatcher, 0.5);
+        LoopDetectorGridSearchCuda gpu(gpuMatcher, 0.5);
+        std::uniform_real_distribution<double> dxy(-0.15, 0.15), dth(-0.03, 0.03);
+        for (int round = 0; round < 2; ++round) {      /* host tail, then device tail */
+            if (round == 1) gpuMatcher->UseDeviceCost(costParams);
+            /* the matcher itself, including a match that stays below the threshold */
+            int bad = 0;
+            for (int k = 0; k < 3; ++k) {
+                const RobotPose2D<double> truth = path[52 + k];
+                const auto scan = MakeScan(world, truth, 541, g);
+                const double far = k == 2 ? 4.0 : 0.0;
+                const RobotPose2D<double> init(truth.mX + dxy(g) + far, truth.mY + dxy(g), truth.mTheta + dth(g));
+                const ScanMatchingSummary a = refMatcher->OptimizePose(builder.LatestMap(), scan, init, 0.55);
+                const ScanMatchingSummary b = gpuMatcher->OptimizePose(builder.LatestMap(), scan, init, 0.55);
+                bad += !(a.mPoseFound == b.mPoseFound && SameBits(a.mNormalizedCost, b.mNormalizedCost) &&
+                         SamePose(a.mInitialPose, b.mInitialPose) && SamePose(a.mEstimatedPose, b.mEstimatedPose) &&
+                         SameMat(a.mEstimatedCovariance, b.mEstimatedCovariance));
+                if (k == 2 && b.mPoseFound) { std::printf("grid search: the far-off match must not be found\n"); ++bad; }
+            }
+            LoopDetectionQueryVector q1, q2;
+            for (size_t m = 0; m + 1 < builder.LocalMaps().size() && m < 2; ++m) {
+                LocalMapInfo info = builder.LocalMapAt(static_cast<int>(m));
+                info.mFinished = true;
+                std::vector<PoseGraph::Node> n1, n2;
+                for (int j = 0; j < 3; ++j) {
+                    const int idx = info.mPoseGraphNodeIdxMin + 2 + 3 * j + round;
+                    const RobotPose2D<double> truth = poseGraph->NodeAt(idx).Pose();
+                    const auto scan = MakeScan(world, truth, 541, g);
+                    const double far = j == 2 ? 3.0 : 0.0;
+                    const RobotPose2D<double> pert(truth.mX + dxy(g) + far, truth.mY + dxy(g) - far, truth.mTheta + dth(g));
+                    n1.emplace_back(3000 + j, pert, scan);
+                    n2.emplace_back(3000 + j, pert, scan);
+                }
+                const PoseGraph::Node& mapNode = poseGraph->NodeAt(info.mPoseGraphNodeIdxMin);
+                q1.emplace_back(std::move(n1), info, mapNode);
+                q2.emplace_back(std::move(n2), info, mapNode);
+            }
+            LoopDetectionResultVector r1, r2;
+            const auto s0 = std::chrono::steady_clock::now();
+            ref.Detect(q1, r1);
+            const auto s1 = std::chrono::steady_clock::now();
+            gpu.Detect(q2, r2);
+            const auto s2 = std::chrono::steady_clock::now();
+            bool ok = bad == 0 && r1.size() == r2.size();
+            for (size_t i = 0; ok && i < r1.size(); ++i)
+                ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) &&
+                     SamePose(r1[i].mStartNodePose, r2[i].mStartNodePose) &&
+                     r1[i].mStartNodeIdx == r2[i].mStartNodeIdx && r1[i].mEndNodeIdx == r2[i].mEndNodeIdx &&
+                     SameMat(r1[i].mEstimatedCovMat, r2[i].mEstimatedCovMat);
+            std::printf("grid-search matcher + loop detector (%s tail): loops ref %zu / cuda %zu %s; Detect reference %.1f ms, "
+                        "cuda %.1f ms\n", round ? "device" : "host", r1.size(), r2.size(), ok ? "IDENTICAL" : "MISMATCH",
+                        std::chrono::duration<double, std::milli>(s1 - s0).count(),
+                        std::chrono::duration<double, std::milli>(s2 - s1).count());
+            failures += !ok;
+            if (r1.empty() || r1.size() == 6) { std::printf("expected some but not all nodes to close a loop\n"); ++failures; }
+        }
+    }
     /* ---- the JSON factories of create_cuda_backends.hpp (instantiated with a flat key table) ---- */
     {
         FlatTree t;
@@ -412,13 +477,16 @@ int main() {
                 {"ScanMatcherConfigGroup", "M"}, {"NodeHeightMax", "6"}, {"ScoreConfigGroup", "S"},
                 {"CostType", "GreedyEndpoint"}, {"CostConfigGroup", "C"}, {"UsableRangeMin", "0.01"},
                 {"UsableRangeMax", "20.0"}, {"Map.NumOfScansForLatestMap", "10"},
-                {"ProbabilityHit", "0.6"}, {"ProbabilityMiss", "0.45"}};
+                {"ProbabilityHit", "0.6"}, {"ProbabilityMiss", "0.45"}, {"SearchStepX", "0.05"},
+                {"SearchStepY", "0.05"}, {"SearchStepTheta", "0.01"}};
         auto costFactory = [&](const FlatTree&, const std::string&, const std::string&) { return CostFuncPtr(cost); };
         auto m = LgsB200::CreateScanMatcherRealTimeCorrelativeCuda(t, "M", costFactory);
         auto d1 = LgsB200::CreateLoopDetectorBranchBoundCuda(t, "D", costFactory);
         auto d2 = LgsB200::CreateLoopDetectorRealTimeCorrelativeCuda(t, "D", costFactory);
         auto b = LgsB200::CreateGridMapBuilderCuda(t, "G");
-        bool ok = m && d1 && d2 && b && b->LocalMaps().empty();
+        auto m3 = LgsB200::CreateScanMatcherGridSearchCuda(t, "M", costFactory);
+        auto d3 = LgsB200::CreateLoopDetectorGridSearchCuda(t, "D", costFactory);
+        bool ok = m && d1 && d2 && b && m3 && d3 && b->LocalMaps().empty();
         /* the factory-made matcher evaluates its tail on the device with the parameters it read from
          * the settings; it must agree with the reference matcher holding the launcher-made cost object */
         {

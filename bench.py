@@ -598,6 +598,49 @@ def run_tail(ctx, grid, dense, min_x, min_y, angles, ranges, inits, results, wit
     return out
 
 
+def run_gs(ctx, grid, dense, min_x, min_y, angles, ranges, inits, with_cpu, n_queries=64):
+    """the exhaustive grid-search matcher behind LoopDetectorGridSearch at the
+    launcher's defaults (2 m x 2 m at 0.05 m, 0.5 rad at 0.005 rad: ~1.7e5 hypotheses per query)."""
+    from my_lidar_graph_slam_b200 import capi
+    Q = min(n_queries, len(ranges))
+    scans = capi.Scans([angles] * Q, ranges[:Q], inits[:Q], range_min=0.02, range_max=30.0)
+    capi.pin(ctx, scans.angles, scans.ranges)
+    out = capi.gs_match(ctx, scans, [grid] * Q)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = capi.gs_match(ctx, scans, [grid] * Q)
+    dt = (time.perf_counter() - t0) / reps
+    capi.unpin(ctx, scans.angles, scans.ranges)
+    hyp = sum(r.n_scored for r in out)
+    res = {"queries_per_s": Q / dt, "hypotheses_per_s": hyp / dt, "ms_per_call": 1e3 * dt, "queries_per_call": Q,
+           "hypotheses_per_query": hyp // Q, "found": int(sum(r.found for r in out)),
+           "host_fixups": int(sum(r.n_fixups for r in out)),
+           "note": "lgs_gs_match end to end (host scans in, result records out); kernels: gs_project, gs_score, "
+                   "gs_select"}
+    if with_cpu:
+        try:
+            from oracle import refapi as R
+            if R.available():
+                rm = R.RefMap.from_dense(dense, min_x, min_y)
+                small = dict(range_x=0.5, range_y=0.5, range_theta=0.05, step_x=0.05, step_y=0.05, step_theta=0.005)
+                t0 = time.perf_counter()
+                ref = R.gs_match(rm, angles, ranges[0], inits[0], **small)
+                cdt = time.perf_counter() - t0
+                one = capi.Scans([angles], [ranges[0]], [inits[0]], range_min=0.02, range_max=30.0)
+                (g,) = capi.gs_match(ctx, one, [grid], **small)
+                same = (g.found, g.ix, g.iy, g.it, g.win_x, g.win_y, g.win_t) == \
+                    (ref.found, ref.ix, ref.iy, ref.it, ref.winX, ref.winY, ref.winT) and \
+                    (not g.found or g.score == ref.score)
+                n = ref.winX * ref.winY * ref.winT
+                res["cpu_reference"] = {"hypotheses_per_s": n / cdt, "cores": 1, "kind": "reference",
+                                        "sample": f"one query on a reduced window ({n} hypotheses, {cdt:.1f} s); "
+                                                  f"device winner and score identical: {bool(same)}"}
+        except Exception as e:                                   # noqa: BLE001
+            res["cpu_reference"] = {"error": str(e)}
+    return res
+
+
 def run_b200(args, rank, world_size, local_rank):
     from my_lidar_graph_slam_b200 import capi
     dist = None
@@ -764,6 +807,8 @@ def run_b200(args, rank, world_size, local_rank):
         if rank == 0:
             side("matcher_tail", lambda: run_tail(ctx, grid, dense, min_x, min_y, angles, ranges, inits,
                                                   results_dev, not args.no_cpu_baseline))
+            side("grid_search", lambda: run_gs(ctx, grid, dense, min_x, min_y, angles, ranges, inits,
+                                               not args.no_cpu_baseline))
             side("grid_integration", lambda: run_c3(ctx, 1024, args.c3_scans, not args.no_cpu_baseline))
         if args.c5_side > 0:
             side("large_map", lambda: run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
