@@ -68,6 +68,10 @@ public:
     const lgs_grid* DeviceLatestMap() const
     { return this->mScratchIsLatest ? this->mDevScratch : nullptr; }
 
+    /* Wall-clock split of the work so far, milliseconds: {host staging of hit points + geometry,
+     * device integration (incl. its synchronisation), map download, write-back into the host maps} */
+    const double* TimingsMs() const { return this->mTimingsMs; }
+
     /* Cell updates applied on the device so far (= BinaryBayesGridCell::Update calls of the CPU) */
     long long NumOfCellUpdates() const { return this->mNumOfUpdates; }
 
@@ -111,6 +115,7 @@ private:
     bool                      mDensePinned;
     bool                      mScratchIsLatest;   /* mDevScratch == mLatestMap */
     long long                 mNumOfUpdates;
+    double                    mTimingsMs[4];
 };
 
 } /* namespace Mapping */

@@ -3,6 +3,7 @@
 #include "lgs_adapters/grid_map_flatten.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,11 @@ void Check(lgs_ctx* ctx, int rc, const char* what)
     std::fprintf(stderr, "GridMapBuilderCuda: %s failed (%d): %s\n", what, rc,
                  ctx != nullptr ? lgs_ctx_last_error(ctx) : "no context");
     std::abort();
+}
+
+inline double MsSince(const std::chrono::steady_clock::time_point& t0)
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 /* Write the device value into one host cell through the cell's public API (see the header) */
@@ -58,7 +64,8 @@ GridMapBuilderCuda::GridMapBuilderCuda(
     mDevScratch(nullptr),
     mDensePinned(false),
     mScratchIsLatest(false),
-    mNumOfUpdates(0)
+    mNumOfUpdates(0),
+    mTimingsMs { 0.0, 0.0, 0.0, 0.0 }
 {
     Check(nullptr, lgs_ctx_create(device, &this->mCtx), "lgs_ctx_create (no usable B200: no CPU fallback)");
 }
@@ -175,15 +182,20 @@ void GridMapBuilderCuda::IntegrateAndSync(lgs_grid* grid, GridMapType& map,
     const lgs_hit_batch batch { static_cast<int>(this->mSensorXY.size() / 2), this->mSensorXY.data(),
                                 this->mHitBegin.data(), this->mHitXY.data() };
     long long updates = 0;
+    auto t0 = std::chrono::steady_clock::now();
     Check(this->mCtx, lgs_grid_integrate_scans(this->mCtx, grid, &batch, this->mProbHit,
           this->mProbMiss, &updates), "lgs_grid_integrate_scans");
     this->mNumOfUpdates += updates;
+    this->mTimingsMs[1] += MsSince(t0);
 
     const int nx = map.NumOfGridCellsX(), ny = map.NumOfGridCellsY();
     if (nx == 0 || ny == 0)
         return;
+    t0 = std::chrono::steady_clock::now();
     this->ReserveDense(static_cast<std::size_t>(nx) * ny);
     Check(this->mCtx, lgs_grid_download(grid, this->mDense.data()), "lgs_grid_download");
+    this->mTimingsMs[2] += MsSince(t0);
+    t0 = std::chrono::steady_clock::now();
     x0 = std::max(x0, 0); y0 = std::max(y0, 0);
     x1 = std::min(x1, nx - 1); y1 = std::min(y1, ny - 1);
     const int patch = this->mPatchSize;
@@ -208,6 +220,7 @@ void GridMapBuilderCuda::IntegrateAndSync(lgs_grid* grid, GridMapType& map,
                     StoreCell(cells[(y - py * patch) * patch + (x - px * patch)],
                               this->mDense[static_cast<std::size_t>(y) * nx + x]);
         }
+    this->mTimingsMs[3] += MsSince(t0);
 }
 
 bool GridMapBuilderCuda::UpdateGridMap(const std::shared_ptr<PoseGraph>& poseGraph)
