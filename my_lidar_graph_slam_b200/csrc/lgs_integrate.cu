@@ -34,6 +34,8 @@
 // is marked, and the owner re-derives that (cell, scan) by testing the beams kmin..kmax itself.
 #include <cmath>
 
+#include <chrono>
+
 #include "lgs_internal.cuh"
 
 namespace {
@@ -595,6 +597,13 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     LGS_CUDA(c, cudaSetDevice(c->device));
     if (!c->integ) c->integ = new lgs_integ_ws();
     lgs_integ_ws& w = *c->integ;
+    // LGS_INTEG_HOSTTIMING=1 (diagnostic): host wall time of the call's phases to stderr when a call
+    // takes longer than a millisecond.
+    static const bool hostTiming = getenv("LGS_INTEG_HOSTTIMING") != nullptr;
+    const auto tStart = std::chrono::steady_clock::now();
+    auto msSince = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    double tStage = 0.0, tPre = 0.0, tLoop = 0.0;
 
     // Stage the whole batch once; the passes then run over chunks of <= 64 scans (one mask bit each).
     LGS_CUDA(c, w.sensor.reserve((size_t)n * 2));
@@ -610,6 +619,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         LGS_CUDA(c, cudaMemcpyAsync(w.hit.p, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     LGS_CUDA(c, cudaMemcpyAsync(w.begin.p, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     LGS_CUDA(c, cudaMemsetAsync(w.counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    tStage = msSince(tStart);
 
     int maxBeams = 0;
     for (int s = 0; s < n; ++s) maxBeams = std::max(maxBeams, scans->hit_begin[s + 1] - scans->hit_begin[s]);
@@ -626,6 +636,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     }
     LGS_CUDA(c, cudaMemcpyAsync(hMeta, dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    tPre = msSince(tStart);
     for (int s = 0; s < n; ++s)
         if (hMeta[s].bad)
             return lgs_fail(c, LGS_ERR_INVALID, "integrate: scan %d touches cells outside the %dx%d grid "
@@ -742,9 +753,13 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         lastBuf = buf;
         stamp();
     }
+    tLoop = msSince(tStart);
     if (overlap && lastBuf >= 0) LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evFold[lastBuf], 0));
     LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hostTiming && msSince(tStart) > 1.0)
+        fprintf(stderr, "[lgs integrate host] %d scans into %dx%d: staged %.3f ms, pre-pass synced %.3f ms, chunks queued "
+                "%.3f ms, done %.3f ms\n", n, grid->nx, grid->ny, tStage, tPre, tLoop, msSince(tStart));
     if (timing) {
         float t[4] = {0, 0, 0, 0};
         for (size_t k = 0; k + 5 <= evs.size(); k += 5)      // 5 stamps per chunk

@@ -44,7 +44,9 @@ int lgs_fail(lgs_ctx* ctx, int code, const char* fmt, ...);
         LGS_CUDA((ctx), cudaGetLastError());                                             \
     } while (0)
 
-// Simple growable device / pinned-host buffers owned by batch objects.
+// Simple growable device / pinned-host buffers owned by batch objects.  Growth is geometric: a
+// request a little above the capacity (scratch sizes follow the data, e.g. the ray lengths of a
+// scan) must not cost a cudaFree + cudaMalloc pair -- milliseconds each -- call after call.
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -52,9 +54,16 @@ struct DevBuf {
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        p = nullptr;
+        size_t want = std::max(n, cap + cap / 2);
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess && want > n) {          // the head room is optional
+            cudaGetLastError();
+            want = n;
+            e = cudaMalloc(&p, want * sizeof(T));
+        }
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -67,9 +76,11 @@ struct PinBuf {
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        p = nullptr;
+        const size_t want = std::max(n, cap + cap / 2);
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }

@@ -1,6 +1,6 @@
 """GPU parity, randomised: many small seeded scenes with random sensor models, map sizes, search
-windows, thresholds and filter probabilities -- integration, both matchers and the pyramid each time,
-every result compared bit for bit with the reference's own classes."""
+windows, thresholds and filter probabilities -- integration, the three matchers, the matchers' tail and
+the pyramid each time, every result compared bit for bit with the reference's own classes."""
 import numpy as np
 import pytest
 
@@ -97,3 +97,28 @@ def test_random_scene_end_to_end(ctx, seed):
             assert (out.found, out.ix, out.iy, out.it) == (ref.found, ref.ix, ref.iy, ref.it), ("bb", k, rep)
             if ref.found:
                 assert out.score == ref.score
+
+    # ---- the matchers' tail at the correlative winner, random cost-function parameters
+    cs = (float(rng.uniform(0.0, 0.3)), float(rng.uniform(5.0, 25.0)), float(rng.uniform(0.03, 0.15)),
+          float(rng.uniform(0.05, 0.5)), float(rng.integers(0, 4)), float(rng.uniform(0.05, 2.0)),
+          float(rng.uniform(0.03, 1.0)))
+    tail_scans = capi.Scans([angles] * 2, [s for s, _ in qs], [p for _, p in qs], range_min=0.02, range_max=30.0)
+    nc, cov, _ = capi.cost_tail(ctx, grid, tail_scans, [p for _, p in qs], cost=cs)
+    for k, (scan, pose) in enumerate(qs):
+        wn, _, wc = R.host_tail(refmap, pose, angles, scan, cost=cs)
+        assert nc[k] == wn and np.array_equal(cov[k], wc), ("tail", k)
+
+    # ---- exhaustive grid search with free (non-resolution) steps, small window
+    gp = dict(range_x=float(rng.uniform(0.1, 0.5)), range_y=float(rng.uniform(0.1, 0.5)),
+              range_theta=float(rng.uniform(0.02, 0.12)), step_x=float(rng.uniform(0.02, 0.12)),
+              step_y=float(rng.uniform(0.02, 0.12)), step_theta=float(rng.uniform(0.004, 0.03)),
+              score_range_min=0.01, score_range_max=float(rng.uniform(5.0, 25.0)))
+    gthr = float(rng.uniform(0.2, 0.7))
+    gout = capi.gs_match(ctx, tail_scans, [grid, grid], norm_threshold=gthr, **gp)
+    for k, (scan, pose) in enumerate(qs):
+        ref = R.gs_match(refmap, angles, scan, pose, thr=gthr, **gp)
+        got = gout[k]
+        assert (got.found, got.ix, got.iy, got.it, got.win_x, got.win_y, got.win_t) == \
+            (ref.found, ref.ix, ref.iy, ref.it, ref.winX, ref.winY, ref.winT), ("gs", k)
+        if ref.found:
+            assert got.score == ref.score
