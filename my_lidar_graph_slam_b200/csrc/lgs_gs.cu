@@ -17,6 +17,9 @@
 //                         gathers a short row segment per beam, like the sweep);
 //   K3 gs_select_kernel   one block per query: max score, ties to the earliest visit (y, x, theta
 //                         loop order), found = max > threshold.
+// When the hypotheses of one theta fit one block (the launcher's 41 x 41 window does), K1 and K2 run
+// fused (gs_fused_kernel): the index runs of 64 beams at a time live in shared memory only, nothing
+// but the block maxima reaches HBM; a near-edge beam sends the chunk through the table path above.
 // The offset lists dx_i, dy_j, dt_k are produced on the host by the reference's own accumulating
 // loops, so the loop lengths (which depend on the rounding of the running sums) are the CPU's.
 // Unknown cells and out-of-range beams add exactly +0.0 (sums are non-negative, so x + 0.0 == x),
@@ -209,6 +212,153 @@ gs_score_kernel(const GsQuery* __restrict__ queries, const int* __restrict__ col
     }
 }
 
+// Fused form for windows whose hypotheses of one theta fit one block (nX * ceil(nY / 4) <= THREADS,
+// e.g. the launcher's 41 x 41): block = (theta_k, query).  The column / row index runs of kFusedBeams
+// beams at a time are built in shared memory and consumed from there, so no index table ever reaches
+// HBM and there is no separate projection launch.  A beam inside the guard band only raises
+// `flagCount`; the host then redoes the chunk through the table path, which has the exact fix-up.
+constexpr int kFusedBeams = 64;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+gs_fused_kernel(const GsQuery* __restrict__ queries, const double* __restrict__ angles,
+                const double* __restrict__ ranges, const double* __restrict__ dX,
+                const double* __restrict__ dY, const double* __restrict__ dT, int nX, int nY, int nYp,
+                int nT, double eps, double* __restrict__ scores, GsPartial* __restrict__ partials,
+                int* __restrict__ flagCount) {
+    extern __shared__ __align__(16) unsigned char shRaw[];
+    double* sRc = reinterpret_cast<double*>(shRaw);                    // r cos, NaN = beam out of range
+    double* sRs = sRc + kFusedBeams;
+    int* sRow = reinterpret_cast<int*>(sRs + kFusedBeams);            // [beam][nYp], 16-byte aligned rows
+    int* sCol = sRow + kFusedBeams * nYp;                             // [beam][nX]
+    __shared__ int sEdge;
+    const GsQuery* q = queries + blockIdx.y;
+    const int k = blockIdx.x;
+    const int nBeams = q->nBeams;
+    const int groups = (nY + kRows - 1) / kRows;
+    const bool active = (int)threadIdx.x < nX * groups;
+    const int jg = active ? threadIdx.x / nX : 0, i = active ? threadIdx.x - jg * nX : 0;
+    const int j0 = jg * kRows;
+    const double sx = q->sx, sy = q->sy, minX = q->minX, minY = q->minY, res = q->res;
+    const double theta = __dadd_rn(q->st, dT[k]);                     // scan_matcher_grid_search.cpp:78-80
+    const double invRes = __ddiv_rn(1.0, res);
+    const double fast = eps + 1e-6;
+    const int gnx = q->nx, gny = q->ny, pitch = q->pitch, offX = q->offX, offY = q->offY;
+    const double* g = q->origin;
+    if (threadIdx.x == 0) sEdge = 0;
+    double sum[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) sum[r] = 0.0;
+    const int per = nX + nYp;
+    for (int c0 = 0; c0 < nBeams; c0 += kFusedBeams) {
+        const int nb = min(kFusedBeams, nBeams - c0);
+        __syncthreads();                                               // previous chunk consumed
+        if ((int)threadIdx.x < nb) {
+            const int b = q->beamBegin + c0 + threadIdx.x;
+            const double r = ranges[b];
+            double rc = nan(""), rs = 0.0;
+            if (!(r >= q->maxRange || r <= q->minRange)) {             // score_function_pixel_accurate.cpp:38-39
+                double s, cs;
+                sincos(__dadd_rn(theta, angles[b]), &s, &cs);          // sensor_data.hpp:168-169
+                rc = __dmul_rn(r, cs); rs = __dmul_rn(r, s);
+            }
+            sRc[threadIdx.x] = rc; sRs[threadIdx.x] = rs;
+        }
+        __syncthreads();
+        bool edge = false;
+        for (int e = threadIdx.x; e < nb * per; e += THREADS) {
+            const int t = e / per, o = e - t * per;
+            const double rc = sRc[t];
+            if (o < nX) {
+                int v = -1;                                            // (-1, -1) is an apron cell: adds +0.0
+                if (rc == rc) {
+                    const double num = __dsub_rn(__dadd_rn(__dadd_rn(sx, dX[o]), rc), minX);
+                    double qx = __dmul_rn(num, invRes);                // estimate; see gs_project_kernel
+                    double f = qx - floor(qx);
+                    if (!(f >= fast && f <= 1.0 - fast && fabs(qx) < 1e6)) {
+                        qx = __ddiv_rn(num, res);                      // grid_map.hpp:779-790
+                        f = qx - floor(qx);
+                        edge |= !(f >= eps && f <= 1.0 - eps);
+                    }
+                    v = min(max(__double2int_rd(qx) - offX, -1), gnx);
+                }
+                sCol[t * nX + o] = v;
+            } else {
+                const int j = o - nX;
+                int v = -pitch;
+                if (rc == rc && j < nY) {
+                    const double num = __dsub_rn(__dadd_rn(__dadd_rn(sy, dY[j]), sRs[t]), minY);
+                    double qy = __dmul_rn(num, invRes);
+                    double f = qy - floor(qy);
+                    if (!(f >= fast && f <= 1.0 - fast && fabs(qy) < 1e6)) {
+                        qy = __ddiv_rn(num, res);
+                        f = qy - floor(qy);
+                        edge |= !(f >= eps && f <= 1.0 - eps);
+                    }
+                    v = min(max(__double2int_rd(qy) - offY, -1), gny) * pitch;
+                }
+                sRow[t * nYp + j] = v;
+            }
+        }
+        if (edge) sEdge = 1;
+        __syncthreads();
+        if (active) {
+            const int* c = sCol + i;
+            const int4* rw = reinterpret_cast<const int4*>(sRow + j0);
+            const int rowStride = nYp / 4;
+            int t = 0;
+            for (; t + 4 <= nb; t += 4) {                              // 16 gathers in flight, adds in beam order
+                double v[4][kRows];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ci = c[(t + u) * nX];
+                    const int4 ro = rw[(t + u) * rowStride];
+                    v[u][0] = __ldg(g + (ro.x + ci)); v[u][1] = __ldg(g + (ro.y + ci));
+                    v[u][2] = __ldg(g + (ro.z + ci)); v[u][3] = __ldg(g + (ro.w + ci));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) sum[r] = __dadd_rn(sum[r], v[u][r]);
+            }
+            for (; t < nb; ++t) {
+                const int ci = c[t * nX];
+                const int4 ro = rw[t * rowStride];
+                sum[0] = __dadd_rn(sum[0], __ldg(g + (ro.x + ci))); sum[1] = __dadd_rn(sum[1], __ldg(g + (ro.y + ci)));
+                sum[2] = __dadd_rn(sum[2], __ldg(g + (ro.z + ci))); sum[3] = __dadd_rn(sum[3], __ldg(g + (ro.w + ci)));
+            }
+        }
+    }
+    double best = -1.0;
+    long long bestVisit = 0x7fffffffffffffffLL;
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int j = j0 + r;
+            if (j >= nY) break;
+            if (scores) scores[q->scoreBegin + ((long long)k * nY + j) * nX + i] = sum[r];
+            const long long visit = ((long long)j * nX + i) * nT + k;      // loop order y, x, theta (:74-76)
+            if (gsBetter(sum[r], visit, best, bestVisit)) { best = sum[r]; bestVisit = visit; }
+        }
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        const double s = __shfl_xor_sync(0xffffffffu, best, w);
+        const long long v = __shfl_xor_sync(0xffffffffu, bestVisit, w);
+        if (gsBetter(s, v, best, bestVisit)) { best = s; bestVisit = v; }
+    }
+    __shared__ double sBest[THREADS / 32];
+    __shared__ long long sVisit[THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { sBest[threadIdx.x >> 5] = best; sVisit[threadIdx.x >> 5] = bestVisit; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < THREADS / 32; ++w)
+            if (gsBetter(sBest[w], sVisit[w], best, bestVisit)) { best = sBest[w]; bestVisit = sVisit[w]; }
+        partials[(long long)blockIdx.y * nT + k] = GsPartial{best, bestVisit};
+        if (sEdge) atomicAdd(flagCount, 1);
+    }
+}
+
 // one block per query over its nT x tiles block partials
 __global__ void __launch_bounds__(256)
 gs_select_kernel(const GsQuery* __restrict__ queries, const GsPartial* __restrict__ partials, int perQuery,
@@ -358,8 +508,6 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
                  rcOut = lgs_fail(c, e__ == cudaErrorMemoryAllocation ? LGS_ERR_NOMEM : LGS_ERR_CUDA, \
                                   "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } } while (0)
         GS_TRY(cudaMallocAsync(&dQ, nq * sizeof(GsQuery), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dCol, std::max<long long>(colCells, 1) * sizeof(int), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dRow, std::max<long long>(rowCells, 1) * sizeof(int), c->stream));
         if (rcOut == LGS_OK && scoreTable) GS_TRY(cudaMallocAsync(&dScores, std::max<long long>(scoreCells, 1) * sizeof(double), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dPart, std::max<size_t>((size_t)nq * perQuery, 1) * sizeof(GsPartial), c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dFlags, kFlagCap * sizeof(GsFlag), c->stream));
@@ -370,6 +518,39 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         if (rcOut != LGS_OK) break;
 
         const long long hyp = (long long)nX * nY;
+        // Fast path: projection fused into the scoring block (no tables); any near-edge beam sends the
+        // chunk through the table path below, which carries the exact host fix-up.
+        const size_t fusedSmem = (size_t)kFusedBeams * (2 * sizeof(double) + (size_t)(nX + nYp) * sizeof(int));
+        const long long fusedThreads = (long long)nX * groups;
+        const bool tablesOnly = getenv("LGS_GS_TABLES") != nullptr;   // test / diagnostic hook: force the table path
+        bool done = false;
+        if (!tablesOnly && hyp > 0 && nT > 0 && maxBeams > 0 && fusedThreads <= 1024 && fusedSmem <= 48 * 1024) {
+            dim3 gf(nT, nq);
+            if (fusedThreads <= 512)
+                gs_fused_kernel<512><<<gf, 512, fusedSmem, c->stream>>>(dQ, dAngles, dRanges, ddX, ddY, ddT, nX, nY, nYp,
+                                                                        nT, eps, dScores, dPart, dFlagCount);
+            else
+                gs_fused_kernel<1024><<<gf, 1024, fusedSmem, c->stream>>>(dQ, dAngles, dRanges, ddX, ddY, ddT, nX, nY, nYp,
+                                                                          nT, eps, dScores, dPart, dFlagCount);
+            c->launches++;
+            int fusedFlags = 0;
+            GS_TRY(cudaMemcpyAsync(&fusedFlags, dFlagCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            if (rcOut == LGS_OK) GS_TRY(cudaStreamSynchronize(c->stream));
+            if (rcOut != LGS_OK) break;
+            if (fusedFlags == 0) {
+                gs_select_kernel<<<nq, 256, 0, c->stream>>>(dQ, dPart, nT, nX, nT, dRes);
+                c->launches++;
+                done = true;
+            } else {
+                GS_TRY(cudaMemsetAsync(dFlagCount, 0, sizeof(int), c->stream));
+                if (rcOut != LGS_OK) break;
+            }
+        }
+        std::vector<int> fixups(nq, 0);
+        if (!done) {
+        GS_TRY(cudaMallocAsync(&dCol, std::max<long long>(colCells, 1) * sizeof(int), c->stream));
+        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dRow, std::max<long long>(rowCells, 1) * sizeof(int), c->stream));
+        if (rcOut != LGS_OK) break;
         if (maxBeams > 0 && nT > 0) {
             dim3 gp((unsigned)(((long long)nT * maxBeams + 127) / 128), nq);
             const size_t stage = (size_t)128 * (nX + nYp) * sizeof(int);
@@ -386,7 +567,6 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         if (rcOut == LGS_OK) GS_TRY(cudaStreamSynchronize(c->stream));
         if (rcOut != LGS_OK) break;
         if (nFlag > kFlagCap) { freeAll(); rcOut = lgs_fail(c, LGS_ERR_OVERFLOW, "gs_match: %d near-edge beams exceed the fix-up list", nFlag); break; }
-        std::vector<int> fixups(nq, 0);
         if (nFlag > 0) {
             // Rare path: the flagged beams' columns and rows with the host's libm, the reference's
             // own arithmetic (sensor_data.hpp:162-173 + grid_map.hpp:779-790)
@@ -422,6 +602,7 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         }
         gs_select_kernel<<<nq, 256, 0, c->stream>>>(dQ, dPart, (hyp > 0 && nT > 0) ? perQuery : 0, nX, nT, dRes);
         c->launches++;
+        }   // table path
         GS_TRY(cudaGetLastError());
         std::vector<GsResult> hr(nq);
         if (rcOut == LGS_OK) GS_TRY(cudaMemcpyAsync(hr.data(), dRes, nq * sizeof(GsResult), cudaMemcpyDeviceToHost, c->stream));

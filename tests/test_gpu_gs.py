@@ -19,6 +19,16 @@ def _ints(r):
     return [r.found, r.ix, r.iy, r.it, r.win_x, r.win_y, r.win_t]
 
 
+@pytest.fixture(params=["fused", "tables"], autouse=True)
+def gs_path(request, monkeypatch):
+    """Every test runs through the fused kernel and through the index-table path (LGS_GS_TABLES)."""
+    if request.param == "tables":
+        monkeypatch.setenv("LGS_GS_TABLES", "1")
+    else:
+        monkeypatch.delenv("LGS_GS_TABLES", raising=False)
+    return request.param
+
+
 def test_gs_golden_vectors(ctx):
     """tests/golden/scene_gs.npz was written by the unmodified reference matcher."""
     g, c = np.load(os.path.join(GOLD, "scene_rooms.npz")), np.load(os.path.join(GOLD, "scene_gs.npz"))
