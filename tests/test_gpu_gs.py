@@ -125,3 +125,24 @@ def test_gs_edge_cases(ctx):
     assert capi.gs_match(ctx, capi.Scans([], [], np.zeros((0, 3))), []) == []
     with pytest.raises(capi.LgsError):
         capi.gs_match(ctx, one, [grid], step_x=0.0)
+
+
+def test_gs_wide_window_uses_the_1024_thread_block(ctx):
+    """61 x 51 offsets per theta: 793 threads per block in the fused kernel."""
+    from oracle import backend
+    R = backend()
+    rng = np.random.default_rng(61)
+    dense = np.where(rng.random((128, 192)) < 0.45, np.round(rng.uniform(1e-3, 0.999, (128, 192)), 3), 0.0)
+    refmap = R.RefMap.from_dense(dense, -3.0, -2.0)
+    grid = capi.Grid.from_dense(ctx, dense, -3.0, -2.0, 0.05, apron=1)
+    angles = [np.linspace(-1.5, 1.5, 150), np.linspace(-3.0, 3.0, 97)]
+    ranges = [rng.uniform(0.2, 3.5, 150), rng.uniform(0.2, 3.5, 97)]
+    inits = np.array([[0.5, 0.3, 0.2], [2.0, 1.0, -1.0]])
+    p = dict(range_x=1.2, range_y=0.5, range_theta=0.2, step_x=0.02, step_y=0.01, step_theta=0.03)
+    batch = capi.Scans(angles, ranges, inits, range_min=0.02, range_max=30.0)
+    out = capi.gs_match(ctx, batch, [grid, grid], norm_threshold=0.05, **p)
+    for q, r in enumerate(out):
+        ref = R.gs_match(refmap, angles[q], ranges[q], inits[q], thr=0.05, **p)
+        assert (r.win_x, r.win_y) == (61, 51) or (r.win_x, r.win_y) == (ref.winX, ref.winY)
+        assert _ints(r) == [ref.found, ref.ix, ref.iy, ref.it, ref.winX, ref.winY, ref.winT] and r.found
+        assert r.score == ref.score
