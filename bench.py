@@ -364,6 +364,84 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
                           "loops_found": int((recQ["found"] != 0).sum())}
         for g in groups:
             g["batch"].close()
+        # The same step on a 2-D rank grid (N > 1): (scan, submap) pairs are independent, so
+        # ranks can split the scans as well as the submaps.  Pm submap groups x Ps scan groups with
+        # Pm * Ps = N; a rank holds the pyramids of its submap group (n_submaps / Pm of them: 250 submaps are
+        # 9.5 GB) and searches its scan group against them in sub-batches of ~4000 pairs.  With 8 ranks that
+        # is ONE sub-batch of 16 scans x 250 submaps per rank -- the shape a single GPU runs eight times --
+        # instead of 64 scans x 63 submaps, whose 64 hit-point projections no rank shares.
+        if world_size > 1:
+            pm_want = int(os.environ.get("LGS_C4_PM", max(1, n_submaps // 250)))
+            Pm = max(d for d in range(1, world_size + 1) if world_size % d == 0 and d <= max(pm_want, 1))
+            Ps = world_size // Pm
+            pm, ps = rank % Pm, rank // Pm
+            group_ids = np.array([g for g in range(n_submaps) if g % Pm == pm], dtype=np.int64)
+            own = {int(g): k for k, g in enumerate(mine)}
+            extra_grids, extra_pyr, group_pyr = [], [], []
+            for g in group_ids:
+                if int(g) in own:
+                    group_pyr.append(pyramids[own[int(g)]])
+                    continue
+                traj_g, scans_g = c4_submap_scans(world, angles, int(g), 8, anchor)
+                grid_g, _ = build_map_on_gpu(ctx, traj_g, angles, scans_g, apron=1)
+                extra_grids.append(grid_g)
+                extra_pyr.append(capi.Pyramid(ctx, grid_g, 6))
+                group_pyr.append(extra_pyr[-1])
+            my_scans = [k for k in range(Q) if k % Ps == ps]
+            ng = len(group_ids)
+            sub2 = max(1, min(len(my_scans), max(8, -(-4000 // max(ng, 1))))) if my_scans else 1
+            groups2 = []
+            for k0 in range(0, len(my_scans), sub2):
+                ks = my_scans[k0:k0 + sub2]
+                groups2.append(dict(
+                    scans=capi.Scans([angles] * len(ks), [qscans[k] for k in ks], [qinits[k] for k in ks],
+                                     range_min=0.02, range_max=30.0),
+                    pair_scan=np.repeat(np.arange(len(ks), dtype=np.int32), ng),
+                    pyr=group_pyr * len(ks),
+                    ids=np.concatenate([k * n_submaps + group_ids for k in ks]),
+                    batch=capi.BbBatch(ctx, **BB)))
+
+            def stepS():
+                recs = []
+                for g in groups2:
+                    g["batch"].upload_pairs(g["scans"], g["pair_scan"], g["pyr"], 0.6)
+                    g["batch"].run()
+                for g in groups2:
+                    recs.append(sharding.pack_array(g["batch"].results_array(), g["ids"]))
+                local = np.concatenate(recs) if recs else np.zeros(0, dtype=sharding.RECORD)
+                return sharding.all_gather_variable(local, Q * n_submaps, world_size, dev)
+
+            for _ in range(2):
+                recS = stepS()
+            ctx.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                recS = stepS()
+            ctx.synchronize()
+            eS = max_over_ranks(time.perf_counter() - t0)
+            for g in groups2:
+                g["batch"].upload_pairs(g["scans"], g["pair_scan"], g["pyr"], 0.6)
+            barrier()
+            ctx.timer_start()
+            for _ in range(steps):
+                for g in groups2:
+                    g["batch"].run()
+            dS = max_over_ranks(ctx.timer_stop())
+            out["batched_2d"] = {
+                "workload": f"{Q} query scans x {n_submaps} submaps per step on a {Ps} x {Pm} rank grid (scan groups x "
+                            f"submap groups): every rank searches {len(my_scans)} scans x {ng} submaps in sub-batches "
+                            f"of {sub2} scans",
+                "loop_queries_per_s": Q * n_submaps * steps / (dS * 1e-3),
+                "loop_queries_per_s_e2e": Q * n_submaps * steps / eS,
+                "ms_per_step": dS / steps, "ms_per_step_e2e": 1e3 * eS / steps,
+                "records_identical_to_submap_sharding": recS.tobytes() == recQ.tobytes()}
+            for g in groups2:
+                g["batch"].close()
+            for p_ in extra_pyr:
+                p_.close()
+            for g in extra_grids:
+                g.close()
     if with_cpu and rank == 0:
         try:
             from oracle import refapi as R
