@@ -192,12 +192,16 @@ void GridMapBuilderCuda::IntegrateAndSync(lgs_grid* grid, GridMapType& map,
     if (nx == 0 || ny == 0)
         return;
     t0 = std::chrono::steady_clock::now();
-    this->ReserveDense(static_cast<std::size_t>(nx) * ny);
-    Check(this->mCtx, lgs_grid_download(grid, this->mDense.data()), "lgs_grid_download");
-    this->mTimingsMs[2] += MsSince(t0);
-    t0 = std::chrono::steady_clock::now();
     x0 = std::max(x0, 0); y0 = std::max(y0, 0);
     x1 = std::min(x1, nx - 1); y1 = std::min(y1, ny - 1);
+    if (x1 < x0 || y1 < y0)
+        return;
+    /* only the region that can have changed comes back, into its place in the full-map staging */
+    this->ReserveDense(static_cast<std::size_t>(nx) * ny);
+    Check(this->mCtx, lgs_grid_download_region(grid, x0, y0, x1 - x0 + 1, y1 - y0 + 1,
+          this->mDense.data() + static_cast<std::size_t>(y0) * nx + x0, nx), "lgs_grid_download_region");
+    this->mTimingsMs[2] += MsSince(t0);
+    t0 = std::chrono::steady_clock::now();
     const int patch = this->mPatchSize;
     for (int py = y0 / patch; py <= y1 / patch; ++py)
         for (int px = x0 / patch; px <= x1 / patch; ++px) {

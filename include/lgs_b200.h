@@ -92,6 +92,11 @@ int lgs_grid_create(lgs_ctx* ctx, int nx, int ny, double min_x, double min_y, do
 int lgs_grid_destroy(lgs_grid* g);
 int lgs_grid_upload(lgs_grid* g, const double* dense);       /* host [ny][nx] -> device */
 int lgs_grid_download(const lgs_grid* g, double* dense);     /* device -> host [ny][nx] */
+/* Cells [x0, x0 + w) x [y0, y0 + h) only: row r of the region goes to dst + r * dst_pitch (pitch in
+ * doubles, >= w).  What a builder needs after integrating one scan: only the scan's bounding box can
+ * have changed (grid_map_builder.cpp:152-186). */
+int lgs_grid_download_region(const lgs_grid* g, int x0, int y0, int w, int h, double* dst,
+                             long long dst_pitch);
 /* Device -> device: `dst` takes the geometry (size, placement, window) and the cells of `src`,
  * keeping its own apron (which stays 0.0).  The grids may belong to different contexts of the same
  * device; the copy runs on dst's stream after src's stream has drained.  This is the hand-over of

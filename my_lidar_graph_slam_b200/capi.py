@@ -459,6 +459,7 @@ SIGNATURES.update({
     "lgs_grid_resize": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]),
     "lgs_grid_clear": (C.c_int, [vp]),
     "lgs_grid_copy": (C.c_int, [vp, vp]),
+    "lgs_grid_download_region": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_longlong]),
     "lgs_grid_integrate_scans": (C.c_int, [vp, vp, C.POINTER(HitBatch), C.c_double, C.c_double,
                                            C.POINTER(C.c_longlong)]),
     "lgs_ctx_integrate_fallback_cells": (C.c_longlong, [vp]),
@@ -515,6 +516,13 @@ def grid_copy(src: Grid, dst: Grid):
     """Device -> device: dst takes src's geometry and cells (lgs_grid_copy)."""
     dst.ctx.check(lib().lgs_grid_copy(src.h, dst.h))
     dst.nx, dst.ny, dst.min_x, dst.min_y = src.nx, src.ny, src.min_x, src.min_y
+
+
+def grid_download_region(grid: Grid, x0: int, y0: int, w: int, h: int) -> np.ndarray:
+    """Cells [x0, x0 + w) x [y0, y0 + h) of the grid as an (h, w) array (lgs_grid_download_region)."""
+    out = np.empty((h, w), dtype=np.float64)
+    grid.ctx.check(lib().lgs_grid_download_region(grid.h, x0, y0, w, h, _dptr(out), max(w, 1)))
+    return out
 
 
 def grid_clear(grid: Grid):

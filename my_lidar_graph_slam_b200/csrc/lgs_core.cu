@@ -179,6 +179,21 @@ int lgs_grid_download(const lgs_grid* g, double* dense) {
     return LGS_OK;
 }
 
+int lgs_grid_download_region(const lgs_grid* g, int x0, int y0, int w, int h, double* dst, long long dstPitch) {
+    if (!g || !dst) return LGS_ERR_INVALID;
+    lgs_ctx* c = g->ctx;
+    if (w == 0 || h == 0) return LGS_OK;
+    if (x0 < 0 || y0 < 0 || w < 0 || h < 0 || x0 + (long long)w > g->nx || y0 + (long long)h > g->ny || dstPitch < w)
+        return lgs_fail(c, LGS_ERR_INVALID, "grid_download_region: [%d, %d) x [%d, %d) of a %dx%d grid, pitch %lld",
+                        x0, x0 + w, y0, y0 + h, g->nx, g->ny, dstPitch);
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)dstPitch * sizeof(double), g->origin() + (size_t)y0 * g->pitch + x0,
+                                  (size_t)g->pitch * sizeof(double), (size_t)w * sizeof(double), h,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LGS_OK;
+}
+
 int lgs_grid_copy(const lgs_grid* src, lgs_grid* dst) {
     if (!src || !dst || src == dst) return LGS_ERR_INVALID;
     lgs_ctx* c = dst->ctx;

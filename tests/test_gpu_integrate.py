@@ -237,6 +237,10 @@ def test_grid_copy_between_contexts_takes_geometry_and_cells(ctx):
     src.upload(dense2)
     capi.grid_copy(src, dst)                                           # same size: plain copy
     assert np.array_equal(dst.download(), dense2)
+    assert np.array_equal(capi.grid_download_region(dst, 7, 11, 40, 23), dense2[11:34, 7:47])
+    assert capi.grid_download_region(dst, 89, 69, 1, 1)[0, 0] == dense2[69, 89]
+    with pytest.raises(capi.LgsError):
+        capi.grid_download_region(dst, 80, 0, 20, 5)                   # runs off the right edge
     bad = capi.Grid(other, 90, 70, -1.5, 2.25, 0.1, apron=1)
     with pytest.raises(capi.LgsError):
         capi.grid_copy(src, bad)                                       # resolution mismatch
