@@ -371,11 +371,10 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
         # is ONE sub-batch of 16 scans x 250 submaps per rank -- the shape a single GPU runs eight times --
         # instead of 64 scans x 63 submaps, whose 64 hit-point projections no rank shares.
         if world_size > 1:
-            pm_want = int(os.environ.get("LGS_C4_PM", max(1, n_submaps // 250)))
-            Pm = max(d for d in range(1, world_size + 1) if world_size % d == 0 and d <= max(pm_want, 1))
-            Ps = world_size // Pm
-            pm, ps = rank % Pm, rank // Pm
-            group_ids = np.array([g for g in range(n_submaps) if g % Pm == pm], dtype=np.int64)
+            Ps, Pm = sharding.rank_grid(world_size, n_submaps,
+                                        want_pm=int(os.environ["LGS_C4_PM"]) if "LGS_C4_PM" in os.environ else None)
+            my_scans, group_ids = sharding.grid_owned(Q, n_submaps, rank, Ps, Pm)
+            my_scans = [int(k) for k in my_scans]
             own = {int(g): k for k, g in enumerate(mine)}
             extra_grids, extra_pyr, group_pyr = [], [], []
             for g in group_ids:
@@ -387,7 +386,6 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
                 extra_grids.append(grid_g)
                 extra_pyr.append(capi.Pyramid(ctx, grid_g, 6))
                 group_pyr.append(extra_pyr[-1])
-            my_scans = [k for k in range(Q) if k % Ps == ps]
             ng = len(group_ids)
             sub2 = max(1, min(len(my_scans), max(8, -(-4000 // max(ng, 1))))) if my_scans else 1
             groups2 = []

@@ -87,6 +87,25 @@ def all_gather_variable(local: np.ndarray, n_items: int, world: int, device=None
     return out
 
 
+def rank_grid(world: int, n_submaps: int, submaps_per_group: int = 250, want_pm: int | None = None):
+    """(Ps, Pm): scan groups x submap groups with Ps * Pm == world.  (scan, submap) pairs are independent,
+    so a batch of scans against many submaps can be split along both axes; Pm is the largest divisor of
+    `world` that still leaves about `submaps_per_group` submaps (a good device sub-batch) per group."""
+    want = max(1, n_submaps // max(submaps_per_group, 1)) if want_pm is None else max(1, int(want_pm))
+    pm = max(d for d in range(1, world + 1) if world % d == 0 and d <= want)
+    return world // pm, pm
+
+
+def grid_owned(n_scans: int, n_submaps: int, rank: int, ps_groups: int, pm_groups: int):
+    """Scans and submaps of `rank` on a ps_groups x pm_groups rank grid (rank = ps * pm_groups + pm):
+    scans k with k % ps_groups == ps, submaps g with g % pm_groups == pm.  Since pm_groups divides the
+    world size, the submaps a rank owns under plain round-robin (g % world == rank) are among them."""
+    pm, ps = rank % pm_groups, rank // pm_groups
+    scans = np.arange(n_scans, dtype=np.int64)
+    submaps = np.arange(n_submaps, dtype=np.int64)
+    return scans[scans % ps_groups == ps], submaps[submaps % pm_groups == pm]
+
+
 def best_candidate(records: np.ndarray):
     """Index of the found record with the highest score (ties: lowest submap index), or -1."""
     ok = np.flatnonzero(records["found"] != 0)

@@ -115,3 +115,58 @@ def test_band_routed_queries_all_gather_world2_gloo():
     rows = (np.arange(n) * 37) % 100
     assert full["submap"].tolist() == list(range(n)) and full["ix"].tolist() == rows.tolist()
     assert full["it"].tolist() == largemap.owner_of_rows(rows, 100, 2).tolist()    # uneven: 6 vs 5 queries
+
+
+# ---- 2-D rank grid for batches of scans x submaps -----------------------------------------------------
+def test_rank_grid_covers_every_pair_exactly_once():
+    from my_lidar_graph_slam_b200 import sharding
+    assert sharding.rank_grid(8, 500) == (4, 2) and sharding.rank_grid(2, 500) == (1, 2)
+    assert sharding.rank_grid(4, 500) == (2, 2) and sharding.rank_grid(1, 500) == (1, 1)
+    assert sharding.rank_grid(8, 100) == (8, 1) and sharding.rank_grid(8, 5000) == (1, 8)
+    assert sharding.rank_grid(2, 500, want_pm=1) == (2, 1) and sharding.rank_grid(6, 500, want_pm=4) == (2, 3)
+    for world in (1, 2, 3, 4, 6, 8):
+        for n_scans, n_submaps in ((64, 500), (5, 7), (1, 500), (64, 1)):
+            ps, pm = sharding.rank_grid(world, n_submaps)
+            assert ps * pm == world
+            seen = np.zeros((n_scans, n_submaps), dtype=np.int32)
+            for rank in range(world):
+                scans, submaps = sharding.grid_owned(n_scans, n_submaps, rank, ps, pm)
+                seen[np.ix_(scans, submaps)] += 1
+                # plain round-robin ownership of submaps is contained in the rank's submap group
+                assert set(sharding.owned(n_submaps, rank, world).tolist()) <= set(submaps.tolist())
+            assert (seen == 1).all()
+
+
+def _grid_worker(rank, world, port, n_scans, n_submaps, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from my_lidar_graph_slam_b200 import sharding
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ps, pm = sharding.rank_grid(world, n_submaps, want_pm=1)          # world 2 -> two scan groups
+    scans, submaps = sharding.grid_owned(n_scans, n_submaps, rank, ps, pm)
+    ids = np.concatenate([k * n_submaps + submaps for k in scans]) if len(scans) else np.zeros(0, dtype=np.int64)
+    local = np.zeros(len(ids), dtype=sharding.RECORD)
+    local["submap"], local["ix"], local["found"], local["score"] = ids, ids % 97, 1, ids * 0.5
+    full = sharding.all_gather_variable(local, n_scans * n_submaps, world)
+    q.put((rank, full.tobytes()))
+    dist.destroy_process_group()
+
+
+def test_scan_group_sharding_all_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    from my_lidar_graph_slam_b200 import sharding
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, n_scans, n_submaps = _free_port(), 5, 9                      # uneven: 3 and 2 scans per rank
+    procs = [ctx.Process(target=_grid_worker, args=(r, 2, port, n_scans, n_submaps, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1]
+    full = np.frombuffer(got[0][1], dtype=sharding.RECORD)
+    ids = np.arange(n_scans * n_submaps)
+    assert full["submap"].tolist() == ids.tolist() and full["ix"].tolist() == (ids % 97).tolist()
+    assert (full["found"] == 1).all() and np.array_equal(full["score"], ids * 0.5)
