@@ -28,7 +28,7 @@ for k in range(Q):
     qs.append(synth.make_scan(world, t, angles, qrng))
     qi.append(t + np.array([0.3, -0.2, 0.08]))
 mine = [k for k in range(Q) if k % (Q // NS) == 0]
-for sub in (16, 8, 4, 2):
+for sub in (16, 8):
     groups = []
     for k0 in range(0, len(mine), sub):
         ks = mine[k0:k0 + sub]
