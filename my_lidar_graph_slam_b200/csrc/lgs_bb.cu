@@ -41,6 +41,8 @@
 #include <cfloat>
 #include <cmath>
 
+#include <chrono>
+
 #include "lgs_internal.cuh"
 
 namespace {
@@ -700,6 +702,8 @@ struct lgs_bb_batch {
     // level counts on the device; lgs_bb_batch_results validates (no pool overflow) and otherwise
     // repeats the run level-synchronously.  Hints = counts of the last run.
     bool haveHints = false, pendingValidate = false;
+    double hostMs[3] = {0.0, 0.0, 0.0};   // LGS_BB_HOSTTIMING: preamble enqueue, flag-count wait, level enqueue
+    long long hostRuns = 0;
     long long hint[kMaxLevels] = {0};
     long long nodesPerLevel[kMaxLevels] = {0};
     long long gathers = 0;
@@ -743,6 +747,10 @@ int lgs_bb_batch_create(lgs_ctx* ctx, const lgs_bb_params* p, lgs_bb_batch** out
 }
 
 int lgs_bb_batch_destroy(lgs_bb_batch* b) {
+    if (b && b->hostRuns > 0 && getenv("LGS_BB_HOSTTIMING"))
+        fprintf(stderr, "[lgs bb host] %lld speculative runs of %d queries: per run preamble enqueue %.3f ms, flag-count "
+                "wait %.3f ms, level enqueue %.3f ms\n", b->hostRuns, b->nq, b->hostMs[0] / b->hostRuns,
+                b->hostMs[1] / b->hostRuns, b->hostMs[2] / b->hostRuns);
     if (!b) return LGS_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
@@ -961,6 +969,11 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     b->gathers = 0;
     if (n == 0) { b->ran = true; return LGS_OK; }
     LGS_CUDA(c, cudaSetDevice(c->device));
+    // LGS_BB_HOSTTIMING=1 (diagnostic): host wall time of a run's three phases, summed per batch
+    // object and printed when it is destroyed.
+    const auto hostT0 = std::chrono::steady_clock::now();
+    auto hostMsSince = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, (2 + kMaxLevels) * sizeof(int), c->stream));
     // Scoring the root level from the hit points pays off when several queries share a scan (the
     // 16-byte hit points are then L2 hits); with one scan per query the 8-byte table rows are cheaper.
@@ -994,7 +1007,10 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
         b->slotPath = false;
         if (wantSlots) {
             LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            b->hostMs[0] += hostMsSince(hostT0);
+            const auto w0 = std::chrono::steady_clock::now();
             LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+            b->hostMs[1] += hostMsSince(w0);
             nFlag = b->hCounters.p[0];
             b->slotPath = nFlag <= kFlagInline;
         }
@@ -1120,6 +1136,7 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
     };
 
     if (spec) {
+        const auto l0 = std::chrono::steady_clock::now();
         for (int h = H; h >= 0; --h) {
             const long long expect = h == H ? b->totalRoots : b->hint[h];
             if (h < H && b->dNodes[h].cap == 0) break;
@@ -1145,6 +1162,8 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
         LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, (2 + kMaxLevels) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         b->pendingValidate = true;
         b->ran = true;
+        b->hostMs[2] += hostMsSince(l0);
+        b->hostRuns++;
         return LGS_OK;
     }
     int nNodes = b->totalRoots;
