@@ -42,3 +42,25 @@ def test_header_is_plain_c(tmp_path):
                         "-I", os.path.join(ROOT, "include"), str(src)],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert p.returncode == 0, p.stdout
+
+
+def test_grid_search_offsets_replay_the_reference_loops():
+    """lgs_gs_offsets (host arithmetic only): the accumulating loops of scan_matcher_grid_search.cpp:74-76,
+    whose lengths depend on the rounding of the running sum -- checked against the loop lengths the
+    unmodified reference produced for tests/golden/scene_gs.npz."""
+    import numpy as np
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "scene_gs.npz"))
+    params = [dict(range_x=0.6, range_y=0.5, range_theta=0.12, step_x=0.05, step_y=0.05, step_theta=0.01),
+              dict(range_x=0.4, range_y=0.4, range_theta=0.1, step_x=0.03, step_y=0.07, step_theta=0.013),
+              dict(range_x=0.3, range_y=0.3, range_theta=0.05, step_x=0.1, step_y=0.1, step_theta=0.005)]
+    for n, ints in enumerate(gold["ints"]):
+        p = params[n % 3]
+        got = [len(capi.gs_offsets(p["range_" + a], p["step_" + a])) for a in ("x", "y", "theta")]
+        assert got == list(ints[4:7])
+    for rng_, step in ((2.0, 0.05), (0.5, 0.005), (0.12, 0.01), (1.0, 0.3), (0.0, 0.1)):
+        want, d = [], -rng_ / 2.0
+        while d <= rng_ / 2.0:
+            want.append(d)
+            d += step
+        assert capi.gs_offsets(rng_, step).tolist() == want
+    assert len(capi.gs_offsets(0.12, 0.01)) == 12          # not 13: the running sum overshoots 0.06
