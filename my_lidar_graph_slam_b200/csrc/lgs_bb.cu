@@ -702,6 +702,7 @@ struct lgs_bb_batch {
     // level counts on the device; lgs_bb_batch_results validates (no pool overflow) and otherwise
     // repeats the run level-synchronously.  Hints = counts of the last run.
     bool haveHints = false, pendingValidate = false;
+    cudaGraphExec_t graphExec = nullptr;  // LGS_BB_GRAPH: the speculative level chain, updated in place run after run
     double hostMs[3] = {0.0, 0.0, 0.0};   // LGS_BB_HOSTTIMING: preamble enqueue, flag-count wait, level enqueue
     long long hostRuns = 0;
     long long hint[kMaxLevels] = {0};
@@ -754,6 +755,7 @@ int lgs_bb_batch_destroy(lgs_bb_batch* b) {
     if (!b) return LGS_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
+    if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
     b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dChunks.release(); b->dQlist.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release(); b->dTab2.release(); b->dSlotQT.release();
     for (auto& sl : b->dSlot) sl.release();
     b->dSortFx.release(); b->dSortFy.release(); b->dSortQx.release(); b->dSortQy.release();
@@ -1137,29 +1139,78 @@ static int bb_run_impl(lgs_bb_batch* b, bool spec) {
 
     if (spec) {
         const auto l0 = std::chrono::steady_clock::now();
+        // Every buffer the level launches need, grown BEFORE anything is enqueued (the launch code's own
+        // reserve() calls are then no-ops), so that the chain below can also be recorded into a CUDA graph.
         for (int h = H; h >= 0; --h) {
             const long long expect = h == H ? b->totalRoots : b->hint[h];
             if (h < H && b->dNodes[h].cap == 0) break;
             const int nMax = h == H ? b->totalRoots : (int)b->dNodes[h].cap;
-            const int* nDev = h == H ? nullptr : b->dCounters.p + 2 + h;      // children of level h + 1
             if (nMax == 0) break;
             if (h > 0) {
                 const size_t want = (size_t)std::min<long long>(std::max<long long>(4LL * expect, 64), 1 << 16);
                 if (b->dNodes[h - 1].cap < want) LGS_CUDA(c, b->dNodes[h - 1].reserve(want));
             }
-            int rc = launchLevel(h, nMax, nDev, expect);
-            if (rc != LGS_OK) return rc;
-            if (slots && h == H) {
-                // survivors expected from the last run (+25 %), never more than the pool can hold
-                b->slotLaunch = (int)std::min<long long>((long long)(b->dNodes[H - 1].cap / 4),
-                                                         b->hint[H - 1] / 4 + b->hint[H - 1] / 16 + 256);
-                rc = launchSlotIndex(b->slotLaunch);
-                if (rc != LGS_OK) return rc;
-            }
+            LGS_CUDA(c, b->dScores[h].reserve(nMax));
+            if (slots && h > 0) LGS_CUDA(c, b->dSlot[h - 1].reserve(std::max<size_t>(b->dNodes[h - 1].cap, 1)));
         }
-        const int rc = finish(H == 0 ? b->totalRoots : (int)b->dNodes[0].cap, H == 0 ? nullptr : b->dCounters.p + 2);
-        if (rc != LGS_OK) return rc;
-        LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, (2 + kMaxLevels) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (slots && H > 0) {
+            const size_t slotStride = b->dNodes[H - 1].cap / 4;
+            LGS_CUDA(c, b->dSlotQT.reserve(std::max<size_t>(slotStride, 1)));
+            if (slotStride > 0) LGS_CUDA(c, b->dTab2.reserve(slotStride * std::max(b->maxUse, 1)));
+        }
+        auto enqueue = [&]() -> int {
+            for (int h = H; h >= 0; --h) {
+                const long long expect = h == H ? b->totalRoots : b->hint[h];
+                if (h < H && b->dNodes[h].cap == 0) break;
+                const int nMax = h == H ? b->totalRoots : (int)b->dNodes[h].cap;
+                const int* nDev = h == H ? nullptr : b->dCounters.p + 2 + h;      // children of level h + 1
+                if (nMax == 0) break;
+                int rc = launchLevel(h, nMax, nDev, expect);
+                if (rc != LGS_OK) return rc;
+                if (slots && h == H) {
+                    // survivors expected from the last run (+25 %), never more than the pool can hold
+                    b->slotLaunch = (int)std::min<long long>((long long)(b->dNodes[H - 1].cap / 4),
+                                                             b->hint[H - 1] / 4 + b->hint[H - 1] / 16 + 256);
+                    rc = launchSlotIndex(b->slotLaunch);
+                    if (rc != LGS_OK) return rc;
+                }
+            }
+            const int rc = finish(H == 0 ? b->totalRoots : (int)b->dNodes[0].cap, H == 0 ? nullptr : b->dCounters.p + 2);
+            if (rc != LGS_OK) return rc;
+            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, (2 + kMaxLevels) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            return LGS_OK;
+        };
+        // LGS_BB_GRAPH=1 (experimental, off by default): the ~25 launches of the chain become one graph
+        // launch -- they carry no host decision (grid sizes are pool capacities, counts stay on the
+        // device).  Meant for many ranks driven from one host, where the launch path is contended
+        // (profiles/r1_scaling.md).  Any capture / instantiate problem falls back to direct launches.
+        bool launched = false;
+        if (getenv("LGS_BB_GRAPH") != nullptr &&
+            cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const long long launchesBefore = c->launches;
+            const int rcCap = enqueue();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t eEnd = cudaStreamEndCapture(c->stream, &graph);
+            if (rcCap == LGS_OK && eEnd == cudaSuccess && graph != nullptr) {
+                cudaGraphExecUpdateResultInfo info;
+                if (b->graphExec != nullptr && cudaGraphExecUpdate(b->graphExec, graph, &info) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(b->graphExec);
+                    b->graphExec = nullptr;
+                }
+                if (b->graphExec == nullptr && cudaGraphInstantiate(&b->graphExec, graph, 0) != cudaSuccess) {
+                    cudaGetLastError();
+                    b->graphExec = nullptr;
+                }
+                if (b->graphExec != nullptr && cudaGraphLaunch(b->graphExec, c->stream) == cudaSuccess) launched = true;
+            }
+            if (graph != nullptr) cudaGraphDestroy(graph);
+            if (!launched) { cudaGetLastError(); c->launches = launchesBefore; }
+        }
+        if (!launched) {
+            const int rc = enqueue();
+            if (rc != LGS_OK) return rc;
+        }
         b->pendingValidate = true;
         b->ran = true;
         b->hostMs[2] += hostMsSince(l0);
