@@ -70,6 +70,13 @@ long long lgs_ctx_launch_count(const lgs_ctx* ctx);
  * upload calls run at full PCIe / C2C speed and asynchronously; optional, any host memory works. */
 int lgs_host_pin(lgs_ctx* ctx, void* ptr, unsigned long long bytes);
 int lgs_host_unpin(lgs_ctx* ctx, void* ptr);
+/* Raw device buffers for record exchange (gather / send / receive buffers of loop detection): plain
+ * cudaMalloc memory of the context's device, so it is reachable from peer devices once peer access is
+ * enabled (lgs_group_create) and registrable with a collective library. */
+int lgs_device_alloc(lgs_ctx* ctx, unsigned long long bytes, void** out);
+int lgs_device_free(lgs_ctx* ctx, void* ptr);
+/* device -> host on the context stream, waits. */
+int lgs_device_download(lgs_ctx* ctx, const void* device_ptr, void* host, unsigned long long bytes);
 const char* lgs_version(void);
 /* Diagnostic (bench.py roofline): measured bandwidth, in GB/s of useful bytes, of warp-wide 8-byte
  * gathers of `row_lanes` (25 or 32) consecutive doubles from an nx x ny array -- the access shape of
@@ -77,11 +84,24 @@ const char* lgs_version(void);
  * few cells (L1 hits) instead of uniformly at random (L2 hits). */
 int lgs_measure_gather_peak(lgs_ctx* ctx, int nx, int ny, int row_lanes, int aligned, int local,
                             double* gbps);
-/* Test hook: width (in cells) of the guard band around cell edges inside which a projected
- * point is re-derived on the host with glibc sin/cos (default 1e-9).  Raising it only moves
- * more points onto the exact host path; results must not change. */
-void lgs_set_edge_eps(double eps);
-double lgs_get_edge_eps(void);
+/* Per-context tuning / diagnostic / test hooks; none of them changes results.  The LGS_* environment
+ * variables only supply the DEFAULTS of a new context (read once inside lgs_ctx_create); no run path
+ * reads the environment or any process-global state afterwards.  Names:
+ *   "edge_eps"          width (in cells) of the guard band around cell edges inside which a projected
+ *                       point is re-derived exactly (default 1e-9; values outside (0, 0.5) restore it).
+ *                       Raising it only moves more points onto the exact paths.
+ *   "csm_flat"          correlative sweep: flattened one-hypothesis-per-thread kernel      (LGS_CSM_FLAT)
+ *   "bb_sync"/"bb_table" branch-and-bound: level-synchronous exact path only       (LGS_BB_SYNC / _TABLE)
+ *   "bb_warp_below"     exact path: node count below which a level scores a warp per node
+ *   "bb_resolve_ulps"   device-only run: half width, in ulps of cos / sin, of the interval that decides
+ *                       near-edge points on the device (default 8; huge values force the exact fallback)
+ *   "bb_blocks_per_sm", "bb_cost_g1" / "_g4" / "_g8" / "_g32"   residency and per-pass cost model (us)
+ *                       of the persistent kernel's warp mappings
+ *   "bb_host_timing", "integ_host_timing", "integ_timing", "integ_diag"   timing reports on stderr
+ *   "integ_side_words"  integration side-buffer size in words (tests shrink it)    (LGS_INTEG_SIDE_WORDS)
+ *   "gs_tables"         grid search through the index tables instead of the fused kernel (LGS_GS_TABLES) */
+int lgs_ctx_set_option(lgs_ctx* ctx, const char* name, double value);
+int lgs_ctx_get_option(const lgs_ctx* ctx, const char* name, double* value);
 
 /* ---- dense device grid ---------------------------------------------------------------------
  * Row-major double[ny][nx], 0.0 = unknown, surrounded by `apron` zero cells on every side so
@@ -246,8 +266,41 @@ int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans,
 int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int n_pairs,
                               const int* pair_scan, lgs_pyramid* const* pyramids,
                               const double* norm_threshold);
+/* Asynchronous: ONE persistent kernel launch on the context stream (hit points, all tree levels with
+ * device-side node counts, winner, verification / CPU-order replay, result records); nothing comes
+ * back to the host until results / records / settle. */
 int lgs_bb_batch_run(lgs_bb_batch* b);
+/* Waits for the run.  A run that met a near-edge point the device could not decide, or a node pool
+ * that was too small, is transparently repeated on the level-synchronous exact path (host-computed
+ * index tables for the near-edge points) before anything is returned. */
 int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out);
+/* The exchange format of loop detection: one 32-byte record per (scan, submap) pair.
+ * Replaces the per-pair outcome of LoopDetectorBranchBound::Detect's inner loop
+ * (mapping/loop_detector_branch_bound.cpp:63-88) before the host tail. */
+typedef struct lgs_loop_record {
+    int found;                  /* scoreMax > scoreThreshold */
+    int ix, iy, it;             /* bestWinX / bestWinY / bestWinTheta */
+    double score;               /* scoreMax, = threshold if !found */
+    long long id;               /* caller's pair id (lgs_bb_batch_set_record_ids), default: index in the batch */
+} lgs_loop_record;
+/* ids[q] is copied into record q by the finalize phase of every later run; takes effect with the
+ * next upload, whose pair count must equal n (n = 0 restores the default). */
+int lgs_bb_batch_set_record_ids(lgs_bb_batch* b, const long long* ids, int n);
+/* Device-side record sink: the finalize phase of every later run stores record q at
+ * device_records[first_slot + q].  The pointer may be memory of ANOTHER GPU mapped into this device
+ * (peer access): the records then cross NVLink as plain stores from the kernel itself, with no host
+ * staging and no separate copy.  NULL restores the batch's own buffer.  The caller orders its reads
+ * after the run (lgs_bb_batch_settle / lgs_ctx_synchronize). */
+int lgs_bb_batch_set_record_sink(lgs_bb_batch* b, lgs_loop_record* device_records, long long first_slot);
+int lgs_bb_batch_records(lgs_bb_batch* b, lgs_loop_record* out);    /* host copy of the records, waits */
+int lgs_bb_batch_settle(lgs_bb_batch* b);    /* wait + validate (+ exact repeat) without copying results out */
+void* lgs_bb_batch_device_records(lgs_bb_batch* b);                 /* the batch's own device record buffer */
+/* Diagnostic (option "bb_host_timing" on before the run): microseconds spent in the phases of the last
+ * device-only run -- [0] hit points, [1] root level, [2 ..] levels H-1 .. 0, then winner, finalize --
+ * and (optional) the lanes-per-node mapping the scoring phases used. */
+int lgs_bb_batch_phase_times(lgs_bb_batch* b, double* us, int* mapping, int n);
+/* How many runs of this batch object were device-only and how many went through the exact path. */
+int lgs_bb_batch_path(const lgs_bb_batch* b, long long* device_runs, long long* exact_runs);
 /* Nodes scored per tree level (index = height) and gathered cells during the last run. */
 int lgs_bb_batch_work(const lgs_bb_batch* b, long long* nodes_per_level, int n_levels,
                       long long* gathers);

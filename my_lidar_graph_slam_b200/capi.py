@@ -48,6 +48,17 @@ MATCH_DTYPE = np.dtype([("found", np.int32), ("ix", np.int32), ("iy", np.int32),
 assert MATCH_DTYPE.itemsize == C.sizeof(MatchResult)
 
 
+class LoopRecord(C.Structure):
+    _fields_ = [("found", C.c_int), ("ix", C.c_int), ("iy", C.c_int), ("it", C.c_int),
+                ("score", C.c_double), ("id", C.c_longlong)]
+
+
+# the 32-byte exchange record of loop detection (lgs_loop_record); "submap" = the caller's pair id
+RECORD_DTYPE = np.dtype([("found", np.int32), ("ix", np.int32), ("iy", np.int32), ("it", np.int32),
+                         ("score", np.float64), ("submap", np.int64)])
+assert RECORD_DTYPE.itemsize == C.sizeof(LoopRecord) == 32
+
+
 class BbParams(C.Structure):
     _fields_ = [("node_height_max", C.c_int), ("range_x", C.c_double), ("range_y", C.c_double),
                 ("range_theta", C.c_double), ("scan_range_max", C.c_double),
@@ -66,8 +77,11 @@ SIGNATURES = {
     "lgs_host_unpin": (C.c_int, [vp, vp]),
     "lgs_measure_gather_peak": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_double)]),
-    "lgs_set_edge_eps": (None, [C.c_double]),
-    "lgs_get_edge_eps": (C.c_double, []),
+    "lgs_device_alloc": (C.c_int, [vp, C.c_ulonglong, C.POINTER(vp)]),
+    "lgs_device_free": (C.c_int, [vp, vp]),
+    "lgs_device_download": (C.c_int, [vp, vp, vp, C.c_ulonglong]),
+    "lgs_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_double]),
+    "lgs_ctx_get_option": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double)]),
     "lgs_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "lgs_ctx_destroy": (C.c_int, [vp]),
     "lgs_ctx_last_error": (C.c_char_p, [vp]),
@@ -107,6 +121,13 @@ SIGNATURES = {
     "lgs_bb_batch_work": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int,
                                     C.POINTER(C.c_longlong)]),
     "lgs_bb_batch_force_replay": (C.c_int, [vp, C.c_int]),
+    "lgs_bb_batch_set_record_ids": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int]),
+    "lgs_bb_batch_set_record_sink": (C.c_int, [vp, vp, C.c_longlong]),
+    "lgs_bb_batch_records": (C.c_int, [vp, C.POINTER(LoopRecord)]),
+    "lgs_bb_batch_settle": (C.c_int, [vp]),
+    "lgs_bb_batch_device_records": (vp, [vp]),
+    "lgs_bb_batch_phase_times": (C.c_int, [vp, c_dp, c_ip, C.c_int]),
+    "lgs_bb_batch_path": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "lgs_bb_match": (C.c_int, [vp, C.POINTER(BbParams), C.POINTER(ScanBatch), C.POINTER(vp), c_dp,
                                C.POINTER(MatchResult)]),
 }
@@ -164,6 +185,18 @@ class Context:
 
     def launch_count(self) -> int:
         return lib().lgs_ctx_launch_count(self.h)
+
+    def set_option(self, name: str, value: float):
+        """Per-context tuning / test hook (lgs_ctx_set_option); never changes results."""
+        self.check(lib().lgs_ctx_set_option(self.h, name.encode(), float(value)))
+
+    def get_option(self, name: str) -> float:
+        v = C.c_double()
+        self.check(lib().lgs_ctx_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def set_edge_eps(self, eps: float):
+        self.set_option("edge_eps", eps)
 
     def adopt(self, child):
         self._children.add(child)
@@ -426,6 +459,45 @@ class BbBatch:
     def force_replay(self, on: bool):
         self.ctx.check(lib().lgs_bb_batch_force_replay(self.h, int(on)))
 
+    def set_record_ids(self, ids):
+        """ids[q] goes into record q (from the next upload on); None restores the batch index."""
+        if ids is None:
+            self.ctx.check(lib().lgs_bb_batch_set_record_ids(self.h, None, 0))
+            return
+        self._ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self.ctx.check(lib().lgs_bb_batch_set_record_ids(
+            self.h, self._ids.ctypes.data_as(C.POINTER(C.c_longlong)), len(self._ids)))
+
+    def set_record_sink(self, device_ptr: int, first_slot: int = 0):
+        """The finalize phase stores record q at device_ptr[first_slot + q] (may be peer memory)."""
+        self.ctx.check(lib().lgs_bb_batch_set_record_sink(self.h, vp(device_ptr) if device_ptr else None,
+                                                          int(first_slot)))
+
+    def records(self) -> np.ndarray:
+        out = np.zeros(max(self.n, 1), dtype=RECORD_DTYPE)
+        self.ctx.check(lib().lgs_bb_batch_records(self.h, out.ctypes.data_as(C.POINTER(LoopRecord))))
+        return out[:self.n]
+
+    def settle(self):
+        self.ctx.check(lib().lgs_bb_batch_settle(self.h))
+
+    def device_records(self) -> int:
+        return lib().lgs_bb_batch_device_records(self.h) or 0
+
+    def phase_times(self):
+        """(us per phase, lanes-per-node per phase) of the last device-only run ("bb_host_timing" on)."""
+        n = self.params.node_height_max + 4
+        us = np.zeros(n, dtype=np.float64)
+        g = np.zeros(n, dtype=np.int32)
+        self.ctx.check(lib().lgs_bb_batch_phase_times(self.h, _dptr(us), g.ctypes.data_as(c_ip), n))
+        return us, g
+
+    def path(self):
+        """(device-only runs, exact-path runs) of this batch object so far."""
+        d, e = C.c_longlong(), C.c_longlong()
+        self.ctx.check(lib().lgs_bb_batch_path(self.h, C.byref(d), C.byref(e)))
+        return d.value, e.value
+
     def close(self):
         if getattr(self, "h", None):
             lib().lgs_bb_batch_destroy(self.h)
@@ -438,8 +510,21 @@ class BbBatch:
             pass
 
 
-def set_edge_eps(eps: float):
-    lib().lgs_set_edge_eps(float(eps))
+def device_alloc(ctx: Context, nbytes: int) -> int:
+    p = vp()
+    ctx.check(lib().lgs_device_alloc(ctx.h, int(nbytes), C.byref(p)))
+    return p.value
+
+
+def device_free(ctx: Context, ptr: int):
+    ctx.check(lib().lgs_device_free(ctx.h, vp(ptr)))
+
+
+def download_records(ctx: Context, device_ptr: int, n: int) -> np.ndarray:
+    """n 32-byte loop records from a device buffer (lgs_device_download)."""
+    out = np.zeros(max(n, 1), dtype=RECORD_DTYPE)
+    ctx.check(lib().lgs_device_download(ctx.h, vp(device_ptr), out.ctypes.data_as(vp), n * RECORD_DTYPE.itemsize))
+    return out[:n]
 
 
 # ---- occupancy-grid integration + host geometry helpers ------------------------------------------

@@ -1,4 +1,5 @@
-// lgs_bb.cu -- branch-and-bound scan matcher (loop detection) on sm_100a.
+// lgs_bb.cu -- branch-and-bound scan matcher (loop detection) on sm_100a: C ABI, host preparation and
+// the level-synchronous EXACT path.  The device-only run (one persistent kernel) is lgs_bb_run.cu.
 //
 // Replaces ScanMatcherBranchBound::OptimizePose(grid, pyramids, scan, pose, thr)
 // (mapping/scan_matcher_branch_bound.cpp:47-163) with ScorePixelAccurate::Score
@@ -8,98 +9,43 @@
 // How the CPU's depth-first search is reproduced exactly by a breadth-first one:
 //  * Node score S(n) is a pure function of (x, y, theta, height).  The CPU visits a node only
 //    if every ancestor scored above the running best, which never drops below the static
-//    threshold thr * NumOfScans().  bb_score_kernel therefore expands, level by level, the
-//    SUPERSET of nodes whose ancestors all score above the static threshold, one thread per
-//    node summing the gathered cells in beam order (bit-identical to the CPU sum).
+//    threshold thr * NumOfScans().  The level kernels therefore expand, level by level, the
+//    SUPERSET of nodes whose ancestors all score above the static threshold, summing the gathered
+//    cells of a node in beam order (bit-identical to the CPU sum).
 //  * Let L* be the superset leaf with the highest score, ties broken by the CPU's LIFO visit
 //    order (carried as an explicit rank: roots are popped x desc, y desc, theta desc; children
 //    (x+w,y+w), (x,y+w), (x+w,y), (x,y); scan_matcher_branch_bound.cpp:85-88, :134-137).  If every
 //    ancestor A of L* has S(A) >= S(L*), the CPU search provably returns L*: no earlier leaf
-//    reaches S(L*), so no ancestor of L* is pruned, and no later leaf beats it.  bb_verify_kernel
+//    reaches S(L*), so no ancestor of L* is pruned, and no later leaf beats it.  The verify step
 //    checks exactly that.
 //  * Otherwise (the win-max maps are not upper bounds where a window index is negative,
-//    SURVEY.md H12) bb_replay_kernel replays the CPU's stack discipline sequentially over the
+//    SURVEY.md H12) the replay step repeats the CPU's stack discipline sequentially over the
 //    stored superset scores; every node the CPU can touch is in the superset.
 //
 // World-coordinate re-projection (H4): the CPU recomputes
 //     ix = floor(((sx + nx*step) + r*cos(theta_t + a_i) - minX) / res)
 // per node and beam.  In exact arithmetic that is I0 + nx with I0 the index at nx = 0; all
 // rounding errors together stay below 1e-11 cells, so I0 + nx is exact unless the fractional
-// cell coordinate lies within the guard band of an edge.  Such (theta, beam) pairs are flagged
-// (bb_flagsearch_kernel / bb_index_kernel) and get per-offset index tables computed on the host
-// with the CPU's own expression (and glibc sin/cos, H5).
+// cell coordinate lies within the guard band of an edge.
 //
-// Two ways to get a beam's cell at node offset (0, 0), chosen per run:
-//  * several queries share a scan (1 scan x 500 submaps): the root level, which visits every
-//    (query, theta), converts the shared hit points on the fly (bb_score_root_kernel) and only the
-//    surviving (query, theta) pairs get index rows (bb_index_slots_kernel); the near-edge flags come
-//    from a sorted-fraction search over the scan's queries instead of an all-pairs pass;
-//  * one scan per query, or more than kFlagInline flagged points: a full per-query index table
-//    (bb_index_kernel), read by every level.
-// After a batch object's first run the levels are launched speculatively over their pools'
-// capacities with device-side node counts (no host round trip per level) and validated afterwards.
+// Two run paths share the node pools, the verify / replay logic and the result records:
+//  * device-only (default, lgs_bb_run.cu): near-edge points are decided on the device by interval
+//    evaluation of the CPU's expression; no host round trip inside a run;
+//  * exact (this file; "bb_sync" / "bb_table" options, and the automatic fallback whenever a
+//    device-only run reports an undecided near-edge point or an overflowed node pool): a full
+//    per-query index table (bb_index_kernel) whose near-edge entries come from per-offset tables
+//    computed on the HOST with the CPU's own expression and glibc sin / cos (H5); one host round
+//    trip per level.
 #include <cfloat>
 #include <cmath>
 
 #include <chrono>
 
-#include "lgs_internal.cuh"
+#include "lgs_bb.cuh"
+
+using namespace lgsbb;
 
 namespace {
-
-constexpr int kFlagCapBB = 1 << 16;
-constexpr int kMaxLevels = 21;
-constexpr int kWarpPerNodeBelow = 8192;     // levels with fewer nodes score one warp per node
-constexpr int kDeepUnrollBelow = 1 << 30;  // levels with fewer nodes keep 32 instead of 16 beams in flight (measured: always better)
-
-struct BbScan {                     // one per DISTINCT (scan, sensor pose): hit points are map independent
-    double sx, sy, st, stepT;
-    int winT, nT, nTpad;            // theta slices, padded to a multiple of 4
-    int nUse, beamBegin;            // usable beams (ScorePixelAccurate range filter)
-    int pad;
-    long long hitBegin;             // into hits: nUse * nTpad (double2), beam-major
-    double invRes;                  // 1 / resolution of the maps this scan is matched against
-    int sortBegin, sortCount;       // this scan's queries sorted by frac(min * invRes) (flag search)
-};
-
-struct BbQuery {
-    double thrAbs;
-    double minX, minY, res, invRes;
-    int nx, ny, pitch;              // submap geometry
-    int offX, offY;                 // window origin (cells) when the grid is a band of a larger map
-    int winX, winY, winT, nT, nTpad;
-    int nrx, nry;                   // roots per axis
-    int nUse, scan;                 // usable beams, index of the distinct scan
-    int rootBegin;                  // first root of this query in the level-H pool
-    long long tabBegin;             // into the base-index table: nUse * nTpad int2, beam-major
-    const double* level[kMaxLevels];// origin() of every pyramid level
-};
-
-struct Node {            // 32 bytes
-    short x, y;          // window offsets of the node's lower-left corner
-    int t;               // theta index 0..nT-1
-    int q;               // query
-    int parent;          // index in the pool one level up (-1 for roots)
-    int childBase;       // child c (visit order) lives at childBase + c * childStride, -1 if pruned
-    int childStride;
-    long long rank;      // CPU visit order among nodes of the same height (lower = earlier)
-};
-
-struct BbBest {          // per query
-    unsigned long long scoreBits;   // max leaf score above threshold (as ordered bits)
-    long long rank;                 // visit rank of the winning leaf
-    int leaf;                       // its index in the level-0 pool
-    int needReplay;
-};
-
-struct BbResult {
-    double score;
-    int found, ix, iy, it;
-    int exactReplay, pad;
-};
-
-struct BbFlag { int q, t, i; };
-constexpr int kFlagInline = 8;      // the root-from-hit-points path handles up to this many near-edge points
 
 // ---- stage A: world hit point of every (distinct scan, usable beam, theta) at node offset (0, 0) ----
 // Threads are theta-fastest so neighbouring lanes differ by one angular step: their hit points are
@@ -126,8 +72,6 @@ __global__ void bb_hit_kernel(const BbScan* __restrict__ scans, const double* __
 // ---- stage B: base cell index in every query's submap + near-edge flags -----------------------------
 // One thread loads a hit point once and converts it for up to kIdxChunk queries that share the
 // scan, so the (L2 resident) hit array is read once per chunk instead of once per query.
-constexpr int kIdxChunk = 16;
-struct IdxChunk { int scan, begin, count; };
 
 __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
                                 const IdxChunk* __restrict__ chunks, const int* __restrict__ qlist,
@@ -165,194 +109,6 @@ __global__ void bb_index_kernel(const BbQuery* __restrict__ qs, const BbScan* __
     }
 }
 
-// ---- stage B': near-edge flags without the all-pairs pass ------------------------------------------------
-// A point is near an edge in query q iff frac((h - min_q) / res) is within eps of 0 or 1, i.e. iff
-// frac(h / res) and frac(min_q / res) are within eps of each other (mod 1, up to ~1e-10 of rounding).
-// The queries of a scan are sorted by frac(min_q / res) per axis on the host; a hit point binary
-// searches the +-delta window (delta = eps + 1e-7, a superset) and runs the exact test of the
-// reference expression only on those candidates.  Every near-edge (query, theta, beam) is registered
-// exactly once: through the x list if x is near an edge, else through the y list.
-__global__ void bb_flagsearch_kernel(const BbScan* __restrict__ scans, const BbQuery* __restrict__ qs,
-                                     const double2* __restrict__ hits, const double* __restrict__ sortFx,
-                                     const int* __restrict__ sortQx, const double* __restrict__ sortFy,
-                                     const int* __restrict__ sortQy, double eps, double delta,
-                                     BbFlag* __restrict__ flags, int* __restrict__ flagCount) {
-    const BbScan& u = scans[blockIdx.z];
-    const int i = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= u.nUse || t >= u.nT) return;
-    const double2 h = hits[u.hitBegin + (long long)i * u.nTpad + t];
-    auto test = [&](int q, bool viaX) {
-        const BbQuery& d = qs[q];
-        const double qx = __dmul_rn(__dsub_rn(h.x, d.minX), d.invRes);
-        const double qy = __dmul_rn(__dsub_rn(h.y, d.minY), d.invRes);
-        const double rx = qx - floor(qx), ry = qy - floor(qy);
-        const bool edgeX = !(rx >= eps && rx <= 1.0 - eps), edgeY = !(ry >= eps && ry <= 1.0 - eps);
-        if (viaX ? !edgeX : (!edgeY || edgeX)) return;
-        const int f = atomicAdd(flagCount, 1);
-        if (f < kFlagCapBB) flags[f] = BbFlag{q, t, i};
-    };
-    auto window = [&](const double* __restrict__ F, const int* __restrict__ Q, double lo, double hi, bool viaX) {
-        int a = 0, b = u.sortCount;                          // first entry >= lo
-        while (a < b) { const int m = (a + b) >> 1; if (F[u.sortBegin + m] < lo) a = m + 1; else b = m; }
-        for (; a < u.sortCount && F[u.sortBegin + a] <= hi; ++a) test(Q[u.sortBegin + a], viaX);
-    };
-    auto axis = [&](double coord, const double* __restrict__ F, const int* __restrict__ Q, bool viaX) {
-        const double a = __dmul_rn(coord, u.invRes);
-        const double fa = a - floor(a);
-        window(F, Q, fa - delta, fa + delta, viaX);
-        if (fa - delta < 0.0) window(F, Q, fa - delta + 1.0, 2.0, viaX);     // wrap around 0 / 1
-        if (fa + delta >= 1.0) window(F, Q, -1.0, fa + delta - 1.0, viaX);
-    };
-    axis(h.x, sortFx, sortQx, true);
-    axis(h.y, sortFy, sortQy, false);
-}
-
-// ---- root level straight from the hit points ------------------------------------------------------------
-// The root level visits every (query, theta), so it would read the whole per-query index table once;
-// instead it converts the shared hit points on the fly (the reference's expression in double: every
-// point outside the eps band floors identically, the <= kFlagInline points inside it come from the
-// host's tables) and only the (query, theta) rows that survive get table rows (bb_index_slots_kernel).
-// A survivor's row slot is childBase / 4: children are allocated four per survivor.
-template <int U>
-__global__ void __launch_bounds__(128)
-bb_score_root_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
-                     const double2* __restrict__ hits, const BbFlag* __restrict__ flags, int nFlag,
-                     const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
-                     Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
-                     Node* __restrict__ next, int nextCap, int* __restrict__ nextCount,
-                     int2* __restrict__ slotQT, int* __restrict__ slotOut, BbBest* __restrict__ best) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = k < nNodes;
-    Node n;
-    bool survive = false;
-    if (active) {
-        n = nodes[k];
-        const BbQuery& d = qs[n.q];
-        const double* __restrict__ lvl = d.level[height];
-        const int stride = d.nTpad;
-        const double2* __restrict__ hb = hits + scans[d.scan].hitBegin + n.t;
-        const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
-        const double minX = d.minX, minY = d.minY, invRes = d.invRes;
-        const int ox = n.x - d.offX, oy = n.y - d.offY;       // node offset minus window origin
-        bool hasFlag = false;
-        for (int f = 0; f < nFlag; ++f) hasFlag |= flags[f].q == n.q && flags[f].t == n.t;
-        double acc = 0.0;
-        auto cellAt = [&](int i) -> const double* {           // slow path: a flagged beam may be among them
-            int ix, iy, ff = -1;
-            for (int f = 0; f < nFlag; ++f)
-                if (flags[f].q == n.q && flags[f].t == n.t && flags[f].i == i) ff = f;
-            if (ff < 0) {
-                const double2 h = __ldg(hb + (long long)i * stride);
-                ix = __double2int_rd(__dmul_rn(__dsub_rn(h.x, minX), invRes)) + ox;
-                iy = __double2int_rd(__dmul_rn(__dsub_rn(h.y, minY), invRes)) + oy;
-            } else {
-                const int* e = exactIdx + (long long)ff * (exactSpanX + exactSpanY);
-                ix = e[n.x + d.winX];
-                iy = e[exactSpanX + n.y + d.winY];
-            }
-            ix = min(max(ix, -1), gx);
-            iy = min(max(iy, -1), gy);
-            return lvl + (long long)iy * pitch + ix;
-        };
-        int i = 0;
-        bool hasNaN = false;
-        if (!hasFlag) {
-#pragma unroll 1
-            for (; i + U <= nb; i += U) {
-                // three separate unrolled loops, so that U hit points, then U map cells are in flight
-                // together (one fused loop lets the compiler serialise the two dependent latencies)
-                double2 hp[U];
-                long long off[U];
-                double v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) hp[u] = __ldg(hb + (long long)(i + u) * stride);
-                // a value that depends on ALL loads gates the rest, so the U loads are issued back to
-                // back (the full-table kernel gets the same effect from its sentinel test)
-                bool odd = false;
-#pragma unroll
-                for (int u = 0; u < U; ++u) odd |= !(hp[u].x == hp[u].x);
-                if (odd) { hasNaN = true; break; }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int ix = min(max(__double2int_rd(__dmul_rn(__dsub_rn(hp[u].x, minX), invRes)) + ox, -1), gx);
-                    const int iy = min(max(__double2int_rd(__dmul_rn(__dsub_rn(hp[u].y, minY), invRes)) + oy, -1), gy);
-                    off[u] = (long long)iy * pitch + ix;
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = __ldg(lvl + off[u]);
-#pragma unroll
-                for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, v[u]);   // unknown cells add 0.0
-            }
-        }
-        (void)hasNaN;                        // a NaN hit point simply continues on the one-beam path below
-        for (; i < nb; ++i) acc = __dadd_rn(acc, __ldg(cellAt(i)));
-        scores[k] = acc;
-        if (acc > d.thrAbs) {                                     // :108 with scoreMax >= threshold
-            if (height == 0)
-                atomicMax(&best[n.q].scoreBits, (unsigned long long)__double_as_longlong(acc));
-            else
-                survive = true;
-        } else {
-            nodes[k].childBase = -1;
-        }
-    }
-    if (height == 0) return;
-    const unsigned m = __ballot_sync(0xffffffffu, survive);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int cnt = __popc(m);
-    int base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(nextCount, 4 * cnt);
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (!survive) return;
-    const int r = __popc(m & ((1u << lane) - 1u));
-    nodes[k].childBase = base + r;
-    nodes[k].childStride = cnt;
-    if (base + 4 * cnt > nextCap) return;       // the pool is too small: this run is repeated
-    const int slot = (base >> 2) + r;           // nextCount only ever grows by multiples of four
-    slotQT[slot] = make_int2(n.q, n.t);
-    const int w = 1 << (height - 1);
-    const int dx[4] = {w, 0, w, 0}, dy[4] = {w, w, 0, 0};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        Node ch;
-        ch.x = (short)(n.x + dx[c]); ch.y = (short)(n.y + dy[c]); ch.t = n.t; ch.q = n.q;
-        ch.rank = n.rank * 4 + c;
-        ch.parent = k; ch.childBase = -1; ch.childStride = 0;
-        next[base + c * cnt + r] = ch;
-        slotOut[base + c * cnt + r] = slot;
-    }
-}
-
-// ---- index rows of the surviving (query, theta) pairs ------------------------------------------------------
-// tab2[beam * slotStride + slot] = cell of the beam at node offset (0, 0); slots of neighbouring thetas
-// are neighbours (warp-aggregated allocation), so the deeper levels' table reads stay coalesced.
-__global__ void bb_index_slots_kernel(const BbQuery* __restrict__ qs, const BbScan* __restrict__ scans,
-                                      const double2* __restrict__ hits, const int2* __restrict__ slotQT,
-                                      const int* __restrict__ childCount, int slotStride,
-                                      const BbFlag* __restrict__ flags, int nFlag, int2* __restrict__ tab2) {
-    constexpr int kBeamsPerThread = 8;
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= min(__ldg(childCount) >> 2, slotStride)) return;
-    const int2 qt = slotQT[slot];
-    const BbQuery& d = qs[qt.x];
-    const double2* __restrict__ hb = hits + scans[d.scan].hitBegin + qt.y;
-    const double minX = d.minX, minY = d.minY, invRes = d.invRes;
-    const int offX = d.offX, offY = d.offY, nb = d.nUse, stride = d.nTpad;
-#pragma unroll
-    for (int j = 0; j < kBeamsPerThread; ++j) {
-        const int i = blockIdx.y * kBeamsPerThread + j;
-        if (i >= nb) break;
-        const double2 h = __ldg(hb + (long long)i * stride);
-        int2 v = make_int2(__double2int_rd(__dmul_rn(__dsub_rn(h.x, minX), invRes)) - offX,
-                           __double2int_rd(__dmul_rn(__dsub_rn(h.y, minY), invRes)) - offY);
-        for (int f = 0; f < nFlag; ++f)
-            if (flags[f].q == qt.x && flags[f].t == qt.y && flags[f].i == i) v = make_int2(INT_MIN, f);
-        tab2[(long long)i * slotStride + slot] = v;
-    }
-}
-
 // ---- roots --------------------------------------------------------------------------------------
 __global__ void bb_roots_kernel(const BbQuery* __restrict__ qs, int nq, int height,
                                 Node* __restrict__ pool) {
@@ -374,23 +130,16 @@ __global__ void bb_roots_kernel(const BbQuery* __restrict__ qs, int nq, int heig
     pool[d.rootBegin + k] = n;
 }
 
-// ---- node scoring + expansion (hot kernel) -------------------------------------------------------
-// One thread per node; ScorePixelAccurate::Score on pyramid level `height`, summed in beam order.
-// Survivors of a warp allocate their children together (one atomic per warp) and store them
-// child-major, so the next level's lanes again walk neighbouring thetas with equal offsets.
+// ---- node scoring + expansion, one thread per node (exact path) -----------------------------------
+// ScorePixelAccurate::Score on pyramid level `height`, summed in beam order, through the full
+// per-query index table.  Survivors of a warp allocate their children together (one atomic per warp)
+// and store them child-major, so the next level's lanes again walk neighbouring thetas.
 template <int U>                           // beams in flight per thread (two dependent latencies each)
 __global__ void __launch_bounds__(128)
 bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                 const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
-                Node* __restrict__ nodes, double* __restrict__ scores, int nMax,
-                const int* __restrict__ nDev, Node* __restrict__ next, int nextCap,
-                int* __restrict__ nextCount, BbBest* __restrict__ best,
-                const int* __restrict__ slotIn, int* __restrict__ slotOut, int slotStride) {
-    // slotIn != nullptr: `tab` holds one row per surviving (query, theta) (bb_index_slots_kernel) and
-    // slotIn[k] is node k's row; otherwise `tab` is the full per-query table.
-    // nDev (speculative, sync-free runs): the level's node count lives on the device; the launch
-    // covers the pool capacity nMax and surplus threads leave here
-    const int nNodes = nDev ? min(__ldg(nDev), nMax) : nMax;
+                Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
+                Node* __restrict__ next, int nextCap, int* __restrict__ nextCount, BbBest* __restrict__ best) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = k < nNodes;
     Node n;
@@ -399,8 +148,8 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
         n = nodes[k];
         const BbQuery& d = qs[n.q];
         const double* __restrict__ lvl = d.level[height];
-        const int stride = slotIn ? slotStride : d.nTpad;
-        const int2* __restrict__ tb = slotIn ? tab + slotIn[k] : tab + d.tabBegin + n.t;
+        const int stride = d.nTpad;
+        const int2* __restrict__ tb = tab + d.tabBegin + n.t;
         const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
         const int nxo = n.x, nyo = n.y;
         double acc = 0.0;
@@ -475,25 +224,18 @@ bb_score_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
         ch.rank = n.rank * 4 + c;
         ch.parent = k; ch.childBase = -1; ch.childStride = 0;
         next[base + c * cnt + r] = ch;
-        if (slotIn) slotOut[base + c * cnt + r] = slotIn[k];
     }
 }
 
-// ---- node scoring, one WARP per node (small levels) ------------------------------------------------
-// A level with few nodes cannot hide the two dependent memory latencies (index table, then map
-// cell) of a 1000-beam walk with one thread per node.  Here the 32 lanes fetch the node's beams 512
-// at a time (16 independent load pairs in flight per lane), park the values in shared memory in
-// beam order, and lane 0 then adds them strictly in that order: still bit-identical to the CPU sum,
-// but a level costs ~2 memory latencies + one dependent add chain instead of ~70 latencies.
+// ---- node scoring, one WARP per node (exact path, small levels) ----------------------------------------
+// The 32 lanes fetch the node's beams 512 at a time, park the values in shared memory in beam order,
+// and lane 0 adds them strictly in that order: still bit-identical to the CPU sum.
 __global__ void __launch_bounds__(128)
 bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ tab,
                      const int* __restrict__ exactIdx, int exactSpanX, int exactSpanY, int height,
-                     Node* __restrict__ nodes, double* __restrict__ scores, int nMax,
-                     const int* __restrict__ nDev, Node* __restrict__ next, int nextCap,
-                     int* __restrict__ nextCount, BbBest* __restrict__ best,
-                     const int* __restrict__ slotIn, int* __restrict__ slotOut, int slotStride) {
+                     Node* __restrict__ nodes, double* __restrict__ scores, int nNodes,
+                     Node* __restrict__ next, int nextCap, int* __restrict__ nextCount, BbBest* __restrict__ best) {
     constexpr int CH = 16, STAGE = 32 * CH;
-    const int nNodes = nDev ? min(__ldg(nDev), nMax) : nMax;
     __shared__ double sv[4][STAGE];
     const int wib = threadIdx.x >> 5;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -502,8 +244,8 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
     const Node n = nodes[k];
     const BbQuery& d = qs[n.q];
     const double* __restrict__ lvl = d.level[height];
-    const int stride = slotIn ? slotStride : d.nTpad;
-    const int2* __restrict__ tb = slotIn ? tab + slotIn[k] : tab + d.tabBegin + n.t;
+    const int stride = d.nTpad;
+    const int2* __restrict__ tb = tab + d.tabBegin + n.t;
     const int pitch = d.pitch, gx = d.nx, gy = d.ny, nb = d.nUse;
     const int nxo = n.x, nyo = n.y;
     double acc = 0.0;
@@ -517,31 +259,19 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
             // a beam past the end projects far outside -> clamps into the zero apron (adds 0.0)
             c[u] = i < nb ? __ldg(tb + (long long)i * stride) : make_int2(-(1 << 28), -(1 << 28));
         }
-        bool exact = false;
 #pragma unroll
-        for (int u = 0; u < CH; ++u) exact |= c[u].x == INT_MIN;
-        if (!__any_sync(0xffffffffu, exact)) {      // branch free: all gathers in flight together
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                const int ix = min(max(c[u].x + nxo, -1), gx);
-                const int iy = min(max(c[u].y + nyo, -1), gy);
-                v[u] = __ldg(lvl + (long long)iy * pitch + ix);
+        for (int u = 0; u < CH; ++u) {
+            int ix, iy;
+            if (c[u].x != INT_MIN) {
+                ix = c[u].x + nxo; iy = c[u].y + nyo;
+            } else {   // near-edge beam: indices from the host-computed exact table
+                const int* e = exactIdx + (long long)c[u].y * (exactSpanX + exactSpanY);
+                ix = e[nxo + d.winX];
+                iy = e[exactSpanX + nyo + d.winY];
             }
-        } else {
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                int ix, iy;
-                if (c[u].x != INT_MIN) {
-                    ix = c[u].x + nxo; iy = c[u].y + nyo;
-                } else {   // near-edge beam: indices from the host-computed exact table
-                    const int* e = exactIdx + (long long)c[u].y * (exactSpanX + exactSpanY);
-                    ix = e[nxo + d.winX];
-                    iy = e[exactSpanX + nyo + d.winY];
-                }
-                ix = min(max(ix, -1), gx);
-                iy = min(max(iy, -1), gy);
-                v[u] = __ldg(lvl + (long long)iy * pitch + ix);
-            }
+            ix = min(max(ix, -1), gx);
+            iy = min(max(iy, -1), gy);
+            v[u] = __ldg(lvl + (long long)iy * pitch + ix);
         }
 #pragma unroll
         for (int u = 0; u < CH; ++u) sv[wib][u * 32 + lane] = v[u];
@@ -580,14 +310,12 @@ bb_score_warp_kernel(const BbQuery* __restrict__ qs, const int2* __restrict__ ta
         ch.rank = n.rank * 4 + cidx;
         ch.parent = k; ch.childBase = -1; ch.childStride = 0;
         next[slot + cidx] = ch;
-        if (slotIn) slotOut[slot + cidx] = slotIn[k];
     }
 }
 
 // ---- winner among the leaves: (score desc, rank asc) ---------------------------------------------
 __global__ void bb_leaf_rank_kernel(const Node* __restrict__ leaves, const double* __restrict__ scores,
-                                    int nMax, const int* __restrict__ nDev, BbBest* __restrict__ best) {
-    const int n = nDev ? min(__ldg(nDev), nMax) : nMax;
+                                    int n, BbBest* __restrict__ best) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int q = leaves[k].q;
@@ -596,8 +324,7 @@ __global__ void bb_leaf_rank_kernel(const Node* __restrict__ leaves, const doubl
 }
 
 __global__ void bb_leaf_pick_kernel(const Node* __restrict__ leaves, const double* __restrict__ scores,
-                                    int nMax, const int* __restrict__ nDev, BbBest* __restrict__ best) {
-    const int n = nDev ? min(__ldg(nDev), nMax) : nMax;
+                                    int n, BbBest* __restrict__ best) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int q = leaves[k].q;
@@ -606,16 +333,13 @@ __global__ void bb_leaf_pick_kernel(const Node* __restrict__ leaves, const doubl
         best[q].leaf = k;
 }
 
-struct LevelView { const Node* nodes; const double* scores; };
-struct LevelViews { LevelView v[kMaxLevels]; };
-
 // ---- verification of the winner's ancestor chain + result record -----------------------------------
 __global__ void bb_verify_kernel(const BbQuery* __restrict__ qs, int nq, int heightMax, LevelViews lv,
                                  BbBest* __restrict__ best, BbResult* __restrict__ res, int forceReplay) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     BbResult r;
-    r.pad = 0; r.exactReplay = 0;
+    r.fixups = 0; r.exactReplay = 0;
     BbBest b = best[q];
     if (b.scoreBits == 0ull || b.leaf < 0) {
         // No superset leaf above the threshold: the CPU cannot accept any leaf either.
@@ -662,7 +386,7 @@ __global__ void bb_replay_kernel(const BbQuery* __restrict__ qs, int nq, int hei
         }
     }
     BbResult r;
-    r.pad = 0; r.exactReplay = 1;
+    r.fixups = 0; r.exactReplay = 1;
     if (bestLeaf >= 0) {
         const Node leaf = lv.v[0].nodes[bestLeaf];
         r.found = 1; r.score = bestScore; r.ix = leaf.x; r.iy = leaf.y; r.it = leaf.t - d.winT;
@@ -675,63 +399,207 @@ __global__ void bb_replay_kernel(const BbQuery* __restrict__ qs, int nq, int hei
 __global__ void bb_init_best_kernel(BbBest* best, int nq) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    best[q].scoreBits = 0ull; best[q].rank = 0x7fffffffffffffffLL; best[q].leaf = -1; best[q].needReplay = 0;
+    BbBest b;
+    b.scoreBits = 0ull; b.rank = 0x7fffffffffffffffLL; b.leaf = -1; b.needReplay = 0;
+    b.rankLeaf = ~0ull; b.fixups = 0; b.pad = 0;
+    best[q] = b;
 }
 
 }  // namespace
 
-struct lgs_bb_batch {
-    lgs_ctx* ctx = nullptr;
-    lgs_bb_params params{};
-    int nq = 0, H = 0;
-    int maxRoots = 0;
-    int maxNTpad = 0, maxUse = 0;   // launch extents of the projection kernels
-    int spanX = 0, spanY = 0;
-    std::vector<BbQuery> qs;
-    std::vector<BbScan> us;         // distinct (scan, pose) pairs
-    std::vector<IdxChunk> chunks;   // <= kIdxChunk queries of one scan each
-    std::vector<int> qlist;         // queries grouped by scan
-    DevBuf<IdxChunk> dChunks;
-    DevBuf<int> dQlist;
-    std::vector<double> hAngles, hRanges;
-    std::vector<int> fixups;
-    long long nTab = 0;
-    int totalRoots = 0;
-    bool uploaded = false, ran = false, forceReplay = false;
-    // Speculative (sync-free) runs: launches are sized by the node pools' capacities and read the
-    // level counts on the device; lgs_bb_batch_results validates (no pool overflow) and otherwise
-    // repeats the run level-synchronously.  Hints = counts of the last run.
-    bool haveHints = false, pendingValidate = false;
-    cudaGraphExec_t graphExec = nullptr;  // LGS_BB_GRAPH: the speculative level chain, updated in place run after run
-    double hostMs[3] = {0.0, 0.0, 0.0};   // LGS_BB_HOSTTIMING: preamble enqueue, flag-count wait, level enqueue
-    long long hostRuns = 0;
-    long long hint[kMaxLevels] = {0};
-    long long nodesPerLevel[kMaxLevels] = {0};
-    long long gathers = 0;
-    DevBuf<BbQuery> dQs;
-    DevBuf<BbScan> dUs;
-    DevBuf<double2> dHits;
-    DevBuf<double> dAngles, dRanges;
-    DevBuf<int2> dTab;               // full per-query index table (only the many-flags fallback path)
-    DevBuf<int2> dTab2, dSlotQT;     // rows of the surviving (query, theta) pairs; their (q, t)
-    DevBuf<int> dSlot[kMaxLevels];   // row slot of every node of a level
-    DevBuf<double> dSortFx, dSortFy; // per scan: its queries sorted by frac(min * invRes), per axis
-    DevBuf<int> dSortQx, dSortQy;
-    std::vector<double> hSortFx, hSortFy;
-    std::vector<int> hSortQx, hSortQy;
-    bool slotPath = false;           // the last run scored the root level from the hit points
-    int nFlagRun = 0;                // near-edge points of the last run
-    int slotLaunch = 0;              // slots the speculative run built index rows for
-    DevBuf<BbFlag> dFlags;
-    DevBuf<int> dCounters;          // [0] flag count, [1 + h] node count of level h
-    DevBuf<int> dExact;
-    DevBuf<Node> dNodes[kMaxLevels];
-    DevBuf<double> dScores[kMaxLevels];
-    DevBuf<BbBest> dBest;
-    DevBuf<BbResult> dRes;
-    PinBuf<BbResult> hRes;
-    PinBuf<int> hCounters;
-};
+namespace {
+
+double ms_since(std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+}
+
+size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// The level-synchronous exact path: full per-query index table, near-edge points from the host (the
+// CPU's expression with glibc sin / cos), one host round trip per level.  Leaves the results in
+// hRes once the context stream has drained.
+int bb_run_exact(lgs_bb_batch* b) {
+    lgs_ctx* c = b->ctx;
+    const int H = b->H, n = b->nq;
+    for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
+    b->gathers = 0;
+    b->pendingValidate = false;
+    b->lastRunDevice = false;
+    b->needDeliver = true;
+    b->exactRuns++;
+    char* blob = b->dBlob.p;
+    const BbQuery* dQs = reinterpret_cast<const BbQuery*>(blob + b->offQs);
+    const BbScan* dUs = reinterpret_cast<const BbScan*>(blob + b->offUs);
+    const int* dQlist = reinterpret_cast<const int*>(blob + b->offQlist);
+    const IdxChunk* dChunks = reinterpret_cast<const IdxChunk*>(blob + b->offChunks);
+    const double* dAngles = reinterpret_cast<const double*>(blob + b->offAngles);
+    const double* dRanges = reinterpret_cast<const double*>(blob + b->offRanges);
+    LGS_CUDA(c, b->dCounters.reserve(kCounters));
+    LGS_CUDA(c, b->dFlags.reserve(kFlagCapBB));
+    LGS_CUDA(c, b->dHits.reserve(std::max<long long>(b->nHits, 1)));
+    LGS_CUDA(c, b->dTab.reserve(std::max<long long>(b->nTab, 1)));
+    LGS_CUDA(c, b->dNodes[H].reserve(b->totalRoots));
+    LGS_CUDA(c, b->dScores[H].reserve(b->totalRoots));
+    LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, kCounters * sizeof(int), c->stream));
+    const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
+    for (size_t u0 = 0; u0 < b->us.size(); u0 += 65535) {
+        const unsigned nu = (unsigned)std::min<size_t>(65535, b->us.size() - u0);
+        bb_hit_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(dUs + u0, dAngles, dRanges, b->dHits.p);
+        LGS_LAUNCH_CHECK(c);
+    }
+    {
+        dim3 gridR((b->maxRoots + 127) / 128, n);
+        bb_roots_kernel<<<gridR, 128, 0, c->stream>>>(dQs, n, H, b->dNodes[H].p);
+        LGS_LAUNCH_CHECK(c);
+        bb_init_best_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(b->dBest.p, n);
+        LGS_LAUNCH_CHECK(c);
+    }
+    for (size_t c0 = 0; c0 < b->chunks.size(); c0 += 65535) {
+        const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
+        bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(dQs, dUs, dChunks + c0, dQlist, b->dHits.p,
+                                                                 c->opt.edgeEps, b->dTab.p, b->dFlags.p,
+                                                                 b->dCounters.p + kCtrFlags);
+        LGS_LAUNCH_CHECK(c);
+    }
+    LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int nFlag = b->hCounters.p[kCtrFlags];
+    const int spanX = b->spanX, spanY = b->spanY;
+    std::fill(b->fixups.begin(), b->fixups.end(), 0);
+    if (nFlag > kFlagCapBB)
+        return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: %d near-edge points exceed the fix-up list", nFlag);
+    if (nFlag > 0) {
+        // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
+        std::vector<BbFlag> fl(nFlag);
+        LGS_CUDA(c, cudaMemcpy(fl.data(), b->dFlags.p, nFlag * sizeof(BbFlag), cudaMemcpyDeviceToHost));
+        std::vector<int> exact((size_t)nFlag * (spanX + spanY), 0);
+        for (int k = 0; k < nFlag; ++k) {
+            const BbQuery& d = b->qs[fl[k].q];
+            const BbScan& u = b->us[d.scan];
+            const double stepX = d.res, stepY = d.res;
+            const double theta = u.st + static_cast<double>(fl[k].t - d.winT) * u.stepT;
+            const double a = theta + b->hAngles[u.beamBegin + fl[k].i];
+            const double cosT = std::cos(a), sinT = std::sin(a);
+            const double r = b->hRanges[u.beamBegin + fl[k].i];
+            int* e = exact.data() + (size_t)k * (spanX + spanY);
+            for (int o = 0; o < spanX; ++o) {
+                const double px = u.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
+                e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res)) - d.offX;
+            }
+            for (int o = 0; o < spanY; ++o) {
+                const double py = u.sy + static_cast<double>(o - d.winY) * stepY;
+                e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res)) - d.offY;
+            }
+            b->fixups[fl[k].q]++;
+        }
+        LGS_CUDA(c, b->dExact.reserve(exact.size()));
+        LGS_CUDA(c, cudaMemcpy(b->dExact.p, exact.data(), exact.size() * sizeof(int), cudaMemcpyHostToDevice));
+    } else {
+        LGS_CUDA(c, b->dExact.reserve(1));
+    }
+    const int warpBelow = c->opt.bbWarpBelow;
+    int nNodes = b->totalRoots;
+    for (int h = H; h >= 0; --h) {
+        b->nodesPerLevel[h] = nNodes;
+        if (nNodes == 0) break;
+        int* nextCount = b->dCounters.p + kCtrChild + h;
+        if (h > 0 && b->dNodes[h - 1].cap < (size_t)std::min<long long>(4LL * nNodes, 1 << 16))
+            LGS_CUDA(c, b->dNodes[h - 1].reserve(std::min<long long>(4LL * nNodes, 1 << 16)));
+        LGS_CUDA(c, b->dScores[h].reserve(std::max<size_t>(nNodes, b->dNodes[h].cap)));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            LGS_CUDA(c, cudaMemsetAsync(nextCount, 0, sizeof(int), c->stream));
+            Node* next = h > 0 ? b->dNodes[h - 1].p : nullptr;
+            const int nextCap = h > 0 ? (int)std::min<size_t>(b->dNodes[h - 1].cap, 0x7fffffff) : 0;
+            if (nNodes >= warpBelow)
+                bb_score_kernel<32><<<(nNodes + 127) / 128, 128, 0, c->stream>>>(
+                    dQs, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p, nNodes, next,
+                    nextCap, nextCount, b->dBest.p);
+            else
+                bb_score_warp_kernel<<<(nNodes + 3) / 4, 128, 0, c->stream>>>(
+                    dQs, b->dTab.p, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p, nNodes, next,
+                    nextCap, nextCount, b->dBest.p);
+            LGS_LAUNCH_CHECK(c);
+            if (h == 0) break;
+            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p + kCtrChild + h, nextCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+            const int want = b->hCounters.p[kCtrChild + h];
+            if ((size_t)want <= b->dNodes[h - 1].cap) break;
+            if (attempt == 1) return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: level %d pool overflow", h - 1);
+            LGS_CUDA(c, b->dNodes[h - 1].reserve((size_t)want + want / 4));   // grow, redo this level
+        }
+        nNodes = h > 0 ? b->hCounters.p[kCtrChild + h] : 0;
+    }
+    const int nLeaves = (int)b->nodesPerLevel[0];
+    if (nLeaves > 0) {
+        bb_leaf_rank_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, b->dBest.p);
+        LGS_LAUNCH_CHECK(c);
+        bb_leaf_pick_kernel<<<(nLeaves + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, nLeaves, b->dBest.p);
+        LGS_LAUNCH_CHECK(c);
+    }
+    LevelViews lv;
+    for (int h = 0; h < kMaxLevels; ++h) lv.v[h] = LevelView{b->dNodes[h].p, b->dScores[h].p};
+    bb_verify_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(dQs, n, H, lv, b->dBest.p, b->dRes.p, b->forceReplay ? 1 : 0);
+    LGS_LAUNCH_CHECK(c);
+    bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(dQs, n, H, lv, b->dBest.p, b->dRes.p);
+    LGS_LAUNCH_CHECK(c);
+    LGS_CUDA(c, cudaMemcpyAsync(b->hRes.p, b->dRes.p, n * sizeof(BbResult), cudaMemcpyDeviceToHost, c->stream));
+    for (int h = 0; h <= H; ++h) b->hint[h] = std::max(b->hint[h], b->nodesPerLevel[h]);
+    return LGS_OK;
+}
+
+void bb_fill_records(const lgs_bb_batch* b, lgs_loop_record* out) {
+    for (int q = 0; q < b->nq; ++q) {
+        const BbResult& r = b->hRes.p[q];
+        out[q].found = r.found; out[q].ix = r.ix; out[q].iy = r.iy; out[q].it = r.it;
+        out[q].score = r.score;
+        out[q].id = b->ids.empty() ? (long long)q : b->ids[q];
+    }
+}
+
+// The exact path leaves its results on the host; the 32-byte records go to the same place the
+// device-only run's finalize phase writes them (the sink, or the batch's own record buffer).
+int bb_deliver_records(lgs_bb_batch* b) {
+    lgs_ctx* c = b->ctx;
+    LGS_CUDA(c, b->dRec.reserve(b->nq));
+    LGS_CUDA(c, b->hRec.reserve(b->nq));
+    bb_fill_records(b, b->hRec.p);
+    lgs_loop_record* dst = b->sink ? b->sink + b->sinkFirst : b->dRec.p;
+    LGS_CUDA(c, cudaMemcpyAsync(dst, b->hRec.p, b->nq * sizeof(lgs_loop_record), cudaMemcpyDefault, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LGS_OK;
+}
+
+// Wait for the last run; a device-only run that could not decide a near-edge point or overflowed a
+// node pool is repeated on the exact path.
+int bb_settle(lgs_bb_batch* b) {
+    lgs_ctx* c = b->ctx;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (b->pendingValidate) {
+        b->pendingValidate = false;
+        const int H = b->H;
+        const int* hc = b->hCounters.p;
+        const bool ok = hc[kCtrDone] == 1 && hc[kCtrOverflow] == 0 && hc[kCtrUnresolved] == 0;
+        for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
+        b->nodesPerLevel[H] = b->totalRoots;
+        for (int h = 0; h < H; ++h) b->nodesPerLevel[h] = hc[kCtrChild + h + 1];
+        for (int h = 0; h <= H; ++h) b->hint[h] = std::max(b->hint[h], b->nodesPerLevel[h]);
+        if (ok) {
+            for (int q = 0; q < b->nq; ++q) b->fixups[q] = b->hRes.p[q].fixups;
+        } else {
+            const int rc = bb_run_exact(b);
+            if (rc != LGS_OK) return rc;
+            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (b->needDeliver) {
+        b->needDeliver = false;
+        return bb_deliver_records(b);
+    }
+    return LGS_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -741,26 +609,30 @@ int lgs_bb_batch_create(lgs_ctx* ctx, const lgs_bb_params* p, lgs_bb_batch** out
     if (p->node_height_max < 0 || p->node_height_max >= kMaxLevels - 1 || !(p->range_x >= 0) ||
         !(p->range_y >= 0) || !(p->range_theta >= 0))
         return lgs_fail(ctx, LGS_ERR_INVALID, "bb_batch_create: bad parameters");
+    LGS_CUDA(ctx, cudaSetDevice(ctx->device));
     lgs_bb_batch* b = new lgs_bb_batch();
     b->ctx = ctx; b->params = *p; b->H = p->node_height_max;
+    if (cudaEventCreateWithFlags(&b->evUpload, cudaEventDisableTiming) != cudaSuccess) {
+        delete b;
+        return lgs_fail(ctx, LGS_ERR_CUDA, "bb_batch_create: cudaEventCreate");
+    }
     *out = b;
     return LGS_OK;
 }
 
 int lgs_bb_batch_destroy(lgs_bb_batch* b) {
-    if (b && b->hostRuns > 0 && getenv("LGS_BB_HOSTTIMING"))
-        fprintf(stderr, "[lgs bb host] %lld speculative runs of %d queries: per run preamble enqueue %.3f ms, flag-count "
-                "wait %.3f ms, level enqueue %.3f ms\n", b->hostRuns, b->nq, b->hostMs[0] / b->hostRuns,
-                b->hostMs[1] / b->hostRuns, b->hostMs[2] / b->hostRuns);
     if (!b) return LGS_OK;
+    if (b->hostRuns > 0 && b->ctx->opt.bbHostTiming)
+        fprintf(stderr, "[lgs bb host] %lld runs of %d queries (%lld device-only, %lld exact): per run upload %.3f ms, "
+                "run enqueue %.3f ms, results wait %.3f ms\n", b->hostRuns, b->nq, b->deviceRuns, b->exactRuns,
+                b->hostMs[0] / b->hostRuns, b->hostMs[1] / b->hostRuns, b->hostMs[2] / b->hostRuns);
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
-    b->dQs.release(); b->dUs.release(); b->dHits.release(); b->dChunks.release(); b->dQlist.release(); b->dAngles.release(); b->dRanges.release(); b->dTab.release(); b->dTab2.release(); b->dSlotQT.release();
-    for (auto& sl : b->dSlot) sl.release();
-    b->dSortFx.release(); b->dSortFy.release(); b->dSortQx.release(); b->dSortQy.release();
-    b->dFlags.release(); b->dCounters.release(); b->dExact.release(); b->dBest.release();
-    b->dRes.release(); b->hRes.release(); b->hCounters.release();
+    if (b->evUpload) cudaEventDestroy(b->evUpload);
+    b->hBlob.release(); b->dBlob.release(); b->dHitsFix.release(); b->dHitsFixT.release(); b->dHits.release(); b->dTab.release();
+    b->dChunks.release(); b->dFlags.release(); b->dCounters.release(); b->dCtr.release(); b->dExact.release();
+    b->dBest.release(); b->dRes.release(); b->dRec.release(); b->hRes.release(); b->hCounters.release();
+    b->hRec.release(); b->dPhase.release(); b->hPhase.release();
     for (int h = 0; h < kMaxLevels; ++h) { b->dNodes[h].release(); b->dScores[h].release(); }
     delete b;
     return LGS_OK;
@@ -769,6 +641,20 @@ int lgs_bb_batch_destroy(lgs_bb_batch* b) {
 int lgs_bb_batch_force_replay(lgs_bb_batch* b, int on) {
     if (!b) return LGS_ERR_INVALID;
     b->forceReplay = on != 0;
+    return LGS_OK;
+}
+
+int lgs_bb_batch_set_record_ids(lgs_bb_batch* b, const long long* ids, int n) {
+    if (!b || n < 0 || (n > 0 && !ids)) return LGS_ERR_INVALID;
+    b->ids.assign(ids, ids + n);
+    b->uploaded = false;            // shipped with the next upload
+    return LGS_OK;
+}
+
+int lgs_bb_batch_set_record_sink(lgs_bb_batch* b, lgs_loop_record* deviceRecords, long long firstSlot) {
+    if (!b || firstSlot < 0) return LGS_ERR_INVALID;
+    b->sink = deviceRecords;
+    b->sinkFirst = deviceRecords ? firstSlot : 0;
     return LGS_OK;
 }
 
@@ -783,6 +669,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
                               const double* normThr) {
     if (!b || !scans) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
+    const auto t0 = std::chrono::steady_clock::now();
     const int n = nPairs;
     if (n < 0 || scans->n_scans < 0 || (n > 0 && (!scans->beam_begin || !scans->sensor_pose || !pyramids)))
         return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_upload: bad arguments");
@@ -791,17 +678,20 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         if (sq < 0 || sq >= scans->n_scans)
             return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_upload: pair %d names scan %d of %d", q, sq, scans->n_scans);
     }
+    if (!b->ids.empty() && (int)b->ids.size() != n)
+        return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_upload: %zu record ids for %d pairs", b->ids.size(), n);
     LGS_CUDA(c, cudaSetDevice(c->device));
     const lgs_bb_params& p = b->params;
     const int H = b->H;
-    b->uploaded = false; b->ran = false;
+    b->uploaded = false; b->ran = false; b->pendingValidate = false;
     b->nq = n;
     b->qs.assign(n, BbQuery{});
     b->us.clear();
     b->fixups.assign(n, 0);
     b->hAngles.clear(); b->hRanges.clear();
     b->maxRoots = 0; b->maxNTpad = 0; b->maxUse = 0; b->spanX = 0; b->spanY = 0;
-    long long nTab = 0, roots = 0, nHits = 0;
+    b->maxAbsCells = 0.0; b->maxReachCells = 0.0;
+    long long nTab = 0, roots = 0, nHits = 0, nHitsT = 0;
     const int winSizeMax = 1 << H;
     // Pairs that name the same scan share its projected hit points (1 scan x many submaps).
     std::vector<int> scanToUnique(std::max(scans->n_scans, 1), -1);
@@ -861,17 +751,27 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
             u.sx = scans->sensor_pose[3 * sq]; u.sy = scans->sensor_pose[3 * sq + 1];
             u.st = scans->sensor_pose[3 * sq + 2];
             u.stepT = stepT; u.winT = d.winT; u.nT = d.nT; u.nTpad = d.nTpad;
-            u.invRes = d.invRes; u.sortBegin = 0; u.sortCount = 0;
+            u.invRes = d.invRes;
+            u.originX = std::floor(u.sx * d.invRes); u.originY = std::floor(u.sy * d.invRes);
+            u.nrx = d.nrx; u.nry = d.nry; u.winX = d.winX; u.winY = d.winY;
+            u.qBegin = 0; u.qCount = 0;
             u.beamBegin = (int)b->hAngles.size();
+            double reach = 0.0;
             for (int i = b0; i < b1; ++i) {
                 const double r = scans->ranges[i];
                 if (r >= maxRangeS || r <= minRange) continue;
                 b->hAngles.push_back(scans->angles[i]);
                 b->hRanges.push_back(r);
+                reach = std::max(reach, std::fabs(r));
             }
             u.nUse = (int)b->hAngles.size() - u.beamBegin;
             u.hitBegin = nHits;
             nHits += (long long)u.nUse * u.nTpad;
+            u.beamPad = (u.nUse + 3) / 4 * 4; u.pad0 = 0;
+            u.hitTBegin = nHitsT;
+            nHitsT += (long long)u.nT * u.beamPad;
+            b->maxAbsCells = std::max(b->maxAbsCells, (std::max(std::fabs(u.sx), std::fabs(u.sy)) + reach) * d.invRes);
+            b->maxReachCells = std::max(b->maxReachCells, reach * d.invRes);
             uidx = (int)b->us.size();
             b->us.push_back(u);
             scanToUnique[sq] = uidx;
@@ -880,6 +780,16 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         d.nUse = b->us[uidx].nUse;
         d.tabBegin = nTab;
         nTab += (long long)d.nUse * d.nTpad;
+        {   // 12.20 fixed-point origin of the query's map relative to the scan origin (+ the window offset of a
+            // banded map), split into fraction bits and whole cells (lgs_bb_run.cu)
+            const BbScan& us = b->us[uidx];
+            const long long mx = std::llrint((d.minX * d.invRes - us.originX) * 1048576.0) + ((long long)d.offX << 20);
+            const long long my = std::llrint((d.minY * d.invRes - us.originY) * 1048576.0) + ((long long)d.offY << 20);
+            d.MloX = (int)(mx & 0xfffff); d.MhiX = (int)(mx >> 20);
+            d.MloY = (int)(my & 0xfffff); d.MhiY = (int)(my >> 20);
+        }
+        b->maxAbsCells = std::max(b->maxAbsCells, std::max(std::fabs(d.minX), std::fabs(d.minY)) * d.invRes +
+                                                  std::max(d.offX, d.offY) + std::max(d.nx, d.ny));
         const long long nr = (long long)d.nrx * d.nry * d.nT;
         if (roots + nr > (1LL << 30)) return lgs_fail(c, LGS_ERR_INVALID, "bb: too many root nodes");
         d.rootBegin = (int)roots;
@@ -891,405 +801,108 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
         b->spanY = std::max(b->spanY, d.nry * winSizeMax);
     }
     b->nTab = nTab;
+    b->nHits = nHits;
+    b->nHitsT = nHitsT;
     b->totalRoots = (int)roots;
-    {   // group the queries by distinct scan, kIdxChunk per index-kernel block
-        std::vector<std::vector<int>> byScan(b->us.size());
-        for (int q = 0; q < n; ++q) byScan[b->qs[q].scan].push_back(q);
-        b->qlist.clear(); b->chunks.clear();
-        // flag search: the queries of every scan sorted by the fractional part of min * invRes
-        b->hSortFx.clear(); b->hSortFy.clear(); b->hSortQx.clear(); b->hSortQy.clear();
-        for (size_t u = 0; u < byScan.size(); ++u) {
-            std::vector<std::pair<double, int>> fx, fy;
-            for (int q : byScan[u]) {
-                const BbQuery& d = b->qs[q];
-                const double ax = d.minX * d.invRes, ay = d.minY * d.invRes;
-                fx.emplace_back(ax - std::floor(ax), q);
-                fy.emplace_back(ay - std::floor(ay), q);
+    const size_t nu = b->us.size();
+    {   // group the queries by distinct scan; kIdxChunk per index-kernel block (exact path)
+        std::vector<int> count(nu, 0);
+        for (int q = 0; q < n; ++q) count[b->qs[q].scan]++;
+        int run = 0;
+        for (size_t u = 0; u < nu; ++u) { b->us[u].qBegin = run; b->us[u].qCount = 0; run += count[u]; }
+        b->qlist.assign(n, 0);
+        for (int q = 0; q < n; ++q) { BbScan& u = b->us[b->qs[q].scan]; b->qlist[u.qBegin + u.qCount++] = q; }
+        b->chunks.clear();
+        for (size_t u = 0; u < nu; ++u)
+            for (int k = 0; k < b->us[u].qCount; k += kIdxChunk)
+                b->chunks.push_back(IdxChunk{(int)u, b->us[u].qBegin + k, std::min(kIdxChunk, b->us[u].qCount - k)});
+        // root-level warp tiles per scan for the four warp mappings (lgs_bb_run.cu)
+        const int gs[4] = {1, 4, 8, 32};
+        bool tilesOk = true;
+        for (int i = 0; i < 4; ++i) {
+            const int npw = 32 / gs[i];
+            b->tileBegin[i].assign(nu + 1, 0);
+            long long acc = 0;
+            for (size_t u = 0; u < nu; ++u) {
+                b->tileBegin[i][u] = (int)acc;
+                acc += (long long)((b->us[u].nT + npw - 1) / npw) * b->us[u].nrx * b->us[u].nry * b->us[u].qCount;
+                if (acc > 0x7fffffffLL) { tilesOk = false; acc = 0x7fffffffLL; }
             }
-            std::sort(fx.begin(), fx.end());
-            std::sort(fy.begin(), fy.end());
-            b->us[u].sortBegin = (int)b->hSortFx.size();
-            b->us[u].sortCount = (int)fx.size();
-            for (size_t k = 0; k < fx.size(); ++k) {
-                b->hSortFx.push_back(fx[k].first); b->hSortQx.push_back(fx[k].second);
-                b->hSortFy.push_back(fy[k].first); b->hSortQy.push_back(fy[k].second);
-            }
+            b->tileBegin[i][nu] = (int)acc;
         }
-        for (size_t u = 0; u < byScan.size(); ++u)
-            for (size_t k = 0; k < byScan[u].size(); k += kIdxChunk) {
-                const int cnt = (int)std::min<size_t>(kIdxChunk, byScan[u].size() - k);
-                b->chunks.push_back(IdxChunk{(int)u, (int)b->qlist.size(), cnt});
-                b->qlist.insert(b->qlist.end(), byScan[u].begin() + k, byScan[u].begin() + k + cnt);
-            }
+        // device-only run: coordinates inside the fixed-point range, rank << 24 | leaf fits 64 bits
+        // device-only run: beams inside the 12.20 fixed-point range around the scan origin, whole-cell parts
+        // inside int32, rank << 24 | leaf inside 64 bits, 32-bit hit-array indices
+        b->deviceOk = tilesOk && b->maxReachCells < 2000.0 && b->maxAbsCells < 5.0e8 && (H > 0 || roots <= (1 << 24)) &&
+                      (double)b->maxRoots * std::pow(4.0, H) < 1099511627776.0 && nHits < 0x7fffffffLL &&
+                      nHitsT < 0x7fffffffLL;
     }
     if (n == 0) { b->uploaded = true; return LGS_OK; }
+    // One staging blob, one H2D copy.
     const size_t nk = b->hAngles.size();
-    LGS_CUDA(c, b->dQs.reserve(n));
-    LGS_CUDA(c, b->dUs.reserve(b->us.size()));
-    LGS_CUDA(c, b->dChunks.reserve(std::max<size_t>(b->chunks.size(), 1)));
-    LGS_CUDA(c, b->dQlist.reserve(std::max<size_t>(b->qlist.size(), 1)));
-    LGS_CUDA(c, b->dHits.reserve(std::max<long long>(nHits, 1)));
-    LGS_CUDA(c, b->dAngles.reserve(std::max<size_t>(nk, 1)));
-    LGS_CUDA(c, b->dRanges.reserve(std::max<size_t>(nk, 1)));
-    LGS_CUDA(c, b->dSortFx.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
-    LGS_CUDA(c, b->dSortFy.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
-    LGS_CUDA(c, b->dSortQx.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
-    LGS_CUDA(c, b->dSortQy.reserve(std::max<size_t>(b->hSortFx.size(), 1)));
-    LGS_CUDA(c, b->dFlags.reserve(kFlagCapBB));
-    LGS_CUDA(c, b->dCounters.reserve(2 + kMaxLevels));
-    LGS_CUDA(c, b->hCounters.reserve(2 + kMaxLevels));
+    size_t off = 0;
+    b->offQs = off;      off = align16(off + (size_t)n * sizeof(BbQuery));
+    b->offUs = off;      off = align16(off + nu * sizeof(BbScan));
+    b->offQlist = off;   off = align16(off + (size_t)n * sizeof(int));
+    b->offTiles = off;   off = align16(off + 4 * (nu + 1) * sizeof(int));
+    b->offChunks = off;  off = align16(off + b->chunks.size() * sizeof(IdxChunk));
+    b->offAngles = off;  off = align16(off + nk * sizeof(double));
+    b->offRanges = off;  off = align16(off + nk * sizeof(double));
+    b->offIds = off;     off = align16(off + b->ids.size() * sizeof(long long));
+    LGS_CUDA(c, cudaEventSynchronize(b->evUpload));        // the previous upload's copy has left the pinned blob
+    LGS_CUDA(c, b->hBlob.reserve(off));
+    if (b->dBlob.cap < off) {
+        LGS_CUDA(c, cudaStreamSynchronize(c->stream));      // a run may still read the old blob
+        LGS_CUDA(c, b->dBlob.reserve(off));
+    }
+    char* hb = b->hBlob.p;
+    memcpy(hb + b->offQs, b->qs.data(), (size_t)n * sizeof(BbQuery));
+    memcpy(hb + b->offUs, b->us.data(), nu * sizeof(BbScan));
+    memcpy(hb + b->offQlist, b->qlist.data(), (size_t)n * sizeof(int));
+    for (int i = 0; i < 4; ++i)
+        memcpy(hb + b->offTiles + (size_t)i * (nu + 1) * sizeof(int), b->tileBegin[i].data(), (nu + 1) * sizeof(int));
+    if (!b->chunks.empty()) memcpy(hb + b->offChunks, b->chunks.data(), b->chunks.size() * sizeof(IdxChunk));
+    if (nk) {
+        memcpy(hb + b->offAngles, b->hAngles.data(), nk * sizeof(double));
+        memcpy(hb + b->offRanges, b->hRanges.data(), nk * sizeof(double));
+    }
+    if (!b->ids.empty()) memcpy(hb + b->offIds, b->ids.data(), b->ids.size() * sizeof(long long));
+    LGS_CUDA(c, b->hCounters.reserve(kCounters));
     LGS_CUDA(c, b->dBest.reserve(n));
     LGS_CUDA(c, b->dRes.reserve(n));
     LGS_CUDA(c, b->hRes.reserve(n));
-    LGS_CUDA(c, b->dNodes[H].reserve(roots));
-    LGS_CUDA(c, b->dScores[H].reserve(roots));
-    LGS_CUDA(c, cudaMemcpyAsync(b->dQs.p, b->qs.data(), n * sizeof(BbQuery), cudaMemcpyHostToDevice, c->stream));
-    LGS_CUDA(c, cudaMemcpyAsync(b->dUs.p, b->us.data(), b->us.size() * sizeof(BbScan), cudaMemcpyHostToDevice, c->stream));
-    LGS_CUDA(c, cudaMemcpyAsync(b->dChunks.p, b->chunks.data(), b->chunks.size() * sizeof(IdxChunk), cudaMemcpyHostToDevice, c->stream));
-    LGS_CUDA(c, cudaMemcpyAsync(b->dQlist.p, b->qlist.data(), b->qlist.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    if (!b->hSortFx.empty()) {
-        const size_t ns = b->hSortFx.size();
-        LGS_CUDA(c, cudaMemcpyAsync(b->dSortFx.p, b->hSortFx.data(), ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        LGS_CUDA(c, cudaMemcpyAsync(b->dSortFy.p, b->hSortFy.data(), ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        LGS_CUDA(c, cudaMemcpyAsync(b->dSortQx.p, b->hSortQx.data(), ns * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        LGS_CUDA(c, cudaMemcpyAsync(b->dSortQy.p, b->hSortQy.data(), ns * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    }
-    if (nk) {
-        LGS_CUDA(c, cudaMemcpyAsync(b->dAngles.p, b->hAngles.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        LGS_CUDA(c, cudaMemcpyAsync(b->dRanges.p, b->hRanges.data(), nk * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    }
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));   // host vectors may be reused by the caller
+    LGS_CUDA(c, cudaMemcpyAsync(b->dBlob.p, hb, off, cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaEventRecord(b->evUpload, c->stream));
     b->uploaded = true;
-    return LGS_OK;
-}
-
-static int bb_run_impl(lgs_bb_batch* b, bool spec) {
-    lgs_ctx* c = b->ctx;
-    if (!b->uploaded) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_run before upload");
-    const int H = b->H, n = b->nq;
-    for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
-    b->gathers = 0;
-    if (n == 0) { b->ran = true; return LGS_OK; }
-    LGS_CUDA(c, cudaSetDevice(c->device));
-    // LGS_BB_HOSTTIMING=1 (diagnostic): host wall time of a run's three phases, summed per batch
-    // object and printed when it is destroyed.
-    const auto hostT0 = std::chrono::steady_clock::now();
-    auto hostMsSince = [](std::chrono::steady_clock::time_point t) {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, (2 + kMaxLevels) * sizeof(int), c->stream));
-    // Scoring the root level from the hit points pays off when several queries share a scan (the
-    // 16-byte hit points are then L2 hits); with one scan per query the 8-byte table rows are cheaper.
-    const bool wantSlots = H >= 1 && getenv("LGS_BB_TABLE") == nullptr &&
-                           ((size_t)n >= 4 * b->us.size() || getenv("LGS_BB_SLOTS") != nullptr);
-    {
-        const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
-        for (size_t u0 = 0; u0 < b->us.size(); u0 += 65535) {
-            const unsigned nu = (unsigned)std::min<size_t>(65535, b->us.size() - u0);
-            bb_hit_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(b->dUs.p + u0, b->dAngles.p, b->dRanges.p, b->dHits.p);
-            LGS_LAUNCH_CHECK(c);
-        }
-        const double eps = g_lgs_edge_eps;
-        for (size_t u0 = 0; wantSlots && u0 < b->us.size(); u0 += 65535) {
-            const unsigned nu = (unsigned)std::min<size_t>(65535, b->us.size() - u0);
-            bb_flagsearch_kernel<<<dim3(gx, gy, nu), 128, 0, c->stream>>>(
-                b->dUs.p + u0, b->dQs.p, b->dHits.p, b->dSortFx.p, b->dSortQx.p, b->dSortFy.p, b->dSortQy.p,
-                eps, eps + 1e-7, b->dFlags.p, b->dCounters.p);
-            LGS_LAUNCH_CHECK(c);
-        }
-        dim3 gridR((b->maxRoots + 127) / 128, n);
-        bb_roots_kernel<<<gridR, 128, 0, c->stream>>>(b->dQs.p, n, H, b->dNodes[H].p);
-        LGS_LAUNCH_CHECK(c);
-        bb_init_best_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(b->dBest.p, n);
-        LGS_LAUNCH_CHECK(c);
-    }
-    const int spanX = b->spanX, spanY = b->spanY;
-    {   // the one host round trip a speculative run keeps (the flag count is almost always 0)
-        // Near-edge beams: exact per-offset index tables from the host (CPU expression + glibc).
-        int nFlag = 0;
-        b->slotPath = false;
-        if (wantSlots) {
-            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            b->hostMs[0] += hostMsSince(hostT0);
-            const auto w0 = std::chrono::steady_clock::now();
-            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-            b->hostMs[1] += hostMsSince(w0);
-            nFlag = b->hCounters.p[0];
-            b->slotPath = nFlag <= kFlagInline;
-        }
-        if (!b->slotPath) {
-            // one scan per query, many near-edge points, or forced: the full per-query table, whose
-            // kernel flags the near-edge points itself
-            LGS_CUDA(c, b->dTab.reserve(std::max<long long>(b->nTab, 1)));
-            LGS_CUDA(c, cudaMemsetAsync(b->dCounters.p, 0, sizeof(int), c->stream));
-            const unsigned gx = (unsigned)((b->maxNTpad + 127) / 128), gy = (unsigned)std::max(b->maxUse, 1);
-            for (size_t c0 = 0; c0 < b->chunks.size(); c0 += 65535) {
-                const unsigned nc = (unsigned)std::min<size_t>(65535, b->chunks.size() - c0);
-                bb_index_kernel<<<dim3(gx, gy, nc), 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dChunks.p + c0, b->dQlist.p,
-                                                                         b->dHits.p, g_lgs_edge_eps, b->dTab.p,
-                                                                         b->dFlags.p, b->dCounters.p);
-                LGS_LAUNCH_CHECK(c);
-            }
-            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-            nFlag = b->hCounters.p[0];
-        }
-        b->nFlagRun = nFlag;
-        std::fill(b->fixups.begin(), b->fixups.end(), 0);
-        if (nFlag > kFlagCapBB)
-            return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: %d near-edge points exceed the fix-up list", nFlag);
-        if (nFlag > 0) {
-            std::vector<BbFlag> fl(nFlag);
-            LGS_CUDA(c, cudaMemcpy(fl.data(), b->dFlags.p, nFlag * sizeof(BbFlag), cudaMemcpyDeviceToHost));
-            std::vector<int> exact((size_t)nFlag * (spanX + spanY), 0);
-            for (int k = 0; k < nFlag; ++k) {
-                const BbQuery& d = b->qs[fl[k].q];
-                const BbScan& u = b->us[d.scan];
-                const double stepX = d.res, stepY = d.res;
-                const double theta = u.st + static_cast<double>(fl[k].t - d.winT) * u.stepT;
-                const double a = theta + b->hAngles[u.beamBegin + fl[k].i];
-                const double cosT = std::cos(a), sinT = std::sin(a);
-                const double r = b->hRanges[u.beamBegin + fl[k].i];
-                int* e = exact.data() + (size_t)k * (spanX + spanY);
-                for (int o = 0; o < spanX; ++o) {
-                    const double px = u.sx + static_cast<double>(o - d.winX) * stepX;       // :96-97
-                    e[o] = static_cast<int>(std::floor(((px + r * cosT) - d.minX) / d.res)) - d.offX;
-                }
-                for (int o = 0; o < spanY; ++o) {
-                    const double py = u.sy + static_cast<double>(o - d.winY) * stepY;
-                    e[spanX + o] = static_cast<int>(std::floor(((py + r * sinT) - d.minY) / d.res)) - d.offY;
-                }
-                b->fixups[fl[k].q]++;
-            }
-            LGS_CUDA(c, b->dExact.reserve(exact.size()));
-            LGS_CUDA(c, cudaMemcpy(b->dExact.p, exact.data(), exact.size() * sizeof(int), cudaMemcpyHostToDevice));
-        } else {
-            LGS_CUDA(c, b->dExact.reserve(1));
-        }
-
-    }
-    // Level-synchronous expansion of the static-threshold superset.
-    int warpBelow = kWarpPerNodeBelow;
-    int deepBelow = kDeepUnrollBelow;
-    if (const char* e = getenv("LGS_BB_WARP_BELOW")) warpBelow = atoi(e);     // tuning hooks
-    if (const char* e = getenv("LGS_BB_DEEP_BELOW")) deepBelow = atoi(e);
-    const bool slots = b->slotPath;
-    const int nFlag = b->nFlagRun;
-    // One level: nLaunch threads / warps, the node count either exact (nDev == nullptr) or on the device.
-    auto launchLevel = [&](int h, int nLaunch, const int* nDev, long long expect) -> int {
-        LGS_CUDA(c, b->dScores[h].reserve(nLaunch));
-        Node* next = h > 0 ? b->dNodes[h - 1].p : nullptr;
-        const int nextCap = h > 0 ? (int)b->dNodes[h - 1].cap : 0;
-        int* nextCount = b->dCounters.p + 1 + h;
-        const int slotStride = (int)(b->dNodes[H - (H > 0 ? 1 : 0)].cap / 4);
-        if (slots && h > 0) LGS_CUDA(c, b->dSlot[h - 1].reserve(std::max(nextCap, 1)));
-        if (slots && h == H) {
-            LGS_CUDA(c, b->dSlotQT.reserve(std::max(slotStride, 1)));
-            bb_score_root_kernel<8><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
-                b->dQs.p, b->dUs.p, b->dHits.p, b->dFlags.p, nFlag, b->dExact.p, spanX, spanY, h, b->dNodes[h].p,
-                b->dScores[h].p, nLaunch, next, nextCap, nextCount, b->dSlotQT.p, b->dSlot[h - 1].p, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
-            return LGS_OK;
-        }
-        const int2* tab = slots ? b->dTab2.p : b->dTab.p;
-        const int* slotIn = slots ? b->dSlot[h].p : nullptr;
-        int* slotOut = slots && h > 0 ? b->dSlot[h - 1].p : nullptr;
-        if (expect >= warpBelow && expect >= deepBelow)
-            bb_score_kernel<16><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
-                b->dQs.p, tab, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                nLaunch, nDev, next, nextCap, nextCount, b->dBest.p, slotIn, slotOut, slotStride);
-        else if (expect >= warpBelow)
-            bb_score_kernel<32><<<(nLaunch + 127) / 128, 128, 0, c->stream>>>(
-                b->dQs.p, tab, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                nLaunch, nDev, next, nextCap, nextCount, b->dBest.p, slotIn, slotOut, slotStride);
-        else
-            bb_score_warp_kernel<<<(nLaunch + 3) / 4, 128, 0, c->stream>>>(
-                b->dQs.p, tab, b->dExact.p, spanX, spanY, h, b->dNodes[h].p, b->dScores[h].p,
-                nLaunch, nDev, next, nextCap, nextCount, b->dBest.p, slotIn, slotOut, slotStride);
-        LGS_LAUNCH_CHECK(c);
-        return LGS_OK;
-    };
-    // After the root level of the slot path: index rows for the survivors (slot count = children / 4).
-    auto launchSlotIndex = [&](int nSlotsLaunch) -> int {
-        const int slotStride = (int)(b->dNodes[H - 1].cap / 4);
-        if (slotStride == 0 || nSlotsLaunch == 0) return LGS_OK;
-        LGS_CUDA(c, b->dTab2.reserve((size_t)slotStride * std::max(b->maxUse, 1)));
-        dim3 gi((nSlotsLaunch + 127) / 128, (std::max(b->maxUse, 1) + 7) / 8);
-        bb_index_slots_kernel<<<gi, 128, 0, c->stream>>>(b->dQs.p, b->dUs.p, b->dHits.p, b->dSlotQT.p,
-                                                        b->dCounters.p + 1 + H, slotStride, b->dFlags.p, nFlag,
-                                                        b->dTab2.p);
-        LGS_LAUNCH_CHECK(c);
-        return LGS_OK;
-    };
-    auto finish = [&](int leafLaunch, const int* leafDev) -> int {   // winner, verification, replay
-        if (leafLaunch > 0) {
-            bb_leaf_rank_kernel<<<(leafLaunch + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafLaunch, leafDev, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
-            bb_leaf_pick_kernel<<<(leafLaunch + 127) / 128, 128, 0, c->stream>>>(b->dNodes[0].p, b->dScores[0].p, leafLaunch, leafDev, b->dBest.p);
-            LGS_LAUNCH_CHECK(c);
-        }
-        LevelViews lv;
-        for (int h = 0; h < kMaxLevels; ++h) lv.v[h] = LevelView{b->dNodes[h].p, b->dScores[h].p};
-        bb_verify_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p,
-                                                              b->forceReplay ? 1 : 0);
-        LGS_LAUNCH_CHECK(c);
-        bb_replay_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(b->dQs.p, n, H, lv, b->dBest.p, b->dRes.p);
-        LGS_LAUNCH_CHECK(c);
-        return LGS_OK;
-    };
-
-    if (spec) {
-        const auto l0 = std::chrono::steady_clock::now();
-        // Every buffer the level launches need, grown BEFORE anything is enqueued (the launch code's own
-        // reserve() calls are then no-ops), so that the chain below can also be recorded into a CUDA graph.
-        for (int h = H; h >= 0; --h) {
-            const long long expect = h == H ? b->totalRoots : b->hint[h];
-            if (h < H && b->dNodes[h].cap == 0) break;
-            const int nMax = h == H ? b->totalRoots : (int)b->dNodes[h].cap;
-            if (nMax == 0) break;
-            if (h > 0) {
-                const size_t want = (size_t)std::min<long long>(std::max<long long>(4LL * expect, 64), 1 << 16);
-                if (b->dNodes[h - 1].cap < want) LGS_CUDA(c, b->dNodes[h - 1].reserve(want));
-            }
-            LGS_CUDA(c, b->dScores[h].reserve(nMax));
-            if (slots && h > 0) LGS_CUDA(c, b->dSlot[h - 1].reserve(std::max<size_t>(b->dNodes[h - 1].cap, 1)));
-        }
-        if (slots && H > 0) {
-            const size_t slotStride = b->dNodes[H - 1].cap / 4;
-            LGS_CUDA(c, b->dSlotQT.reserve(std::max<size_t>(slotStride, 1)));
-            if (slotStride > 0) LGS_CUDA(c, b->dTab2.reserve(slotStride * std::max(b->maxUse, 1)));
-        }
-        auto enqueue = [&]() -> int {
-            for (int h = H; h >= 0; --h) {
-                const long long expect = h == H ? b->totalRoots : b->hint[h];
-                if (h < H && b->dNodes[h].cap == 0) break;
-                const int nMax = h == H ? b->totalRoots : (int)b->dNodes[h].cap;
-                const int* nDev = h == H ? nullptr : b->dCounters.p + 2 + h;      // children of level h + 1
-                if (nMax == 0) break;
-                int rc = launchLevel(h, nMax, nDev, expect);
-                if (rc != LGS_OK) return rc;
-                if (slots && h == H) {
-                    // survivors expected from the last run (+25 %), never more than the pool can hold
-                    b->slotLaunch = (int)std::min<long long>((long long)(b->dNodes[H - 1].cap / 4),
-                                                             b->hint[H - 1] / 4 + b->hint[H - 1] / 16 + 256);
-                    rc = launchSlotIndex(b->slotLaunch);
-                    if (rc != LGS_OK) return rc;
-                }
-            }
-            const int rc = finish(H == 0 ? b->totalRoots : (int)b->dNodes[0].cap, H == 0 ? nullptr : b->dCounters.p + 2);
-            if (rc != LGS_OK) return rc;
-            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p, b->dCounters.p, (2 + kMaxLevels) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            return LGS_OK;
-        };
-        // LGS_BB_GRAPH=1 (experimental, off by default): the ~25 launches of the chain become one graph
-        // launch -- they carry no host decision (grid sizes are pool capacities, counts stay on the
-        // device).  Meant for many ranks driven from one host, where the launch path is contended
-        // (profiles/r1_scaling.md).  Any capture / instantiate problem falls back to direct launches.
-        bool launched = false;
-        if (getenv("LGS_BB_GRAPH") != nullptr &&
-            cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const long long launchesBefore = c->launches;
-            const int rcCap = enqueue();
-            cudaGraph_t graph = nullptr;
-            const cudaError_t eEnd = cudaStreamEndCapture(c->stream, &graph);
-            if (rcCap == LGS_OK && eEnd == cudaSuccess && graph != nullptr) {
-                cudaGraphExecUpdateResultInfo info;
-                if (b->graphExec != nullptr && cudaGraphExecUpdate(b->graphExec, graph, &info) != cudaSuccess) {
-                    cudaGetLastError();
-                    cudaGraphExecDestroy(b->graphExec);
-                    b->graphExec = nullptr;
-                }
-                if (b->graphExec == nullptr && cudaGraphInstantiate(&b->graphExec, graph, 0) != cudaSuccess) {
-                    cudaGetLastError();
-                    b->graphExec = nullptr;
-                }
-                if (b->graphExec != nullptr && cudaGraphLaunch(b->graphExec, c->stream) == cudaSuccess) launched = true;
-            }
-            if (graph != nullptr) cudaGraphDestroy(graph);
-            if (!launched) { cudaGetLastError(); c->launches = launchesBefore; }
-        }
-        if (!launched) {
-            const int rc = enqueue();
-            if (rc != LGS_OK) return rc;
-        }
-        b->pendingValidate = true;
-        b->ran = true;
-        b->hostMs[2] += hostMsSince(l0);
-        b->hostRuns++;
-        return LGS_OK;
-    }
-    int nNodes = b->totalRoots;
-    for (int h = H; h >= 0; --h) {
-        b->nodesPerLevel[h] = nNodes;
-        if (nNodes == 0) break;
-        int* nextCount = b->dCounters.p + 1 + h;
-        if (h > 0 && b->dNodes[h - 1].cap < (size_t)std::min<long long>(4LL * nNodes, 1 << 16))
-            LGS_CUDA(c, b->dNodes[h - 1].reserve(std::min<long long>(4LL * nNodes, 1 << 16)));
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            LGS_CUDA(c, cudaMemsetAsync(nextCount, 0, sizeof(int), c->stream));
-            const int rc = launchLevel(h, nNodes, nullptr, nNodes);
-            if (rc != LGS_OK) return rc;
-            if (h == 0) break;
-            LGS_CUDA(c, cudaMemcpyAsync(b->hCounters.p + 1 + h, nextCount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-            const int want = b->hCounters.p[1 + h];
-            if ((size_t)want <= b->dNodes[h - 1].cap) break;
-            if (attempt == 1) return lgs_fail(c, LGS_ERR_OVERFLOW, "bb: level %d pool overflow", h - 1);
-            LGS_CUDA(c, b->dNodes[h - 1].reserve((size_t)want + want / 4));   // grow, redo this level
-        }
-        nNodes = h > 0 ? b->hCounters.p[1 + h] : 0;
-        if (slots && h == H && nNodes > 0) {
-            const int rc = launchSlotIndex(nNodes / 4);
-            if (rc != LGS_OK) return rc;
-        }
-    }
-    for (int h = 0; h <= H; ++h) b->gathers += b->nodesPerLevel[h];   // refined per query below
-    {
-        const int rc = finish((int)b->nodesPerLevel[0], nullptr);
-        if (rc != LGS_OK) return rc;
-    }
-    b->ran = true;
-    b->pendingValidate = false;
-    for (int h = 0; h < kMaxLevels; ++h) b->hint[h] = b->nodesPerLevel[h];
-    b->haveHints = true;
-    return LGS_OK;
-}
-
-// Wait for a speculative run and validate it; repeat level-synchronously if it cannot be trusted.
-static int bb_finish(lgs_bb_batch* b) {
-    lgs_ctx* c = b->ctx;
-    if (!b->pendingValidate) return LGS_OK;
-    LGS_CUDA(c, cudaSetDevice(c->device));
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-    b->pendingValidate = false;
-    const int H = b->H;
-    bool ok = !b->slotPath || H < 1 || b->hCounters.p[1 + H] / 4 <= b->slotLaunch;   // every survivor got its row
-    for (int h = 1; h <= H && ok; ++h)
-        ok = (size_t)b->hCounters.p[1 + h] <= b->dNodes[h - 1].cap;   // no pool overflow
-    if (!ok) return bb_run_impl(b, false);
-    for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
-    b->nodesPerLevel[H] = b->totalRoots;
-    for (int h = 1; h <= H; ++h) b->nodesPerLevel[h - 1] = b->hCounters.p[1 + h];
-    for (int h = 0; h < kMaxLevels; ++h) b->hint[h] = b->nodesPerLevel[h];
+    b->hostMs[0] += ms_since(t0);
     return LGS_OK;
 }
 
 int lgs_bb_batch_run(lgs_bb_batch* b) {
     if (!b) return LGS_ERR_INVALID;
-    // LGS_BB_SYNC=1 (diagnostic) forces the level-synchronous path
-    const bool spec = b->haveHints && !b->forceReplay && getenv("LGS_BB_SYNC") == nullptr;
-    return bb_run_impl(b, spec);
+    lgs_ctx* c = b->ctx;
+    if (!b->uploaded) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_run before upload");
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
+    if (b->nq == 0) { b->ran = true; return LGS_OK; }
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    // "bb_sync" / "bb_table" (diagnostic and test hooks) force the level-synchronous exact path
+    const bool device = b->deviceOk && !c->opt.bbSync && !c->opt.bbTable;
+    const int rc = device ? lgs_bb_launch_device_run(b) : bb_run_exact(b);
+    if (rc != LGS_OK) return rc;
+    b->ran = true;
+    b->hostMs[1] += ms_since(t0);
+    b->hostRuns++;
+    return LGS_OK;
 }
-
 
 int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out) {
     if (!b || (!out && b->nq > 0)) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
     if (!b->ran) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_results before run");
     if (b->nq == 0) return LGS_OK;
-    { const int rc = bb_finish(b); if (rc != LGS_OK) return rc; }
-    LGS_CUDA(c, cudaSetDevice(c->device));
-    LGS_CUDA(c, cudaMemcpyAsync(b->hRes.p, b->dRes.p, b->nq * sizeof(BbResult), cudaMemcpyDeviceToHost, c->stream));
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    { const int rc = bb_settle(b); if (rc != LGS_OK) return rc; }
     long long total = 0;
     for (int h = 0; h <= b->H; ++h) total += b->nodesPerLevel[h];
     for (int q = 0; q < b->nq; ++q) {
@@ -1303,14 +916,36 @@ int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out) {
         o.score = r.score;
         o.n_scored = total;          // batch-wide count of nodes scored (all queries)
         o.exact_replay = r.exactReplay;
-        o.reserved = 0;
+        o.reserved = b->lastRunDevice ? 0 : 1;     // 1: the level-synchronous exact path produced this result
     }
+    b->hostMs[2] += ms_since(t0);
     return LGS_OK;
 }
 
+int lgs_bb_batch_records(lgs_bb_batch* b, lgs_loop_record* out) {
+    if (!b || (!out && b->nq > 0)) return LGS_ERR_INVALID;
+    lgs_ctx* c = b->ctx;
+    if (!b->ran) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_records before run");
+    if (b->nq == 0) return LGS_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    { const int rc = bb_settle(b); if (rc != LGS_OK) return rc; }
+    bb_fill_records(b, out);
+    b->hostMs[2] += ms_since(t0);
+    return LGS_OK;
+}
+
+int lgs_bb_batch_settle(lgs_bb_batch* b) {
+    if (!b) return LGS_ERR_INVALID;
+    if (!b->ran) return lgs_fail(b->ctx, LGS_ERR_INVALID, "bb_batch_settle before run");
+    if (b->nq == 0) return LGS_OK;
+    return bb_settle(b);
+}
+
+void* lgs_bb_batch_device_records(lgs_bb_batch* b) { return b ? (void*)b->dRec.p : nullptr; }
+
 int lgs_bb_batch_work(const lgs_bb_batch* b, long long* nodesPerLevel, int nLevels, long long* gathers) {
     if (!b) return LGS_ERR_INVALID;
-    { const int rc = bb_finish(const_cast<lgs_bb_batch*>(b)); if (rc != LGS_OK) return rc; }
+    if (b->ran && b->nq > 0) { const int rc = bb_settle(const_cast<lgs_bb_batch*>(b)); if (rc != LGS_OK) return rc; }
     long long total = 0;
     for (int h = 0; h < kMaxLevels; ++h) {
         if (nodesPerLevel && h < nLevels) nodesPerLevel[h] = b->nodesPerLevel[h];
@@ -1323,6 +958,32 @@ int lgs_bb_batch_work(const lgs_bb_batch* b, long long* nodesPerLevel, int nLeve
         avgUse = b->qs.empty() ? 0 : avgUse / b->qs.size();
         *gathers = (long long)(total * avgUse);
     }
+    return LGS_OK;
+}
+
+// Diagnostic ("bb_host_timing" must be on before the run): microseconds between the phase boundaries
+// of the last device-only run -- hit points, root level, levels H-1..0, winner, finalize -- and the
+// warp mapping (lanes per node) each level used.
+int lgs_bb_batch_phase_times(lgs_bb_batch* b, double* us, int* mapping, int n) {
+    if (!b || !us || n < 0) return LGS_ERR_INVALID;
+    if (!b->lastRunDevice || !b->ctx->opt.bbHostTiming || !b->hPhase.p) return LGS_ERR_INVALID;
+    { const int rc = bb_settle(b); if (rc != LGS_OK) return rc; }
+    const int phases = b->H + 4;
+    for (int k = 0; k < n; ++k) {
+        us[k] = k < phases ? (double)(b->hPhase.p[k + 1] - b->hPhase.p[k]) * 1e-3 : 0.0;
+        if (mapping) mapping[k] = 0;
+    }
+    if (mapping) {
+        const int* g = reinterpret_cast<const int*>(b->hPhase.p + kPhases);
+        for (int h = b->H; h >= 0; --h) { const int k = 1 + (b->H - h); if (k < n) mapping[k] = g[h]; }
+    }
+    return LGS_OK;
+}
+
+int lgs_bb_batch_path(const lgs_bb_batch* b, long long* deviceRuns, long long* exactRuns) {
+    if (!b) return LGS_ERR_INVALID;
+    if (deviceRuns) *deviceRuns = b->deviceRuns;
+    if (exactRuns) *exactRuns = b->exactRuns;
     return LGS_OK;
 }
 

@@ -5,7 +5,17 @@
 // outside the map both return the unknown value 0.0 through Value(x, y, unknown)
 // (grid_map.hpp:859-873), so a dense row-major array whose unknown cells hold 0.0 and which
 // is surrounded by a zero apron is value-equivalent for every reader on the path.
+#include <cstddef>
+
 #include "lgs_internal.cuh"
+
+cudaError_t lgs_grid_acquire(lgs_ctx* user, const lgs_grid* g) {
+    if (!g || g->ctx == user) return cudaSuccess;
+    g->foreign = true;
+    cudaError_t e = cudaEventRecord(user->evOrder, g->ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamWaitEvent(user->stream, user->evOrder, 0);
+}
 
 int lgs_fail(lgs_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
@@ -17,12 +27,80 @@ int lgs_fail(lgs_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-double g_lgs_edge_eps = LGS_EDGE_EPS_DEFAULT;
+namespace {
+
+struct OptField { const char* name; const char* env; int kind; size_t off; };   // kind 0 int, 1 double, 2 long long
+#define LGS_OPT(name, env, kind, field) {name, env, kind, offsetof(lgs_opts, field)}
+const OptField kOptFields[] = {
+    LGS_OPT("edge_eps", nullptr, 1, edgeEps),
+    LGS_OPT("csm_flat", "LGS_CSM_FLAT", 0, csmFlat),
+    LGS_OPT("bb_sync", "LGS_BB_SYNC", 0, bbSync),
+    LGS_OPT("bb_table", "LGS_BB_TABLE", 0, bbTable),
+    LGS_OPT("bb_warp_below", "LGS_BB_WARP_BELOW", 0, bbWarpBelow),
+    LGS_OPT("bb_resolve_ulps", "LGS_BB_RESOLVE_ULPS", 0, bbResolveUlps),
+    LGS_OPT("bb_variant", "LGS_BB_VARIANT", 0, bbVariant),
+    LGS_OPT("bb_blocks_per_sm", "LGS_BB_BLOCKS_PER_SM", 0, bbBlocksPerSm),
+    LGS_OPT("bb_cost_g1", nullptr, 1, bbCost[0]),
+    LGS_OPT("bb_cost_g4", nullptr, 1, bbCost[1]),
+    LGS_OPT("bb_cost_g8", nullptr, 1, bbCost[2]),
+    LGS_OPT("bb_cost_g32", nullptr, 1, bbCost[3]),
+    LGS_OPT("bb_host_timing", "LGS_BB_HOSTTIMING", 0, bbHostTiming),
+    LGS_OPT("integ_host_timing", "LGS_INTEG_HOSTTIMING", 0, integHostTiming),
+    LGS_OPT("integ_timing", "LGS_INTEG_TIMING", 0, integTiming),
+    LGS_OPT("integ_diag", "LGS_INTEG_DIAG", 0, integDiag),
+    LGS_OPT("integ_side_words", "LGS_INTEG_SIDE_WORDS", 2, integSideWords),
+    LGS_OPT("gs_tables", "LGS_GS_TABLES", 0, gsTables),
+};
+#undef LGS_OPT
+
+void opt_store(lgs_opts* o, const OptField& f, double v) {
+    char* base = reinterpret_cast<char*>(o) + f.off;
+    if (f.kind == 0) *reinterpret_cast<int*>(base) = (int)v;
+    else if (f.kind == 1) *reinterpret_cast<double*>(base) = v;
+    else *reinterpret_cast<long long*>(base) = (long long)v;
+}
+
+double opt_load(const lgs_opts* o, const OptField& f) {
+    const char* base = reinterpret_cast<const char*>(o) + f.off;
+    if (f.kind == 0) return *reinterpret_cast<const int*>(base);
+    if (f.kind == 1) return *reinterpret_cast<const double*>(base);
+    return (double)*reinterpret_cast<const long long*>(base);
+}
+
+// The one place the environment is read: defaults of a NEW context.
+void opts_from_env(lgs_opts* o) {
+    for (const OptField& f : kOptFields) {
+        if (!f.env) continue;
+        const char* e = getenv(f.env);
+        if (!e) continue;
+        char* end = nullptr;
+        const double v = strtod(e, &end);
+        opt_store(o, f, end != e ? v : 1.0);      // "LGS_X=" or a non-number means "on"
+    }
+}
+
+}  // namespace
 
 extern "C" {
 
-void lgs_set_edge_eps(double eps) { g_lgs_edge_eps = (eps > 0.0 && eps < 0.5) ? eps : LGS_EDGE_EPS_DEFAULT; }
-double lgs_get_edge_eps(void) { return g_lgs_edge_eps; }
+int lgs_ctx_set_option(lgs_ctx* c, const char* name, double value) {
+    if (!c || !name) return LGS_ERR_INVALID;
+    for (const OptField& f : kOptFields)
+        if (strcmp(f.name, name) == 0) {
+            if (strcmp(name, "edge_eps") == 0 && !(value > 0.0 && value < 0.5)) value = LGS_EDGE_EPS_DEFAULT;
+            opt_store(&c->opt, f, value);
+            if (strncmp(name, "bb_", 3) == 0) c->bbBlocks = 0;   // re-size the persistent grid
+            return LGS_OK;
+        }
+    return lgs_fail(c, LGS_ERR_INVALID, "ctx_set_option: unknown option '%s'", name);
+}
+
+int lgs_ctx_get_option(const lgs_ctx* c, const char* name, double* value) {
+    if (!c || !name || !value) return LGS_ERR_INVALID;
+    for (const OptField& f : kOptFields)
+        if (strcmp(f.name, name) == 0) { *value = opt_load(&c->opt, f); return LGS_OK; }
+    return LGS_ERR_INVALID;
+}
 
 const char* lgs_version(void) { return "lgs_b200 0.1 (sm_100a)"; }
 
@@ -33,21 +111,32 @@ int lgs_ctx_create(int device, lgs_ctx** out) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
         return LGS_ERR_CUDA;   // no CPU fallback: the caller must fail loudly
     lgs_ctx* c = new lgs_ctx();
+    opts_from_env(&c->opt);
     c->device = device;
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return LGS_ERR_CUDA; }
     if (prop.major < 10) { delete c; return LGS_ERR_CUDA; }   // sm_100a code only
     c->sm_count = prop.multiProcessorCount;
-    {   // keep freed stream-ordered allocations (pyramid slabs) in the pool instead of returning them
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
+    {   // A PRIVATE pool that keeps freed stream-ordered allocations (pyramid slabs, grids): the device's
+        // default pool is process-global, so raising ITS release threshold would change the memory
+        // behaviour of every other user of the process (e.g. PyTorch's async allocations).
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) { delete c; return LGS_ERR_CUDA; }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->evOrder, cudaEventDisableTiming) != cudaSuccess) {
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        cudaMemPoolDestroy(c->pool);
         delete c;
         return LGS_ERR_CUDA;
     }
@@ -61,9 +150,11 @@ int lgs_ctx_destroy(lgs_ctx* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evOrder) cudaEventDestroy(c->evOrder);
     c->scratch.release();
     if (c->integ) { c->integ->release(); delete c->integ; }
     lgs_cost_ws_destroy(c->cost);
+    if (c->pool) cudaMemPoolDestroy(c->pool);   // grids / pyramids still alive keep their memory until freed
     delete c;
     return LGS_OK;
 }
@@ -87,6 +178,34 @@ int lgs_host_pin(lgs_ctx* c, void* ptr, unsigned long long bytes) {
 int lgs_host_unpin(lgs_ctx* c, void* ptr) {
     if (!c || !ptr) return LGS_ERR_INVALID;
     LGS_CUDA(c, cudaHostUnregister(ptr));
+    return LGS_OK;
+}
+
+int lgs_device_alloc(lgs_ctx* c, unsigned long long bytes, void** out) {
+    if (!c || !out || bytes == 0) return LGS_ERR_INVALID;
+    *out = nullptr;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(out, (size_t)bytes);
+    if (e != cudaSuccess) return lgs_fail(c, LGS_ERR_NOMEM, "device_alloc(%llu) -> %s", bytes, cudaGetErrorString(e));
+    LGS_CUDA(c, cudaMemsetAsync(*out, 0, (size_t)bytes, c->stream));
+    return LGS_OK;
+}
+
+int lgs_device_free(lgs_ctx* c, void* ptr) {
+    if (!c) return LGS_ERR_INVALID;
+    if (!ptr) return LGS_OK;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    LGS_CUDA(c, cudaFree(ptr));
+    return LGS_OK;
+}
+
+int lgs_device_download(lgs_ctx* c, const void* devicePtr, void* host, unsigned long long bytes) {
+    if (!c || (bytes > 0 && (!devicePtr || !host))) return LGS_ERR_INVALID;
+    if (bytes == 0) return LGS_OK;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaMemcpyAsync(host, devicePtr, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
     return LGS_OK;
 }
 
@@ -128,7 +247,7 @@ int lgs_grid_create(lgs_ctx* c, int nx, int ny, double min_x, double min_y, doub
     g->min_x = min_x; g->min_y = min_y; g->res = res;
     const size_t bytes = (size_t)pitch * rows * sizeof(double);
     // stream-ordered pool allocation: lgs_grid_resize can then swap buffers without a device sync
-    cudaError_t e = cudaMallocAsync(&g->d, std::max<size_t>(bytes, 8), c->stream);
+    cudaError_t e = lgs_alloc_async(c, &g->d, std::max<size_t>(bytes, 8));
     if (e != cudaSuccess) {
         delete g;
         return lgs_fail(c, LGS_ERR_NOMEM, "grid_create: cudaMallocAsync(%zu) -> %s", bytes,
@@ -147,8 +266,8 @@ int lgs_grid_destroy(lgs_grid* g) {
     if (!g) return LGS_OK;
     cudaSetDevice(g->ctx->device);
     if (g->d && g->owns) {
-        cudaDeviceSynchronize();            // readers on other contexts' streams (like cudaFree did)
-        cudaFreeAsync(g->d, g->ctx->stream);
+        if (g->foreign) cudaDeviceSynchronize();   // another context's stream may still read it
+        cudaFreeAsync(g->d, g->ctx->stream);        // ordered after every use on the owner's stream
     }
     delete g;
     return LGS_OK;
@@ -209,8 +328,8 @@ int lgs_grid_copy(const lgs_grid* src, lgs_grid* dst) {
     }
     dst->min_x = src->min_x; dst->min_y = src->min_y;
     dst->off_x = src->off_x; dst->off_y = src->off_y;
-    // everything queued on the source's stream (its last integration) must have landed
-    if (src->ctx != c) LGS_CUDA(c, cudaStreamSynchronize(src->ctx->stream));
+    // everything queued on the source's stream (its last integration) is ordered before the copy
+    LGS_CUDA(c, lgs_grid_acquire(c, src));
     if (src->nx > 0 && src->ny > 0)
         LGS_CUDA(c, cudaMemcpy2DAsync(dst->origin(), (size_t)dst->pitch * sizeof(double), src->origin(),
                                       (size_t)src->pitch * sizeof(double), (size_t)src->nx * sizeof(double),

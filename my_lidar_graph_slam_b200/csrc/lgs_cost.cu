@@ -219,6 +219,7 @@ int lgs_cost_greedy_endpoint(lgs_ctx* c, const lgs_grid* grid, const lgs_cost_pa
     int rc = buildTables(c, grid, params, &tab);
     if (rc != LGS_OK) return rc;
     LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, lgs_grid_acquire(c, grid));
     if (!c->cost) c->cost = new lgs_cost_ws();
     lgs_cost_ws* ws = c->cost;
 
@@ -262,11 +263,11 @@ int lgs_cost_greedy_endpoint(lgs_ctx* c, const lgs_grid* grid, const lgs_cost_pa
     LGS_CUDA(c, cudaMemsetAsync(ws->dFlagCount.p, 0, sizeof(int), c->stream));
     if (tab.K == 1)
         cost_kernel<false, 1><<<nPoses, kThreads, 0, c->stream>>>(dPoses, nullptr, dAngles, dRanges, gv, tab,
-                                                                  g_lgs_edge_eps, nullptr, nullptr, ws->dFlags.p,
+                                                                  c->opt.edgeEps, nullptr, nullptr, ws->dFlags.p,
                                                                   ws->dFlagCount.p, ws->dCost.p);
     else
         cost_kernel<false, -1><<<nPoses, kThreads, 0, c->stream>>>(dPoses, nullptr, dAngles, dRanges, gv, tab,
-                                                                   g_lgs_edge_eps, nullptr, nullptr, ws->dFlags.p,
+                                                                   c->opt.edgeEps, nullptr, nullptr, ws->dFlags.p,
                                                                    ws->dFlagCount.p, ws->dCost.p);
     LGS_LAUNCH_CHECK(c);
     LGS_CUDA(c, cudaMemcpyAsync(ws->hCost.p, ws->dCost.p, nPoses * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -305,14 +306,14 @@ int lgs_cost_greedy_endpoint(lgs_ctx* c, const lgs_grid* grid, const lgs_cost_pa
         patchBegin.push_back(nFlag);
         const int nRedo = (int)poseList.size();
         CostPatch* dPatches = nullptr; int* dList = nullptr; int* dBegin = nullptr;
-        LGS_CUDA(c, cudaMallocAsync(&dPatches, nFlag * sizeof(CostPatch), c->stream));
-        LGS_CUDA(c, cudaMallocAsync(&dList, nRedo * sizeof(int), c->stream));
-        LGS_CUDA(c, cudaMallocAsync(&dBegin, (nRedo + 1) * sizeof(int), c->stream));
+        LGS_CUDA(c, lgs_alloc_async(c, &dPatches, nFlag * sizeof(CostPatch)));
+        LGS_CUDA(c, lgs_alloc_async(c, &dList, nRedo * sizeof(int)));
+        LGS_CUDA(c, lgs_alloc_async(c, &dBegin, (nRedo + 1) * sizeof(int)));
         LGS_CUDA(c, cudaMemcpyAsync(dPatches, patches.data(), nFlag * sizeof(CostPatch), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(dList, poseList.data(), nRedo * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(dBegin, patchBegin.data(), (nRedo + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         cost_kernel<true, -1><<<nRedo, kThreads, 0, c->stream>>>(dPoses, dList, dAngles, dRanges, gv, tab,
-                                                                 g_lgs_edge_eps, dPatches, dBegin, nullptr,
+                                                                 c->opt.edgeEps, dPatches, dBegin, nullptr,
                                                                  nullptr, ws->dCost.p);
         LGS_LAUNCH_CHECK(c);
         LGS_CUDA(c, cudaMemcpyAsync(ws->hCost.p, ws->dCost.p, nPoses * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -30,7 +30,7 @@
 namespace {
 
 constexpr int kBeamPad = 8;          // kept-beam count is padded to a multiple of this
-constexpr int kFlagCap = 1 << 16;    // capacity of the near-edge fix-up list
+constexpr int kFlagCap = 1 << 16;    // initial capacity of the near-edge fix-up list (grown on demand)
 
 struct CsmDesc {
     double sx, sy, st;       // sensor pose
@@ -81,7 +81,7 @@ __global__ void csm_project_kernel(const CsmDesc* __restrict__ descs,
                                    const double* __restrict__ angles,
                                    const double* __restrict__ ranges, GridGeom g, CsmWindow w, double eps,
                                    int* __restrict__ offs, int2* __restrict__ cells,
-                                   FlagEntry* __restrict__ flags, int* __restrict__ flagCount) {
+                                   FlagEntry* __restrict__ flags, int flagCap, int* __restrict__ flagCount) {
     const CsmDesc d = descs[blockIdx.y];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)d.nT * d.nKeptPad) return;
@@ -108,7 +108,7 @@ __global__ void csm_project_kernel(const CsmDesc* __restrict__ descs,
     const bool edge = !(rx >= eps && rx <= 1.0 - eps && ry >= eps && ry <= 1.0 - eps);
     if (edge) {
         const int k = atomicAdd(flagCount, 1);
-        if (k < kFlagCap) flags[k] = FlagEntry{(int)blockIdx.y, t, i};
+        if (k < flagCap) flags[k] = FlagEntry{(int)blockIdx.y, t, i};
     }
     const int cx = __double2int_rd(qx), cy = __double2int_rd(qy);
     cells[d.cellBegin + (long long)t * d.nKept + i] = make_int2(cx, cy);
@@ -425,6 +425,11 @@ struct lgs_rtcsm_batch {
     DevBuf<int> dOffs, dBlockArg, dFlagCount;
     DevBuf<int2> dCells;
     DevBuf<FlagEntry> dFlags;
+    int flagCap = kFlagCap;
+    // near-edge fix-up values (results()): kept with the batch, no per-call cudaMalloc
+    DevBuf<int> dFixOff;
+    DevBuf<int2> dFixCell;
+    DevBuf<long long> dFixWhere;
     DevBuf<DevResult> dResults;
     PinBuf<DevResult> hResults;
     PinBuf<int> hFlagCount;
@@ -496,6 +501,7 @@ int lgs_rtcsm_batch_destroy(lgs_rtcsm_batch* b) {
     b->dDescs.release(); b->dAngles.release(); b->dRanges.release(); b->dFine.release();
     b->dCoarse.release(); b->dBlockMax.release(); b->dOffs.release(); b->dBlockArg.release();
     b->dFlagCount.release(); b->dCells.release(); b->dFlags.release(); b->dResults.release();
+    b->dFixOff.release(); b->dFixCell.release(); b->dFixWhere.release();
     b->hResults.release(); b->hFlagCount.release(); b->hDescs.release(); b->hStage.release();
     delete b;
     return LGS_OK;
@@ -534,7 +540,7 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     w.block = pick_block(w.slots);
     w.tilesFine = (w.slots + w.block - 1) / w.block;
     w.rows = 0; w.xChunks = 1; w.rowGroups = 0;
-    if (w.hpt == 4 && getenv("LGS_CSM_FLAT") == nullptr) {
+    if (w.hpt == 4 && !c->opt.csmFlat) {
         // row-mapped sweep: lanes = x offsets of one window row, ROWS rows per thread
         w.rows = (w.nyw % 5 == 0) ? 5 : 4;
         w.xChunks = (w.nxw + 31) / 32;
@@ -616,7 +622,7 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     LGS_CUDA(c, b->dBlockMax.reserve(nCoarse));
     LGS_CUDA(c, b->dBlockArg.reserve(nCoarse));
     LGS_CUDA(c, b->dFlagCount.reserve(1));
-    LGS_CUDA(c, b->dFlags.reserve(kFlagCap));
+    LGS_CUDA(c, b->dFlags.reserve(b->flagCap));
     LGS_CUDA(c, b->dResults.reserve(n));
     LGS_CUDA(c, b->hResults.reserve(n));
     LGS_CUDA(c, b->hFlagCount.reserve(1));
@@ -653,6 +659,21 @@ int lgs_rtcsm_batch_upload(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_s
     return LGS_OK;
 }
 
+static int csm_launch_project(lgs_rtcsm_batch* b) {
+    lgs_ctx* c = b->ctx;
+    for (int m0 = 0; m0 < b->nMatch; m0 += 65535) {
+        const int nm = std::min(65535, b->nMatch - m0);
+        const long long per = (long long)b->maxNT * b->maxKeptPad;
+        dim3 gridDim((unsigned)((per + 255) / 256), nm);
+        csm_project_kernel<<<gridDim, 256, 0, c->stream>>>(b->dDescs.p + m0, b->dAngles.p,
+                                                           b->dRanges.p, b->geom, b->win,
+                                                           c->opt.edgeEps, b->dOffs.p, b->dCells.p, b->dFlags.p,
+                                                           b->flagCap, b->dFlagCount.p);
+        LGS_LAUNCH_CHECK(c);
+    }
+    return LGS_OK;
+}
+
 static int csm_run_impl(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid* coarse, float* ms) {
     if (!b || !grid || !coarse) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
@@ -663,22 +684,16 @@ static int csm_run_impl(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_grid
     if (ms) ms[0] = ms[1] = ms[2] = 0.f;
     if (b->nMatch == 0) { b->ran = true; return LGS_OK; }
     LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, lgs_grid_acquire(c, grid));     // maps owned by another context (the builder's latest map)
+    LGS_CUDA(c, lgs_grid_acquire(c, coarse));
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (ms) for (auto& e : ev) LGS_CUDA(c, cudaEventCreate(&e));
     LGS_CUDA(c, cudaMemsetAsync(b->dFlagCount.p, 0, sizeof(int), c->stream));
     if (ms) LGS_CUDA(c, cudaEventRecord(ev[0], c->stream));
-    for (int m0 = 0; m0 < b->nMatch; m0 += 65535) {
-        const int nm = std::min(65535, b->nMatch - m0);
-        const long long per = (long long)b->maxNT * b->maxKeptPad;
-        dim3 gridDim((unsigned)((per + 255) / 256), nm);
-        csm_project_kernel<<<gridDim, 256, 0, c->stream>>>(b->dDescs.p + m0, b->dAngles.p,
-                                                           b->dRanges.p, b->geom, b->win,
-                                                           g_lgs_edge_eps, b->dOffs.p, b->dCells.p, b->dFlags.p,
-                                                           b->dFlagCount.p);
-        LGS_LAUNCH_CHECK(c);
-    }
+    int rc = csm_launch_project(b);
+    if (rc != LGS_OK) return rc;
     if (ms) LGS_CUDA(c, cudaEventRecord(ev[1], c->stream));
-    int rc = csm_launch_sweep(b, grid, coarse);
+    rc = csm_launch_sweep(b, grid, coarse);
     if (rc != LGS_OK) return rc;
     if (ms) LGS_CUDA(c, cudaEventRecord(ev[2], c->stream));
     rc = csm_launch_select(b);
@@ -716,13 +731,25 @@ int lgs_rtcsm_batch_results(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_
     LGS_CUDA(c, cudaMemcpyAsync(b->hResults.p, b->dResults.p, b->nMatch * sizeof(DevResult),
                                 cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-    const int nFlag = *b->hFlagCount.p;
+    int nFlag = *b->hFlagCount.p;
     std::fill(b->fixups.begin(), b->fixups.end(), 0);
+    if (nFlag > b->flagCap) {
+        // More near-edge points than the list holds (only with a widened guard band): grow the list
+        // and project again -- the projection is deterministic, so it now records every one of them.
+        b->flagCap = nFlag + nFlag / 8;
+        LGS_CUDA(c, b->dFlags.reserve(b->flagCap));
+        LGS_CUDA(c, cudaMemsetAsync(b->dFlagCount.p, 0, sizeof(int), c->stream));
+        const int rcp = csm_launch_project(b);
+        if (rcp != LGS_OK) return rcp;
+        LGS_CUDA(c, cudaMemcpyAsync(b->hFlagCount.p, b->dFlagCount.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+        nFlag = *b->hFlagCount.p;
+        if (nFlag > b->flagCap)
+            return lgs_fail(c, LGS_ERR_OVERFLOW, "rtcsm: %d near-edge points exceed the regrown fix-up list", nFlag);
+    }
     if (nFlag > 0) {
         // Rare path: re-derive the flagged points with the host's libm (the reference's own
         // arithmetic, sensor_data.hpp:162-173 + grid_map.hpp:779-790), patch, and redo the sweep.
-        if (nFlag > kFlagCap)
-            return lgs_fail(c, LGS_ERR_OVERFLOW, "rtcsm: %d near-edge points exceed the fix-up list", nFlag);
         std::vector<FlagEntry> fl(nFlag);
         LGS_CUDA(c, cudaMemcpy(fl.data(), b->dFlags.p, nFlag * sizeof(FlagEntry), cudaMemcpyDeviceToHost));
         std::vector<int> offVal(nFlag);
@@ -747,10 +774,10 @@ int lgs_rtcsm_batch_results(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_
             where[2 * k + 1] = d.cellBegin + (long long)t * d.nKept + i;
             b->fixups[fl[k].m]++;
         }
-        int* dOffVal = nullptr; int2* dCellVal = nullptr; long long* dWhere = nullptr;
-        LGS_CUDA(c, cudaMalloc(&dOffVal, nFlag * sizeof(int)));
-        LGS_CUDA(c, cudaMalloc(&dCellVal, nFlag * sizeof(int2)));
-        LGS_CUDA(c, cudaMalloc(&dWhere, 2 * (size_t)nFlag * sizeof(long long)));
+        LGS_CUDA(c, b->dFixOff.reserve(nFlag));
+        LGS_CUDA(c, b->dFixCell.reserve(nFlag));
+        LGS_CUDA(c, b->dFixWhere.reserve(2 * (size_t)nFlag));
+        int* dOffVal = b->dFixOff.p; int2* dCellVal = b->dFixCell.p; long long* dWhere = b->dFixWhere.p;
         LGS_CUDA(c, cudaMemcpy(dOffVal, offVal.data(), nFlag * sizeof(int), cudaMemcpyHostToDevice));
         LGS_CUDA(c, cudaMemcpy(dCellVal, cellVal.data(), nFlag * sizeof(int2), cudaMemcpyHostToDevice));
         LGS_CUDA(c, cudaMemcpy(dWhere, where.data(), 2 * (size_t)nFlag * sizeof(long long), cudaMemcpyHostToDevice));
@@ -762,7 +789,6 @@ int lgs_rtcsm_batch_results(lgs_rtcsm_batch* b, const lgs_grid* grid, const lgs_
         LGS_CUDA(c, cudaMemcpyAsync(b->hResults.p, b->dResults.p, b->nMatch * sizeof(DevResult),
                                     cudaMemcpyDeviceToHost, c->stream));
         LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(dOffVal); cudaFree(dCellVal); cudaFree(dWhere);
         // The patched offsets stay valid for a re-run of results(); a new run() re-projects.
         LGS_CUDA(c, cudaMemsetAsync(b->dFlagCount.p, 0, sizeof(int), c->stream));
     }

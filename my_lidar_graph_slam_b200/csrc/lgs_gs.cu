@@ -440,13 +440,13 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         return lgs_fail(c, LGS_ERR_INVALID, "gs_match: %d x %d x %d hypotheses per query", nX, nY, nT);
     if (scoreTable && nQ != 1) return lgs_fail(c, LGS_ERR_INVALID, "gs_match: the score table is a 1-query diagnostic");
     LGS_CUDA(c, cudaSetDevice(c->device));
-    const double eps = g_lgs_edge_eps;
+    const double eps = c->opt.edgeEps;
     const size_t nBeamsAll = (size_t)scans->beam_begin[nQ];
 
     double *dAngles = nullptr, *dRanges = nullptr, *dOff = nullptr;
-    LGS_CUDA(c, cudaMallocAsync(&dAngles, std::max<size_t>(nBeamsAll, 1) * sizeof(double), c->stream));
-    LGS_CUDA(c, cudaMallocAsync(&dRanges, std::max<size_t>(nBeamsAll, 1) * sizeof(double), c->stream));
-    LGS_CUDA(c, cudaMallocAsync(&dOff, (size_t)(nX + nY + nT + 1) * sizeof(double), c->stream));
+    LGS_CUDA(c, lgs_alloc_async(c, &dAngles, std::max<size_t>(nBeamsAll, 1) * sizeof(double)));
+    LGS_CUDA(c, lgs_alloc_async(c, &dRanges, std::max<size_t>(nBeamsAll, 1) * sizeof(double)));
+    LGS_CUDA(c, lgs_alloc_async(c, &dOff, (size_t)(nX + nY + nT + 1) * sizeof(double)));
     if (nBeamsAll) {
         LGS_CUDA(c, cudaMemcpyAsync(dAngles, scans->angles, nBeamsAll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         LGS_CUDA(c, cudaMemcpyAsync(dRanges, scans->ranges, nBeamsAll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -471,6 +471,7 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
             const lgs_grid* g = grids[q1];
             if (!g) { rcOut = lgs_fail(c, LGS_ERR_INVALID, "gs_match: query %d has no grid", q1); break; }
             if (g->ctx->device != c->device) { rcOut = lgs_fail(c, LGS_ERR_INVALID, "gs_match: grid of query %d on another device", q1); break; }
+            if (lgs_grid_acquire(c, g) != cudaSuccess) { rcOut = lgs_fail(c, LGS_ERR_CUDA, "gs_match: cannot order after the grid of query %d", q1); break; }
             const int nb = scans->beam_begin[q1 + 1] - scans->beam_begin[q1];
             const long long cc = (long long)nT * nb * nX, rr = (long long)nT * nb * nYp;
             if (q1 > q0 && (size_t)(colCells + rowCells + cc + rr) * sizeof(int) > kTableBudget) break;
@@ -507,12 +508,12 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
              if (e__ != cudaSuccess) { freeAll();                                                  \
                  rcOut = lgs_fail(c, e__ == cudaErrorMemoryAllocation ? LGS_ERR_NOMEM : LGS_ERR_CUDA, \
                                   "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); } } while (0)
-        GS_TRY(cudaMallocAsync(&dQ, nq * sizeof(GsQuery), c->stream));
-        if (rcOut == LGS_OK && scoreTable) GS_TRY(cudaMallocAsync(&dScores, std::max<long long>(scoreCells, 1) * sizeof(double), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dPart, std::max<size_t>((size_t)nq * perQuery, 1) * sizeof(GsPartial), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dFlags, kFlagCap * sizeof(GsFlag), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dFlagCount, sizeof(int), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dRes, nq * sizeof(GsResult), c->stream));
+        GS_TRY(lgs_alloc_async(c, &dQ, nq * sizeof(GsQuery)));
+        if (rcOut == LGS_OK && scoreTable) GS_TRY(lgs_alloc_async(c, &dScores, std::max<long long>(scoreCells, 1) * sizeof(double)));
+        if (rcOut == LGS_OK) GS_TRY(lgs_alloc_async(c, &dPart, std::max<size_t>((size_t)nq * perQuery, 1) * sizeof(GsPartial)));
+        if (rcOut == LGS_OK) GS_TRY(lgs_alloc_async(c, &dFlags, kFlagCap * sizeof(GsFlag)));
+        if (rcOut == LGS_OK) GS_TRY(lgs_alloc_async(c, &dFlagCount, sizeof(int)));
+        if (rcOut == LGS_OK) GS_TRY(lgs_alloc_async(c, &dRes, nq * sizeof(GsResult)));
         if (rcOut == LGS_OK) GS_TRY(cudaMemcpyAsync(dQ, hq.data(), nq * sizeof(GsQuery), cudaMemcpyHostToDevice, c->stream));
         if (rcOut == LGS_OK) GS_TRY(cudaMemsetAsync(dFlagCount, 0, sizeof(int), c->stream));
         if (rcOut != LGS_OK) break;
@@ -522,7 +523,7 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         // chunk through the table path below, which carries the exact host fix-up.
         const size_t fusedSmem = (size_t)kFusedBeams * (2 * sizeof(double) + (size_t)(nX + nYp) * sizeof(int));
         const long long fusedThreads = (long long)nX * groups;
-        const bool tablesOnly = getenv("LGS_GS_TABLES") != nullptr;   // test / diagnostic hook: force the table path
+        const bool tablesOnly = c->opt.gsTables != 0;   // test / diagnostic hook: force the table path
         bool done = false;
         if (!tablesOnly && hyp > 0 && nT > 0 && maxBeams > 0 && fusedThreads <= 1024 && fusedSmem <= 48 * 1024) {
             dim3 gf(nT, nq);
@@ -548,8 +549,8 @@ int lgs_gs_match(lgs_ctx* c, const lgs_gs_params* p, const lgs_scan_batch* scans
         }
         std::vector<int> fixups(nq, 0);
         if (!done) {
-        GS_TRY(cudaMallocAsync(&dCol, std::max<long long>(colCells, 1) * sizeof(int), c->stream));
-        if (rcOut == LGS_OK) GS_TRY(cudaMallocAsync(&dRow, std::max<long long>(rowCells, 1) * sizeof(int), c->stream));
+        GS_TRY(lgs_alloc_async(c, &dCol, std::max<long long>(colCells, 1) * sizeof(int)));
+        if (rcOut == LGS_OK) GS_TRY(lgs_alloc_async(c, &dRow, std::max<long long>(rowCells, 1) * sizeof(int)));
         if (rcOut != LGS_OK) break;
         if (maxBeams > 0 && nT > 0) {
             dim3 gp((unsigned)(((long long)nT * maxBeams + 127) / 128), nq);

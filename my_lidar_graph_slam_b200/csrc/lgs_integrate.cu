@@ -595,11 +595,12 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     const long long total = scans->hit_begin[n];
     if (total > 0 && !scans->hit_xy) return lgs_fail(c, LGS_ERR_INVALID, "integrate: hit_xy is NULL");
     LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, lgs_grid_acquire(c, grid));
     if (!c->integ) c->integ = new lgs_integ_ws();
     lgs_integ_ws& w = *c->integ;
     // LGS_INTEG_HOSTTIMING=1 (diagnostic): host wall time of the call's phases to stderr when a call
     // takes longer than a millisecond.
-    static const bool hostTiming = getenv("LGS_INTEG_HOSTTIMING") != nullptr;
+    const bool hostTiming = c->opt.integHostTiming != 0;
     const auto tStart = std::chrono::steady_clock::now();
     auto msSince = [](std::chrono::steady_clock::time_point t) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -650,12 +651,12 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     // Side buffer for touch sequences that fit no record format (words; LGS_INTEG_SIDE_WORDS is a test
     // hook that shrinks it to exercise the exhaustive fallback).
     size_t sideCap = (size_t)8 << 20;
-    if (const char* e = getenv("LGS_INTEG_SIDE_WORDS")) sideCap = (size_t)std::max(8, atoi(e));
+    if (c->opt.integSideWords > 0) sideCap = (size_t)std::max<long long>(8, c->opt.integSideWords);
     // tiles of scan s's reach: the square of half side maxLen around the sensor cell
     auto tileSpan = [](int lo, int hi) { return (hi >> kTileShift) - (lo >> kTileShift) + 1; };
     // LGS_INTEG_TIMING=1 (diagnostic): CUDA-event time of every pass, summed over the call, to stderr.
-    const bool timing = getenv("LGS_INTEG_TIMING") != nullptr;
-    const bool diag = timing && getenv("LGS_INTEG_DIAG") != nullptr;   // + per-cell update counts (slows the fold)
+    const bool timing = c->opt.integTiming != 0;
+    const bool diag = timing && c->opt.integDiag != 0;   // + per-cell update counts (slows the fold)
     std::vector<cudaEvent_t> evs;
     auto stamp = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
     // The fold pass runs on a second stream so that it overlaps the next chunk's touch passes
@@ -787,7 +788,7 @@ int lgs_grid_resize(lgs_grid* g, int nx, int ny, double minX, double minY, int s
     const size_t bytes = (size_t)pitch * rows * sizeof(double);
     // stream-ordered: the new buffer comes from the pool and the old one returns to it after the
     // copy, without synchronising the device (a map that grows every few frames pays microseconds)
-    cudaError_t e = cudaMallocAsync(&nd, std::max<size_t>(bytes, 8), c->stream);
+    cudaError_t e = lgs_alloc_async(c, &nd, std::max<size_t>(bytes, 8));
     if (e != cudaSuccess) return lgs_fail(c, LGS_ERR_NOMEM, "grid_resize: cudaMallocAsync(%zu) -> %s", bytes, cudaGetErrorString(e));
     LGS_CUDA(c, cudaMemsetAsync(nd, 0, bytes, c->stream));
     if (nx > 0 && ny > 0) {

@@ -23,6 +23,7 @@ struct lgs_grid {
     // conversions stay global (bit-identical to the whole map) and subtract the offset.
     int off_x = 0, off_y = 0;
     bool owns = true;     // false for pyramid levels (views into the pyramid's slab)
+    mutable bool foreign = false;   // a stream of ANOTHER context has read it (lgs_grid_acquire): destroy drains the device
     double* d = nullptr;  // rows * pitch doubles; cell (x, y) at d[(y + apron) * pitch + x + apron]
     __host__ __device__ const double* origin() const { return d + (size_t)apron * pitch + apron; }
     __host__ __device__ double* origin() { return d + (size_t)apron * pitch + apron; }
@@ -126,11 +127,36 @@ struct lgs_integ_ws {
 struct lgs_cost_ws;
 void lgs_cost_ws_destroy(lgs_cost_ws* ws);
 
+// Tuning / diagnostic / test hooks of one context.  The LGS_* environment variables only supply the
+// DEFAULTS, read once in lgs_ctx_create; afterwards lgs_ctx_set_option is the only way to change
+// them, so no run path reads the environment or any process-global state.
+struct lgs_opts {
+    double edgeEps = 1e-9;      // "edge_eps"        fractional-cell guard band (see below)
+    int csmFlat = 0;            // "csm_flat"        LGS_CSM_FLAT: flattened correlative sweep
+    int bbSync = 0;             // "bb_sync"         LGS_BB_SYNC: level-synchronous B&B runs only
+    int bbTable = 0;            // "bb_table"        LGS_BB_TABLE: level-synchronous runs through the full index table
+    int bbWarpBelow = 8192;     // "bb_warp_below"   LGS_BB_WARP_BELOW: node count below which a level scores a warp per node
+    int bbResolveUlps = 8;      // "bb_resolve_ulps" half width (ulps of cos / sin) of the on-device near-edge resolution
+    int bbVariant = 0;          // "bb_variant"      persistent kernel build: 0 = 16 beams in flight x 2 CTAs/SM, 1 = 8 x 4
+    int bbBlocksPerSm = 0;      // "bb_blocks_per_sm" persistent B&B kernel residency (0 = occupancy limit)
+    double bbCost[4] = {70.0, 24.0, 15.0, 9.0};   // "bb_cost_g1/g4/g8/g32" per-pass cost (us) of the warp mappings
+    int bbHostTiming = 0;       // "bb_host_timing"  LGS_BB_HOSTTIMING
+    int integHostTiming = 0;    // "integ_host_timing" LGS_INTEG_HOSTTIMING
+    int integTiming = 0;        // "integ_timing"    LGS_INTEG_TIMING
+    int integDiag = 0;          // "integ_diag"      LGS_INTEG_DIAG
+    long long integSideWords = 0; // "integ_side_words" LGS_INTEG_SIDE_WORDS (0 = default size)
+    int gsTables = 0;           // "gs_tables"       LGS_GS_TABLES: grid search through the index tables
+};
+
 struct lgs_ctx {
+    lgs_opts opt;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;            // PRIVATE stream-ordered pool (grids, pyramid slabs, call scratch)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evOrder = nullptr;           // cross-context ordering (lgs_grid_acquire)
     int sm_count = 148;
+    int bbBlocks = 0;         // grid of the persistent branch-and-bound kernel (0: not yet sized)
     long long launches = 0;
     char err[512] = {0};
     DevBuf<double> scratch;   // reusable device scratch (precompute intermediate)
@@ -143,7 +169,20 @@ struct lgs_ctx {
 // differ from glibc's in the last ulp.  Device-vs-host differences are
 // below 1e-11 cells for |coordinates| < 1e4 m, so 1e-9 leaves two orders of magnitude.
 #define LGS_EDGE_EPS_DEFAULT 1e-9
-extern double g_lgs_edge_eps;
+
+// Stream-ordered allocation from the context's private pool (freed with cudaFreeAsync).
+inline cudaError_t lgs_alloc_async(lgs_ctx* c, void** p, size_t bytes) {
+    return cudaMallocFromPoolAsync(p, bytes, c->pool, c->stream);
+}
+template <typename T>
+inline cudaError_t lgs_alloc_async(lgs_ctx* c, T** p, size_t bytes) {
+    return lgs_alloc_async(c, reinterpret_cast<void**>(p), bytes);
+}
+// Context `user` is about to read grid `g` on its stream.  If the grid belongs to another context
+// (the builder's latest map read by the matcher's context), everything already queued on the owner's
+// stream is ordered before the reader, and the grid remembers the foreign reader so that destroying
+// it drains the device first (its buffer is freed stream-ordered on the OWNER's stream only).
+cudaError_t lgs_grid_acquire(lgs_ctx* user, const lgs_grid* g);
 
 // Pyramid levels are plain grids sharing the geometry of the map they were built from.
 const lgs_grid* lgs_pyramid_level(const lgs_pyramid* p, int level);

@@ -114,10 +114,16 @@ struct lgs_pyramid {
     double* slab = nullptr;             // all levels, contiguous
     std::vector<lgs_grid*> levels;      // headers into the slab (owns == false)
     bool foreign = false;               // read by a context other than the owner (another stream)
+    const lgs_ctx* lastUser = nullptr;  // the foreign context already ordered after the build
 };
 
 void lgs_pyramid_note_user(const lgs_pyramid* p, const lgs_ctx* user) {
-    if (p && user != p->ctx) const_cast<lgs_pyramid*>(p)->foreign = true;
+    if (!p || user == p->ctx || user == p->lastUser) return;   // the levels never change after the build
+    const_cast<lgs_pyramid*>(p)->foreign = true;
+    const_cast<lgs_pyramid*>(p)->lastUser = user;
+    // the build queued on the owner's stream is ordered before the foreign reader
+    lgs_ctx* u = const_cast<lgs_ctx*>(user);
+    if (cudaEventRecord(u->evOrder, p->ctx->stream) == cudaSuccess) cudaStreamWaitEvent(u->stream, u->evOrder, 0);
 }
 
 const lgs_grid* lgs_pyramid_level(const lgs_pyramid* p, int level) {
@@ -133,6 +139,8 @@ int lgs_precompute(lgs_ctx* c, const lgs_grid* in, int win, lgs_grid* out) {
         return lgs_fail(c, LGS_ERR_INVALID, "precompute: output must be a distinct grid of equal geometry");
     if (in->nx == 0 || in->ny == 0) return LGS_OK;
     LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, lgs_grid_acquire(c, in));      // pending integration / resize work of another context
+    LGS_CUDA(c, lgs_grid_acquire(c, out));
     LGS_CUDA(c, c->scratch.reserve((size_t)in->nx * in->ny));
     dim3 block(256), gridDim((in->nx + 255) / 256, in->ny);
     winmax_y_kernel<<<gridDim, block, 0, c->stream>>>(in->origin(), c->scratch.p, in->nx, in->ny,
@@ -149,6 +157,7 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
     *outp = nullptr;
     if (heightMax < 0 || heightMax > 20) return lgs_fail(c, LGS_ERR_INVALID, "pyramid: height %d", heightMax);
     LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, lgs_grid_acquire(c, in));      // pending integration / resize work of another context
     lgs_pyramid* p = new lgs_pyramid();
     p->ctx = c;
     // One slab for all levels (one cudaMalloc + one memset instead of one per level): every level
@@ -157,7 +166,7 @@ int lgs_pyramid_create(lgs_ctx* c, const lgs_grid* in, int heightMax, lgs_pyrami
     const size_t bytes = levelCells * (size_t)(heightMax + 1) * sizeof(double);
     // Stream-ordered allocation from the device pool (kept warm by lgs_ctx_create's release
     // threshold): rebuilding a pyramid does not pay a synchronous cudaMalloc of the whole slab.
-    cudaError_t me = cudaMallocAsync(&p->slab, std::max<size_t>(bytes, 8), c->stream);
+    cudaError_t me = lgs_alloc_async(c, &p->slab, std::max<size_t>(bytes, 8));
     if (me != cudaSuccess) {
         delete p;
         return lgs_fail(c, LGS_ERR_NOMEM, "pyramid: cudaMallocAsync(%zu) -> %s", bytes, cudaGetErrorString(me));

@@ -9,16 +9,16 @@ from my_lidar_graph_slam_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["table", "slots"])
-def bb_root_path(request, monkeypatch):
-    """Every test runs twice: with the library's own choice between the full per-query index table and
-    the root-from-hit-points path (queries here mostly have their own scan -> table), and with the
-    hit-point path forced."""
-    if request.param == "slots":
-        monkeypatch.setenv("LGS_BB_SLOTS", "1")
-    else:
-        monkeypatch.delenv("LGS_BB_SLOTS", raising=False)
+@pytest.fixture(autouse=True, params=["device", "device-b", "exact"])
+def bb_run_path(request, ctx):
+    """Every test runs three times: through the device-only run (ONE persistent kernel: fixed-point
+    cells, near-edge points decided on the device) in both of its builds, and through the
+    level-synchronous exact path (full index table, near-edge points from the host)."""
+    ctx.set_option("bb_sync", 1 if request.param == "exact" else 0)
+    ctx.set_option("bb_variant", 1 if request.param == "device-b" else 0)
     yield request.param
+    ctx.set_option("bb_sync", 0)
+    ctx.set_option("bb_variant", 0)
 
 DEF = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0, scan_range_max=20.0,
            score_range_min=0.01, score_range_max=20.0)
@@ -122,11 +122,12 @@ def test_bb_parameter_sweep(ctx, submap, params, thr):
 
 
 def test_bb_near_edge_fixups_do_not_change_results(ctx, submap):
-    """Widen the edge guard band so ~5 % of the projected points take the host-exact path."""
+    """Widen the edge guard band so ~5 % of the projected points take the exact evaluation (on the
+    device: interval evaluation of the CPU's expression; exact path: the host's glibc tables)."""
     from oracle import backend
     R = backend()
     qs = _queries(submap, 2, seed=21)
-    capi.set_edge_eps(0.025)
+    ctx.set_edge_eps(0.025)
     try:
         for scan, init in qs:
             ref = R.bb_match(submap["refmap"], submap["angles"], scan, init, pyramid=submap["refpyr"],
@@ -139,7 +140,7 @@ def test_bb_near_edge_fixups_do_not_change_results(ctx, submap):
             assert out.n_fixups > 1000
             _same(out, ref)
     finally:
-        capi.set_edge_eps(1e-9)
+        ctx.set_edge_eps(1e-9)
 
 
 def test_bb_low_edge_overhang_uses_replay(ctx):
@@ -185,40 +186,77 @@ def test_bb_empty_batch_and_bad_pyramid(ctx, submap):
         batch.upload(capi.Scans([submap["angles"]], [scan], [init]), [shallow], 0.6)
 
 
-def test_speculative_sync_free_runs_match_the_level_synchronous_run(ctx, submap, monkeypatch):
-    """The first run of a batch object is level-synchronous; later runs launch every level without
-    waiting for its node count (pool capacities + device-side counts) and are validated afterwards.
-    Both must give identical results -- also when the pools sized by a small batch overflow."""
-    qs = _queries(submap, 6, seed=21)
+def test_device_only_runs_match_the_exact_path_and_survive_pool_overflow(ctx, submap, bb_run_path):
+    """A device-only run never talks to the host; its node pools are sized from earlier runs.  A batch
+    that outgrows them (low threshold: almost the whole tree survives) is detected on the device and
+    repeated on the exact path, which also re-sizes the pools for the following device-only runs."""
+    qs = _queries(submap, 4, seed=21)
+    params = dict(DEF, node_height_max=4, range_x=1.0, range_y=1.0, range_theta=0.3)
+    pyr = capi.Pyramid(ctx, submap["grid"], 4)
     mk = lambda sub: capi.Scans([submap["angles"]] * len(sub), [s for s, _ in sub], [p for _, p in sub],
                                 range_min=0.02, range_max=30.0)
     key = lambda o: (o.found, o.ix, o.iy, o.it, o.score)
-    monkeypatch.setenv("LGS_BB_SYNC", "1")
-    ref_batch = capi.BbBatch(ctx, **DEF)
-    ref_batch.upload(mk(qs), [submap["pyr"]] * len(qs), 0.5)
-    ref_batch.run()
-    want = [key(o) for o in ref_batch.results()]
-    want_levels = ref_batch.work()[0]
-    monkeypatch.delenv("LGS_BB_SYNC")
-    batch = capi.BbBatch(ctx, **DEF)
-    batch.upload(mk(qs[:1]), [submap["pyr"]], 0.5)        # small batch: sizes the pools, leaves hints
-    batch.run()
-    assert [key(o) for o in batch.results()] == want[:1]
-    batch.upload(mk(qs), [submap["pyr"]] * len(qs), 0.5)   # 6x the work: speculative run overflows -> redone
-    batch.run()
-    assert [key(o) for o in batch.results()] == want
-    for _ in range(3):                                    # steady state: speculative runs validate
+    ctx.set_option("bb_sync", 1)
+    ref_batch = capi.BbBatch(ctx, **params)
+    want, want_levels = {}, {}
+    for thr in (0.5, 0.02):
+        ref_batch.upload(mk(qs), [pyr] * len(qs), thr)
+        ref_batch.run()
+        want[thr] = [key(o) for o in ref_batch.results()]
+        want_levels[thr] = ref_batch.work()[0]
+    ctx.set_option("bb_sync", 1 if bb_run_path == "exact" else 0)
+    assert sum(want_levels[0.02]) > 4 * sum(want_levels[0.5])
+    batch = capi.BbBatch(ctx, **params)
+    batch.upload(mk(qs), [pyr] * len(qs), 0.5)
+    for _ in range(2):
         batch.run()
-        assert [key(o) for o in batch.results()] == want
-        assert batch.work()[0] == want_levels
+        assert [key(o) for o in batch.results()] == want[0.5]
+        assert batch.work()[0] == want_levels[0.5]
+    dev0, exact0 = batch.path()
+    batch.upload(mk(qs), [pyr] * len(qs), 0.02)            # the pools sized so far overflow
+    batch.run()
+    assert [key(o) for o in batch.results()] == want[0.02]
+    assert batch.work()[0] == want_levels[0.02]
+    dev1, exact1 = batch.path()
+    if bb_run_path != "exact":
+        assert dev0 == 2 and exact0 == 0
+        assert dev1 == 3 and exact1 == 1                  # the overflowed run was repeated exactly
+    for _ in range(2):                                    # steady state: the grown pools hold the tree
+        batch.run()
+        assert [key(o) for o in batch.results()] == want[0.02]
+    if bb_run_path != "exact":
+        assert batch.path() == (5, 1)
 
 
-def test_bb_root_from_hit_points_with_a_few_near_edge_points(ctx, submap):
-    """With at most 8 near-edge points the root level is scored straight from the hit points and only
-    surviving (query, theta) rows get index rows; the flagged points still take the host's exact
-    tables.  Widen the guard band just enough to flag a handful of points and compare with the
-    reference; LGS_BB_TABLE=1 (full per-query table) must give the same answers."""
-    import os
+def test_undecided_near_edge_points_fall_back_to_the_exact_path(ctx, submap, bb_run_path):
+    """The device decides a near-edge point by evaluating the CPU's expression at both ends of an
+    interval around its own cos / sin.  With an absurdly wide interval ("bb_resolve_ulps") and a wide
+    guard band the ends disagree for many points: the run must report them, be repeated on the exact
+    path, and still return the reference's answer."""
+    from oracle import backend
+    R = backend()
+    (scan, init), = _queries(submap, 1, seed=44)
+    ref = R.bb_match(submap["refmap"], submap["angles"], scan, init, pyramid=submap["refpyr"],
+                     thr=0.6, **_ref_kwargs(DEF))
+    try:
+        ctx.set_edge_eps(1e-4)
+        ctx.set_option("bb_resolve_ulps", 2_000_000_000)
+        batch = capi.BbBatch(ctx, **DEF)
+        batch.upload(capi.Scans([submap["angles"]], [scan], [init], range_min=0.02, range_max=30.0),
+                     [submap["pyr"]], 0.6)
+        batch.run()
+        (out,) = batch.results()
+        _same(out, ref)
+        if bb_run_path != "exact":
+            assert batch.path() == (1, 1) and out.reserved == 1
+    finally:
+        ctx.set_edge_eps(1e-9)
+        ctx.set_option("bb_resolve_ulps", 8)
+
+
+def test_a_few_near_edge_points_are_decided_identically_on_both_paths(ctx, submap):
+    """Widen the guard band just enough to flag a handful of points and compare with the reference;
+    the device-only run (on-device interval evaluation) and the exact path (host tables) must agree."""
     from oracle import backend
     R = backend()
     qs = _queries(submap, 3, seed=33)
@@ -229,26 +267,50 @@ def test_bb_root_from_hit_points_with_a_few_near_edge_points(ctx, submap):
     seen_small = False
     try:
         for eps in (1e-9, 3e-7, 6e-7, 1.2e-6, 2.4e-6):
-            capi.set_edge_eps(eps)
-            for table in (False, True):
-                os.environ["LGS_BB_SLOTS"] = "1"       # one scan per query here: force the hit-point root path
-                if table:
-                    os.environ["LGS_BB_TABLE"] = "1"
-                else:
-                    os.environ.pop("LGS_BB_TABLE", None)
-                batch = capi.BbBatch(ctx, **DEF)
-                batch.upload(scans, [submap["pyr"]] * len(qs), 0.5)
-                for rep in range(2):
-                    batch.run()
-                    outs = batch.results()
-                    for out, ref in zip(outs, refs):
-                        _same(out, ref)
-                nfix = sum(o.n_fixups for o in outs)
-                if not table and 1 <= nfix <= 8:
-                    seen_small = True
-                batch.close()
+            ctx.set_edge_eps(eps)
+            batch = capi.BbBatch(ctx, **DEF)
+            batch.upload(scans, [submap["pyr"]] * len(qs), 0.5)
+            for rep in range(2):
+                batch.run()
+                outs = batch.results()
+                for out, ref in zip(outs, refs):
+                    _same(out, ref)
+            nfix = sum(o.n_fixups for o in outs)
+            if 1 <= nfix <= 16:
+                seen_small = True
+            batch.close()
     finally:
-        os.environ.pop("LGS_BB_TABLE", None)
-        os.environ.pop("LGS_BB_SLOTS", None)
-        capi.set_edge_eps(1e-9)
-    assert seen_small, "no guard band produced between 1 and 8 near-edge points"
+        ctx.set_edge_eps(1e-9)
+    assert seen_small, "no guard band produced between 1 and 16 near-edge points"
+
+
+def test_records_and_device_sink(ctx, submap):
+    """The finalize phase writes one 32-byte record per pair: into the batch's own buffer and, when a
+    sink is set, at sink[first_slot + q] -- here a second batch's record buffer stands in for the
+    peer-mapped gather buffer of another GPU."""
+    qs = _queries(submap, 5, seed=8)
+    scans = capi.Scans([submap["angles"]] * len(qs), [s for s, _ in qs], [p for _, p in qs],
+                       range_min=0.02, range_max=30.0)
+    batch = capi.BbBatch(ctx, **DEF)
+    ids = np.array([70, 10, 40, 20, 90], dtype=np.int64)
+    batch.set_record_ids(ids)
+    batch.upload(scans, [submap["pyr"]] * len(qs), 0.6)
+    batch.run()
+    outs = batch.results()
+    rec = batch.records()
+    assert rec["submap"].tolist() == ids.tolist()
+    for o, r in zip(outs, rec):
+        assert (o.found, o.ix, o.iy, o.it, o.score) == (int(r["found"]), int(r["ix"]), int(r["iy"]), int(r["it"]), float(r["score"]))
+    # sink: slots 3.. of a larger device buffer (owned by another batch object that has run 8 queries)
+    other = capi.BbBatch(ctx, **DEF)
+    qs8 = _queries(submap, 8, seed=9)
+    other.upload(capi.Scans([submap["angles"]] * 8, [s for s, _ in qs8], [p for _, p in qs8],
+                            range_min=0.02, range_max=30.0), [submap["pyr"]] * 8, 0.6)
+    other.run()
+    other.settle()
+    batch.set_record_sink(other.device_records(), 3)
+    batch.run()
+    batch.settle()
+    got = capi.download_records(ctx, other.device_records(), 8)
+    assert got[3:].tobytes() == rec.tobytes()
+    batch.set_record_sink(0)

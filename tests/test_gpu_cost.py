@@ -83,10 +83,10 @@ def test_cost_host_fixups_leave_results_identical(ctx):
     wn, _, wc = R.host_tail(refmap, traj[11], angles, scan)
     assert base_nc[0] == wn and np.array_equal(base_cov[0], wc) and wn < 0.0
     try:
-        capi.set_edge_eps(0.3)
+        ctx.set_edge_eps(0.3)
         nc, cov, fix = capi.cost_tail(ctx, grid, batch, [traj[11]])
     finally:
-        capi.set_edge_eps(0.0)          # restores the default
+        ctx.set_edge_eps(0.0)          # restores the default
     assert fix > 1000 and fix0 < 5
     assert nc[0] == wn and np.array_equal(cov[0], wc)
 

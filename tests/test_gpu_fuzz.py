@@ -85,14 +85,12 @@ def test_random_scene_end_to_end(ctx, seed):
                        range_x=bp["range_x"], range_y=bp["range_y"], range_theta=bp["range_theta"],
                        scan_range_max=bp["scan_range_max"], score_range_min=0.01,
                        score_range_max=bp["score_range_max"]) for scan, init in qs]
-    import os
-    for rep in range(3):                      # later runs take the speculative sync-free path; the last
-        if rep == 2:                          # one forces the root-from-hit-points path
-            os.environ["LGS_BB_SLOTS"] = "1"
+    for rep in range(3):                      # device-only runs (one persistent kernel); the last one is forced
+        ctx.set_option("bb_sync", 1 if rep == 2 else 0)      # through the level-synchronous exact path
         try:
             bb.run()
         finally:
-            os.environ.pop("LGS_BB_SLOTS", None)
+            ctx.set_option("bb_sync", 0)
         for k, (out, ref) in enumerate(zip(bb.results(), refs)):
             assert (out.found, out.ix, out.iy, out.it) == (ref.found, ref.ix, ref.iy, ref.it), ("bb", k, rep)
             if ref.found:

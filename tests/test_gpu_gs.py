@@ -20,13 +20,11 @@ def _ints(r):
 
 
 @pytest.fixture(params=["fused", "tables"], autouse=True)
-def gs_path(request, monkeypatch):
-    """Every test runs through the fused kernel and through the index-table path (LGS_GS_TABLES)."""
-    if request.param == "tables":
-        monkeypatch.setenv("LGS_GS_TABLES", "1")
-    else:
-        monkeypatch.delenv("LGS_GS_TABLES", raising=False)
-    return request.param
+def gs_path(request, ctx):
+    """Every test runs through the fused kernel and through the index-table path ("gs_tables")."""
+    ctx.set_option("gs_tables", 1 if request.param == "tables" else 0)
+    yield request.param
+    ctx.set_option("gs_tables", 0)
 
 
 def test_gs_golden_vectors(ctx):
@@ -73,10 +71,10 @@ def test_gs_every_hypothesis_score_bit_exact(ctx):
     assert r.score == ref.score == want.max()
     # forced host fix-ups (huge guard band: every beam takes the glibc path) change nothing
     try:
-        capi.set_edge_eps(0.3)
+        ctx.set_edge_eps(0.3)
         (r2,), table2 = capi.gs_match(ctx, batch, [grid], norm_threshold=0.1, want_table=True, **p)
     finally:
-        capi.set_edge_eps(0.0)
+        ctx.set_edge_eps(0.0)
     assert r2.n_fixups > 1000 and np.array_equal(table2, table) and _ints(r2) == _ints(r)
 
 

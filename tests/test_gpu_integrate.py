@@ -132,8 +132,8 @@ def test_real_scans_never_need_the_exhaustive_fallback(ctx):
     assert capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h) == before
 
 
-def test_exhausted_side_buffer_falls_back_to_exact_beam_tests(ctx, monkeypatch):
-    """LGS_INTEG_SIDE_WORDS shrinks the side buffer to nothing: every long mixed sequence takes the
+def test_exhausted_side_buffer_falls_back_to_exact_beam_tests(ctx):
+    """The "integ_side_words" option shrinks the side buffer to nothing: every long mixed sequence takes the
     exhaustive per-beam path in the fold pass and the map must still be bit-identical."""
     from oracle import backend
     R = backend()
@@ -148,10 +148,7 @@ def test_exhausted_side_buffer_falls_back_to_exact_beam_tests(ctx, monkeypatch):
     want = sum(R.map_integrate_hits(ref, p[:2], h) for p, h in zip(traj, hits))
     maps = []
     for side in ("8", None):
-        if side:
-            monkeypatch.setenv("LGS_INTEG_SIDE_WORDS", side)
-        else:
-            monkeypatch.delenv("LGS_INTEG_SIDE_WORDS")
+        ctx.set_option("integ_side_words", int(side) if side else 0)
         grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
         before = capi.lib().lgs_ctx_integrate_fallback_cells(ctx.h)
         assert capi.integrate_scans(ctx, grid, traj[:, :2], hits) == want

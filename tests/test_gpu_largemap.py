@@ -8,16 +8,14 @@ from my_lidar_graph_slam_b200 import capi, largemap, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["table", "slots"])
-def bb_root_path(request, monkeypatch):
-    """Every test runs twice: with the library's own choice between the full per-query index table and
-    the root-from-hit-points path (queries here mostly have their own scan -> table), and with the
-    hit-point path forced."""
-    if request.param == "slots":
-        monkeypatch.setenv("LGS_BB_SLOTS", "1")
-    else:
-        monkeypatch.delenv("LGS_BB_SLOTS", raising=False)
+@pytest.fixture(autouse=True, params=["device", "exact"])
+def bb_run_path(request, ctx):
+    """Every test runs twice: through the device-only run (one persistent kernel, fixed-point cells,
+    near-edge points decided on the device) and through the level-synchronous exact path (full index
+    table, near-edge points from the host)."""
+    ctx.set_option("bb_sync", 1 if request.param == "exact" else 0)
     yield request.param
+    ctx.set_option("bb_sync", 0)
 
 # short usable range so that three bands of a ~900-row map are real windows (margins ~100 / ~230 rows)
 P = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=0.5, scan_range_max=4.0,
