@@ -57,9 +57,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-// Two builds of the kernel (option "bb_variant"): 0 = 16 beams in flight per lane, 2 CTAs per SM
-// (128 registers); 1 = 16 beams in flight, 3 CTAs per SM (80 registers): same loads in flight per SM,
-// twice the nodes per pass.
+// 16 beams in flight per lane, 2 CTAs per SM (128 registers).
 template <int KU> struct StageRow { static constexpr int value = 32 * KU + 8; };   // doubles of staging per warp: (32 / G) rows of KU * G + 1
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -73,9 +71,12 @@ struct NodeRef {
     bool active;
 };
 
-// The CPU's cell of beam i of (query, theta, node offset) -- or, if the interval around the device's
-// cos / sin straddles a cell edge, an unresolved point (counted; the host repeats the run exactly).
-__device__ __noinline__ double bb_exact_value(const RunArgs& a, int q, int t, int i, int x, int y, int h) {
+// The CPU's cell of beam i of (query, theta, node offset), as an offset into the level's padded grid --
+// or, if the interval around the device's cos / sin straddles a cell edge, an unresolved point
+// (counted; the host repeats the run exactly).  Called BEFORE the gathers of a round are issued, when
+// only the round's offsets are live (a call with the cell values and the prefetched hit points in
+// registers spills them).
+__device__ __noinline__ int bb_exact_offset(const RunArgs& a, int q, int t, int i, int x, int y, int h) {
     const BbQuery& d = a.qs[q];
     const BbScan& u = a.us[d.scan];
     // nodePose (scan_matcher_branch_bound.cpp:96-99), HitPoint (sensor_data.hpp:162-173),
@@ -99,7 +100,7 @@ __device__ __noinline__ double bb_exact_value(const RunArgs& a, int q, int t, in
     if (h == a.H) atomicAdd(&a.best[q].fixups, 1);
     const int ix = min(max(ix0 - d.offX, -1), d.nx);
     const int iy = min(max(iy0 - d.offY, -1), d.ny);
-    return __ldg(d.level[h] + (long long)iy * d.pitch + ix);
+    return iy * d.pitch + ix;           // relative to the level's cell (0, 0)
 }
 
 // Lane roles of the warp mappings.  G = 1 / 4 read the [beam][theta] hit array: lanes that are
@@ -122,110 +123,155 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
     (void)sub; (void)row;
     const BbQuery* dq = a.qs + (n.active ? n.q : 0);
     const BbScan* su = a.us + dq->scan;
-    const double* __restrict__ lvl = dq->level[h];
     const int t = n.active ? n.t : 0;
     // hit point of beam b: hb[b * stride]
     const int2* hb = LaneMap<G>::kBeamMajor ? a.hitsT + su->hitTBegin + (long long)t * su->beamPad
                                             : a.hits + su->hitBegin + t;
-    const int stride = LaneMap<G>::kBeamMajor ? 1 : su->nTpad;
-    // cell = ((H - Mlo) >> 20) - (Mhi - node offset); frac = (H - Mlo) & (2^20 - 1)
+    const unsigned stride = LaneMap<G>::kBeamMajor ? 1u : (unsigned)su->nTpad;
+    // cell + 1 = ((H - Mlo) >> 20) - (Mhi - node offset - 1), frac = (H - Mlo) & (2^20 - 1).  The + 1
+    // turns "clamp into [-1, n]" (out of the map -> zero apron) into ONE unsigned min: a cell left of /
+    // below the map wraps to a huge unsigned value and lands in the right / upper apron, which is zero too.
     const int mlx = dq->MloX, mly = dq->MloY;
-    const int cx = dq->MhiX - n.x, cy = dq->MhiY - n.y;
-    const int pitch = dq->pitch, gx = dq->nx, gy = dq->ny;
+    const int cx = dq->MhiX - n.x - 1, cy = dq->MhiY - n.y - 1;
+    const int pitch = dq->pitch;
+    const unsigned gx1 = (unsigned)dq->nx + 1u, gy1 = (unsigned)dq->ny + 1u;
+    const double* __restrict__ lvl = dq->level[h] - pitch - 1;        // cell (-1, -1) of the padded level
     const int nb = n.active ? dq->nUse : 0;
     const unsigned E = a.edgeUnits, E2 = 2u * a.edgeUnits;
     double acc = 0.0;
 
-    auto offset = [&](const int2 hp, unsigned& edge) -> int {
+    // offset of the beam's cell; `near` keeps the smallest distance-to-edge measure seen so far
+    // (one compare per round instead of one per beam and axis)
+    auto offset = [&](const int2 hp, unsigned& near) -> unsigned {
         const int dx = hp.x - mlx, dy = hp.y - mly;
-        edge = ((((unsigned)dx + E) & 0xfffffu) < E2) | ((((unsigned)dy + E) & 0xfffffu) < E2);
-        const int ix = min(max((dx >> 20) - cx, -1), gx);      // out of the map -> zero apron
-        const int iy = min(max((dy >> 20) - cy, -1), gy);
-        return iy * pitch + ix;
+        near = min(near, min(((unsigned)dx + E) & 0xfffffu, ((unsigned)dy + E) & 0xfffffu));
+        const unsigned ix = min((unsigned)((dx >> 20) - cx), gx1);
+        const unsigned iy = min((unsigned)((dy >> 20) - cy), gy1);
+        return iy * (unsigned)pitch + ix;
+    };
+    auto is_near = [&](const int2 hp) -> bool {
+        const int dx = hp.x - mlx, dy = hp.y - mly;
+        return ((((unsigned)dx + E) & 0xfffffu) < E2) | ((((unsigned)dy + E) & 0xfffffu) < E2);
+    };
+    // near-edge beam: the CPU's own cell, + 1 per axis like `offset`
+    auto exact = [&](int beam) -> unsigned {
+        return (unsigned)(bb_exact_offset(a, n.q, n.t, beam, n.x, n.y, h) + pitch + 1);
     };
 
     if constexpr (G == 1) {
         if (!n.active) return 0.0;
-        int i = 0;
+        const int nFull = nb / kU;
+        const int2* hr = hb;                           // hit points of the current round: hr[u * stride]
+        const size_t roundStep = (size_t)kU * stride;
+        int2 hp[kU];
 #pragma unroll 1
-        for (; i + kU <= nb; i += kU) {
-            int2 hp[kU];
-            int off[kU];
+        for (int r = 0; r < nFull; ++r) {
+            unsigned off[kU];
             double v[kU];
-            unsigned fl = 0;
+            unsigned near = 0xffffffffu;
 #pragma unroll
-            for (int u = 0; u < kU; ++u) hp[u] = hb[(i + u) * stride];
+            for (int u = 0; u < kU; ++u) hp[u] = hr[(unsigned)u * stride];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                unsigned e;
-                off[u] = offset(hp[u], e);
-                fl |= e << u;
+            for (int u = 0; u < kU; ++u) off[u] = offset(hp[u], near);
+            if (near < E2) {                 // rare: one call site, the patch is a select chain (off[] stays in registers)
+#pragma unroll 1
+                for (int u = 0; u < kU; ++u) {
+                    int2 hq = hp[0];
+#pragma unroll
+                    for (int w = 1; w < kU; ++w) hq = (w == u) ? hp[w] : hq;
+                    if (!is_near(hq)) continue;
+                    const unsigned o = exact(r * kU + u);
+#pragma unroll
+                    for (int w = 0; w < kU; ++w) off[w] = (w == u) ? o : off[w];
+                }
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) v[u] = __ldg(lvl + off[u]);
-            if (fl) {
-#pragma unroll
-                for (int u = 0; u < kU; ++u)
-                    if ((fl >> u) & 1u) v[u] = bb_exact_value(a, n.q, n.t, i + u, n.x, n.y, h);
-            }
+            hr += roundStep;
 #pragma unroll
             for (int u = 0; u < kU; ++u) acc = __dadd_rn(acc, v[u]);      // beam order; unknown cells add 0.0
         }
-        for (; i < nb; ++i) {
-            unsigned e;
-            const int off = offset(hb[i * stride], e);
-            const double v = e ? bb_exact_value(a, n.q, n.t, i, n.x, n.y, h) : __ldg(lvl + off);
-            acc = __dadd_rn(acc, v);
+        for (int i = nFull * kU; i < nb; ++i) {
+            unsigned near = 0xffffffffu;
+            const int2 hq = hb[(unsigned)i * stride];
+            unsigned off = offset(hq, near);
+            if (near < E2) off = exact(i);
+            acc = __dadd_rn(acc, __ldg(lvl + off));
         }
         return acc;
     } else {
-        constexpr int S = kU * G;              // beams per stage
-        constexpr int RS = S + 1;              // row stride (doubles): odd, so the adding lanes hit distinct banks
+        // Stage s = beams [s * S, (s + 1) * S): every lane fetches kV of them, the values are parked in
+        // shared memory in beam order and the node's first lane adds them in that order.  (Measured and
+        // dropped: a software pipeline that keeps the next stage's cells in flight under the adding lanes.
+        // The scoring phases are bound by L1 request wavefronts, not by exposed latency; halving the
+        // stage to afford the second set of registers doubled the per-stage overhead instead.)
+        constexpr int kV = kU;                     // beams per lane per stage
+        constexpr int S = kV * G;                  // beams per stage
+        constexpr int RS = S + 1;                  // row stride (doubles): odd, so the adding lanes hit distinct banks
         const int nbMax = __reduce_max_sync(0xffffffffu, nb);
-        double* rowp = svw + row * RS;
-#pragma unroll 1
-        for (int base = 0; base < nbMax; base += S) {
-            int2 hp[kU];
-            int off[kU];
-            double v[kU];
-            unsigned fl = 0, okm = 0;
+        const int nStages = (nbMax + S - 1) / S;
+        int2 hp[kV];
+        double v[kV];
+        unsigned okm = 0;
+        auto load_hits = [&](int s) {
+            okm = 0;
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int b = base + u * G + sub;
+            for (int u = 0; u < kV; ++u) {
+                const int b = s * S + u * G + sub;
                 const bool ok = b < nb;
                 okm |= (ok ? 1u : 0u) << u;
-                hp[u] = ok ? hb[b * stride] : make_int2(mlx, mly);
+                hp[u] = ok ? hb[(unsigned)b * stride] : make_int2(mlx + 0x80000, mly + 0x80000);   // mid-cell: never near an edge
+            }
+        };
+        auto gather = [&](int s) {      // consumes hp / okm of stage s, leaves the requests for v in flight
+            unsigned off[kV];
+            unsigned near = 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < kV; ++u) off[u] = offset(hp[u], near);
+            if (near < E2) {                 // rare: one call site, the patch is a select chain
+#pragma unroll 1
+                for (int u = 0; u < kV; ++u) {
+                    int2 hq = hp[0];
+#pragma unroll
+                    for (int w = 1; w < kV; ++w) hq = (w == u) ? hp[w] : hq;
+                    if (!((okm >> u) & 1u) || !is_near(hq)) continue;
+                    const unsigned o = exact(s * S + u * G + sub);
+#pragma unroll
+                    for (int w = 0; w < kV; ++w) off[w] = (w == u) ? o : off[w];
+                }
             }
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                unsigned e;
-                off[u] = offset(hp[u], e);
-                fl |= (e & (okm >> u)) << u;
-            }
+            for (int u = 0; u < kV; ++u) v[u] = ((okm >> u) & 1u) ? __ldg(lvl + off[u]) : 0.0;
+        };
+        auto park = [&](int s) {   // v -> shared memory, beam order
+            double* rowp = svw + row * RS;
 #pragma unroll
-            for (int u = 0; u < kU; ++u) v[u] = ((okm >> u) & 1u) ? __ldg(lvl + off[u]) : 0.0;
-            if (fl) {
-#pragma unroll
-                for (int u = 0; u < kU; ++u)
-                    if ((fl >> u) & 1u) v[u] = bb_exact_value(a, n.q, n.t, base + u * G + sub, n.x, n.y, h);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) rowp[u * G + sub] = v[u];
-            __syncwarp();
-            if (sub == 0 && nb > base) {
-                const int m = min(S, nb - base);
+            for (int u = 0; u < kV; ++u) rowp[u * G + sub] = v[u];
+        };
+        auto chain = [&](int s) {  // the node's first lane adds stage s in beam order
+            if (sub == 0 && nb > s * S) {
+                const double* rowp = svw + row * RS;
+                const int m = min(S, nb - s * S);
                 int j = 0;
                 for (; j + 8 <= m; j += 8) {
                     double t8[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) t8[u] = rowp[j + u];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t8[u]);      // beam order
+                    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, t8[u]);
                 }
                 for (; j < m; ++j) acc = __dadd_rn(acc, rowp[j]);
             }
-            __syncwarp();
-        }
+        };
+#pragma unroll 1
+            for (int s = 0; s < nStages; ++s) {
+                load_hits(s);
+                gather(s);
+                park(s);
+                __syncwarp();
+                chain(s);
+                __syncwarp();
+            }
         return acc;
     }
 }
@@ -530,12 +576,10 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
         LGS_CUDA(c, cudaMemsetAsync(b->dCtr.p, 0, 2 * kCounters * sizeof(int), c->stream));
         b->parity = 0;
     }
-    const void* kernel = c->opt.bbVariant == 1 ? (const void*)bb_run_kernel<16, 3> : (const void*)bb_run_kernel<16, 2>;
+    const void* kernel = (const void*)bb_run_kernel<16, 2>;
     if (c->bbBlocks == 0) {
         int perSm = 0;
-        LGS_CUDA(c, c->opt.bbVariant == 1
-                        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bb_run_kernel<16, 3>, kThreads, 0)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bb_run_kernel<16, 2>, kThreads, 0));
+        LGS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, bb_run_kernel<16, 2>, kThreads, 0));
         if (perSm < 1) return lgs_fail(c, LGS_ERR_CUDA, "bb: the persistent kernel does not fit an SM");
         if (c->opt.bbBlocksPerSm > 0) perSm = std::min(perSm, c->opt.bbBlocksPerSm);
         c->bbBlocks = perSm * c->sm_count;

@@ -38,7 +38,6 @@ const OptField kOptFields[] = {
     LGS_OPT("bb_table", "LGS_BB_TABLE", 0, bbTable),
     LGS_OPT("bb_warp_below", "LGS_BB_WARP_BELOW", 0, bbWarpBelow),
     LGS_OPT("bb_resolve_ulps", "LGS_BB_RESOLVE_ULPS", 0, bbResolveUlps),
-    LGS_OPT("bb_variant", "LGS_BB_VARIANT", 0, bbVariant),
     LGS_OPT("bb_blocks_per_sm", "LGS_BB_BLOCKS_PER_SM", 0, bbBlocksPerSm),
     LGS_OPT("bb_cost_g1", nullptr, 1, bbCost[0]),
     LGS_OPT("bb_cost_g4", nullptr, 1, bbCost[1]),

@@ -137,9 +137,8 @@ struct lgs_opts {
     int bbTable = 0;            // "bb_table"        LGS_BB_TABLE: level-synchronous runs through the full index table
     int bbWarpBelow = 8192;     // "bb_warp_below"   LGS_BB_WARP_BELOW: node count below which a level scores a warp per node
     int bbResolveUlps = 8;      // "bb_resolve_ulps" half width (ulps of cos / sin) of the on-device near-edge resolution
-    int bbVariant = 0;          // "bb_variant"      persistent kernel build: 0 = 16 beams in flight x 2 CTAs/SM, 1 = 8 x 4
     int bbBlocksPerSm = 0;      // "bb_blocks_per_sm" persistent B&B kernel residency (0 = occupancy limit)
-    double bbCost[4] = {70.0, 24.0, 15.0, 9.0};   // "bb_cost_g1/g4/g8/g32" per-pass cost (us) of the warp mappings
+    double bbCost[4] = {100.0, 60.0, 36.0, 21.0};   // "bb_cost_g1/g4/g8/g32" per-pass cost (us) of the warp mappings
     int bbHostTiming = 0;       // "bb_host_timing"  LGS_BB_HOSTTIMING
     int integHostTiming = 0;    // "integ_host_timing" LGS_INTEG_HOSTTIMING
     int integTiming = 0;        // "integ_timing"    LGS_INTEG_TIMING

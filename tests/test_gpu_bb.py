@@ -9,16 +9,14 @@ from my_lidar_graph_slam_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["device", "device-b", "exact"])
+@pytest.fixture(autouse=True, params=["device", "exact"])
 def bb_run_path(request, ctx):
-    """Every test runs three times: through the device-only run (ONE persistent kernel: fixed-point
-    cells, near-edge points decided on the device) in both of its builds, and through the
-    level-synchronous exact path (full index table, near-edge points from the host)."""
+    """Every test runs twice: through the device-only run (ONE persistent kernel: fixed-point cells,
+    near-edge points decided on the device) and through the level-synchronous exact path (full index
+    table, near-edge points from the host)."""
     ctx.set_option("bb_sync", 1 if request.param == "exact" else 0)
-    ctx.set_option("bb_variant", 1 if request.param == "device-b" else 0)
     yield request.param
     ctx.set_option("bb_sync", 0)
-    ctx.set_option("bb_variant", 0)
 
 DEF = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0, scan_range_max=20.0,
            score_range_min=0.01, score_range_max=20.0)
