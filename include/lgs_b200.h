@@ -55,6 +55,7 @@ typedef struct lgs_pyramid lgs_pyramid;
 typedef struct lgs_bb_batch lgs_bb_batch;
 
 /* ---- context --------------------------------------------------------------------------- */
+int lgs_device_count(void);                 /* usable CUDA devices (0 without a driver / GPU) */
 int lgs_ctx_create(int device, lgs_ctx** out);
 int lgs_ctx_destroy(lgs_ctx* ctx);
 const char* lgs_ctx_last_error(const lgs_ctx* ctx);
@@ -290,7 +291,10 @@ int lgs_bb_batch_set_record_ids(lgs_bb_batch* b, const long long* ids, int n);
  * device_records[first_slot + q].  The pointer may be memory of ANOTHER GPU mapped into this device
  * (peer access): the records then cross NVLink as plain stores from the kernel itself, with no host
  * staging and no separate copy.  NULL restores the batch's own buffer.  The caller orders its reads
- * after the run (lgs_bb_batch_settle / lgs_ctx_synchronize). */
+ * after the run (lgs_bb_batch_settle / lgs_ctx_synchronize).  One STATUS record follows the batch's
+ * records, at device_records[first_slot + n_pairs] (so the sink needs room for n_pairs + 1): id = -1,
+ * found = 1 if the run stands, -1 if it has to be repeated on the exact path (lgs_bb_batch_settle does
+ * that and rewrites records and status) -- ranks that only see the exchanged buffer learn it from there. */
 int lgs_bb_batch_set_record_sink(lgs_bb_batch* b, lgs_loop_record* device_records, long long first_slot);
 int lgs_bb_batch_records(lgs_bb_batch* b, lgs_loop_record* out);    /* host copy of the records, waits */
 int lgs_bb_batch_settle(lgs_bb_batch* b);    /* wait + validate (+ exact repeat) without copying results out */
@@ -310,6 +314,40 @@ int lgs_bb_batch_force_replay(lgs_bb_batch* b, int on);
 int lgs_bb_match(lgs_ctx* ctx, const lgs_bb_params* params, const lgs_scan_batch* scans,
                  lgs_pyramid* const* pyramids, const double* norm_threshold,
                  lgs_match_result* out);
+
+/* ---- loop detection across the GPUs of one box ---------------------------------------
+ * LoopDetectorBranchBound::Detect's pair loop (mapping/loop_detector_branch_bound.cpp:38-90) carries
+ * nothing from one (node, local map) pair to the next, so the pairs shard by the submap they name.
+ *
+ * lgs_group: ONE process drives all devices -- one lgs_ctx and one persistent host thread per device,
+ * peer access between all members.  Build the grids / pyramids of submap i with lgs_group_ctx(g, i % G);
+ * lgs_group_bb_detect then runs every pair on the device that holds its pyramid (one persistent kernel
+ * per member, all members concurrently) and each member's kernel stores its 32-byte records straight
+ * into the root device's gather buffer over NVLink (peer stores, no host staging); one device -> host
+ * copy returns them.  Results are in pair order and identical to a single-device lgs_bb_batch run. */
+typedef struct lgs_group lgs_group;
+typedef struct lgs_group_bb lgs_group_bb;
+int lgs_group_create(const int* devices, int n, lgs_group** out);
+int lgs_group_destroy(lgs_group* g);
+int lgs_group_size(const lgs_group* g);
+lgs_ctx* lgs_group_ctx(lgs_group* g, int member);
+const char* lgs_group_last_error(const lgs_group* g);
+int lgs_group_bb_create(lgs_group* g, const lgs_bb_params* params, lgs_group_bb** out);
+int lgs_group_bb_destroy(lgs_group_bb* d);
+int lgs_group_bb_detect(lgs_group_bb* d, const lgs_scan_batch* scans, int n_pairs, const int* pair_scan,
+                        lgs_pyramid* const* pyramids, const double* norm_threshold, lgs_match_result* out);
+int lgs_group_bb_records(const lgs_group_bb* d, lgs_loop_record* out);   /* the exchanged records, pair order */
+
+/* lgs_comm: one process PER device (torchrun-style launch).  An all-gather of fixed-size loop records
+ * on the context stream, device to device, through NCCL (libnccl.so.2 is resolved at run time).  Rank 0
+ * creates the 128-byte id and hands it to the others over any host channel.  With send_device == NULL the
+ * all-gather runs IN PLACE: rank r's records are expected in its own slice recv_device[r * count ..), which
+ * is where a batch whose sink is (recv_device, r * count) has written them. */
+typedef struct lgs_comm lgs_comm;
+int lgs_comm_unique_id(void* id128);
+int lgs_comm_create(lgs_ctx* ctx, int world, int rank, const void* id128, lgs_comm** out);
+int lgs_comm_destroy(lgs_comm* c);
+int lgs_comm_all_gather_records(lgs_comm* c, const void* send_device, void* recv_device, int count);
 
 /* ---- exhaustive grid-search matcher ------------------------------------------------------------
  * Replaces ScanMatcherGridSearch::OptimizePose (scan_matcher_grid_search.cpp:45-114) with

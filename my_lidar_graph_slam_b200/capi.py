@@ -82,6 +82,7 @@ SIGNATURES = {
     "lgs_device_download": (C.c_int, [vp, vp, vp, C.c_ulonglong]),
     "lgs_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_double]),
     "lgs_ctx_get_option": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double)]),
+    "lgs_device_count": (C.c_int, []),
     "lgs_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "lgs_ctx_destroy": (C.c_int, [vp]),
     "lgs_ctx_last_error": (C.c_char_p, [vp]),
@@ -128,6 +129,20 @@ SIGNATURES = {
     "lgs_bb_batch_device_records": (vp, [vp]),
     "lgs_bb_batch_phase_times": (C.c_int, [vp, c_dp, c_ip, C.c_int]),
     "lgs_bb_batch_path": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "lgs_group_create": (C.c_int, [c_ip, C.c_int, C.POINTER(vp)]),
+    "lgs_group_destroy": (C.c_int, [vp]),
+    "lgs_group_size": (C.c_int, [vp]),
+    "lgs_group_ctx": (vp, [vp, C.c_int]),
+    "lgs_group_last_error": (C.c_char_p, [vp]),
+    "lgs_group_bb_create": (C.c_int, [vp, C.POINTER(BbParams), C.POINTER(vp)]),
+    "lgs_group_bb_destroy": (C.c_int, [vp]),
+    "lgs_group_bb_detect": (C.c_int, [vp, C.POINTER(ScanBatch), C.c_int, c_ip, C.POINTER(vp), c_dp,
+                                      C.POINTER(MatchResult)]),
+    "lgs_group_bb_records": (C.c_int, [vp, C.POINTER(LoopRecord)]),
+    "lgs_comm_unique_id": (C.c_int, [vp]),
+    "lgs_comm_create": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]),
+    "lgs_comm_destroy": (C.c_int, [vp]),
+    "lgs_comm_all_gather_records": (C.c_int, [vp, vp, vp, C.c_int]),
     "lgs_bb_match": (C.c_int, [vp, C.POINTER(BbParams), C.POINTER(ScanBatch), C.POINTER(vp), c_dp,
                                C.POINTER(MatchResult)]),
 }
@@ -152,6 +167,10 @@ def lib():
 
 def _dptr(a):
     return a.ctypes.data_as(c_dp)
+
+
+def device_count() -> int:
+    return lib().lgs_device_count()
 
 
 class Context:
@@ -205,7 +224,8 @@ class Context:
         if self.h:
             for child in list(self._children):
                 child.close()
-            lib().lgs_ctx_destroy(self.h)
+            if not getattr(self, "_borrowed", False):      # a Group owns its members' contexts
+                lib().lgs_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -501,6 +521,125 @@ class BbBatch:
     def close(self):
         if getattr(self, "h", None):
             lib().lgs_bb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """lgs_group: all devices of one box driven from this process (one context + host thread per device)."""
+
+    def __init__(self, devices):
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self.h = vp()
+        rc = lib().lgs_group_create(arr, len(self.devices), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise LgsError(f"lgs_group_create({self.devices}) failed with {ERRORS.get(rc, rc)}: peer-capable "
+                           "B200-class GPUs are required, there is no fallback")
+        self.ctxs = []
+        for m in range(len(self.devices)):
+            c = Context.__new__(Context)
+            c.h = vp(lib().lgs_group_ctx(self.h, m))
+            c._children = weakref.WeakSet()
+            c._borrowed = True
+            self.ctxs.append(c)
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = lib().lgs_group_last_error(self.h)
+            raise LgsError(f"{ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self.ctxs:
+                for child in list(c._children):
+                    child.close()
+                c.h = None
+            lib().lgs_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupBb:
+    """lgs_group_bb: branch-and-bound loop detection sharded over a Group by the device of each pyramid."""
+
+    def __init__(self, group: Group, node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0,
+                 scan_range_max=20.0, score_range_min=0.01, score_range_max=20.0):
+        self.group = group
+        self.params = BbParams(int(node_height_max), float(range_x), float(range_y), float(range_theta),
+                               float(scan_range_max), float(score_range_min), float(score_range_max))
+        self.h = vp()
+        group.check(lib().lgs_group_bb_create(group.h, C.byref(self.params), C.byref(self.h)))
+        self.n = 0
+
+    def detect(self, scans: "Scans", pair_scan, pyramids, norm_threshold=0.6) -> np.ndarray:
+        n = len(pyramids)
+        pairs = np.ascontiguousarray(pair_scan, dtype=np.int32)
+        assert len(pairs) == n
+        if getattr(self, "_pyr_src", None) is not pyramids:
+            self._pyr = (vp * max(n, 1))(*[p.h for p in pyramids])
+            self._pyr_src = pyramids
+        thr = None
+        if norm_threshold is not None:
+            self._thr = np.ascontiguousarray(np.broadcast_to(np.asarray(norm_threshold, dtype=np.float64), (n,)))
+            thr = _dptr(self._thr)
+        out = np.zeros(max(n, 1), dtype=MATCH_DTYPE)
+        self.group.check(lib().lgs_group_bb_detect(self.h, C.byref(scans.c), n, pairs.ctypes.data_as(c_ip), self._pyr,
+                                                   thr, out.ctypes.data_as(C.POINTER(MatchResult))))
+        self.n = n
+        return out[:n]
+
+    def records(self) -> np.ndarray:
+        out = np.zeros(max(self.n, 1), dtype=RECORD_DTYPE)
+        self.group.check(lib().lgs_group_bb_records(self.h, out.ctypes.data_as(C.POINTER(LoopRecord))))
+        return out[:self.n]
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.group, "h", None):
+            lib().lgs_group_bb_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """lgs_comm: NCCL all-gather of loop records between one-process-per-GPU ranks."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        if lib().lgs_comm_unique_id(buf) != 0:
+            raise LgsError("lgs_comm_unique_id failed: libnccl.so.2 not loadable")
+        return buf.raw
+
+    def __init__(self, ctx: Context, world: int, rank: int, uid: bytes):
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        self.h = vp()
+        buf = C.create_string_buffer(uid, 128)
+        ctx.check(lib().lgs_comm_create(ctx.h, self.world, self.rank, buf, C.byref(self.h)))
+
+    def all_gather_records(self, recv_device: int, count: int, send_device: int = 0):
+        self.ctx.check(lib().lgs_comm_all_gather_records(self.h, vp(send_device) if send_device else None,
+                                                         vp(recv_device), int(count)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lgs_comm_destroy(self.h)
             self.h = None
 
     def __del__(self):

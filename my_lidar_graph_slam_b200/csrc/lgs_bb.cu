@@ -560,11 +560,13 @@ void bb_fill_records(const lgs_bb_batch* b, lgs_loop_record* out) {
 // device-only run's finalize phase writes them (the sink, or the batch's own record buffer).
 int bb_deliver_records(lgs_bb_batch* b) {
     lgs_ctx* c = b->ctx;
-    LGS_CUDA(c, b->dRec.reserve(b->nq));
-    LGS_CUDA(c, b->hRec.reserve(b->nq));
+    LGS_CUDA(c, b->dRec.reserve(b->nq + 1));
+    LGS_CUDA(c, b->hRec.reserve(b->nq + 1));
     bb_fill_records(b, b->hRec.p);
+    lgs_loop_record& st = b->hRec.p[b->nq];          // status record: valid
+    st.found = 1; st.ix = 0; st.iy = 0; st.it = 0; st.score = 0.0; st.id = -1;
     lgs_loop_record* dst = b->sink ? b->sink + b->sinkFirst : b->dRec.p;
-    LGS_CUDA(c, cudaMemcpyAsync(dst, b->hRec.p, b->nq * sizeof(lgs_loop_record), cudaMemcpyDefault, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(dst, b->hRec.p, (b->nq + 1) * sizeof(lgs_loop_record), cudaMemcpyDefault, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
     return LGS_OK;
 }

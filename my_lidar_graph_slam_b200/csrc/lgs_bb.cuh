@@ -103,6 +103,7 @@ struct RunArgs {
     lgs_loop_record* rec;           // optional record sink (may be peer memory of another GPU), slot = recFirst + q
     const long long* recIds;        // optional ids copied into the records (NULL: the query index)
     long long recFirst;
+    int recStatus;                  // also write the run's status record at slot recFirst + nq
     int nq, nu, H;
     int totalRoots, rootTiles, rootG;
     unsigned edgeUnits;             // guard band in 2^-20 cells

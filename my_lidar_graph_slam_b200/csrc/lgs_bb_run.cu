@@ -548,7 +548,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) bb_run_kernel(const __gr
             a.rec[a.recFirst + q] = rc;
         }
     }
-    if (gt == 0) { a.ctr[kCtrDone] = 1; a.phaseNs[phase] = global_ns(); }
+    if (gt == 0) {
+        if (a.recStatus) {
+            // Status record behind the batch's records: consumers of an exchanged buffer (other ranks) learn
+            // from it whether this run has to be repeated on the exact path before its records count.
+            const int overflow = __ldcg(a.ctr + kCtrOverflow), unresolved = __ldcg(a.ctr + kCtrUnresolved);
+            lgs_loop_record st;
+            st.found = (overflow == 0 && unresolved == 0) ? 1 : -1;
+            st.ix = overflow; st.iy = unresolved; st.it = 0; st.score = 0.0; st.id = -1;
+            a.rec[a.recFirst + a.nq] = st;
+        }
+        a.ctr[kCtrDone] = 1;
+        a.phaseNs[phase] = global_ns();
+    }
 }
 
 }  // namespace
@@ -569,8 +581,8 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
     LGS_CUDA(c, b->dScores[H].reserve(b->totalRoots));
     LGS_CUDA(c, b->dHitsFix.reserve(std::max<long long>(b->nHits, 1)));
     LGS_CUDA(c, b->dHitsFixT.reserve(std::max<long long>(b->nHitsT, 1)));
-    LGS_CUDA(c, b->dRec.reserve(n));
-    LGS_CUDA(c, b->hRec.reserve(n));
+    LGS_CUDA(c, b->dRec.reserve(n + 1));
+    LGS_CUDA(c, b->hRec.reserve(n + 1));
     if (b->dCtr.cap == 0) {
         LGS_CUDA(c, b->dCtr.reserve(2 * kCounters));
         LGS_CUDA(c, cudaMemsetAsync(b->dCtr.p, 0, 2 * kCounters * sizeof(int), c->stream));
@@ -610,6 +622,7 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
     a.res = b->dRes.p;
     a.rec = b->sink ? b->sink : b->dRec.p;
     a.recFirst = b->sink ? b->sinkFirst : 0;
+    a.recStatus = 1;
     a.nq = n; a.nu = (int)b->us.size(); a.H = H;
     a.totalRoots = b->totalRoots;
     a.costUs[0] = (float)c->opt.bbCost[0]; a.costUs[1] = (float)c->opt.bbCost[1];

@@ -103,6 +103,12 @@ int lgs_ctx_get_option(const lgs_ctx* c, const char* name, double* value) {
 
 const char* lgs_version(void) { return "lgs_b200 0.1 (sm_100a)"; }
 
+int lgs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int lgs_ctx_create(int device, lgs_ctx** out) {
     if (!out) return LGS_ERR_INVALID;
     *out = nullptr;

@@ -2,17 +2,23 @@
 
 (scan, submap) branch-and-bound queries are independent, so submap i (with its device-resident
 pyramid) lives on rank i mod world and every rank searches only its own pairs.  The one exchange
-step is an all-gather of the fixed-size result records (found, ix, iy, itheta, score), after
-which every rank holds the full result list in global submap order and can pick the best
-candidate.  torch.distributed is plumbing only: NCCL over NVLink on the GPU box, gloo in the CPU
-tests.
+step is an all-gather of the fixed-size result records (found, ix, iy, itheta, score, id), after
+which every rank holds the full result list in global order and can pick the best candidate.
+
+Two drivers, both inside the C ABI (csrc/lgs_group.cu):
+  * one process, all devices: capi.Group / capi.GroupBb (peer stores into the root's gather buffer);
+  * one process per device (torchrun): RecordExchange below -- the batch's finalize phase writes the
+    rank's records straight into its slice of the receive buffer and lgs_comm_all_gather_records runs
+    the NCCL all-gather in place on the context stream; nothing touches the host until the gathered
+    buffer is downloaded once.
+torch.distributed is plumbing only (rendezvous of the 128-byte NCCL id; gloo in the CPU tests).
 """
 from __future__ import annotations
 
 import numpy as np
 
 RECORD = np.dtype([("found", np.int32), ("ix", np.int32), ("iy", np.int32), ("it", np.int32),
-                   ("score", np.float64), ("submap", np.int64)])   # 32 bytes
+                   ("score", np.float64), ("submap", np.int64)])   # 32 bytes = lgs_loop_record
 
 
 def owned(n_items: int, rank: int, world: int) -> np.ndarray:
@@ -20,15 +26,25 @@ def owned(n_items: int, rank: int, world: int) -> np.ndarray:
     return np.arange(rank, n_items, world, dtype=np.int64)
 
 
-def pack(results, global_ids) -> np.ndarray:
-    rec = np.zeros(len(global_ids), dtype=RECORD)
-    for k, (r, g) in enumerate(zip(results, global_ids)):
-        rec[k] = (r.found, r.ix, r.iy, r.it, r.score, g)
-    return rec
+def slots_per_rank(n_items: int, world: int) -> int:
+    """Record slots every rank contributes to the all-gather: its (padded) share + one status record."""
+    return (n_items + world - 1) // world + 1
+
+
+def assemble(gathered: np.ndarray, counts, per: int, n_items: int):
+    """Gathered buffer (world x per records, rank r's `counts[r]` records first in its slice, then its
+    status record) -> (records in global order, all runs valid?)."""
+    out = np.zeros(n_items, dtype=RECORD)
+    ok = True
+    for r, cnt in enumerate(counts):
+        sl = gathered[r * per:r * per + cnt]
+        out[sl["submap"]] = sl
+        ok &= int(gathered[r * per + cnt]["found"]) == 1
+    return out, bool(ok)
 
 
 def pack_array(results: np.ndarray, global_ids) -> np.ndarray:
-    """pack() for a structured result array (capi.BbBatch.results_array), vectorised."""
+    """Records from a structured result array (host-side path of the gloo tests)."""
     rec = np.zeros(len(global_ids), dtype=RECORD)
     for f in ("found", "ix", "iy", "it", "score"):
         rec[f] = results[f]
@@ -36,55 +52,88 @@ def pack_array(results: np.ndarray, global_ids) -> np.ndarray:
     return rec
 
 
-def all_gather_records(local: np.ndarray, n_items: int, rank: int, world: int, device=None):
-    """All-gather per-rank record arrays -> one array of n_items records in global order."""
+def all_gather_host(local: np.ndarray, counts, n_items: int, rank: int, world: int):
+    """The exchange of RecordExchange with host tensors over torch.distributed (gloo): used by the CPU
+    tests of the partitioning / assembly logic, never by a GPU run.  counts[r] = records of rank r
+    (every rank can compute all of them: ownership is a pure function of the indices)."""
+    per = max(counts) + 1
+    assert len(local) == counts[rank]
     if world == 1:
         out = np.zeros(n_items, dtype=RECORD)
         out[local["submap"]] = local
         return out
     import torch
     import torch.distributed as dist
-    per = (n_items + world - 1) // world          # ranks own per or per-1 items: pad to per
     buf = np.zeros(per, dtype=RECORD)
-    buf["submap"] = -1
     buf[:len(local)] = local
+    buf[len(local)]["found"] = 1
+    buf[len(local)]["submap"] = -1
     send = torch.from_numpy(buf.view(np.uint8).copy())
-    if device is not None:
-        send = send.to(device)
-    recv = torch.empty(world * send.numel(), dtype=torch.uint8, device=send.device)
+    recv = torch.empty(world * send.numel(), dtype=torch.uint8)
     dist.all_gather_into_tensor(recv, send)
-    allrec = recv.cpu().numpy().view(RECORD)
-    allrec = allrec[allrec["submap"] >= 0]
-    out = np.zeros(n_items, dtype=RECORD)
-    out[allrec["submap"]] = allrec
+    out, ok = assemble(recv.numpy().view(RECORD), counts, per, n_items)
+    assert ok
     return out
 
 
-def all_gather_variable(local: np.ndarray, n_items: int, world: int, device=None):
-    """All-gather record arrays whose per-rank counts are arbitrary (queries follow the band their
-    sensor cell falls in): one all-reduce(MAX) of the counts, then one padded all-gather."""
+def make_comm(ctx, rank: int, world: int):
+    """lgs_comm over the ranks of an initialised torch.distributed job (the 128-byte NCCL id travels
+    through broadcast_object_list; the data path never touches torch)."""
+    from . import capi
     if world == 1:
-        out = np.zeros(n_items, dtype=RECORD)
-        out[local["submap"]] = local
-        return out
-    import torch
+        return None
     import torch.distributed as dist
-    cnt = torch.tensor([len(local)], dtype=torch.int64, device=device if device is not None else "cpu")
-    dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
-    per = max(int(cnt.item()), 1)
-    buf = np.zeros(per, dtype=RECORD)
-    buf["submap"] = -1
-    buf[:len(local)] = local
-    send = torch.from_numpy(buf.view(np.uint8).copy())
-    if device is not None:
-        send = send.to(device)
-    recv = torch.empty(world * send.numel(), dtype=torch.uint8, device=send.device)
-    dist.all_gather_into_tensor(recv, send)
-    allrec = recv.cpu().numpy().view(RECORD)
-    allrec = allrec[allrec["submap"] >= 0]
-    out = np.zeros(n_items, dtype=RECORD)
-    out[allrec["submap"]] = allrec
-    return out
+    box = [capi.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return capi.Comm(ctx, world, rank, box[0])
+
+
+class RecordExchange:
+    """Device-resident exchange of loop records between one-process-per-GPU ranks."""
+
+    def __init__(self, ctx, comm, n_items: int, rank: int, world: int, counts=None):
+        from . import capi
+        self.ctx, self.comm, self.n_items, self.rank, self.world = ctx, comm, int(n_items), rank, world
+        self.counts = [len(owned(n_items, r, world)) for r in range(world)] if counts is None else list(counts)
+        self.per = max(self.counts) + 1
+        self.buf = capi.device_alloc(ctx, world * self.per * RECORD.itemsize)
+        self._ids_of = None
+
+    def attach(self, batch, ids):
+        """Point the batch's finalize phase at this rank's slice (records + status record)."""
+        if self._ids_of is not batch:
+            batch.set_record_ids(ids)
+            batch.set_record_sink(self.buf, self.rank * self.per)
+            self._ids_of = batch
+
+    def gather(self) -> np.ndarray:
+        """All-gather on the context stream (in place), one download, assembly in global order."""
+        from . import capi
+        if self.comm is not None:
+            self.comm.all_gather_records(self.buf, self.per)
+        raw = capi.download_records(self.ctx, self.buf, self.world * self.per)
+        return assemble(raw, self.counts, self.per, self.n_items)
+
+    def step(self, batch, scans, pair_scan, pyramids, ids, thr):
+        """One sharded loop-detection step: upload, ONE kernel launch, in-place all-gather, download.
+        If any rank's run has to be repeated exactly (status record), every rank sees it in the
+        gathered buffer, the affected rank settles (exact path, records rewritten) and the gather is
+        repeated -- the decision is collective because it is taken from exchanged data."""
+        self.attach(batch, ids)
+        batch.upload_pairs(scans, pair_scan, pyramids, thr)
+        batch.run()
+        out, ok = self.gather()
+        if not ok:
+            batch.settle()
+            out, ok = self.gather()
+            assert ok
+        return out
+
+    def close(self):
+        from . import capi
+        if self.buf:
+            capi.device_free(self.ctx, self.buf)
+            self.buf = 0
 
 
 def rank_grid(world: int, n_submaps: int, submaps_per_group: int = 250, want_pm: int | None = None):

@@ -299,16 +299,15 @@ def test_records_and_device_sink(ctx, submap):
     assert rec["submap"].tolist() == ids.tolist()
     for o, r in zip(outs, rec):
         assert (o.found, o.ix, o.iy, o.it, o.score) == (int(r["found"]), int(r["ix"]), int(r["iy"]), int(r["it"]), float(r["score"]))
-    # sink: slots 3.. of a larger device buffer (owned by another batch object that has run 8 queries)
-    other = capi.BbBatch(ctx, **DEF)
-    qs8 = _queries(submap, 8, seed=9)
-    other.upload(capi.Scans([submap["angles"]] * 8, [s for s, _ in qs8], [p for _, p in qs8],
-                            range_min=0.02, range_max=30.0), [submap["pyr"]] * 8, 0.6)
-    other.run()
-    other.settle()
-    batch.set_record_sink(other.device_records(), 3)
+    # sink: slots 3.. of a separate device buffer, followed by the run's status record
+    buf = capi.device_alloc(ctx, 12 * 32)
+    batch.set_record_sink(buf, 3)
     batch.run()
     batch.settle()
-    got = capi.download_records(ctx, other.device_records(), 8)
-    assert got[3:].tobytes() == rec.tobytes()
+    got = capi.download_records(ctx, buf, 12)
+    assert got[3:8].tobytes() == rec.tobytes()
+    assert int(got[8]["submap"]) == -1 and int(got[8]["found"]) == 1          # status: the run stands
+    assert not got[:3].tobytes().strip(b"\0") and not got[9:].tobytes().strip(b"\0")
     batch.set_record_sink(0)
+    batch.close()
+    capi.device_free(ctx, buf)

@@ -21,12 +21,11 @@ def _worker(rank, world, port, n_items, q):
     from my_lidar_graph_slam_b200 import sharding
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     ids = sharding.owned(n_items, rank, world)
-
-    class R:   # stand-in for lgs_match_result
-        def __init__(self, g):
-            self.found, self.ix, self.iy, self.it, self.score = int(g % 3 == 0), g, -g, 2 * g, 100.0 + (g * 7) % 11
-    local = sharding.pack([R(int(g)) for g in ids], ids)
-    full = sharding.all_gather_records(local, n_items, rank, world)
+    local = np.zeros(len(ids), dtype=sharding.RECORD)     # what the finalize phase writes into the rank's slice
+    local["found"], local["ix"], local["iy"], local["it"] = ids % 3 == 0, ids, -ids, 2 * ids
+    local["score"], local["submap"] = 100.0 + (ids * 7) % 11, ids
+    counts = [len(sharding.owned(n_items, r, world)) for r in range(world)]
+    full = sharding.all_gather_host(local, counts, n_items, rank, world)
     q.put((rank, full.tobytes(), sharding.best_candidate(full)))
     dist.destroy_process_group()
 
@@ -38,6 +37,25 @@ def test_round_robin_ownership_partitions_everything():
             parts = [sharding.owned(n, r, world) for r in range(world)]
             assert sorted(np.concatenate(parts).tolist()) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_assemble_orders_records_and_reports_invalid_runs():
+    from my_lidar_graph_slam_b200 import sharding
+    n, world = 7, 3
+    counts = [len(sharding.owned(n, r, world)) for r in range(world)]
+    per = sharding.slots_per_rank(n, world)
+    assert per == max(counts) + 1
+    buf = np.zeros(world * per, dtype=sharding.RECORD)
+    for r in range(world):
+        ids = sharding.owned(n, r, world)
+        buf["submap"][r * per:r * per + len(ids)] = ids
+        buf["ix"][r * per:r * per + len(ids)] = 10 * ids
+        buf["found"][r * per + len(ids)] = 1
+        buf["submap"][r * per + len(ids)] = -1
+    out, ok = sharding.assemble(buf, counts, per, n)
+    assert ok and out["submap"].tolist() == list(range(n)) and out["ix"].tolist() == [10 * k for k in range(n)]
+    buf["found"][1 * per + counts[1]] = -1              # rank 1's run has to be repeated exactly
+    assert sharding.assemble(buf, counts, per, n)[1] is False
 
 
 def test_all_gather_records_world2_gloo():
@@ -86,13 +104,13 @@ def _band_worker(rank, world, port, n_queries, q):
     from my_lidar_graph_slam_b200 import largemap, sharding
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     rows = (np.arange(n_queries) * 37) % 100                 # sensor rows of the queries in a 100-row map
-    mine = np.flatnonzero(largemap.owner_of_rows(rows, 100, world) == rank)
-
-    class R:
-        def __init__(self, g):
-            self.found, self.ix, self.iy, self.it, self.score = 1, int(rows[g]), g, rank, float(g)
-    local = sharding.pack([R(int(g)) for g in mine], mine)
-    full = sharding.all_gather_variable(local, n_queries, world)
+    owner = largemap.owner_of_rows(rows, 100, world)
+    mine = np.flatnonzero(owner == rank)
+    local = np.zeros(len(mine), dtype=sharding.RECORD)
+    local["found"], local["ix"], local["iy"], local["it"], local["score"] = 1, rows[mine], mine, rank, mine
+    local["submap"] = mine
+    counts = [int((owner == r).sum()) for r in range(world)]
+    full = sharding.all_gather_host(local, counts, n_queries, rank, world)
     q.put((rank, full.tobytes()))
     dist.destroy_process_group()
 
@@ -147,7 +165,11 @@ def _grid_worker(rank, world, port, n_scans, n_submaps, q):
     ids = np.concatenate([k * n_submaps + submaps for k in scans]) if len(scans) else np.zeros(0, dtype=np.int64)
     local = np.zeros(len(ids), dtype=sharding.RECORD)
     local["submap"], local["ix"], local["found"], local["score"] = ids, ids % 97, 1, ids * 0.5
-    full = sharding.all_gather_variable(local, n_scans * n_submaps, world)
+    counts = []
+    for r in range(world):
+        sc, sm = sharding.grid_owned(n_scans, n_submaps, r, ps, pm)
+        counts.append(len(sc) * len(sm))
+    full = sharding.all_gather_host(local, counts, n_scans * n_submaps, rank, world)
     q.put((rank, full.tobytes()))
     dist.destroy_process_group()
 
