@@ -7,13 +7,16 @@
  * pass the launcher's own CreateCostFunction (see INTEGRATION.md for the five-line patch).
  *
  * New settings keys (all optional): "Device" (int, default 0) and "DeviceCost" (bool, default true)
- * in the matcher / detector group.
+ * in the matcher / detector group; in the branch-and-bound loop detector group also
+ * "Devices": [0, 1, ..., 7] -- the GPUs of the box the local maps are spread over (local map i on
+ * device i mod G).  "Devices" wins over "Device".
  */
 #ifndef LGS_ADAPTERS_CREATE_CUDA_BACKENDS_HPP
 #define LGS_ADAPTERS_CREATE_CUDA_BACKENDS_HPP
 
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "lgs_adapters/grid_map_builder_cuda.hpp"
 #include "lgs_adapters/grid_search_cuda.hpp"
@@ -42,6 +45,20 @@ lgs_cost_params ReadCostGreedyEndpointParams(const Ptree& jsonSettings, const st
     p.scaling_factor = config.get("StandardDeviation", 0.05);      /* constructor's 6th argument */
     p.standard_deviation = config.get("ScalingFactor", 1.0);       /* constructor's 7th argument */
     return p;
+}
+
+/* "Devices": [0, 1, ...] of a detector group, or { "Device" } when the key is absent.  A JSON array is
+ * a child whose elements have empty keys (boost::property_tree) */
+template <typename Ptree>
+std::vector<int> ReadDevices(const Ptree& config)
+{
+    std::vector<int> devices;
+    if (auto list = config.get_child_optional("Devices"))
+        for (const auto& item : *list)
+            devices.push_back(item.second.template get_value<int>());
+    if (devices.empty())
+        devices.push_back(config.get("Device", 0));
+    return devices;
 }
 
 /* "ScanMatcherType": "RealTimeCorrelativeCuda" -- same keys and defaults as
@@ -78,7 +95,7 @@ std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorBranchBoundCuda(
 {
     const Ptree& config = jsonSettings.get_child(configGroup);
     const double scoreThreshold = config.template get<double>("ScoreThreshold");
-    const int device = config.get("Device", 0);
+    const std::vector<int> devices = ReadDevices(config);
     const std::string matcherGroup = config.template get<std::string>("ScanMatcherConfigGroup");
 
     const Ptree& matcher = jsonSettings.get_child(matcherGroup);
@@ -98,7 +115,7 @@ std::shared_ptr<Mapping::LoopDetector> CreateLoopDetectorBranchBoundCuda(
     auto pCostFunc = createCostFunction(jsonSettings, costType, costGroup);
     auto pDetector = std::make_shared<Mapping::LoopDetectorBranchBoundCuda>(
         usableRangeMin, usableRangeMax, pCostFunc, nodeHeightMax, rangeX, rangeY, rangeTheta,
-        scanRangeMax, scoreThreshold, device);
+        scanRangeMax, scoreThreshold, devices);
     if (costType == "GreedyEndpoint" && config.get("DeviceCost", true))
         pDetector->UseDeviceCost(ReadCostGreedyEndpointParams(jsonSettings, costGroup));
     return pDetector;

@@ -2,6 +2,7 @@
 
 #include "lgs_adapters/loop_detector_branch_bound_cuda.hpp"
 
+#include <algorithm>
 #include <cassert>
 
 #include "lgs_adapters/grid_map_flatten.hpp"
@@ -19,6 +20,14 @@ void Check(lgs_ctx* ctx, int rc, const char* what)
         std::abort();
     }
 }
+void CheckGroup(lgs_group* group, int rc, const char* what)
+{
+    if (rc != LGS_OK) {
+        std::cerr << "lgs_b200: " << what << " failed (" << rc << "): "
+                  << (group ? lgs_group_last_error(group) : "no device group") << std::endl;
+        std::abort();
+    }
+}
 } /* namespace */
 
 LoopDetectorBranchBoundCuda::LoopDetectorBranchBoundCuda(
@@ -26,51 +35,76 @@ LoopDetectorBranchBoundCuda::LoopDetectorBranchBoundCuda(
     const CostFuncPtr& costFunc, const int nodeHeightMax, const double rangeX,
     const double rangeY, const double rangeTheta, const double scanRangeMax,
     const double scoreThreshold, const int device) :
+    LoopDetectorBranchBoundCuda(scoreUsableRangeMin, scoreUsableRangeMax, costFunc, nodeHeightMax,
+                                rangeX, rangeY, rangeTheta, scanRangeMax, scoreThreshold,
+                                std::vector<int> { device })
+{
+}
+
+LoopDetectorBranchBoundCuda::LoopDetectorBranchBoundCuda(
+    const double scoreUsableRangeMin, const double scoreUsableRangeMax,
+    const CostFuncPtr& costFunc, const int nodeHeightMax, const double rangeX,
+    const double rangeY, const double rangeTheta, const double scanRangeMax,
+    const double scoreThreshold, const std::vector<int>& devices) :
     mCostFunc(costFunc),
     mParams { nodeHeightMax, rangeX, rangeY, rangeTheta, scanRangeMax,
               scoreUsableRangeMin, scoreUsableRangeMax },
-    mScoreThreshold(scoreThreshold), mCtx(nullptr), mBatch(nullptr),
+    mScoreThreshold(scoreThreshold), mGroup(nullptr), mDetector(nullptr),
     mDeviceCost(false), mCostParams()
 {
     assert(scoreThreshold > 0.0);      /* loop_detector_branch_bound.cpp:20-21 */
     assert(scoreThreshold <= 1.0);
-    Check(nullptr, lgs_ctx_create(device, &this->mCtx), "lgs_ctx_create (a B200 is required)");
-    Check(this->mCtx, lgs_bb_batch_create(this->mCtx, &this->mParams, &this->mBatch),
-          "lgs_bb_batch_create");
+    assert(!devices.empty());
+    CheckGroup(nullptr, lgs_group_create(devices.data(), static_cast<int>(devices.size()),
+               &this->mGroup), "lgs_group_create (peer-capable B200s are required)");
+    CheckGroup(this->mGroup, lgs_group_bb_create(this->mGroup, &this->mParams, &this->mDetector),
+               "lgs_group_bb_create");
 }
 
 LoopDetectorBranchBoundCuda::~LoopDetectorBranchBoundCuda()
 {
-    lgs_bb_batch_destroy(this->mBatch);
+    lgs_group_bb_destroy(this->mDetector);
     for (auto& kv : this->mDeviceMaps) {
         lgs_pyramid_destroy(kv.second.mPyramid);
         lgs_grid_destroy(kv.second.mGrid);
     }
-    lgs_ctx_destroy(this->mCtx);
+    lgs_group_destroy(this->mGroup);
 }
 
 /* Device pyramid of a local map: built on first use, rebuilt when the builder has reset
- * mPrecomputed after a loop closure (loop_detector_branch_bound.cpp:51-60) */
-lgs_pyramid* LoopDetectorBranchBoundCuda::PyramidFor(LocalMapInfo& localMapInfo)
+ * mPrecomputed after a loop closure (loop_detector_branch_bound.cpp:51-60).  Local map i lives on
+ * device i mod G.  Every LoopDetectionQuery carries its own COPY of LocalMapInfo, so a second
+ * query of the same Detect() call that names the same local map still says mPrecomputed == false:
+ * `builtThisCall` keeps it from destroying the pyramid the batch under construction points to. */
+lgs_pyramid* LoopDetectorBranchBoundCuda::PyramidFor(
+    LocalMapInfo& localMapInfo, std::vector<int>& builtThisCall)
 {
     auto it = this->mDeviceMaps.find(localMapInfo.mIdx);
-    if (it != this->mDeviceMaps.end() && localMapInfo.mPrecomputed)
+    const bool fresh = std::find(builtThisCall.begin(), builtThisCall.end(), localMapInfo.mIdx) !=
+                       builtThisCall.end();
+    if (it != this->mDeviceMaps.end() && (localMapInfo.mPrecomputed || fresh)) {
+        localMapInfo.mPrecomputed = true;
         return it->second.mPyramid;
+    }
     if (it != this->mDeviceMaps.end()) {
         lgs_pyramid_destroy(it->second.mPyramid);
         lgs_grid_destroy(it->second.mGrid);
         this->mDeviceMaps.erase(it);
     }
     const GridMapType& map = localMapInfo.mMap;
-    DeviceMap dev { nullptr, nullptr };
-    Check(this->mCtx, lgs_grid_create(this->mCtx, map.NumOfGridCellsX(),
+    const int numOfMembers = lgs_group_size(this->mGroup);
+    const int member = ((localMapInfo.mIdx % numOfMembers) + numOfMembers) % numOfMembers;
+    lgs_ctx* ctx = lgs_group_ctx(this->mGroup, member);
+    DeviceMap dev { nullptr, nullptr, member };
+    Check(ctx, lgs_grid_create(ctx, map.NumOfGridCellsX(),
           map.NumOfGridCellsY(), map.MinPos().mX, map.MinPos().mY, map.Resolution(), 1,
           &dev.mGrid), "lgs_grid_create");
     LgsB200::FlattenGridMap(map, this->mDense);
-    Check(this->mCtx, lgs_grid_upload(dev.mGrid, this->mDense.data()), "lgs_grid_upload");
-    Check(this->mCtx, lgs_pyramid_create(this->mCtx, dev.mGrid, this->mParams.node_height_max,
+    Check(ctx, lgs_grid_upload(dev.mGrid, this->mDense.data()), "lgs_grid_upload");
+    Check(ctx, lgs_pyramid_create(ctx, dev.mGrid, this->mParams.node_height_max,
           &dev.mPyramid), "lgs_pyramid_create");
     this->mDeviceMaps.emplace(localMapInfo.mIdx, dev);
+    builtThisCall.push_back(localMapInfo.mIdx);
     /* The host-side pyramids stay empty; the flag alone is what the SLAM parent copies back
      * (lidar_graph_slam.cpp:285-303) */
     localMapInfo.mPrecomputed = true;
@@ -91,13 +125,14 @@ void LoopDetectorBranchBoundCuda::Detect(
     std::vector<int> beamBegin { 0 };
     std::vector<double> angles, ranges, poses, rangeMin, rangeMax, thresholds;
     std::vector<lgs_pyramid*> pyramids;
+    std::vector<int> builtThisCall;
 
     for (auto& query : loopDetectionQueries) {
         auto& localMapInfo = query.mLocalMapInfo;
         assert(query.mLocalMapNode.Index() >= localMapInfo.mPoseGraphNodeIdxMin &&
                query.mLocalMapNode.Index() <= localMapInfo.mPoseGraphNodeIdxMax);
         assert(localMapInfo.mFinished);
-        lgs_pyramid* pyramid = this->PyramidFor(localMapInfo);
+        lgs_pyramid* pyramid = this->PyramidFor(localMapInfo, builtThisCall);
 
         for (const auto& node : query.mPoseGraphNodes) {
             const auto& scanData = node.ScanData();
@@ -119,11 +154,10 @@ void LoopDetectorBranchBoundCuda::Detect(
     if (numOfPairs > 0) {
         const lgs_scan_batch scans { numOfPairs, beamBegin.data(), angles.data(), ranges.data(),
                                      poses.data(), rangeMin.data(), rangeMax.data() };
-        Check(this->mCtx, lgs_bb_batch_upload(this->mBatch, &scans, pyramids.data(),
-              thresholds.data()), "lgs_bb_batch_upload");
-        Check(this->mCtx, lgs_bb_batch_run(this->mBatch), "lgs_bb_batch_run");
-        Check(this->mCtx, lgs_bb_batch_results(this->mBatch, this->mLast.data()),
-              "lgs_bb_batch_results");
+        /* Every pair on the device of its local map, all devices at once; one kernel launch per
+         * device, records exchanged on the devices (lgs_group_bb_detect) */
+        CheckGroup(this->mGroup, lgs_group_bb_detect(this->mDetector, &scans, numOfPairs, nullptr,
+                   pyramids.data(), thresholds.data(), this->mLast.data()), "lgs_group_bb_detect");
     }
 
     /* Host tail and loop closing edges in the reference's order
@@ -169,8 +203,9 @@ void LoopDetectorBranchBoundCuda::Detect(
             const lgs_scan_batch tailScans { numOfFound, tailBegin.data(), tailAngles.data(),
                                              tailRanges.data(), best.data(), tailMin.data(), tailMax.data() };
             covariances.resize(9 * foundNodes.size());
-            Check(this->mCtx, lgs_cost_tail(this->mCtx,
-                  this->mDeviceMaps.at(query.mLocalMapInfo.mIdx).mGrid, &this->mCostParams,
+            const DeviceMap& deviceMap = this->mDeviceMaps.at(query.mLocalMapInfo.mIdx);
+            lgs_ctx* ctx = lgs_group_ctx(this->mGroup, deviceMap.mMember);
+            Check(ctx, lgs_cost_tail(ctx, deviceMap.mGrid, &this->mCostParams,
                   &tailScans, best.data(), nullptr, covariances.data(), nullptr), "lgs_cost_tail");
         }
 

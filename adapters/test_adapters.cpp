@@ -111,6 +111,28 @@ struct FlatTree {
         return it == kv.end() ? def : conv<T>(it->second);
     }
     std::string get(const std::string& key, const char* def) const { return get<std::string>(key, def); }
+    /* JSON arrays ("Devices": [0, 1]) as boost::property_tree shows them: a child whose elements have
+     * empty keys; here the flat table holds them as one comma-separated string */
+    struct Item { int v; template <typename T> T get_value() const { return static_cast<T>(v); } };
+    struct ItemList {
+        std::vector<std::pair<std::string, Item>> items;
+        bool present = false;
+        explicit operator bool() const { return present; }
+        const std::vector<std::pair<std::string, Item>>& operator*() const { return items; }
+    };
+    ItemList get_child_optional(const std::string& key) const {
+        ItemList list;
+        const auto it = kv.find(key);
+        if (it == kv.end()) return list;
+        list.present = true;
+        std::string tok;
+        for (char ch : it->second + ",") {
+            if (ch != ',') { tok += ch; continue; }
+            if (!tok.empty()) list.items.push_back({std::string(), Item{std::stoi(tok)}});
+            tok.clear();
+        }
+        return list;
+    }
 };
 
 /* Geometry, patch allocation and every cell value, as bit patterns */
@@ -425,6 +447,60 @@ int main() {
             if (r1.empty()) { std::printf("expected at least one detected loop\n"); ++failures; }
         }
     }
+    /* ---- loop detector over every GPU of the box: local map i on device i mod G, one
+     * process, one host thread per device, records exchanged on the devices.  Also a Detect() call in
+     * which two queries name the SAME local map (each query owns a copy of LocalMapInfo whose
+     * mPrecomputed flag is still false: the pyramid built for the first must survive the second). ---- */
+    {
+        const int numOfDevices = lgs_device_count();
+        std::vector<int> devices;
+        for (int k = 0; k < numOfDevices && k < 8; ++k) devices.push_back(k);
+        auto score = std::make_shared<ScorePixelAccurate>(0.01, 20.0);
+        auto bb = std::make_shared<ScanMatcherBranchBound>(score, cost, 6, 2.0, 2.0, 1.0, 20.0);
+        LoopDetectorBranchBound ref(bb, 0.6);
+        LoopDetectorBranchBoundCuda gpu(0.01, 20.0, cost, 6, 2.0, 2.0, 1.0, 20.0, 0.6, devices);
+        gpu.UseDeviceCost(costParams);
+        std::uniform_real_distribution<double> dxy(-0.5, 0.5), dth(-0.25, 0.25);
+        LoopDetectionQueryVector q1, q2;
+        const size_t numOfMaps = std::min<size_t>(builder.LocalMaps().size() - 1, 4);
+        for (size_t k = 0; k < numOfMaps + 1; ++k) {
+            const size_t m = k < numOfMaps ? k : 0;          /* the last query names local map 0 again */
+            LocalMapInfo info = builder.LocalMapAt(static_cast<int>(m));
+            info.mFinished = true;
+            std::vector<PoseGraph::Node> n1, n2;
+            for (int j = 0; j < 2; ++j) {
+                const int idx = info.mPoseGraphNodeIdxMin + 1 + 4 * j + static_cast<int>(k);
+                const RobotPose2D<double> truth = poseGraph->NodeAt(std::min(idx, info.mPoseGraphNodeIdxMax)).Pose();
+                const auto scan = MakeScan(world, truth, 541, g);
+                const RobotPose2D<double> pert(truth.mX + dxy(g), truth.mY + dxy(g), truth.mTheta + dth(g));
+                n1.emplace_back(3000 + 10 * static_cast<int>(k) + j, pert, scan);
+                n2.emplace_back(3000 + 10 * static_cast<int>(k) + j, pert, scan);
+            }
+            const PoseGraph::Node& mapNode = poseGraph->NodeAt(info.mPoseGraphNodeIdxMin);
+            q1.emplace_back(std::move(n1), info, mapNode);
+            q2.emplace_back(std::move(n2), info, mapNode);
+        }
+        LoopDetectionResultVector r1, r2;
+        ref.Detect(q1, r1);
+        const auto d1 = std::chrono::steady_clock::now();
+        gpu.Detect(q2, r2);
+        const auto d2 = std::chrono::steady_clock::now();
+        LoopDetectionResultVector r3;
+        gpu.Detect(q2, r3);                                   /* cached pyramids on every device */
+        const auto d3 = std::chrono::steady_clock::now();
+        bool ok = r1.size() == r2.size() && r1.size() == r3.size();
+        for (size_t i = 0; ok && i < r1.size(); ++i)
+            ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) && SamePose(r1[i].mRelativePose, r3[i].mRelativePose) &&
+                 r1[i].mStartNodeIdx == r2[i].mStartNodeIdx && r1[i].mEndNodeIdx == r2[i].mEndNodeIdx &&
+                 SameMat(r1[i].mEstimatedCovMat, r2[i].mEstimatedCovMat) && SameMat(r1[i].mEstimatedCovMat, r3[i].mEstimatedCovMat);
+        for (auto& q : q2) ok = ok && q.mLocalMapInfo.mPrecomputed;
+        std::printf("loop detector on %zu device(s): %zu queries (one local map twice), loops ref %zu / cuda %zu, "
+                    "Detect %.1f ms then %.1f ms: %s\n", devices.size(), q1.size(), r1.size(), r2.size(),
+                    std::chrono::duration<double, std::milli>(d2 - d1).count(),
+                    std::chrono::duration<double, std::milli>(d3 - d2).count(), ok ? "IDENTICAL" : "MISMATCH");
+        failures += !ok;
+        if (r1.empty()) { std::printf("expected at least one detected loop\n"); ++failures; }
+    }
     /* ---- loop detector built on the correlative matcher ---- */
     {
         auto refMatcher = std::make_shared<ScanMatcherRealTimeCorrelative>(cost, 5, 1.5, 1.5, 0.6, 20.0);
@@ -547,7 +623,7 @@ int main() {
                 {"CostType", "GreedyEndpoint"}, {"CostConfigGroup", "C"}, {"UsableRangeMin", "0.01"},
                 {"UsableRangeMax", "20.0"}, {"Map.NumOfScansForLatestMap", "10"},
                 {"ProbabilityHit", "0.6"}, {"ProbabilityMiss", "0.45"}, {"SearchStepX", "0.05"},
-                {"SearchStepY", "0.05"}, {"SearchStepTheta", "0.01"}};
+                {"SearchStepY", "0.05"}, {"SearchStepTheta", "0.01"}, {"Devices", "0"}};
         auto costFactory = [&](const FlatTree&, const std::string&, const std::string&) { return CostFuncPtr(cost); };
         auto m = LgsB200::CreateScanMatcherRealTimeCorrelativeCuda(t, "M", costFactory);
         auto d1 = LgsB200::CreateLoopDetectorBranchBoundCuda(t, "D", costFactory);

@@ -1,27 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native scan-matching backend.
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8(d) "C2"): real-time correlative sweep,
-1081-beam 270-degree scans, +-0.5 m / +-30 deg window at 0.05 m / 0.5 deg, lowRes 5,
-ScanRangeMax 5.7296 m, against one ~800x800-cell map.  One STEP = the coarse win-max
-precompute of the map + one batch of `--matches` independent matches (different scans and
-perturbed initial poses) through the C ABI.  metric = pose hypotheses scored per second
-(fine + coarse hypotheses, each a full sum over the kept beams).
+BASELINE.json metric: "pose hypotheses scored/sec; loop-closure queries/sec at 1/2/4/8 B200".
 
-  value      kernels only, inputs resident in HBM, CUDA events on the context stream,
-             max over ranks (N > 1: every rank runs its own batch = weak scaling, no collective;
-             the single-scan front-end match does not shard).
-  e2e        same metric through the public API with HOST buffers: grid + scans H2D, kernels,
-             result records D2H, wall clock with a device sync on both sides.
-  roofline   the sweep kernel: algorithmic gathered bytes / its CUDA-event duration vs the
-             measured HBM copy peak (MEASURED_PEAKS.json).  The map is L1/L2 resident by
-             design, so frac > 1 is expected; DESIGN.md explains the L1-wavefront bound.
+  --gpus 1   headline = C2 (BASELINE configs[1]): real-time correlative sweep, 1081-beam 270-degree scans,
+             +-0.5 m / +-30 deg window at 0.05 m / 0.5 deg, lowRes 5, one ~800x800 map.  One STEP = the coarse
+             win-max precompute of the map + one batch of `--matches` matches through the C ABI.
+             metric = pose hypotheses scored per second.  The loop-closure half of the metric (C4) is
+             measured in the same run and reported in the `loop_closure` block of the line.
+  --gpus N   headline = C4 (BASELINE configs[3]): branch-and-bound loop detection against 500 submaps,
+             7 precompute levels, STRONG scaling: submap i lives on rank i mod N, every rank searches its own
+             pairs with ONE persistent kernel launch per device batch, the 32-byte result records are written
+             by that kernel into the rank's slice of the exchange buffer and all-gathered in place on the
+             device (lgs_comm: NCCL on the context stream).  value = loop queries/s for a step of 64 query
+             scans x 500 submaps (the throughput form); `single_scan` = one scan x 500 submaps (the
+             latency form).  Rank 0 also measures the same steps with all 500 submaps on its own GPU
+             (`n1_same_run`), so the line carries its own strong-scaling reference.  The C2 replicas
+             (weak scaling; the front-end match does not shard) move to `extra`.
+
+  value      kernels only, inputs resident in HBM, CUDA events on the context stream, max over ranks.
+  e2e        the same step through the public API with HOST buffers (H2D of the inputs, kernels, record
+             exchange, D2H of the records), wall clock with a device sync on both sides, max over ranks.
+  roofline   bound "l1_gather": the scoring kernels read maps that are L1/L2 resident by design; achieved =
+             algorithmic gathered bytes / kernel time, peak = the gather bandwidth measured in this run
+             (lgs_measure_gather_peak), `peak_theoretical` = 148 SMs x 128 B/clk x f_sm; the HBM view is in
+             `hbm` (traffic needs ncu: profiles/).
   cpu_baseline / --impl reference
-             the UNMODIFIED reference matcher (oracle/_ref/liblgs_ref.so) on the host cores.
+             the UNMODIFIED reference classes (oracle/_ref/liblgs_ref.so) on the host cores: the correlative
+             matcher at N = 1, the branch-and-bound matcher at N > 1 (rank 0 only).
+Details that do not fit the one-line contract go to gpurun_out/bench_details_n<N>.json.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -158,51 +170,25 @@ def hyps_per_match(res):
     return (2 * res.winT + 1) * (nbx * 5 * nby * 5 + nbx * nby)
 
 
-def run_reference(args, rank, world_size):
-    if rank != 0:
-        return
-    from oracle import refapi as R
-    cores = os.cpu_count() or 1
-    if not R.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblgs_ref.so not built"}))
-        return
-    per_step = max(16 * cores, 64)      # enough matches per step to keep every host thread busy
-    total = per_step * (args.steps + args.warmup)
-    traj, map_scans, angles, ranges, inits = c2_workload(total, seed=1)
-    builder = R.RefBuilder(n_latest=len(traj))
-    for p, r in zip(traj, map_scans):
-        builder.append_scan(p, angles, r)
-    refmap = builder.local_map(0)
-    dense = refmap.dense()
-    _, _, min_x, min_y, _ = refmap.geometry()
-    times, hyps = [], 0
-    for s in range(args.steps + args.warmup):
-        sl = slice(s * per_step, (s + 1) * per_step)
-        dt, res = ref_time_matches(dense, min_x, min_y, angles, ranges[sl], inits[sl], cores)
-        if s >= args.warmup:
-            times.append(dt)
-            hyps += sum(hyps_per_match(r) for r in res)
-    total_t = sum(times)
-    value = hyps / total_t
-    sample = (f"{per_step} C2 matches per step x {args.steps} steps on {cores} threads; "
-              "hypotheses = full window size per match (the CPU prunes inside it)")
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "C2 real-time correlative sweep, reference CPU matcher",
-                   "matches_per_step": per_step, **C2},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+
+def c2_config(M):
+    """The `config` object of the C2 line -- shared by both arms so that they describe the same workload."""
+    return {"workload": "C2 real-time correlative sweep: 1081 beams 270 deg, +-0.5 m/+-30 deg at 0.05 m/0.5 deg, "
+                        "lowRes 5, one ~800x800-cell map", "matches_per_step": int(M), **C2}
 
 
-
-# ---- extra workloads reported beside the headline (same JSON line, key "extra") --------------------
+# ---- C4: branch-and-bound loop detection -------------------------------------------------------------
 BB = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0, scan_range_max=20.0,
           score_range_min=0.01, score_range_max=20.0)
+C4_METRIC = "loop-closure queries/sec (branch-and-bound loop detection, C4)"
+C4_UNIT = "loop queries/s"
+C4_SCANS = 64
+
+
+def c4_config(n_submaps, world):
+    return {"workload": f"C4 branch-and-bound loop detection: {C4_SCANS} query scans x {n_submaps} submaps per step "
+                        "(1081 beams), 7 precompute levels, 2 m x 2 m x 1 rad, threshold 0.6",
+            "submaps": int(n_submaps), "scans_per_step": C4_SCANS, **BB}
 
 
 def c4_submap_scans(world, angles, submap_id, n_scans, anchor):
@@ -220,50 +206,98 @@ def c4_submap_scans(world, angles, submap_id, n_scans, anchor):
     return traj, [synth.make_scan(world, p, angles, rng) for p in traj]
 
 
-def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps, steps, with_cpu, n_batched_scans=64):
-    """C4: one 1081-beam scan against n_submaps submaps, 7 pyramid levels, threshold 0.6.
-    Submap i lives on rank i mod N; results are all-gathered (32-byte records)."""
-    from my_lidar_graph_slam_b200 import capi, sharding
+def c4_scene():
     world = synth.RoomsWorld(60.0, 5.0, seed=4)
     angles = synth.beam_angles(1081, 270.0)
     anchor = synth.trajectory(world, 1, seed=77)[0]
-    mine = sharding.owned(n_submaps, rank, world_size)
-    t0 = time.perf_counter()
-    grids, pyramids, cells = [], [], 0
-    for g in mine:
-        traj, scans = c4_submap_scans(world, angles, int(g), 8, anchor)
-        grid, _ = build_map_on_gpu(ctx, traj, angles, scans, apron=1)
-        grids.append(grid)
-        cells += grid.nx * grid.ny
-    build_s = time.perf_counter() - t0
-    # pyramids: the first build grows the stream-ordered memory pool (one-time allocation cost); the
-    # timed build is a REbuild of every pyramid, which is what the loop detector does whenever a
-    # submap has changed (loop_detector_branch_bound.cpp:44-53)
-    for grid in grids:
-        pyramids.append(capi.Pyramid(ctx, grid, 6))
-    for p in pyramids:
-        p.close()
-    pyramids = []
-    ctx.synchronize()
-    ctx.timer_start()
-    for grid in grids:
-        pyramids.append(capi.Pyramid(ctx, grid, 6))
-    pyr_ms = ctx.timer_stop()
     qrng = np.random.default_rng(5)
     truth = anchor + np.array([0.2, -0.1, 0.05])
-    scan = synth.make_scan(world, truth, angles, qrng)
-    init = truth + np.array([0.4, -0.3, 0.1])
-    nq = len(mine)
-    scans = capi.Scans([angles], [scan], [init], range_min=0.02, range_max=30.0)   # ONE query scan
-    pair_scan = np.zeros(nq, dtype=np.int32)
-    batch = capi.BbBatch(ctx, **BB)
-    dev = f"cuda:{local_rank}" if world_size > 1 else None
+    scans, inits = [synth.make_scan(world, truth, angles, qrng)], [truth + np.array([0.4, -0.3, 0.1])]
+    for k in range(1, C4_SCANS):
+        t = anchor + np.array([0.3 * np.cos(k), 0.3 * np.sin(k), 0.04 * k])
+        scans.append(synth.make_scan(world, t, angles, qrng))
+        inits.append(t + np.array([0.3, -0.2, 0.08]))
+    return world, angles, anchor, scans, inits
+
+
+class C4Shard:
+    """The submaps `ids` of the C4 scene on one context (grids + pyramids), and the loop-detection steps
+    of one rank against them."""
+
+    def __init__(self, ctx, scene, ids):
+        from my_lidar_graph_slam_b200 import capi
+        world, angles, anchor, self.qscans, self.qinits = scene
+        self.ctx, self.angles, self.ids = ctx, angles, np.asarray(ids, dtype=np.int64)
+        self.grids, self.pyramids, self.cells = [], [], 0
+        for g in self.ids:
+            traj, scans = c4_submap_scans(world, angles, int(g), 8, anchor)
+            grid, _ = build_map_on_gpu(ctx, traj, angles, scans, apron=1)
+            self.grids.append(grid)
+            self.cells += grid.nx * grid.ny
+        # the first build of the pyramids grows the stream-ordered memory pool (one-time cost); the timed
+        # build is a REbuild of every pyramid, which is what the loop detector does whenever a submap
+        # has changed (loop_detector_branch_bound.cpp:44-53)
+        warm = [capi.Pyramid(ctx, g, 6) for g in self.grids]
+        for p in warm:
+            p.close()
+        ctx.synchronize()
+        ctx.timer_start()
+        self.pyramids = [capi.Pyramid(ctx, g, 6) for g in self.grids]
+        self.pyramid_ms = ctx.timer_stop()
+
+    def groups(self, n_scans, n_submaps_total, sub_scans):
+        """Device sub-batches of `sub_scans` query scans x this shard's submaps: (Scans, pair_scan, pyramids,
+        global pair ids) per sub-batch.  Pair id = scan * n_submaps_total + submap."""
+        from my_lidar_graph_slam_b200 import capi
+        out = []
+        nq = len(self.ids)
+        for k0 in range(0, n_scans, sub_scans):
+            ks = list(range(k0, min(k0 + sub_scans, n_scans)))
+            out.append(dict(
+                scans=capi.Scans([self.angles] * len(ks), [self.qscans[k] for k in ks], [self.qinits[k] for k in ks],
+                                 range_min=0.02, range_max=30.0),
+                pair_scan=np.repeat(np.arange(len(ks), dtype=np.int32), nq),
+                pyr=self.pyramids * len(ks),
+                ids=np.concatenate([k * n_submaps_total + self.ids for k in ks]) if nq else np.zeros(0, dtype=np.int64)))
+        return out
+
+    def close(self):
+        for p in self.pyramids:
+            p.close()
+        for g in self.grids:
+            g.close()
+
+
+def c4_sub_scans(n_scans, nq):
+    """Query scans per device sub-batch: ~8000 pairs, so that a sub-batch's hit points (2.7 MB per scan and
+    layout) stay L2 resident while its levels are large enough to fill the persistent grid."""
+    if "LGS_C4_SUB" in os.environ:
+        return max(1, int(os.environ["LGS_C4_SUB"]))
+    return max(1, min(n_scans, -(-8000 // max(nq, 1))))
+
+
+def c4_steps(ctx, shard, comm, rank, world, n_submaps, n_scans, steps, barrier, max_over_ranks, thr=0.6):
+    """Time the loop-detection step `n_scans` query scans x `n_submaps` submaps with this rank's shard:
+    kernels only (inputs resident) and end to end (host scans in, gathered records out)."""
+    from my_lidar_graph_slam_b200 import capi, sharding
+    nq = len(shard.ids)
+    sub = c4_sub_scans(n_scans, nq)
+    groups = shard.groups(n_scans, n_submaps, sub)
+    seg = []
+    for r in range(world):
+        cnt = len(sharding.owned(n_submaps, r, world))
+        seg.append([cnt * len(range(k0, min(k0 + sub, n_scans))) for k0 in range(0, n_scans, sub)])
+    ex = sharding.RecordExchange(ctx, comm, n_scans * n_submaps, rank, world, seg)
+    batches = [capi.BbBatch(ctx, **BB) for _ in groups]
+    for k, (b, g) in enumerate(zip(batches, groups)):
+        ex.attach(b, g["ids"], k)
+    h2d = 0
 
     def step():
-        batch.upload_pairs(scans, pair_scan, pyramids, 0.6)
-        batch.run()
-        res = batch.results_array()
-        return sharding.all_gather_records(sharding.pack_array(res, mine), n_submaps, rank, world_size, dev)
+        for b, g in zip(batches, groups):
+            b.upload_pairs(g["scans"], g["pair_scan"], g["pyr"], thr)
+            b.run()
+        return ex.finish(batches)
 
     for _ in range(3):
         rec = step()
@@ -274,212 +308,49 @@ def run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks, n_submaps
         rec = step()
     ctx.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    # kernels only (scan + pyramids resident)
-    batch.upload_pairs(scans, pair_scan, pyramids, 0.6)
+    # kernels only: scans + pyramids resident, one persistent kernel launch per sub-batch and step
+    for b, g in zip(batches, groups):
+        b.upload_pairs(g["scans"], g["pair_scan"], g["pyr"], thr)
+    ctx.synchronize()
     barrier()
+    launches0 = ctx.launch_count()
     ctx.timer_start()
     for _ in range(steps):
-        batch.run()
+        for b in batches:
+            b.run()
     dev_ms = max_over_ranks(ctx.timer_stop())
-    levels, gathers = batch.work()
-    out = {"workload": f"C4 branch-and-bound loop detection: 1 scan x {n_submaps} submaps, 7 levels, "
-                       "2 m x 2 m x 1 rad, thr 0.6",
-           "loop_queries_per_s": n_submaps * steps / (dev_ms * 1e-3),
-           "loop_queries_per_s_e2e": n_submaps * steps / e2e_s,
-           "ms_per_query_batch": dev_ms / steps, "ms_per_query_batch_e2e": 1e3 * e2e_s / steps,
-           "nodes_scored_per_batch_rank0": int(sum(levels)), "nodes_per_level_rank0": levels,
-           "gathered_cells_per_batch_rank0": int(gathers),
-           "roofline": {"bound": "latency (breadth-first levels of 1-40 k nodes; a node's ordered 1081-beam double "
-                                 "sum is a ~9 k-cycle dependent chain)",
-                        "achieved": float(gathers) * 8 / (dev_ms / steps * 1e-3) / 1e9, "unit": "GB/s",
-                        "peak": measured_peaks()[0], "frac": float(gathers) * 8 / (dev_ms / steps * 1e-3) / 1e9 / measured_peaks()[0],
-                        "algorithmic_bytes": "SURVEY 8(d): nodes scored x usable beams x 8 B (the gathered map cell; "
-                                             "index / hit-point traffic not credited), rank 0's share",
-                        "note": "root level 234 us, six deeper levels 348 us at their latency floor: DESIGN.md 3.3, "
-                                "profiles/r1_launches_c4_bb_slots.csv"},
-           "loops_found": int((rec["found"] != 0).sum()), "best_submap": sharding.best_candidate(rec),
-           "submaps_per_rank": int(nq), "submap_cells_rank0": int(cells),
-           "pyramid_build_ms_rank0": pyr_ms,
-           "pyramid_cells_levels_per_s": cells * 7 / (pyr_ms * 1e-3) if pyr_ms > 0 else None,
-           "submap_build_s_rank0": build_s, "n_gpus": world_size,
-           "scaling": "strong (fixed 500 submaps, round-robin over ranks, all-gather of records)"}
-    # Throughput form of the same workload: a batch of Q query scans x all submaps per step (the
-    # reference's Detect() takes a vector of queries, loop_detector.hpp:92-107).  One scan x 500
-    # submaps is ~1 ms of device time, too little to amortise launch latency once it is split 8 ways.
-    Q = n_batched_scans
-    if Q > 1:
-        qscans, qinits = [], []
-        for k in range(Q):
-            t = anchor + np.array([0.3 * np.cos(k), 0.3 * np.sin(k), 0.04 * k])
-            qscans.append(synth.make_scan(world, t, angles, qrng))
-            qinits.append(t + np.array([0.3, -0.2, 0.08]))
-        # Device sub-batches of ~4000 pairs and at least 8 scans: the shared hit points of a sub-batch
-        # (7 MB per scan) stay L2 resident and the breadth-first levels are large enough to amortise
-        # their launch latency.  One rank of 8 takes its 63 submaps x 64 scans in one go, a single GPU
-        # walks eight sub-batches of 8 scans x 500 submaps.
-        sub = max(8, min(Q, -(-4000 // max(nq, 1))))
-        groups = []
-        for k0 in range(0, Q, sub):
-            ks = list(range(k0, min(k0 + sub, Q)))
-            groups.append(dict(
-                scans=capi.Scans([angles] * len(ks), [qscans[k] for k in ks], [qinits[k] for k in ks],
-                                 range_min=0.02, range_max=30.0),
-                pair_scan=np.repeat(np.arange(len(ks), dtype=np.int32), nq),
-                pyr=pyramids * len(ks),
-                ids=np.concatenate([k * n_submaps + mine for k in ks]) if nq else np.zeros(0, dtype=np.int64),
-                batch=capi.BbBatch(ctx, **BB)))
-
-        def stepQ():
-            recs = []
-            for g in groups:
-                g["batch"].upload_pairs(g["scans"], g["pair_scan"], g["pyr"], 0.6)
-                g["batch"].run()
-            for g in groups:
-                recs.append(sharding.pack_array(g["batch"].results_array(), g["ids"]))
-            local = np.concatenate(recs) if recs else np.zeros(0, dtype=sharding.RECORD)
-            return sharding.all_gather_variable(local, Q * n_submaps, world_size, dev)
-
-        for _ in range(2):
-            recQ = stepQ()
-        ctx.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            recQ = stepQ()
-        ctx.synchronize()
-        eQ = max_over_ranks(time.perf_counter() - t0)
-        for g in groups:
-            g["batch"].upload_pairs(g["scans"], g["pair_scan"], g["pyr"], 0.6)
-        barrier()
-        ctx.timer_start()
-        for _ in range(steps):
-            for g in groups:
-                g["batch"].run()
-        dQ = max_over_ranks(ctx.timer_stop())
-        out["batched"] = {"workload": f"{Q} query scans x {n_submaps} submaps per step, device sub-batches of "
-                                      f"{sub} scans x {nq} submaps on every rank",
-                          "loop_queries_per_s": Q * n_submaps * steps / (dQ * 1e-3),
-                          "loop_queries_per_s_e2e": Q * n_submaps * steps / eQ,
-                          "ms_per_step": dQ / steps, "ms_per_step_e2e": 1e3 * eQ / steps,
-                          "loops_found": int((recQ["found"] != 0).sum())}
-        for g in groups:
-            g["batch"].close()
-        # The same step on a 2-D rank grid (N > 1): (scan, submap) pairs are independent, so
-        # ranks can split the scans as well as the submaps.  Pm submap groups x Ps scan groups with
-        # Pm * Ps = N; a rank holds the pyramids of its submap group (n_submaps / Pm of them: 250 submaps are
-        # 9.5 GB) and searches its scan group against them in sub-batches of ~4000 pairs.  With 8 ranks that
-        # is ONE sub-batch of 16 scans x 250 submaps per rank -- the shape a single GPU runs eight times --
-        # instead of 64 scans x 63 submaps, whose 64 hit-point projections no rank shares.
-        if world_size > 1:
-            Ps, Pm = sharding.rank_grid(world_size, n_submaps,
-                                        want_pm=int(os.environ["LGS_C4_PM"]) if "LGS_C4_PM" in os.environ else None)
-            my_scans, group_ids = sharding.grid_owned(Q, n_submaps, rank, Ps, Pm)
-            my_scans = [int(k) for k in my_scans]
-            own = {int(g): k for k, g in enumerate(mine)}
-            extra_grids, extra_pyr, group_pyr = [], [], []
-            for g in group_ids:
-                if int(g) in own:
-                    group_pyr.append(pyramids[own[int(g)]])
-                    continue
-                traj_g, scans_g = c4_submap_scans(world, angles, int(g), 8, anchor)
-                grid_g, _ = build_map_on_gpu(ctx, traj_g, angles, scans_g, apron=1)
-                extra_grids.append(grid_g)
-                extra_pyr.append(capi.Pyramid(ctx, grid_g, 6))
-                group_pyr.append(extra_pyr[-1])
-            ng = len(group_ids)
-            sub2 = max(1, min(len(my_scans), max(8, -(-4000 // max(ng, 1))))) if my_scans else 1
-            groups2 = []
-            for k0 in range(0, len(my_scans), sub2):
-                ks = my_scans[k0:k0 + sub2]
-                groups2.append(dict(
-                    scans=capi.Scans([angles] * len(ks), [qscans[k] for k in ks], [qinits[k] for k in ks],
-                                     range_min=0.02, range_max=30.0),
-                    pair_scan=np.repeat(np.arange(len(ks), dtype=np.int32), ng),
-                    pyr=group_pyr * len(ks),
-                    ids=np.concatenate([k * n_submaps + group_ids for k in ks]),
-                    batch=capi.BbBatch(ctx, **BB)))
-
-            def stepS():
-                recs = []
-                for g in groups2:
-                    g["batch"].upload_pairs(g["scans"], g["pair_scan"], g["pyr"], 0.6)
-                    g["batch"].run()
-                for g in groups2:
-                    recs.append(sharding.pack_array(g["batch"].results_array(), g["ids"]))
-                local = np.concatenate(recs) if recs else np.zeros(0, dtype=sharding.RECORD)
-                return sharding.all_gather_variable(local, Q * n_submaps, world_size, dev)
-
-            for _ in range(2):
-                recS = stepS()
-            ctx.synchronize()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(steps):
-                recS = stepS()
-            ctx.synchronize()
-            eS = max_over_ranks(time.perf_counter() - t0)
-            for g in groups2:
-                g["batch"].upload_pairs(g["scans"], g["pair_scan"], g["pyr"], 0.6)
-            barrier()
-            ctx.timer_start()
-            for _ in range(steps):
-                for g in groups2:
-                    g["batch"].run()
-            dS = max_over_ranks(ctx.timer_stop())
-            out["batched_2d"] = {
-                "workload": f"{Q} query scans x {n_submaps} submaps per step on a {Ps} x {Pm} rank grid (scan groups x "
-                            f"submap groups): every rank searches {len(my_scans)} scans x {ng} submaps in sub-batches "
-                            f"of {sub2} scans",
-                "loop_queries_per_s": Q * n_submaps * steps / (dS * 1e-3),
-                "loop_queries_per_s_e2e": Q * n_submaps * steps / eS,
-                "ms_per_step": dS / steps, "ms_per_step_e2e": 1e3 * eS / steps,
-                "records_identical_to_submap_sharding": recS.tobytes() == recQ.tobytes()}
-            for g in groups2:
-                g["batch"].close()
-            for p_ in extra_pyr:
-                p_.close()
-            for g in extra_grids:
-                g.close()
-    if with_cpu and rank == 0:
-        try:
-            from oracle import refapi as R
-            if R.available():
-                cores = os.cpu_count() or 1
-                ns = min(nq, max(cores, 16))
-                from concurrent.futures import ThreadPoolExecutor
-                maps = []
-                for k in range(ns):
-                    g = grids[k]
-                    m = R.RefMap.from_dense(g.download(), g.min_x, g.min_y)
-                    maps.append((m, m.pyramid(6)))
-
-                def one(k):
-                    return R.bb_match(maps[k][0], angles, scan, init, pyramid=maps[k][1], thr=0.6)
-                one(0)
-                t0 = time.perf_counter()
-                with ThreadPoolExecutor(max_workers=cores) as ex:
-                    ref = list(ex.map(one, range(ns)))
-                dt = time.perf_counter() - t0
-                bad = sum((a.found, a.ix, a.iy, a.it) != (int(b["found"]), int(b["ix"]), int(b["iy"]), int(b["it"]))
-                          or (a.found and a.score != float(b["score"]))
-                          for a, b in zip(ref, rec[mine[:ns]]))
-                out["cpu_baseline"] = {"value": ns / dt, "unit": "loop queries/s", "cores": cores,
-                                       "kind": "reference",
-                                       "sample": f"first {ns} submaps on {cores} threads ({dt:.1f} s), "
-                                                 f"pyramids prebuilt; GPU results identical on {ns - bad}/{ns}"}
-        except Exception as e:
-            out["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
-    for p in pyramids:
-        p.close()
-    for g in grids:
-        g.close()
-    return out
+    launches = ctx.launch_count() - launches0
+    nodes, gathers, dev_runs, exact_runs = 0, 0, 0, 0
+    for b in batches:
+        lv, ga = b.work()
+        nodes += int(sum(lv))
+        gathers += int(ga)
+        d_, e_ = b.path()
+        dev_runs += d_
+        exact_runs += e_
+    for g in groups:
+        h2d += g["scans"].nbytes + len(g["ids"]) * 312          # scans + per-pair query descriptors
+    pairs = n_scans * n_submaps
+    out = {"qps": pairs * steps / (dev_ms * 1e-3), "qps_e2e": pairs * steps / e2e_s,
+           "ms": dev_ms / steps, "ms_e2e": 1e3 * e2e_s / steps, "launches_per_step": launches / steps,
+           "sub_batches": len(groups), "scans_per_sub_batch": sub, "nodes_rank0": nodes, "gathers_rank0": gathers,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(ex.d2h_bytes),
+           "device_runs": dev_runs, "exact_runs": exact_runs,
+           "found": int((rec["found"] != 0).sum()), "best": sharding.best_candidate(rec),
+           "sha": hashlib.sha256(rec.tobytes()).hexdigest()[:16]}
+    for b in batches:
+        b.close()
+    ex.close()
+    return out, rec
 
 
-def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_ranks, side, n_queries, steps):
-    """C5: one side x side map (8 x 8 stitched copies of a GPU-integrated 1000 x 1000 tile), 7 pyramid
-    levels, split into world_size row bands (band + margin per GPU, largemap.py), then a batch of loop
-    queries routed to the band of their sensor cell and all-gathered."""
+# ---- C5: large map ---------------------------------------------------------------------------------------
+def run_c5(ctx, comm, rank, world_size, barrier, max_over_ranks, sum_over_ranks, side, n_queries, steps):
+    """C5: one side x side map (8 x 8 stitched copies of a GPU-integrated 1000 x 1000 tile), 7 pyramid levels.
+    Precompute: split into world_size row bands (band + margin per GPU, largemap.py; banded == whole map
+    bit for bit, tests/test_gpu_largemap.py).  Batch loop closure: SURVEY 8(e) offers "each holding the
+    full pyramid" -- the whole 7-level pyramid is 3.6 GB, so every GPU builds its own copy (cheaper than
+    any exchange) and the queries are split round-robin; records are exchanged like C4's."""
     from my_lidar_graph_slam_b200 import capi, largemap, sharding
     T = 1000                                            # tile side (cells) = 50 m
     world = synth.RoomsWorld(40.0, 5.0, seed=12)
@@ -499,15 +370,26 @@ def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_
     def rows_provider(a, b):                            # rows [a, b) of the stitched map
         return np.tile(tile[np.arange(a, b) % T], (1, n_t))
 
+    # (1) precompute sharded in row bands
     band = largemap.BandedMap(ctx, rows_provider, nx, ny, -25.0, -25.0, 0.05, rank, world_size, BB["node_height_max"],
                               reach_m=BB["score_range_max"], range_y_m=BB["range_y"])
+    band.build_pyramid()                                # warm-up: grows the memory pool
+    band.pyramid.close()
     ctx.synchronize()
     barrier()
     ctx.timer_start()
     band.build_pyramid()
     pyr_ms = max_over_ranks(ctx.timer_stop())
     owned_cells = (band.r1 - band.r0) * nx
-    # queries: a pose of the tile trajectory moved into a random tile, perturbed
+    band_cells = band.cells
+    band.close()
+    # (2) batch loop closure: full pyramid on every GPU, queries round-robin
+    whole = capi.Grid(ctx, nx, ny, -25.0, -25.0, 0.05, apron=1)
+    whole.upload(rows_provider(0, ny))
+    ctx.synchronize()
+    ctx.timer_start()
+    pyr = capi.Pyramid(ctx, whole, BB["node_height_max"])
+    full_ms = ctx.timer_stop()
     qr = np.random.default_rng(14)
     q_scans, q_init = [], []
     for k in range(n_queries):
@@ -515,21 +397,16 @@ def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_
         off = np.array([qr.integers(0, n_t) * T * 0.05, qr.integers(0, n_t) * T * 0.05, 0.0])
         q_scans.append(synth.make_scan(world, base, angles, qr))
         q_init.append(base + off + np.array([qr.uniform(-0.4, 0.4), qr.uniform(-0.4, 0.4), qr.uniform(-0.1, 0.1)]))
-    q_init = np.asarray(q_init)
-    owner = largemap.owner_of_rows(largemap.sensor_rows(q_init[:, 1], -25.0, 0.05), ny, world_size)
-    mine = np.flatnonzero(owner == rank)
-    dev = f"cuda:{local_rank}" if world_size > 1 else None
+    mine = sharding.owned(n_queries, rank, world_size)
+    ex = sharding.RecordExchange(ctx, comm, n_queries, rank, world_size)
     batch = capi.BbBatch(ctx, **BB)
     sc = capi.Scans([angles] * len(mine), [q_scans[k] for k in mine], [q_init[k] for k in mine],
-                    range_min=0.02, range_max=30.0) if len(mine) else None
+                    range_min=0.02, range_max=30.0)
+    plist = [pyr] * len(mine)
+    pair = np.arange(len(mine), dtype=np.int32)
 
     def step():
-        res = []
-        if sc is not None:
-            batch.upload(sc, [band.pyramid] * len(mine), 0.6)
-            batch.run()
-            res = batch.results()
-        return sharding.all_gather_variable(sharding.pack(res, mine), n_queries, world_size, dev)
+        return ex.step(batch, sc, pair, plist, mine, 0.6)
 
     for _ in range(2):
         rec = step()
@@ -540,34 +417,24 @@ def run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks, sum_over_
         rec = step()
     ctx.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    dev_ms = 0.0
-    if sc is not None:
-        batch.upload(sc, [band.pyramid] * len(mine), 0.6)
+    batch.upload_pairs(sc, pair, plist, 0.6)
+    ctx.synchronize()
     barrier()
     ctx.timer_start()
     for _ in range(steps):
-        if sc is not None:
-            batch.run()
+        batch.run()
     dev_ms = max_over_ranks(ctx.timer_stop())
-    out = {"workload": f"C5 large map {nx}x{ny} cells (8x8 stitched GPU-integrated tiles), 7 levels, "
-                       f"{world_size} row band(s) + margins, {n_queries} loop queries routed by sensor row",
-           "precompute_ms": pyr_ms,
-           "precompute_cells_levels_per_s": sum_over_ranks(float(owned_cells)) * 7 / (pyr_ms * 1e-3),
-           "precompute_algorithmic_GBps": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9,
-           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": measured_peaks()[0] * world_size,
-                        "achieved": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9,
-                        "frac": sum_over_ranks(float(band.cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9 / (measured_peaks()[0] * world_size),
-                        "algorithmic_bytes": "16 B per cell per built level (6 levels); the whole build also copies "
-                                             "level 0 and clears the aprons",
-                        "note": "the level kernel alone: 5.0 TB/s = 76 % of the HBM peak (ncu, "
-                                "profiles/r1_kernels_v3.md section 2)"},
-           "band_rows_rank0": [int(band.w0), int(band.w1)], "queries_rank0": int(len(mine)),
-           "loop_queries_per_s": n_queries * steps / (dev_ms * 1e-3) if dev_ms > 0 else None,
-           "loop_queries_per_s_e2e": n_queries * steps / e2e_s,
-           "loops_found": int((rec["found"] != 0).sum()), "n_gpus": world_size,
-           "scaling": "strong (fixed map and query batch; bands and their queries per rank, all-gather of records)"}
+    peak = measured_peaks()[0] * world_size
+    algo = sum_over_ranks(float(band_cells)) * 6 * 16 / (pyr_ms * 1e-3) / 1e9
+    out = {"map_cells": [int(nx), int(ny)], "bands": world_size,
+           "precompute_ms": pyr_ms, "precompute_cells_levels_per_s": sum_over_ranks(float(owned_cells)) * 7 / (pyr_ms * 1e-3),
+           "precompute_hbm_frac": algo / peak, "full_pyramid_ms_per_gpu": full_ms,
+           "queries": n_queries, "qps": n_queries * steps / (dev_ms * 1e-3), "qps_e2e": n_queries * steps / e2e_s,
+           "found": int((rec["found"] != 0).sum()), "sha": hashlib.sha256(rec.tobytes()).hexdigest()[:16]}
     batch.close()
-    band.close()
+    ex.close()
+    pyr.close()
+    whole.close()
     return out
 
 
@@ -716,39 +583,12 @@ def run_gs(ctx, grid, dense, min_x, min_y, angles, ranges, inits, with_cpu, n_qu
             res["cpu_reference"] = {"error": str(e)}
     return res
 
-
-def run_b200(args, rank, world_size, local_rank):
+# ---- C2: the real-time correlative sweep -----------------------------------------------------------------
+def measure_c2(ctx, ctx_index, args, barrier, max_over_ranks, sum_over_ranks, with_clock_sampler):
+    """One rank's C2 measurement (every rank the same batch against its own copy of the map)."""
     from my_lidar_graph_slam_b200 import capi
-    dist = None
-    if world_size > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     M = args.matches
-    traj, map_scans, angles, ranges, inits = c2_workload(M, seed=1)   # identical replicas on every rank
-    ctx = capi.Context(local_rank)
+    traj, map_scans, angles, ranges, inits = c2_workload(M, seed=1)
     grid, _ = build_map_on_gpu(ctx, traj, angles, map_scans, apron=32)
     dense, min_x, min_y = grid.download(), grid.min_x, grid.min_y
     coarse = grid.like()
@@ -770,14 +610,13 @@ def run_b200(args, rank, world_size, local_rank):
         batch.run(grid, coarse)
         return batch.results(grid, coarse)
 
-    # ---- device-resident timing ------------------------------------------------------------
     batch.upload(grid, scans)
     hyp, gathers = batch.work()
     for _ in range(max(args.warmup, 3)):
         step_device()
     ctx.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(ctx_index) if with_clock_sampler else None
+    if sampler:
         sampler.start()
     barrier()
     launches0 = ctx.launch_count()
@@ -787,32 +626,21 @@ def run_b200(args, rank, world_size, local_rank):
     ms = ctx.timer_stop()
     launches = ctx.launch_count() - launches0
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(ms)
     total_hyp = sum_over_ranks(float(hyp)) * args.steps
-    value = total_hyp / (ms * 1e-3)
-
-    # ---- per-kernel timing for the roofline (sweep kernel) ---------------------------------------
+    # per-kernel timing for the roofline (sweep kernel), CUDA events on the context stream
     sweep_ms = []
     for _ in range(max(3, min(args.steps, 10))):
         ctx.check(lib.lgs_precompute(ctx.h, grid.h, 5, coarse.h))
         sweep_ms.append(batch.run_timed(grid, coarse))
     k_proj, k_sweep, k_sel = (statistics.mean(x[i] for x in sweep_ms) for i in range(3))
-    peak, peak_src = measured_peaks()
-    achieved = gathers * 8 / (k_sweep * 1e-3) / 1e9
-    # measured gather ceilings for this map size (lgs_measure_gather_peak; SURVEY 8(d) asks for a
-    # micro-benchmark of the same access width because MEASURED_PEAKS.json has no L1/L2 figure)
     gnx, gny = int(dense.shape[1]), int(dense.shape[0])
-    gather_peak = {
-        "rows32_aligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 32, True, True),
-        "rows32_unaligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 32, False, True),
-        "rows25_unaligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 25, False, True),
-        "rows25_unaligned_l2": capi.measure_gather_peak(ctx, gnx, gny, 25, False, False),
-    }
+    gather_peak = {"rows32_aligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 32, True, True),
+                   "rows25_unaligned_l1": capi.measure_gather_peak(ctx, gnx, gny, 25, False, True),
+                   "rows25_unaligned_l2": capi.measure_gather_peak(ctx, gnx, gny, 25, False, False)}
     results_dev = batch.results(grid, coarse)
-
-    # ---- end to end through the public API with host buffers ---------------------------------
-    # (a) strictly sequential: upload -> kernels -> results, one step after the other
+    # end to end, (a) strictly sequential: upload -> kernels -> results, one step after the other
     for _ in range(2):
         step_e2e()
     ctx.synchronize()
@@ -823,11 +651,10 @@ def run_b200(args, rank, world_size, local_rank):
     ctx.synchronize()
     e2e_seq_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    # (b) the way a caller with a stream of match batches uses the API: two contexts (= two CUDA
-    # streams), each with its own grid / batch object; step k + 1 is uploaded (host prep + H2D from
-    # page-locked memory) while step k's kernels run, and every step still moves its own inputs to
-    # the device and its own result records back.  This is the reported e2e value.
-    ctx2 = capi.Context(local_rank)
+    # (b) the way a caller with a stream of match batches uses the API: two contexts (= two CUDA streams),
+    # each with its own grid / batch object; step k + 1 is uploaded while step k's kernels run, and every
+    # step still moves its own inputs to the device and its own result records back.
+    ctx2 = capi.Context(ctx_index)
     grid2 = capi.Grid(ctx2, grid.nx, grid.ny, grid.min_x, grid.min_y, grid.res, apron=32)
     coarse2 = grid2.like()
     batch2 = capi.RtcsmBatch(ctx2, **C2)
@@ -856,99 +683,350 @@ def run_b200(args, rank, world_size, local_rank):
     ctx.synchronize(); ctx2.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = total_hyp / e2e_s
-    e2e_seq_value = total_hyp / e2e_seq_s
-    h2d = dense.nbytes + scans.nbytes + M * 96            # grid + scans + match descriptors
-    d2h = M * 32 + 4                                      # result records + fix-up counter
     assert all((a.found, a.ix, a.iy, a.it, a.score) == (b.found, b.ix, b.iy, b.it, b.score)
                for a, b in zip(results_dev, res_e2e))
+    batch2.close(); coarse2.close(); grid2.close(); ctx2.close()
+    capi.unpin(ctx, dense, scans.angles, scans.ranges, scans.sensor_pose)
+    return dict(value=total_hyp / (ms * 1e-3), ms_per_step=ms / args.steps, launches=int(launches), clocks=clocks,
+                hyp=int(hyp), gathers=int(gathers), k_proj=k_proj, k_sweep=k_sweep, k_sel=k_sel,
+                gather_peak=gather_peak, e2e=total_hyp / e2e_s, e2e_seq=total_hyp / e2e_seq_s,
+                e2e_ms=1e3 * e2e_s / args.steps, h2d=int(dense.nbytes + scans.nbytes + M * 96), d2h=int(M * 32 + 4),
+                grid=grid, coarse=coarse, batch=batch, dense=dense, min_x=min_x, min_y=min_y, angles=angles,
+                ranges=ranges, inits=inits, results=results_dev)
 
+
+def gather_roofline(achieved_gbps, gather_peak_gbps, sm_mhz, n_gpus, kernel, hbm_peak):
+    """The `roofline` object of a scoring kernel: bound = the L1 gather path (maps are cache resident)."""
+    theo = 148 * 128 * (sm_mhz or 1965.0) * 1e6 / 1e9 * n_gpus       # 148 SMs x 128 B/clk x f_sm
+    peak = gather_peak_gbps * n_gpus
+    return {"bound": "l1_gather", "achieved": achieved_gbps, "peak": peak, "unit": "GB/s", "frac": achieved_gbps / peak,
+            "peak_source": "measured in this run: lgs_measure_gather_peak, 32 doubles on 256-B boundaries, L1-friendly walk",
+            "peak_theoretical": theo, "frac_theoretical": achieved_gbps / theo, "kernel": kernel,
+            "hbm": {"peak": hbm_peak * n_gpus, "achieved_over_peak": achieved_gbps / (hbm_peak * n_gpus)},
+            "traffic": None}
+
+
+# ---- reference arm ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world_size):
+    """The UNMODIFIED reference classes on the box's host cores, same metric / unit / config as the GPU arm
+    of the same N: the correlative matcher (C2) at N = 1, the branch-and-bound matcher (C4) at N > 1."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import refapi as R
+    cores = os.cpu_count() or 1
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblgs_ref.so not built"}))
+        return
+    if world_size == 1 and args.gpus <= 1:
+        M = args.matches
+        per_step = min(M, max(16 * cores, 64))      # bounded sample of every step: enough to keep every thread busy
+        total = per_step * (args.steps + args.warmup)
+        traj, map_scans, angles, ranges, inits = c2_workload(max(total, M), seed=1)
+        builder = R.RefBuilder(n_latest=len(traj))
+        for p, r in zip(traj, map_scans):
+            builder.append_scan(p, angles, r)
+        refmap = builder.local_map(0)
+        dense = refmap.dense()
+        _, _, min_x, min_y, _ = refmap.geometry()
+        times, hyps = [], 0
+        for s in range(args.steps + args.warmup):
+            sl = slice(s * per_step, (s + 1) * per_step)
+            dt, res = ref_time_matches(dense, min_x, min_y, angles, ranges[sl], inits[sl], cores)
+            if s >= args.warmup:
+                times.append(dt)
+                hyps += sum(hyps_per_match(r) for r in res)
+        total_t = sum(times)
+        value = hyps / total_t
+        sample = (f"{per_step} of the {M} C2 matches of a step, {args.steps} steps, {cores} threads; hypotheses = "
+                  "full window per match (the CPU prunes inside it)")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps * (M / per_step),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": c2_config(M),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    # N > 1: branch-and-bound loop detection (C4).  Sample: one query scan against the first submaps.
+    scene = c4_scene()
+    world, angles, anchor, qscans, qinits = scene
+    n_maps = max(cores, 16)
+    maps = []
+    for g in range(n_maps):
+        traj, scans = c4_submap_scans(world, angles, g, 8, anchor)
+        b = R.RefBuilder(n_latest=len(traj))
+        for p, r in zip(traj, scans):
+            b.append_scan(p, angles, r)
+        m = b.local_map(0)
+        maps.append((m, m.pyramid(6)))
+
+    def one(job):
+        k, g = job
+        return R.bb_match(maps[g][0], angles, qscans[k], qinits[k], pyramid=maps[g][1], thr=0.6)
+
+    times, n_done = [], 0
+    for s in range(args.steps + args.warmup):
+        jobs = [((s + j // n_maps) % C4_SCANS, j % n_maps) for j in range(n_maps)]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            list(ex.map(one, jobs))
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            n_done += len(jobs)
+    total_t = sum(times)
+    value = n_done / total_t
+    pairs = C4_SCANS * args.submaps
+    sample = (f"{n_maps} (scan, submap) pairs per step (first {n_maps} submaps, pyramids prebuilt) on {cores} threads, "
+              f"{args.steps} steps; a full step is {pairs} pairs")
+    print(json.dumps({
+        "impl": "reference", "metric": C4_METRIC, "value": value, "unit": C4_UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * pairs / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": c4_config(args.submaps, args.gpus),
+        "cpu_baseline": {"value": value, "unit": C4_UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": C4_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def write_details(n, details):
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"bench_details_n{n}.json"), "w") as f:
+            json.dump(details, f, indent=1, default=lambda o: float(o) if isinstance(o, np.floating) else str(o))
+    except OSError:
+        pass
+
+
+def r3(x):
+    """3 significant digits (the one-line contract must stay short)."""
+    return None if x is None else float(f"{float(x):.3g}")
+
+
+def run_b200(args, rank, world_size, local_rank):
+    from my_lidar_graph_slam_b200 import capi, sharding
+    dist = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def reduce_(x, op):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(x):
+        return reduce_(x, dist.ReduceOp.MAX) if dist is not None else x
+
+    def sum_over_ranks(x):
+        return reduce_(x, dist.ReduceOp.SUM) if dist is not None else x
+
+    ctx = capi.Context(local_rank)
+    comm = sharding.make_comm(ctx, rank, world_size)
+    hbm_peak, hbm_src = measured_peaks()
+    details = {"n_gpus": world_size}
+    steps_side = max(3, min(args.steps, 10))
+
+    # ---- C2 (headline at N = 1, `extra.c2_replicas` at N > 1) ------------------------------------------------
+    c2 = measure_c2(ctx, local_rank, args, barrier, max_over_ranks, sum_over_ranks, rank == 0)
+    sm_mhz = (c2["clocks"] or {}).get("sm_mhz") if rank == 0 else None
+    gpeak = c2["gather_peak"]["rows32_aligned_l1"]
+    c2_achieved = c2["gathers"] * 8 / (c2["k_sweep"] * 1e-3) / 1e9
+
+    # ---- C4 loop closure: this rank's shard of the 500 submaps ---------------------------------------------------
+    c4 = None
+    if not args.no_c4:
+        scene = c4_scene()
+        mine = sharding.owned(args.submaps, rank, world_size)
+        t0 = time.perf_counter()
+        shard = C4Shard(ctx, scene, mine)
+        build_s = time.perf_counter() - t0
+        single, rec1 = c4_steps(ctx, shard, comm, rank, world_size, args.submaps, 1, steps_side, barrier, max_over_ranks)
+        batched, recq = c4_steps(ctx, shard, comm, rank, world_size, args.submaps, C4_SCANS, max(2, steps_side // 2),
+                                 barrier, max_over_ranks)
+        c4 = {"single": single, "batched": batched, "submaps_rank0": int(len(mine)),
+              "pyramid_rebuild_ms_rank0": shard.pyramid_ms, "submap_build_s_rank0": build_s,
+              "pyramid_cells_levels_per_s_rank0": shard.cells * 7 / (shard.pyramid_ms * 1e-3) if shard.pyramid_ms > 0 else None}
+        c4["gathers_all"] = sum_over_ranks(float(batched["gathers_rank0"]))
+        shard.close()
+        # the same steps with ALL submaps on rank 0's GPU alone: the strong-scaling reference of this very run
+        if world_size > 1:
+            n1 = None
+            if rank == 0:
+                full = C4Shard(ctx, scene, np.arange(args.submaps))
+                nb = lambda: None
+                s1, r1 = c4_steps(ctx, full, None, 0, 1, args.submaps, 1, steps_side, nb, lambda x: x)
+                sq, rq = c4_steps(ctx, full, None, 0, 1, args.submaps, C4_SCANS, max(2, steps_side // 2), nb, lambda x: x)
+                full.close()
+                n1 = {"single": s1, "batched": sq,
+                      "records_identical": bool(r1.tobytes() == rec1.tobytes() and rq.tobytes() == recq.tobytes())}
+            barrier()
+            c4["n1_same_run"] = n1
+        # CPU reference on a bounded sample, parity-checked (N = 1 only)
+        if world_size == 1 and not args.no_cpu_baseline:
+            try:
+                from concurrent.futures import ThreadPoolExecutor
+
+                from oracle import refapi as R
+                if R.available():
+                    cores = os.cpu_count() or 1
+                    ns = max(cores, 16)
+                    world, angles, anchor, qscans, qinits = scene
+                    maps = []
+                    for g in range(ns):
+                        traj, scans = c4_submap_scans(world, angles, g, 8, anchor)
+                        b = R.RefBuilder(n_latest=len(traj))
+                        for p, r in zip(traj, scans):
+                            b.append_scan(p, angles, r)
+                        m = b.local_map(0)
+                        maps.append((m, m.pyramid(6)))
+                    t0 = time.perf_counter()
+                    with ThreadPoolExecutor(max_workers=cores) as ex:
+                        ref = list(ex.map(lambda g: R.bb_match(maps[g][0], angles, qscans[0], qinits[0],
+                                                               pyramid=maps[g][1], thr=0.6), range(ns)))
+                    dt = time.perf_counter() - t0
+                    bad = sum((a.found, a.ix, a.iy, a.it) != (int(b["found"]), int(b["ix"]), int(b["iy"]), int(b["it"]))
+                              or (a.found and a.score != float(b["score"])) for a, b in zip(ref, rec1[:ns]))
+                    c4["cpu_baseline"] = {"value": ns / dt, "unit": C4_UNIT, "cores": cores, "kind": "reference",
+                                          "sample": f"first {ns} submaps x 1 scan on {cores} threads ({dt:.1f} s), pyramids "
+                                                    f"prebuilt; GPU records identical on {ns - bad}/{ns}"}
+            except Exception as e:                                   # noqa: BLE001
+                c4["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
+    details["c4"] = c4
+
+    # ---- side measurements ---------------------------------------------------------------------------------------
     extra = {}
 
     def side(name, fn):
-        """A side measurement must never take the headline line down with it (single process only:
-        with several ranks a failure has to propagate, or the other ranks wait in a collective)."""
+        """A side measurement must never take the headline line down with it (single process only: with
+        several ranks a failure has to propagate, or the other ranks wait in a collective)."""
         if world_size > 1:
-            extra[name] = fn()
+            details[name] = fn()
             return
         try:
-            extra[name] = fn()
+            details[name] = fn()
         except Exception as e:                                   # noqa: BLE001
-            extra[name] = {"error": f"{type(e).__name__}: {e}"}
+            details[name] = {"error": f"{type(e).__name__}: {e}"}
 
     if not args.no_extra:
-        side("loop_detection", lambda: run_c4(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
-                                              args.submaps, max(3, min(args.steps, 10)),
-                                              world_size == 1 and not args.no_cpu_baseline))
-        if rank == 0:
-            side("matcher_tail", lambda: run_tail(ctx, grid, dense, min_x, min_y, angles, ranges, inits,
-                                                  results_dev, not args.no_cpu_baseline))
-            side("grid_search", lambda: run_gs(ctx, grid, dense, min_x, min_y, angles, ranges, inits,
-                                               not args.no_cpu_baseline))
-            side("grid_integration", lambda: run_c3(ctx, 1024, args.c3_scans, not args.no_cpu_baseline))
         if args.c5_side > 0:
-            side("large_map", lambda: run_c5(ctx, rank, world_size, local_rank, barrier, max_over_ranks,
-                                             sum_over_ranks, args.c5_side, args.c5_queries,
-                                             max(2, min(args.steps, 5))))
+            side("c5", lambda: run_c5(ctx, comm, rank, world_size, barrier, max_over_ranks, sum_over_ranks,
+                                      args.c5_side, args.c5_queries, max(2, min(args.steps, 5))))
+        if rank == 0 and world_size == 1:
+            cpu_side = not args.no_cpu_baseline
+            side("matcher_tail", lambda: run_tail(ctx, c2["grid"], c2["dense"], c2["min_x"], c2["min_y"], c2["angles"],
+                                                  c2["ranges"], c2["inits"], c2["results"], cpu_side))
+            side("grid_search", lambda: run_gs(ctx, c2["grid"], c2["dense"], c2["min_x"], c2["min_y"], c2["angles"],
+                                               c2["ranges"], c2["inits"], cpu_side))
+            side("c3", lambda: run_c3(ctx, 1024, args.c3_scans, cpu_side))
+            side("c1", lambda: run_c1())
     if rank != 0:
         return
-    # ---- CPU baseline: the unmodified reference on a bounded sample, parity-checked ------------
+
+    # ---- CPU baseline of the headline: the unmodified reference on a bounded sample, parity-checked -----------------
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:
         try:
             from oracle import refapi as R
             if R.available():
                 cores = os.cpu_count() or 1
-                ns = min(M, max(16 * cores, 64))
-                dt, ref = ref_time_matches(dense, min_x, min_y, angles, ranges[:ns], inits[:ns], cores)
+                ns = min(args.matches, max(16 * cores, 64))
+                dt, ref = ref_time_matches(c2["dense"], c2["min_x"], c2["min_y"], c2["angles"], c2["ranges"][:ns],
+                                           c2["inits"][:ns], cores)
                 bad = sum((a.found, a.ix, a.iy, a.it, a.score) != (b.found, b.ix, b.iy, b.it, b.score)
-                          for a, b in zip(ref, results_dev[:ns]))
-                cpu = {"value": sum(hyps_per_match(r) for r in ref) / dt, "unit": UNIT,
-                       "cores": cores, "kind": "reference",
-                       "sample": f"first {ns} matches of the step on {cores} threads "
-                                 f"({dt:.1f} s); hypotheses = full window per match; "
-                                 f"GPU winners/scores identical on {ns - bad}/{ns}"}
+                          for a, b in zip(ref, c2["results"][:ns]))
+                cpu = {"value": r3(sum(hyps_per_match(r) for r in ref) / dt), "unit": UNIT, "cores": cores,
+                       "kind": "reference", "sample": f"first {ns} matches of the step, {cores} threads, {dt:.1f} s; "
+                                                      f"GPU winners/scores identical {ns - bad}/{ns}"}
         except Exception as e:   # the baseline is reported, never required
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                   "sample": f"failed: {e}"}
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 real-time correlative sweep: 1081 beams 270 deg, +-0.5 m/+-30 deg "
-                               "at 0.05 m/0.5 deg, lowRes 5, one map of %dx%d cells" % dense.shape[::-1],
-                   "matches_per_step": M, "hypotheses_per_step": hyp, **C2,
-                   "l2": "no flush: per-step working set (projected offsets + score tables) %.0f MB > 126 MB "
-                         "L2; the map itself is cache-resident by design"
-                         % ((hyp * 8 + hyp / 650.0 * (gathers / max(hyp, 1)) * 4) / 1e6),
-                   "parallelism": "replicas only: every rank runs the same 1000-match batch against its own copy of the map (SURVEY 8(e): the front-end match does not shard)" if world_size > 1 else "1 GPU"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "sequential_value": e2e_seq_value,
-                "note": "value: steps pipelined over two contexts (upload of step k+1 under the kernels of "
-                        "step k); sequential_value: upload -> kernels -> results strictly one after the other"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": 0.8305e6 * M, "kernel": "csm_sweep_rows_kernel<4,5>",
-                     "traffic_source": "ncu --set full: dram__bytes_read+write = 166.1 MB per 200-match "
-                                       "launch (profiles/r1_kernels_v2.md), scaled to this launch",
-                     "peak_source": peak_src, "kernel_ms": k_sweep,
-                     "algorithmic_bytes_per_launch": gathers * 8,
-                     "note": "gathers are served from L1/L2 (map is cache resident), so the HBM "
-                             "roofline is not the binding limit; see DESIGN.md"},
-        "gather_roofline": {"bound": "l1 gather (8-byte warp-wide loads, map cache resident)",
-                            "achieved": achieved, "peak": gather_peak["rows32_aligned_l1"], "unit": "GB/s",
-                            "frac": achieved / gather_peak["rows32_aligned_l1"], "measured_peaks": gather_peak,
-                            "peak_source": "lgs_measure_gather_peak in this run: best of 3 launches, rows of 32 "
-                                           "doubles on 256-byte boundaries, L1-friendly walk over an array of "
-                                           "the map's size; the other entries are the sweep's own shapes"},
-        "kernel_ms": {"csm_project": k_proj, "csm_sweep": k_sweep, "csm_select": k_sel},
-        "cpu_baseline": cpu,
-        "extra": extra,
-    }
+    c2_block = {"value": r3(c2["value"]), "e2e": r3(c2["e2e"]), "e2e_sequential": r3(c2["e2e_seq"]),
+                "ms_per_step": r3(c2["ms_per_step"]), "sweep_ms": r3(c2["k_sweep"])}
+    details["c2"] = {k: v for k, v in c2.items() if k not in ("grid", "coarse", "batch", "dense", "angles", "ranges",
+                                                              "inits", "results")}
+    for name, keys in (("c5", ("precompute_ms", "precompute_hbm_frac", "qps", "qps_e2e", "found", "sha")),
+                       ("c3", ("scans_per_s", "cell_updates_per_s")), ("matcher_tail", ("tails_per_s",)),
+                       ("grid_search", ("hypotheses_per_s",)), ("c1", ("frames_per_s", "ref_frames_per_s", "identical"))):
+        d = details.get(name)
+        if isinstance(d, dict):
+            extra[name] = {k: (r3(d[k]) if isinstance(d.get(k), float) else d.get(k)) for k in keys if k in d} \
+                if "error" not in d else {"error": d["error"][:80]}
+
+    def c4_compact(c):
+        return {"q1": {"k": r3(c["single"]["qps"]), "e2e": r3(c["single"]["qps_e2e"]), "ms": r3(c["single"]["ms"])},
+                "q64": {"k": r3(c["batched"]["qps"]), "e2e": r3(c["batched"]["qps_e2e"]), "ms": r3(c["batched"]["ms"])}}
+
+    if world_size == 1:
+        line = {
+            "metric": METRIC, "value": c2["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": c2["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": c2_config(args.matches),
+            "timing_notes": {"l2": "per-step working set (offsets + score tables) > 126 MB L2: no flush"},
+            "e2e": {"value": c2["e2e"], "unit": UNIT, "h2d_bytes_per_step": c2["h2d"], "d2h_bytes_per_step": c2["d2h"],
+                    "sequential_value": r3(c2["e2e_seq"])},
+            "gpu_launches": c2["launches"], "clocks": c2["clocks"],
+            "roofline": gather_roofline(c2_achieved, gpeak, sm_mhz, 1, "csm_sweep_rows_kernel<4,5>", hbm_peak),
+            "cpu_baseline": cpu,
+        }
+        if c4:
+            line["loop_closure"] = {"unit": C4_UNIT, **c4_compact(c4),
+                                    "l1_gather_frac": r3(c4["gathers_all"] * 8 / (c4["batched"]["ms"] * 1e-3) / 1e9 / gpeak),
+                                    "sha": c4["batched"]["sha"],
+                                    "found": c4["batched"]["found"], "launches_per_run": 1,
+                                    "cpu": r3((c4.get("cpu_baseline") or {}).get("value"))}
+        line["extra"] = extra
+    else:
+        b = c4["batched"]
+        line = {
+            "metric": C4_METRIC, "value": b["qps"], "unit": C4_UNIT, "n_gpus": world_size, "steps": max(2, steps_side // 2),
+            "warmup": 3, "ms_per_step": b["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": c4_config(args.submaps, world_size),
+            "timing_notes": {"parallelism": f"submap i on rank i mod {world_size}; one persistent kernel per device batch "
+                                            "writes its records into the exchange buffer; in-place NCCL all-gather (lgs_comm)",
+                             "l2": "pyramids 41 MB per submap >> L2: no flush"},
+            "e2e": {"value": b["qps_e2e"], "unit": C4_UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": b["d2h_bytes_per_step"]},
+            "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]), "ms": r3(c4["single"]["ms"])},
+            "records_sha256": b["sha"], "loops_found": b["found"],
+            "gpu_launches": int(round(b["launches_per_step"] * max(2, steps_side // 2))), "clocks": c2["clocks"],
+            "roofline": gather_roofline(c4["gathers_all"] * 8 / (b["ms"] * 1e-3) / 1e9, gpeak, sm_mhz, world_size,
+                                        "bb_run_kernel<16,2>", hbm_peak),
+            "cpu_baseline": None,
+        }
+        if c4.get("n1_same_run"):
+            n1 = c4["n1_same_run"]
+            line["n1_same_run"] = {**c4_compact(n1), "records_identical": n1["records_identical"]}
+        extra["c2_replicas"] = c2_block
+        line["extra"] = extra
+    write_details(world_size, details)
     print(json.dumps(line))
+
+
+def run_c1():
+    """C1 (BASELINE configs[0]): the default-settings front-end frame loop (180-beam log, correlative match +
+    map update per frame) through the C++ adapters beside the reference's own classes
+    (adapters/c1_bench.cpp, built where the reference tree exists)."""
+    exe = os.path.join(ROOT, "adapters", "_build", "c1_bench")
+    if not os.path.exists(exe):
+        return {"error": "adapters/_build/c1_bench not built (needs the reference tree at build time)"}
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    if p.returncode != 0:
+        return {"error": f"c1_bench exit {p.returncode}: {p.stdout[-200:]} {p.stderr[-200:]}"}
+    return json.loads(p.stdout.strip().splitlines()[-1])
 
 
 def main():
@@ -957,10 +1035,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--matches", type=int, default=1000, help="matches per step (C2: 1000)")
+    ap.add_argument("--matches", type=int, default=1000, help="C2: matches per step (1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C3 side measurements")
-    ap.add_argument("--submaps", type=int, default=500, help="C4: submaps per loop query batch")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C5 / C1 / tail / grid-search side measurements")
+    ap.add_argument("--no-c4", action="store_true", help="skip the loop-closure measurement (N = 1 only)")
+    ap.add_argument("--submaps", type=int, default=500, help="C4: submaps")
     ap.add_argument("--c5-side", type=int, default=8000, help="C5: map side in cells (multiple of 1000; 0 = skip)")
     ap.add_argument("--c5-queries", type=int, default=256, help="C5: loop queries per batch")
     ap.add_argument("--c3-scans", type=int, default=102400, help="C3: scans streamed (BASELINE config: 100k)")
@@ -968,6 +1047,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        args.no_c4 = False
     if args.impl == "reference":
         run_reference(args, rank, world_size)
     else:

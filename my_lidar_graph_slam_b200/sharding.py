@@ -31,15 +31,24 @@ def slots_per_rank(n_items: int, world: int) -> int:
     return (n_items + world - 1) // world + 1
 
 
+def _segments(counts):
+    """Normalise per-rank record counts: an int (one batch) or a list (one entry per sub-batch)."""
+    return [[int(c)] if np.isscalar(c) else [int(x) for x in c] for c in counts]
+
+
 def assemble(gathered: np.ndarray, counts, per: int, n_items: int):
-    """Gathered buffer (world x per records, rank r's `counts[r]` records first in its slice, then its
-    status record) -> (records in global order, all runs valid?)."""
+    """Gathered buffer (world x per records) -> (records in global order, all runs valid?).  Rank r's
+    slice holds, for each of its sub-batches in turn, `counts[r][k]` records followed by that run's
+    status record (lgs_bb_batch_set_record_sink)."""
     out = np.zeros(n_items, dtype=RECORD)
     ok = True
-    for r, cnt in enumerate(counts):
-        sl = gathered[r * per:r * per + cnt]
-        out[sl["submap"]] = sl
-        ok &= int(gathered[r * per + cnt]["found"]) == 1
+    for r, seg in enumerate(_segments(counts)):
+        pos = r * per
+        for cnt in seg:
+            sl = gathered[pos:pos + cnt]
+            out[sl["submap"]] = sl
+            ok &= int(gathered[pos + cnt]["found"]) == 1
+            pos += cnt + 1
     return out, bool(ok)
 
 
@@ -89,24 +98,35 @@ def make_comm(ctx, rank: int, world: int):
 
 
 class RecordExchange:
-    """Device-resident exchange of loop records between one-process-per-GPU ranks."""
+    """Device-resident exchange of loop records between one-process-per-GPU ranks.
+
+    counts[r] = number of records of rank r (an int), or a list with one entry per device sub-batch of
+    rank r; every rank computes all of them, ownership being a pure function of the indices."""
 
     def __init__(self, ctx, comm, n_items: int, rank: int, world: int, counts=None):
         from . import capi
         self.ctx, self.comm, self.n_items, self.rank, self.world = ctx, comm, int(n_items), rank, world
-        self.counts = [len(owned(n_items, r, world)) for r in range(world)] if counts is None else list(counts)
-        self.per = max(self.counts) + 1
+        if counts is None:
+            counts = [len(owned(n_items, r, world)) for r in range(world)]
+        self.counts = _segments(counts)
+        self.per = max(sum(c + 1 for c in seg) for seg in self.counts)
         self.buf = capi.device_alloc(ctx, world * self.per * RECORD.itemsize)
-        self._ids_of = None
+        self.first = np.concatenate([[0], np.cumsum([c + 1 for c in self.counts[rank]])])[:-1] + rank * self.per
+        self._attached = {}
 
-    def attach(self, batch, ids):
-        """Point the batch's finalize phase at this rank's slice (records + status record)."""
-        if self._ids_of is not batch:
+    @property
+    def d2h_bytes(self) -> int:
+        return self.world * self.per * RECORD.itemsize
+
+    def attach(self, batch, ids, k: int = 0):
+        """Point the finalize phase of sub-batch k at its slots of this rank's slice."""
+        if self._attached.get(k) is not batch:
+            assert len(ids) == self.counts[self.rank][k]
             batch.set_record_ids(ids)
-            batch.set_record_sink(self.buf, self.rank * self.per)
-            self._ids_of = batch
+            batch.set_record_sink(self.buf, int(self.first[k]))
+            self._attached[k] = batch
 
-    def gather(self) -> np.ndarray:
+    def gather(self):
         """All-gather on the context stream (in place), one download, assembly in global order."""
         from . import capi
         if self.comm is not None:
@@ -114,20 +134,24 @@ class RecordExchange:
         raw = capi.download_records(self.ctx, self.buf, self.world * self.per)
         return assemble(raw, self.counts, self.per, self.n_items)
 
-    def step(self, batch, scans, pair_scan, pyramids, ids, thr):
-        """One sharded loop-detection step: upload, ONE kernel launch, in-place all-gather, download.
-        If any rank's run has to be repeated exactly (status record), every rank sees it in the
-        gathered buffer, the affected rank settles (exact path, records rewritten) and the gather is
-        repeated -- the decision is collective because it is taken from exchanged data."""
-        self.attach(batch, ids)
-        batch.upload_pairs(scans, pair_scan, pyramids, thr)
-        batch.run()
+    def finish(self, batches):
+        """gather(); if any rank's run has to be repeated exactly (its status record says so), every rank
+        sees that in the gathered buffer, the ranks settle their batches (exact path, records rewritten
+        in place) and the gather is repeated -- a collective decision taken from exchanged data."""
         out, ok = self.gather()
         if not ok:
-            batch.settle()
+            for b in batches:
+                b.settle()
             out, ok = self.gather()
             assert ok
         return out
+
+    def step(self, batch, scans, pair_scan, pyramids, ids, thr):
+        """One sharded loop-detection step: upload, ONE kernel launch, in-place all-gather, download."""
+        self.attach(batch, ids)
+        batch.upload_pairs(scans, pair_scan, pyramids, thr)
+        batch.run()
+        return self.finish([batch])
 
     def close(self):
         from . import capi
