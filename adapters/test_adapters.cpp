@@ -173,7 +173,92 @@ bool SameBuilders(const A& a, const B& b) {
 
 }  // namespace
 
-int main() {
+/* ---- config C1: the front end's own frame loop (lidar_graph_slam_frontend.cpp:85-127) with the
+ *      default launcher settings (launcher_settings_default.json:42-50, :175-185) on a 180-beam
+ *      180-degree log with drifting odometry: reference classes vs the device pipeline (builder's
+ *      device-resident latest map -> matcher -> device tail); poses feed back into the maps, so one
+ *      differing bit anywhere compounds.  json: print one JSON line for bench.py (`extra.c1`). ---- */
+int RunC1(const bool json) {
+    std::mt19937 g(11);
+    const World world(7);
+    auto cost = std::make_shared<CostGreedyEndpoint>(0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0);
+    const lgs_cost_params costParams { 0.01, 20.0, 0.075, 0.1, 1, 0.05, 1.0 };
+    int failures = 0;
+    const int numOfFrames = 150;
+    std::vector<RobotPose2D<double>> truth, odom;
+    for (int k = 0; k < numOfFrames; ++k) {
+        truth.emplace_back(-9.9 + 0.09 * k * std::cos(0.004 * k), -9.8 + 0.5 * std::sin(0.05 * k), 0.1 * std::sin(0.03 * k));
+        odom.emplace_back(truth[k].mX + 0.0015 * k, truth[k].mY - 0.001 * k, truth[k].mTheta + 0.0004 * k);
+    }
+    auto pgRef = std::make_shared<PoseGraph>(), pgCuda = std::make_shared<PoseGraph>();
+    GridMapBuilder bRef(0.05, 64, 10, 20.0, 0.01, 20.0, 0.6, 0.45);
+    GridMapBuilderCuda bCuda(0.05, 64, 10, 20.0, 0.01, 20.0, 0.6, 0.45, 0);
+    ScanMatcherRealTimeCorrelative mRef(cost, 5, 0.2, 0.2, 0.5, 20.0);
+    ScanMatcherRealTimeCorrelativeCuda mCuda(cost, 5, 0.2, 0.2, 0.5, 20.0, 0);
+    mCuda.UseDeviceCost(costParams);
+    double msRef = 0.0, msCuda = 0.0, msMatch = 0.0, warm[4] = { 0.0, 0.0, 0.0, 0.0 };
+    int bad = 0, lost = 0;
+    for (int k = 0; k < numOfFrames; ++k) {
+        if (k == 5) for (int j = 0; j < 4; ++j) warm[j] = bCuda.TimingsMs()[j];   /* allocations settle first */
+        const auto scan = MakeScan(world, truth[k], 180, g, 3.14159265358979323846);
+        const auto t0 = std::chrono::steady_clock::now();
+        if (k == 0) {
+            pgRef->AppendNode(truth[0], scan);
+        } else {
+            const RobotPose2D<double> initial =
+                Compound(pgRef->LatestNode().Pose(), InverseCompound(odom[k - 1], odom[k]));
+            const ScanMatchingQuery query(GridMapType(bRef.LatestMap()), scan, initial);
+            const ScanMatchingSummary a = mRef.OptimizePose(query);
+            lost += !a.mPoseFound;
+            pgRef->AppendNode(a.mEstimatedPose, scan);
+        }
+        bRef.AppendScan(pgRef);
+        const auto t1 = std::chrono::steady_clock::now();
+        if (k == 0) {
+            pgCuda->AppendNode(truth[0], scan);
+        } else {
+            const RobotPose2D<double> initial =
+                Compound(pgCuda->LatestNode().Pose(), InverseCompound(odom[k - 1], odom[k]));
+            const ScanMatchingSummary b = mCuda.OptimizePose(bCuda.DeviceLatestMap(), scan, initial,
+                                                             std::numeric_limits<double>::min());
+            pgCuda->AppendNode(b.mEstimatedPose, scan);
+        }
+        if (k >= 5) msMatch += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        bCuda.AppendScan(pgCuda);
+        const auto t2 = std::chrono::steady_clock::now();
+        if (k >= 5) { msRef += std::chrono::duration<double, std::milli>(t1 - t0).count();
+                      msCuda += std::chrono::duration<double, std::milli>(t2 - t1).count(); }
+        bad += !SamePose(pgRef->LatestNode().Pose(), pgCuda->LatestNode().Pose());
+    }
+    const bool maps = SameBuilders(bRef, bCuda);
+    const RobotPose2D<double>& last = pgCuda->LatestNode().Pose();
+    const double err = std::hypot(last.mX - truth.back().mX, last.mY - truth.back().mY);
+    std::printf("C1 front-end loop, %d frames of 180 beams (default settings): poses %s, maps %s; per frame reference "
+                "%.2f ms, cuda %.2f ms; end position error %.3f m (odometry alone %.3f m), %d lost\n", numOfFrames,
+                bad ? "MISMATCH" : "IDENTICAL", maps ? "IDENTICAL" : "MISMATCH", msRef / (numOfFrames - 5),
+                msCuda / (numOfFrames - 5), err, std::hypot(0.0015, 0.001) * (numOfFrames - 1), lost);
+    const double* tm = bCuda.TimingsMs();
+    const int steady = numOfFrames - 5;
+    std::printf("C1 cuda split per frame after 5 warm-up frames: match %.2f ms; builder: integrate %.2f ms, download %.2f ms, "
+                "host write-back %.2f ms (local map %dx%d, latest map %dx%d)\n", msMatch / steady,
+                (tm[1] - warm[1]) / steady, (tm[2] - warm[2]) / steady, (tm[3] - warm[3]) / steady,
+                bCuda.LocalMaps().back().mMap.NumOfGridCellsX(),
+                bCuda.LocalMaps().back().mMap.NumOfGridCellsY(), bCuda.LatestMap().NumOfGridCellsX(),
+                bCuda.LatestMap().NumOfGridCellsY());
+    failures += (bad != 0) + !maps + (lost != 0);
+    if (json)
+        std::printf("{\"frames\": %d, \"beams\": 180, \"frames_per_s\": %.1f, \"ref_frames_per_s\": %.1f, "
+                    "\"ms_per_frame\": %.3f, \"ref_ms_per_frame\": %.3f, \"ms_match\": %.3f, \"ms_integrate\": %.3f, "
+                    "\"ms_download\": %.3f, \"ms_host_writeback\": %.3f, \"identical\": %s, \"lost\": %d}\n",
+                    numOfFrames, 1e3 * steady / msCuda, 1e3 * steady / msRef, msCuda / steady, msRef / steady,
+                    msMatch / steady, (tm[1] - warm[1]) / steady, (tm[2] - warm[2]) / steady, (tm[3] - warm[3]) / steady,
+                    (bad == 0 && maps) ? "true" : "false", lost);
+    return failures;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && std::string(argv[1]) == "--c1-json")
+        return RunC1(true) ? 1 : 0;
     std::mt19937 g(5);
     const World world(7);
     auto poseGraph = std::make_shared<PoseGraph>();
@@ -325,75 +410,7 @@ int main() {
         if (live.DeviceLatestMap() != nullptr) { std::printf("device latest map must be invalid after ConstructGlobalMap\n"); ++failures; }
     }
 
-    /* ---- config C1: the front end's own frame loop (lidar_graph_slam_frontend.cpp:85-127) with the
-     *      default launcher settings (launcher_settings_default.json:42-50, :175-185) on a 180-beam
-     *      180-degree log with drifting odometry: reference classes vs the device pipeline (builder's
-     *      device-resident latest map -> matcher -> device tail); poses feed back into the maps, so one
-     *      differing bit anywhere compounds ---- */
-    {
-        const int numOfFrames = 150;
-        std::vector<RobotPose2D<double>> truth, odom;
-        for (int k = 0; k < numOfFrames; ++k) {
-            truth.emplace_back(-9.9 + 0.09 * k * std::cos(0.004 * k), -9.8 + 0.5 * std::sin(0.05 * k), 0.1 * std::sin(0.03 * k));
-            odom.emplace_back(truth[k].mX + 0.0015 * k, truth[k].mY - 0.001 * k, truth[k].mTheta + 0.0004 * k);
-        }
-        auto pgRef = std::make_shared<PoseGraph>(), pgCuda = std::make_shared<PoseGraph>();
-        GridMapBuilder bRef(0.05, 64, 10, 20.0, 0.01, 20.0, 0.6, 0.45);
-        GridMapBuilderCuda bCuda(0.05, 64, 10, 20.0, 0.01, 20.0, 0.6, 0.45, 0);
-        ScanMatcherRealTimeCorrelative mRef(cost, 5, 0.2, 0.2, 0.5, 20.0);
-        ScanMatcherRealTimeCorrelativeCuda mCuda(cost, 5, 0.2, 0.2, 0.5, 20.0, 0);
-        mCuda.UseDeviceCost(costParams);
-        double msRef = 0.0, msCuda = 0.0, msMatch = 0.0, warm[4] = { 0.0, 0.0, 0.0, 0.0 };
-        int bad = 0, lost = 0;
-        for (int k = 0; k < numOfFrames; ++k) {
-            if (k == 5) for (int j = 0; j < 4; ++j) warm[j] = bCuda.TimingsMs()[j];   /* allocations settle first */
-            const auto scan = MakeScan(world, truth[k], 180, g, 3.14159265358979323846);
-            const auto t0 = std::chrono::steady_clock::now();
-            if (k == 0) {
-                pgRef->AppendNode(truth[0], scan);
-            } else {
-                const RobotPose2D<double> initial =
-                    Compound(pgRef->LatestNode().Pose(), InverseCompound(odom[k - 1], odom[k]));
-                const ScanMatchingQuery query(GridMapType(bRef.LatestMap()), scan, initial);
-                const ScanMatchingSummary a = mRef.OptimizePose(query);
-                lost += !a.mPoseFound;
-                pgRef->AppendNode(a.mEstimatedPose, scan);
-            }
-            bRef.AppendScan(pgRef);
-            const auto t1 = std::chrono::steady_clock::now();
-            if (k == 0) {
-                pgCuda->AppendNode(truth[0], scan);
-            } else {
-                const RobotPose2D<double> initial =
-                    Compound(pgCuda->LatestNode().Pose(), InverseCompound(odom[k - 1], odom[k]));
-                const ScanMatchingSummary b = mCuda.OptimizePose(bCuda.DeviceLatestMap(), scan, initial,
-                                                                 std::numeric_limits<double>::min());
-                pgCuda->AppendNode(b.mEstimatedPose, scan);
-            }
-            if (k >= 5) msMatch += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
-            bCuda.AppendScan(pgCuda);
-            const auto t2 = std::chrono::steady_clock::now();
-            if (k >= 5) { msRef += std::chrono::duration<double, std::milli>(t1 - t0).count();
-                          msCuda += std::chrono::duration<double, std::milli>(t2 - t1).count(); }
-            bad += !SamePose(pgRef->LatestNode().Pose(), pgCuda->LatestNode().Pose());
-        }
-        const bool maps = SameBuilders(bRef, bCuda);
-        const RobotPose2D<double>& last = pgCuda->LatestNode().Pose();
-        const double err = std::hypot(last.mX - truth.back().mX, last.mY - truth.back().mY);
-        std::printf("C1 front-end loop, %d frames of 180 beams (default settings): poses %s, maps %s; per frame reference "
-                    "%.2f ms, cuda %.2f ms; end position error %.3f m (odometry alone %.3f m), %d lost\n", numOfFrames,
-                    bad ? "MISMATCH" : "IDENTICAL", maps ? "IDENTICAL" : "MISMATCH", msRef / (numOfFrames - 5),
-                    msCuda / (numOfFrames - 5), err, std::hypot(0.0015, 0.001) * (numOfFrames - 1), lost);
-        const double* tm = bCuda.TimingsMs();
-        const int steady = numOfFrames - 5;
-        std::printf("C1 cuda split per frame after 5 warm-up frames: match %.2f ms; builder: integrate %.2f ms, download %.2f ms, "
-                    "host write-back %.2f ms (local map %dx%d, latest map %dx%d)\n", msMatch / steady,
-                    (tm[1] - warm[1]) / steady, (tm[2] - warm[2]) / steady, (tm[3] - warm[3]) / steady,
-                    bCuda.LocalMaps().back().mMap.NumOfGridCellsX(),
-                    bCuda.LocalMaps().back().mMap.NumOfGridCellsY(), bCuda.LatestMap().NumOfGridCellsX(),
-                    bCuda.LatestMap().NumOfGridCellsY());
-        failures += (bad != 0) + !maps + (lost != 0);
-    }
+    failures += RunC1(false);
 
     /* ---- loop detector ---- */
     {

@@ -51,7 +51,7 @@ if ROOT not in sys.path:
 from my_lidar_graph_slam_b200 import synth  # noqa: E402
 
 C2 = dict(low_res=5, range_x=1.0, range_y=1.0, range_theta=1.0471975512, scan_range_max=5.7296)
-METRIC = "pose hypotheses scored/sec (real-time correlative sweep, C2)"
+METRIC = "pose hypotheses scored/sec (C2 correlative sweep)"
 UNIT = "hypotheses/s"
 
 
@@ -173,21 +173,19 @@ def hyps_per_match(res):
 
 def c2_config(M):
     """The `config` object of the C2 line -- shared by both arms so that they describe the same workload."""
-    return {"workload": "C2 real-time correlative sweep: 1081 beams 270 deg, +-0.5 m/+-30 deg at 0.05 m/0.5 deg, "
-                        "lowRes 5, one ~800x800-cell map", "matches_per_step": int(M), **C2}
+    return {"workload": "C2 rtcsm sweep, 1081 beams, +-0.5m/+-30deg @0.05m/0.5deg", "matches_per_step": int(M), **C2}
 
 
 # ---- C4: branch-and-bound loop detection -------------------------------------------------------------
 BB = dict(node_height_max=6, range_x=2.0, range_y=2.0, range_theta=1.0, scan_range_max=20.0,
           score_range_min=0.01, score_range_max=20.0)
-C4_METRIC = "loop-closure queries/sec (branch-and-bound loop detection, C4)"
+C4_METRIC = "loop-closure queries/sec (C4 branch-and-bound)"
 C4_UNIT = "loop queries/s"
 C4_SCANS = 64
 
 
 def c4_config(n_submaps, world):
-    return {"workload": f"C4 branch-and-bound loop detection: {C4_SCANS} query scans x {n_submaps} submaps per step "
-                        "(1081 beams), 7 precompute levels, 2 m x 2 m x 1 rad, threshold 0.6",
+    return {"workload": f"C4 B&B loop detection, {C4_SCANS} scans x {n_submaps} submaps/step, 7 levels, thr 0.6",
             "submaps": int(n_submaps), "scans_per_step": C4_SCANS, **BB}
 
 
@@ -699,10 +697,10 @@ def gather_roofline(achieved_gbps, gather_peak_gbps, sm_mhz, n_gpus, kernel, hbm
     """The `roofline` object of a scoring kernel: bound = the L1 gather path (maps are cache resident)."""
     theo = 148 * 128 * (sm_mhz or 1965.0) * 1e6 / 1e9 * n_gpus       # 148 SMs x 128 B/clk x f_sm
     peak = gather_peak_gbps * n_gpus
-    return {"bound": "l1_gather", "achieved": achieved_gbps, "peak": peak, "unit": "GB/s", "frac": achieved_gbps / peak,
-            "peak_source": "measured in this run: lgs_measure_gather_peak, 32 doubles on 256-B boundaries, L1-friendly walk",
-            "peak_theoretical": theo, "frac_theoretical": achieved_gbps / theo, "kernel": kernel,
-            "hbm": {"peak": hbm_peak * n_gpus, "achieved_over_peak": achieved_gbps / (hbm_peak * n_gpus)},
+    return {"bound": "l1_gather", "achieved": r3(achieved_gbps), "peak": r3(peak), "unit": "GB/s",
+            "frac": r3(achieved_gbps / peak), "peak_kind": "measured (lgs_measure_gather_peak, this run)",
+            "peak_theoretical": r3(theo), "frac_theoretical": r3(achieved_gbps / theo), "kernel": kernel,
+            "hbm": {"peak": r3(hbm_peak * n_gpus), "achieved_over_peak": r3(achieved_gbps / (hbm_peak * n_gpus))},
             "traffic": None}
 
 
@@ -800,9 +798,9 @@ def write_details(n, details):
         pass
 
 
-def r3(x):
+def r3(x, digits=3):
     """3 significant digits (the one-line contract must stay short)."""
-    return None if x is None else float(f"{float(x):.3g}")
+    return None if x is None else float(f"{float(x):.{digits}g}")
 
 
 def run_b200(args, rank, world_size, local_rank):
@@ -947,8 +945,7 @@ def run_b200(args, rank, world_size, local_rank):
                 bad = sum((a.found, a.ix, a.iy, a.it, a.score) != (b.found, b.ix, b.iy, b.it, b.score)
                           for a, b in zip(ref, c2["results"][:ns]))
                 cpu = {"value": r3(sum(hyps_per_match(r) for r in ref) / dt), "unit": UNIT, "cores": cores,
-                       "kind": "reference", "sample": f"first {ns} matches of the step, {cores} threads, {dt:.1f} s; "
-                                                      f"GPU winners/scores identical {ns - bad}/{ns}"}
+                       "kind": "reference", "sample": f"first {ns} matches of the step, {dt:.1f} s; GPU identical {ns - bad}/{ns}"}
         except Exception as e:   # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -970,12 +967,12 @@ def run_b200(args, rank, world_size, local_rank):
 
     if world_size == 1:
         line = {
-            "metric": METRIC, "value": c2["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": c2["ms_per_step"], "higher_is_better": True,
+            "metric": METRIC, "value": r3(c2["value"], 6), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": r3(c2["ms_per_step"], 6), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": c2_config(args.matches),
-            "timing_notes": {"l2": "per-step working set (offsets + score tables) > 126 MB L2: no flush"},
-            "e2e": {"value": c2["e2e"], "unit": UNIT, "h2d_bytes_per_step": c2["h2d"], "d2h_bytes_per_step": c2["d2h"],
+            "l2": "step working set > L2, no flush",
+            "e2e": {"value": r3(c2["e2e"], 6), "unit": UNIT, "h2d_bytes_per_step": c2["h2d"], "d2h_bytes_per_step": c2["d2h"],
                     "sequential_value": r3(c2["e2e_seq"])},
             "gpu_launches": c2["launches"], "clocks": c2["clocks"],
             "roofline": gather_roofline(c2_achieved, gpeak, sm_mhz, 1, "csm_sweep_rows_kernel<4,5>", hbm_peak),
@@ -991,14 +988,12 @@ def run_b200(args, rank, world_size, local_rank):
     else:
         b = c4["batched"]
         line = {
-            "metric": C4_METRIC, "value": b["qps"], "unit": C4_UNIT, "n_gpus": world_size, "steps": max(2, steps_side // 2),
-            "warmup": 3, "ms_per_step": b["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": C4_METRIC, "value": r3(b["qps"], 6), "unit": C4_UNIT, "n_gpus": world_size, "steps": max(2, steps_side // 2),
+            "warmup": 3, "ms_per_step": r3(b["ms"], 6), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": c4_config(args.submaps, world_size),
-            "timing_notes": {"parallelism": f"submap i on rank i mod {world_size}; one persistent kernel per device batch "
-                                            "writes its records into the exchange buffer; in-place NCCL all-gather (lgs_comm)",
-                             "l2": "pyramids 41 MB per submap >> L2: no flush"},
-            "e2e": {"value": b["qps_e2e"], "unit": C4_UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"],
+            "l2": "pyramids >> L2, no flush", "parallelism": f"submap i on rank i%{world_size}, in-place NCCL all-gather of records",
+            "e2e": {"value": r3(b["qps_e2e"], 6), "unit": C4_UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": b["d2h_bytes_per_step"]},
             "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]), "ms": r3(c4["single"]["ms"])},
             "records_sha256": b["sha"], "loops_found": b["found"],
@@ -1019,11 +1014,12 @@ def run_b200(args, rank, world_size, local_rank):
 def run_c1():
     """C1 (BASELINE configs[0]): the default-settings front-end frame loop (180-beam log, correlative match +
     map update per frame) through the C++ adapters beside the reference's own classes
-    (adapters/c1_bench.cpp, built where the reference tree exists)."""
-    exe = os.path.join(ROOT, "adapters", "_build", "c1_bench")
+    (adapters/test_adapters.cpp --c1-json, built where the reference tree exists): frames/s of both, and
+    whether every pose and every map came out identical although the poses feed back into the maps."""
+    exe = os.path.join(ROOT, "adapters", "_build", "test_adapters")
     if not os.path.exists(exe):
-        return {"error": "adapters/_build/c1_bench not built (needs the reference tree at build time)"}
-    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        return {"error": "adapters/_build/test_adapters not built (needs the reference tree at build time)"}
+    p = subprocess.run([exe, "--c1-json"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     if p.returncode != 0:
         return {"error": f"c1_bench exit {p.returncode}: {p.stdout[-200:]} {p.stderr[-200:]}"}
     return json.loads(p.stdout.strip().splitlines()[-1])

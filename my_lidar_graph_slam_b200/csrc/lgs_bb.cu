@@ -38,6 +38,7 @@
 //    trip per level.
 #include <cfloat>
 #include <cmath>
+#include <cstdint>
 
 #include <chrono>
 
@@ -687,7 +688,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     const int H = b->H;
     b->uploaded = false; b->ran = false; b->pendingValidate = false;
     b->nq = n;
-    b->qs.assign(n, BbQuery{});
+    b->qs.resize(n);                  // every field is written below (template copy + scan-dependent part)
     b->us.clear();
     b->fixups.assign(n, 0);
     b->hAngles.clear(); b->hRanges.clear();
@@ -699,63 +700,92 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     std::vector<int> scanToUnique(std::max(scans->n_scans, 1), -1);
     std::vector<double> scanMaxR(std::max(scans->n_scans, 1), 0.0);
     std::vector<char> haveMaxR(std::max(scans->n_scans, 1), 0);
+    // Host preparation is on the end-to-end path of every step, so everything that depends only on the
+    // submap (geometry, level pointers) or only on the (scan, resolution) (search step, window, usable
+    // beams) is derived once and copied: a 64-scan x 63-submap share is 4032 pairs but 63 + 64 of those.
+    struct PyrInfo { const lgs_pyramid* pyr; BbQuery tmpl; };
+    std::vector<PyrInfo> pyrCache;
+    pyrCache.reserve(64);
+    std::vector<int> pyrSlot(1024, -1);                // open-addressed pointer hash -> pyrCache index
+    auto pyrLookup = [&](const lgs_pyramid* pyr) -> int {
+        size_t mask = pyrSlot.size() - 1;
+        size_t h = ((size_t)reinterpret_cast<uintptr_t>(pyr) >> 4) * 0x9E3779B97F4A7C15ull;
+        for (size_t k = h & mask;; k = (k + 1) & mask) {
+            if (pyrSlot[k] < 0) return -(int)k - 1;
+            if (pyrCache[pyrSlot[k]].pyr == pyr) return pyrSlot[k];
+        }
+    };
     for (int q = 0; q < n; ++q) {
         const int sq = pairScan ? pairScan[q] : q;
         const int b0 = scans->beam_begin[sq], b1 = scans->beam_begin[sq + 1];
         const int nb = b1 - b0;
         if (nb <= 0) return lgs_fail(c, LGS_ERR_INVALID, "bb: scan %d has no beams", q);
         const lgs_pyramid* pyr = pyramids[q];
-        if (!pyr || lgs_pyramid_levels(pyr) < H + 1)
-            return lgs_fail(c, LGS_ERR_INVALID, "bb: query %d needs a pyramid with %d levels", q, H + 1);
-        const lgs_grid* g0 = lgs_pyramid_level(pyr, 0);
-        lgs_pyramid_note_user(pyr, c);
-        if (g0->ctx->device != c->device)
-            return lgs_fail(c, LGS_ERR_INVALID, "bb: pyramid of query %d lives on another device", q);
-        BbQuery& d = b->qs[q];
-        d.minX = g0->min_x; d.minY = g0->min_y; d.res = g0->res; d.invRes = 1.0 / g0->res;
-        d.nx = g0->nx; d.ny = g0->ny; d.pitch = g0->pitch;
-        d.offX = g0->off_x; d.offY = g0->off_y;
-        for (int h = 0; h <= H; ++h) d.level[h] = lgs_pyramid_level(pyr, h)->origin();
-        // ComputeSearchStep (scan_matcher_branch_bound.cpp:178-197)
-        if (!haveMaxR[sq]) {           // std::max_element over the scan, once per scan
-            double m = scans->ranges[b0];
-            for (int i = b0 + 1; i < b1; ++i) m = std::max(m, scans->ranges[i]);
-            scanMaxR[sq] = m;
-            haveMaxR[sq] = 1;
+        int slot = pyr ? pyrLookup(pyr) : 0;
+        if (!pyr || slot < 0) {
+            if (!pyr || lgs_pyramid_levels(pyr) < H + 1)
+                return lgs_fail(c, LGS_ERR_INVALID, "bb: query %d needs a pyramid with %d levels", q, H + 1);
+            const lgs_grid* g0 = lgs_pyramid_level(pyr, 0);
+            lgs_pyramid_note_user(pyr, c);
+            if (g0->ctx->device != c->device)
+                return lgs_fail(c, LGS_ERR_INVALID, "bb: pyramid of query %d lives on another device", q);
+            PyrInfo info;
+            info.pyr = pyr;
+            BbQuery& t = info.tmpl;
+            t = BbQuery{};
+            t.minX = g0->min_x; t.minY = g0->min_y; t.res = g0->res; t.invRes = 1.0 / g0->res;
+            t.nx = g0->nx; t.ny = g0->ny; t.pitch = g0->pitch;
+            t.offX = g0->off_x; t.offY = g0->off_y;
+            for (int h = 0; h <= H; ++h) t.level[h] = lgs_pyramid_level(pyr, h)->origin();
+            if (2 * (pyrCache.size() + 1) > pyrSlot.size()) {          // grow + rehash
+                std::vector<int> old;
+                old.swap(pyrSlot);
+                pyrSlot.assign(old.size() * 4, -1);
+                for (int idx : old) if (idx >= 0) pyrSlot[(size_t)(-pyrLookup(pyrCache[idx].pyr) - 1)] = idx;
+                slot = pyrLookup(pyr);
+            }
+            pyrSlot[(size_t)(-slot - 1)] = (int)pyrCache.size();
+            slot = (int)pyrCache.size();
+            pyrCache.push_back(info);
         }
-        const double maxR = scanMaxR[sq];
-        const double maxRange = std::min(maxR, p.scan_range_max);
-        const double th = d.res / maxRange;
-        const double stepX = d.res, stepY = d.res;
-        const double stepT = std::acos(1.0 - 0.5 * th * th);
-        d.winX = static_cast<int>(std::ceil(0.5 * p.range_x / stepX));                 // :68-73
-        d.winY = static_cast<int>(std::ceil(0.5 * p.range_y / stepY));
-        d.winT = static_cast<int>(std::ceil(0.5 * p.range_theta / stepT));
-        if (!(stepT > 0.0) || d.winT < 0 || d.winT > (1 << 20))
-            return lgs_fail(c, LGS_ERR_INVALID, "bb: scan %d gives stepTheta=%g winTheta=%d", q, stepT, d.winT);
-        if (d.winX + 2 * winSizeMax > 32000 || d.winY + 2 * winSizeMax > 32000)
-            return lgs_fail(c, LGS_ERR_INVALID, "bb: search window too large for 16-bit node offsets");
-        d.nT = 2 * d.winT + 1;
-        d.nTpad = (d.nT + 3) / 4 * 4;
-        d.nrx = (2 * d.winX) / winSizeMax + 1;                                         // :85-86
-        d.nry = (2 * d.winY) / winSizeMax + 1;
-        const double thr = normThr ? normThr[q] : DBL_MIN;
-        d.thrAbs = thr * static_cast<double>(static_cast<size_t>(nb));                 // :75-76
-        // ScorePixelAccurate range filter (score_function_pixel_accurate.cpp:27-41)
-        const double sMin = scans->range_min ? scans->range_min[sq] : 0.0;
-        const double sMax = scans->range_max ? scans->range_max[sq] : HUGE_VAL;
-        const double minRange = std::max(p.score_range_min, sMin);
-        const double maxRangeS = std::min(p.score_range_max, sMax);
+        BbQuery& d = b->qs[q];
+        d = pyrCache[slot].tmpl;
         int uidx = scanToUnique[sq];
-        if (uidx >= 0 && (b->us[uidx].stepT != stepT || b->us[uidx].invRes != d.invRes)) uidx = -1;   // other map resolution
+        if (uidx >= 0 && b->us[uidx].invRes != d.invRes) uidx = -1;        // another map resolution
         if (uidx < 0) {
+            // ComputeSearchStep (scan_matcher_branch_bound.cpp:178-197)
+            if (!haveMaxR[sq]) {           // std::max_element over the scan, once per scan
+                double m = scans->ranges[b0];
+                for (int i = b0 + 1; i < b1; ++i) m = std::max(m, scans->ranges[i]);
+                scanMaxR[sq] = m;
+                haveMaxR[sq] = 1;
+            }
+            const double maxRange = std::min(scanMaxR[sq], p.scan_range_max);
+            const double th = d.res / maxRange;
+            const double stepX = d.res, stepY = d.res;
+            const double stepT = std::acos(1.0 - 0.5 * th * th);
             BbScan u{};
+            u.winX = static_cast<int>(std::ceil(0.5 * p.range_x / stepX));                 // :68-73
+            u.winY = static_cast<int>(std::ceil(0.5 * p.range_y / stepY));
+            u.winT = static_cast<int>(std::ceil(0.5 * p.range_theta / stepT));
+            if (!(stepT > 0.0) || u.winT < 0 || u.winT > (1 << 20))
+                return lgs_fail(c, LGS_ERR_INVALID, "bb: scan %d gives stepTheta=%g winTheta=%d", q, stepT, u.winT);
+            if (u.winX + 2 * winSizeMax > 32000 || u.winY + 2 * winSizeMax > 32000)
+                return lgs_fail(c, LGS_ERR_INVALID, "bb: search window too large for 16-bit node offsets");
+            u.nT = 2 * u.winT + 1;
+            u.nTpad = (u.nT + 3) / 4 * 4;
+            u.nrx = (2 * u.winX) / winSizeMax + 1;                                         // :85-86
+            u.nry = (2 * u.winY) / winSizeMax + 1;
+            // ScorePixelAccurate range filter (score_function_pixel_accurate.cpp:27-41)
+            const double sMin = scans->range_min ? scans->range_min[sq] : 0.0;
+            const double sMax = scans->range_max ? scans->range_max[sq] : HUGE_VAL;
+            const double minRange = std::max(p.score_range_min, sMin);
+            const double maxRangeS = std::min(p.score_range_max, sMax);
             u.sx = scans->sensor_pose[3 * sq]; u.sy = scans->sensor_pose[3 * sq + 1];
             u.st = scans->sensor_pose[3 * sq + 2];
-            u.stepT = stepT; u.winT = d.winT; u.nT = d.nT; u.nTpad = d.nTpad;
+            u.stepT = stepT;
             u.invRes = d.invRes;
             u.originX = std::floor(u.sx * d.invRes); u.originY = std::floor(u.sy * d.invRes);
-            u.nrx = d.nrx; u.nry = d.nry; u.winX = d.winX; u.winY = d.winY;
             u.qBegin = 0; u.qCount = 0;
             u.beamBegin = (int)b->hAngles.size();
             double reach = 0.0;
@@ -776,15 +806,21 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
             b->maxReachCells = std::max(b->maxReachCells, reach * d.invRes);
             uidx = (int)b->us.size();
             b->us.push_back(u);
+            // a scan matched against maps of several resolutions keeps one entry per resolution; the
+            // lookup remembers the last one (maps of one resolution are the rule)
             scanToUnique[sq] = uidx;
         }
+        const BbScan& us = b->us[uidx];
+        d.winX = us.winX; d.winY = us.winY; d.winT = us.winT; d.nT = us.nT; d.nTpad = us.nTpad;
+        d.nrx = us.nrx; d.nry = us.nry;
+        const double thr = normThr ? normThr[q] : DBL_MIN;
+        d.thrAbs = thr * static_cast<double>(static_cast<size_t>(nb));                 // :75-76
         d.scan = uidx;
-        d.nUse = b->us[uidx].nUse;
+        d.nUse = us.nUse;
         d.tabBegin = nTab;
         nTab += (long long)d.nUse * d.nTpad;
         {   // 12.20 fixed-point origin of the query's map relative to the scan origin (+ the window offset of a
             // banded map), split into fraction bits and whole cells (lgs_bb_run.cu)
-            const BbScan& us = b->us[uidx];
             const long long mx = std::llrint((d.minX * d.invRes - us.originX) * 1048576.0) + ((long long)d.offX << 20);
             const long long my = std::llrint((d.minY * d.invRes - us.originY) * 1048576.0) + ((long long)d.offY << 20);
             d.MloX = (int)(mx & 0xfffff); d.MhiX = (int)(mx >> 20);
