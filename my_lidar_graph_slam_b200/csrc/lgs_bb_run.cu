@@ -137,21 +137,23 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
     const unsigned gx1 = (unsigned)dq->nx + 1u, gy1 = (unsigned)dq->ny + 1u;
     const double* __restrict__ lvl = dq->level[h] - pitch - 1;        // cell (-1, -1) of the padded level
     const int nb = n.active ? dq->nUse : 0;
-    const unsigned E = a.edgeUnits, E2 = 2u * a.edgeUnits;
+    // near-edge test on the 20 fraction bits moved to the top of the word: ((d << 12) + (E << 12)) < (2E << 12)
+    // in wrapping unsigned arithmetic -- one shift-add (LEA) per axis instead of add + mask
+    const unsigned E = a.edgeUnits << 12, E2 = (2u * a.edgeUnits) << 12;
     double acc = 0.0;
 
     // offset of the beam's cell; `near` keeps the smallest distance-to-edge measure seen so far
     // (one compare per round instead of one per beam and axis)
     auto offset = [&](const int2 hp, unsigned& near) -> unsigned {
         const int dx = hp.x - mlx, dy = hp.y - mly;
-        near = min(near, min(((unsigned)dx + E) & 0xfffffu, ((unsigned)dy + E) & 0xfffffu));
+        near = min(near, min(((unsigned)dx << 12) + E, ((unsigned)dy << 12) + E));
         const unsigned ix = min((unsigned)((dx >> 20) - cx), gx1);
         const unsigned iy = min((unsigned)((dy >> 20) - cy), gy1);
         return iy * (unsigned)pitch + ix;
     };
     auto is_near = [&](const int2 hp) -> bool {
         const int dx = hp.x - mlx, dy = hp.y - mly;
-        return ((((unsigned)dx + E) & 0xfffffu) < E2) | ((((unsigned)dy + E) & 0xfffffu) < E2);
+        return ((((unsigned)dx << 12) + E) < E2) | ((((unsigned)dy << 12) + E) < E2);
     };
     // near-edge beam: the CPU's own cell, + 1 per axis like `offset`
     auto exact = [&](int beam) -> unsigned {

@@ -2,7 +2,7 @@
 of the persistent kernel, and the effect of its build / residency / cost-model options.
 
   BB_SUBMAPS (500)  submaps          BB_SCANS (1)  query scans per batch
-  BB_VARIANTS ("0,1")  kernel builds to try      BB_REPS (20)
+  BB_BLOCKS ("0")  CTAs per SM to try (0 = occupancy limit)      BB_REPS (20)
 """
 import os
 import sys
@@ -17,7 +17,7 @@ from my_lidar_graph_slam_b200 import capi, synth  # noqa: E402
 NM = int(os.environ.get("BB_SUBMAPS", 500))
 NS = int(os.environ.get("BB_SCANS", 1))
 REPS = int(os.environ.get("BB_REPS", 20))
-VARIANTS = [int(v) for v in os.environ.get("BB_VARIANTS", "0,1").split(",")]
+BLOCKS = [int(v) for v in os.environ.get("BB_BLOCKS", "0").split(",")]
 EXTRA = os.environ.get("BB_OPTS", "")      # e.g. "bb_cost_g1=50,bb_cost_g4=20"
 
 ctx = capi.Context(0)
@@ -84,11 +84,9 @@ ctx.set_option("bb_sync", 0)
 for kv in [x for x in EXTRA.split(",") if x]:
     k, v = kv.split("=")
     ctx.set_option(k, float(v))
-for var in VARIANTS:
-    ctx.set_option("bb_variant", var)
-    for bps in ([0] if var else [0, 1]):
-        ctx.set_option("bb_blocks_per_sm", bps)
-        found, res = measure(f"device-only variant {var} blocks/SM {bps or 'max'}")
-        same = all(np.array_equal(res[f], res_ref[f]) for f in ("found", "ix", "iy", "it", "score"))
-        print(f"    found {found} (exact path {found_ref}); identical to the exact path: {same}", flush=True)
+for bps in BLOCKS:
+    ctx.set_option("bb_blocks_per_sm", bps)
+    found, res = measure(f"device-only, CTAs/SM {bps or 'max'}")
+    same = all(np.array_equal(res[f], res_ref[f]) for f in ("found", "ix", "iy", "it", "score"))
+    print(f"    found {found} (exact path {found_ref}); identical to the exact path: {same}", flush=True)
 ctx.close()
