@@ -666,6 +666,11 @@ def download_records(ctx: Context, device_ptr: int, n: int) -> np.ndarray:
     return out[:n]
 
 
+def download_into(ctx: Context, device_ptr: int, out: np.ndarray):
+    """Device -> an existing (ideally page-locked) host array."""
+    ctx.check(lib().lgs_device_download(ctx.h, vp(device_ptr), out.ctypes.data_as(vp), out.nbytes))
+
+
 # ---- occupancy-grid integration + host geometry helpers ------------------------------------------
 class HitBatch(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("sensor_xy", c_dp), ("hit_begin", c_ip), ("hit_xy", c_dp)]

@@ -113,6 +113,20 @@ class RecordExchange:
         self.buf = capi.device_alloc(ctx, world * self.per * RECORD.itemsize)
         self.first = np.concatenate([[0], np.cumsum([c + 1 for c in self.counts[rank]])])[:-1] + rank * self.per
         self._attached = {}
+        # page-locked landing buffer of the one download per step, and the positions of records / status
+        # records in it (a pure function of the counts); the order of the ids is learnt from the first gather
+        self.host = np.zeros(world * self.per, dtype=RECORD)
+        capi.pin(ctx, self.host)
+        rec_pos, status_pos = [], []
+        for r, seg in enumerate(self.counts):
+            pos = r * self.per
+            for cnt in seg:
+                rec_pos.append(np.arange(pos, pos + cnt))
+                status_pos.append(pos + cnt)
+                pos += cnt + 1
+        self.rec_pos = np.concatenate(rec_pos) if rec_pos else np.zeros(0, dtype=np.int64)
+        self.status_pos = np.asarray(status_pos, dtype=np.int64)
+        self.perm = None
 
     @property
     def d2h_bytes(self) -> int:
@@ -131,8 +145,14 @@ class RecordExchange:
         from . import capi
         if self.comm is not None:
             self.comm.all_gather_records(self.buf, self.per)
-        raw = capi.download_records(self.ctx, self.buf, self.world * self.per)
-        return assemble(raw, self.counts, self.per, self.n_items)
+        capi.download_into(self.ctx, self.buf, self.host)
+        ok = bool((self.host["found"][self.status_pos] == 1).all())
+        if self.perm is None:               # global id -> position in the gathered buffer, fixed for this exchange
+            ids = self.host["submap"][self.rec_pos]
+            perm = np.empty(self.n_items, dtype=np.int64)
+            perm[ids] = self.rec_pos
+            self.perm = perm
+        return self.host[self.perm], ok
 
     def finish(self, batches):
         """gather(); if any rank's run has to be repeated exactly (its status record says so), every rank
@@ -156,6 +176,7 @@ class RecordExchange:
     def close(self):
         from . import capi
         if self.buf:
+            capi.unpin(self.ctx, self.host)
             capi.device_free(self.ctx, self.buf)
             self.buf = 0
 
