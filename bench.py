@@ -956,7 +956,7 @@ def run_b200(args, rank, world_size, local_rank):
                                                               "inits", "results")}
     for name, keys in (("c5", ("precompute_ms", "precompute_hbm_frac", "qps", "qps_e2e", "found", "sha")),
                        ("c3", ("scans_per_s", "cell_updates_per_s")), ("matcher_tail", ("tails_per_s",)),
-                       ("grid_search", ("hypotheses_per_s",)), ("c1", ("frames_per_s", "ref_frames_per_s", "identical"))):
+                       ("grid_search", ("hypotheses_per_s",)), ("c1", ("frames_per_s", "ref_frames_per_s", "identical", "launcher_frames_per_s", "launcher_ref_frames_per_s", "launcher_identical"))):
         d = details.get(name)
         if isinstance(d, dict):
             extra[name] = {k: (r3(d[k]) if isinstance(d.get(k), float) else d.get(k)) for k in keys if k in d} \
@@ -1013,17 +1013,51 @@ def run_b200(args, rank, world_size, local_rank):
 
 
 def run_c1():
-    """C1 (BASELINE configs[0]): the default-settings front-end frame loop (180-beam log, correlative match +
-    map update per frame) through the C++ adapters beside the reference's own classes
-    (adapters/test_adapters.cpp --c1-json, built where the reference tree exists): frames/s of both, and
-    whether every pose and every map came out identical although the poses feed back into the maps."""
+    """C1 (BASELINE configs[0]): default launcher settings on a synthetic 180-beam log.
+    (1) adapters/test_adapters --c1-json: the front end's frame loop (correlative match + map update per
+        frame) through the C++ adapters beside the reference's own classes: frames/s of both, and whether
+        every pose and every map came out identical although the poses feed back into the maps;
+    (2) adapters/_build/lgs_slam_launch: the same configuration from a CARMEN log file and
+        launcher_settings_default.json through the reference's own reader, LidarGraphSlam, front end and
+        back end -- once with the unchanged settings (CPU matcher and loop detector), once with the B200
+        type strings; the written pose graphs must be the same."""
+    import tempfile
+    out = {}
     exe = os.path.join(ROOT, "adapters", "_build", "test_adapters")
     if not os.path.exists(exe):
         return {"error": "adapters/_build/test_adapters not built (needs the reference tree at build time)"}
     p = subprocess.run([exe, "--c1-json"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     if p.returncode != 0:
-        return {"error": f"c1_bench exit {p.returncode}: {p.stdout[-200:]} {p.stderr[-200:]}"}
-    return json.loads(p.stdout.strip().splitlines()[-1])
+        return {"error": f"test_adapters --c1-json exit {p.returncode}: {p.stdout[-200:]} {p.stderr[-200:]}"}
+    out.update(json.loads(p.stdout.strip().splitlines()[-1]))
+    launch = os.path.join(ROOT, "adapters", "_build", "lgs_slam_launch")
+    settings = os.path.join(ROOT, "tests", "golden", "launcher_settings_default.json")
+    if os.path.exists(launch):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_carmen_log
+        with tempfile.TemporaryDirectory() as tmp:
+            log = os.path.join(tmp, "c1.log")
+            make_carmen_log.write_log(log, 600, 5)
+            runs = {}
+            for name, sets in (("cpu", []), ("b200", ["Frontend.LocalSlam.ScanMatcherType=RealTimeCorrelativeCuda",
+                                                      "Backend.LoopDetectorType=BranchBoundCuda"])):
+                cmd = [launch, log, settings, os.path.join(tmp, name), "--set", "Backend.PoseGraphOptimizerType=None"]
+                for kv in sets:
+                    cmd += ["--set", kv]
+                q = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+                if q.returncode != 0:
+                    out["launcher_error"] = f"{name}: exit {q.returncode}: {q.stderr[-200:]}"
+                    return out
+                runs[name] = json.loads(q.stdout.strip().splitlines()[-1])
+            same = all(open(os.path.join(tmp, "cpu" + ext)).read() == open(os.path.join(tmp, "b200" + ext)).read()
+                       for ext in (".poses.txt", ".edges.txt"))
+            out["launcher"] = {"frames": runs["b200"]["frames"], "loop_edges": runs["b200"]["loop_edges"],
+                               "frames_per_s": runs["b200"]["frames_per_s"], "ref_frames_per_s": runs["cpu"]["frames_per_s"],
+                               "pose_graph_identical": bool(same)}
+            out["launcher_frames_per_s"] = runs["b200"]["frames_per_s"]
+            out["launcher_ref_frames_per_s"] = runs["cpu"]["frames_per_s"]
+            out["launcher_identical"] = bool(same)
+    return out
 
 
 def main():
