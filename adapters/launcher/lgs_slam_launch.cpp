@@ -12,6 +12,14 @@
  * so config C1 (default settings on a 180-beam log) runs end to end from a log file and a settings
  * file, with the correlative front end on the CPU (default JSON unchanged) or on the GPU (one key).
  *
+ * Back end: by default its iterations (loop search -> Detect -> AppendLoopClosingEdges -> Optimize ->
+ * AfterLoopClosure, lidar_graph_slam_backend.cpp:21-61) run on the main thread at the frames where the
+ * front end notifies it (lidar_graph_slam_frontend.cpp:127-130), so a run is reproducible and two runs
+ * with different matcher / detector types can be compared pose by pose; AfterLoopClosure is applied once
+ * the next frame has been appended, because it asserts that a newer odometry edge exists
+ * (lidar_graph_slam.cpp:341-347 -- in slam_launch the optimiser is slow enough for that to hold).
+ * `--async-backend` runs the reference's own back-end thread instead (StartBackend / StopBackend).
+ *
  * Differences from slam_launch, all stated on stderr when they apply:
  *   - no gnuplot GUI and no PNG output: the result is written as text, <output>.poses.txt (pose-graph
  *     nodes, 17 significant digits) and <output>.edges.txt;
@@ -202,7 +210,16 @@ std::shared_ptr<Mapping::PoseGraphOptimizer> CreateOptimizer(const std::string& 
          "pass --set Backend.PoseGraphOptimizerType=None (loop-closing edges are still detected and appended)");
 }
 
-std::shared_ptr<Mapping::LidarGraphSlam> CreateLidarGraphSlam(const Ptree& settings)
+/* The back-end parts, kept by the launcher as well so that it can run an iteration synchronously */
+struct BackendParts
+{
+    std::shared_ptr<Mapping::PoseGraphOptimizer> mOptimizer;
+    std::shared_ptr<Mapping::LoopSearcher>       mSearcher;
+    std::shared_ptr<Mapping::LoopDetector>       mDetector;
+    int                                          mLoopDetectionInterval;
+};
+
+std::shared_ptr<Mapping::LidarGraphSlam> CreateLidarGraphSlam(const Ptree& settings, BackendParts& parts)
 {
     const Ptree& top = settings.get_child("LidarGraphSlam");
     /* grid map builder (slam_launcher.cpp:711-737) */
@@ -244,6 +261,7 @@ std::shared_ptr<Mapping::LidarGraphSlam> CreateLidarGraphSlam(const Ptree& setti
     auto detector = CreateLoopDetector(settings, back.get("LoopDetectorType", "GridSearch"),
                                        back.get("LoopDetectorConfigGroup", "LoopDetectorGridSearch"));
     auto backend = std::make_shared<Mapping::LidarGraphSlamBackend>(optimizer, searcher, detector);
+    parts = BackendParts { optimizer, searcher, detector, front.get("LoopDetectionInterval", 10) };
     return std::make_shared<Mapping::LidarGraphSlam>(frontend, backend, builder, poseGraph);
 }
 
@@ -253,9 +271,12 @@ int main(int argc, char** argv)
 {
     std::vector<std::string> positional;
     std::vector<std::pair<std::string, std::string>> overrides;
+    bool asyncBackend = false;
     for (int k = 1; k < argc; ++k) {
         const std::string arg = argv[k];
-        if (arg == "--set" && k + 1 < argc) {
+        if (arg == "--async-backend") {
+            asyncBackend = true;
+        } else if (arg == "--set" && k + 1 < argc) {
             const std::string kv = argv[++k];
             const std::size_t eq = kv.find('=');
             if (eq == std::string::npos)
@@ -267,7 +288,7 @@ int main(int argc, char** argv)
     }
     if (positional.size() < 2) {
         std::cerr << "Usage: " << argv[0] << " <Carmen log file name> <JSON settings file name> [output name] "
-                     "[--set Key=Value ...]" << std::endl;
+                     "[--set Key=Value ...] [--async-backend]" << std::endl;
         return EXIT_FAILURE;
     }
     const std::string output = positional.size() > 2 ? positional[2] : std::string("lgs_slam_launch_out");
@@ -297,24 +318,59 @@ int main(int argc, char** argv)
         std::cerr << "lgs_slam_launch: Launcher.GuiEnabled is ignored (no gnuplot here)" << std::endl;
 
     std::shared_ptr<Mapping::LidarGraphSlam> slam;
+    BackendParts backendParts;
     try {
-        slam = CreateLidarGraphSlam(settings);
+        slam = CreateLidarGraphSlam(settings, backendParts);
     } catch (const std::exception& e) {
         Fail(e.what());
     }
 
-    slam->StartBackend();
-    int numOfScans = 0, numOfFrames = 0;
+    if (asyncBackend)
+        slam->StartBackend();
+    int numOfScans = 0, numOfFrames = 0, numOfDetects = 0;
+    /* synchronous back end: the optimised nodes of an iteration wait here until the next frame exists */
+    bool closurePending = false;
+    std::vector<Mapping::PoseGraph::Node> closureNodes;
     const auto t0 = std::chrono::steady_clock::now();
     for (const auto& sensorData : logData) {
         auto scanData = std::dynamic_pointer_cast<const Sensor::ScanData<double>>(sensorData);
         if (scanData == nullptr)
             continue;
         ++numOfScans;
-        numOfFrames += slam->ProcessScan(scanData, scanData->OdomPose()) ? 1 : 0;
+        if (!slam->ProcessScan(scanData, scanData->OdomPose()))
+            continue;
+        ++numOfFrames;
+        if (asyncBackend)
+            continue;
+        if (closurePending) {
+            slam->AfterLoopClosure(closureNodes);
+            closurePending = false;
+        }
+        /* the front end's own condition for NotifyBackend, on the count before its increment */
+        const int count = slam->ProcessCount() - 1;
+        if (count <= backendParts.mLoopDetectionInterval || count % backendParts.mLoopDetectionInterval != 0)
+            continue;
+        /* one iteration of LidarGraphSlamBackend::Run (lidar_graph_slam_backend.cpp:27-60) */
+        auto candidates = backendParts.mSearcher->Search(slam->GetLoopSearchHint());
+        auto queries = slam->GetLoopDetectionQueries(candidates);
+        Mapping::LoopDetectionResultVector results;
+        backendParts.mDetector->Detect(queries, results);
+        ++numOfDetects;
+        slam->UpdatePrecomputedGridMaps(queries);
+        if (results.empty())
+            continue;
+        slam->AppendLoopClosingEdges(results);
+        std::vector<Mapping::PoseGraph::Edge> closureEdges;
+        closureNodes.clear();
+        slam->GetPoseGraph(closureNodes, closureEdges);
+        backendParts.mOptimizer->Optimize(closureNodes, closureEdges);
+        closurePending = true;
     }
     const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    slam->StopBackend();
+    if (asyncBackend)
+        slam->StopBackend();
+    else if (closurePending)
+        std::cerr << "lgs_slam_launch: the log ended before the last loop closure could be applied" << std::endl;
 
     /* result as text instead of MapSaver's PNG / JSON (map_saver.cpp:413-535) */
     std::vector<Mapping::PoseGraph::Node> nodes;
@@ -341,9 +397,10 @@ int main(int argc, char** argv)
     std::size_t loops = 0;
     for (const auto& e : edges) loops += e.IsOdometricConstraint() ? 0 : 1;
     std::printf("{\"scans\": %d, \"frames\": %d, \"seconds\": %.3f, \"frames_per_s\": %.2f, \"nodes\": %zu, "
-                "\"edges\": %zu, \"loop_edges\": %zu, \"latest_map_cells\": [%d, %d], \"scan_matcher\": \"%s\", "
-                "\"loop_detector\": \"%s\"}\n", numOfScans, numOfFrames, seconds, numOfFrames / seconds,
-                nodes.size(), edges.size(), loops, latest.NumOfGridCellsX(), latest.NumOfGridCellsY(),
+                "\"edges\": %zu, \"loop_edges\": %zu, \"detect_calls\": %d, \"latest_map_cells\": [%d, %d], "
+                "\"scan_matcher\": \"%s\", \"loop_detector\": \"%s\"}\n", numOfScans, numOfFrames, seconds,
+                numOfFrames / seconds, nodes.size(), edges.size(), loops, numOfDetects,
+                latest.NumOfGridCellsX(), latest.NumOfGridCellsY(),
                 settings.get("Frontend.LocalSlam.ScanMatcherType", "HillClimbing").c_str(),
                 settings.get("Backend.LoopDetectorType", "GridSearch").c_str());
     return EXIT_SUCCESS;
