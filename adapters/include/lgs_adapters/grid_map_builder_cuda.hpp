@@ -52,11 +52,20 @@ public:
     /* Construct the global map */
     GridMapType ConstructGlobalMap(const std::shared_ptr<PoseGraph>& poseGraph);
 
-    inline const std::vector<LocalMapInfo>& LocalMaps() const { return this->mLocalMaps; }
-    inline LocalMapInfo& LocalMapAt(int localMapIdx) { return this->mLocalMaps.at(localMapIdx); }
+    /* The host maps.  With lazy host maps (SetLazyHostMaps) these accessors first bring the host copies
+     * up to date with the device (FlushHostMaps); what they return is always identical to the CPU builder's */
+    inline const std::vector<LocalMapInfo>& LocalMaps() const { this->FlushHostMaps(); return this->mLocalMaps; }
+    inline LocalMapInfo& LocalMapAt(int localMapIdx) { this->FlushHostMaps(); return this->mLocalMaps.at(localMapIdx); }
     inline const LocalMapInfo& LocalMapAt(int localMapIdx) const
-    { return this->mLocalMaps.at(localMapIdx); }
-    inline const GridMapType& LatestMap() const { return this->mLatestMap; }
+    { this->FlushHostMaps(); return this->mLocalMaps.at(localMapIdx); }
+    inline const GridMapType& LatestMap() const { this->FlushHostMaps(); return this->mLatestMap; }
+
+    /* Lazy host maps: AppendScan only integrates on the device and remembers which cells of the host maps
+     * are stale; they are downloaded and written back when a host reader asks (the accessors above, a new
+     * local map, ConstructGlobalMap) instead of after every frame.  A front end that hands the device map
+     * to the matcher (DeviceLatestMap) reads the host maps only when the loop detector runs. */
+    void SetLazyHostMaps(bool lazy) { if (!lazy) this->FlushHostMaps(); this->mLazy = lazy; }
+    void FlushHostMaps() const;
     inline double AccumTravelDist() const { return this->mAccumTravelDist; }
     inline int LatestScanIdxMin() const { return this->mLatestScanIdxMin; }
     inline int LatestScanIdxMax() const { return this->mLatestScanIdxMax; }
@@ -84,9 +93,11 @@ private:
                                int nodeIdxMin, int nodeIdxMax);
     /* (Re)create `grid` so that it mirrors the geometry of `map`, all cells unknown */
     void MirrorGeometry(lgs_grid*& grid, const GridMapType& map);
-    void ReserveDense(std::size_t cells);
-    /* Integrate the staged hits into `grid`, then copy the cells [x0, x1] x [y0, y1] into `map` */
-    void IntegrateAndSync(lgs_grid* grid, GridMapType& map, int x0, int y0, int x1, int y1);
+    void ReserveDense(std::size_t cells) const;
+    /* Integrate the staged hits into `grid` */
+    void Integrate(lgs_grid* grid);
+    /* Copy the cells [x0, x1] x [y0, y1] of `grid` into `map` (download + patch write-back) */
+    void SyncRegion(const lgs_grid* grid, GridMapType& map, int x0, int y0, int x1, int y1) const;
 
     const double              mResolution;
     const int                 mPatchSize;
@@ -111,11 +122,15 @@ private:
     std::vector<double>       mSensorXY;     /* staged lgs_hit_batch */
     std::vector<int>          mHitBegin;
     std::vector<double>       mHitXY;
-    std::vector<double>       mDense;        /* page-locked download staging */
-    bool                      mDensePinned;
+    mutable std::vector<double> mDense;      /* page-locked download staging */
+    mutable bool              mDensePinned;
+    bool                      mLazy;              /* host maps are synchronised on demand */
+    mutable bool              mLocalPending;      /* cells mLocalBox of the current local map are stale on the host */
+    mutable int               mLocalBox[4];       /* x0, y0, x1, y1 */
+    mutable bool              mLatestPending;     /* the host latest map is stale (all of it) */
     bool                      mScratchIsLatest;   /* mDevScratch == mLatestMap */
     long long                 mNumOfUpdates;
-    double                    mTimingsMs[4];
+    mutable double            mTimingsMs[4];
 };
 
 } /* namespace Mapping */

@@ -63,6 +63,10 @@ GridMapBuilderCuda::GridMapBuilderCuda(
     mDevLocal(nullptr),
     mDevScratch(nullptr),
     mDensePinned(false),
+    mLazy(false),
+    mLocalPending(false),
+    mLocalBox { 0, 0, -1, -1 },
+    mLatestPending(false),
     mScratchIsLatest(false),
     mNumOfUpdates(0),
     mTimingsMs { 0.0, 0.0, 0.0, 0.0 }
@@ -88,7 +92,12 @@ bool GridMapBuilderCuda::AppendScan(const std::shared_ptr<PoseGraph>& poseGraph)
 
 void GridMapBuilderCuda::AfterLoopClosure(const std::shared_ptr<PoseGraph>& poseGraph)
 {
-    /* every local map is rebuilt from the corrected poses (grid_map_builder.cpp:62-80) */
+    /* every local map is rebuilt from the corrected poses (grid_map_builder.cpp:62-80); stale host cells of
+     * the current local map are about to be recomputed anyway */
+    this->mLocalPending = false;
+    this->mLatestPending = false;
+    const bool lazy = this->mLazy;
+    this->mLazy = false;                        /* the rebuilds share one scratch grid: synchronise each at once */
     for (auto& info : this->mLocalMaps) {
         this->ConstructMapFromScans(info.mMap, poseGraph,
                                     info.mPoseGraphNodeIdxMin, info.mPoseGraphNodeIdxMax);
@@ -107,6 +116,7 @@ void GridMapBuilderCuda::AfterLoopClosure(const std::shared_ptr<PoseGraph>& pose
             Check(this->mCtx, lgs_grid_upload(this->mDevLocal, this->mDense.data()), "lgs_grid_upload");
         }
     }
+    this->mLazy = lazy;
     this->UpdateLatestMap(poseGraph);
 
     /* accumulated travel distance from the corrected poses (:210-224) */
@@ -119,8 +129,12 @@ void GridMapBuilderCuda::AfterLoopClosure(const std::shared_ptr<PoseGraph>& pose
 GridMapType GridMapBuilderCuda::ConstructGlobalMap(const std::shared_ptr<PoseGraph>& poseGraph)
 {
     GridMapType gridMap { this->mResolution, this->mPatchSize, 0, 0, Point2D<double>(0.0, 0.0) };
+    this->FlushHostMaps();                      /* the scratch grid is about to hold the global map */
+    const bool lazy = this->mLazy;
+    this->mLazy = false;
     this->ConstructMapFromScans(gridMap, poseGraph, poseGraph->Nodes().front().Index(),
                                 poseGraph->Nodes().back().Index());
+    this->mLazy = lazy;
     return gridMap;
 }
 
@@ -162,7 +176,7 @@ void GridMapBuilderCuda::MirrorGeometry(lgs_grid*& grid, const GridMapType& map)
           map.Resolution(), 1, &grid), "lgs_grid_create");
 }
 
-void GridMapBuilderCuda::ReserveDense(std::size_t cells)
+void GridMapBuilderCuda::ReserveDense(std::size_t cells) const
 {
     /* page-locked staging for the map downloads; re-registered only when it has to grow */
     if (cells > this->mDense.capacity()) {
@@ -176,22 +190,40 @@ void GridMapBuilderCuda::ReserveDense(std::size_t cells)
     this->mDense.resize(cells);
 }
 
-void GridMapBuilderCuda::IntegrateAndSync(lgs_grid* grid, GridMapType& map,
-                                          int x0, int y0, int x1, int y1)
+void GridMapBuilderCuda::Integrate(lgs_grid* grid)
 {
     const lgs_hit_batch batch { static_cast<int>(this->mSensorXY.size() / 2), this->mSensorXY.data(),
                                 this->mHitBegin.data(), this->mHitXY.data() };
     long long updates = 0;
-    auto t0 = std::chrono::steady_clock::now();
+    const auto t0 = std::chrono::steady_clock::now();
     Check(this->mCtx, lgs_grid_integrate_scans(this->mCtx, grid, &batch, this->mProbHit,
           this->mProbMiss, &updates), "lgs_grid_integrate_scans");
     this->mNumOfUpdates += updates;
     this->mTimingsMs[1] += MsSince(t0);
+}
 
+void GridMapBuilderCuda::FlushHostMaps() const
+{
+    if (this->mLocalPending) {
+        this->mLocalPending = false;
+        GridMapType& map = const_cast<GridMapType&>(this->mLocalMaps.back().mMap);
+        this->SyncRegion(this->mDevLocal, map, this->mLocalBox[0], this->mLocalBox[1],
+                         this->mLocalBox[2], this->mLocalBox[3]);
+    }
+    if (this->mLatestPending) {
+        this->mLatestPending = false;
+        GridMapType& map = const_cast<GridMapType&>(this->mLatestMap);
+        this->SyncRegion(this->mDevScratch, map, 0, 0, map.NumOfGridCellsX() - 1, map.NumOfGridCellsY() - 1);
+    }
+}
+
+void GridMapBuilderCuda::SyncRegion(const lgs_grid* grid, GridMapType& map,
+                                    int x0, int y0, int x1, int y1) const
+{
     const int nx = map.NumOfGridCellsX(), ny = map.NumOfGridCellsY();
     if (nx == 0 || ny == 0)
         return;
-    t0 = std::chrono::steady_clock::now();
+    auto t0 = std::chrono::steady_clock::now();
     x0 = std::max(x0, 0); y0 = std::max(y0, 0);
     x1 = std::min(x1, nx - 1); y1 = std::min(y1, ny - 1);
     if (x1 < x0 || y1 < y0)
@@ -243,6 +275,7 @@ bool GridMapBuilderCuda::UpdateGridMap(const std::shared_ptr<PoseGraph>& poseGra
         isFirstScan || this->mTravelDistLastLocalMap >= this->mTravelDistThreshold;
 
     if (createNewLocalMap) {
+        this->FlushHostMaps();                  /* the device mirror is about to follow the NEW local map */
         if (!isFirstScan)
             this->mLocalMaps.back().mFinished = true;
         GridMapType newLocalMap { this->mResolution, this->mPatchSize, 0, 0,
@@ -276,12 +309,26 @@ bool GridMapBuilderCuda::UpdateGridMap(const std::shared_ptr<PoseGraph>& poseGra
         const int shiftY = static_cast<int>(std::lround((localMap.MinPos().mY - oldMin.mY) / this->mResolution));
         Check(this->mCtx, lgs_grid_resize(this->mDevLocal, nx, ny, localMap.MinPos().mX,
               localMap.MinPos().mY, shiftX, shiftY), "lgs_grid_resize");
+        /* new cell (x, y) holds old cell (x + shift, y + shift): stale host cells move with the map */
+        this->mLocalBox[0] -= shiftX; this->mLocalBox[2] -= shiftX;
+        this->mLocalBox[1] -= shiftY; this->mLocalBox[3] -= shiftY;
     }
 
     /* one scan of integration on the device; only the scan's bounding box can have changed */
     const Point2D<int> c0 = localMap.WorldCoordinateToGridCellIndex(bbox[0], bbox[1]);
     const Point2D<int> c1 = localMap.WorldCoordinateToGridCellIndex(bbox[2], bbox[3]);
-    this->IntegrateAndSync(this->mDevLocal, localMap, c0.mX, c0.mY, c1.mX, c1.mY);
+    this->Integrate(this->mDevLocal);
+    if (this->mLazy) {
+        if (!this->mLocalPending) {
+            this->mLocalBox[0] = c0.mX; this->mLocalBox[1] = c0.mY; this->mLocalBox[2] = c1.mX; this->mLocalBox[3] = c1.mY;
+        } else {
+            this->mLocalBox[0] = std::min(this->mLocalBox[0], c0.mX); this->mLocalBox[1] = std::min(this->mLocalBox[1], c0.mY);
+            this->mLocalBox[2] = std::max(this->mLocalBox[2], c1.mX); this->mLocalBox[3] = std::max(this->mLocalBox[3], c1.mY);
+        }
+        this->mLocalPending = true;
+    } else {
+        this->SyncRegion(this->mDevLocal, localMap, c0.mX, c0.mY, c1.mX, c1.mY);
+    }
 
     info.mPoseGraphNodeIdxMax = nodeIdx;
     return createNewLocalMap;
@@ -314,9 +361,14 @@ void GridMapBuilderCuda::ConstructMapFromScans(
 
     /* all scans in one device batch, applied in node order like the CPU loop (:285-329) */
     this->mScratchIsLatest = false;
+    this->mLatestPending = false;               /* whatever the scratch grid held is being replaced */
     this->MirrorGeometry(this->mDevScratch, gridMap);
-    this->IntegrateAndSync(this->mDevScratch, gridMap, 0, 0,
-                           gridMap.NumOfGridCellsX() - 1, gridMap.NumOfGridCellsY() - 1);
+    this->Integrate(this->mDevScratch);
+    if (this->mLazy && &gridMap == &this->mLatestMap)
+        this->mLatestPending = true;            /* the host latest map follows when somebody reads it */
+    else
+        this->SyncRegion(this->mDevScratch, gridMap, 0, 0,
+                         gridMap.NumOfGridCellsX() - 1, gridMap.NumOfGridCellsY() - 1);
 }
 
 } /* namespace Mapping */

@@ -193,6 +193,7 @@ int RunC1(const bool json) {
     auto pgRef = std::make_shared<PoseGraph>(), pgCuda = std::make_shared<PoseGraph>();
     GridMapBuilder bRef(0.05, 64, 10, 20.0, 0.01, 20.0, 0.6, 0.45);
     GridMapBuilderCuda bCuda(0.05, 64, 10, 20.0, 0.01, 20.0, 0.6, 0.45, 0);
+    bCuda.SetLazyHostMaps(true);     /* the matcher takes the device map; the host maps follow when they are read */
     ScanMatcherRealTimeCorrelative mRef(cost, 5, 0.2, 0.2, 0.5, 20.0);
     ScanMatcherRealTimeCorrelativeCuda mCuda(cost, 5, 0.2, 0.2, 0.5, 20.0, 0);
     mCuda.UseDeviceCost(costParams);
