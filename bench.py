@@ -275,9 +275,14 @@ def c4_sub_scans(n_scans, nq):
     return max(1, min(-(-n_scans // 2), 4000 // max(nq, 1)))
 
 
-def c4_steps(ctx, shard, comm, rank, world, n_submaps, n_scans, steps, barrier, max_over_ranks, thr=0.6):
+def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_over_ranks, thr=0.6):
     """Time the loop-detection step `n_scans` query scans x `n_submaps` submaps with this rank's shard:
-    kernels only (inputs resident) and end to end (host scans in, gathered records out)."""
+    kernels only (inputs resident) and end to end (host scans in, gathered records out).
+    lanes = [(ctx, comm), (ctx2, comm2)]: the end-to-end value pipelines consecutive steps over the two
+    contexts (= two CUDA streams, each with its own batch objects, exchange buffer and communicator): the host
+    preparation and upload of step k + 1 run under the kernel of step k, and every step still moves its own
+    inputs to the device and its own gathered records back; `qps_e2e_sequential` is the strictly sequential
+    figure (upload -> kernel -> exchange -> download, one step after the other)."""
     from my_lidar_graph_slam_b200 import capi, sharding
     nq = len(shard.ids)
     sub = c4_sub_scans(n_scans, nq)
@@ -286,31 +291,54 @@ def c4_steps(ctx, shard, comm, rank, world, n_submaps, n_scans, steps, barrier, 
     for r in range(world):
         cnt = len(sharding.owned(n_submaps, r, world))
         seg.append([cnt * len(range(k0, min(k0 + sub, n_scans))) for k0 in range(0, n_scans, sub)])
-    ex = sharding.RecordExchange(ctx, comm, n_scans * n_submaps, rank, world, seg)
-    batches = [capi.BbBatch(ctx, **BB) for _ in groups]
-    for k, (b, g) in enumerate(zip(batches, groups)):
-        ex.attach(b, g["ids"], k)
-    h2d = 0
+    L = []
+    for ctx_l, comm_l in lanes:
+        ex = sharding.RecordExchange(ctx_l, comm_l, n_scans * n_submaps, rank, world, seg)
+        batches = [capi.BbBatch(ctx_l, **BB) for _ in groups]
+        for k, (b, g) in enumerate(zip(batches, groups)):
+            ex.attach(b, g["ids"], k)
+        L.append(dict(ctx=ctx_l, ex=ex, batches=batches))
+    ctx = L[0]["ctx"]
 
-    def step():
-        for b, g in zip(batches, groups):
+    def submit(lane):
+        for b, g in zip(lane["batches"], groups):
             b.upload_pairs(g["scans"], g["pair_scan"], g["pyr"], thr)
             b.run()
-        return ex.finish(batches)
+        lane["ex"].launch_gather()
 
-    for _ in range(3):
-        rec = step()
-    ctx.synchronize()
+    def collect(lane):
+        return lane["ex"].finish_launched(lane["batches"])
+
+    def sync_all():
+        for lane in L:
+            lane["ctx"].synchronize()
+
+    for lane in L:
+        for _ in range(2):
+            submit(lane)
+            rec = collect(lane)
+    sync_all()
     barrier()
-    t0 = time.perf_counter()
+    t0 = time.perf_counter()                                  # (a) strictly sequential
     for _ in range(steps):
-        rec = step()
-    ctx.synchronize()
+        submit(L[0])
+        rec = collect(L[0])
+    sync_all()
+    e2e_seq_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    t0 = time.perf_counter()                                  # (b) pipelined over the lanes
+    submit(L[0])
+    for k in range(1, steps):
+        submit(L[k % len(L)])
+        rec = collect(L[(k - 1) % len(L)])
+    rec = collect(L[(steps - 1) % len(L)])
+    sync_all()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     # kernels only: scans + pyramids resident, one persistent kernel launch per sub-batch and step
+    batches = L[0]["batches"]
     for b, g in zip(batches, groups):
         b.upload_pairs(g["scans"], g["pair_scan"], g["pyr"], thr)
-    ctx.synchronize()
+    sync_all()
     barrier()
     launches0 = ctx.launch_count()
     ctx.timer_start()
@@ -324,22 +352,27 @@ def c4_steps(ctx, shard, comm, rank, world, n_submaps, n_scans, steps, barrier, 
         lv, ga = b.work()
         nodes += int(sum(lv))
         gathers += int(ga)
-        d_, e_ = b.path()
-        dev_runs += d_
-        exact_runs += e_
+    for lane in L:
+        for b in lane["batches"]:
+            d_, e_ = b.path()
+            dev_runs += d_
+            exact_runs += e_
+    h2d = 0
     for g in groups:
         h2d += g["scans"].nbytes + len(g["ids"]) * 312          # scans + per-pair query descriptors
     pairs = n_scans * n_submaps
     out = {"qps": pairs * steps / (dev_ms * 1e-3), "qps_e2e": pairs * steps / e2e_s,
+           "qps_e2e_sequential": pairs * steps / e2e_seq_s,
            "ms": dev_ms / steps, "ms_e2e": 1e3 * e2e_s / steps, "launches_per_step": launches / steps,
            "sub_batches": len(groups), "scans_per_sub_batch": sub, "nodes_rank0": nodes, "gathers_rank0": gathers,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(ex.d2h_bytes),
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(L[0]["ex"].d2h_bytes),
            "device_runs": dev_runs, "exact_runs": exact_runs,
            "found": int((rec["found"] != 0).sum()), "best": sharding.best_candidate(rec),
            "sha": hashlib.sha256(rec.tobytes()).hexdigest()[:16]}
-    for b in batches:
-        b.close()
-    ex.close()
+    for lane in L:
+        for b in lane["batches"]:
+            b.close()
+        lane["ex"].close()
     return out, rec
 
 
@@ -833,6 +866,9 @@ def run_b200(args, rank, world_size, local_rank):
 
     ctx = capi.Context(local_rank)
     comm = sharding.make_comm(ctx, rank, world_size)
+    ctx_b = capi.Context(local_rank)                    # second lane of the pipelined end-to-end steps
+    comm_b = sharding.make_comm(ctx_b, rank, world_size)
+    lanes = [(ctx, comm), (ctx_b, comm_b)]
     hbm_peak, hbm_src = measured_peaks()
     details = {"n_gpus": world_size}
     steps_side = max(3, min(args.steps, 10))
@@ -851,8 +887,8 @@ def run_b200(args, rank, world_size, local_rank):
         t0 = time.perf_counter()
         shard = C4Shard(ctx, scene, mine)
         build_s = time.perf_counter() - t0
-        single, rec1 = c4_steps(ctx, shard, comm, rank, world_size, args.submaps, 1, steps_side, barrier, max_over_ranks)
-        batched, recq = c4_steps(ctx, shard, comm, rank, world_size, args.submaps, C4_SCANS, max(2, steps_side // 2),
+        single, rec1 = c4_steps(lanes, shard, rank, world_size, args.submaps, 1, steps_side, barrier, max_over_ranks)
+        batched, recq = c4_steps(lanes, shard, rank, world_size, args.submaps, C4_SCANS, max(2, steps_side // 2),
                                  barrier, max_over_ranks)
         c4 = {"single": single, "batched": batched, "submaps_rank0": int(len(mine)),
               "pyramid_rebuild_ms_rank0": shard.pyramid_ms, "submap_build_s_rank0": build_s,
@@ -865,8 +901,9 @@ def run_b200(args, rank, world_size, local_rank):
             if rank == 0:
                 full = C4Shard(ctx, scene, np.arange(args.submaps))
                 nb = lambda: None
-                s1, r1 = c4_steps(ctx, full, None, 0, 1, args.submaps, 1, steps_side, nb, lambda x: x)
-                sq, rq = c4_steps(ctx, full, None, 0, 1, args.submaps, C4_SCANS, max(2, steps_side // 2), nb, lambda x: x)
+                solo = [(ctx, None), (ctx_b, None)]
+                s1, r1 = c4_steps(solo, full, 0, 1, args.submaps, 1, steps_side, nb, lambda x: x)
+                sq, rq = c4_steps(solo, full, 0, 1, args.submaps, C4_SCANS, max(2, steps_side // 2), nb, lambda x: x)
                 full.close()
                 n1 = {"single": s1, "batched": sq,
                       "records_identical": bool(r1.tobytes() == rec1.tobytes() and rq.tobytes() == recq.tobytes())}
@@ -963,8 +1000,10 @@ def run_b200(args, rank, world_size, local_rank):
                 if "error" not in d else {"error": d["error"][:80]}
 
     def c4_compact(c):
-        return {"q1": {"k": r3(c["single"]["qps"]), "e2e": r3(c["single"]["qps_e2e"]), "ms": r3(c["single"]["ms"])},
-                "q64": {"k": r3(c["batched"]["qps"]), "e2e": r3(c["batched"]["qps_e2e"]), "ms": r3(c["batched"]["ms"])}}
+        return {"q1": {"k": r3(c["single"]["qps"]), "e2e": r3(c["single"]["qps_e2e"]),
+                       "e2e_seq": r3(c["single"]["qps_e2e_sequential"]), "ms": r3(c["single"]["ms"])},
+                "q64": {"k": r3(c["batched"]["qps"]), "e2e": r3(c["batched"]["qps_e2e"]),
+                        "e2e_seq": r3(c["batched"]["qps_e2e_sequential"]), "ms": r3(c["batched"]["ms"])}}
 
     if world_size == 1:
         line = {
@@ -995,8 +1034,9 @@ def run_b200(args, rank, world_size, local_rank):
             "config": c4_config(args.submaps, world_size),
             "l2": "pyramids >> L2, no flush", "parallelism": f"submap i on rank i%{world_size}, in-place NCCL all-gather of records",
             "e2e": {"value": r3(b["qps_e2e"], 6), "unit": C4_UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"],
-                    "d2h_bytes_per_step": b["d2h_bytes_per_step"]},
-            "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]), "ms": r3(c4["single"]["ms"])},
+                    "d2h_bytes_per_step": b["d2h_bytes_per_step"], "sequential_value": r3(b["qps_e2e_sequential"])},
+            "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]),
+                            "e2e_seq": r3(c4["single"]["qps_e2e_sequential"]), "ms": r3(c4["single"]["ms"])},
             "records_sha256": b["sha"], "loops_found": b["found"],
             "gpu_launches": int(round(b["launches_per_step"] * max(2, steps_side // 2))), "clocks": c2["clocks"],
             "roofline": gather_roofline(c4["gathers_all"] * 8 / (b["ms"] * 1e-3) / 1e9, gpeak, sm_mhz, world_size,

@@ -140,11 +140,19 @@ class RecordExchange:
             batch.set_record_sink(self.buf, int(self.first[k]))
             self._attached[k] = batch
 
-    def gather(self):
-        """All-gather on the context stream (in place), one download, assembly in global order."""
-        from . import capi
+    def launch_gather(self):
+        """Enqueue the in-place all-gather on the context stream, behind the kernels that fill the slice."""
         if self.comm is not None:
             self.comm.all_gather_records(self.buf, self.per)
+
+    def gather(self):
+        """All-gather on the context stream (in place), one download, assembly in global order."""
+        self.launch_gather()
+        return self.collect()
+
+    def collect(self):
+        """One download of the gathered buffer (waits for the context stream), assembly in global order."""
+        from . import capi
         capi.download_into(self.ctx, self.buf, self.host)
         ok = bool((self.host["found"][self.status_pos] == 1).all())
         if self.perm is None:               # global id -> position in the gathered buffer, fixed for this exchange
@@ -158,7 +166,11 @@ class RecordExchange:
         """gather(); if any rank's run has to be repeated exactly (its status record says so), every rank
         sees that in the gathered buffer, the ranks settle their batches (exact path, records rewritten
         in place) and the gather is repeated -- a collective decision taken from exchanged data."""
-        out, ok = self.gather()
+        return self.finish_launched(batches, launched=False)
+
+    def finish_launched(self, batches, launched=True):
+        """finish() for a caller that has already enqueued the all-gather (launch_gather) behind its kernels."""
+        out, ok = self.collect() if launched else self.gather()
         if not ok:
             for b in batches:
                 b.settle()
