@@ -173,7 +173,7 @@ def hyps_per_match(res):
 
 def c2_config(M):
     """The `config` object of the C2 line -- shared by both arms so that they describe the same workload."""
-    return {"workload": "C2 rtcsm sweep, 1081 beams, +-0.5m/+-30deg @0.05m/0.5deg", "matches_per_step": int(M), **C2}
+    return {"workload": "C2 rtcsm 1081 beams +-0.5m/+-30deg", "matches_per_step": int(M), **C2}
 
 
 # ---- C4: branch-and-bound loop detection -------------------------------------------------------------
@@ -185,7 +185,7 @@ C4_SCANS = 64
 
 
 def c4_config(n_submaps, world):
-    return {"workload": f"C4 B&B loop detection, {C4_SCANS} scans x {n_submaps} submaps/step, 7 levels, thr 0.6",
+    return {"workload": f"C4 B&B {C4_SCANS} scans x {n_submaps} submaps, 7 levels",
             "submaps": int(n_submaps), "scans_per_step": C4_SCANS, **BB}
 
 
@@ -732,10 +732,9 @@ def gather_roofline(achieved_gbps, gather_peak_gbps, sm_mhz, n_gpus, kernel, hbm
     theo = 148 * 128 * (sm_mhz or 1965.0) * 1e6 / 1e9 * n_gpus       # 148 SMs x 128 B/clk x f_sm
     peak = gather_peak_gbps * n_gpus
     return {"bound": "l1_gather", "achieved": r3(achieved_gbps), "peak": r3(peak), "unit": "GB/s",
-            "frac": r3(achieved_gbps / peak), "peak_kind": "measured (lgs_measure_gather_peak, this run)",
+            "frac": r3(achieved_gbps / peak), "peak_kind": "measured in-run gather peak",
             "peak_theoretical": r3(theo), "frac_theoretical": r3(achieved_gbps / theo), "kernel": kernel,
-            "hbm": {"peak": r3(hbm_peak * n_gpus), "achieved_over_peak": r3(achieved_gbps / (hbm_peak * n_gpus))},
-            "traffic": None}
+            "hbm_peak": r3(hbm_peak * n_gpus), "hbm_frac": r3(achieved_gbps / (hbm_peak * n_gpus)), "traffic": None}
 
 
 # ---- reference arm ------------------------------------------------------------------------------------------
@@ -983,7 +982,7 @@ def run_b200(args, rank, world_size, local_rank):
                 bad = sum((a.found, a.ix, a.iy, a.it, a.score) != (b.found, b.ix, b.iy, b.it, b.score)
                           for a, b in zip(ref, c2["results"][:ns]))
                 cpu = {"value": r3(sum(hyps_per_match(r) for r in ref) / dt), "unit": UNIT, "cores": cores,
-                       "kind": "reference", "sample": f"first {ns} matches of the step, {dt:.1f} s; GPU identical {ns - bad}/{ns}"}
+                       "kind": "reference", "sample": f"first {ns} matches, {dt:.1f} s; GPU identical {ns - bad}/{ns}"}
         except Exception as e:   # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -991,13 +990,20 @@ def run_b200(args, rank, world_size, local_rank):
                 "ms_per_step": r3(c2["ms_per_step"]), "sweep_ms": r3(c2["k_sweep"])}
     details["c2"] = {k: v for k, v in c2.items() if k not in ("grid", "coarse", "batch", "dense", "angles", "ranges",
                                                               "inits", "results")}
-    for name, keys in (("c5", ("precompute_ms", "precompute_hbm_frac", "qps", "qps_e2e", "found", "sha")),
-                       ("c3", ("scans_per_s", "cell_updates_per_s")), ("matcher_tail", ("tails_per_s",)),
-                       ("grid_search", ("hypotheses_per_s",)), ("c1", ("frames_per_s", "ref_frames_per_s", "identical", "launcher_frames_per_s", "launcher_ref_frames_per_s", "launcher_identical"))):
+    short = {"precompute_ms": "pre_ms", "precompute_hbm_frac": "pre_hbm_frac", "qps": "qps", "qps_e2e": "qps_e2e",
+             "found": "found", "scans_per_s": "scans_per_s", "cell_updates_per_s": "updates_per_s",
+             "tails_per_s": "per_s", "hypotheses_per_s": "hyp_per_s", "frames_per_s": "fps", "ref_frames_per_s": "ref_fps",
+             "identical": "same", "launcher_frames_per_s": "launch_fps", "launcher_ref_frames_per_s": "launch_ref_fps",
+             "launcher_identical": "launch_same"}
+    for name, out_name, keys in (("c5", "c5", ("precompute_ms", "precompute_hbm_frac", "qps", "qps_e2e", "found")),
+                                 ("c3", "c3", ("scans_per_s", "cell_updates_per_s")), ("matcher_tail", "tail", ("tails_per_s",)),
+                                 ("grid_search", "gs", ("hypotheses_per_s",)),
+                                 ("c1", "c1", ("frames_per_s", "ref_frames_per_s", "identical", "launcher_frames_per_s",
+                                               "launcher_ref_frames_per_s", "launcher_identical"))):
         d = details.get(name)
         if isinstance(d, dict):
-            extra[name] = {k: (r3(d[k]) if isinstance(d.get(k), float) else d.get(k)) for k in keys if k in d} \
-                if "error" not in d else {"error": d["error"][:80]}
+            extra[out_name] = {short[k]: (r3(d[k]) if isinstance(d.get(k), float) else d.get(k)) for k in keys if k in d} \
+                if "error" not in d else {"error": d["error"][:60]}
 
     def c4_compact(c):
         return {"q1": {"k": r3(c["single"]["qps"]), "e2e": r3(c["single"]["qps_e2e"]),
@@ -1011,7 +1017,7 @@ def run_b200(args, rank, world_size, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": r3(c2["ms_per_step"], 6), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": c2_config(args.matches),
-            "l2": "step working set > L2, no flush",
+            "l2": "working set > L2",
             "e2e": {"value": r3(c2["e2e"], 6), "unit": UNIT, "h2d_bytes_per_step": c2["h2d"], "d2h_bytes_per_step": c2["d2h"],
                     "sequential_value": r3(c2["e2e_seq"])},
             "gpu_launches": c2["launches"], "clocks": c2["clocks"],
@@ -1020,9 +1026,8 @@ def run_b200(args, rank, world_size, local_rank):
         }
         if c4:
             line["loop_closure"] = {"unit": C4_UNIT, **c4_compact(c4),
-                                    "l1_gather_frac": r3(c4["gathers_all"] * 8 / (c4["batched"]["ms"] * 1e-3) / 1e9 / gpeak),
-                                    "sha": c4["batched"]["sha"],
-                                    "found": c4["batched"]["found"], "launches_per_run": 1,
+                                    "roof_frac": r3(c4["gathers_all"] * 8 / (c4["batched"]["ms"] * 1e-3) / 1e9 / gpeak),
+                                    "sha": c4["batched"]["sha"], "found": c4["batched"]["found"],
                                     "cpu": r3((c4.get("cpu_baseline") or {}).get("value"))}
         line["extra"] = extra
     else:
@@ -1032,7 +1037,7 @@ def run_b200(args, rank, world_size, local_rank):
             "warmup": 3, "ms_per_step": r3(b["ms"], 6), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": c4_config(args.submaps, world_size),
-            "l2": "pyramids >> L2, no flush", "parallelism": f"submap i on rank i%{world_size}, in-place NCCL all-gather of records",
+            "l2": "pyramids >> L2", "parallelism": f"submap i on rank i%{world_size}, in-place NCCL all-gather",
             "e2e": {"value": r3(b["qps_e2e"], 6), "unit": C4_UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": b["d2h_bytes_per_step"], "sequential_value": r3(b["qps_e2e_sequential"])},
             "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]),
