@@ -49,6 +49,7 @@ constexpr int kSegWords = kSeg / 32;
 constexpr unsigned kRawMax = 26;               // touches a raw record holds
 constexpr unsigned kRecOverflow = 0xFFFFFFFFu;
 constexpr unsigned kRecSide = 31u << 26;
+constexpr int kFoldBatch = 8;                  // records a fold thread keeps in flight
 constexpr size_t kRecordBudget = (size_t)1 << 30;   // bytes of records per chunk before it is split
 
 struct ScanMeta {
@@ -214,13 +215,10 @@ integ_mark_kernel(const ScanMeta* __restrict__ meta, const int2* __restrict__ re
 // Descriptor = two int4: {ox, oy, k0, k1} (tile origin relative to the scan's sensor cell, beam range)
 // and {beamBegin, tile, scan, 0}, so the touch pass needs no further dependent look-ups.
 // One warp per tile: lanes read the tile's 64 kmax entries (non-zero = the scan touches the tile).
-// A tile with pairs joins the chunk's active list together with the sequence number of the previous
-// chunk that touched the same tile of the grid's lattice (the fold of this chunk waits for that one).
 __global__ void __launch_bounds__(128)
-integ_pairs_kernel(int nTiles, const ScanMeta* __restrict__ meta, int x0, int y0, int tw, int latticeW, unsigned seq,
+integ_pairs_kernel(int nTiles, const ScanMeta* __restrict__ meta, int x0, int y0, int tw,
                    unsigned* __restrict__ kmin, unsigned* __restrict__ kmax,
-                   uint2* __restrict__ tileInfo, int4* __restrict__ pairs, unsigned* __restrict__ nPairs,
-                   uint2* __restrict__ act, unsigned* __restrict__ nAct, unsigned* __restrict__ lastSeq) {
+                   uint2* __restrict__ tileInfo, int4* __restrict__ pairs, unsigned* __restrict__ nPairs) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= nTiles) return;
@@ -229,13 +227,7 @@ integ_pairs_kernel(int nTiles, const ScanMeta* __restrict__ meta, int x0, int y0
     const unsigned mA = __ballot_sync(0xffffffffu, hiA != 0u), mB = __ballot_sync(0xffffffffu, hiB != 0u);
     const unsigned cnt = (unsigned)(__popc(mA) + __popc(mB));
     unsigned base = 0;
-    if (cnt && lane == 0) {
-        base = atomicAdd(nPairs, cnt);
-        const size_t lt = (size_t)((y0 >> kTileShift) + t / tw) * latticeW + (x0 >> kTileShift) + t % tw;
-        const unsigned prev = lastSeq[lt];
-        lastSeq[lt] = seq;
-        act[atomicAdd(nAct, 1u)] = make_uint2((unsigned)t, prev);
-    }
+    if (cnt && lane == 0) base = atomicAdd(nPairs, cnt);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (lane == 0) tileInfo[t] = make_uint2(base, cnt);
     const unsigned below = (1u << lane) - 1u;
@@ -281,70 +273,26 @@ struct TouchSeq {
     }
 };
 
-// The beams [seg, seg + nb) of a pair drop their cells of the tile into the per-cell bitmaps (bit = beam
-// within the segment).  `per` threads per beam (4 for segments of <= 64 beams, else 2) share the <= 16
-// steps whose major coordinate lies inside the tile; the minor coordinate
-// floor((2 amin k + amaj) / (2 amaj)) is divided out once per thread and then carried with its
-// remainder (2 amin <= 2 amaj: at most one increment a step).
-__device__ __forceinline__ int lanesPerBeam(int nb) { return nb <= kTileCells / 4 ? 4 : 2; }
-
-__device__ __forceinline__ void scatterBeam(const int2 e, int ox, int oy, int b, int sub, int per,
-                                            unsigned* __restrict__ sTouch, unsigned* __restrict__ sHit) {
-    const int ax = abs(e.x), ay = abs(e.y);
-    const bool xMajor = ax > ay;
-    const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
-    const int eMaj = xMajor ? e.x : e.y, eMin = xMajor ? e.y : e.x;
-    const int oMaj = xMajor ? ox : oy, oMin = xMajor ? oy : ox;
-    const int steps = kTile / per;
-    const int kBase = (eMaj >= 0 ? oMaj : -oMaj - (kTile - 1)) + sub * steps;
-    const int kLo = max(kBase, 0);
-    const int kHi = min(kBase + steps - 1, amaj);
-    if (kLo > kHi) return;
-    const int m2 = 2 * amaj, d2 = 2 * amin;
-    int minor = amaj ? minorAt(amin, amaj, kLo) : 0;
-    int rem = d2 * kLo + amaj - minor * m2;
-    const unsigned bitb = 1u << (b & 31);
-    unsigned* tw_ = sTouch + (b >> 5) * kTileCells;
-    unsigned* hw_ = sHit + (b >> 5) * kTileCells;
-    for (int k = kLo; k <= kHi; ++k) {
-        const int j = eMaj >= 0 ? k - oMaj : -k - oMaj;              // column (row) in the tile
-        const int lMin = (eMin < 0 ? -minor : minor) - oMin;
-        if ((unsigned)lMin < (unsigned)kTile) {
-            const int cell = xMajor ? (lMin * kTile + j) : (j * kTile + lMin);
-            atomicOr(tw_ + cell, bitb);
-            if (k == amaj) atomicOr(hw_ + cell, bitb);
-        }
-        rem += d2;
-        if (rem >= m2) { rem -= m2; ++minor; }
-    }
-}
-
-// One barrier per 128-beam segment: the bitmaps are double buffered and every cell clears its own words
-// as it reads them, so the buffer a segment scatters into was emptied two segments ago by threads that
-// have all passed the barrier in between.  A pair with a cell whose sequence fits no record format is
-// appended to the chunk's side list (once: the flag lives in the pair descriptor) and its raw bitmap
-// words are streamed by integ_touch_side_kernel.
-__global__ void __launch_bounds__(kTileCells, 5)
-integ_touch_kernel(const int2* __restrict__ rel, int4* __restrict__ pairs,
+__global__ void __launch_bounds__(kTileCells, 4)
+integ_touch_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs,
                    const unsigned* __restrict__ nPairs, unsigned* __restrict__ records, unsigned* __restrict__ side,
-                   unsigned* __restrict__ sideCursor, unsigned sideCap, unsigned* __restrict__ sideList,
-                   unsigned* __restrict__ nSideList, unsigned long long* __restrict__ counters) {
+                   unsigned* __restrict__ sideCursor, unsigned sideCap,
+                   unsigned long long* __restrict__ counters) {
     __shared__ unsigned sBits[2][2 * kSegWords * kTileCells];   // double buffered; [touch | hit][word][cell]
+    int buf = 0;
     __shared__ unsigned sSum[kTileCells / 32];
     const int tid = threadIdx.x;
     const unsigned nP = *nPairs;
     unsigned total = 0, overflow = 0;
     int4 nextA = make_int4(0, 0, 0, 0), nextB = nextA;
+    // Threads per beam in the scatter step: 4 (4 steps each) for segments of <= 64 beams, else 2.
+    auto lanesPerBeam = [](int nb) { return nb <= kTileCells / 4 ? 4 : 2; };
     int2 eNext = make_int2(0, 0);                            // this thread's beam of the next pair's first segment
     if (blockIdx.x < nP) {
         nextA = pairs[2 * (size_t)blockIdx.x]; nextB = pairs[2 * (size_t)blockIdx.x + 1];
         const int nb = min(kSeg, nextA.w - nextA.z), b = tid / lanesPerBeam(nb);
         if (b < nb) eNext = __ldg(rel + nextB.x + nextA.z + b);
     }
-#pragma unroll
-    for (int w = 0; w < 2 * kSegWords; ++w) { sBits[0][w * kTileCells + tid] = 0u; sBits[1][w * kTileCells + tid] = 0u; }
-    __syncthreads();
-    int buf = 0;
     for (unsigned p = blockIdx.x; p < nP; p += gridDim.x) {
         const int4 pr = nextA;                              // .x/.y tile origin - sensor cell, .z/.w beams
         const int2* __restrict__ E = rel + nextB.x;
@@ -355,51 +303,104 @@ integ_touch_kernel(const int2* __restrict__ rel, int4* __restrict__ pairs,
             nextB = pairs[2 * (size_t)(p + gridDim.x) + 1];
         }
         bool fetched = false;
+        const int ox = pr.x, oy = pr.y;
         TouchSeq seq;
+        unsigned rec = 0u, sideOff = 0u;
         int wFirst = 0x7fffffff, wLast = -1;                   // non-empty bitmap words of this cell
-        for (int seg = pr.z; seg < pr.w; seg += kSeg) {
-            unsigned* sTouch = sBits[buf];
-            unsigned* sHit = sBits[buf] + kSegWords * kTileCells;
-            buf ^= 1;
-            const int nb = min(kSeg, pr.w - seg);
-            const int nW = (nb + 31) >> 5;
-            const int per = lanesPerBeam(nb), b = tid / per;
-            if (b < nb) scatterBeam(seg == pr.z ? eFirst : __ldg(E + seg + b), pr.x, pr.y, b, tid - b * per, per, sTouch, sHit);
-            if (more && !fetched) {                     // next pair's beams: in flight during the extraction
-                fetched = true;
-                const int nbN = min(kSeg, nextA.w - nextA.z), bN = tid / lanesPerBeam(nbN);
-                if (bN < nbN) eNext = __ldg(rel + nextB.x + nextA.z + bN);
-            }
-            __syncthreads();
-            for (int w = 0; w < nW; ++w) {
-                unsigned t = sTouch[w * kTileCells + tid];
-                if (t == 0u) continue;
-                const unsigned h = sHit[w * kTileCells + tid];
-                sTouch[w * kTileCells + tid] = 0u;
-                if (h) sHit[w * kTileCells + tid] = 0u;
-                const int gw = ((seg - pr.z) / kSeg) * kSegWords + w;
-                wFirst = min(wFirst, gw); wLast = gw;
-                while (t) {                              // maximal runs of equal type, ascending beams
-                    const int type = (h >> (__ffs(t) - 1)) & 1;
-                    const unsigned same = type ? (t & h) : (t & ~h);
-                    const unsigned other = t & ~same;
-                    const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
-                    const unsigned run = same & upto;
-                    seq.append(type, (unsigned)__popc(run));
-                    t &= ~run;
+        // pass 0 builds the records; pass 1 (only if a cell of this pair fits no record format)
+        // repeats the bitmaps and streams the raw words of those cells to the side buffer
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int seg = pr.z; seg < pr.w; seg += kSeg) {
+                // Two barriers per segment: the buffer cleared here was last read two segments ago.
+                buf ^= 1;
+                unsigned* sTouch = sBits[buf];
+                unsigned* sHit = sBits[buf] + kSegWords * kTileCells;
+                const int nW = (min(kSeg, pr.w - seg) + 31) >> 5;
+                for (int w = 0; w < nW; ++w) { sTouch[w * kTileCells + tid] = 0u; sHit[w * kTileCells + tid] = 0u; }
+                __syncthreads();
+                const int nb = min(kSeg, pr.w - seg);
+                const int per = lanesPerBeam(nb), b = tid / per;
+                if (b < nb) {
+                    // `per` threads per beam share the <= 16 steps whose major coordinate lies inside
+                    // the tile; the minor coordinate floor((2 amin k + amaj) / (2 amaj)) is divided
+                    // out once per thread and then carried with its remainder (2 amin <= 2 amaj: at
+                    // most one increment a step)
+                    const int2 e = (pass == 0 && seg == pr.z) ? eFirst : __ldg(E + seg + b);
+                    const int ax = abs(e.x), ay = abs(e.y);
+                    const bool xMajor = ax > ay;
+                    const int amaj = xMajor ? ax : ay, amin = xMajor ? ay : ax;
+                    const int eMaj = xMajor ? e.x : e.y, eMin = xMajor ? e.y : e.x;
+                    const int oMaj = xMajor ? ox : oy, oMin = xMajor ? oy : ox;
+                    const int steps = kTile / per, sub = tid - b * per;
+                    const int kBase = (eMaj >= 0 ? oMaj : -oMaj - (kTile - 1)) + sub * steps;
+                    const int kLo = max(kBase, 0);
+                    const int kHi = min(kBase + steps - 1, amaj);
+                    if (kLo <= kHi) {
+                        const int m2 = 2 * amaj, d2 = 2 * amin;
+                        int minor = amaj ? minorAt(amin, amaj, kLo) : 0;
+                        int rem = d2 * kLo + amaj - minor * m2;
+                        const unsigned bitb = 1u << (b & 31);
+                        unsigned* tw_ = sTouch + (b >> 5) * kTileCells;
+                        unsigned* hw_ = sHit + (b >> 5) * kTileCells;
+                        for (int k = kLo; k <= kHi; ++k) {
+                            const int j = eMaj >= 0 ? k - oMaj : -k - oMaj;              // column (row) in the tile
+                            const int lMin = (eMin < 0 ? -minor : minor) - oMin;
+                            if ((unsigned)lMin < (unsigned)kTile) {
+                                const int cell = xMajor ? (lMin * kTile + j) : (j * kTile + lMin);
+                                atomicOr(tw_ + cell, bitb);
+                                if (k == amaj) atomicOr(hw_ + cell, bitb);
+                            }
+                            rem += d2;
+                            if (rem >= m2) { rem -= m2; ++minor; }
+                        }
+                    }
+                }
+                if (more && !fetched) {                     // next pair's beams: in flight during the extraction
+                    fetched = true;
+                    const int nbN = min(kSeg, nextA.w - nextA.z), bN = tid / lanesPerBeam(nbN);
+                    if (bN < nbN) eNext = __ldg(rel + nextB.x + nextA.z + bN);
+                }
+                __syncthreads();
+                if (pass == 0) {
+                    for (int w = 0; w < nW; ++w) {
+                        unsigned t = sTouch[w * kTileCells + tid];
+                        if (t == 0u) continue;
+                        const int gw = ((seg - pr.z) / kSeg) * kSegWords + w;
+                        wFirst = min(wFirst, gw); wLast = gw;
+                        const unsigned h = sHit[w * kTileCells + tid];
+                        while (t) {                              // maximal runs of equal type, ascending beams
+                            const int type = (h >> (__ffs(t) - 1)) & 1;
+                            const unsigned same = type ? (t & h) : (t & ~h);
+                            const unsigned other = t & ~same;
+                            const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
+                            const unsigned run = same & upto;
+                            seq.append(type, (unsigned)__popc(run));
+                            t &= ~run;
+                        }
+                    }
+                } else if ((rec >> 26) == 31u) {
+                    unsigned* out = side + (size_t)sideOff + 2;
+                    for (int w = 0; w < nW; ++w) {
+                        const int gw = ((seg - pr.z) / kSeg) * kSegWords + w;
+                        if (gw < wFirst || gw > wLast) continue;
+                        out[2 * (gw - wFirst)] = sTouch[w * kTileCells + tid];
+                        out[2 * (gw - wFirst) + 1] = sHit[w * kTileCells + tid];
+                    }
                 }
             }
-        }
-        unsigned rec = seq.record();
-        if (rec == kRecOverflow) {
-            // header {first word | words << 16, -} + (touch, hit) word pairs, in units of 8 words
-            const unsigned nWords = (unsigned)(wLast - wFirst + 1);
-            const unsigned words = (2u + 2u * nWords + 7u) & ~7u;
-            const unsigned sideOff = atomicAdd(sideCursor, words);
-            if (sideOff + words <= sideCap && nWords < 65536u) {
-                rec = kRecSide | (sideOff >> 3);
-                side[sideOff] = (unsigned)wFirst | (nWords << 16);
-                if (atomicExch(&pairs[2 * (size_t)p + 1].w, 1) == 0) sideList[atomicAdd(nSideList, 1u)] = p;
+            if (pass == 0) {
+                rec = seq.record();
+                if (rec == kRecOverflow) {
+                    // header {first word | words << 16, -} + (touch, hit) word pairs, in units of 8 words
+                    const unsigned nWords = (unsigned)(wLast - wFirst + 1);
+                    const unsigned words = (2u + 2u * nWords + 7u) & ~7u;
+                    sideOff = atomicAdd(sideCursor, words);
+                    if (sideOff + words <= sideCap && nWords < 65536u) {
+                        rec = kRecSide | (sideOff >> 3);
+                        side[sideOff] = (unsigned)wFirst | (nWords << 16);
+                    }
+                }
+                if (!__syncthreads_or((rec >> 26) == 31u)) break;
             }
         }
         records[(size_t)p * kTileCells + tid] = rec;
@@ -421,101 +422,28 @@ integ_touch_kernel(const int2* __restrict__ rel, int4* __restrict__ pairs,
     if ((tid & 31) == 0 && ov) atomicAdd(counters + 1, (unsigned long long)ov);
 }
 
-// The pairs of the side list once more: the bitmaps are rebuilt segment by segment and every cell whose
-// record points into the side buffer streams its raw (touch, hit) words there.
-__global__ void __launch_bounds__(kTileCells)
-integ_touch_side_kernel(const int2* __restrict__ rel, const int4* __restrict__ pairs, const unsigned* __restrict__ records,
-                        unsigned* __restrict__ side, const unsigned* __restrict__ sideList,
-                        const unsigned* __restrict__ nSideList) {
-    __shared__ unsigned sBits[2 * kSegWords * kTileCells];
-    const int tid = threadIdx.x;
-    const unsigned nL = *nSideList;
-    unsigned* sTouch = sBits;
-    unsigned* sHit = sBits + kSegWords * kTileCells;
-    for (unsigned i = blockIdx.x; i < nL; i += gridDim.x) {
-        const unsigned p = sideList[i];
-        const int4 pr = pairs[2 * (size_t)p];
-        const int2* __restrict__ E = rel + pairs[2 * (size_t)p + 1].x;
-        const unsigned rec = records[(size_t)p * kTileCells + tid];
-        const bool mine = (rec >> 26) == 31u && rec != kRecOverflow;
-        unsigned* out = nullptr;
-        int wFirst = 0, wLast = -1;
-        if (mine) {
-            unsigned* S = side + (size_t)(rec & ((1u << 26) - 1u)) * 8u;
-            wFirst = (int)(S[0] & 0xFFFFu);
-            wLast = wFirst + (int)(S[0] >> 16) - 1;
-            out = S + 2;
-        }
-        for (int seg = pr.z; seg < pr.w; seg += kSeg) {
-            const int nb = min(kSeg, pr.w - seg);
-            const int nW = (nb + 31) >> 5;
-            for (int w = 0; w < nW; ++w) { sTouch[w * kTileCells + tid] = 0u; sHit[w * kTileCells + tid] = 0u; }
-            __syncthreads();
-            const int per = lanesPerBeam(nb), b = tid / per;
-            if (b < nb) scatterBeam(__ldg(E + seg + b), pr.x, pr.y, b, tid - b * per, per, sTouch, sHit);
-            __syncthreads();
-            if (mine)
-                for (int w = 0; w < nW; ++w) {
-                    const int gw = ((seg - pr.z) / kSeg) * kSegWords + w;
-                    if (gw < wFirst || gw > wLast) continue;
-                    out[2 * (gw - wFirst)] = sTouch[w * kTileCells + tid];
-                    out[2 * (gw - wFirst) + 1] = sHit[w * kTileCells + tid];
-                }
-            __syncthreads();
-        }
-    }
-}
-
-// ---- 4. fold: one thread owns one cell; ONE persistent launch per segment of chunks ---------------------
-// The fold of a chunk cannot start before its touch pass, and a cell must see the chunks in order, but
-// nothing else orders the folds: a wall cell that alternates between hits and misses carries a chain of
-// several hundred dependent updates per chunk (two IEEE divisions each, ~280 cycles), while most cells
-// finish after a handful.  With one launch per chunk every chunk waited for its longest chain (SMs
-// active 24 % of the pass).  Here the warps of one persistent kernel pull work items
-//     (chunk, active tile, 2-row slice of the tile = 32 cells)
-// in chunk order from per-chunk cursors; an item waits (i) for its chunk to be published by the touch
-// stream and (ii) for the previous chunk that touched the same tile to have folded the same slice
-// (sequence numbers in `done`).  Items are handed out in chunk order and a warp only ever waits for an
-// OLDER item, which a running warp holds, so the scheme cannot deadlock; the kernel occupies one CTA
-// per SM and leaves the rest of the machine to the mark / pairs / touch passes it is waiting for.
-struct FoldChunk {                 // one per chunk of the segment (device copy in the arena)
-    const uint2* tileInfo;         // per region tile: {first pair, pairs}
-    const uint2* act;              // per active tile: {region tile, sequence number of the tile's previous chunk}
+// ---- 4. fold: one thread owns one cell ---------------------------------------------------------------
+struct FoldArgs {
+    const int2* rel;
+    const uint2* tileInfo;
     const int4* pairs;
     const unsigned* records;
-    int x0, y0, tw;                // tile-aligned region origin (cells), tiles per region row
-    unsigned seq;                  // this chunk's sequence number
-};
-
-struct FoldArgs {
-    const FoldChunk* chunks;
-    int nChunks;
-    const unsigned* ready;         // per chunk: non-zero once the chunk's records are complete
-    const unsigned* nAct;          // per chunk: active tiles
-    unsigned* cursor;              // per chunk: next work item
-    unsigned* done;                // per (lattice tile, slice): sequence number of the last chunk folded
-    unsigned* abort;               // set by a worker that waited longer than kFoldPatienceNs: every worker leaves
-    int latticeW;
-    const int2* rel;
     const unsigned* side;
     unsigned long long* diag;      // LGS_INTEG_TIMING: [2] max / [3] sum of computed updates per thread
-    unsigned long long* fail;      // counts workers that left because of the watchdog
     double pHit, pMiss, oddsHit, oddsMiss;
 };
 
-constexpr int kFoldWarps = 8;
-// A worker never waits long: the passes it waits for are queued before or right after its launch and take
-// well under a millisecond per chunk.  Should they not arrive at all (the kernels of the other streams
-// cannot become resident beside this one), the workers give up instead of hanging the device and the
-// call fails.
-constexpr unsigned long long kFoldPatienceNs = 4000000000ull;
-constexpr int kSlices = kTileCells / 32;          // 2-row slices of a tile, one warp each
-
-// Per-cell state: the value and the rules for touches that cannot change it (a value sitting on the
-// probability clamp the observation pushes towards: the clamp makes the update idempotent there).
+// One thread owns one cell.  Raw records (the common case) are queued per lane and applied only when
+// some lane of the warp is about to overflow its 64-touch queue: neighbouring cells see similar
+// numbers of touches over a chunk, so the lanes of a warp then have similar amounts of work, while
+// applying every record at once would run the ~100-instruction update under heavy divergence.
+// A touch that cannot change the value (cell already at the clamp the observation pushes towards:
+// the clamp makes the update idempotent there) is skipped without arithmetic.
 struct Folder {
     const FoldArgs& a;
     double v;
+    unsigned long long q = 0ull;
+    int qn = 0;
     bool missSat, hitSat;
     unsigned computed = 0;
     __device__ __forceinline__ Folder(const FoldArgs& args, double v0) : a(args), v(v0) {
@@ -529,6 +457,25 @@ struct Folder {
     __device__ __forceinline__ void touch(bool hit) {
         if (!saturated(hit)) { v = bayesUpdate(v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss); ++computed; }
     }
+    // Every iteration performs exactly one COMPUTED update per lane: a lane first drops, without
+    // iterating, the leading touches that cannot change a value sitting on a clamp, so a warp
+    // iterates max-over-lanes(computed updates) times, not max-over-lanes(queue length) times.
+    __device__ __forceinline__ void drain() {
+        while (qn) {
+            const bool atLo = missSat && v == 1e-3, atHi = hitSat && v == 1.0 - 1e-3;
+            if (atLo || atHi) {
+                const unsigned long long x = atLo ? q : ~q;            // first touch of the other type
+                const int n = min(qn, x ? __ffsll((long long)x) - 1 : 64);
+                q = n >= 64 ? 0ull : q >> n;
+                qn -= n;
+                if (!qn) break;
+            }
+            const bool hit = q & 1ull;
+            v = bayesUpdate(v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss);
+            ++computed;
+            q >>= 1; --qn;
+        }
+    }
     __device__ __forceinline__ void run(bool hit, unsigned n) {
         for (unsigned j = 0; j < n; ++j) {
             if (saturated(hit)) break;
@@ -540,153 +487,83 @@ struct Folder {
     }
 };
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// Lane 0 of a worker polls *p until it equals `want` (or, with want == 0 and `nonZero`, until it is
-// non-zero); false = gave up (watchdog or another worker's abort).
-__device__ __forceinline__ bool wait_word(const unsigned* p, unsigned want, bool nonZero, unsigned* abort, unsigned ns) {
-    unsigned long long t0 = 0ull;
-    for (unsigned spin = 0;; ++spin) {
-        const unsigned v = ld_acquire(p);
-        if (nonZero ? v != 0u : v == want) return true;
-        __nanosleep(ns);
-        if ((spin & 63u) == 63u) {
-            if (ld_acquire(abort) != 0u) return false;
-            const unsigned long long t = global_ns();
-            if (t0 == 0ull) t0 = t;
-            else if (t - t0 > kFoldPatienceNs) { atomicExch(abort, 1u); return false; }
+__global__ void __launch_bounds__(kTileCells)
+integ_fold_kernel(FoldArgs a, GridRef g, int x0, int y0, int tw) {
+    const uint2 info = a.tileInfo[blockIdx.x];
+    if (info.y == 0u) return;
+    const int tid = threadIdx.x;
+    const int cx = x0 + (blockIdx.x % tw) * kTile + (tid & (kTile - 1));
+    const int cy = y0 + (blockIdx.x / tw) * kTile + (tid >> kTileShift);
+    const bool inside = cx < g.nx && cy < g.ny;
+    double* cell = g.origin + (size_t)cy * g.pitch + cx;
+    const double v0 = inside ? *cell : 0.0;
+    Folder f(a, v0);
+    // Records are prefetched kFoldBatch pairs at a time (they do not depend on the cell value): the
+    // loads of the next batch are in flight while this thread's own column of the shared staging
+    // buffer is consumed, so a tile touched by all 64 scans pays 8 memory round trips, not 64.
+    __shared__ unsigned sRec[kFoldBatch * kTileCells];
+    const unsigned* __restrict__ R = a.records + (size_t)info.x * kTileCells + tid;
+    unsigned pre[kFoldBatch];
+#pragma unroll
+    for (int u = 0; u < kFoldBatch; ++u) pre[u] = (unsigned)u < info.y ? __ldcs(R + (size_t)u * kTileCells) : 0u;
+    for (unsigned j = 0; j < info.y; ++j) {
+        const unsigned u0 = j % kFoldBatch;
+        if (u0 == 0u) {
+#pragma unroll
+            for (int u = 0; u < kFoldBatch; ++u) sRec[u * kTileCells + tid] = pre[u];
+#pragma unroll
+            for (int u = 0; u < kFoldBatch; ++u) {
+                const unsigned jj = j + kFoldBatch + u;
+                pre[u] = jj < info.y ? __ldcs(R + (size_t)jj * kTileCells) : 0u;
+            }
+        }
+        const unsigned rec = sRec[u0 * kTileCells + tid];
+        if (__any_sync(0xffffffffu, f.qn > 64 - (int)kRawMax)) f.drain();
+        const unsigned cnt = rec >> 26;
+        if (cnt <= kRawMax) {                                   // raw (or empty): queue
+            f.q |= (unsigned long long)(rec & ((1u << 26) - 1u)) << f.qn;
+            f.qn += (int)cnt;
+            continue;
+        }
+        f.drain();
+        if (rec == kRecOverflow) {
+            const int4 pr = a.pairs[2 * (size_t)(info.x + j)];
+            const int2* __restrict__ E = a.rel + a.pairs[2 * (size_t)(info.x + j) + 1].x;
+            const int rx = pr.x + (tid & (kTile - 1)), ry = pr.y + (tid >> kTileShift);
+            for (int i = pr.z; i < pr.w; ++i) {
+                const int2 e = __ldg(E + i);
+                const int ty = rayTouch(rx, ry, e.x, e.y);
+                if (ty) f.touch(ty == 2);
+            }
+        } else if (cnt == 31u) {
+            const unsigned* __restrict__ S = a.side + (size_t)(rec & ((1u << 26) - 1u)) * 8u;
+            const unsigned nWords = S[0] >> 16;
+            const uint2* __restrict__ W = reinterpret_cast<const uint2*>(S + 2);
+            uint2 nx = W[0];
+            for (unsigned w = 0; w < nWords; ++w) {
+                unsigned t = nx.x;
+                const unsigned h = nx.y;
+                if (w + 1 < nWords) nx = W[w + 1];
+                while (t) {
+                    const bool hit = (h >> (__ffs(t) - 1)) & 1u;
+                    const unsigned same = hit ? (t & h) : (t & ~h);
+                    const unsigned other = t & ~same;
+                    const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
+                    const unsigned run = same & upto;
+                    f.run(hit, (unsigned)__popc(run));
+                    t &= ~run;
+                }
+            }
+        } else {                                                // three alternating runs
+            const bool first = (rec >> 30) & 1u;
+            f.run(first, (rec >> 20) & 1023u);
+            f.run(!first, (rec >> 10) & 1023u);
+            f.run(first, rec & 1023u);
         }
     }
-}
-
-__global__ void __launch_bounds__(kFoldWarps * 32, 4)
-integ_fold_kernel(const __grid_constant__ FoldArgs a, GridRef g) {
-    extern __shared__ unsigned sRecAll[];                        // [warp][record][lane]
-    const int lane = threadIdx.x & 31;
-    unsigned* sRec = sRecAll + (threadIdx.x >> 5) * (kChunk * 32);
-    int c = 0;
-    unsigned nItems = 0;
-    bool haveChunk = false;
-    for (;;) {
-        // ---- next work item (lane 0 decides, chunk order) ----
-        unsigned item = 0;
-        if (lane == 0) {
-            while (c < a.nChunks) {
-                if (!haveChunk) {
-                    if (!wait_word(a.ready + c, 0u, true, a.abort, 200u)) { c = a.nChunks; break; }
-                    nItems = __ldcg(a.nAct + c) * (unsigned)kSlices;
-                    haveChunk = true;
-                }
-                item = atomicAdd(a.cursor + c, 1u);
-                if (item < nItems) break;
-                ++c; haveChunk = false;
-            }
-        }
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= a.nChunks) break;
-        item = __shfl_sync(0xffffffffu, item, 0);
-        const FoldChunk ch = a.chunks[c];
-        const uint2 at = __ldcg(ch.act + (item / kSlices));
-        const int slice = (int)(item % kSlices);
-        const uint2 info = __ldcg(ch.tileInfo + at.x);
-        const int tx = (int)at.x % ch.tw, ty = (int)at.x / ch.tw;
-        const int cxl = lane & (kTile - 1), cyl = slice * 2 + (lane >> kTileShift);     // cell within the tile
-        const int cx = ch.x0 + tx * kTile + cxl, cy = ch.y0 + ty * kTile + cyl;
-        const bool inside = cx < g.nx && cy < g.ny;
-        // the slice's records do not depend on the cell values: all loads in flight before the wait
-        const unsigned* __restrict__ R = ch.records + (size_t)info.x * kTileCells + slice * 32 + lane;
-        const unsigned cnt = info.y;
-        for (unsigned j0 = 0; j0 < cnt; j0 += 8) {
-            unsigned r8[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r8[u] = j0 + u < cnt ? __ldcg(R + (size_t)(j0 + u) * kTileCells) : 0u;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) if (j0 + u < cnt) sRec[(j0 + u) * 32 + lane] = r8[u];
-        }
-        unsigned* doneSlot = a.done + ((size_t)((ch.y0 >> kTileShift) + ty) * a.latticeW + (ch.x0 >> kTileShift) + tx) * kSlices + slice;
-        bool ok = true;
-        if (lane == 0) ok = wait_word(doneSlot, at.y, false, a.abort, 100u);
-        if (!__shfl_sync(0xffffffffu, ok, 0)) break;
-        double* cell = g.origin + (size_t)cy * g.pitch + cx;
-        const double v0 = inside ? __ldcg(cell) : 0.0;
-        Folder f(a, v0);
-        // Every lane walks its own cell's records at its own pace: an iteration of the warp performs at
-        // most one COMPUTED update per lane (leading touches that cannot change a clamped value are
-        // dropped without arithmetic), so the warp iterates max-over-lanes(computed updates) times.
-        unsigned q = 0u, j = 0u;
-        int qn = 0;
-        for (;;) {
-            while (qn == 0 && j < cnt) {
-                const unsigned rec = sRec[j * 32 + lane];
-                const unsigned n = rec >> 26;
-                if (n <= kRawMax) {                                 // raw (or empty): queue
-                    q = rec & ((1u << 26) - 1u); qn = (int)n;
-                } else if (rec == kRecOverflow) {                   // re-derive the sequence from the beams
-                    const int4 pr = __ldcg(ch.pairs + 2 * (size_t)(info.x + j));
-                    const int2* __restrict__ E = a.rel + __ldcg(ch.pairs + 2 * (size_t)(info.x + j) + 1).x;
-                    const int rx = pr.x + cxl, ry = pr.y + cyl;
-                    for (int i = pr.z; i < pr.w; ++i) {
-                        const int2 e = __ldg(E + i);
-                        const int ty2 = rayTouch(rx, ry, e.x, e.y);
-                        if (ty2) f.touch(ty2 == 2);
-                    }
-                } else if (n == 31u) {                              // raw bitmap words in the side buffer
-                    const unsigned* __restrict__ S = a.side + (size_t)(rec & ((1u << 26) - 1u)) * 8u;
-                    const unsigned nWords = __ldcg(S) >> 16;
-                    const uint2* __restrict__ W = reinterpret_cast<const uint2*>(S + 2);
-                    uint2 nx = __ldcg(W);
-                    for (unsigned w = 0; w < nWords; ++w) {
-                        unsigned t = nx.x;
-                        const unsigned h = nx.y;
-                        if (w + 1 < nWords) nx = __ldcg(W + w + 1);
-                        while (t) {
-                            const bool hit = (h >> (__ffs(t) - 1)) & 1u;
-                            const unsigned same = hit ? (t & h) : (t & ~h);
-                            const unsigned other = t & ~same;
-                            const unsigned upto = other ? ((1u << (__ffs(other) - 1)) - 1u) : 0xFFFFFFFFu;
-                            const unsigned run = same & upto;
-                            f.run(hit, (unsigned)__popc(run));
-                            t &= ~run;
-                        }
-                    }
-                } else {                                            // three alternating runs
-                    const bool first = (rec >> 30) & 1u;
-                    f.run(first, (rec >> 20) & 1023u);
-                    f.run(!first, (rec >> 10) & 1023u);
-                    f.run(first, rec & 1023u);
-                }
-                ++j;
-            }
-            if (qn == 0) break;
-            const bool atLo = f.missSat && f.v == 1e-3, atHi = f.hitSat && f.v == 1.0 - 1e-3;
-            if (atLo || atHi) {                                     // bits at and above qn are zero
-                const unsigned x = atLo ? q : ~q;                   // first touch of the other type
-                const int n = min(qn, x ? __ffs((int)x) - 1 : 32);
-                q >>= n; qn -= n;
-                if (!qn) continue;
-            }
-            const bool hit = q & 1u;
-            f.v = bayesUpdate(f.v, hit ? a.pHit : a.pMiss, hit ? a.oddsHit : a.oddsMiss);
-            ++f.computed;
-            q >>= 1; --qn;
-        }
-        if (a.diag) { atomicMax(a.diag + 2, (unsigned long long)f.computed); atomicAdd(a.diag + 3, (unsigned long long)f.computed); }
-        if (inside && f.v != v0) *cell = f.v;
-        __syncwarp();
-        if (lane == 0) st_release(doneSlot, ch.seq);
-    }
-    if (lane == 0 && ld_acquire(a.abort) != 0u) atomicAdd(a.fail, 1ull);
+    f.drain();
+    if (a.diag) { atomicMax(a.diag + 2, (unsigned long long)f.computed); atomicAdd(a.diag + 3, (unsigned long long)f.computed); }
+    if (inside && f.v != v0) *cell = f.v;
 }
 
 __global__ void grid_shift_copy_kernel(const double* __restrict__ src, int srcNx, int srcNy, int srcPitch,
@@ -782,16 +659,20 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     const bool diag = timing && c->opt.integDiag != 0;   // + per-cell update counts (slows the fold)
     std::vector<cudaEvent_t> evs;
     auto stamp = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
-
-    // ---- plan: chunks of <= 64 scans within the record budget, segments of chunks within the arena budget ----
-    struct Chunk {
-        int cs, ns, x0, y0, tw, subBeams, subLen;
-        size_t nTiles, pairBound;
-        size_t offInfo, offAct, offPairs, offRec, offList;      // byte offsets into the segment's arena
-    };
-    std::vector<Chunk> chunks;
-    size_t maxTiles = 0;
-    for (int s0 = 0; s0 < n;) {
+    // The fold pass runs on a second stream so that it overlaps the next chunk's touch passes
+    // (LGS_INTEG_TIMING serialises everything on the context stream to time the passes).
+    const bool overlap = !timing;
+    if (!w.foldStream) {
+        LGS_CUDA(c, cudaStreamCreateWithFlags(&w.foldStream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            LGS_CUDA(c, cudaEventCreateWithFlags(&w.evTouch[b], cudaEventDisableTiming));
+            LGS_CUDA(c, cudaEventCreateWithFlags(&w.evFold[b], cudaEventDisableTiming));
+        }
+    }
+    bool usedBuf[2] = {false, false};
+    int chunkIdx = 0, lastBuf = -1;
+    int s0 = 0;
+    while (s0 < n) {
         // grow the chunk while it stays within 64 scans and the record budget
         int x0 = grid->nx, y0 = grid->ny, x1 = -1, y1 = -1, subBeams = 0, subLen = 0, ns = 0;
         size_t pairBound = 0;
@@ -818,172 +699,60 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         const size_t nTiles = (size_t)tw * th;
         if (nTiles * kChunk >= ((size_t)1 << 31)) return lgs_fail(c, LGS_ERR_INVALID, "integrate: region of %dx%d tiles is too large", tw, th);
         pairBound = std::min(pairBound, nTiles * ns);
-        chunks.push_back(Chunk{cs, ns, x0, y0, tw, subBeams, subLen, nTiles, pairBound, 0, 0, 0, 0, 0});
-        maxTiles = std::max(maxTiles, nTiles);
-    }
 
-    // Everything is reserved BEFORE the first launch of a segment: growing a buffer frees the old one,
-    // which synchronises the device, and the persistent fold kernel of a segment must never be waited
-    // for by the thread that still has to enqueue the work it is waiting for.
-    const int latticeW = (grid->nx + kTile - 1) / kTile, latticeH = (grid->ny + kTile - 1) / kTile;
-    const size_t latticeTiles = (size_t)latticeW * latticeH;
-    if (w.dirty) { w.cleanTiles = 0; w.dirty = false; }
-    if (!chunks.empty()) {
-        if (maxTiles * kChunk > w.kmin.cap) w.cleanTiles = 0;         // reserve() reallocates
-        LGS_CUDA(c, w.kmin.reserve(maxTiles * kChunk));
-        LGS_CUDA(c, w.kmax.reserve(maxTiles * kChunk));
-        if (latticeTiles > w.lastSeq.cap) {
-            // all earlier folds are complete (every call ends synchronised): the order state starts over
-            LGS_CUDA(c, w.lastSeq.reserve(latticeTiles));
-            LGS_CUDA(c, w.done.reserve(w.lastSeq.cap * kSlices));
-            LGS_CUDA(c, cudaMemsetAsync(w.lastSeq.p, 0, w.lastSeq.cap * sizeof(unsigned), c->stream));
-            LGS_CUDA(c, cudaMemsetAsync(w.done.p, 0, w.done.cap * sizeof(unsigned), c->stream));
-        }
-    }
-    if (!w.foldStream) {
-        LGS_CUDA(c, cudaStreamCreateWithFlags(&w.foldStream, cudaStreamNonBlocking));
-        LGS_CUDA(c, cudaStreamCreateWithFlags(&w.markStream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
-            LGS_CUDA(c, cudaEventCreateWithFlags(&w.evSeg[b], cudaEventDisableTiming));
-            LGS_CUDA(c, cudaEventCreateWithFlags(&w.evFold[b], cudaEventDisableTiming));
-        }
-        for (int b = 0; b < 4; ++b) LGS_CUDA(c, cudaEventCreateWithFlags(&w.evPairs[b], cudaEventDisableTiming));
-        LGS_CUDA(c, cudaEventCreateWithFlags(&w.evTouch, cudaEventDisableTiming));
-        LGS_CUDA(c, cudaFuncSetAttribute(integ_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kFoldWarps * kChunk * 32 * (int)sizeof(unsigned)));
-        // The persistent fold kernel shares every SM with the passes it waits for.  An SM only changes its
-        // L1 / shared-memory split when it is idle, so a kernel whose blocks do not fit the split chosen for
-        // the resident fold CTA would wait for it forever: all kernels of the integration ask for the same
-        // (largest) split.
-        LGS_CUDA(c, cudaFuncSetAttribute(integ_fold_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        LGS_CUDA(c, cudaFuncSetAttribute(integ_touch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        LGS_CUDA(c, cudaFuncSetAttribute(integ_touch_side_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        LGS_CUDA(c, cudaFuncSetAttribute(integ_mark_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        LGS_CUDA(c, cudaFuncSetAttribute(integ_pairs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
-    // The mark / pairs passes run one chunk ahead of the touch pass on their own stream, the fold trails
-    // on a third (LGS_INTEG_TIMING serialises everything on the context stream, one chunk per segment,
-    // to time the passes).
-    const bool overlap = !timing;
-    cudaStream_t ms = overlap ? w.markStream : c->stream, fs = overlap ? w.foldStream : c->stream;
-    if (overlap) {      // the other streams start behind what the context stream has queued (grid acquire, order-state reset)
-        LGS_CUDA(c, cudaEventRecord(w.evTouch, c->stream));
-        LGS_CUDA(c, cudaStreamWaitEvent(ms, w.evTouch, 0));
-    }
-    constexpr size_t kArenaBudget = (size_t)2 << 30;
-    constexpr int kSegChunks = 64;
-    auto align256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    bool usedBuf[2] = {false, false};
-    int segIdx = 0, lastBuf = -1, pairsEv = 0;
-    for (size_t c0 = 0; c0 < chunks.size();) {
-        // segment = chunks [c0, c1): control words, chunk descriptors, then every chunk's buffers
-        size_t c1 = c0;
-        const size_t ctlBytes = align256((5 * kSegChunks + 2) * sizeof(unsigned));
-        const size_t descBytes = align256(kSegChunks * sizeof(FoldChunk));
-        size_t bytes = ctlBytes + descBytes;
-        while (c1 < chunks.size() && (int)(c1 - c0) < (timing ? 1 : kSegChunks)) {
-            Chunk& k = chunks[c1];
-            const size_t need = align256(k.nTiles * sizeof(uint2)) * 2 + align256(2 * k.pairBound * sizeof(int4)) +
-                                align256(k.pairBound * kTileCells * sizeof(unsigned)) + align256(k.pairBound * sizeof(unsigned));
-            if (c1 > c0 && bytes + need > kArenaBudget) break;
-            k.offInfo = bytes;
-            k.offAct = k.offInfo + align256(k.nTiles * sizeof(uint2));
-            k.offPairs = k.offAct + align256(k.nTiles * sizeof(uint2));
-            k.offRec = k.offPairs + align256(2 * k.pairBound * sizeof(int4));
-            k.offList = k.offRec + align256(k.pairBound * kTileCells * sizeof(unsigned));
-            bytes += need;
-            ++c1;
-        }
-        const int nSeg = (int)(c1 - c0);
-        const int buf = segIdx & 1;
-        ++segIdx;
-        // this arena's previous segment (s - 2) must be folded before it is overwritten; waiting on the
-        // host (rarely blocks: the fold trails the touch pass closely) also makes reallocation safe
+        // mark buffers: kept in their reset state by the pair pass; (re)initialise what is new
+        if (w.dirty) { w.cleanTiles = 0; w.dirty = false; }
+        if (nTiles * kChunk > w.kmin.cap) w.cleanTiles = 0;           // reserve() reallocates
+        LGS_CUDA(c, w.kmin.reserve(nTiles * kChunk));
+        LGS_CUDA(c, w.kmax.reserve(nTiles * kChunk));
+        const int buf = chunkIdx & 1;
+        ++chunkIdx;
+        // this buffer's previous fold (chunk k - 2) must be done before it is overwritten; waiting on
+        // the host (rarely blocks: the fold runs two chunks behind) also makes reallocation safe
         if (usedBuf[buf]) LGS_CUDA(c, cudaEventSynchronize(w.evFold[buf]));
-        if (bytes > w.arena[buf].cap || sideCap > w.side[buf].cap) {
-            // growing frees: wait for the other arena's fold first, its kernel may be waiting for work of
-            // ITS segment that is already queued (fine) but never for anything queued after this point
-            LGS_CUDA(c, w.arena[buf].reserve(bytes));
-            LGS_CUDA(c, w.side[buf].reserve(sideCap));
+        LGS_CUDA(c, w.tileInfo[buf].reserve(nTiles));
+        LGS_CUDA(c, w.pairs[buf].reserve(2 * pairBound));
+        LGS_CUDA(c, w.records[buf].reserve(pairBound * kTileCells));
+        LGS_CUDA(c, w.side[buf].reserve(sideCap));
+        if (nTiles > w.cleanTiles) {
+            const size_t a0 = w.cleanTiles, cnt = w.kmin.cap / kChunk - a0;   // initialise up to the capacity
+            LGS_CUDA(c, cudaMemsetAsync(w.kmin.p + a0 * kChunk, 0xFF, cnt * kChunk * sizeof(unsigned), c->stream));
+            LGS_CUDA(c, cudaMemsetAsync(w.kmax.p + a0 * kChunk, 0, cnt * kChunk * sizeof(unsigned), c->stream));
+            w.cleanTiles = w.kmin.cap / kChunk;
         }
-        LGS_CUDA(c, w.hDesc[buf].reserve(descBytes));
-        char* A = w.arena[buf].p;
-        unsigned* ctl = reinterpret_cast<unsigned*>(A);               // [ready | nAct | cursor | nPairs | nSideList][64], side cursor
-        unsigned* dReady = ctl, *dNAct = ctl + kSegChunks, *dCursor = ctl + 2 * kSegChunks, *dNPairs = ctl + 3 * kSegChunks;
-        unsigned* dNList = ctl + 4 * kSegChunks, *dSideCursor = ctl + 5 * kSegChunks, *dAbort = ctl + 5 * kSegChunks + 1;
-        FoldChunk* hDesc = reinterpret_cast<FoldChunk*>(w.hDesc[buf].p);
-        FoldChunk* dDesc = reinterpret_cast<FoldChunk*>(A + ctlBytes);
-        for (int i = 0; i < nSeg; ++i) {
-            const Chunk& k = chunks[c0 + i];
-            hDesc[i] = FoldChunk{reinterpret_cast<const uint2*>(A + k.offInfo), reinterpret_cast<const uint2*>(A + k.offAct),
-                                 reinterpret_cast<const int4*>(A + k.offPairs), reinterpret_cast<const unsigned*>(A + k.offRec),
-                                 k.x0, k.y0, k.tw, w.seq + 1u + (unsigned)i};
-        }
-        LGS_CUDA(c, cudaMemsetAsync(ctl, 0, ctlBytes, ms));
-        LGS_CUDA(c, cudaMemcpyAsync(dDesc, hDesc, nSeg * sizeof(FoldChunk), cudaMemcpyHostToDevice, ms));
-        FoldArgs a{dDesc, nSeg, dReady, dNAct, dCursor, w.done.p, dAbort, latticeW, w.rel.p, w.side[buf].p,
-                   diag ? w.counters.p : nullptr, w.counters.p + 4, pHit, pMiss, oddsHit, oddsMiss};
-        auto launchFold = [&]() -> int {
-            integ_fold_kernel<<<c->sm_count, kFoldWarps * 32, kFoldWarps * kChunk * 32 * sizeof(unsigned), fs>>>(a, g);
-            LGS_LAUNCH_CHECK(c);
-            return LGS_OK;
-        };
-        if (overlap) {
-            LGS_CUDA(c, cudaEventRecord(w.evSeg[buf], ms));
-            LGS_CUDA(c, cudaStreamWaitEvent(fs, w.evSeg[buf], 0));
-            if (int rc = launchFold()) return rc;
-        }
-        for (int i = 0; i < nSeg; ++i) {
-            const Chunk& k = chunks[c0 + i];
-            if (k.nTiles > w.cleanTiles) {
-                const size_t a0 = w.cleanTiles, cnt = w.kmin.cap / kChunk - a0;   // initialise up to the capacity
-                LGS_CUDA(c, cudaMemsetAsync(w.kmin.p + a0 * kChunk, 0xFF, cnt * kChunk * sizeof(unsigned), ms));
-                LGS_CUDA(c, cudaMemsetAsync(w.kmax.p + a0 * kChunk, 0, cnt * kChunk * sizeof(unsigned), ms));
-                w.cleanTiles = w.kmin.cap / kChunk;
-            }
-            w.dirty = true;
-            stamp();
-            const int beamsPad = (k.subBeams + 31) & ~31, pieces = k.subLen / kTile + 1;
-            dim3 gm((unsigned)(((size_t)beamsPad * pieces + 127) / 128), k.ns);
-            integ_mark_kernel<<<gm, 128, 0, ms>>>(dMeta + k.cs, w.rel.p, k.x0, k.y0, k.tw, beamsPad, w.kmin.p, w.kmax.p);
-            LGS_LAUNCH_CHECK(c);
-            stamp();
-            integ_pairs_kernel<<<(unsigned)((k.nTiles * 32 + 127) / 128), 128, 0, ms>>>(
-                (int)k.nTiles, dMeta + k.cs, k.x0, k.y0, k.tw, latticeW, hDesc[i].seq, w.kmin.p, w.kmax.p,
-                reinterpret_cast<uint2*>(A + k.offInfo), reinterpret_cast<int4*>(A + k.offPairs), dNPairs + i,
-                reinterpret_cast<uint2*>(A + k.offAct), dNAct + i, w.lastSeq.p);
-            LGS_LAUNCH_CHECK(c);
-            stamp();
-            w.dirty = false;
-            if (overlap) {
-                LGS_CUDA(c, cudaEventRecord(w.evPairs[pairsEv], ms));
-                LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evPairs[pairsEv], 0));
-                pairsEv = (pairsEv + 1) & 3;
-            }
-            const unsigned touchBlocks = (unsigned)std::min<size_t>(k.pairBound, (size_t)c->sm_count * 4);
-            integ_touch_kernel<<<touchBlocks, kTileCells, 0, c->stream>>>(w.rel.p, reinterpret_cast<int4*>(A + k.offPairs), dNPairs + i,
-                                                                          reinterpret_cast<unsigned*>(A + k.offRec), w.side[buf].p,
-                                                                          dSideCursor, (unsigned)sideCap,
-                                                                          reinterpret_cast<unsigned*>(A + k.offList), dNList + i, w.counters.p);
-            LGS_LAUNCH_CHECK(c);
-            integ_touch_side_kernel<<<(unsigned)std::min<size_t>(k.pairBound, (size_t)c->sm_count), kTileCells, 0, c->stream>>>(
-                w.rel.p, reinterpret_cast<const int4*>(A + k.offPairs), reinterpret_cast<const unsigned*>(A + k.offRec), w.side[buf].p,
-                reinterpret_cast<const unsigned*>(A + k.offList), dNList + i);
-            LGS_LAUNCH_CHECK(c);
-            // publish the chunk to the fold workers (any non-zero word)
-            LGS_CUDA(c, cudaMemsetAsync(dReady + i, 1, sizeof(unsigned), c->stream));
-            stamp();
-            if (!overlap) {
-                // timing mode: one chunk per segment, folded right behind its touch pass
-                if (int rc = launchFold()) return rc;
-            }
-            stamp();
-        }
-        w.seq += (unsigned)nSeg;
+        unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 4 + buf);   // [0] pairs, [1] side-buffer cursor
+        LGS_CUDA(c, cudaMemsetAsync(nPairs, 0, 2 * sizeof(unsigned), c->stream));
+
+        w.dirty = true;
+        stamp();
+        const int beamsPad = (subBeams + 31) & ~31, pieces = subLen / kTile + 1;
+        dim3 gm((unsigned)(((size_t)beamsPad * pieces + 127) / 128), ns);
+        integ_mark_kernel<<<gm, 128, 0, c->stream>>>(dMeta + cs, w.rel.p, x0, y0, tw, beamsPad, w.kmin.p, w.kmax.p);
+        LGS_LAUNCH_CHECK(c);
+        stamp();
+        integ_pairs_kernel<<<(unsigned)((nTiles * 32 + 127) / 128), 128, 0, c->stream>>>((int)nTiles, dMeta + cs, x0, y0, tw, w.kmin.p, w.kmax.p,
+                                                                                       w.tileInfo[buf].p, w.pairs[buf].p, nPairs);
+        LGS_LAUNCH_CHECK(c);
+        stamp();
+        w.dirty = false;
+        const unsigned touchBlocks = (unsigned)std::min<size_t>(pairBound, (size_t)c->sm_count * 4);
+        integ_touch_kernel<<<touchBlocks, kTileCells, 0, c->stream>>>(w.rel.p, w.pairs[buf].p, nPairs, w.records[buf].p,
+                                                                      w.side[buf].p, nPairs + 1, (unsigned)sideCap,
+                                                                      w.counters.p);
+        LGS_LAUNCH_CHECK(c);
+        stamp();
+        // fold on its own stream: it only has to follow this chunk's touch pass and the previous fold
+        LGS_CUDA(c, cudaEventRecord(w.evTouch[buf], c->stream));
+        cudaStream_t fs = overlap ? w.foldStream : c->stream;
+        if (overlap) LGS_CUDA(c, cudaStreamWaitEvent(fs, w.evTouch[buf], 0));
+        FoldArgs a{w.rel.p, w.tileInfo[buf].p, w.pairs[buf].p, w.records[buf].p, w.side[buf].p,
+                   diag ? w.counters.p : nullptr, pHit, pMiss, oddsHit, oddsMiss};
+        integ_fold_kernel<<<(unsigned)nTiles, kTileCells, 0, fs>>>(a, g, x0, y0, tw);
+        LGS_LAUNCH_CHECK(c);
         LGS_CUDA(c, cudaEventRecord(w.evFold[buf], fs));
         usedBuf[buf] = true;
         lastBuf = buf;
-        c0 = c1;
+        stamp();
     }
     tLoop = msSince(tStart);
     if (overlap && lastBuf >= 0) LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evFold[lastBuf], 0));
@@ -995,15 +764,12 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     if (timing) {
         float t[4] = {0, 0, 0, 0};
         for (size_t k = 0; k + 5 <= evs.size(); k += 5)      // 5 stamps per chunk
-            for (int j = 0; j < 4; ++j) { float ms2 = 0; cudaEventElapsedTime(&ms2, evs[k + j], evs[k + j + 1]); t[j] += ms2; }
+            for (int j = 0; j < 4; ++j) { float ms = 0; cudaEventElapsedTime(&ms, evs[k + j], evs[k + j + 1]); t[j] += ms; }
         fprintf(stderr, "[lgs integrate] %d scans: mark %.3f ms, pairs %.3f ms, touch %.3f ms, fold %.3f ms; computed updates: "
-                "max per cell and chunk %llu, total %llu of %llu touches\n", n, t[0], t[1], t[2], t[3],
+                "max per cell and call %llu, total %llu of %llu touches\n", n, t[0], t[1], t[2], t[3],
                 w.hCounters.p[2], w.hCounters.p[3], w.hCounters.p[0]);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
     }
-    if (w.hCounters.p[4] != 0ull)
-        return lgs_fail(c, LGS_ERR_CUDA, "integrate: the fold workers gave up waiting for the touch passes (%llu warps); "
-                        "the grid is incomplete", w.hCounters.p[4]);
     if (nUpdatesOut) *nUpdatesOut = (long long)w.hCounters.p[0];
     w.fallbackCells += (long long)w.hCounters.p[1];
     return LGS_OK;

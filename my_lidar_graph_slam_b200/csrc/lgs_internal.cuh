@@ -94,20 +94,14 @@ struct lgs_integ_ws {
     DevBuf<char> meta;                       // ScanMeta per scan
     DevBuf<int2> rel;                        // per beam: hit cell - sensor cell
     DevBuf<unsigned> kmin, kmax;             // per (tile, scan): beam index range [kmin, kmax)
-    // Segments of chunks alternate between two arenas: the persistent fold kernel of segment s (own
-    // stream) trails the mark / pairs / touch passes of its chunks and may still be on the last ones
-    // while segment s + 1 is being produced into the other arena.
-    DevBuf<char> arena[2];                   // per chunk: tileInfo, active-tile list, pair descriptors, records
+    // Double buffered: the fold pass of chunk k (own stream) overlaps the mark / pairs / touch
+    // passes of chunk k + 1.
+    DevBuf<uint2> tileInfo[2];               // per tile: {first pair, pairs}
+    DevBuf<int4> pairs[2];                   // two int4 per (tile, scan) pair
+    DevBuf<unsigned> records[2];             // per (pair, cell): encoded ordered touch sequence
     DevBuf<unsigned> side[2];                // raw touch / hit bitmap words of sequences no record holds
-    PinBuf<char> hDesc[2];                   // staging of a segment's chunk descriptors
-    // Order of the folds on one cell across chunks: lastSeq = sequence number of the last chunk in which
-    // the tile was active (written by the pair pass, stream ordered), done = sequence number of the last
-    // chunk a (tile, 2-row slice) has been folded for (written by the fold workers).
-    DevBuf<unsigned> lastSeq, done;
-    unsigned seq = 0;                        // chunks integrated by this context so far
-    cudaStream_t foldStream = nullptr, markStream = nullptr;
-    cudaEvent_t evSeg[2] = {nullptr, nullptr}, evFold[2] = {nullptr, nullptr}, evPairs[4] = {nullptr, nullptr, nullptr, nullptr},
-                evTouch = nullptr;
+    cudaStream_t foldStream = nullptr;
+    cudaEvent_t evTouch[2] = {nullptr, nullptr}, evFold[2] = {nullptr, nullptr};
     DevBuf<unsigned long long> counters;
     PinBuf<char> hMeta;
     PinBuf<unsigned long long> hCounters;
@@ -117,19 +111,14 @@ struct lgs_integ_ws {
     void release() {
         sensor.release(); hit.release(); begin.release(); meta.release(); rel.release();
         kmin.release(); kmax.release(); counters.release(); hMeta.release(); hCounters.release();
-        lastSeq.release(); done.release();
         for (int b = 0; b < 2; ++b) {
-            arena[b].release(); side[b].release(); hDesc[b].release();
-            if (evSeg[b]) cudaEventDestroy(evSeg[b]);
+            tileInfo[b].release(); pairs[b].release(); records[b].release(); side[b].release();
+            if (evTouch[b]) cudaEventDestroy(evTouch[b]);
             if (evFold[b]) cudaEventDestroy(evFold[b]);
-            evSeg[b] = evFold[b] = nullptr;
+            evTouch[b] = evFold[b] = nullptr;
         }
-        for (int b = 0; b < 4; ++b) { if (evPairs[b]) cudaEventDestroy(evPairs[b]); evPairs[b] = nullptr; }
-        if (evTouch) cudaEventDestroy(evTouch);
-        evTouch = nullptr;
         if (foldStream) cudaStreamDestroy(foldStream);
-        if (markStream) cudaStreamDestroy(markStream);
-        foldStream = markStream = nullptr;
+        foldStream = nullptr;
         cleanTiles = 0;
     }
 };
