@@ -222,16 +222,21 @@ class C4Shard:
     """The submaps `ids` of the C4 scene on one context (grids + pyramids), and the loop-detection steps
     of one rank against them."""
 
-    def __init__(self, ctx, scene, ids):
+    def __init__(self, ctx, scene, ids, reuse=None):
         from my_lidar_graph_slam_b200 import capi
         world, angles, anchor, self.qscans, self.qinits = scene
         self.ctx, self.angles, self.ids = ctx, angles, np.asarray(ids, dtype=np.int64)
         self.grids, self.pyramids, self.cells = [], [], 0
+        reuse = reuse or {}                                   # submap id -> grid already on this device (re-placement)
         for g in self.ids:
-            traj, scans = c4_submap_scans(world, angles, int(g), 8, anchor)
-            grid, _ = build_map_on_gpu(ctx, traj, angles, scans, apron=1)
+            grid = reuse.pop(int(g), None)
+            if grid is None:
+                traj, scans = c4_submap_scans(world, angles, int(g), 8, anchor)
+                grid, _ = build_map_on_gpu(ctx, traj, angles, scans, apron=1)
             self.grids.append(grid)
             self.cells += grid.nx * grid.ny
+        for grid in reuse.values():
+            grid.close()
         # the first build of the pyramids grows the stream-ordered memory pool (one-time cost); the timed
         # build is a REbuild of every pyramid, which is what the loop detector does whenever a submap
         # has changed (loop_detector_branch_bound.cpp:44-53)
@@ -259,6 +264,48 @@ class C4Shard:
                 ids=np.concatenate([k * n_submaps_total + self.ids for k in ks]) if nq else np.zeros(0, dtype=np.int64)))
         return out
 
+    def submap_cost_terms(self, n_submaps_total, thr=0.6):
+        """One plain step of all query scans against this shard's submaps with the kernel's phase clock on:
+        (deep nodes scored per submap, [root us, root nodes, deeper-level us, deeper-level nodes]).  Root
+        nodes are the same for every pair; what differs between submaps is how deep the search goes, and a
+        node of a deeper level costs more than a root node (scattered parents), so the placement weighs
+        the two with their measured times."""
+        from my_lidar_graph_slam_b200 import capi
+        deep = np.zeros(n_submaps_total, dtype=np.float64)
+        terms = np.zeros(4, dtype=np.float64)
+        nq = len(self.ids)
+        if nq == 0:
+            return deep, terms
+        sub = c4_sub_scans(len(self.qscans), nq)
+        self.ctx.set_option("bb_host_timing", 1)
+        try:
+            for g in self.groups(len(self.qscans), n_submaps_total, sub):
+                b = capi.BbBatch(self.ctx, **BB)
+                b.upload_pairs(g["scans"], g["pair_scan"], g["pyr"], thr)
+                b.run()
+                res = b.results_array()
+                b.run()                                           # pools sized: a clean device-only run to time
+                res = b.results_array()
+                us, _ = b.phase_times()
+                levels, _ = b.work()
+                roots = levels[-1] / max(len(g["ids"]), 1)
+                np.add.at(deep, g["ids"] % n_submaps_total, res["n_scored"].astype(np.float64) - roots)
+                H = len(levels) - 1
+                terms += [us[1], levels[-1], float(sum(us[2:2 + H])), float(sum(levels[:-1]))]
+                b.close()
+        finally:
+            self.ctx.set_option("bb_host_timing", 0)
+        return deep, terms
+
+    def release_grids(self):
+        """Close the pyramids and hand the grids over (submap id -> grid) to the shard that replaces this one."""
+        for p in self.pyramids:
+            p.close()
+        self.pyramids = []
+        out = {int(g): grid for g, grid in zip(self.ids, self.grids)}
+        self.grids = []
+        return out
+
     def close(self):
         for p in self.pyramids:
             p.close()
@@ -275,7 +322,7 @@ def c4_sub_scans(n_scans, nq):
     return max(1, min(n_scans, -(-8000 // max(nq, 1))))
 
 
-def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_over_ranks, thr=0.6):
+def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_over_ranks, thr=0.6, placement=None):
     """Time the loop-detection step `n_scans` query scans x `n_submaps` submaps with this rank's shard:
     kernels only (inputs resident) and end to end (host scans in, gathered records out).
     lanes = [(ctx, comm), (ctx2, comm2)]: the end-to-end value pipelines consecutive steps over the two
@@ -288,8 +335,10 @@ def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_
     sub = c4_sub_scans(n_scans, nq)
     groups = shard.groups(n_scans, n_submaps, sub)
     seg = []
+    if placement is None:
+        placement = sharding.round_robin_placement(n_submaps, world)
     for r in range(world):
-        cnt = len(sharding.owned(n_submaps, r, world))
+        cnt = len(placement[r])
         seg.append([cnt * len(range(k0, min(k0 + sub, n_scans))) for k0 in range(0, n_scans, sub)])
     L = []
     for ctx_l, comm_l in lanes:
@@ -300,9 +349,19 @@ def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_
         L.append(dict(ctx=ctx_l, ex=ex, batches=batches))
     ctx = L[0]["ctx"]
 
+    lane_order = world > 1 and os.environ.get("LGS_C4_LANE_ORDER", "0") != "0"   # measured at 8 GPUs: no gain
+
     def submit(lane):
         for b, g in zip(lane["batches"], groups):
             b.upload_pairs(g["scans"], g["pair_scan"], g["pyr"], thr)
+        if lane_order:
+            # the uploads above may run under the other lane's kernels; this lane's persistent kernels (which
+            # take every SM) start only behind the other lane's record exchange, whose NCCL kernel would
+            # otherwise wait a whole step for an SM
+            for other in L:
+                if other is not lane:
+                    lane["ctx"].wait_for(other["ctx"])
+        for b in lane["batches"]:
             b.run()
         lane["ex"].launch_gather()
 
@@ -886,10 +945,33 @@ def run_b200(args, rank, world_size, local_rank):
         t0 = time.perf_counter()
         shard = C4Shard(ctx, scene, mine)
         build_s = time.perf_counter() - t0
-        single, rec1 = c4_steps(lanes, shard, rank, world_size, args.submaps, 1, steps_side, barrier, max_over_ranks)
+        placement, balance = None, None
+        if world_size > 1 and os.environ.get("LGS_C4_PLACEMENT", "lpt") != "rr":
+            # cost-aware placement: the nodes scored against every submap in one plain step under round-robin
+            # placement (all-reduced), spread over the ranks longest-first; the submaps that changed owner are
+            # rebuilt there.  A few submaps (the true loop candidates) carry half of the work.
+            import torch
+            deep, terms = shard.submap_cost_terms(args.submaps)
+            wt = torch.from_numpy(np.concatenate([deep, terms])).to(f"cuda:{local_rank}")
+            dist.all_reduce(wt)
+            wt = wt.cpu().numpy()
+            deep, terms = wt[:args.submaps], wt[args.submaps:]
+            us_root = terms[0] / max(terms[1], 1.0)               # us per root node, us per deeper node
+            us_deep = terms[2] / max(terms[3], 1.0)
+            weights = us_root * (terms[1] / args.submaps) + us_deep * np.maximum(deep, 0.0)
+            placement = sharding.balanced_placement(weights, world_size)
+            rr = [float(weights[sharding.owned(args.submaps, r, world_size)].sum()) for r in range(world_size)]
+            lp = [float(weights[p].sum()) for p in placement]
+            balance = {"round_robin_max_over_mean": max(rr) / (sum(rr) / world_size),
+                       "lpt_max_over_mean": max(lp) / (sum(lp) / world_size),
+                       "ns_per_root_node": 1e3 * us_root, "ns_per_deeper_node": 1e3 * us_deep}
+            mine = placement[rank]
+            shard = C4Shard(ctx, scene, mine, reuse=shard.release_grids())
+        single, rec1 = c4_steps(lanes, shard, rank, world_size, args.submaps, 1, steps_side, barrier, max_over_ranks,
+                                placement=placement)
         batched, recq = c4_steps(lanes, shard, rank, world_size, args.submaps, C4_SCANS, max(2, steps_side // 2),
-                                 barrier, max_over_ranks)
-        c4 = {"single": single, "batched": batched, "submaps_rank0": int(len(mine)),
+                                 barrier, max_over_ranks, placement=placement)
+        c4 = {"single": single, "batched": batched, "submaps_rank0": int(len(mine)), "placement": balance,
               "pyramid_rebuild_ms_rank0": shard.pyramid_ms, "submap_build_s_rank0": build_s,
               "pyramid_cells_levels_per_s_rank0": shard.cells * 7 / (shard.pyramid_ms * 1e-3) if shard.pyramid_ms > 0 else None}
         c4["gathers_all"] = sum_over_ranks(float(batched["gathers_rank0"]))
@@ -1037,7 +1119,10 @@ def run_b200(args, rank, world_size, local_rank):
             "warmup": 3, "ms_per_step": r3(b["ms"], 6), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": c4_config(args.submaps, world_size),
-            "l2": "pyramids >> L2", "parallelism": f"submap i on rank i%{world_size}, in-place NCCL all-gather",
+            "l2": "pyramids >> L2",
+            "parallelism": ("submaps on ranks by measured cost (LPT), " if c4.get("placement") else f"submap i on rank i%{world_size}, ") +
+                           "in-place NCCL all-gather",
+            "placement": ({k: r3(v) for k, v in c4["placement"].items()} if c4.get("placement") else None),
             "e2e": {"value": r3(b["qps_e2e"], 6), "unit": C4_UNIT, "h2d_bytes_per_step": b["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": b["d2h_bytes_per_step"], "sequential_value": r3(b["qps_e2e_sequential"])},
             "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]),

@@ -60,6 +60,11 @@ int lgs_ctx_create(int device, lgs_ctx** out);
 int lgs_ctx_destroy(lgs_ctx* ctx);
 const char* lgs_ctx_last_error(const lgs_ctx* ctx);
 int lgs_ctx_synchronize(lgs_ctx* ctx);
+/* Stream order across two contexts of one device: everything enqueued on `ctx` after this call runs
+ * after everything enqueued on `other` before it (an event wait, nothing blocks on the host).  Used by
+ * callers that pipeline steps over two contexts and need step k's record exchange to get its SMs
+ * before step k + 1's persistent kernel takes all of them. */
+int lgs_ctx_wait_ctx(lgs_ctx* ctx, lgs_ctx* other);
 /* The cudaStream_t every call on this context is ordered on (for event timing). */
 void* lgs_ctx_stream(lgs_ctx* ctx);
 /* CUDA-event stopwatch on the context stream: start, enqueue work, stop -> milliseconds. */

@@ -87,6 +87,7 @@ SIGNATURES = {
     "lgs_ctx_destroy": (C.c_int, [vp]),
     "lgs_ctx_last_error": (C.c_char_p, [vp]),
     "lgs_ctx_synchronize": (C.c_int, [vp]),
+    "lgs_ctx_wait_ctx": (C.c_int, [vp, vp]),
     "lgs_ctx_stream": (vp, [vp]),
     "lgs_ctx_timer_start": (C.c_int, [vp]),
     "lgs_ctx_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
@@ -190,6 +191,10 @@ class Context:
 
     def synchronize(self):
         self.check(lib().lgs_ctx_synchronize(self.h))
+
+    def wait_for(self, other: "Context"):
+        """Stream order: what this context enqueues from now on runs after what `other` has enqueued so far."""
+        self.check(lib().lgs_ctx_wait_ctx(self.h, other.h))
 
     def stream(self) -> int:
         return lib().lgs_ctx_stream(self.h) or 0

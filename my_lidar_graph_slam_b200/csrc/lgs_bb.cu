@@ -695,6 +695,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     b->maxRoots = 0; b->maxNTpad = 0; b->maxUse = 0; b->spanX = 0; b->spanY = 0;
     b->maxAbsCells = 0.0; b->maxReachCells = 0.0;
     long long nTab = 0, roots = 0, nHits = 0, nHitsT = 0;
+    int projTiles = 0;
     const int winSizeMax = 1 << H;
     // Pairs that name the same scan share its projected hit points (1 scan x many submaps).
     std::vector<int> scanToUnique(std::max(scans->n_scans, 1), -1);
@@ -799,7 +800,9 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
             u.nUse = (int)b->hAngles.size() - u.beamBegin;
             u.hitBegin = nHits;
             nHits += (long long)u.nUse * u.nTpad;
-            u.beamPad = (u.nUse + 3) / 4 * 4; u.pad0 = 0;
+            u.beamPad = (u.nUse + 3) / 4 * 4;
+            u.projBegin = projTiles;
+            projTiles += ((u.nUse + 7) / 8) * ((u.nT + 31) / 32);
             u.hitTBegin = nHitsT;
             nHitsT += (long long)u.nT * u.beamPad;
             b->maxAbsCells = std::max(b->maxAbsCells, (std::max(std::fabs(u.sx), std::fabs(u.sy)) + reach) * d.invRes);
@@ -841,6 +844,7 @@ int lgs_bb_batch_upload_pairs(lgs_bb_batch* b, const lgs_scan_batch* scans, int 
     b->nTab = nTab;
     b->nHits = nHits;
     b->nHitsT = nHitsT;
+    b->projTiles = projTiles;
     b->totalRoots = (int)roots;
     const size_t nu = b->us.size();
     {   // group the queries by distinct scan; kIdxChunk per index-kernel block (exact path)

@@ -30,7 +30,7 @@ struct BbScan {                     // one per DISTINCT (scan, sensor pose, map 
     int nrx, nry, winX, winY;       // root lattice of its queries (same resolution => same window)
     long long hitBegin;             // into the hit arrays: nUse * nTpad, beam-major ([beam][theta])
     long long hitTBegin;            // into the transposed hit array: nT * beamPad ([theta][beam]), device-only run
-    int beamPad, pad0;              // nUse padded to a multiple of 4
+    int beamPad, projBegin;         // nUse padded to a multiple of 4; first 8 x 32 (beam, theta) projection tile of this scan
     double invRes;                  // 1 / resolution of the maps this scan is matched against
     double originX, originY;        // floor(sensor * invRes): the cell the 12.20 fixed-point hit points are relative to
 };
@@ -106,6 +106,7 @@ struct RunArgs {
     int recStatus;                  // also write the run's status record at slot recFirst + nq
     int nq, nu, H;
     int totalRoots, rootTiles, rootG;
+    int projTiles;                  // 8 x 32 (beam, theta) tiles of the hit-point projection, all scans
     unsigned edgeUnits;             // guard band in 2^-20 cells
     int resolveUlps;
     int forceReplay;
@@ -132,6 +133,7 @@ struct lgs_bb_batch {
     std::vector<long long> ids;     // record ids (empty: the query index)
     std::vector<int> fixups;
     long long nTab = 0, nHits = 0, nHitsT = 0;
+    int projTiles = 0;              // 8 x 32 (beam, theta) projection tiles of the batch's distinct scans
     double maxReachCells = 0.0;     // longest usable beam of the batch in cells (12.20 fixed-point range check)
     int totalRoots = 0;
     double maxAbsCells = 0.0;       // largest |coordinate| * invRes of the batch (fixed-point range check)

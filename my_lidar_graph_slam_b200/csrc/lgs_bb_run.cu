@@ -425,26 +425,55 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) bb_run_kernel(const __gr
         b.rankLeaf = ~0ull; b.fixups = 0; b.pad = 0;
         a.best[q] = b;
     }
-    for (int u = 0; u < a.nu; ++u) {
-        const BbScan& s = a.us[u];
-        const long long total = (long long)s.nUse * s.nTpad;
-        for (long long idx = gt; idx < total; idx += nt) {
-            const int i = (int)(idx / s.nTpad), t = (int)(idx - (long long)i * s.nTpad);
-            if (t >= s.nT) continue;
-            // nodePose.mTheta = sensorPose.mTheta + node.mTheta * stepTheta (scan_matcher_branch_bound.cpp:96-99)
-            const double theta = __dadd_rn(s.st, __dmul_rn((double)(t - s.winT), s.stepT));
-            const double ang = __dadd_rn(theta, a.angles[s.beamBegin + i]);
-            double sn, cs;
-            sincos(ang, &sn, &cs);
-            const double r = a.ranges[s.beamBegin + i];
-            const double hx = __dadd_rn(s.sx, __dmul_rn(r, cs));          // sensor_data.hpp:171-172
-            const double hy = __dadd_rn(s.sy, __dmul_rn(r, sn));
-            // 12.20 fixed-point cells relative to the scan origin, in both layouts
-            const int2 hp = make_int2(__double2int_rn(__dmul_rn(__dsub_rn(__dmul_rn(hx, s.invRes), s.originX), 1048576.0)),
-                                      __double2int_rn(__dmul_rn(__dsub_rn(__dmul_rn(hy, s.invRes), s.originY), 1048576.0)));
-            a.hits[s.hitBegin + idx] = hp;
-            a.hitsT[s.hitTBegin + (long long)t * s.beamPad + i] = hp;
+    // Hit points: a warp takes an 8 x 32 tile of (beam, theta) of one scan; a lane owns one theta.  The
+    // [beam][theta] copy is written straight from the registers (a row of thetas per beam), the
+    // [theta][beam] copy through the warp's staging rows (64-byte runs of eight beams per theta).
+    for (int tile = gw; tile < a.projTiles; tile += tw) {
+        int lo = 0, hi = a.nu;                          // scan of this tile: projBegin[lo] <= tile < projBegin[lo + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.us[mid].projBegin <= tile) lo = mid; else hi = mid;
         }
+        const BbScan& s = a.us[lo];
+        const int rel = tile - s.projBegin;
+        const int nTT = (s.nT + 31) >> 5;
+        const int i0 = (rel / nTT) << 3, t = ((rel % nTT) << 5) + lane;
+        // nodePose.mTheta = sensorPose.mTheta + node.mTheta * stepTheta (scan_matcher_branch_bound.cpp:96-99)
+        const double theta = __dadd_rn(s.st, __dmul_rn((double)(t - s.winT), s.stepT));
+        const bool tOk = t < s.nT;
+        int2* stage = reinterpret_cast<int2*>(svw);     // [8 beams][33]
+        double ang8[8], r8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = min(i0 + u, s.nUse - 1);
+            ang8[u] = a.angles[s.beamBegin + i];
+            r8[u] = a.ranges[s.beamBegin + i];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u;
+            int2 hp = make_int2(0, 0);
+            if (i < s.nUse && tOk) {
+                double sn, cs;
+                sincos(__dadd_rn(theta, ang8[u]), &sn, &cs);
+                const double hx = __dadd_rn(s.sx, __dmul_rn(r8[u], cs));          // sensor_data.hpp:171-172
+                const double hy = __dadd_rn(s.sy, __dmul_rn(r8[u], sn));
+                // 12.20 fixed-point cells relative to the scan origin
+                hp = make_int2(__double2int_rn(__dmul_rn(__dsub_rn(__dmul_rn(hx, s.invRes), s.originX), 1048576.0)),
+                               __double2int_rn(__dmul_rn(__dsub_rn(__dmul_rn(hy, s.invRes), s.originY), 1048576.0)));
+                a.hits[s.hitBegin + (long long)i * s.nTpad + t] = hp;
+            }
+            stage[u * 33 + lane] = hp;
+        }
+        __syncwarp();
+        const int ub = lane & 7;                        // beam within the group of eight
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int tl = (lane >> 3) + 4 * k, tt = (t - lane) + tl;
+            const int i = i0 + ub;
+            if (tt < s.nT && i < s.nUse) a.hitsT[s.hitTBegin + (long long)tt * s.beamPad + i] = stage[ub * 33 + tl];
+        }
+        __syncwarp();
     }
     grid.sync();
     stamp();
@@ -627,6 +656,7 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
     a.recStatus = 1;
     a.nq = n; a.nu = (int)b->us.size(); a.H = H;
     a.totalRoots = b->totalRoots;
+    a.projTiles = b->projTiles;
     a.costUs[0] = (float)c->opt.bbCost[0]; a.costUs[1] = (float)c->opt.bbCost[1];
     a.costUs[2] = (float)c->opt.bbCost[2]; a.costUs[3] = (float)c->opt.bbCost[3];
     {   // root mapping: same cost model as the device uses for the deeper levels

@@ -173,6 +173,15 @@ int lgs_ctx_synchronize(lgs_ctx* c) {
     return LGS_OK;
 }
 
+int lgs_ctx_wait_ctx(lgs_ctx* c, lgs_ctx* other) {
+    if (!c || !other) return LGS_ERR_INVALID;
+    if (c == other) return LGS_OK;
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaEventRecord(c->evOrder, other->stream));
+    LGS_CUDA(c, cudaStreamWaitEvent(c->stream, c->evOrder, 0));
+    return LGS_OK;
+}
+
 int lgs_host_pin(lgs_ctx* c, void* ptr, unsigned long long bytes) {
     if (!c || !ptr || bytes == 0) return LGS_ERR_INVALID;
     LGS_CUDA(c, cudaSetDevice(c->device));
