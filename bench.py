@@ -288,8 +288,7 @@ class C4Shard:
                 res = b.results_array()
                 us, _ = b.phase_times()
                 levels, _ = b.work()
-                roots = levels[-1] / max(len(g["ids"]), 1)
-                np.add.at(deep, g["ids"] % n_submaps_total, res["n_scored"].astype(np.float64) - roots)
+                np.add.at(deep, g["ids"] % n_submaps_total, b.query_nodes(len(g["ids"])).astype(np.float64))
                 H = len(levels) - 1
                 terms += [us[1], levels[-1], float(sum(us[2:2 + H])), float(sum(levels[:-1]))]
                 b.close()
@@ -349,7 +348,7 @@ def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_
         L.append(dict(ctx=ctx_l, ex=ex, batches=batches))
     ctx = L[0]["ctx"]
 
-    lane_order = world > 1 and os.environ.get("LGS_C4_LANE_ORDER", "0") != "0"   # measured at 8 GPUs: no gain
+    lane_order = world > 1 and os.environ.get("LGS_C4_LANE_ORDER", "1") != "0"   # 8 GPUs: 6.9 -> 7.5 M queries/s end to end
 
     def submit(lane):
         for b, g in zip(lane["batches"], groups):
@@ -404,8 +403,21 @@ def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_
     for _ in range(steps):
         for b in batches:
             b.run()
-    dev_ms = max_over_ranks(ctx.timer_stop())
+    dev_ms_local = ctx.timer_stop()
+    dev_ms = max_over_ranks(dev_ms_local)
     launches = ctx.launch_count() - launches0
+    if os.environ.get("LGS_C4_RANK_DIAG"):                      # per-rank kernel time / work of this step shape (scratch)
+        ctx.set_option("bb_host_timing", 1)
+        ph = []
+        for b in batches:
+            b.run()
+            b.results_array()
+            ph.append([round(float(x), 1) for x in b.phase_times()[0]])
+        ctx.set_option("bb_host_timing", 0)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"c4_rank{rank}_of{world}_q{n_scans}.json"), "w") as f:
+            json.dump({"rank": rank, "submaps": int(nq), "ms_per_step": dev_ms_local / steps, "phases_us": ph,
+                       "levels": [b.work()[0] for b in batches]}, f)
     nodes, gathers, dev_runs, exact_runs = 0, 0, 0, 0
     for b in batches:
         lv, ga = b.work()
@@ -930,6 +942,8 @@ def run_b200(args, rank, world_size, local_rank):
     hbm_peak, hbm_src = measured_peaks()
     details = {"n_gpus": world_size}
     steps_side = max(3, min(args.steps, 10))
+    # timed steps of the 64-scan loop-detection batch: the headline at N > 1 times exactly --steps of them
+    c4_nsteps = max(2, args.steps) if world_size > 1 else max(4, steps_side)
 
     # ---- C2 (headline at N = 1, `extra.c2_replicas` at N > 1) ------------------------------------------------
     c2 = measure_c2(ctx, local_rank, args, barrier, max_over_ranks, sum_over_ranks, rank == 0)
@@ -969,7 +983,7 @@ def run_b200(args, rank, world_size, local_rank):
             shard = C4Shard(ctx, scene, mine, reuse=shard.release_grids())
         single, rec1 = c4_steps(lanes, shard, rank, world_size, args.submaps, 1, steps_side, barrier, max_over_ranks,
                                 placement=placement)
-        batched, recq = c4_steps(lanes, shard, rank, world_size, args.submaps, C4_SCANS, max(2, steps_side // 2),
+        batched, recq = c4_steps(lanes, shard, rank, world_size, args.submaps, C4_SCANS, c4_nsteps,
                                  barrier, max_over_ranks, placement=placement)
         c4 = {"single": single, "batched": batched, "submaps_rank0": int(len(mine)), "placement": balance,
               "pyramid_rebuild_ms_rank0": shard.pyramid_ms, "submap_build_s_rank0": build_s,
@@ -984,7 +998,7 @@ def run_b200(args, rank, world_size, local_rank):
                 nb = lambda: None
                 solo = [(ctx, None), (ctx_b, None)]
                 s1, r1 = c4_steps(solo, full, 0, 1, args.submaps, 1, steps_side, nb, lambda x: x)
-                sq, rq = c4_steps(solo, full, 0, 1, args.submaps, C4_SCANS, max(2, steps_side // 2), nb, lambda x: x)
+                sq, rq = c4_steps(solo, full, 0, 1, args.submaps, C4_SCANS, c4_nsteps, nb, lambda x: x)
                 full.close()
                 n1 = {"single": s1, "batched": sq,
                       "records_identical": bool(r1.tobytes() == rec1.tobytes() and rq.tobytes() == recq.tobytes())}
@@ -1115,7 +1129,7 @@ def run_b200(args, rank, world_size, local_rank):
     else:
         b = c4["batched"]
         line = {
-            "metric": C4_METRIC, "value": r3(b["qps"], 6), "unit": C4_UNIT, "n_gpus": world_size, "steps": max(2, steps_side // 2),
+            "metric": C4_METRIC, "value": r3(b["qps"], 6), "unit": C4_UNIT, "n_gpus": world_size, "steps": c4_nsteps,
             "warmup": 3, "ms_per_step": r3(b["ms"], 6), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": c4_config(args.submaps, world_size),
@@ -1128,7 +1142,7 @@ def run_b200(args, rank, world_size, local_rank):
             "single_scan": {"value": r3(c4["single"]["qps"]), "e2e": r3(c4["single"]["qps_e2e"]),
                             "e2e_seq": r3(c4["single"]["qps_e2e_sequential"]), "ms": r3(c4["single"]["ms"])},
             "records_sha256": b["sha"], "loops_found": b["found"],
-            "gpu_launches": int(round(b["launches_per_step"] * max(2, steps_side // 2))), "clocks": c2["clocks"],
+            "gpu_launches": int(round(b["launches_per_step"] * c4_nsteps)), "clocks": c2["clocks"],
             "roofline": gather_roofline(c4["gathers_all"] * 8 / (b["ms"] * 1e-3) / 1e9, gpeak, sm_mhz, world_size,
                                         "bb_run_kernel<16,2>", hbm_peak),
             "cpu_baseline": None,

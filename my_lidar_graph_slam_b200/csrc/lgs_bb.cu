@@ -1022,6 +1022,22 @@ int lgs_bb_batch_phase_times(lgs_bb_batch* b, double* us, int* mapping, int n) {
     return LGS_OK;
 }
 
+// Diagnostic ("bb_host_timing" must be on before the run): nodes[q] = nodes of the levels below the root
+// that the last device-only run scored for query q (the root level is the same for every query of a
+// scan).  What a cost-aware placement of submaps on devices weighs (sharding.balanced_placement).
+int lgs_bb_batch_query_nodes(lgs_bb_batch* b, long long* nodes, int n) {
+    if (!b || !nodes || n < b->nq) return LGS_ERR_INVALID;
+    lgs_ctx* c = b->ctx;
+    if (!b->lastRunDevice || !c->opt.bbHostTiming) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_query_nodes: needs a device-only run with bb_host_timing on");
+    { const int rc = bb_settle(b); if (rc != LGS_OK) return rc; }
+    std::vector<BbBest> best(b->nq);
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaMemcpyAsync(best.data(), b->dBest.p, (size_t)b->nq * sizeof(BbBest), cudaMemcpyDeviceToHost, c->stream));
+    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < b->nq; ++q) nodes[q] = best[q].pad;
+    return LGS_OK;
+}
+
 int lgs_bb_batch_path(const lgs_bb_batch* b, long long* deviceRuns, long long* exactRuns) {
     if (!b) return LGS_ERR_INVALID;
     if (deviceRuns) *deviceRuns = b->deviceRuns;

@@ -110,6 +110,7 @@ struct RunArgs {
     unsigned edgeUnits;             // guard band in 2^-20 cells
     int resolveUlps;
     int forceReplay;
+    int countNodes;                 // count the nodes of the deeper levels per query (BbBest::pad)
     float costUs[4];                // per-pass cost model of the G = 1 / 4 / 8 / 32 mappings (us)
     unsigned long long* phaseNs;    // [kPhases] globaltimer at the phase boundaries (diagnostic)
     int* phaseG;                    // [kMaxLevels] warp mapping used per level (diagnostic)

@@ -297,6 +297,7 @@ __device__ __forceinline__ void expand(const RunArgs& a, int h, int k, const Nod
                 survive = true;
         }
     }
+    if (a.countNodes && survive) atomicAdd(&a.best[n.q].pad, 4);        // nodes of the deeper levels, per query (placement weights)
     int childBase = -1, childStride = 0;
     const unsigned m = __ballot_sync(0xffffffffu, survive);
     if (m != 0u) {
@@ -681,6 +682,7 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
     }
     a.resolveUlps = std::max(c->opt.bbResolveUlps, 0);
     a.forceReplay = b->forceReplay ? 1 : 0;
+    a.countNodes = c->opt.bbHostTiming ? 1 : 0;
     void* params[] = {&a};
     LGS_CUDA(c, cudaLaunchCooperativeKernel(kernel, dim3(c->bbBlocks), dim3(kThreads), params, 0,
                                             c->stream));
