@@ -79,6 +79,10 @@ private:
     std::map<int, DeviceMap>      mDeviceMaps;
     std::vector<double>           mDense;
     std::vector<lgs_match_result> mLast;
+    /* Nodes scored so far against the local maps of every device: a new local map goes to the
+     * device that has carried the least work (the true loop candidates cost ~40x the others) */
+    std::vector<double>           mMemberLoad;
+    std::vector<int>              mMemberMaps;
     bool                          mDeviceCost;
     lgs_cost_params               mCostParams;
 };

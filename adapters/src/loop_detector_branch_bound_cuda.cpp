@@ -59,6 +59,13 @@ LoopDetectorBranchBoundCuda::LoopDetectorBranchBoundCuda(
                &this->mGroup), "lgs_group_create (peer-capable B200s are required)");
     CheckGroup(this->mGroup, lgs_group_bb_create(this->mGroup, &this->mParams, &this->mDetector),
                "lgs_group_bb_create");
+    const int numOfMembers = lgs_group_size(this->mGroup);
+    this->mMemberLoad.assign(numOfMembers, 0.0);
+    this->mMemberMaps.assign(numOfMembers, 0);
+    /* lgs_match_result::n_scored per pair (not per batch): the cost the placement balances */
+    for (int m = 0; m < numOfMembers; ++m)
+        Check(lgs_group_ctx(this->mGroup, m), lgs_ctx_set_option(lgs_group_ctx(this->mGroup, m),
+              "bb_count_nodes", 1.0), "lgs_ctx_set_option(bb_count_nodes)");
 }
 
 LoopDetectorBranchBoundCuda::~LoopDetectorBranchBoundCuda()
@@ -72,8 +79,9 @@ LoopDetectorBranchBoundCuda::~LoopDetectorBranchBoundCuda()
 }
 
 /* Device pyramid of a local map: built on first use, rebuilt when the builder has reset
- * mPrecomputed after a loop closure (loop_detector_branch_bound.cpp:51-60).  Local map i lives on
- * device i mod G.  Every LoopDetectionQuery carries its own COPY of LocalMapInfo, so a second
+ * mPrecomputed after a loop closure (loop_detector_branch_bound.cpp:51-60).  A new local map goes
+ * to the device that has scored the fewest nodes so far (ties: fewest maps, lowest index -- round
+ * robin while nothing has been measured); a rebuilt one stays where it is.  Every LoopDetectionQuery carries its own COPY of LocalMapInfo, so a second
  * query of the same Detect() call that names the same local map still says mPrecomputed == false:
  * `builtThisCall` keeps it from destroying the pyramid the batch under construction points to. */
 lgs_pyramid* LoopDetectorBranchBoundCuda::PyramidFor(
@@ -86,14 +94,22 @@ lgs_pyramid* LoopDetectorBranchBoundCuda::PyramidFor(
         localMapInfo.mPrecomputed = true;
         return it->second.mPyramid;
     }
+    const int numOfMembers = lgs_group_size(this->mGroup);
+    int member = 0;
     if (it != this->mDeviceMaps.end()) {
+        member = it->second.mMember;
         lgs_pyramid_destroy(it->second.mPyramid);
         lgs_grid_destroy(it->second.mGrid);
         this->mDeviceMaps.erase(it);
+    } else {
+        for (int m = 1; m < numOfMembers; ++m)
+            if (this->mMemberLoad[m] < this->mMemberLoad[member] ||
+                (this->mMemberLoad[m] == this->mMemberLoad[member] &&
+                 this->mMemberMaps[m] < this->mMemberMaps[member]))
+                member = m;
+        this->mMemberMaps[member]++;
     }
     const GridMapType& map = localMapInfo.mMap;
-    const int numOfMembers = lgs_group_size(this->mGroup);
-    const int member = ((localMapInfo.mIdx % numOfMembers) + numOfMembers) % numOfMembers;
     lgs_ctx* ctx = lgs_group_ctx(this->mGroup, member);
     DeviceMap dev { nullptr, nullptr, member };
     Check(ctx, lgs_grid_create(ctx, map.NumOfGridCellsX(),
@@ -158,6 +174,18 @@ void LoopDetectorBranchBoundCuda::Detect(
          * device, records exchanged on the devices (lgs_group_bb_detect) */
         CheckGroup(this->mGroup, lgs_group_bb_detect(this->mDetector, &scans, numOfPairs, nullptr,
                    pyramids.data(), thresholds.data(), this->mLast.data()), "lgs_group_bb_detect");
+    }
+
+    /* What the pairs cost goes to the load of the device their local map lives on */
+    {
+        int pairIdx = 0;
+        for (const auto& query : loopDetectionQueries) {
+            const auto it = this->mDeviceMaps.find(query.mLocalMapInfo.mIdx);
+            for (size_t k = 0; k < query.mPoseGraphNodes.size(); ++k, ++pairIdx)
+                if (it != this->mDeviceMaps.end())
+                    this->mMemberLoad[it->second.mMember] +=
+                        static_cast<double>(this->mLast[pairIdx].n_scored);
+        }
     }
 
     /* Host tail and loop closing edges in the reference's order

@@ -445,13 +445,13 @@ int main(int argc, char** argv) {
             const auto d1 = std::chrono::steady_clock::now();
             gpu.Detect(q2, r2);
             const auto d2 = std::chrono::steady_clock::now();
-            long long fix = 0, replay = 0;
-            for (const auto& r : gpu.LastResults()) { fix += r.n_fixups; replay += r.exact_replay; }
+            long long fix = 0, replay = 0, scored = 0;          /* n_scored is per pair (bb_count_nodes) */
+            for (const auto& r : gpu.LastResults()) { fix += r.n_fixups; replay += r.exact_replay; scored += r.n_scored; }
             std::printf("loop round %d Detect: reference %.1f ms, cuda %.1f ms (%lld nodes scored, %lld host fix-ups, "
                         "%lld CPU-order replays)\n", round,
                         std::chrono::duration<double, std::milli>(d1 - d0).count(),
                         std::chrono::duration<double, std::milli>(d2 - d1).count(),
-                        gpu.LastResults().empty() ? 0LL : gpu.LastResults()[0].n_scored, fix, replay);
+                        scored, fix, replay);
             bool ok = r1.size() == r2.size();
             for (size_t i = 0; ok && i < r1.size(); ++i)
                 ok = SamePose(r1[i].mRelativePose, r2[i].mRelativePose) &&

@@ -308,8 +308,9 @@ void* lgs_bb_batch_device_records(lgs_bb_batch* b);                 /* the batch
  * device-only run -- [0] hit points, [1] root level, [2 ..] levels H-1 .. 0, then winner, finalize --
  * and (optional) the lanes-per-node mapping the scoring phases used. */
 int lgs_bb_batch_phase_times(lgs_bb_batch* b, double* us, int* mapping, int n);
-/* With "bb_host_timing" on: nodes[q] = nodes below the root level scored for query q by the last
- * device-only run (n >= queries of the batch) -- the per-submap cost a placement can balance. */
+/* With the context option "bb_count_nodes" (or "bb_host_timing") on: nodes[q] = nodes below the root
+ * level scored for query q by the last device-only run (n >= queries of the batch) -- the per-submap
+ * cost a placement can balance; lgs_match_result::n_scored is then per query too (roots + these). */
 int lgs_bb_batch_query_nodes(lgs_bb_batch* b, long long* nodes, int n);
 /* How many runs of this batch object were device-only and how many went through the exact path. */
 int lgs_bb_batch_path(const lgs_bb_batch* b, long long* device_runs, long long* exact_runs);

@@ -956,7 +956,9 @@ int lgs_bb_batch_results(lgs_bb_batch* b, lgs_match_result* out) {
         o.n_fixups = b->fixups[q];
         o.step_x = d.res; o.step_y = d.res; o.step_t = b->us[d.scan].stepT;
         o.score = r.score;
-        o.n_scored = total;          // batch-wide count of nodes scored (all queries)
+        // nodes scored: of this query when the run counted them ("bb_count_nodes"), else of the whole batch
+        const bool perQuery = b->lastRunDevice && (c->opt.bbCountNodes || c->opt.bbHostTiming);
+        o.n_scored = perQuery ? (long long)d.nrx * d.nry * d.nT + r.nodes : total;
         o.exact_replay = r.exactReplay;
         o.reserved = b->lastRunDevice ? 0 : 1;     // 1: the level-synchronous exact path produced this result
     }
@@ -1028,13 +1030,10 @@ int lgs_bb_batch_phase_times(lgs_bb_batch* b, double* us, int* mapping, int n) {
 int lgs_bb_batch_query_nodes(lgs_bb_batch* b, long long* nodes, int n) {
     if (!b || !nodes || n < b->nq) return LGS_ERR_INVALID;
     lgs_ctx* c = b->ctx;
-    if (!b->lastRunDevice || !c->opt.bbHostTiming) return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_query_nodes: needs a device-only run with bb_host_timing on");
+    if (!b->lastRunDevice || !(c->opt.bbHostTiming || c->opt.bbCountNodes))
+        return lgs_fail(c, LGS_ERR_INVALID, "bb_batch_query_nodes: needs a device-only run with bb_count_nodes (or bb_host_timing) on");
     { const int rc = bb_settle(b); if (rc != LGS_OK) return rc; }
-    std::vector<BbBest> best(b->nq);
-    LGS_CUDA(c, cudaSetDevice(c->device));
-    LGS_CUDA(c, cudaMemcpyAsync(best.data(), b->dBest.p, (size_t)b->nq * sizeof(BbBest), cudaMemcpyDeviceToHost, c->stream));
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int q = 0; q < b->nq; ++q) nodes[q] = best[q].pad;
+    for (int q = 0; q < b->nq; ++q) nodes[q] = b->hRes.p[q].nodes;
     return LGS_OK;
 }
 

@@ -74,6 +74,7 @@ struct BbResult {
     double score;
     int found, ix, iy, it;
     int exactReplay, fixups;
+    int nodes, pad;                 // device-only run with node counting on: nodes of the levels below the root
 };
 
 struct BbFlag { int q, t, i; };                // exact path: a near-edge (query, theta, beam)

@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) bb_run_kernel(const __gr
         const BbQuery& d = a.qs[q];
         const BbBest b = a.best[q];
         BbResult r;
-        r.exactReplay = 0; r.fixups = b.fixups;
+        r.exactReplay = 0; r.fixups = b.fixups; r.nodes = b.pad; r.pad = 0;
         r.found = 0; r.score = d.thrAbs; r.ix = 0; r.iy = 0; r.it = 0;
         bool replay = false;
         if (b.scoreBits != 0ull && b.rankLeaf != ~0ull) {
@@ -682,7 +682,7 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
     }
     a.resolveUlps = std::max(c->opt.bbResolveUlps, 0);
     a.forceReplay = b->forceReplay ? 1 : 0;
-    a.countNodes = c->opt.bbHostTiming ? 1 : 0;
+    a.countNodes = (c->opt.bbHostTiming || c->opt.bbCountNodes) ? 1 : 0;
     void* params[] = {&a};
     LGS_CUDA(c, cudaLaunchCooperativeKernel(kernel, dim3(c->bbBlocks), dim3(kThreads), params, 0,
                                             c->stream));

@@ -44,6 +44,7 @@ const OptField kOptFields[] = {
     LGS_OPT("bb_cost_g8", nullptr, 1, bbCost[2]),
     LGS_OPT("bb_cost_g32", nullptr, 1, bbCost[3]),
     LGS_OPT("bb_host_timing", "LGS_BB_HOSTTIMING", 0, bbHostTiming),
+    LGS_OPT("bb_count_nodes", nullptr, 0, bbCountNodes),
     LGS_OPT("integ_host_timing", "LGS_INTEG_HOSTTIMING", 0, integHostTiming),
     LGS_OPT("integ_timing", "LGS_INTEG_TIMING", 0, integTiming),
     LGS_OPT("integ_diag", "LGS_INTEG_DIAG", 0, integDiag),

@@ -316,7 +316,8 @@ int lgs_group_bb_detect(lgs_group_bb* d, const lgs_scan_batch* scans, int nPairs
             o.n_fixups = b->fixups[k];
             o.step_x = qd.res; o.step_y = qd.res; o.step_t = b->us[qd.scan].stepT;
             o.score = r.score;
-            o.n_scored = total;
+            const bool perQuery = b->lastRunDevice && (b->ctx->opt.bbCountNodes || b->ctx->opt.bbHostTiming);
+            o.n_scored = perQuery ? (long long)qd.nrx * qd.nry * qd.nT + b->hRes.p[k].nodes : total;
             o.exact_replay = b->hRes.p[k].exactReplay;
             o.reserved = b->lastRunDevice ? 0 : 1;
         }

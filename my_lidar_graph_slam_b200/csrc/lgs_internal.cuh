@@ -140,6 +140,7 @@ struct lgs_opts {
     int bbBlocksPerSm = 0;      // "bb_blocks_per_sm" persistent B&B kernel residency (0 = occupancy limit)
     double bbCost[4] = {100.0, 60.0, 36.0, 21.0};   // "bb_cost_g1/g4/g8/g32" per-pass cost (us) of the warp mappings
     int bbHostTiming = 0;       // "bb_host_timing"  LGS_BB_HOSTTIMING
+    int bbCountNodes = 0;       // "bb_count_nodes": lgs_match_result::n_scored per query instead of per batch
     int integHostTiming = 0;    // "integ_host_timing" LGS_INTEG_HOSTTIMING
     int integTiming = 0;        // "integ_timing"    LGS_INTEG_TIMING
     int integDiag = 0;          // "integ_diag"      LGS_INTEG_DIAG

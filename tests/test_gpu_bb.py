@@ -311,3 +311,35 @@ def test_records_and_device_sink(ctx, submap):
     batch.set_record_sink(0)
     batch.close()
     capi.device_free(ctx, buf)
+
+
+def test_per_query_node_counts(ctx, submap, bb_run_path):
+    """With "bb_count_nodes" on, a device-only run reports the nodes it scored below the root level per
+    query (what a cost-aware placement of submaps on devices balances): they add up to the batch's
+    level totals, n_scored becomes per query, and the results do not change."""
+    if bb_run_path == "exact":
+        pytest.skip("node counts belong to the device-only run")
+    qs = _queries(submap, 6, seed=11)
+    scans = capi.Scans([submap["angles"]] * len(qs), [s for s, _ in qs], [p for _, p in qs],
+                       range_min=0.02, range_max=30.0)
+    batch = capi.BbBatch(ctx, **DEF)
+    batch.upload(scans, [submap["pyr"]] * len(qs), 0.55)
+    batch.run()
+    plain = batch.results_array().copy()
+    with pytest.raises(capi.LgsError):
+        batch.query_nodes(len(qs))
+    ctx.set_option("bb_count_nodes", 1)
+    try:
+        batch.run()
+        res = batch.results_array().copy()
+        nodes = batch.query_nodes(len(qs))
+    finally:
+        ctx.set_option("bb_count_nodes", 0)
+    levels, _ = batch.work()
+    assert batch.path()[1] == 0                                       # both runs stayed on the device
+    assert int(nodes.sum()) == int(sum(levels[:-1]))
+    assert int(res["n_scored"].sum()) == int(sum(levels))
+    assert len(set(plain["n_scored"].tolist())) == 1 and int(plain["n_scored"][0]) == int(sum(levels))
+    for f in ("found", "ix", "iy", "it", "score"):
+        assert np.array_equal(plain[f], res[f])
+    batch.close()
