@@ -494,16 +494,19 @@ def run_c5(ctx, comm, rank, world_size, barrier, max_over_ranks, sum_over_ranks,
     pyr = capi.Pyramid(ctx, whole, BB["node_height_max"])
     full_ms = ctx.timer_stop()
     qr = np.random.default_rng(14)
-    q_scans, q_init = [], []
+    n_distinct = min(n_queries, 256)                    # distinct query scans; query k re-uses scan k % n_distinct
+    q_scans, q_base, q_init = [], [], []                # at another place of the stitched map / another first guess
+    for k in range(n_distinct):
+        q_base.append(traj[int(qr.integers(0, len(traj)))])
+        q_scans.append(synth.make_scan(world, q_base[-1], angles, qr))
     for k in range(n_queries):
-        base = traj[int(qr.integers(0, len(traj)))]
         off = np.array([qr.integers(0, n_t) * T * 0.05, qr.integers(0, n_t) * T * 0.05, 0.0])
-        q_scans.append(synth.make_scan(world, base, angles, qr))
-        q_init.append(base + off + np.array([qr.uniform(-0.4, 0.4), qr.uniform(-0.4, 0.4), qr.uniform(-0.1, 0.1)]))
+        q_init.append(q_base[k % n_distinct] + off + np.array([qr.uniform(-0.4, 0.4), qr.uniform(-0.4, 0.4), qr.uniform(-0.1, 0.1)]))
     mine = sharding.owned(n_queries, rank, world_size)
     ex = sharding.RecordExchange(ctx, comm, n_queries, rank, world_size)
     batch = capi.BbBatch(ctx, **BB)
-    sc = capi.Scans([angles] * len(mine), [q_scans[k] for k in mine], [q_init[k] for k in mine],
+    # a query = (scan, first guess): the sensor pose belongs to the pair, so every query is its own scan entry
+    sc = capi.Scans([angles] * len(mine), [q_scans[k % n_distinct] for k in mine], [q_init[k] for k in mine],
                     range_min=0.02, range_max=30.0)
     plist = [pyr] * len(mine)
     pair = np.arange(len(mine), dtype=np.int32)
@@ -934,6 +937,15 @@ def run_b200(args, rank, world_size, local_rank):
     def sum_over_ranks(x):
         return reduce_(x, dist.ReduceOp.SUM) if dist is not None else x
 
+    # C1 runs in child processes (the adapters' own executables): first, while this process holds no CUDA
+    # context yet -- beside the bench's resident contexts the same loop measured 1.3 instead of 0.37 ms per frame
+    c1_early = None
+    if world_size == 1 and not args.no_extra:
+        try:
+            c1_early = run_c1()
+        except Exception as e:                                   # noqa: BLE001
+            c1_early = {"error": f"{type(e).__name__}: {e}"}
+
     ctx = capi.Context(local_rank)
     comm = sharding.make_comm(ctx, rank, world_size)
     ctx_b = capi.Context(local_rank)                    # second lane of the pipelined end-to-end steps
@@ -1061,7 +1073,7 @@ def run_b200(args, rank, world_size, local_rank):
             side("grid_search", lambda: run_gs(ctx, c2["grid"], c2["dense"], c2["min_x"], c2["min_y"], c2["angles"],
                                                c2["ranges"], c2["inits"], cpu_side))
             side("c3", lambda: run_c3(ctx, 1024, args.c3_scans, cpu_side))
-            side("c1", lambda: run_c1())
+            details["c1"] = c1_early
     if rank != 0:
         return
 
@@ -1216,7 +1228,7 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip the loop-closure measurement (N = 1 only)")
     ap.add_argument("--submaps", type=int, default=500, help="C4: submaps")
     ap.add_argument("--c5-side", type=int, default=8000, help="C5: map side in cells (multiple of 1000; 0 = skip)")
-    ap.add_argument("--c5-queries", type=int, default=256, help="C5: loop queries per batch")
+    ap.add_argument("--c5-queries", type=int, default=1024, help="C5: loop queries per batch")
     ap.add_argument("--c3-scans", type=int, default=102400, help="C3: scans streamed (BASELINE config: 100k)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -46,6 +46,7 @@ const OptField kOptFields[] = {
     LGS_OPT("bb_host_timing", "LGS_BB_HOSTTIMING", 0, bbHostTiming),
     LGS_OPT("bb_count_nodes", nullptr, 0, bbCountNodes),
     LGS_OPT("integ_host_timing", "LGS_INTEG_HOSTTIMING", 0, integHostTiming),
+    LGS_OPT("integ_host_timing_min_ms", "LGS_INTEG_HOSTTIMING_MIN_MS", 1, integHostTimingMinMs),
     LGS_OPT("integ_timing", "LGS_INTEG_TIMING", 0, integTiming),
     LGS_OPT("integ_diag", "LGS_INTEG_DIAG", 0, integDiag),
     LGS_OPT("integ_side_words", "LGS_INTEG_SIDE_WORDS", 2, integSideWords),

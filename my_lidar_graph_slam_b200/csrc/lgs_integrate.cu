@@ -758,7 +758,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     if (overlap && lastBuf >= 0) LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evFold[lastBuf], 0));
     LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     LGS_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (hostTiming && msSince(tStart) > 1.0)
+    if (hostTiming && msSince(tStart) > c->opt.integHostTimingMinMs)
         fprintf(stderr, "[lgs integrate host] %d scans into %dx%d: staged %.3f ms, pre-pass synced %.3f ms, chunks queued "
                 "%.3f ms, done %.3f ms\n", n, grid->nx, grid->ny, tStage, tPre, tLoop, msSince(tStart));
     if (timing) {

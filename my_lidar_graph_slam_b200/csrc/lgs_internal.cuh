@@ -142,6 +142,7 @@ struct lgs_opts {
     int bbHostTiming = 0;       // "bb_host_timing"  LGS_BB_HOSTTIMING
     int bbCountNodes = 0;       // "bb_count_nodes": lgs_match_result::n_scored per query instead of per batch
     int integHostTiming = 0;    // "integ_host_timing" LGS_INTEG_HOSTTIMING
+    double integHostTimingMinMs = 1.0;  // "integ_host_timing_min_ms" LGS_INTEG_HOSTTIMING_MIN_MS: report calls slower than this
     int integTiming = 0;        // "integ_timing"    LGS_INTEG_TIMING
     int integDiag = 0;          // "integ_diag"      LGS_INTEG_DIAG
     long long integSideWords = 0; // "integ_side_words" LGS_INTEG_SIDE_WORDS (0 = default size)
