@@ -418,11 +418,12 @@ def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_
         with open(os.path.join(ROOT, "gpurun_out", f"c4_rank{rank}_of{world}_q{n_scans}.json"), "w") as f:
             json.dump({"rank": rank, "submaps": int(nq), "ms_per_step": dev_ms_local / steps, "phases_us": ph,
                        "levels": [b.work()[0] for b in batches]}, f)
-    nodes, gathers, dev_runs, exact_runs = 0, 0, 0, 0
+    nodes, gathers, skipped, dev_runs, exact_runs = 0, 0, 0, 0, 0
     for b in batches:
         lv, ga = b.work()
         nodes += int(sum(lv))
         gathers += int(ga)
+        skipped += b.skipped_gathers()
     for lane in L:
         for b in lane["batches"]:
             d_, e_ = b.path()
@@ -436,6 +437,7 @@ def c4_steps(lanes, shard, rank, world, n_submaps, n_scans, steps, barrier, max_
            "qps_e2e_sequential": pairs * steps / e2e_seq_s,
            "ms": dev_ms / steps, "ms_e2e": 1e3 * e2e_s / steps, "launches_per_step": launches / steps,
            "sub_batches": len(groups), "scans_per_sub_batch": sub, "nodes_rank0": nodes, "gathers_rank0": gathers,
+           "gathers_issued_frac_rank0": (1.0 - skipped / gathers) if gathers else None,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(L[0]["ex"].d2h_bytes),
            "device_runs": dev_runs, "exact_runs": exact_runs,
            "found": int((rec["found"] != 0).sum()), "best": sharding.best_candidate(rec),

@@ -308,6 +308,11 @@ void* lgs_bb_batch_device_records(lgs_bb_batch* b);                 /* the batch
  * device-only run -- [0] hit points, [1] root level, [2 ..] levels H-1 .. 0, then winner, finalize --
  * and (optional) the lanes-per-node mapping the scoring phases used. */
 int lgs_bb_batch_phase_times(lgs_bb_batch* b, double* us, int* mapping, int n);
+/* Beams the last device-only run left out through early rejection ("bb_early_reject": a node whose
+ * partial sum plus one per remaining beam cannot exceed its threshold is pruned by the CPU whatever the
+ * rest of its sum is; grid cells are probabilities <= 1).  lgs_bb_batch_work counts every beam of every
+ * node -- the reference's cost; the difference was actually gathered. */
+long long lgs_bb_batch_skipped_gathers(const lgs_bb_batch* b);
 /* With the context option "bb_count_nodes" (or "bb_host_timing") on: nodes[q] = nodes below the root
  * level scored for query q by the last device-only run (n >= queries of the batch) -- the per-submap
  * cost a placement can balance; lgs_match_result::n_scored is then per query too (roots + these). */

@@ -130,6 +130,7 @@ SIGNATURES = {
     "lgs_bb_batch_device_records": (vp, [vp]),
     "lgs_bb_batch_phase_times": (C.c_int, [vp, c_dp, c_ip, C.c_int]),
     "lgs_bb_batch_query_nodes": (C.c_int, [vp, C.POINTER(C.c_longlong), C.c_int]),
+    "lgs_bb_batch_skipped_gathers": (C.c_longlong, [vp]),
     "lgs_bb_batch_path": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "lgs_group_create": (C.c_int, [c_ip, C.c_int, C.POINTER(vp)]),
     "lgs_group_destroy": (C.c_int, [vp]),
@@ -517,6 +518,10 @@ class BbBatch:
         g = np.zeros(n, dtype=np.int32)
         self.ctx.check(lib().lgs_bb_batch_phase_times(self.h, _dptr(us), g.ctypes.data_as(c_ip), n))
         return us, g
+
+    def skipped_gathers(self) -> int:
+        """Beams the last device-only run left out through early rejection."""
+        return int(lib().lgs_bb_batch_skipped_gathers(self.h))
 
     def query_nodes(self, n: int) -> np.ndarray:
         """Nodes below the root level scored per query by the last device-only run ("bb_host_timing" on)."""

@@ -586,6 +586,7 @@ int bb_settle(lgs_bb_batch* b) {
         for (int h = 0; h < kMaxLevels; ++h) b->nodesPerLevel[h] = 0;
         b->nodesPerLevel[H] = b->totalRoots;
         for (int h = 0; h < H; ++h) b->nodesPerLevel[h] = hc[kCtrChild + h + 1];
+        b->skippedBeams = 16LL * hc[kCtrSkipped];
         for (int h = 0; h <= H; ++h) b->hint[h] = std::max(b->hint[h], b->nodesPerLevel[h]);
         if (ok) {
             for (int q = 0; q < b->nq; ++q) b->fixups[q] = b->hRes.p[q].fixups;
@@ -1003,6 +1004,14 @@ int lgs_bb_batch_work(const lgs_bb_batch* b, long long* nodesPerLevel, int nLeve
         *gathers = (long long)(total * avgUse);
     }
     return LGS_OK;
+}
+
+// Beams the last device-only run did not have to gather because the node was rejected early (a lower
+// bound, counted in rounds of 16): algorithmic gathers (lgs_bb_batch_work) minus these were issued.
+long long lgs_bb_batch_skipped_gathers(const lgs_bb_batch* b) {
+    if (!b) return 0;
+    if (b->ran && b->nq > 0 && bb_settle(const_cast<lgs_bb_batch*>(b)) != LGS_OK) return 0;
+    return b->lastRunDevice ? b->skippedBeams : 0;
 }
 
 // Diagnostic ("bb_host_timing" must be on before the run): microseconds between the phase boundaries

@@ -20,6 +20,7 @@ constexpr int kCtrUnresolved = 24;          // near-edge points the device could
 constexpr int kCtrOverflow = 25;            // bit h: the pool of level h was too small
 constexpr int kCtrFixups = 26;              // near-edge points resolved on the device (root level)
 constexpr int kCtrDone = 27;                // 1 once the finalize phase has written every record
+constexpr int kCtrSkipped = 28;             // rounds of 16 beams that early rejection did not have to gather
 constexpr int kCounters = 32;
 
 struct BbScan {                     // one per DISTINCT (scan, sensor pose, map resolution): hit points are map independent
@@ -112,6 +113,7 @@ struct RunArgs {
     int resolveUlps;
     int forceReplay;
     int countNodes;                 // count the nodes of the deeper levels per query (BbBest::pad)
+    int earlyReject;                // stop a node's sum once the remaining beams cannot lift it over the threshold
     float costUs[4];                // per-pass cost model of the G = 1 / 4 / 8 / 32 mappings (us)
     unsigned long long* phaseNs;    // [kPhases] globaltimer at the phase boundaries (diagnostic)
     int* phaseG;                    // [kMaxLevels] warp mapping used per level (diagnostic)
@@ -135,6 +137,7 @@ struct lgs_bb_batch {
     std::vector<long long> ids;     // record ids (empty: the query index)
     std::vector<int> fixups;
     long long nTab = 0, nHits = 0, nHitsT = 0;
+    long long skippedBeams = 0;     // beams early rejection left out in the last device-only run
     int projTiles = 0;              // 8 x 32 (beam, theta) projection tiles of the batch's distinct scans
     double maxReachCells = 0.0;     // longest usable beam of the batch in cells (12.20 fixed-point range check)
     int totalRoots = 0;

@@ -118,7 +118,7 @@ template <int G> struct LaneMap {
 // `lane` works for node LaneMap<G>::row(lane) and fetches the beams congruent to LaneMap<G>::sub(lane)
 // modulo G; the sum is returned in the lanes with sub == 0.
 template <int G, int kU>
-__device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n, int h, int lane, double* svw) {
+__device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n, int h, int lane, double* svw, int& skipped) {
     const int sub = LaneMap<G>::sub(lane), row = LaneMap<G>::row(lane);
     (void)sub; (void)row;
     const BbQuery* dq = a.qs + (n.active ? n.q : 0);
@@ -141,6 +141,8 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
     // in wrapping unsigned arithmetic -- one shift-add (LEA) per axis instead of add + mask
     const unsigned E = a.edgeUnits << 12, E2 = (2u * a.edgeUnits) << 12;
     double acc = 0.0;
+    // cell values are probabilities (<= 1): remaining beams bound the rest of the sum ("bb_early_reject")
+    const double lim = a.earlyReject ? dq->thrAbs - 1e-6 : -1.0e300;
 
     // offset of the beam's cell; `near` keeps the smallest distance-to-edge measure seen so far
     // (one compare per round instead of one per beam and axis)
@@ -192,6 +194,10 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
             hr += roundStep;
 #pragma unroll
             for (int u = 0; u < kU; ++u) acc = __dadd_rn(acc, v[u]);      // beam order; unknown cells add 0.0
+            // early rejection: even if every remaining beam hit a cell of value 1 the node would stay at
+            // or below the threshold -- the CPU prunes it whatever the rest of its sum is, and a stored
+            // partial sum (<= threshold) makes every later test on this node come out the same
+            if (acc + (double)(nb - (r + 1) * kU) <= lim) { skipped += (nb - (r + 1) * kU) / kU; return acc; }
         }
         for (int i = nFull * kU; i < nb; ++i) {
             unsigned near = 0xffffffffu;
@@ -212,6 +218,9 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
         constexpr int RS = S + 1;                  // row stride (doubles): odd, so the adding lanes hit distinct banks
         const int nbMax = __reduce_max_sync(0xffffffffu, nb);
         const int nStages = (nbMax + S - 1) / S;
+        const int nbAll = nb;
+        int nbLive = nb;                           // 0 once the node is rejected early (see G == 1)
+        const int leader = LaneMap<G>::kBeamMajor ? row * G : row;
         int2 hp[kV];
         double v[kV];
         unsigned okm = 0;
@@ -220,7 +229,7 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
 #pragma unroll
             for (int u = 0; u < kV; ++u) {
                 const int b = s * S + u * G + sub;
-                const bool ok = b < nb;
+                const bool ok = b < nbLive;
                 okm |= (ok ? 1u : 0u) << u;
                 hp[u] = ok ? hb[(unsigned)b * stride] : make_int2(mlx + 0x80000, mly + 0x80000);   // mid-cell: never near an edge
             }
@@ -251,9 +260,9 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
             for (int u = 0; u < kV; ++u) rowp[u * G + sub] = v[u];
         };
         auto chain = [&](int s) {  // the node's first lane adds stage s in beam order
-            if (sub == 0 && nb > s * S) {
+            if (sub == 0 && nbLive > s * S) {
                 const double* rowp = svw + row * RS;
-                const int m = min(S, nb - s * S);
+                const int m = min(S, nbLive - s * S);
                 int j = 0;
                 for (; j + 8 <= m; j += 8) {
                     double t8[8];
@@ -273,6 +282,9 @@ __device__ __forceinline__ double score_group(const RunArgs& a, const NodeRef& n
                 __syncwarp();
                 chain(s);
                 __syncwarp();
+                const bool out = nbLive == 0 || (sub == 0 && acc + (double)max(nbAll - (s + 1) * S, 0) <= lim);
+                if (__shfl_sync(0xffffffffu, out, leader)) { if (sub == 0 && nbLive) skipped += max(nbAll - (s + 1) * S, 0) / 16; nbLive = 0; }
+                if (__all_sync(0xffffffffu, nbLive <= (s + 1) * S)) break;
             }
         return acc;
     }
@@ -342,10 +354,17 @@ __device__ __forceinline__ void expand(const RunArgs& a, int h, int k, const Nod
 // Root level: every (query, root cell, theta).  A warp tile = 32 / G consecutive thetas of one (query,
 // root cell); consecutive tiles are consecutive QUERIES of the same scan and theta range, so the warps
 // of a CTA read the same hit-point lines (L1) while gathering from different submaps.
+// One atomic per warp and phase: rounds of 16 beams left out by early rejection (diagnostic).
+__device__ __forceinline__ void flush_skipped(const RunArgs& a, int skipped) {
+    skipped = __reduce_add_sync(0xffffffffu, skipped);
+    if ((threadIdx.x & 31) == 0 && skipped) atomicAdd(a.ctr + kCtrSkipped, skipped);
+}
+
 template <int G, int kU>
 __device__ __forceinline__ void root_phase(const RunArgs& a, int lane, int gw, int tw, double* svw) {
     constexpr int NPW = 32 / G;
     const int H = a.H;
+    int skipped = 0;
     for (int tile = gw; tile < a.rootTiles; tile += tw) {
         int lo = 0, hi = a.nu;                          // scan of this tile: tileBegin[lo] <= tile < tileBegin[lo + 1]
         while (hi - lo > 1) {
@@ -366,14 +385,16 @@ __device__ __forceinline__ void root_phase(const RunArgs& a, int lane, int gw, i
         // push order x asc, y asc, theta asc (scan_matcher_branch_bound.cpp:85-88); LIFO pops reverse it
         const int kLocal = (kx * s.nry + ky) * s.nT + t;
         const int k = a.qs[q].rootBegin + kLocal;
-        const double acc = score_group<G, kU>(a, n, H, lane, svw);
+        const double acc = score_group<G, kU>(a, n, H, lane, svw, skipped);
         expand<G>(a, H, k, n, (long long)(nrxy * s.nT - 1 - kLocal), true, acc, lane);
     }
+    flush_skipped(a, skipped);
 }
 
 template <int G, int kU>
 __device__ __forceinline__ void level_phase(const RunArgs& a, int h, int nNodes, int lane, int gw, int tw, double* svw) {
     constexpr int NPW = 32 / G;
+    int skipped = 0;
     const int nGroups = (nNodes + NPW - 1) / NPW;
     for (int g = gw; g < nGroups; g += tw) {
         const int k = g * NPW + LaneMap<G>::row(lane);
@@ -386,9 +407,10 @@ __device__ __forceinline__ void level_phase(const RunArgs& a, int h, int nNodes,
             n.q = nd.q; n.t = nd.t; n.x = nd.x; n.y = nd.y;
             rank = nd.rank;
         }
-        const double acc = score_group<G, kU>(a, n, h, lane, svw);
+        const double acc = score_group<G, kU>(a, n, h, lane, svw, skipped);
         expand<G>(a, h, k, n, rank, false, acc, lane);
     }
+    flush_skipped(a, skipped);
 }
 
 // Which warp mapping serves a level of n nodes fastest on `tw` warps: passes x per-pass cost.
@@ -683,6 +705,7 @@ int lgs_bb_launch_device_run(lgs_bb_batch* b) {
     a.resolveUlps = std::max(c->opt.bbResolveUlps, 0);
     a.forceReplay = b->forceReplay ? 1 : 0;
     a.countNodes = (c->opt.bbHostTiming || c->opt.bbCountNodes) ? 1 : 0;
+    a.earlyReject = c->opt.bbEarlyReject ? 1 : 0;
     void* params[] = {&a};
     LGS_CUDA(c, cudaLaunchCooperativeKernel(kernel, dim3(c->bbBlocks), dim3(kThreads), params, 0,
                                             c->stream));

@@ -45,6 +45,7 @@ const OptField kOptFields[] = {
     LGS_OPT("bb_cost_g32", nullptr, 1, bbCost[3]),
     LGS_OPT("bb_host_timing", "LGS_BB_HOSTTIMING", 0, bbHostTiming),
     LGS_OPT("bb_count_nodes", nullptr, 0, bbCountNodes),
+    LGS_OPT("bb_early_reject", "LGS_BB_EARLY_REJECT", 0, bbEarlyReject),
     LGS_OPT("integ_host_timing", "LGS_INTEG_HOSTTIMING", 0, integHostTiming),
     LGS_OPT("integ_host_timing_min_ms", "LGS_INTEG_HOSTTIMING_MIN_MS", 1, integHostTimingMinMs),
     LGS_OPT("integ_timing", "LGS_INTEG_TIMING", 0, integTiming),

@@ -141,6 +141,7 @@ struct lgs_opts {
     double bbCost[4] = {100.0, 60.0, 36.0, 21.0};   // "bb_cost_g1/g4/g8/g32" per-pass cost (us) of the warp mappings
     int bbHostTiming = 0;       // "bb_host_timing"  LGS_BB_HOSTTIMING
     int bbCountNodes = 0;       // "bb_count_nodes": lgs_match_result::n_scored per query instead of per batch
+    int bbEarlyReject = 1;      // "bb_early_reject" LGS_BB_EARLY_REJECT: device-only run stops hopeless sums early
     int integHostTiming = 0;    // "integ_host_timing" LGS_INTEG_HOSTTIMING
     double integHostTimingMinMs = 1.0;  // "integ_host_timing_min_ms" LGS_INTEG_HOSTTIMING_MIN_MS: report calls slower than this
     int integTiming = 0;        // "integ_timing"    LGS_INTEG_TIMING

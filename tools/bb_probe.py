@@ -62,7 +62,8 @@ def measure(label):
         batch.run()
     dev = ctx.timer_stop() / REPS
     levels, gathers = batch.work()
-    line = f"{label}: kernels {dev * 1e3:.1f} us, e2e {e2e * 1e6:.1f} us per run; path {batch.path()}; levels {levels}"
+    line = (f"{label}: kernels {dev * 1e3:.1f} us, e2e {e2e * 1e6:.1f} us per run; path {batch.path()}; levels {levels}; "
+            f"gathers issued {1.0 - batch.skipped_gathers() / max(gathers, 1):.3f} of nodes x beams")
     try:
         ctx.set_option("bb_host_timing", 1)
         batch.run()
@@ -86,6 +87,10 @@ for kv in [x for x in EXTRA.split(",") if x]:
     ctx.set_option(k, float(v))
 for bps in BLOCKS:
     ctx.set_option("bb_blocks_per_sm", bps)
+    if os.environ.get("BB_BOTH"):
+        ctx.set_option("bb_early_reject", 0)
+        measure(f"device-only, no early rejection, CTAs/SM {bps or 'max'}")
+        ctx.set_option("bb_early_reject", 1)
     found, res = measure(f"device-only, CTAs/SM {bps or 'max'}")
     same = all(np.array_equal(res[f], res_ref[f]) for f in ("found", "ix", "iy", "it", "score"))
     print(f"    found {found} (exact path {found_ref}); identical to the exact path: {same}", flush=True)
