@@ -264,7 +264,11 @@ typedef struct lgs_bb_params {
 int lgs_bb_batch_create(lgs_ctx* ctx, const lgs_bb_params* params, lgs_bb_batch** out);
 int lgs_bb_batch_destroy(lgs_bb_batch* b);
 /* scans->n_scans queries; pyramids[q] is the submap query q is matched against (pyramids may
- * repeat); norm_threshold[q] as for the correlative matcher. */
+ * repeat); norm_threshold[q] as for the correlative matcher.
+ * Precondition of the device-only run: the cells of the submaps are occupancy probabilities, 0 (unknown)
+ * or within (0, 1] -- the reference's BinaryBayesGridCell values are clamped to [0.001, 0.999].  The run
+ * stops a node's sum once `partial + remaining beams <= threshold` ("bb_early_reject", default on); for
+ * grids with larger values switch the option off (lgs_ctx_set_option) or take the exact path ("bb_sync"). */
 int lgs_bb_batch_upload(lgs_bb_batch* b, const lgs_scan_batch* scans,
                         lgs_pyramid* const* pyramids, const double* norm_threshold);
 /* Same, for scans shared by several queries: pair q matches scans[pair_scan[q]] against
