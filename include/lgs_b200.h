@@ -159,6 +159,16 @@ typedef struct lgs_hit_batch {
 } lgs_hit_batch;
 int lgs_grid_integrate_scans(lgs_ctx* ctx, lgs_grid* grid, const lgs_hit_batch* scans,
                              double p_hit, double p_miss, long long* n_updates);
+/* The same call in two halves, for a caller that streams scans (config C3): submit returns once the
+ * call's work is queued (it waits only for the pre-pass that bounds the scans, and fails before anything
+ * touches the grid if a scan leaves it); wait returns the update count of the OLDEST submitted call.  Up
+ * to two calls may be in flight: the host-to-device copy and the pre-pass of call k + 1 then run under
+ * the passes of call k (staging is double buffered).  The host arrays of a call must stay valid until
+ * submit returns; cells are folded in submission order.  The grid is defined again -- for downloads,
+ * matchers, resizes, copies -- once every submitted call has been waited for. */
+int lgs_grid_integrate_submit(lgs_ctx* ctx, lgs_grid* grid, const lgs_hit_batch* scans,
+                              double p_hit, double p_miss);
+int lgs_grid_integrate_wait(lgs_ctx* ctx, long long* n_updates);
 
 /* Diagnostics: cells (cumulative over this context) whose fast candidate search disagreed with
  * the mark pass and were redone by the exhaustive exact path; expected to stay 0. */

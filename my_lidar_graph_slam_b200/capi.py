@@ -708,6 +708,8 @@ SIGNATURES.update({
     "lgs_grid_download_region": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_longlong]),
     "lgs_grid_integrate_scans": (C.c_int, [vp, vp, C.POINTER(HitBatch), C.c_double, C.c_double,
                                            C.POINTER(C.c_longlong)]),
+    "lgs_grid_integrate_submit": (C.c_int, [vp, vp, C.POINTER(HitBatch), C.c_double, C.c_double]),
+    "lgs_grid_integrate_wait": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
     "lgs_ctx_integrate_fallback_cells": (C.c_longlong, [vp]),
     "lgs_scan_hit_points": (C.c_int, [c_dp, C.c_int, c_dp, c_dp, C.c_double, C.c_double, c_dp,
                                       c_ip, c_dp]),
@@ -797,6 +799,18 @@ class PackedHits:
 def integrate_packed(ctx: Context, grid: Grid, packed: PackedHits, p_hit=0.6, p_miss=0.45) -> int:
     cnt = C.c_longlong()
     ctx.check(lib().lgs_grid_integrate_scans(ctx.h, grid.h, C.byref(packed.c), p_hit, p_miss, C.byref(cnt)))
+    return cnt.value
+
+
+def integrate_submit(ctx: Context, grid: Grid, packed: PackedHits, p_hit=0.6, p_miss=0.45):
+    """First half of integrate_packed: returns once the call is queued (up to two calls in flight)."""
+    ctx.check(lib().lgs_grid_integrate_submit(ctx.h, grid.h, C.byref(packed.c), p_hit, p_miss))
+
+
+def integrate_wait(ctx: Context) -> int:
+    """Second half: cell updates of the oldest submitted call, once it is complete."""
+    cnt = C.c_longlong()
+    ctx.check(lib().lgs_grid_integrate_wait(ctx.h, C.byref(cnt)))
     return cnt.value
 
 

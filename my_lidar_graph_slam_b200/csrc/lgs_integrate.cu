@@ -582,22 +582,59 @@ __global__ void grid_shift_copy_kernel(const double* __restrict__ src, int srcNx
 
 extern "C" {
 
-int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* scans, double pHit,
-                             double pMiss, long long* nUpdatesOut) {
-    if (!c || !grid || !scans) return LGS_ERR_INVALID;
+}  // extern "C"
+
+namespace {
+
+// Completion of the OLDEST submitted call: its update count, the fallback statistics, its staging set.
+int integ_wait(lgs_ctx* c, long long* nUpdatesOut) {
     if (nUpdatesOut) *nUpdatesOut = 0;
+    if (!c->integ || c->integ->nPending == 0) return LGS_OK;
+    lgs_integ_ws& w = *c->integ;
+    lgs_integ_ws::Stage& st = w.stage[(w.calls - (unsigned long long)w.nPending) & 1];
+    LGS_CUDA(c, cudaSetDevice(c->device));
+    LGS_CUDA(c, cudaEventSynchronize(st.evDone));
+    st.pending = false;
+    --w.nPending;
+    if (nUpdatesOut) *nUpdatesOut = (long long)st.hCounters.p[0];
+    w.fallbackCells += (long long)st.hCounters.p[1];
+    return LGS_OK;
+}
+
+// Everything of a call up to the last enqueue; the host waits only for the pre-pass (scan bounds).
+int integ_submit(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* scans, double pHit, double pMiss) {
     const int n = scans->n_scans;
     if (n < 0 || (n > 0 && (!scans->sensor_xy || !scans->hit_begin)))
         return lgs_fail(c, LGS_ERR_INVALID, "integrate: bad scan batch");
-    if (n == 0) return LGS_OK;
+    if (n == 0) return LGS_OK;                       // nothing in flight: the matching wait reports 0 updates
     if (grid->off_x || grid->off_y)
         return lgs_fail(c, LGS_ERR_INVALID, "integrate: windowed grids (lgs_grid_set_window) are not supported");
-    const long long total = scans->hit_begin[n];
+    const long long total = n > 0 ? scans->hit_begin[n] : 0;
     if (total > 0 && !scans->hit_xy) return lgs_fail(c, LGS_ERR_INVALID, "integrate: hit_xy is NULL");
     LGS_CUDA(c, cudaSetDevice(c->device));
     LGS_CUDA(c, lgs_grid_acquire(c, grid));
     if (!c->integ) c->integ = new lgs_integ_ws();
-    lgs_integ_ws& w = *c->integ;
+    lgs_integ_ws& ws = *c->integ;
+    if (ws.nPending >= 2 || ws.stage[ws.calls & 1].pending)
+        return lgs_fail(c, LGS_ERR_INVALID, "integrate: two calls are in flight, wait for the older one first");
+    lgs_integ_ws::Stage& w0 = ws.stage[ws.calls & 1];
+    if (!ws.copyStream) LGS_CUDA(c, cudaStreamCreateWithFlags(&ws.copyStream, cudaStreamNonBlocking));
+    if (!w0.evDone) {
+        LGS_CUDA(c, cudaEventCreateWithFlags(&w0.evDone, cudaEventDisableTiming));
+        LGS_CUDA(c, cudaEventCreateWithFlags(&w0.evCounters, cudaEventDisableTiming));
+    }
+    // `w` = the shared workspace with this call's staging set in front of it
+    struct View {
+        lgs_integ_ws& s; lgs_integ_ws::Stage& t;
+        DevBuf<double>& sensor; DevBuf<double>& hit; DevBuf<int>& begin; DevBuf<char>& meta; DevBuf<int2>& rel;
+        DevBuf<unsigned long long>& counters; PinBuf<char>& hMeta; PinBuf<unsigned long long>& hCounters;
+        DevBuf<unsigned>& kmin; DevBuf<unsigned>& kmax;
+        DevBuf<uint2>* tileInfo; DevBuf<int4>* pairs; DevBuf<unsigned>* records; DevBuf<unsigned>* side;
+        cudaStream_t& foldStream; cudaEvent_t* evTouch; cudaEvent_t* evFold;
+        size_t& cleanTiles; bool& dirty;
+    } w{ws, w0, w0.sensor, w0.hit, w0.begin, w0.meta, w0.rel, w0.counters, w0.hMeta, w0.hCounters, ws.kmin, ws.kmax,
+        ws.tileInfo, ws.pairs, ws.records, ws.side, ws.foldStream, ws.evTouch, ws.evFold, ws.cleanTiles, ws.dirty};
+    cudaStream_t cs0 = ws.copyStream;
     // LGS_INTEG_HOSTTIMING=1 (diagnostic): host wall time of the call's phases to stderr when a call
     // takes longer than a millisecond.
     const bool hostTiming = c->opt.integHostTiming != 0;
@@ -606,7 +643,8 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     double tStage = 0.0, tPre = 0.0, tLoop = 0.0;
 
-    // Stage the whole batch once; the passes then run over chunks of <= 64 scans (one mask bit each).
+    // Stage the whole batch once, on the copy stream (under the chunks of an earlier call that is still
+    // running); the passes then run over chunks of <= 64 scans (one mask bit each).
     LGS_CUDA(c, w.sensor.reserve((size_t)n * 2));
     LGS_CUDA(c, w.hit.reserve(std::max<size_t>((size_t)total, 1) * 2));
     LGS_CUDA(c, w.begin.reserve((size_t)n + 1));
@@ -615,11 +653,11 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     LGS_CUDA(c, w.counters.reserve(8));
     LGS_CUDA(c, w.hMeta.reserve((size_t)n * sizeof(ScanMeta)));
     LGS_CUDA(c, w.hCounters.reserve(8));
-    LGS_CUDA(c, cudaMemcpyAsync(w.sensor.p, scans->sensor_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(w.sensor.p, scans->sensor_xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, cs0));
     if (total)
-        LGS_CUDA(c, cudaMemcpyAsync(w.hit.p, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    LGS_CUDA(c, cudaMemcpyAsync(w.begin.p, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    LGS_CUDA(c, cudaMemsetAsync(w.counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+        LGS_CUDA(c, cudaMemcpyAsync(w.hit.p, scans->hit_xy, (size_t)total * 2 * sizeof(double), cudaMemcpyHostToDevice, cs0));
+    LGS_CUDA(c, cudaMemcpyAsync(w.begin.p, scans->hit_begin, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, cs0));
+    LGS_CUDA(c, cudaMemsetAsync(w.counters.p, 0, 8 * sizeof(unsigned long long), cs0));
     tStage = msSince(tStart);
 
     int maxBeams = 0;
@@ -628,15 +666,15 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
     ScanMeta* hMeta = reinterpret_cast<ScanMeta*>(w.hMeta.p);
     GridRef g{grid->origin(), grid->nx, grid->ny, grid->pitch, grid->min_x, grid->min_y, grid->res};
     // Pre-pass over the whole batch: sensor cells, relative end cells, ray lengths, bounds check.
-    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(w.sensor.p, w.begin.p, n, g, dMeta);
+    integ_sensor_kernel<<<(n + 127) / 128, 128, 0, cs0>>>(w.sensor.p, w.begin.p, n, g, dMeta);
     LGS_LAUNCH_CHECK(c);
     if (maxBeams > 0) {
         dim3 gb((maxBeams + 127) / 128, n);
-        integ_beam_kernel<<<gb, 128, 0, c->stream>>>(w.hit.p, g, dMeta, w.rel.p);
+        integ_beam_kernel<<<gb, 128, 0, cs0>>>(w.hit.p, g, dMeta, w.rel.p);
         LGS_LAUNCH_CHECK(c);
     }
-    LGS_CUDA(c, cudaMemcpyAsync(hMeta, dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, c->stream));
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    LGS_CUDA(c, cudaMemcpyAsync(hMeta, dMeta, (size_t)n * sizeof(ScanMeta), cudaMemcpyDeviceToHost, cs0));
+    LGS_CUDA(c, cudaStreamSynchronize(cs0));
     tPre = msSince(tStart);
     for (int s = 0; s < n; ++s)
         if (hMeta[s].bad)
@@ -669,8 +707,7 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
             LGS_CUDA(c, cudaEventCreateWithFlags(&w.evFold[b], cudaEventDisableTiming));
         }
     }
-    bool usedBuf[2] = {false, false};
-    int chunkIdx = 0, lastBuf = -1;
+    int lastBuf = -1;
     int s0 = 0;
     while (s0 < n) {
         // grow the chunk while it stays within 64 scans and the record budget
@@ -705,11 +742,17 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         if (nTiles * kChunk > w.kmin.cap) w.cleanTiles = 0;           // reserve() reallocates
         LGS_CUDA(c, w.kmin.reserve(nTiles * kChunk));
         LGS_CUDA(c, w.kmax.reserve(nTiles * kChunk));
-        const int buf = chunkIdx & 1;
-        ++chunkIdx;
-        // this buffer's previous fold (chunk k - 2) must be done before it is overwritten; waiting on
-        // the host (rarely blocks: the fold runs two chunks behind) also makes reallocation safe
-        if (usedBuf[buf]) LGS_CUDA(c, cudaEventSynchronize(w.evFold[buf]));
+        const int buf = (int)(ws.chunks & 1);
+        ++ws.chunks;
+        // this buffer's previous fold (chunk k - 2, possibly of the previous call) must be done before it is
+        // overwritten: the context stream waits for it; only a buffer that has to grow makes the host wait
+        // (reallocation frees)
+        if (ws.usedBuf[buf]) {
+            const bool grows = nTiles > w.tileInfo[buf].cap || 2 * pairBound > w.pairs[buf].cap ||
+                               pairBound * kTileCells > w.records[buf].cap || sideCap > w.side[buf].cap;
+            if (grows) LGS_CUDA(c, cudaEventSynchronize(w.evFold[buf]));
+            else LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evFold[buf], 0));
+        }
         LGS_CUDA(c, w.tileInfo[buf].reserve(nTiles));
         LGS_CUDA(c, w.pairs[buf].reserve(2 * pairBound));
         LGS_CUDA(c, w.records[buf].reserve(pairBound * kTileCells));
@@ -750,18 +793,31 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
         integ_fold_kernel<<<(unsigned)nTiles, kTileCells, 0, fs>>>(a, g, x0, y0, tw);
         LGS_LAUNCH_CHECK(c);
         LGS_CUDA(c, cudaEventRecord(w.evFold[buf], fs));
-        usedBuf[buf] = true;
+        ws.usedBuf[buf] = true;
         lastBuf = buf;
         stamp();
     }
     tLoop = msSince(tStart);
-    if (overlap && lastBuf >= 0) LGS_CUDA(c, cudaStreamWaitEvent(c->stream, w.evFold[lastBuf], 0));
+    // The call is complete when its counters are back AND its last fold is done.  The context stream does
+    // not wait for that fold: the next call's first chunk starts under it (the record buffers and the
+    // fold stream's own order keep the cells right); lgs_grid_integrate_wait is what orders everything
+    // else behind the call.
     LGS_CUDA(c, cudaMemcpyAsync(w.hCounters.p, w.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    LGS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (overlap && lastBuf >= 0) {
+        LGS_CUDA(c, cudaEventRecord(w0.evCounters, c->stream));
+        LGS_CUDA(c, cudaStreamWaitEvent(w.foldStream, w0.evCounters, 0));
+        LGS_CUDA(c, cudaEventRecord(w0.evDone, w.foldStream));
+    } else {
+        LGS_CUDA(c, cudaEventRecord(w0.evDone, c->stream));
+    }
+    w0.pending = true;
+    ++ws.calls;
+    ++ws.nPending;
     if (hostTiming && msSince(tStart) > c->opt.integHostTimingMinMs)
         fprintf(stderr, "[lgs integrate host] %d scans into %dx%d: staged %.3f ms, pre-pass synced %.3f ms, chunks queued "
-                "%.3f ms, done %.3f ms\n", n, grid->nx, grid->ny, tStage, tPre, tLoop, msSince(tStart));
+                "%.3f ms\n", n, grid->nx, grid->ny, tStage, tPre, tLoop);
     if (timing) {
+        LGS_CUDA(c, cudaStreamSynchronize(c->stream));
         float t[4] = {0, 0, 0, 0};
         for (size_t k = 0; k + 5 <= evs.size(); k += 5)      // 5 stamps per chunk
             for (int j = 0; j < 4; ++j) { float ms = 0; cudaEventElapsedTime(&ms, evs[k + j], evs[k + j + 1]); t[j] += ms; }
@@ -770,9 +826,33 @@ int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* sc
                 w.hCounters.p[2], w.hCounters.p[3], w.hCounters.p[0]);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
     }
-    if (nUpdatesOut) *nUpdatesOut = (long long)w.hCounters.p[0];
-    w.fallbackCells += (long long)w.hCounters.p[1];
     return LGS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lgs_grid_integrate_scans(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* scans, double pHit,
+                             double pMiss, long long* nUpdatesOut) {
+    if (!c || !grid || !scans) return LGS_ERR_INVALID;
+    if (nUpdatesOut) *nUpdatesOut = 0;
+    // calls submitted asynchronously before this one finish first (their counts are dropped)
+    while (c->integ && c->integ->nPending > 0) { const int rc = integ_wait(c, nullptr); if (rc != LGS_OK) return rc; }
+    if (scans->n_scans == 0) return LGS_OK;
+    const int rc = integ_submit(c, grid, scans, pHit, pMiss);
+    if (rc != LGS_OK) return rc;
+    return integ_wait(c, nUpdatesOut);
+}
+
+int lgs_grid_integrate_submit(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* scans, double pHit, double pMiss) {
+    if (!c || !grid || !scans) return LGS_ERR_INVALID;
+    return integ_submit(c, grid, scans, pHit, pMiss);
+}
+
+int lgs_grid_integrate_wait(lgs_ctx* c, long long* nUpdatesOut) {
+    if (!c) return LGS_ERR_INVALID;
+    return integ_wait(c, nUpdatesOut);
 }
 
 long long lgs_ctx_integrate_fallback_cells(const lgs_ctx* c) { return (c && c->integ) ? c->integ->fallbackCells : 0; }

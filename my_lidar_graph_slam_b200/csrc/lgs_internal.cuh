@@ -89,37 +89,59 @@ struct PinBuf {
 
 // Persistent scratch of lgs_grid_integrate_scans (grown on demand, freed with the context).
 struct lgs_integ_ws {
-    DevBuf<double> sensor, hit;
-    DevBuf<int> begin;
-    DevBuf<char> meta;                       // ScanMeta per scan
-    DevBuf<int2> rel;                        // per beam: hit cell - sensor cell
+    // Staging of one call (host inputs, pre-pass results, counters).  Two sets: an asynchronous caller
+    // (lgs_grid_integrate_submit / _wait) stages call k + 1 on the copy stream while the chunks of call k
+    // still read set k.
+    struct Stage {
+        DevBuf<double> sensor, hit;
+        DevBuf<int> begin;
+        DevBuf<char> meta;                   // ScanMeta per scan
+        DevBuf<int2> rel;                    // per beam: hit cell - sensor cell
+        DevBuf<unsigned long long> counters;
+        PinBuf<char> hMeta;
+        PinBuf<unsigned long long> hCounters;
+        cudaEvent_t evDone = nullptr;        // the call's counters are back and its last fold is done
+        cudaEvent_t evCounters = nullptr;
+        bool pending = false;                // submitted, not yet waited for
+        void release() {
+            sensor.release(); hit.release(); begin.release(); meta.release(); rel.release();
+            counters.release(); hMeta.release(); hCounters.release();
+            if (evDone) cudaEventDestroy(evDone);
+            if (evCounters) cudaEventDestroy(evCounters);
+            evDone = evCounters = nullptr; pending = false;
+        }
+    } stage[2];
+    unsigned long long calls = 0;            // calls submitted so far (set = calls & 1)
+    int nPending = 0;
+    cudaStream_t copyStream = nullptr;       // staging + pre-pass of a call
     DevBuf<unsigned> kmin, kmax;             // per (tile, scan): beam index range [kmin, kmax)
     // Double buffered: the fold pass of chunk k (own stream) overlaps the mark / pairs / touch
-    // passes of chunk k + 1.
+    // passes of chunk k + 1 -- across calls too.
     DevBuf<uint2> tileInfo[2];               // per tile: {first pair, pairs}
     DevBuf<int4> pairs[2];                   // two int4 per (tile, scan) pair
     DevBuf<unsigned> records[2];             // per (pair, cell): encoded ordered touch sequence
     DevBuf<unsigned> side[2];                // raw touch / hit bitmap words of sequences no record holds
     cudaStream_t foldStream = nullptr;
     cudaEvent_t evTouch[2] = {nullptr, nullptr}, evFold[2] = {nullptr, nullptr};
-    DevBuf<unsigned long long> counters;
-    PinBuf<char> hMeta;
-    PinBuf<unsigned long long> hCounters;
+    bool usedBuf[2] = {false, false};
+    unsigned long long chunks = 0;           // chunks queued so far (buffer = chunks & 1)
     size_t cleanTiles = 0;                   // kmin / kmax are in their reset state up to here
     bool dirty = false;                      // a call failed between the mark and the pair pass
     long long fallbackCells = 0;
     void release() {
-        sensor.release(); hit.release(); begin.release(); meta.release(); rel.release();
-        kmin.release(); kmax.release(); counters.release(); hMeta.release(); hCounters.release();
+        stage[0].release(); stage[1].release();
+        kmin.release(); kmax.release();
         for (int b = 0; b < 2; ++b) {
             tileInfo[b].release(); pairs[b].release(); records[b].release(); side[b].release();
             if (evTouch[b]) cudaEventDestroy(evTouch[b]);
             if (evFold[b]) cudaEventDestroy(evFold[b]);
             evTouch[b] = evFold[b] = nullptr;
+            usedBuf[b] = false;
         }
         if (foldStream) cudaStreamDestroy(foldStream);
-        foldStream = nullptr;
-        cleanTiles = 0;
+        if (copyStream) cudaStreamDestroy(copyStream);
+        foldStream = copyStream = nullptr;
+        cleanTiles = 0; nPending = 0;
     }
 };
 

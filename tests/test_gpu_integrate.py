@@ -242,3 +242,54 @@ def test_grid_copy_between_contexts_takes_geometry_and_cells(ctx):
     with pytest.raises(capi.LgsError):
         capi.grid_copy(src, bad)                                       # resolution mismatch
     other.close()
+
+
+def test_streamed_submit_wait_matches_reference(ctx):
+    """lgs_grid_integrate_submit / _wait: calls of 40 scans with two in flight (the staging of call k + 1
+    runs on the copy stream under the passes of call k, records double buffered across calls): update
+    counts per call, every cell, and the rules of the pair (third submit refused, a bad call leaves the
+    grid alone, the synchronous call drains what is in flight)."""
+    from oracle import backend
+    R = backend()
+    world = synth.RoomsWorld(40.0, 5.0, seed=31)
+    angles = synth.beam_angles(541, 240.0)
+    traj = synth.trajectory(world, 200, step=0.12, seed=31)
+    noise = np.random.default_rng(32)
+    geo = capi.Geometry(0, 0, traj[0][0], traj[0][1], 0.05, 64)
+    hits = []
+    for p in traj:
+        h, bbox = capi.scan_hit_points(p, angles, synth.make_scan(world, p, angles, noise), 0.02, 20.0)
+        geo, _, _, _ = capi.geometry_expand(geo, bbox)
+        hits.append(h)
+    ref = R.RefMap.from_dense(np.zeros((geo.ny, geo.nx)), geo.min_x, geo.min_y)
+    grid = capi.Grid(ctx, geo.nx, geo.ny, geo.min_x, geo.min_y, 0.05, apron=1)
+    calls = [capi.PackedHits(traj[k:k + 40, :2], hits[k:k + 40]) for k in range(0, 200, 40)]
+    want = [sum(R.map_integrate_hits(ref, p[:2], h) for p, h in zip(traj[k:k + 40], hits[k:k + 40]))
+            for k in range(0, 200, 40)]
+    got, in_flight = [], 0
+    for c in calls:
+        capi.integrate_submit(ctx, grid, c)
+        in_flight += 1
+        if in_flight == 2:
+            if len(got) == 0:                                        # two in flight: a third is refused
+                with pytest.raises(capi.LgsError, match="in flight"):
+                    capi.integrate_submit(ctx, grid, calls[0])
+            got.append(capi.integrate_wait(ctx))
+            in_flight -= 1
+    while in_flight:
+        got.append(capi.integrate_wait(ctx))
+        in_flight -= 1
+    assert got == want
+    assert capi.integrate_wait(ctx) == 0                             # nothing in flight
+    assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
+    # a call that leaves the grid fails at submit and changes nothing; one in flight is drained by the
+    # synchronous call that follows
+    before = grid.download()
+    with pytest.raises(capi.LgsError, match="outside"):
+        capi.integrate_submit(ctx, grid, capi.PackedHits([[traj[0][0], traj[0][1]]], [np.array([[1e4, 0.0]])]))
+    assert np.array_equal(_bits(grid.download()), _bits(before))
+    capi.integrate_submit(ctx, grid, calls[0])
+    more = sum(R.map_integrate_hits(ref, p[:2], h) for p, h in zip(traj[:40], hits[:40]))
+    more2 = sum(R.map_integrate_hits(ref, p[:2], h) for p, h in zip(traj[40:80], hits[40:80]))
+    assert capi.integrate_packed(ctx, grid, calls[1]) == more2 and more > 0
+    assert np.array_equal(_bits(grid.download()), _bits(ref.dense()))
