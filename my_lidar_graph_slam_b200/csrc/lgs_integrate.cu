@@ -625,14 +625,13 @@ int integ_submit(lgs_ctx* c, lgs_grid* grid, const lgs_hit_batch* scans, double 
     }
     // `w` = the shared workspace with this call's staging set in front of it
     struct View {
-        lgs_integ_ws& s; lgs_integ_ws::Stage& t;
         DevBuf<double>& sensor; DevBuf<double>& hit; DevBuf<int>& begin; DevBuf<char>& meta; DevBuf<int2>& rel;
         DevBuf<unsigned long long>& counters; PinBuf<char>& hMeta; PinBuf<unsigned long long>& hCounters;
         DevBuf<unsigned>& kmin; DevBuf<unsigned>& kmax;
         DevBuf<uint2>* tileInfo; DevBuf<int4>* pairs; DevBuf<unsigned>* records; DevBuf<unsigned>* side;
         cudaStream_t& foldStream; cudaEvent_t* evTouch; cudaEvent_t* evFold;
         size_t& cleanTiles; bool& dirty;
-    } w{ws, w0, w0.sensor, w0.hit, w0.begin, w0.meta, w0.rel, w0.counters, w0.hMeta, w0.hCounters, ws.kmin, ws.kmax,
+    } w{w0.sensor, w0.hit, w0.begin, w0.meta, w0.rel, w0.counters, w0.hMeta, w0.hCounters, ws.kmin, ws.kmax,
         ws.tileInfo, ws.pairs, ws.records, ws.side, ws.foldStream, ws.evTouch, ws.evFold, ws.cleanTiles, ws.dirty};
     cudaStream_t cs0 = ws.copyStream;
     // LGS_INTEG_HOSTTIMING=1 (diagnostic): host wall time of the call's phases to stderr when a call
